@@ -1,0 +1,620 @@
+/* TEST INFRASTRUCTURE ONLY (oracle). Never linked into, imported by or called from the product
+ * path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library, and only as the checker.
+ *
+ * Plain-C restatement of the reference's algorithm for the SDR++ signal-path hot loop
+ * (SURVEY.md section 8a). Every function cites the reference file:line it follows (paths relative
+ * to /root/reference/core/src unless noted). Arithmetic that the reference delegates to VOLK is
+ * restated with VOLK's published *generic* kernel semantics (sequential fp32 accumulation;
+ * rotator renormalised every 512 samples and at the end of a call) -- VOLK itself is an
+ * un-vendored, unpinned dependency (core/CMakeLists.txt:144), as is FFTW3f (:143).
+ *
+ * Parity pinning: the reference has no tests or golden vectors for this path (SURVEY.md section
+ * 4), so this port is pinned against the reference's own headers compiled here
+ * (oracle/_ref/libsdrpp_ref.so, tests/test_oracle_vs_ref.py: bit-exact) and against golden
+ * vectors generated from that library (tests/golden/, tools/make_golden.py).
+ *
+ * Build: gcc -std=c11 -O2 -ffp-contract=off (IEEE semantics, no FMA contraction, no fast-math;
+ * see SURVEY App. C.1 for why the canon has to be stated).
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define API __attribute__((visibility("default")))
+#define ORC_PI 3.14159265358979323846 /* DB_M_PI, dsp/math/constants.h:2 */
+
+typedef struct { float re, im; } cf32; /* dsp::complex_t, dsp/types.h:6-91 */
+
+/* ------------------------------------------------------------------------------------------ */
+/* A1. Source-side integer -> cf32 conversions (per scalar, I and Q alike)                     */
+/* ------------------------------------------------------------------------------------------ */
+enum {
+    ORC_FMT_CF32 = 0,
+    ORC_FMT_U8_RTL = 1,   /* source_modules/rtl_sdr_source/src/main.cpp:526-527, file_source/src/main.cpp:489 */
+    ORC_FMT_U8_TCP = 2,   /* source_modules/rtl_tcp_source/src/rtl_tcp_client.cpp:86-87 */
+    ORC_FMT_I8 = 3,       /* volk_8i_s32f_convert_32f(.., 128.0f): hackrf_source/src/main.cpp:386 */
+    ORC_FMT_I16_FILE = 4, /* source_modules/file_source/src/main.cpp:506 */
+    ORC_FMT_I16_VOLK = 5, /* volk_16i_s32f_convert_32f(.., 32768): bladerf main.cpp:587, plutosdr main.cpp:261-265 */
+};
+
+API int orc_convert(int fmt, const void* in, int nscalars, float* out) {
+    int i;
+    switch (fmt) {
+    case ORC_FMT_CF32:
+        memcpy(out, in, sizeof(float) * (size_t)nscalars);
+        return 0;
+    case ORC_FMT_U8_RTL: {
+        const uint8_t* p = (const uint8_t*)in;
+        /* int subtract, float add, fp32 divide -- exactly as the source text reads */
+        for (i = 0; i < nscalars; i++) out[i] = (p[i] - 128 + 0.5f) / (128.0f - 0.5f);
+        return 0;
+    }
+    case ORC_FMT_U8_TCP: {
+        const uint8_t* p = (const uint8_t*)in;
+        for (i = 0; i < nscalars; i++) out[i] = (float)(((double)p[i] - 128.0) / 128.0);
+        return 0;
+    }
+    case ORC_FMT_I8: {
+        const int8_t* p = (const int8_t*)in;
+        for (i = 0; i < nscalars; i++) out[i] = (float)p[i] / 128.0f;
+        return 0;
+    }
+    case ORC_FMT_I16_FILE: {
+        const int16_t* p = (const int16_t*)in;
+        for (i = 0; i < nscalars; i++) out[i] = (p[i] + 0.5f) / (32768.0f - 0.5f);
+        return 0;
+    }
+    case ORC_FMT_I16_VOLK: {
+        const int16_t* p = (const int16_t*)in;
+        for (i = 0; i < nscalars; i++) out[i] = (float)p[i] / 32768.0f;
+        return 0;
+    }
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A9. Window design: dsp/window/window.h:38-64, cosine.h:7-16, coefficient headers            */
+/* ------------------------------------------------------------------------------------------ */
+static double orc_cosine(double n, double N, const double* c, int cnt) {
+    /* dsp/window/cosine.h:7-16 */
+    double win = 0.0, sign = 1.0;
+    int i;
+    for (i = 0; i < cnt; i++) {
+        win += sign * c[i] * cos((double)i * 2.0 * ORC_PI * n / N);
+        sign = -sign;
+    }
+    return win;
+}
+
+static const double C_RECT[] = { 1.0 };                                       /* rectangular.h */
+static const double C_HAMMING[] = { 0.53836, 0.46164 };                       /* hamming.h:6 */
+static const double C_HANN[] = { 0.5, 0.5 };                                  /* hann.h:6 */
+static const double C_BLACKMAN[] = { 0.42, 0.5, 0.08 };                       /* blackman.h:6 */
+static const double C_NUTTALL[] = { 0.355768, 0.487396, 0.144232, 0.012604 }; /* nuttall.h:6 */
+static const double C_BH4[] = { 0.35875, 0.48829, 0.14128, 0.01168 };         /* blackman_harris4.h:6 */
+static const double C_BH7[] = { 0.27105140069342, 0.43329793923448, 0.21812299954311, 0.06592544638803,
+                                0.01081174209837, 0.00077658482522, 0.00001388721735 }; /* blackman_harris7.h:22-30 */
+
+/* enum order of dsp::window::windowType, window.h:28-36 */
+static int orc_window_coefs(int type, const double** c) {
+    switch (type) {
+    case 0: *c = C_RECT; return 1;
+    case 1: *c = C_HAMMING; return 2;
+    case 2: *c = C_HANN; return 2;
+    case 3: *c = C_BLACKMAN; return 3;
+    case 4: *c = C_NUTTALL; return 4;
+    case 5: *c = C_BH4; return 4;
+    case 6: *c = C_BH7; return 7;
+    }
+    return 0;
+}
+
+/* createWindow (window.h:38-64). buf needs size+1 floats when centered and size is odd. */
+API int orc_window(int type, float* buf, int size, int centered) {
+    const double* c;
+    int cnt = orc_window_coefs(type, &c), i;
+    double wscale = 0.0;
+    if (!cnt) return -1;
+    for (i = 0; i < size; i++) buf[i] = (float)orc_cosine((double)i, (double)size, c, cnt);
+    for (i = 0; i < size; i++) wscale += buf[i];        /* double += float */
+    wscale = 1.0 / wscale;
+    if (!centered) {
+        for (i = 0; i < size; i++) buf[i] = (float)((double)buf[i] * wscale);
+    } else {
+        for (i = 0; i < size; i += 2) {                 /* float *= double: product in double */
+            buf[i] = (float)((double)buf[i] * -wscale);
+            buf[i + 1] = (float)((double)buf[i + 1] * wscale);
+        }
+    }
+    return 0;
+}
+
+/* A2. genReshapeParams, signal_path/iq_frontend.h:56-60 */
+API void orc_reshape_params(double sampleRate, int size, double rate, int* skip, int* nz) {
+    int interval = (int)round(sampleRate / rate);
+    *nz = interval < size ? interval : size;
+    *skip = interval - *nz;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A5. Tap design: taps/low_pass.h:7-11, windowed_sinc.h:9-29, estimate_tap_count.h:4-6        */
+/* ------------------------------------------------------------------------------------------ */
+API int orc_lowpass_tap_count(double transWidth, double sampleRate) {
+    return (int)(3.8 * sampleRate / transWidth);
+}
+
+API int orc_lowpass_taps(double cutoff, double transWidth, double sampleRate, float* out, int cap) {
+    int count = orc_lowpass_tap_count(transWidth, sampleRate), i;
+    double omega = 2.0 * ORC_PI * (cutoff / sampleRate); /* math/hz_to_rads.h:6-8 */
+    double half = (double)count / 2.0;
+    double corr = 1.0 * omega / ORC_PI;
+    if (!out) return count;
+    for (i = 0; i < count && i < cap; i++) {
+        double t = (double)i - half + 0.5;
+        double x = t * omega;
+        double sinc = (x == 0.0) ? 1.0 : (sin(x) / x);  /* math/sinc.h:5-7 */
+        out[i] = (float)(sinc * orc_cosine(t - half, (double)count, C_NUTTALL, 4) * corr);
+    }
+    return count;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Decimation plans: multirate/decim/plans.h:126-140 (data blob, see tools/extract_decim_plans.py) */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { uint32_t len, off; } plan_fir;
+typedef struct { uint32_t ratio, nstages; struct { uint32_t decim, fir; } st[4]; } plan_ent;
+static struct { int loaded; uint32_t nfirs, nplans, pool_len; plan_fir* firs; plan_ent* plans; float* pool; } g_plans;
+
+API int orc_load_plans(const char* path) {
+    FILE* f = fopen(path, "rb");
+    uint32_t hdr[5];
+    if (!f) return -1;
+    if (fread(hdr, 4, 5, f) != 5 || hdr[0] != 0x50445053u || hdr[1] != 1) { fclose(f); return -2; }
+    free(g_plans.firs); free(g_plans.plans); free(g_plans.pool);
+    g_plans.nfirs = hdr[2]; g_plans.nplans = hdr[3]; g_plans.pool_len = hdr[4];
+    g_plans.firs = (plan_fir*)malloc(sizeof(plan_fir) * hdr[2]);
+    g_plans.plans = (plan_ent*)malloc(sizeof(plan_ent) * hdr[3]);
+    g_plans.pool = (float*)malloc(sizeof(float) * hdr[4]);
+    if (fread(g_plans.firs, sizeof(plan_fir), hdr[2], f) != hdr[2] ||
+        fread(g_plans.plans, sizeof(plan_ent), hdr[3], f) != hdr[3] ||
+        fread(g_plans.pool, sizeof(float), hdr[4], f) != hdr[4]) { fclose(f); return -3; }
+    fclose(f);
+    g_plans.loaded = 1;
+    return 0;
+}
+
+/* PowerDecimator::reconfigure plan pick: planId = log2(ratio) - 1 (power_decimator.h:97-98) */
+API int orc_decim_plan(int ratio, int* decimation, int* tapcount, const float** taps) {
+    uint32_t i, s;
+    if (!g_plans.loaded) return -1;
+    for (i = 0; i < g_plans.nplans; i++) {
+        if ((int)g_plans.plans[i].ratio != ratio) continue;
+        for (s = 0; s < g_plans.plans[i].nstages; s++) {
+            const plan_fir* fr = &g_plans.firs[g_plans.plans[i].st[s].fir];
+            decimation[s] = (int)g_plans.plans[i].st[s].decim;
+            tapcount[s] = (int)fr->len;
+            taps[s] = g_plans.pool + fr->off;
+        }
+        return (int)g_plans.plans[i].nstages;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A4/A14. FIR and decimating FIR: filter/fir.h:62-83, filter/decimating_fir.h:45-68           */
+/* State: T-1 past inputs (zero at reset) and the integer `offset` (0 at reset).               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int ntaps, decim, offset;
+    float* taps;
+    cf32* buf;      /* history (ntaps-1) followed by the current block */
+    int cap;
+} orc_fir;
+
+static void dot_cf(cf32* res, const cf32* x, const float* t, int n) {
+    /* volk_32fc_32f_dot_prod_32fc generic: sequential fp32, separate re/im sums */
+    float re = 0.0f, im = 0.0f;
+    int k;
+    for (k = 0; k < n; k++) {
+        re += x[k].re * t[k];
+        im += x[k].im * t[k];
+    }
+    res->re = re; res->im = im;
+}
+
+API orc_fir* orc_fir_create(const float* taps, int ntaps, int decim) {
+    orc_fir* f = (orc_fir*)calloc(1, sizeof(orc_fir));
+    f->ntaps = ntaps; f->decim = decim < 1 ? 1 : decim; f->offset = 0;
+    f->taps = (float*)malloc(sizeof(float) * (size_t)ntaps);
+    memcpy(f->taps, taps, sizeof(float) * (size_t)ntaps);
+    f->cap = 0; f->buf = NULL;
+    return f;
+}
+static void fir_reserve(orc_fir* f, int count) {
+    int need = f->ntaps - 1 + count;
+    if (need > f->cap) {
+        cf32* nb = (cf32*)calloc((size_t)need + 16, sizeof(cf32));
+        if (f->buf) { memcpy(nb, f->buf, sizeof(cf32) * (size_t)(f->ntaps - 1)); free(f->buf); }
+        f->buf = nb; f->cap = need;
+    }
+}
+API void orc_fir_reset(orc_fir* f) {
+    f->offset = 0;
+    if (f->buf) memset(f->buf, 0, sizeof(cf32) * (size_t)(f->ntaps - 1));
+}
+API int orc_fir_offset(const orc_fir* f) { return f->offset; }
+API int orc_fir_process(orc_fir* f, int count, const cf32* in, cf32* out) {
+    int n = 0;
+    fir_reserve(f, count);
+    memcpy(f->buf + (f->ntaps - 1), in, sizeof(cf32) * (size_t)count);
+    if (f->decim == 1) {
+        /* fir.h:68-78: one output per input */
+        for (n = 0; n < count; n++) dot_cf(&out[n], &f->buf[n], f->taps, f->ntaps);
+    } else {
+        /* decimating_fir.h:51-62 */
+        for (; f->offset < count; f->offset += f->decim) dot_cf(&out[n++], &f->buf[f->offset], f->taps, f->ntaps);
+        f->offset -= count;
+    }
+    memmove(f->buf, f->buf + count, sizeof(cf32) * (size_t)(f->ntaps - 1));
+    return n;
+}
+API void orc_fir_destroy(orc_fir* f) { if (f) { free(f->taps); free(f->buf); free(f); } }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A3. PowerDecimator: multirate/power_decimator.h:51-67,91-107                                */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int ratio, nstages; orc_fir* st[4]; } orc_pdec;
+
+API orc_pdec* orc_powerdecim_create(int ratio) {
+    int dec[4], cnt[4], n, i;
+    const float* tp[4];
+    orc_pdec* p = (orc_pdec*)calloc(1, sizeof(orc_pdec));
+    p->ratio = ratio;
+    if (ratio > 1) {
+        n = orc_decim_plan(ratio, dec, cnt, tp);
+        if (n <= 0) { free(p); return NULL; }
+        p->nstages = n;
+        for (i = 0; i < n; i++) p->st[i] = orc_fir_create(tp[i], cnt[i], dec[i]);
+    }
+    return p;
+}
+API int orc_powerdecim_process(orc_pdec* p, int count, const cf32* in, cf32* out) {
+    const cf32* data = in;
+    int i;
+    if (p->ratio == 1) { memmove(out, in, sizeof(cf32) * (size_t)count); return count; }
+    for (i = 0; i < p->nstages; i++) { count = orc_fir_process(p->st[i], count, data, out); data = out; }
+    return count;
+}
+API int orc_powerdecim_offsets(const orc_pdec* p, int* offsets) {
+    int i;
+    for (i = 0; i < p->nstages; i++) offsets[i] = p->st[i]->offset;
+    return p->nstages;
+}
+API void orc_powerdecim_reset(orc_pdec* p) { int i; for (i = 0; i < p->nstages; i++) orc_fir_reset(p->st[i]); }
+API void orc_powerdecim_destroy(orc_pdec* p) { int i; if (!p) return; for (i = 0; i < p->nstages; i++) orc_fir_destroy(p->st[i]); free(p); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A13. Polyphase resampler: multirate/polyphase_bank.h:15-48, polyphase_resampler.h:69-99     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int interp, decim, tpp, phase, offset;
+    float* bank;    /* [interp][tpp] */
+    cf32* buf; int cap;
+} orc_poly;
+
+API orc_poly* orc_polyphase_create(int interp, int decim, const float* taps, int ntaps) {
+    orc_poly* p = (orc_poly*)calloc(1, sizeof(orc_poly));
+    int i, tot;
+    p->interp = interp; p->decim = decim;
+    p->tpp = (ntaps + interp - 1) / interp;                       /* polyphase_bank.h:24 */
+    p->bank = (float*)calloc((size_t)interp * (size_t)p->tpp, sizeof(float));
+    tot = interp * p->tpp;
+    for (i = 0; i < tot; i++)                                     /* polyphase_bank.h:31-34 */
+        p->bank[((interp - 1) - (i % interp)) * p->tpp + (i / interp)] = (i < ntaps) ? taps[i] : 0.0f;
+    return p;
+}
+API int orc_polyphase_tpp(const orc_poly* p) { return p->tpp; }
+API void orc_polyphase_state(const orc_poly* p, int* phase, int* offset) { *phase = p->phase; *offset = p->offset; }
+API void orc_polyphase_reset(orc_poly* p) {
+    p->phase = 0; p->offset = 0;
+    if (p->buf) memset(p->buf, 0, sizeof(cf32) * (size_t)(p->tpp - 1));
+}
+API int orc_polyphase_process(orc_poly* p, int count, const cf32* in, cf32* out) {
+    int n = 0, need = p->tpp - 1 + count;
+    if (need > p->cap) {
+        cf32* nb = (cf32*)calloc((size_t)need + 16, sizeof(cf32));
+        if (p->buf) { memcpy(nb, p->buf, sizeof(cf32) * (size_t)(p->tpp - 1)); free(p->buf); }
+        p->buf = nb; p->cap = need;
+    }
+    memcpy(p->buf + (p->tpp - 1), in, sizeof(cf32) * (size_t)count);
+    while (p->offset < count) {                                   /* polyphase_resampler.h:75-93 */
+        dot_cf(&out[n++], &p->buf[p->offset], p->bank + (size_t)p->phase * (size_t)p->tpp, p->tpp);
+        p->phase += p->decim;
+        p->offset += p->phase / p->interp;
+        p->phase = p->phase % p->interp;
+    }
+    p->offset -= count;
+    memmove(p->buf, p->buf + count, sizeof(cf32) * (size_t)(p->tpp - 1));
+    return n;
+}
+API void orc_polyphase_destroy(orc_poly* p) { if (p) { free(p->bank); free(p->buf); free(p); } }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A12. RationalResampler plan + process: multirate/rational_resampler.h:121-167,83-97         */
+/* ------------------------------------------------------------------------------------------ */
+static int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a < 0 ? -a : a; }
+
+typedef struct {
+    int mode;        /* 0 BOTH, 1 DECIM_ONLY, 2 RESAMP_ONLY, 3 NONE (enum order, :114-119) */
+    int predec, interp, decim, ntaps;
+    orc_pdec* pd; orc_poly* pp;
+} orc_resamp;
+
+/* info[0]=mode [1]=predec [2]=interp [3]=decim [4]=ntaps [5]=tpp; taps (optional) are interp-scaled */
+API int orc_resampler_plan(double inSR, double outSR, int* info, float* taps, int cap) {
+    const int maxRatio = 1 << 13;                                       /* getMaxRatio(), power_decimator.h:28-30 */
+    int predecPower = (int)floor(log2(inSR / outSR));
+    int predecRatio, useDecim, IntSR, OutSR, g, interp, decim, ntaps, i;
+    double intSR = inSR, tapSR, tapBW, tapTW;
+    if (predecPower > maxRatio) predecPower = maxRatio;                 /* :123 clamps the exponent against 8192 */
+    predecRatio = (predecPower >= 0 && predecPower < 31) ? (1 << predecPower) : ((predecPower < 0) ? 0 : maxRatio);
+    if (predecRatio > maxRatio) predecRatio = maxRatio;                 /* :124 */
+    useDecim = (inSR > outSR && predecPower > 0);
+    if (useDecim) intSR = inSR / (double)predecRatio;
+    IntSR = (int)round(intSR); OutSR = (int)round(outSR);
+    g = gcd_i(IntSR, OutSR);
+    interp = OutSR / g; decim = IntSR / g;
+    info[1] = useDecim ? predecRatio : 1;
+    if (interp == decim) {
+        info[0] = useDecim ? 1 : 3; info[2] = 1; info[3] = 1; info[4] = 0; info[5] = 0;
+        return 0;
+    }
+    tapSR = intSR * (double)interp;
+    tapBW = (inSR < outSR ? inSR : outSR) / 2.0;
+    tapTW = tapBW * 0.1;
+    ntaps = orc_lowpass_taps(tapBW, tapTW, tapSR, taps, taps ? cap : 0);
+    if (taps) for (i = 0; i < ntaps && i < cap; i++) taps[i] *= (float)interp;   /* :160 */
+    info[0] = useDecim ? 0 : 2; info[2] = interp; info[3] = decim; info[4] = ntaps;
+    info[5] = (ntaps + interp - 1) / interp;
+    return 0;
+}
+
+API orc_resamp* orc_resampler_create(double inSR, double outSR) {
+    int info[6];
+    orc_resamp* r = (orc_resamp*)calloc(1, sizeof(orc_resamp));
+    orc_resampler_plan(inSR, outSR, info, NULL, 0);
+    r->mode = info[0]; r->predec = info[1]; r->interp = info[2]; r->decim = info[3]; r->ntaps = info[4];
+    if (r->mode == 0 || r->mode == 1) r->pd = orc_powerdecim_create(r->predec);
+    if (r->mode == 0 || r->mode == 2) {
+        float* t = (float*)malloc(sizeof(float) * (size_t)r->ntaps);
+        orc_resampler_plan(inSR, outSR, info, t, r->ntaps);
+        r->pp = orc_polyphase_create(r->interp, r->decim, t, r->ntaps);
+        free(t);
+    }
+    return r;
+}
+API int orc_resampler_process(orc_resamp* r, int count, const cf32* in, cf32* out) {
+    switch (r->mode) {
+    case 0: count = orc_powerdecim_process(r->pd, count, in, out); return orc_polyphase_process(r->pp, count, out, out);
+    case 1: return orc_powerdecim_process(r->pd, count, in, out);
+    case 2: return orc_polyphase_process(r->pp, count, in, out);
+    default: memmove(out, in, sizeof(cf32) * (size_t)count); return count;
+    }
+}
+API void orc_resampler_reset(orc_resamp* r) { if (r->pd) orc_powerdecim_reset(r->pd); if (r->pp) orc_polyphase_reset(r->pp); }
+API void orc_resampler_destroy(orc_resamp* r) { if (!r) return; orc_powerdecim_destroy(r->pd); orc_polyphase_destroy(r->pp); free(r); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A11. FrequencyXlator: channel/frequency_xlator.h:15-23,43-50 on VOLK's generic rotator2     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { cf32 phase, delta; } orc_xlat;
+
+static cf32 cmul(cf32 a, cf32 b) { cf32 r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+
+API void orc_xlator_set_offset(orc_xlat* x, double offsetHz, double sampleRate) {
+    double w = 2.0 * ORC_PI * (offsetHz / sampleRate);     /* math/hz_to_rads.h:6-8 */
+    x->delta.re = (float)cos(w); x->delta.im = (float)sin(w);
+}
+API orc_xlat* orc_xlator_create(double offsetHz, double sampleRate) {
+    orc_xlat* x = (orc_xlat*)calloc(1, sizeof(orc_xlat));
+    x->phase.re = 1.0f; x->phase.im = 0.0f;
+    orc_xlator_set_offset(x, offsetHz, sampleRate);
+    return x;
+}
+API void orc_xlator_reset(orc_xlat* x) { x->phase.re = 1.0f; x->phase.im = 0.0f; }
+API void orc_xlator_state(const orc_xlat* x, float* phase, float* delta) {
+    phase[0] = x->phase.re; phase[1] = x->phase.im; delta[0] = x->delta.re; delta[1] = x->delta.im;
+}
+API int orc_xlator_process(orc_xlat* x, int count, const cf32* in, cf32* out) {
+    int i = 0, j, nfull = count / 512, tail = count % 512;
+    for (j = 0; j < nfull; j++) {
+        int k;
+        for (k = 0; k < 512; k++, i++) { out[i] = cmul(in[i], x->phase); x->phase = cmul(x->phase, x->delta); }
+        { float h = hypotf(x->phase.re, x->phase.im); x->phase.re /= h; x->phase.im /= h; }
+    }
+    for (j = 0; j < tail; j++, i++) { out[i] = cmul(in[i], x->phase); x->phase = cmul(x->phase, x->delta); }
+    if (tail) { float h = hypotf(x->phase.re, x->phase.im); x->phase.re /= h; x->phase.im /= h; }
+    return count;
+}
+API void orc_xlator_destroy(orc_xlat* x) { free(x); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A15. RxVFO: channel/rx_vfo.h:19-33,89-100,117-121                                           */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double inSR, outSR, bw, offset;
+    orc_xlat* x; orc_resamp* r; orc_fir* f; int filterNeeded;
+} orc_vfo;
+
+static void vfo_make_filter(orc_vfo* v) {
+    double fw = v->bw / 2.0;                                   /* generateTaps, rx_vfo.h:117-121 */
+    int n = orc_lowpass_taps(fw, fw * 0.1, v->outSR, NULL, 0);
+    float* t = (float*)malloc(sizeof(float) * (size_t)n);
+    orc_lowpass_taps(fw, fw * 0.1, v->outSR, t, n);
+    orc_fir_destroy(v->f);
+    v->f = orc_fir_create(t, n, 1);
+    fir_reserve(v->f, 1);
+    free(t);
+}
+API orc_vfo* orc_rxvfo_create(double inSR, double outSR, double bw, double offset) {
+    orc_vfo* v = (orc_vfo*)calloc(1, sizeof(orc_vfo));
+    v->inSR = inSR; v->outSR = outSR; v->bw = bw; v->offset = offset;
+    v->filterNeeded = (bw != outSR);
+    v->x = orc_xlator_create(-offset, inSR);
+    v->r = orc_resampler_create(inSR, outSR);
+    vfo_make_filter(v);
+    return v;
+}
+API int orc_rxvfo_process(orc_vfo* v, int count, const cf32* in, cf32* out) {
+    orc_xlator_process(v->x, count, in, out);
+    count = orc_resampler_process(v->r, count, out, out);
+    if (v->filterNeeded) orc_fir_process(v->f, count, out, out);
+    return count;
+}
+API void orc_rxvfo_set_offset(orc_vfo* v, double offset) { v->offset = offset; orc_xlator_set_offset(v->x, -offset, v->inSR); }
+API void orc_rxvfo_reset(orc_vfo* v) { orc_xlator_reset(v->x); orc_resampler_reset(v->r); orc_fir_reset(v->f); }
+API int orc_rxvfo_info(const orc_vfo* v, int* info) {
+    info[0] = v->r->mode; info[1] = v->r->predec; info[2] = v->r->interp; info[3] = v->r->decim; info[4] = v->r->ntaps;
+    info[5] = v->r->pp ? v->r->pp->tpp : 0; info[6] = v->filterNeeded ? v->f->ntaps : 0;
+    return 0;
+}
+API void orc_rxvfo_destroy(orc_vfo* v) { if (!v) return; orc_xlator_destroy(v->x); orc_resampler_destroy(v->r); orc_fir_destroy(v->f); free(v); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A5 (DC blocker), A6 (conjugate)                                                             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { float rate; cf32 off; } orc_dcb;
+API orc_dcb* orc_dcblock_create(double rate) { orc_dcb* d = (orc_dcb*)calloc(1, sizeof(orc_dcb)); d->rate = (float)rate; return d; }
+API int orc_dcblock_process(orc_dcb* d, int count, const cf32* in, cf32* out) {
+    int i;                                                     /* correction/dc_blocker.h:54-60 */
+    for (i = 0; i < count; i++) {
+        cf32 o; o.re = in[i].re - d->off.re; o.im = in[i].im - d->off.im;
+        out[i] = o;
+        d->off.re += o.re * d->rate; d->off.im += o.im * d->rate;
+    }
+    return count;
+}
+API void orc_dcblock_destroy(orc_dcb* d) { free(d); }
+API int orc_conjugate(int count, const cf32* in, cf32* out) {
+    int i;                                                     /* math/conjugate.h:12-15 */
+    for (i = 0; i < count; i++) { out[i].re = in[i].re; out[i].im = -in[i].im; }
+    return count;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A16-A18. Demodulator front ends                                                             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { float invDev; cf32 din; } orc_quad;
+API orc_quad* orc_quadrature_create(double deviation, double sampleRate) {
+    orc_quad* q = (orc_quad*)calloc(1, sizeof(orc_quad));     /* demod/quadrature.h:21-28; _din zeroed as by reset() */
+    q->invDev = (float)(1.0 / (2.0 * ORC_PI * (deviation / sampleRate)));
+    return q;
+}
+API int orc_quadrature_process(orc_quad* q, int count, const cf32* in, float* out) {
+    int i;                                                     /* demod/quadrature.h:41-56, USE_QUAD_FM_DEMOD branch */
+    for (i = 0; i < count; i++) {
+        cf32 y = in[i], c, d;
+        c.re = q->din.re; c.im = -q->din.im;
+        d = cmul(y, c);                                        /* types.h:23-25 operator* */
+        out[i] = atan2f(d.im, d.re) * q->invDev;
+        q->din = y;
+    }
+    return count;
+}
+API void orc_quadrature_destroy(orc_quad* q) { free(q); }
+
+API int orc_am_magnitude(int count, const cf32* in, float* out) {
+    int i;                                                     /* volk_32fc_magnitude_32f, demod/am.h:122 */
+    for (i = 0; i < count; i++) out[i] = sqrtf(in[i].re * in[i].re + in[i].im * in[i].im);
+    return count;
+}
+
+typedef struct { orc_xlat* x; } orc_ssb;
+API orc_ssb* orc_ssb_create(int mode, double bandwidth, double sampleRate) {
+    orc_ssb* s = (orc_ssb*)calloc(1, sizeof(orc_ssb));        /* demod/ssb.h:119-126: USB +bw/2, LSB -bw/2, DSB 0 */
+    double tr = (mode == 0) ? bandwidth / 2.0 : (mode == 1) ? -bandwidth / 2.0 : 0.0;
+    s->x = orc_xlator_create(tr, sampleRate);
+    return s;
+}
+API int orc_ssb_process(orc_ssb* s, int count, const cf32* in, float* out) {
+    cf32* tmp = (cf32*)malloc(sizeof(cf32) * (size_t)(count + 1));
+    int i;                                                     /* demod/ssb.h:90-95; convert/complex_to_real.h:15 */
+    orc_xlator_process(s->x, count, in, tmp);
+    for (i = 0; i < count; i++) out[i] = tmp[i].re;
+    free(tmp);
+    return count;
+}
+API void orc_ssb_destroy(orc_ssb* s) { if (s) { orc_xlator_destroy(s->x); free(s); } }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A10. Spectrum line: signal_path/iq_frontend.cpp:230-249 (+ :272-296 zero padding)           */
+/* FFTW3f (absent) computes a forward unnormalised DFT; restated as an iterative radix-2 FFT.  */
+/* ------------------------------------------------------------------------------------------ */
+#define DEF_FFT(NAME, R)                                                                         \
+    static void NAME(R* a /* interleaved */, int n) {                                            \
+        int i, j, len, k;                                                                        \
+        R* w = (R*)malloc(sizeof(R) * (size_t)n);                                                \
+        for (i = 1, j = 0; i < n; i++) {                                                         \
+            int bit = n >> 1;                                                                    \
+            for (; j & bit; bit >>= 1) j ^= bit;                                                 \
+            j ^= bit;                                                                            \
+            if (i < j) { R tr = a[2*i], ti = a[2*i+1]; a[2*i] = a[2*j]; a[2*i+1] = a[2*j+1]; a[2*j] = tr; a[2*j+1] = ti; } \
+        }                                                                                        \
+        for (k = 0; k < n / 2; k++) { double ang = -2.0 * ORC_PI * (double)k / (double)n; w[2*k] = (R)cos(ang); w[2*k+1] = (R)sin(ang); } \
+        for (len = 2; len <= n; len <<= 1) {                                                     \
+            int half = len >> 1, step = n / len;                                                 \
+            for (i = 0; i < n; i += len) {                                                       \
+                for (k = 0; k < half; k++) {                                                     \
+                    R ur = a[2*(i+k)], ui = a[2*(i+k)+1];                                        \
+                    R tr = a[2*(i+k+half)], ti = a[2*(i+k+half)+1];                              \
+                    R wr = w[2*k*step], wi = w[2*k*step+1];                                      \
+                    R vr = tr * wr - ti * wi, vi = tr * wi + ti * wr;                            \
+                    a[2*(i+k)] = ur + vr; a[2*(i+k)+1] = ui + vi;                                \
+                    a[2*(i+k+half)] = ur - vr; a[2*(i+k+half)+1] = ui - vi;                      \
+                }                                                                                \
+            }                                                                                    \
+        }                                                                                        \
+        free(w);                                                                                 \
+    }
+DEF_FFT(fft_f32, float)
+DEF_FFT(fft_f64, double)
+
+/* frame: nz samples, window: nz floats (orc_window(..., centered=1)).
+ * row32  (opt): the reference way -- fp32 FFT, then VOLK power spectrum log2(x)*3.0103 with -inf -> -127.
+ * X64    (opt): fp64 DFT of the fp32 windowed frame, N interleaved complex doubles.
+ * row64  (opt): 10*log10 |X64|^2. */
+API int orc_spectrum(int N, int nz, const cf32* frame, const float* window, float* row32, double* X64, double* row64) {
+    int i;
+    float* u;
+    if (N <= 0 || (N & (N - 1)) || nz > N || nz < 0) return -1;
+    u = (float*)calloc((size_t)N * 2, sizeof(float));
+    for (i = 0; i < nz; i++) { u[2*i] = frame[i].re * window[i]; u[2*i+1] = frame[i].im * window[i]; }  /* :234 */
+    if (X64 || row64) {
+        double* a = (double*)malloc(sizeof(double) * (size_t)N * 2);
+        for (i = 0; i < 2 * N; i++) a[i] = (double)u[i];
+        fft_f64(a, N);
+        for (i = 0; i < N; i++) {
+            if (X64) { X64[2*i] = a[2*i]; X64[2*i+1] = a[2*i+1]; }
+            if (row64) row64[i] = 10.0 * log10(a[2*i] * a[2*i] + a[2*i+1] * a[2*i+1]);
+        }
+        free(a);
+    }
+    if (row32) {
+        fft_f32(u, N);                                                                           /* :237 */
+        for (i = 0; i < N; i++) {                                                                /* :244 */
+            float re = u[2*i] * 1.0f, im = u[2*i+1] * 1.0f;
+            float l = log2f(re * re + im * im);
+            if (isinf(l)) l = copysignf(127.0f, l);
+            row32[i] = 3.01029995663981209120f * l;
+        }
+    }
+    free(u);
+    return 0;
+}
+
+API const char* orc_build_info(void) { return "oracle port: plain-C restatement, IEEE fp32, generic-VOLK semantics"; }
