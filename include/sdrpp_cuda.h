@@ -1,0 +1,190 @@
+/* sdrpp_cuda.h -- C ABI of the B200-native SDR++ signal-path hot loop.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types. The host-side C++
+ * mirror of the reference's dsp:: / sigpath:: interface (include/sdrpp/...) forwards to these
+ * entry points; SDR++ modules never see them. Each entry point cites the reference interface it
+ * replaces (paths relative to the reference tree's core/src unless noted).
+ *
+ * Conventions: every int-returning call returns >= 0 on success and < 0 on error
+ * (SDRPP_ERR_*); the message of the last error on the calling thread is
+ * sdrpp_cuda_last_error(). There is NO CPU fallback: without a CUDA device every compute call
+ * fails with SDRPP_ERR_CUDA.
+ */
+#ifndef SDRPP_CUDA_H
+#define SDRPP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SDRPP_API __attribute__((visibility("default")))
+#else
+#define SDRPP_API
+#endif
+
+/* dsp::complex_t (dsp/types.h:6-91): interleaved {float re, im} */
+typedef struct { float re, im; } sdrpp_cf32;
+
+enum {
+    SDRPP_OK = 0,
+    SDRPP_ERR_ARG = -1,      /* bad argument (the reference asserts or returns NULL) */
+    SDRPP_ERR_CUDA = -2,     /* CUDA runtime error, sticky per handle */
+    SDRPP_ERR_STATE = -3,    /* call not valid in this state (e.g. duplicate / unknown id) */
+    SDRPP_ERR_NOMEM = -4
+};
+
+/* Input sample formats = the per-source conversion formulas on the reference's input edge. */
+enum {
+    SDRPP_FMT_CF32 = 0,      /* already dsp::complex_t */
+    SDRPP_FMT_U8_RTL = 1,    /* (u8-128+0.5f)/(128.0f-0.5f): source_modules/rtl_sdr_source/src/main.cpp:526-527, file_source/src/main.cpp:489 */
+    SDRPP_FMT_U8_TCP = 2,    /* (float)(((double)u8-128.0)/128.0): source_modules/rtl_tcp_source/src/rtl_tcp_client.cpp:86-87 */
+    SDRPP_FMT_I8 = 3,        /* volk_8i_s32f_convert_32f(..,128.0f): source_modules/hackrf_source/src/main.cpp:386 */
+    SDRPP_FMT_I16_FILE = 4,  /* (i16+0.5f)/(32768.0f-0.5f): source_modules/file_source/src/main.cpp:506 */
+    SDRPP_FMT_I16_VOLK = 5,  /* volk_16i_s32f_convert_32f(..,32768): bladerf_source/src/main.cpp:587, plutosdr_source/src/main.cpp:261-265 */
+    SDRPP_FMT_COUNT = 6
+};
+
+/* dsp::window::windowType (dsp/window/window.h:28-36) -- persisted as an int in the config */
+enum {
+    SDRPP_WIN_RECTANGULAR = 0, SDRPP_WIN_HAMMING, SDRPP_WIN_HANN, SDRPP_WIN_BLACKMAN,
+    SDRPP_WIN_NUTTALL, SDRPP_WIN_BLACKMAN_HARRIS4, SDRPP_WIN_BLACKMAN_HARRIS7, SDRPP_WIN_COUNT
+};
+
+/* Demodulator front end fused behind a VFO. */
+enum {
+    SDRPP_DEMOD_NONE = 0,
+    SDRPP_DEMOD_QUADRATURE = 1, /* dsp::demod::Quadrature::process (dsp/demod/quadrature.h:41-56), deviation = bw/2 (demod/fm.h:31) */
+    SDRPP_DEMOD_AM = 2,         /* volk_32fc_magnitude_32f in dsp::demod::AM::process (dsp/demod/am.h:122) */
+    SDRPP_DEMOD_USB = 3,        /* dsp::demod::SSB::process xlate(+bw/2) + ComplexToReal (dsp/demod/ssb.h:90-101,119-126) */
+    SDRPP_DEMOD_LSB = 4,        /* same, -bw/2 */
+    SDRPP_DEMOD_DSB = 5         /* same, 0 */
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * Library
+ * ------------------------------------------------------------------------------------------ */
+SDRPP_API const char* sdrpp_cuda_version(void);
+SDRPP_API const char* sdrpp_cuda_last_error(void);
+SDRPP_API int sdrpp_cuda_device_count(void);
+/* Select the CUDA device used by objects created afterwards on this thread. */
+SDRPP_API int sdrpp_cuda_init(int device);
+/* Pinned host memory for IQ blocks (replaces volk_malloc in dsp::stream, dsp/stream.h:28-29,125-126). */
+SDRPP_API void* sdrpp_cuda_host_alloc(size_t bytes);
+SDRPP_API void sdrpp_cuda_host_free(void* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side design maths (double precision, no GPU needed). These define filter shapes and index
+ * arithmetic and must agree exactly with the reference.
+ * ------------------------------------------------------------------------------------------ */
+/* dsp::window::createWindow (dsp/window/window.h:38-64). buf holds size+1 floats. */
+SDRPP_API int sdrpp_cuda_design_window(int type, float* buf, int size, int centered);
+/* dsp::taps::lowPass (dsp/taps/low_pass.h:7-11). Returns the tap count; writes min(count,cap). */
+SDRPP_API int sdrpp_cuda_design_lowpass(double cutoff, double transWidth, double sampleRate, float* out, int cap);
+/* dsp::multirate::RationalResampler::reconfigure (dsp/multirate/rational_resampler.h:121-167).
+ * info[0]=mode (0 BOTH,1 DECIM_ONLY,2 RESAMP_ONLY,3 NONE) [1]=predec ratio [2]=interp [3]=decim
+ * [4]=tap count [5]=taps per phase; taps (optional) are already scaled by interp. */
+SDRPP_API int sdrpp_cuda_design_resampler(double inSR, double outSR, int* info, float* taps, int cap);
+/* dsp::multirate::decim::plans (dsp/multirate/decim/plans.h:126-140). Returns the stage count. */
+SDRPP_API int sdrpp_cuda_design_decim_plan(int ratio, int* decimation, int* tapcount, const float** taps);
+/* IQFrontEnd::genReshapeParams (signal_path/iq_frontend.h:56-60). */
+SDRPP_API void sdrpp_cuda_design_reshape(double sampleRate, int fftSize, double fftRate, int* skip, int* nz);
+
+/* ---------------------------------------------------------------------------------------------
+ * One-shot block operations on HOST buffers (H2D + kernel + D2H inside the call)
+ * ------------------------------------------------------------------------------------------ */
+/* Source conversions (see SDRPP_FMT_*). in: nsamples interleaved I,Q pairs. Bit-exact. */
+SDRPP_API int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf32* out);
+/* IQFrontEnd::handler (signal_path/iq_frontend.cpp:230-249): window * frame -> zero-padded forward
+ * DFT of size N -> 10*log10|X|^2. frame: nz samples of format fmt; window: nz floats.
+ * row: N floats (may be NULL); X: N complex FFT outputs (may be NULL; parity/debug). */
+SDRPP_API int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* window,
+                                  float* row, sdrpp_cf32* X);
+
+/* ---------------------------------------------------------------------------------------------
+ * Front end: the device-resident signal path (sigpath::iqFrontEnd + sigpath::vfoManager's
+ * dsp::channel::RxVFO set + demod front ends) of one GPU.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrpp_cuda_frontend sdrpp_cuda_frontend;
+
+typedef struct {
+    double sample_rate;   /* IQFrontEnd::init sampleRate */
+    int decim_ratio;      /* decimRatio: 1 or 2^k (dsp/multirate/power_decimator.h:22-25) */
+    int dc_blocking;      /* dcBlocking */
+    int invert_iq;        /* setInvertIQ */
+    int fft_size;         /* fftSize, power of two 2^6..2^22; 0 disables the spectrum branch */
+    double fft_rate;      /* fftRate (lines/s) */
+    int fft_window;       /* SDRPP_WIN_* */
+    int max_block;        /* largest sample count of one submit (<= 1e6 in the reference, dsp/stream.h:9); 0 = 1000000 */
+    int ring_log2;        /* log2 of the device IQ ring length in samples; 0 = auto */
+    int max_fft_rows;     /* spectrum rows buffered per block; 0 = auto */
+} sdrpp_cuda_frontend_cfg;
+
+SDRPP_API sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* cfg);
+SDRPP_API int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe);
+
+/* IQFrontEnd setters (signal_path/iq_frontend.cpp:51-174). Applied at the next block boundary. */
+SDRPP_API int sdrpp_cuda_frontend_set_sample_rate(sdrpp_cuda_frontend* fe, double sampleRate);
+SDRPP_API int sdrpp_cuda_frontend_set_decimation(sdrpp_cuda_frontend* fe, int ratio);
+SDRPP_API int sdrpp_cuda_frontend_set_dc_blocking(sdrpp_cuda_frontend* fe, int enabled);
+SDRPP_API int sdrpp_cuda_frontend_set_invert_iq(sdrpp_cuda_frontend* fe, int enabled);
+SDRPP_API int sdrpp_cuda_frontend_set_fft_size(sdrpp_cuda_frontend* fe, int size);
+SDRPP_API int sdrpp_cuda_frontend_set_fft_rate(sdrpp_cuda_frontend* fe, double rate);
+SDRPP_API int sdrpp_cuda_frontend_set_fft_window(sdrpp_cuda_frontend* fe, int window);
+SDRPP_API double sdrpp_cuda_frontend_effective_samplerate(sdrpp_cuda_frontend* fe); /* getEffectiveSamplerate */
+
+/* IQFrontEnd::addVFO / VFOManager::createVFO (signal_path/iq_frontend.cpp:122-142, vfo_manager.cpp:95-103)
+ * -> dsp::channel::RxVFO(in, effectiveSr, outSR, bw, offset) (+ demod front end). Returns the VFO id (>=0). */
+SDRPP_API int sdrpp_cuda_vfo_create(sdrpp_cuda_frontend* fe, double outSR, double bandwidth, double offset, int demod);
+SDRPP_API int sdrpp_cuda_vfo_destroy(sdrpp_cuda_frontend* fe, int vfo);                       /* removeVFO */
+SDRPP_API int sdrpp_cuda_vfo_set_offset(sdrpp_cuda_frontend* fe, int vfo, double offset);     /* RxVFO::setOffset, rx_vfo.h:72-77 */
+SDRPP_API int sdrpp_cuda_vfo_set_bandwidth(sdrpp_cuda_frontend* fe, int vfo, double bw);      /* RxVFO::setBandwidth, rx_vfo.h:60-70 */
+SDRPP_API int sdrpp_cuda_vfo_set_out_samplerate(sdrpp_cuda_frontend* fe, int vfo, double outSR, double bw); /* rx_vfo.h:46-58 */
+SDRPP_API int sdrpp_cuda_vfo_reset(sdrpp_cuda_frontend* fe, int vfo);                         /* RxVFO::reset, rx_vfo.h:79-87 */
+/* info[0..5] as sdrpp_cuda_design_resampler, info[6] = channel filter taps (0 if bypassed),
+ * info[7] = stage-1 decimation fused with the NCO, info[8] = stage-1 taps. */
+SDRPP_API int sdrpp_cuda_vfo_info(sdrpp_cuda_frontend* fe, int vfo, int* info);
+
+/* One IQ block through the whole path (the work of threads A..L of SURVEY 3.2 for one
+ * stream.swap()): conversion -> [PowerDecimator] -> [DCBlocker] -> [Conjugate] -> device ring ->
+ * spectrum frames that complete in this block + every VFO + demod front ends -> pinned host
+ * results. Asynchronous: returns after enqueueing; results are valid after _wait().
+ * `in` is host memory (pinned memory from sdrpp_cuda_host_alloc avoids a staging copy). */
+SDRPP_API int sdrpp_cuda_frontend_submit(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count);
+/* Same, with `in` already in device memory on this GPU (e.g. the target of an NCCL broadcast). */
+SDRPP_API int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt, const void* dev_in, int count);
+/* Block until the last submitted block's results are on the host. */
+SDRPP_API int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe);
+/* Skip the device->host copies of results (kernel-only timing); default 1 = copy. */
+SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled);
+
+/* Results of the last waited block. Pointers are into pinned host memory owned by the front end
+ * and stay valid until the next submit. */
+/* RxVFO::out for this block: returns the output sample count; *iq -> cf32[count];
+ * *demod -> float[count] (NULL when demod == NONE). */
+SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cf32** iq, const float** demod);
+/* Spectrum rows completed in this block (each fft_size floats, the buffer handed to
+ * acquireFFTBuffer/releaseFFTBuffer in the reference): returns the row count. */
+SDRPP_API int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows);
+/* The post-preprocessing IQ block as the Splitter would hand it to bound streams
+ * (IQFrontEnd::bindIQStream, signal_path/iq_frontend.cpp:114-116; recorder tap). Copies up to cap
+ * samples of the last block to `out` (device->host); returns the count. */
+SDRPP_API int sdrpp_cuda_frontend_read_iq(sdrpp_cuda_frontend* fe, sdrpp_cf32* out, int cap);
+
+/* Kernel launch counter (kernels of this library launched since creation) and the CUDA stream
+ * (cudaStream_t) the front end enqueues on, for device-side timing with events. */
+SDRPP_API long long sdrpp_cuda_frontend_launches(sdrpp_cuda_frontend* fe);
+SDRPP_API void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe);
+/* Device-time of the kernels of the last waited block, by kernel family, measured with CUDA
+ * events on the front end's stream when profiling is enabled (ms). idx: 0 ingest/preproc,
+ * 1 spectrum, 2 channelizer stage 1, 3 channelizer tail. */
+SDRPP_API int sdrpp_cuda_frontend_set_profiling(sdrpp_cuda_frontend* fe, int enabled);
+SDRPP_API float sdrpp_cuda_frontend_kernel_ms(sdrpp_cuda_frontend* fe, int idx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDRPP_CUDA_H */

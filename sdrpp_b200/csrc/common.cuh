@@ -1,0 +1,64 @@
+// Shared device/host helpers for the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+namespace sdrpp {
+
+// Last error text of the calling thread (returned by sdrpp_cuda_last_error()).
+void set_last_error(const std::string& msg);
+
+#define SDRPP_CUDA_TRY(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::sdrpp::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+            return SDRPP_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Bit-exact sample conversion. Each formula keeps the reference's operation
+// order with IEEE round-to-nearest intrinsics so the compiler can neither contract to FMA nor
+// replace the divide by a reciprocal multiply (App. C.1).
+__device__ __forceinline__ float cvt_u8_rtl(unsigned int v) {
+    return __fdiv_rn(__fadd_rn((float)((int)v - 128), 0.5f), 127.5f);
+}
+__device__ __forceinline__ float cvt_u8_tcp(unsigned int v) {
+    return (float)__ddiv_rn((double)v - 128.0, 128.0);
+}
+__device__ __forceinline__ float cvt_i8(int v) { return __fdiv_rn((float)v, 128.0f); }
+__device__ __forceinline__ float cvt_i16_file(int v) {
+    return __fdiv_rn(__fadd_rn((float)v, 0.5f), 32767.5f);
+}
+__device__ __forceinline__ float cvt_i16_volk(int v) { return __fdiv_rn((float)v, 32768.0f); }
+
+// Load one complex sample of input format FMT at sample index i and convert it.
+template <int FMT>
+__device__ __forceinline__ float2 load_sample(const void* __restrict__ base, size_t i) {
+    if constexpr (FMT == 0) {
+        return __ldg(reinterpret_cast<const float2*>(base) + i);
+    } else if constexpr (FMT == 1 || FMT == 2) {
+        const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + i);
+        return FMT == 1 ? make_float2(cvt_u8_rtl(v.x), cvt_u8_rtl(v.y)) : make_float2(cvt_u8_tcp(v.x), cvt_u8_tcp(v.y));
+    } else if constexpr (FMT == 3) {
+        const char2 v = __ldg(reinterpret_cast<const char2*>(base) + i);
+        return make_float2(cvt_i8(v.x), cvt_i8(v.y));
+    } else {
+        const short2 v = __ldg(reinterpret_cast<const short2*>(base) + i);
+        return FMT == 4 ? make_float2(cvt_i16_file(v.x), cvt_i16_file(v.y)) : make_float2(cvt_i16_volk(v.x), cvt_i16_volk(v.y));
+    }
+}
+
+__host__ __device__ constexpr int fmt_bytes_per_sample(int fmt) {
+    return fmt == 0 ? 8 : (fmt == 1 || fmt == 2 || fmt == 3) ? 2 : 4;
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+} // namespace sdrpp

@@ -1,0 +1,50 @@
+// Host-side design maths of the signal path: window tables, windowed-sinc taps, the
+// RationalResampler plan and the PowerDecimator stage tables. All double precision, stored to
+// float exactly as the reference does, because these define the filter shapes and the integer
+// index arithmetic that results must reproduce.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace sdrpp {
+
+constexpr double kPi = 3.14159265358979323846; // DB_M_PI, dsp/math/constants.h:2
+
+// dsp::window::createWindow (dsp/window/window.h:38-64). buf needs size+1 floats.
+int design_window(int type, float* buf, int size, bool centered);
+
+// dsp::taps::estimateTapCount / lowPass (dsp/taps/estimate_tap_count.h:4-6, low_pass.h:7-11)
+int lowpass_tap_count(double transWidth, double sampleRate);
+std::vector<float> design_lowpass(double cutoff, double transWidth, double sampleRate);
+
+// One stage of a PowerDecimator plan (dsp/multirate/decim/plans.h:36-140)
+struct DecimStage {
+    int decimation;
+    int ntaps;
+    const float* taps;
+    int fir_id; // index into the distinct FIR table (13 filters)
+};
+// Stage list for ratio = 2^k, k in 1..13; empty if the ratio is invalid.
+std::vector<DecimStage> decim_plan(int ratio);
+
+// dsp::multirate::RationalResampler::reconfigure (dsp/multirate/rational_resampler.h:121-167)
+struct ResamplerPlan {
+    int mode = 3;   // 0 BOTH, 1 DECIM_ONLY, 2 RESAMP_ONLY, 3 NONE
+    int predec = 1; // power-of-two pre-decimation ratio
+    int interp = 1, decim = 1;
+    int tpp = 0;               // taps per phase
+    std::vector<float> taps;   // polyphase prototype, already scaled by interp
+};
+ResamplerPlan design_resampler(double inSR, double outSR);
+
+// dsp::multirate::PolyphaseBank (dsp/multirate/polyphase_bank.h:15-48): bank[phase][j], tpp each
+std::vector<float> build_polyphase_bank(const std::vector<float>& taps, int interp, int* tpp);
+
+// IQFrontEnd::genReshapeParams (signal_path/iq_frontend.h:56-60)
+void reshape_params(double sampleRate, int size, double rate, int* skip, int* nz);
+
+// FrequencyXlator increment (dsp/channel/frequency_xlator.h:15-23): the fp32-quantised phasor
+// (cos w, sin w) and the frequency it actually realises, in turns per sample.
+void xlator_increment(double offsetHz, double sampleRate, float* inc_re, float* inc_im, double* turns_eff);
+
+} // namespace sdrpp

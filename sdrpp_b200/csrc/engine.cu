@@ -1,0 +1,1205 @@
+// The front-end engine behind the C ABI (include/sdrpp_cuda.h): device IQ ring, spectrum framing,
+// VFO registry/grouping, per-block launch sequencing, pinned result buffers.
+//
+// Mirrors the wiring of IQFrontEnd (signal_path/iq_frontend.cpp:15-228) and the per-VFO objects
+// built by RxVFO::init (dsp/channel/rx_vfo.h:19-33), but as one stream-ordered launch sequence per
+// IQ block instead of a thread per block.
+#include "common.cuh"
+#include "design.h"
+#include "kernels.h"
+#include "../../include/sdrpp_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace sdrpp {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+static int fail(int code, const std::string& msg) { set_last_error(msg); return code; }
+
+static uint64_t turns_to_u64(double turns) {
+    // fractional turns in [-0.5, 0.5] -> 64-bit phase step (two's complement wrap)
+    double f = turns - floor(turns);
+    long double v = (long double)f * 18446744073709551616.0L;
+    if (v >= 18446744073709551615.0L) return 0;
+    return (uint64_t)v;
+}
+
+template <class T>
+static cudaError_t dev_alloc(T** p, size_t n, bool zero = true) {
+    cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VFO plan: the stage list RxVFO::init would build for (inSR, outSR, bw)
+// ---------------------------------------------------------------------------------------------
+struct TailPlanStage {
+    int type = TAIL_FIR, T = 1, D = 1, interp = 1;
+    std::vector<float> taps; // FIR taps or polyphase bank
+    float* d_taps = nullptr;
+    uint32_t in_off = 0;     // slab offset of the input data area
+    int cap_in = 0;
+};
+
+struct VfoPlan {
+    double inSR = 0, outSR = 0, bw = 0;
+    ResamplerPlan rp;
+    bool filter_needed = false;
+    int chan_taps = 0;
+    // stage 1
+    bool s1_fir = false;
+    int s1_D = 1, s1_T = 1, s1_A = 1;
+    std::vector<float> s1_taps;
+    std::vector<TailPlanStage> tail;
+    uint32_t final_off = 0;
+    int cap_final = 0;
+    size_t slab_elems = 0;
+    int max_block = 0;
+
+    ~VfoPlan() { for (auto& s : tail) if (s.d_taps) cudaFree(s.d_taps); }
+};
+
+static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_block, std::string* err) {
+    p.inSR = inSR; p.outSR = outSR; p.bw = bw; p.max_block = max_block;
+    if (!(inSR > 0) || !(outSR > 0) || !(bw > 0)) { *err = "sample rates and bandwidth must be positive"; return SDRPP_ERR_ARG; }
+    p.rp = design_resampler(inSR, outSR);
+    p.filter_needed = (bw != outSR); // rx_vfo.h:24
+    std::vector<DecimStage> dst;
+    if (p.rp.mode == 0 || p.rp.mode == 1) {
+        dst = decim_plan(p.rp.predec);
+        if (dst.empty()) { *err = "no PowerDecimator plan for ratio " + std::to_string(p.rp.predec); return SDRPP_ERR_ARG; }
+    }
+    size_t first_tail = 0;
+    if (!dst.empty()) {
+        const int D = dst[0].decimation, T = dst[0].ntaps, A = ceil_div(T, D);
+        if (stage1_supported(A, D)) {
+            p.s1_fir = true; p.s1_D = D; p.s1_T = T; p.s1_A = A;
+            p.s1_taps.assign(dst[0].taps, dst[0].taps + T);
+            first_tail = 1;
+        }
+    }
+    for (size_t i = first_tail; i < dst.size(); i++) {
+        TailPlanStage s;
+        s.type = TAIL_DECFIR; s.T = dst[i].ntaps; s.D = dst[i].decimation;
+        s.taps.assign(dst[i].taps, dst[i].taps + dst[i].ntaps);
+        p.tail.push_back(std::move(s));
+    }
+    if (p.rp.mode == 0 || p.rp.mode == 2) {
+        TailPlanStage s;
+        s.type = TAIL_POLY; s.D = p.rp.decim; s.interp = p.rp.interp;
+        int tpp = 0;
+        s.taps = build_polyphase_bank(p.rp.taps, p.rp.interp, &tpp);
+        s.T = tpp;
+        p.tail.push_back(std::move(s));
+    }
+    if (p.filter_needed) {
+        TailPlanStage s;
+        s.type = TAIL_FIR;
+        const double fw = bw / 2.0; // RxVFO::generateTaps, rx_vfo.h:117-121
+        s.taps = design_lowpass(fw, fw * 0.1, outSR);
+        s.T = (int)s.taps.size();
+        if (s.T < 1) { *err = "channel filter has no taps"; return SDRPP_ERR_ARG; }
+        p.chan_taps = s.T;
+        p.tail.push_back(std::move(s));
+    }
+    if ((int)p.tail.size() > kTailMaxStages) { *err = "too many stages"; return SDRPP_ERR_ARG; }
+    // capacities and slab layout
+    long long cap = p.s1_fir ? (max_block / p.s1_D + 2) : max_block;
+    uint32_t off = 0;
+    for (auto& s : p.tail) {
+        if (s.T - 1 > 2048) { *err = "filter longer than 2049 taps is not supported"; return SDRPP_ERR_ARG; }
+        const uint32_t hc = (uint32_t)((s.T - 1 + 1) & ~1);
+        s.in_off = off + hc;
+        s.cap_in = (int)cap;
+        off = s.in_off + (uint32_t)((cap + 1) & ~1LL);
+        if (s.type == TAIL_DECFIR) cap = cap / s.D + 2;
+        else if (s.type == TAIL_POLY) cap = cap * s.interp / s.D + 2;
+    }
+    p.final_off = off + 2;
+    p.cap_final = (int)cap;
+    p.slab_elems = (size_t)p.final_off + (size_t)((cap + 1) & ~1LL);
+    for (auto& s : p.tail) {
+        if (dev_alloc(&s.d_taps, s.taps.size(), false) != cudaSuccess ||
+            cudaMemcpy(s.d_taps, s.taps.data(), s.taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            *err = std::string("tap upload: ") + cudaGetErrorString(cudaGetLastError());
+            return SDRPP_ERR_CUDA;
+        }
+    }
+    return SDRPP_OK;
+}
+
+// Integer state of one group (identical for all members: same plan, same epoch).
+struct GroupState {
+    int s1_offset = 0;
+    int st_offset[kTailMaxStages] = { 0 };
+    int st_phase[kTailMaxStages] = { 0 };
+    int64_t abs_valid = 0; // epoch: samples before this absolute index read as zero
+    int64_t abs_out = 0;   // output samples produced since the epoch
+};
+
+struct Vfo {
+    bool alive = false;
+    double outSR = 0, bw = 0, offset = 0;
+    int demod = 0;
+    std::shared_ptr<VfoPlan> plan;
+    int group = -1;
+    // NCO
+    uint64_t phi_ref = 0; int64_t n_ref = 0; uint64_t dphi = 0; uint64_t dphi2 = 0;
+    double turns = 0; // phase step in turns (for the folded taps)
+    float2* slab = nullptr;
+    uint32_t out_off = 0;
+    int dev_index = -1;
+};
+
+struct Group {
+    std::shared_ptr<VfoPlan> plan;
+    int demod = 0;
+    GroupState st;
+    std::vector<int> members;
+    int first_dev = 0;
+    float4* d_G = nullptr;
+    std::vector<float4> h_G;
+    bool g_dirty = true;
+    int last_n_final = 0;
+};
+
+struct ResultSet {
+    sdrpp_cf32* iq = nullptr;
+    float* demod = nullptr;
+    float* rows = nullptr;
+    int nrows = 0;
+    std::vector<int> counts; // per VFO id
+    cudaEvent_t done = nullptr;
+    bool pending = false;
+};
+
+} // namespace sdrpp
+
+using namespace sdrpp;
+
+struct sdrpp_cuda_frontend {
+    int device = 0;
+    sdrpp_cuda_frontend_cfg cfg{};
+    double eff_sr = 0;
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    long long launches = 0;
+    std::string sticky;
+
+    // input staging
+    void* h_stage[2] = { nullptr, nullptr };
+    void* d_raw[2] = { nullptr, nullptr };
+    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
+    bool consumed_valid[2] = { false, false };
+    size_t raw_cap = 0;
+    long long seq = 0;
+
+    // pre-processing
+    std::vector<DecimStage> fe_stages;
+    std::vector<float*> fe_taps;
+    std::vector<float2*> fe_buf;   // per stage: [T-1 hist | max input]
+    std::vector<int> fe_offset;
+    float2* dc_in = nullptr; float2* dc_state = nullptr; float2* dc_scratch = nullptr;
+
+    // ring
+    float2* ring = nullptr; uint32_t ring_mask = 0; int ring_log2 = 0;
+    int64_t abs_pos = 0; // absolute index of the next sample to be written
+    int last_count = 0;  // post-preprocessing samples of the last block
+
+    // spectrum
+    int nz = 0, skip = 0;
+    float* d_window = nullptr;
+    float2* d_inter = nullptr; int inter_frames = 0;
+    float* d_rows = nullptr; int rows_cap = 0;
+    int64_t fft_next = 0;
+
+    // VFOs
+    std::vector<Vfo> vfos;
+    std::vector<Group> groups;
+    std::map<std::tuple<double, double, double>, std::weak_ptr<VfoPlan>> plan_cache;
+    bool layout_dirty = true;
+    VfoDev* d_vfos = nullptr; int d_vfos_cap = 0;
+    float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; size_t arena_cap = 0, arena_used = 0;
+
+    // results
+    ResultSet rs[2];
+    size_t rs_arena_cap = 0; int rs_rows_cap = 0; int rs_rows_n = 0;
+    int cur = -1; // result set of the last waited block
+    long long waited = 0;
+    bool readback = true;
+
+    // profiling
+    bool profiling = false;
+    cudaEvent_t pev[5] = { nullptr };
+    float kernel_ms[4] = { 0, 0, 0, 0 };
+    bool pev_valid = false;
+};
+
+namespace sdrpp {
+
+#define FE_TRY(fe, expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            (fe)->sticky = std::string(#expr) + ": " + cudaGetErrorString(_e);                   \
+            set_last_error((fe)->sticky);                                                        \
+            return SDRPP_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+static int fe_check(sdrpp_cuda_frontend* fe) {
+    if (!fe) return fail(SDRPP_ERR_ARG, "null front end");
+    if (!fe->sticky.empty()) { set_last_error(fe->sticky); return SDRPP_ERR_CUDA; }
+    cudaError_t e = cudaSetDevice(fe->device);
+    if (e != cudaSuccess) return fail(SDRPP_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return SDRPP_OK;
+}
+
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// ---- pre-processing configuration ----------------------------------------------------------
+static int configure_preproc(sdrpp_cuda_frontend* fe) {
+    for (float* t : fe->fe_taps) cudaFree(t);
+    for (float2* b : fe->fe_buf) cudaFree(b);
+    fe->fe_taps.clear(); fe->fe_buf.clear(); fe->fe_offset.clear(); fe->fe_stages.clear();
+    const int ratio = fe->cfg.decim_ratio;
+    if (ratio > 1) {
+        fe->fe_stages = decim_plan(ratio);
+        if (fe->fe_stages.empty()) return fail(SDRPP_ERR_ARG, "invalid decimation ratio (PowerDecimator::checkRatio)");
+        int cap = fe->cfg.max_block;
+        for (const DecimStage& s : fe->fe_stages) {
+            float* t = nullptr; float2* b = nullptr;
+            FE_TRY(fe, dev_alloc(&t, (size_t)s.ntaps, false));
+            FE_TRY(fe, cudaMemcpy(t, s.taps, sizeof(float) * s.ntaps, cudaMemcpyHostToDevice));
+            FE_TRY(fe, dev_alloc(&b, (size_t)(s.ntaps - 1) + (size_t)cap + 8));
+            fe->fe_taps.push_back(t); fe->fe_buf.push_back(b); fe->fe_offset.push_back(0);
+            cap = cap / s.decimation + 2;
+        }
+    }
+    fe->eff_sr = fe->cfg.sample_rate / (double)std::max(1, ratio);
+    if (!fe->dc_in) {
+        FE_TRY(fe, dev_alloc(&fe->dc_in, (size_t)fe->cfg.max_block + 8));
+        FE_TRY(fe, dev_alloc(&fe->dc_state, 1));
+        FE_TRY(fe, dev_alloc(&fe->dc_scratch, (size_t)dc_block_chunks(fe->cfg.max_block) + 8));
+    }
+    return SDRPP_OK;
+}
+
+// ---- spectrum configuration (IQFrontEnd::updateFFTPath / updateFFTSize) ------------------------
+static int configure_fft(sdrpp_cuda_frontend* fe) {
+    if (fe->d_window) { cudaFree(fe->d_window); fe->d_window = nullptr; }
+    if (fe->d_inter) { cudaFree(fe->d_inter); fe->d_inter = nullptr; }
+    if (fe->d_rows) { cudaFree(fe->d_rows); fe->d_rows = nullptr; }
+    for (int i = 0; i < 2; i++) if (fe->rs[i].rows) { cudaFreeHost(fe->rs[i].rows); fe->rs[i].rows = nullptr; }
+    fe->rows_cap = 0; fe->rs_rows_cap = 0;
+    const int N = fe->cfg.fft_size;
+    if (N == 0) return SDRPP_OK;
+    int N1, N2;
+    if (spectrum_split(N, &N1, &N2) < 0) return fail(SDRPP_ERR_ARG, "fft_size must be a power of two in 64..4194304");
+    if (!(fe->cfg.fft_rate > 0)) return fail(SDRPP_ERR_ARG, "fft_rate must be positive");
+    if (fe->cfg.fft_window < 0 || fe->cfg.fft_window >= SDRPP_WIN_COUNT) return fail(SDRPP_ERR_ARG, "unknown window type");
+    reshape_params(fe->eff_sr, N, fe->cfg.fft_rate, &fe->skip, &fe->nz);
+    if (fe->nz < 1) return fail(SDRPP_ERR_ARG, "fft_rate too high for this sample rate");
+    const long long interval = (long long)fe->nz + fe->skip;
+    if ((long long)fe->nz + fe->cfg.max_block + 4096 > (1LL << fe->ring_log2))
+        return fail(SDRPP_ERR_ARG, "ring too small for this fft size / block size");
+    std::vector<float> w((size_t)fe->nz + 2);
+    design_window(fe->cfg.fft_window, w.data(), fe->nz, true);
+    FE_TRY(fe, dev_alloc(&fe->d_window, (size_t)fe->nz, false));
+    FE_TRY(fe, cudaMemcpy(fe->d_window, w.data(), sizeof(float) * fe->nz, cudaMemcpyHostToDevice));
+    int rows = fe->cfg.max_fft_rows > 0 ? fe->cfg.max_fft_rows : (int)(fe->cfg.max_block / interval + 2);
+    fe->rows_cap = rows;
+    FE_TRY(fe, dev_alloc(&fe->d_rows, (size_t)rows * N, false));
+    if (N1 > 1) {
+        // frames per launch group: keep the four-step intermediate within ~32 MB so it stays in L2
+        fe->inter_frames = std::max(1, std::min(rows, (int)((32u << 20) / ((size_t)N * 8))));
+        FE_TRY(fe, dev_alloc(&fe->d_inter, (size_t)fe->inter_frames * N, false));
+    } else {
+        fe->inter_frames = rows;
+    }
+    for (int i = 0; i < 2; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].rows, (size_t)rows * N * sizeof(float)));
+    fe->rs_rows_cap = rows;
+    fe->fft_next = fe->abs_pos;
+    return SDRPP_OK;
+}
+
+// ---- VFO layout ------------------------------------------------------------------------------
+static void fill_g_for_vfo(Group& g, int lane_index, const Vfo& v) {
+    const VfoPlan& p = *g.plan;
+    const int A = p.s1_A, D = p.s1_D, pcp = stage1_pcp(D);
+    for (int k = 0; k < A * D; k++) {
+        float re = 0.0f, im = 0.0f;
+        if (k < p.s1_T) {
+            // g[k] = h[k] * exp(+j*2*pi*turns*k): the NCO advance over k samples folded into the tap
+            double ang = v.turns * (double)k;
+            ang -= floor(ang);
+            re = (float)((double)p.s1_taps[(size_t)k] * cos(2.0 * kPi * ang));
+            im = (float)((double)p.s1_taps[(size_t)k] * sin(2.0 * kPi * ang));
+        }
+        size_t idx; int half;
+        stage1_g_index(A, D, pcp, lane_index, k, &idx, &half);
+        float4& e = g.h_G[idx];
+        if (half == 0) { e.x = re; e.y = im; } else { e.z = re; e.w = im; }
+    }
+}
+
+static int rebuild_layout(sdrpp_cuda_frontend* fe) {
+    // device VFO table ordered by group; arena offsets by VFO
+    int total = 0;
+    size_t arena = 0;
+    for (Group& g : fe->groups) { g.first_dev = total; total += (int)g.members.size(); }
+    std::vector<VfoDev> h((size_t)std::max(total, 1));
+    for (Group& g : fe->groups) {
+        for (size_t i = 0; i < g.members.size(); i++) {
+            Vfo& v = fe->vfos[(size_t)g.members[i]];
+            v.dev_index = g.first_dev + (int)i;
+            v.out_off = (uint32_t)arena;
+            arena += (size_t)((g.plan->cap_final + 3) & ~3);
+            VfoDev& d = h[(size_t)v.dev_index];
+            d.slab = v.slab; d.phi_ref = v.phi_ref; d.n_ref = v.n_ref; d.dphi = v.dphi; d.dphi2 = v.dphi2;
+            d.out_off = v.out_off; d.pad = 0;
+        }
+        if (g.plan->s1_fir && g.g_dirty) {
+            const size_t n = stage1_g_elems(g.plan->s1_A, g.plan->s1_D, (int)g.members.size());
+            g.h_G.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
+            for (size_t i = 0; i < g.members.size(); i++) fill_g_for_vfo(g, (int)i, fe->vfos[(size_t)g.members[i]]);
+            if (g.d_G) { FE_TRY(fe, cudaStreamSynchronize(fe->st)); cudaFree(g.d_G); g.d_G = nullptr; }
+            FE_TRY(fe, dev_alloc(&g.d_G, n, false));
+            FE_TRY(fe, cudaMemcpyAsync(g.d_G, g.h_G.data(), n * sizeof(float4), cudaMemcpyHostToDevice, fe->st));
+            FE_TRY(fe, cudaStreamSynchronize(fe->st));
+            g.g_dirty = false;
+        }
+    }
+    if (total > fe->d_vfos_cap) {
+        if (fe->d_vfos) { FE_TRY(fe, cudaStreamSynchronize(fe->st)); cudaFree(fe->d_vfos); }
+        fe->d_vfos_cap = std::max(total, 64);
+        FE_TRY(fe, dev_alloc(&fe->d_vfos, (size_t)fe->d_vfos_cap));
+    }
+    if (total > 0) {
+        FE_TRY(fe, cudaMemcpyAsync(fe->d_vfos, h.data(), sizeof(VfoDev) * (size_t)total, cudaMemcpyHostToDevice, fe->st));
+        FE_TRY(fe, cudaStreamSynchronize(fe->st));
+    }
+    fe->arena_used = arena;
+    if (arena > fe->arena_cap) {
+        FE_TRY(fe, cudaStreamSynchronize(fe->st));
+        if (fe->d_arena_iq) cudaFree(fe->d_arena_iq);
+        if (fe->d_arena_demod) cudaFree(fe->d_arena_demod);
+        fe->arena_cap = arena + arena / 2 + 1024;
+        FE_TRY(fe, dev_alloc(&fe->d_arena_iq, fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_demod, fe->arena_cap));
+    }
+    if (arena > fe->rs_arena_cap) {
+        FE_TRY(fe, cudaStreamSynchronize(fe->st));
+        for (int i = 0; i < 2; i++) {
+            if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
+            if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
+            FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].iq, fe->arena_cap * sizeof(sdrpp_cf32)));
+            FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].demod, fe->arena_cap * sizeof(float)));
+        }
+        fe->rs_arena_cap = fe->arena_cap;
+    }
+    fe->layout_dirty = false;
+    return SDRPP_OK;
+}
+
+static void remove_from_group(sdrpp_cuda_frontend* fe, int id) {
+    Vfo& v = fe->vfos[(size_t)id];
+    if (v.group < 0) return;
+    Group& g = fe->groups[(size_t)v.group];
+    g.members.erase(std::remove(g.members.begin(), g.members.end(), id), g.members.end());
+    g.g_dirty = true;
+    v.group = -1;
+    // drop empty groups (and fix up indices)
+    for (size_t gi = 0; gi < fe->groups.size();) {
+        if (fe->groups[gi].members.empty()) {
+            if (fe->groups[gi].d_G) { cudaStreamSynchronize(fe->st); cudaFree(fe->groups[gi].d_G); }
+            fe->groups.erase(fe->groups.begin() + (long)gi);
+            for (Vfo& o : fe->vfos) if (o.alive && o.group > (int)gi) o.group--;
+        } else gi++;
+    }
+    fe->layout_dirty = true;
+}
+
+// Put a VFO into the group of its (plan, demod, epoch); a fresh epoch = zero history from now on.
+static void join_group(sdrpp_cuda_frontend* fe, int id, int64_t epoch) {
+    Vfo& v = fe->vfos[(size_t)id];
+    for (size_t gi = 0; gi < fe->groups.size(); gi++) {
+        Group& g = fe->groups[gi];
+        if (g.plan == v.plan && g.demod == v.demod && g.st.abs_valid == epoch && g.st.abs_out == 0 && epoch == fe->abs_pos) {
+            g.members.push_back(id); g.g_dirty = true; v.group = (int)gi; fe->layout_dirty = true;
+            return;
+        }
+    }
+    Group g;
+    g.plan = v.plan; g.demod = v.demod; g.st.abs_valid = epoch;
+    g.members.push_back(id);
+    fe->groups.push_back(std::move(g));
+    v.group = (int)fe->groups.size() - 1;
+    fe->layout_dirty = true;
+}
+
+static void set_nco(sdrpp_cuda_frontend* fe, Vfo& v, double offset, bool keep_phase) {
+    // phase continuity on retune (frequency_xlator.h:25-29): phase at the next input sample is kept
+    const int64_t now = fe->abs_pos;
+    uint64_t phi_now = 0;
+    if (keep_phase) phi_now = v.phi_ref + (uint64_t)(now - v.n_ref) * v.dphi;
+    double turns;
+    xlator_increment(-offset, fe->eff_sr, nullptr, nullptr, &turns); // RxVFO: xlator.init(NULL, -_offset, inSR), rx_vfo.h:27
+    v.turns = turns;
+    v.dphi = turns_to_u64(turns);
+    v.phi_ref = phi_now; v.n_ref = now;
+    v.offset = offset;
+    // SSB second translation (demod/ssb.h:119-126) at the output rate
+    double tr = 0.0;
+    if (v.demod == SDRPP_DEMOD_USB) tr = v.bw / 2.0;
+    else if (v.demod == SDRPP_DEMOD_LSB) tr = -v.bw / 2.0;
+    double t2;
+    xlator_increment(tr, v.outSR, nullptr, nullptr, &t2);
+    v.dphi2 = turns_to_u64(t2);
+}
+
+static int get_plan(sdrpp_cuda_frontend* fe, double outSR, double bw, std::shared_ptr<VfoPlan>* out) {
+    auto key = std::make_tuple(fe->eff_sr, outSR, bw);
+    auto it = fe->plan_cache.find(key);
+    if (it != fe->plan_cache.end()) {
+        if (auto sp = it->second.lock()) { *out = sp; return SDRPP_OK; }
+    }
+    auto sp = std::make_shared<VfoPlan>();
+    std::string err;
+    int rc = build_plan(*sp, fe->eff_sr, outSR, bw, fe->cfg.max_block, &err);
+    if (rc != SDRPP_OK) return fail(rc, err);
+    fe->plan_cache[key] = sp;
+    *out = sp;
+    return SDRPP_OK;
+}
+
+// ---- one block -------------------------------------------------------------------------------
+static void advance_decim(int& offset, int D, int count, int* nout) {
+    // for (; offset < count; offset += D) out++; offset -= count;   (decimating_fir.h:51-62)
+    int n = 0;
+    if (offset < count) n = (count - offset + D - 1) / D;
+    offset = offset + n * D - count;
+    *nout = n;
+}
+
+static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int count, ResultSet& rs) {
+    cudaStream_t st = fe->st;
+    const bool prof = fe->profiling;
+    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[0], st));
+
+    // ---- pre-processing chain: [decim] -> [dc block] -> [conjugate] -> ring (iq_frontend.cpp:30-37)
+    const RingRef ring{ fe->ring, fe->ring_mask };
+    const uint32_t wpos = (uint32_t)((uint64_t)fe->abs_pos & fe->ring_mask);
+    const bool conj = fe->cfg.invert_iq != 0;
+    const bool dc = fe->cfg.dc_blocking != 0;
+    int n = count;
+    if (fe->fe_stages.empty() && !dc) {
+        FE_TRY(fe, launch_ingest(fmt, d_in, count, ring, wpos, conj, st)); fe->launches++;
+    } else {
+        const RingRef lin_dc{ fe->dc_in, 0xFFFFFFFFu };
+        if (fe->fe_stages.empty()) {
+            FE_TRY(fe, launch_ingest(fmt, d_in, count, lin_dc, 0, false, st)); fe->launches++;
+        } else {
+            const size_t ns = fe->fe_stages.size();
+            RingRef first{ fe->fe_buf[0], 0xFFFFFFFFu };
+            FE_TRY(fe, launch_ingest(fmt, d_in, count, first, (uint32_t)(fe->fe_stages[0].ntaps - 1), false, st)); fe->launches++;
+            for (size_t s = 0; s < ns; s++) {
+                const DecimStage& ds = fe->fe_stages[s];
+                int off = fe->fe_offset[s], nout = 0;
+                const int off0 = off;
+                advance_decim(off, ds.decimation, n, &nout);
+                const bool last = (s + 1 == ns);
+                RingRef dst; uint32_t pos; bool cj = false;
+                if (!last) { dst = RingRef{ fe->fe_buf[s + 1], 0xFFFFFFFFu }; pos = (uint32_t)(fe->fe_stages[s + 1].ntaps - 1); }
+                else if (dc) { dst = lin_dc; pos = 0; }
+                else { dst = ring; pos = wpos; cj = conj; }
+                FE_TRY(fe, launch_decim_stage(fe->fe_buf[s], fe->fe_taps[s], ds.ntaps, ds.decimation, off0, nout, dst, pos, cj, st));
+                FE_TRY(fe, launch_shift_history(fe->fe_buf[s], ds.ntaps - 1, n, st));
+                fe->launches += (nout > 0 ? 1 : 0) + ((ds.ntaps > 1 && n > 0) ? 1 : 0);
+                fe->fe_offset[s] = off;
+                n = nout;
+            }
+        }
+        if (dc) {
+            const float rate = (float)(50.0 / fe->eff_sr); // IQFrontEnd::genDCBlockRate, iq_frontend.h:52-54
+            FE_TRY(fe, launch_dc_block(fe->dc_in, n, rate, fe->dc_state, fe->dc_scratch, ring, wpos, conj, st, &fe->launches));
+        }
+    }
+    const int64_t abs_block = fe->abs_pos;
+    fe->abs_pos += n;
+    fe->last_count = n;
+    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[1], st));
+
+    // ---- spectrum frames completed by this block (reshaper.h:102-129 keep/skip + handler) --------
+    rs.nrows = 0;
+    if (fe->cfg.fft_size > 0) {
+        const int N = fe->cfg.fft_size;
+        const int64_t interval = (int64_t)fe->nz + fe->skip;
+        int frames = 0;
+        const int64_t first = fe->fft_next;
+        while (fe->fft_next + fe->nz <= fe->abs_pos && frames < fe->rows_cap) { frames++; fe->fft_next += interval; }
+        // frames beyond the row buffer are dropped (like a waterfall that cannot keep up)
+        while (fe->fft_next + fe->nz <= fe->abs_pos) fe->fft_next += interval;
+        for (int f0 = 0; f0 < frames; f0 += fe->inter_frames) {
+            SpectrumArgs a{};
+            a.in = fe->ring; a.ring_mask = fe->ring_mask;
+            a.start = (uint32_t)((uint64_t)(first + (int64_t)f0 * interval) & fe->ring_mask);
+            a.frame_stride = (uint32_t)interval;
+            a.nz = fe->nz; a.window = fe->d_window; a.inter = fe->d_inter;
+            a.rows = fe->d_rows + (size_t)f0 * N; a.X = nullptr;
+            a.frames = std::min(fe->inter_frames, frames - f0);
+            FE_TRY(fe, launch_spectrum(N, a, st, &fe->launches));
+        }
+        rs.nrows = frames;
+    }
+    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[2], st));
+
+    // ---- channelizer ----------------------------------------------------------------------------
+    if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
+    std::vector<TailArgs> tails;
+    std::vector<int> tail_totals;
+    for (Group& g : fe->groups) {
+        const VfoPlan& p = *g.plan;
+        Stage1Args a{};
+        a.ring = ring;
+        a.nvfo = (int)g.members.size();
+        a.vfos = fe->d_vfos + g.first_dev;
+        a.abs_valid = g.st.abs_valid;
+        a.out_off = p.tail.empty() ? p.final_off : p.tail[0].in_off;
+        int nprev = 0;
+        if (p.s1_fir) {
+            int off = g.st.s1_offset;
+            const int off0 = off;
+            advance_decim(off, p.s1_D, n, &nprev);
+            g.st.s1_offset = off;
+            a.D = p.s1_D; a.T = p.s1_T; a.A = p.s1_A; a.pcp = stage1_pcp(p.s1_D);
+            a.M = nprev; a.G = g.d_G;
+            a.abs_first = abs_block - (p.s1_T - 1) + off0;
+            a.ring_first = (uint32_t)((uint64_t)a.abs_first & fe->ring_mask);
+            FE_TRY(fe, launch_stage1(a, st));
+        } else {
+            nprev = n;
+            a.D = 1; a.T = 1; a.A = 1; a.pcp = 1; a.M = n; a.G = nullptr;
+            a.abs_first = abs_block;
+            a.ring_first = wpos;
+            FE_TRY(fe, launch_mix_only(a, st));
+        }
+        if (nprev > 0) fe->launches++;
+
+        if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
+            TailArgs t{};
+            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq; t.arena_demod = fe->d_arena_demod;
+            tails.push_back(t); tail_totals.push_back(0);
+        }
+        TailArgs& t = tails.back();
+        TailGroup& tg = t.g[t.ngroups++];
+        tail_totals.back() += (int)g.members.size();
+        tg.first_vfo = g.first_dev; tg.nvfo = (int)g.members.size();
+        tg.nstages = (int)p.tail.size();
+        for (size_t s = 0; s < p.tail.size(); s++) {
+            const TailPlanStage& ps = p.tail[s];
+            TailStage& ts = tg.st[s];
+            ts.type = ps.type; ts.T = ps.T; ts.D = ps.D; ts.interp = ps.interp; ts.taps = ps.d_taps; ts.in_off = ps.in_off;
+            ts.n_in = nprev; ts.offset = g.st.st_offset[s]; ts.phase = g.st.st_phase[s];
+            int nout = 0;
+            if (ps.type == TAIL_DECFIR) {
+                advance_decim(g.st.st_offset[s], ps.D, nprev, &nout);
+            } else if (ps.type == TAIL_FIR) {
+                nout = nprev;
+            } else {
+                // polyphase_resampler.h:75-93 in closed form
+                const long long c = (long long)nprev - ts.offset;
+                long long cnt = 0;
+                if (c > 0) cnt = (c * ps.interp - ts.phase + ps.D - 1) / ps.D;
+                const long long P = (long long)ts.phase + cnt * ps.D;
+                g.st.st_offset[s] = (int)((long long)ts.offset + P / ps.interp - nprev);
+                g.st.st_phase[s] = (int)(P % ps.interp);
+                nout = (int)cnt;
+            }
+            ts.n_out = nout;
+            nprev = nout;
+        }
+        tg.final_off = p.final_off; tg.n_final = nprev; tg.demod = g.demod;
+        tg.inv_dev = (float)(1.0 / (2.0 * kPi * ((p.bw / 2.0) / p.outSR))); // quadrature.h:21-28 with dev = bw/2 (fm.h:31)
+        tg.abs_out = g.st.abs_out;
+        g.st.abs_out += nprev;
+        g.last_n_final = nprev;
+    }
+    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[3], st));
+    for (size_t i = 0; i < tails.size(); i++) {
+        FE_TRY(fe, launch_tail(tails[i], tail_totals[i], st));
+        if (tail_totals[i] > 0) fe->launches++;
+    }
+    if (prof) { FE_TRY(fe, cudaEventRecord(fe->pev[4], st)); fe->pev_valid = true; }
+
+    // ---- results to pinned host memory --------------------------------------------------------------
+    rs.counts.assign(fe->vfos.size(), 0);
+    for (const Group& g : fe->groups)
+        for (int id : g.members) rs.counts[(size_t)id] = g.last_n_final;
+    if (fe->readback) {
+        if (fe->arena_used > 0) {
+            FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, st));
+            FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        if (rs.nrows > 0)
+            FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    FE_TRY(fe, cudaEventRecord(rs.done, st));
+    rs.pending = true;
+    return SDRPP_OK;
+}
+
+static int wait_set(sdrpp_cuda_frontend* fe, int idx) {
+    ResultSet& rs = fe->rs[idx];
+    if (rs.pending) {
+        FE_TRY(fe, cudaEventSynchronize(rs.done));
+        rs.pending = false;
+    }
+    return SDRPP_OK;
+}
+
+static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count, bool device_src) {
+    int rc = fe_check(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (fmt < 0 || fmt >= SDRPP_FMT_COUNT) return fail(SDRPP_ERR_ARG, "unknown sample format");
+    if (!in || count <= 0 || count > fe->cfg.max_block) return fail(SDRPP_ERR_ARG, "count must be in 1..max_block");
+    const int slot = (int)(fe->seq & 1);
+    ResultSet& rs = fe->rs[slot];
+    rc = wait_set(fe, slot); // the block that used this result set two submits ago must be done
+    if (rc != SDRPP_OK) return rc;
+    const void* d_in = in;
+    if (!device_src) {
+        const size_t bytes = (size_t)count * fmt_bytes_per_sample(fmt);
+        const void* src = in;
+        cudaPointerAttributes attr{};
+        bool pinned = (cudaPointerGetAttributes(&attr, in) == cudaSuccess) && (attr.type == cudaMemoryTypeHost);
+        cudaGetLastError();
+        if (fe->consumed_valid[slot]) FE_TRY(fe, cudaStreamWaitEvent(fe->st_copy, fe->ev_consumed[slot], 0));
+        if (!pinned) {
+            // pageable source: the staging buffer is reusable once its previous H2D copy has finished
+            FE_TRY(fe, cudaEventSynchronize(fe->ev_h2d[slot]));
+            memcpy(fe->h_stage[slot], in, bytes);
+            src = fe->h_stage[slot];
+        }
+        FE_TRY(fe, cudaMemcpyAsync(fe->d_raw[slot], src, bytes, cudaMemcpyHostToDevice, fe->st_copy));
+        FE_TRY(fe, cudaEventRecord(fe->ev_h2d[slot], fe->st_copy));
+        FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_h2d[slot], 0));
+        d_in = fe->d_raw[slot];
+    }
+    rc = process_block(fe, fmt, d_in, count, rs);
+    if (rc != SDRPP_OK) return rc;
+    if (!device_src) {
+        // the raw buffer may be overwritten once this block's kernels are done
+        FE_TRY(fe, cudaEventRecord(fe->ev_consumed[slot], fe->st));
+        fe->consumed_valid[slot] = true;
+    }
+    fe->seq++;
+    return SDRPP_OK;
+}
+
+// ---- one-shot context ----------------------------------------------------------------------------
+struct OneShot {
+    std::mutex mtx;
+    cudaStream_t st = nullptr;
+    void* d_a = nullptr; size_t cap_a = 0;
+    void* d_b = nullptr; size_t cap_b = 0;
+    void* d_c = nullptr; size_t cap_c = 0;
+    void* d_d = nullptr; size_t cap_d = 0;
+    int device = -1;
+};
+static OneShot g_os;
+static thread_local int g_device = 0;
+
+static cudaError_t os_reserve(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return cudaSuccess;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) *cap = bytes;
+    return e;
+}
+static int os_prepare() {
+    SDRPP_CUDA_TRY(cudaSetDevice(g_device));
+    if (g_os.device != g_device) {
+        if (g_os.st) { cudaStreamDestroy(g_os.st); g_os.st = nullptr; }
+        g_os.d_a = g_os.d_b = g_os.d_c = g_os.d_d = nullptr;
+        g_os.cap_a = g_os.cap_b = g_os.cap_c = g_os.cap_d = 0;
+        g_os.device = g_device;
+    }
+    if (!g_os.st) SDRPP_CUDA_TRY(cudaStreamCreateWithFlags(&g_os.st, cudaStreamNonBlocking));
+    return SDRPP_OK;
+}
+
+} // namespace sdrpp
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* sdrpp_cuda_version(void) { return "sdrpp-b200 0.1 (sm_100a)"; }
+const char* sdrpp_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int sdrpp_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sdrpp_cuda_init(int device) {
+    int n = sdrpp_cuda_device_count();
+    if (n <= 0) return fail(SDRPP_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= n) return fail(SDRPP_ERR_ARG, "device index out of range");
+    SDRPP_CUDA_TRY(cudaSetDevice(device));
+    g_device = device;
+    return SDRPP_OK;
+}
+
+void* sdrpp_cuda_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_last_error(std::string("cudaMallocHost: ") + cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void sdrpp_cuda_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- design maths ----------------------------------------------------------------------------
+int sdrpp_cuda_design_window(int type, float* buf, int size, int centered) {
+    if (design_window(type, buf, size, centered != 0) != 0) return fail(SDRPP_ERR_ARG, "bad window type or size");
+    return SDRPP_OK;
+}
+int sdrpp_cuda_design_lowpass(double cutoff, double transWidth, double sampleRate, float* out, int cap) {
+    if (!(transWidth > 0) || !(sampleRate > 0)) return fail(SDRPP_ERR_ARG, "bad filter spec");
+    const int n = lowpass_tap_count(transWidth, sampleRate);
+    if (out && cap > 0) {
+        std::vector<float> t = design_lowpass(cutoff, transWidth, sampleRate);
+        memcpy(out, t.data(), sizeof(float) * (size_t)std::min(n, cap));
+    }
+    return n;
+}
+int sdrpp_cuda_design_resampler(double inSR, double outSR, int* info, float* taps, int cap) {
+    if (!(inSR > 0) || !(outSR > 0) || !info) return fail(SDRPP_ERR_ARG, "bad rates");
+    ResamplerPlan p = design_resampler(inSR, outSR);
+    info[0] = p.mode; info[1] = p.predec; info[2] = p.interp; info[3] = p.decim;
+    info[4] = (int)p.taps.size(); info[5] = p.tpp;
+    if (taps && cap > 0) memcpy(taps, p.taps.data(), sizeof(float) * std::min<size_t>(p.taps.size(), (size_t)cap));
+    return SDRPP_OK;
+}
+int sdrpp_cuda_design_decim_plan(int ratio, int* decimation, int* tapcount, const float** taps) {
+    std::vector<DecimStage> s = decim_plan(ratio);
+    for (size_t i = 0; i < s.size(); i++) {
+        if (decimation) decimation[i] = s[i].decimation;
+        if (tapcount) tapcount[i] = s[i].ntaps;
+        if (taps) taps[i] = s[i].taps;
+    }
+    return (int)s.size();
+}
+void sdrpp_cuda_design_reshape(double sampleRate, int fftSize, double fftRate, int* skip, int* nz) {
+    reshape_params(sampleRate, fftSize, fftRate, skip, nz);
+}
+
+// ---- one-shot operations -----------------------------------------------------------------------
+int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf32* out) {
+    if (fmt < 0 || fmt >= SDRPP_FMT_COUNT || nsamples < 0 || (nsamples > 0 && (!in || !out))) return fail(SDRPP_ERR_ARG, "bad argument");
+    if (nsamples == 0) return SDRPP_OK;
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    const size_t inb = (size_t)nsamples * fmt_bytes_per_sample(fmt), outb = (size_t)nsamples * 8;
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, inb));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, outb));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, in, inb, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(launch_ingest(fmt, g_os.d_a, nsamples, RingRef{ (float2*)g_os.d_b, 0xFFFFFFFFu }, 0, false, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_b, outb, cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* window, float* row, sdrpp_cf32* X) {
+    int N1, N2;
+    if (spectrum_split(N, &N1, &N2) < 0) return fail(SDRPP_ERR_ARG, "N must be a power of two in 64..4194304");
+    if (nz < 1 || nz > N || !frame || !window || fmt < 0 || fmt >= SDRPP_FMT_COUNT) return fail(SDRPP_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    const size_t inb = (size_t)nz * fmt_bytes_per_sample(fmt);
+    // d_a: raw frame; d_b: [cf32 frame nz | window nz floats]; d_c: four-step intermediate; d_d: [row N floats | X N cf32]
+    const size_t woff = ((size_t)nz * 8 + 63) & ~(size_t)63;
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, inb));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, woff + (size_t)nz * 4));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, (size_t)N * 8));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_d, &g_os.cap_d, (size_t)N * 12));
+    float2* d_frame = (float2*)g_os.d_b;
+    float* d_win = (float*)((char*)g_os.d_b + woff);
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, frame, inb, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(d_win, window, (size_t)nz * 4, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(launch_ingest(fmt, g_os.d_a, nz, RingRef{ d_frame, 0xFFFFFFFFu }, 0, false, g_os.st));
+    SpectrumArgs a{};
+    a.in = d_frame; a.ring_mask = 0xFFFFFFFFu; a.start = 0; a.frame_stride = 0; a.nz = nz; a.window = d_win;
+    a.inter = (float2*)g_os.d_c;
+    a.rows = row ? (float*)g_os.d_d : nullptr;
+    a.X = X ? (float2*)((char*)g_os.d_d + (size_t)N * 4) : nullptr;
+    a.frames = 1;
+    SDRPP_CUDA_TRY(launch_spectrum(N, a, g_os.st, nullptr));
+    if (row) SDRPP_CUDA_TRY(cudaMemcpyAsync(row, a.rows, (size_t)N * 4, cudaMemcpyDeviceToHost, g_os.st));
+    if (X) SDRPP_CUDA_TRY(cudaMemcpyAsync(X, a.X, (size_t)N * 8, cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    return SDRPP_OK;
+}
+
+// ---- front end ---------------------------------------------------------------------------------
+sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* cfg) {
+    if (!cfg) { set_last_error("null cfg"); return nullptr; }
+    if (!(cfg->sample_rate > 0)) { set_last_error("sample_rate must be positive"); return nullptr; }
+    if (cfg->decim_ratio != 0 && cfg->decim_ratio != 1 && (!is_pow2(cfg->decim_ratio) || cfg->decim_ratio > 8192)) {
+        set_last_error("decim_ratio must be 1 or a power of two <= 8192"); return nullptr;
+    }
+    if (sdrpp_cuda_device_count() <= 0) { set_last_error("no CUDA device: this library has no CPU fallback"); return nullptr; }
+    auto* fe = new sdrpp_cuda_frontend();
+    fe->device = g_device;
+    fe->cfg = *cfg;
+    if (fe->cfg.decim_ratio < 1) fe->cfg.decim_ratio = 1;
+    if (fe->cfg.max_block <= 0) fe->cfg.max_block = 1000000;
+    auto bail = [&](const std::string& why) -> sdrpp_cuda_frontend* {
+        if (!why.empty()) set_last_error(why);
+        sdrpp_cuda_frontend_destroy(fe);
+        return nullptr;
+    };
+    if (cudaSetDevice(fe->device) != cudaSuccess) return bail("cudaSetDevice failed");
+    // ring: history for the longest filter + a whole spectrum frame + one block, rounded up
+    {
+        long long need = (long long)fe->cfg.max_block * 2 + std::max(fe->cfg.fft_size, 0) * 2LL + 8192;
+        int lg = 16;
+        while ((1LL << lg) < need) lg++;
+        if (fe->cfg.ring_log2 > 0) lg = fe->cfg.ring_log2;
+        if (lg < 12 || lg > 30) return bail("ring_log2 out of range");
+        fe->ring_log2 = lg;
+        fe->ring_mask = (uint32_t)((1u << lg) - 1u);
+    }
+    if (cudaStreamCreateWithFlags(&fe->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_copy, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
+    if (dev_alloc(&fe->ring, (size_t)1 << fe->ring_log2) != cudaSuccess) return bail("ring allocation failed");
+    fe->raw_cap = (size_t)fe->cfg.max_block * 8;
+    for (int i = 0; i < 2; i++) {
+        if (cudaMallocHost(&fe->h_stage[i], fe->raw_cap) != cudaSuccess) return bail("pinned staging allocation failed");
+        if (cudaMalloc(&fe->d_raw[i], fe->raw_cap) != cudaSuccess) return bail("raw buffer allocation failed");
+        if (cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+        if (cudaEventCreateWithFlags(&fe->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+        if (cudaEventCreateWithFlags(&fe->rs[i].done, cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+        cudaEventRecord(fe->ev_h2d[i], fe->st_copy);
+    }
+    for (int i = 0; i < 5; i++) if (cudaEventCreate(&fe->pev[i]) != cudaSuccess) return bail("event creation failed");
+    if (configure_preproc(fe) != SDRPP_OK) return bail("");
+    if (configure_fft(fe) != SDRPP_OK) return bail("");
+    if (cudaDeviceSynchronize() != cudaSuccess) return bail("device sync failed");
+    return fe;
+}
+
+int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
+    if (!fe) return SDRPP_OK;
+    cudaSetDevice(fe->device);
+    if (fe->st) cudaStreamSynchronize(fe->st);
+    if (fe->st_copy) cudaStreamSynchronize(fe->st_copy);
+    for (Vfo& v : fe->vfos) if (v.slab) cudaFree(v.slab);
+    for (Group& g : fe->groups) if (g.d_G) cudaFree(g.d_G);
+    fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
+    for (float* t : fe->fe_taps) cudaFree(t);
+    for (float2* b : fe->fe_buf) cudaFree(b);
+    cudaFree(fe->dc_in); cudaFree(fe->dc_state); cudaFree(fe->dc_scratch);
+    cudaFree(fe->ring); cudaFree(fe->d_window); cudaFree(fe->d_inter); cudaFree(fe->d_rows);
+    cudaFree(fe->d_vfos); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod);
+    for (int i = 0; i < 2; i++) {
+        if (fe->h_stage[i]) cudaFreeHost(fe->h_stage[i]);
+        if (fe->d_raw[i]) cudaFree(fe->d_raw[i]);
+        if (fe->ev_h2d[i]) cudaEventDestroy(fe->ev_h2d[i]);
+        if (fe->ev_consumed[i]) cudaEventDestroy(fe->ev_consumed[i]);
+        if (fe->rs[i].done) cudaEventDestroy(fe->rs[i].done);
+        if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
+        if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
+        if (fe->rs[i].rows) cudaFreeHost(fe->rs[i].rows);
+    }
+    for (int i = 0; i < 5; i++) if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
+    if (fe->st) cudaStreamDestroy(fe->st);
+    if (fe->st_copy) cudaStreamDestroy(fe->st_copy);
+    cudaGetLastError();
+    delete fe;
+    return SDRPP_OK;
+}
+
+static int fe_quiesce(sdrpp_cuda_frontend* fe) {
+    int rc = fe_check(fe);
+    if (rc != SDRPP_OK) return rc;
+    FE_TRY(fe, cudaStreamSynchronize(fe->st_copy));
+    FE_TRY(fe, cudaStreamSynchronize(fe->st));
+    return SDRPP_OK;
+}
+
+// A sample-rate / decimation change re-plans every VFO (IQFrontEnd::setSampleRate, iq_frontend.cpp:55-80)
+static int replan_all(sdrpp_cuda_frontend* fe) {
+    for (size_t id = 0; id < fe->vfos.size(); id++) {
+        Vfo& v = fe->vfos[id];
+        if (!v.alive) continue;
+        remove_from_group(fe, (int)id);
+        std::shared_ptr<VfoPlan> plan;
+        int rc = get_plan(fe, v.outSR, v.bw, &plan);
+        if (rc != SDRPP_OK) return rc;
+        v.plan = plan;
+        if (v.slab) cudaFree(v.slab);
+        v.slab = nullptr;
+        FE_TRY(fe, dev_alloc(&v.slab, plan->slab_elems));
+        set_nco(fe, v, v.offset, true);
+        join_group(fe, (int)id, fe->abs_pos);
+    }
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_set_sample_rate(sdrpp_cuda_frontend* fe, double sampleRate) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (!(sampleRate > 0)) return fail(SDRPP_ERR_ARG, "sample_rate must be positive");
+    fe->cfg.sample_rate = sampleRate;
+    fe->eff_sr = sampleRate / fe->cfg.decim_ratio;
+    if ((rc = configure_fft(fe)) != SDRPP_OK) return rc;
+    return replan_all(fe);
+}
+int sdrpp_cuda_frontend_set_decimation(sdrpp_cuda_frontend* fe, int ratio) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (ratio != 1 && (!is_pow2(ratio) || ratio > 8192)) return fail(SDRPP_ERR_ARG, "ratio must be 1 or a power of two <= 8192");
+    fe->cfg.decim_ratio = ratio;
+    if ((rc = configure_preproc(fe)) != SDRPP_OK) return rc;
+    if ((rc = configure_fft(fe)) != SDRPP_OK) return rc;
+    return replan_all(fe);
+}
+int sdrpp_cuda_frontend_set_dc_blocking(sdrpp_cuda_frontend* fe, int enabled) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    fe->cfg.dc_blocking = enabled != 0;
+    return SDRPP_OK;
+}
+int sdrpp_cuda_frontend_set_invert_iq(sdrpp_cuda_frontend* fe, int enabled) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    fe->cfg.invert_iq = enabled != 0;
+    return SDRPP_OK;
+}
+int sdrpp_cuda_frontend_set_fft_size(sdrpp_cuda_frontend* fe, int size) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    const int old = fe->cfg.fft_size;
+    fe->cfg.fft_size = size;
+    if ((rc = configure_fft(fe)) != SDRPP_OK) { fe->cfg.fft_size = old; configure_fft(fe); return rc; }
+    return SDRPP_OK;
+}
+int sdrpp_cuda_frontend_set_fft_rate(sdrpp_cuda_frontend* fe, double rate) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    const double old = fe->cfg.fft_rate;
+    fe->cfg.fft_rate = rate;
+    if ((rc = configure_fft(fe)) != SDRPP_OK) { fe->cfg.fft_rate = old; configure_fft(fe); return rc; }
+    return SDRPP_OK;
+}
+int sdrpp_cuda_frontend_set_fft_window(sdrpp_cuda_frontend* fe, int window) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    const int old = fe->cfg.fft_window;
+    fe->cfg.fft_window = window;
+    if ((rc = configure_fft(fe)) != SDRPP_OK) { fe->cfg.fft_window = old; configure_fft(fe); return rc; }
+    return SDRPP_OK;
+}
+double sdrpp_cuda_frontend_effective_samplerate(sdrpp_cuda_frontend* fe) { return fe ? fe->eff_sr : 0.0; }
+
+int sdrpp_cuda_vfo_create(sdrpp_cuda_frontend* fe, double outSR, double bandwidth, double offset, int demod) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (demod < SDRPP_DEMOD_NONE || demod > SDRPP_DEMOD_DSB) return fail(SDRPP_ERR_ARG, "unknown demod");
+    std::shared_ptr<VfoPlan> plan;
+    if ((rc = get_plan(fe, outSR, bandwidth, &plan)) != SDRPP_OK) return rc;
+    int id = -1;
+    for (size_t i = 0; i < fe->vfos.size(); i++) if (!fe->vfos[i].alive) { id = (int)i; break; }
+    if (id < 0) { fe->vfos.emplace_back(); id = (int)fe->vfos.size() - 1; }
+    Vfo& v = fe->vfos[(size_t)id];
+    v = Vfo();
+    v.alive = true; v.outSR = outSR; v.bw = bandwidth; v.demod = demod; v.plan = plan;
+    FE_TRY(fe, dev_alloc(&v.slab, plan->slab_elems));
+    set_nco(fe, v, offset, false);
+    join_group(fe, id, fe->abs_pos);
+    return id;
+}
+
+static int vfo_get(sdrpp_cuda_frontend* fe, int id, Vfo** out) {
+    if (!fe || id < 0 || id >= (int)fe->vfos.size() || !fe->vfos[(size_t)id].alive) return fail(SDRPP_ERR_STATE, "unknown VFO id");
+    *out = &fe->vfos[(size_t)id];
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_destroy(sdrpp_cuda_frontend* fe, int id) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    remove_from_group(fe, id);
+    if (v->slab) cudaFree(v->slab);
+    *v = Vfo();
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_set_offset(sdrpp_cuda_frontend* fe, int id, double offset) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    set_nco(fe, *v, offset, true);
+    fe->groups[(size_t)v->group].g_dirty = true;
+    fe->layout_dirty = true;
+    return SDRPP_OK;
+}
+
+static int vfo_replan(sdrpp_cuda_frontend* fe, int id, double outSR, double bw, bool new_epoch) {
+    Vfo* v;
+    int rc = vfo_get(fe, id, &v);
+    if (rc != SDRPP_OK) return rc;
+    std::shared_ptr<VfoPlan> plan;
+    if ((rc = get_plan(fe, outSR, bw, &plan)) != SDRPP_OK) return rc;
+    remove_from_group(fe, id);
+    v->outSR = outSR; v->bw = bw; v->plan = plan;
+    if (v->slab) cudaFree(v->slab);
+    v->slab = nullptr;
+    FE_TRY(fe, dev_alloc(&v->slab, plan->slab_elems));
+    set_nco(fe, *v, v->offset, true);
+    (void)new_epoch;
+    join_group(fe, id, fe->abs_pos);
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_set_bandwidth(sdrpp_cuda_frontend* fe, int id, double bw) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    return vfo_replan(fe, id, v->outSR, bw, false);
+}
+int sdrpp_cuda_vfo_set_out_samplerate(sdrpp_cuda_frontend* fe, int id, double outSR, double bw) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    return vfo_replan(fe, id, outSR, bw, true);
+}
+int sdrpp_cuda_vfo_reset(sdrpp_cuda_frontend* fe, int id) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    remove_from_group(fe, id);
+    FE_TRY(fe, cudaMemset(v->slab, 0, v->plan->slab_elems * sizeof(float2)));
+    // xlator.reset(): phase = 1 at the next sample (frequency_xlator.h:31-34)
+    v->phi_ref = 0; v->n_ref = fe->abs_pos;
+    join_group(fe, id, fe->abs_pos);
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_info(sdrpp_cuda_frontend* fe, int id, int* info) {
+    Vfo* v;
+    int rc = vfo_get(fe, id, &v);
+    if (rc != SDRPP_OK) return rc;
+    if (!info) return fail(SDRPP_ERR_ARG, "null info");
+    const VfoPlan& p = *v->plan;
+    info[0] = p.rp.mode; info[1] = p.rp.predec; info[2] = p.rp.interp; info[3] = p.rp.decim;
+    info[4] = (int)p.rp.taps.size(); info[5] = p.rp.tpp; info[6] = p.filter_needed ? p.chan_taps : 0;
+    info[7] = p.s1_fir ? p.s1_D : 1; info[8] = p.s1_fir ? p.s1_T : 0;
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_submit(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count) {
+    return submit_common(fe, fmt, in, count, false);
+}
+int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt, const void* dev_in, int count) {
+    return submit_common(fe, fmt, dev_in, count, true);
+}
+
+int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe) {
+    int rc = fe_check(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (fe->seq == 0) return fail(SDRPP_ERR_STATE, "nothing submitted");
+    // oldest block not yet waited for
+    if (fe->waited < fe->seq - 2) fe->waited = fe->seq - 2;
+    if (fe->waited >= fe->seq) fe->waited = fe->seq - 1;
+    const int slot = (int)(fe->waited & 1);
+    if ((rc = wait_set(fe, slot)) != SDRPP_OK) return rc;
+    fe->cur = slot;
+    fe->waited++;
+    if (fe->profiling && fe->pev_valid && fe->waited == fe->seq) {
+        for (int i = 0; i < 4; i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, fe->pev[i], fe->pev[i + 1]) == cudaSuccess) fe->kernel_ms[i] = ms;
+            else cudaGetLastError();
+        }
+    }
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    fe->readback = enabled != 0;
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int id, const sdrpp_cf32** iq, const float** demod) {
+    Vfo* v;
+    int rc = vfo_get(fe, id, &v);
+    if (rc != SDRPP_OK) return rc;
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    const ResultSet& rs = fe->rs[fe->cur];
+    const int n = (size_t)id < rs.counts.size() ? rs.counts[(size_t)id] : 0;
+    if (iq) *iq = rs.iq ? rs.iq + v->out_off : nullptr;
+    if (demod) *demod = (v->demod != SDRPP_DEMOD_NONE && rs.demod) ? rs.demod + v->out_off : nullptr;
+    return n;
+}
+
+int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows) {
+    if (!fe) return fail(SDRPP_ERR_ARG, "null front end");
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    const ResultSet& rs = fe->rs[fe->cur];
+    if (rows) *rows = rs.rows;
+    return rs.nrows;
+}
+
+int sdrpp_cuda_frontend_read_iq(sdrpp_cuda_frontend* fe, sdrpp_cf32* out, int cap) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    const int n = std::min(cap, fe->last_count);
+    if (n <= 0 || !out) return 0;
+    const uint32_t start = (uint32_t)((uint64_t)(fe->abs_pos - fe->last_count) & fe->ring_mask);
+    const uint32_t len = fe->ring_mask + 1u;
+    const uint32_t first = std::min<uint32_t>((uint32_t)n, len - start);
+    FE_TRY(fe, cudaMemcpy(out, fe->ring + start, (size_t)first * 8, cudaMemcpyDeviceToHost));
+    if (first < (uint32_t)n) FE_TRY(fe, cudaMemcpy(out + first, fe->ring, (size_t)(n - first) * 8, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+long long sdrpp_cuda_frontend_launches(sdrpp_cuda_frontend* fe) { return fe ? fe->launches : 0; }
+void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe) { return fe ? (void*)fe->st : nullptr; }
+int sdrpp_cuda_frontend_set_profiling(sdrpp_cuda_frontend* fe, int enabled) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    fe->profiling = enabled != 0;
+    fe->pev_valid = false;
+    return SDRPP_OK;
+}
+float sdrpp_cuda_frontend_kernel_ms(sdrpp_cuda_frontend* fe, int idx) {
+    if (!fe || idx < 0 || idx > 3) return 0.f;
+    return fe->kernel_ms[idx];
+}
+
+} // extern "C"

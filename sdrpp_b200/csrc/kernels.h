@@ -1,0 +1,126 @@
+// Kernel launch interfaces shared between the .cu files and the engine.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace sdrpp {
+
+// ---------------------------------------------------------------------------------------------
+// Device IQ ring: cf32 samples at (index & mask). mask = 0xFFFFFFFF addresses a linear buffer.
+// ---------------------------------------------------------------------------------------------
+struct RingRef {
+    float2* base;
+    uint32_t mask;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Ingest / pre-processing (convert.cu, preproc.cu)
+// ---------------------------------------------------------------------------------------------
+// raw samples of format fmt -> cf32 at dst[(pos+i)&mask], optional conjugate (dsp/math/conjugate.h:12-15)
+cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st);
+
+// One decimating FIR stage of the front-end PowerDecimator (dsp/filter/decimating_fir.h:45-68):
+// out[m] = sum_k buf[offset + m*D + k] * taps[k], buf = [T-1 history | count new samples] (linear).
+cudaError_t launch_decim_stage(const float2* buf, const float* taps, int T, int D, int offset, int nout,
+                               RingRef dst, uint32_t pos, bool conj, cudaStream_t st);
+// Move the last `hist` samples of buf[0 .. hist+count) to the front (history carry, fir.h:80).
+cudaError_t launch_shift_history(float2* buf, int hist, int count, cudaStream_t st);
+// DC blocker (dsp/correction/dc_blocker.h:54-60) as a chunked linear-recurrence scan.
+// state: one float2 (the offset estimate) in device memory, updated in place. scratch: >= 2*nchunks float2.
+cudaError_t launch_dc_block(const float2* in, int count, float rate, float2* state, float2* scratch,
+                            RingRef dst, uint32_t pos, bool conj, cudaStream_t st, long long* launches);
+int dc_block_chunks(int count);
+
+// ---------------------------------------------------------------------------------------------
+// Spectrum (fft.cu)
+// ---------------------------------------------------------------------------------------------
+struct SpectrumArgs {
+    const void* in;        // cf32 samples (ring or linear)
+    uint32_t ring_mask;
+    uint32_t start;        // index of the first sample of frame 0
+    uint32_t frame_stride; // samples between frame starts
+    int nz;                // windowed samples per frame (rest of the N-point input is zero)
+    const float* window;   // nz floats
+    float2* inter;         // four-step intermediate, frames*N (unused for N <= 4096)
+    float* rows;           // frames*N dB rows (may be null)
+    float2* X;             // frames*N complex spectra (may be null; parity/debug)
+    int frames;
+};
+int spectrum_split(int N, int* N1, int* N2);
+cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long long* launches);
+
+// ---------------------------------------------------------------------------------------------
+// Channelizer (channelizer.cu)
+// ---------------------------------------------------------------------------------------------
+// Per-VFO device record.
+struct VfoDev {
+    float2* slab;        // this VFO's stage buffers
+    uint64_t phi_ref;    // NCO phase (turns * 2^64) of absolute input sample n_ref
+    int64_t n_ref;
+    uint64_t dphi;       // NCO phase step per input sample (turns * 2^64), from the fp32-quantised increment
+    uint64_t dphi2;      // SSB second translation, per output sample
+    uint32_t out_off;    // offset of this VFO's rows in the output arenas (samples)
+    uint32_t pad;
+};
+
+constexpr int kStage1MT = 8;        // outputs per thread
+constexpr int kStage1Warps = 8;     // warps per CTA, each a different output sub-tile
+constexpr int kStage1TM = kStage1MT * kStage1Warps; // outputs per CTA
+constexpr int kStage1Stages = 3;    // tap-chunk pipeline depth
+
+// Stage 1 of a group of VFOs sharing one plan: NCO translation folded into the first decimating
+// FIR (dsp/channel/frequency_xlator.h:43-50 + dsp/filter/decimating_fir.h:45-68).
+struct Stage1Args {
+    RingRef ring;
+    uint32_t ring_first;   // ring index of buf[offset] for output 0 (i.e. first sample of dot product 0)
+    int64_t abs_first;     // absolute index of that sample
+    int64_t abs_valid;     // samples with absolute index < abs_valid read as zero (reset / stream start)
+    int D, T, A;           // decimation, taps, ceil(T/D)
+    int pcp;               // tap pairs per chunk
+    int M;                 // outputs this block
+    int nvfo;              // VFOs in the group
+    const float4* G;       // folded taps [vb][chunk][a][ppc][lane] (pairs of complex taps)
+    const VfoDev* vfos;    // group members, contiguous
+    uint32_t out_off;      // slab offset (in float2) where output 0 goes
+};
+bool stage1_supported(int A, int D);
+size_t stage1_g_elems(int A, int D, int nvfo);          // float4 elements of G
+void stage1_g_index(int A, int D, int pcp, int v, int k, size_t* idx4, int* half); // where tap k of VFO v lives
+int stage1_pcp(int D);
+cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st);
+// D = 1, T = 1 (no pre-decimation): pure translation.
+cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st);
+
+enum { TAIL_DECFIR = 0, TAIL_POLY = 1, TAIL_FIR = 2 };
+struct TailStage {
+    int type;
+    int T;          // taps (per phase for POLY)
+    int D;          // decimation (DECFIR), polyphase decim (POLY), 1 (FIR)
+    int interp;     // POLY
+    const float* taps; // FIR taps or polyphase bank [interp][T]
+    uint32_t in_off;   // slab offset of the data area of this stage's input; history sits just before it
+    int n_in, n_out;
+    int offset, phase; // integer state at the start of this block
+};
+constexpr int kTailMaxStages = 6;
+constexpr int kTailMaxGroups = 6;
+struct TailGroup {
+    int first_vfo, nvfo;
+    int nstages;
+    TailStage st[kTailMaxStages];
+    uint32_t final_off;  // slab offset of the final output data area (one sample of history before it)
+    int n_final;         // output samples this block
+    int demod;
+    float inv_dev;       // Quadrature: 1/(2*pi*dev/sr)
+    int64_t abs_out;     // absolute index of the first output sample of this block (SSB phase)
+};
+struct TailArgs {
+    int ngroups;
+    TailGroup g[kTailMaxGroups];
+    const VfoDev* vfos;
+    float2* arena_iq;
+    float* arena_demod;
+};
+cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st);
+
+} // namespace sdrpp
