@@ -1,0 +1,473 @@
+#!/usr/bin/env python3
+"""bench.py -- sustained input MS/s of the SDR++ signal-path hot loop on B200.
+
+Workload (BASELINE.json configs[4] + the 1M-point spectrum the metric is quoted on): 122.88 MS/s
+complex64 IQ in blocks of 614,400 samples (sr/200), a saturated 1,048,576-point Blackman-Harris-4
+spectrum (every sample enters one frame) and 512 VFOs alternating NFM (12.5 kHz -> 48 kS/s,
+quadrature demod) and AM (12 kHz -> 24 kS/s, magnitude). A "step" is one IQ block through
+conversion/ingest -> spectrum frames -> 512-VFO channelizer -> demod front ends.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun, one rank per GPU): the VFO set is sharded across ranks, every step the block is
+broadcast from rank 0 over NCCL (NVLink) and the spectrum stays on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SR = 122.88e6
+BLOCK = 614400
+FFT_N = 1 << 20
+NVFO = 512
+NFM = (48e3, 12.5e3, 1)   # outSR, bw, demod (quadrature)
+AM = (24e3, 12e3, 2)      # outSR, bw, demod (magnitude)
+WORKLOAD = ("122.88 MS/s cf32 IQ, blocks of 614400; saturated 1048576-pt Blackman-Harris-4 spectrum; "
+            "512 VFOs alternating NFM 12.5k->48k (quadrature) / AM 12k->24k (magnitude)")
+METRIC = "sustained input MS/s (1M-pt FFT + N-VFO channelizer); % of B200 HBM roofline"
+
+
+def vfo_list():
+    from sdrpp_b200 import synth
+    offs = synth.vfo_grid(NVFO, SR)
+    return [((NFM if i % 2 == 0 else AM)[0], (NFM if i % 2 == 0 else AM)[1], float(offs[i]), (NFM if i % 2 == 0 else AM)[2])
+            for i in range(NVFO)]
+
+
+def make_blocks(nblocks, seed=5):
+    """Synthetic IQ: a few tones/carriers + white noise at -40 dBFS, complex64, nblocks x BLOCK."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = nblocks * BLOCK
+    out = np.empty(n, dtype=np.complex64)
+    offs = [v[2] for v in vfo_list()[::64]]
+    chunk = 1 << 20
+    sigma = np.float32(10.0 ** (-40.0 / 20.0) / np.sqrt(2.0))
+    for s in range(0, n, chunk):
+        m = min(chunk, n - s)
+        t = (np.arange(s, s + m, dtype=np.float64)) / SR
+        x = np.zeros(m, dtype=np.complex64)
+        for i, f in enumerate(offs):
+            ph = (2.0 * np.pi) * ((f * t) % 1.0)
+            x += np.float32(0.05) * (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64)
+        x += sigma * (rng.standard_normal(m, dtype=np.float32) + 1j * rng.standard_normal(m, dtype=np.float32))
+        out[s:s + m] = x
+    return out.reshape(nblocks, BLOCK)
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work per input sample
+# ---------------------------------------------------------------------------------------------
+def algorithmic_model(vfos):
+    from sdrpp_b200 import cuda
+    flops = 0.0
+    out_bytes = 0.0
+    s1_flops = 0.0
+    for (osr, bw, _off, demod) in vfos:
+        info, _ = cuda.design_resampler(SR, osr)
+        f = 8.0  # NCO complex multiply + phase advance per input sample
+        rate = 1.0
+        stages = cuda.design_decim_plan(info["predec"]) if info["mode"] in (0, 1) else []
+        for i, (d, taps) in enumerate(stages):
+            c = 4.0 * len(taps) * rate / d   # 2 mul + 2 add per tap per output
+            f += c
+            if i == 0:
+                s1_flops += 8.0 + c
+            rate /= d
+        if info["mode"] in (0, 2):
+            f += 4.0 * info["tpp"] * (osr / SR)
+        if bw != osr:
+            f += 4.0 * int(3.8 * osr / (bw / 20.0)) * (osr / SR)
+        flops += f
+        out_bytes += (osr / SR) * (8 + (4 if demod else 0))
+    return dict(flops_per_sample=flops, stage1_flops_per_sample=s1_flops, chan_bytes_per_sample=8.0 + out_bytes,
+                fft_bytes_per_sample=12.0, fft_flops_per_sample=5.0 * 20 + 12)
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm / baseline: the reference's own dsp/ headers (oracle/_ref, release flags)
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(nblocks=2, sample_vfos=None, fft_frames=1):
+    """Times the reference's CPU implementation of the path on a bounded sample of the workload:
+    `sample_vfos` of the 512 VFOs (thread-per-VFO multiplexed on all host cores, as
+    ref_bench_channelizer does) on nblocks blocks plus fft_frames 1M-point spectrum lines, scaled to
+    the full VFO count. Returns (MS/s, info dict)."""
+    from oracle import pyoracle as po
+    cores = os.cpu_count() or 1
+    kind = "reference"
+    if po.have_ref("fast"):
+        lib = po.Ref("fast")
+    elif po.have_ref(""):
+        lib = po.Ref("")
+    else:
+        lib = None
+    vf = vfo_list()
+    if sample_vfos is None:
+        sample_vfos = min(NVFO, 2 * cores)
+    pick = [vf[(i * NVFO) // sample_vfos] for i in range(sample_vfos)]
+    blocks = make_blocks(2, seed=5).reshape(-1)  # 1,228,800 samples >= one spectrum frame
+    if lib is not None:
+        win = lib.window(po.WIN_BH4, FFT_N)
+        # the block handed to every VFO thread is the first BLOCK samples; the spectrum thread reads FFT_N
+        buf = np.ascontiguousarray(blocks[:max(BLOCK, FFT_N)])
+        # ref_bench_channelizer(count=len(block)): pass exactly BLOCK for the VFOs by timing the two legs apart
+        t_ch = lib.bench_channelizer(SR, pick, buf[:BLOCK], nblocks, cores)
+        t_fft = lib.bench_channelizer(SR, pick[:1], buf, 0, 1, fft=(FFT_N, win, fft_frames))
+    else:
+        kind = "port"
+        port = po.Port()
+        t0 = time.perf_counter()
+        for v in pick:
+            o = port.rxvfo(SR, v[0], v[1], v[2])
+            for _ in range(nblocks):
+                o.process(blocks[:BLOCK])
+        t_ch = time.perf_counter() - t0
+        cores_used = 1
+        t0 = time.perf_counter()
+        win = port.window(po.WIN_BH4, FFT_N)
+        for _ in range(fft_frames):
+            port.spectrum(FFT_N, blocks[:FFT_N], win, want64=False)
+        t_fft = time.perf_counter() - t0
+        cores = cores_used
+    # the channelizer workers and the spectrum thread run concurrently in the reference; the stream
+    # advances at the pace of the slower consumer
+    sec_per_sample_ch = (t_ch * (NVFO / float(sample_vfos))) / (nblocks * BLOCK)
+    sec_per_sample_fft = t_fft / (fft_frames * FFT_N)
+    msps = 1e-6 / max(sec_per_sample_ch, sec_per_sample_fft)
+    info = dict(kind=kind, cores=cores,
+                sample=f"{sample_vfos} of {NVFO} VFOs x {nblocks} blocks of {BLOCK} (scaled x{NVFO / sample_vfos:g}) on {cores} threads "
+                       f"+ {fft_frames} x 1M-pt spectrum line on 1 thread; generic-VOLK shim, -O3 -ffast-math",
+                channelizer_msps=1e-6 / sec_per_sample_ch, spectrum_msps=1e-6 / sec_per_sample_fft,
+                seconds=t_ch + t_fft)
+    return msps, info
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    vals, info = [], None
+    for i in range(args.warmup + args.steps):
+        v, info = cpu_reference(nblocks=1)
+        if i >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * BLOCK / (value * 1e6), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "block": BLOCK, "vfos": NVFO, "fft": FFT_N},
+        "cpu_baseline": {"value": value, "unit": "MS/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sdrpp_b200 import cuda
+    from oracle import pyoracle as po  # only for the cpu_baseline leg below (rank 0, N = 1)
+
+    if cuda.device_count() <= 0:
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    cuda.init(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    vf_all = vfo_list()
+    # shard VFOs round-robin (NFM/AM alternate, so every rank gets the same mix = balanced cost)
+    mine = [v for i, v in enumerate(vf_all) if (i // 2) % world == rank] if world > 1 else vf_all
+    with_fft = (rank == 0)
+    fe = cuda.Frontend(SR, fft_size=FFT_N if with_fft else 0, fft_rate=SR / FFT_N, fft_window=cuda.WIN_BH4, max_block=BLOCK)
+    ids = [fe.add_vfo(*v) for v in mine]
+    st = torch.cuda.ExternalStream(fe.stream, device=dev)
+
+    NB = args.input_blocks
+    host = make_blocks(NB) if rank == 0 else None
+    d_blocks = torch.empty((NB, BLOCK, 2), dtype=torch.float32, device=dev)  # > L2 (126 MB) when NB >= 32
+    if rank == 0:
+        d_blocks.copy_(torch.from_numpy(host.view(np.float32).reshape(NB, BLOCK, 2)))
+    if world > 1:
+        d_stage = [torch.empty((BLOCK, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+    torch.cuda.synchronize()
+
+    def step_device(i):
+        blk = d_blocks[i % NB]
+        if world > 1:
+            # NVLink broadcast of the IQ block from the ingest GPU, then every rank channelizes its VFOs
+            buf = d_stage[i % 2]
+            if rank == 0:
+                buf.copy_(blk, non_blocking=True)
+            dist.broadcast(buf, src=0)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            st.wait_event(ev)
+            fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
+            # the staging buffer is reused two steps later: make torch's stream wait for the front end
+            ev2 = torch.cuda.Event()
+            ev2.record(st)
+            torch.cuda.current_stream().wait_event(ev2)
+        else:
+            fe.submit_device(cuda.FMT_CF32, blk.data_ptr(), BLOCK)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) ------------------------------------------------------------
+    fe.set_readback(False)
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = fe.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    e1.record(st)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = fe.launches - l0
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt.item())
+    value = args.steps * BLOCK / (ms * 1e-3) / 1e6
+
+    # ---- per-kernel-family device time (CUDA events on the front end's stream, inside the library) ----
+    fe.set_profiling(True)
+    fam = np.zeros(4)
+    nprof = max(4, min(args.steps, 16))
+    for i in range(nprof):
+        step_device(i)
+        fe.wait()
+        fam += np.array(fe.kernel_ms())
+    fam /= nprof
+    fe.set_profiling(False)
+
+    # ---- end to end through the host API (e2e): pinned host block -> H2D -> path -> D2H results --------
+    fe.set_readback(True)
+    e2e = None
+    if world == 1:
+        pin = [cuda.PinnedArray((BLOCK,), np.complex64) for _ in range(4)]
+        for j, p in enumerate(pin):
+            p.array[:] = host[j % NB]
+        touched = 0.0
+
+        def step_host(i):
+            fe.submit(cuda.FMT_CF32, pin[i % len(pin)], BLOCK)
+
+        def consume():
+            nonlocal touched
+            fe.wait()
+            iq, dm = fe.vfo_output(ids[0], copy=False)
+            rows = fe.fft_rows(copy=False)
+            touched += float(iq[0].real) if len(iq) else 0.0
+            touched += float(rows[0, 0]) if len(rows) else 0.0
+
+        for i in range(args.warmup):
+            step_host(i); consume()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        step_host(0)
+        for i in range(1, args.steps):
+            step_host(i)      # block i is copied in while block i-1 is still computing
+            consume()         # results of block i-1
+        consume()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        d2h = 0
+        for vid, v in zip(ids, mine):
+            n = len(fe.vfo_output(vid, copy=False)[0])
+            d2h += n * (8 + 4)
+        d2h += int(FFT_N * 4 * BLOCK / FFT_N)
+        e2e = {"value": args.steps * BLOCK / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
+               "note": "pinned host block -> cudaMemcpyAsync H2D -> full path -> D2H of all VFO outputs + spectrum rows; wall clock"}
+        for p in pin:
+            p.free()
+    else:
+        # multi-GPU: the host edge is rank 0's; report the same sharded run fed from pinned host memory on rank 0
+        pin = cuda.PinnedArray((BLOCK,), np.complex64) if rank == 0 else None
+        if rank == 0:
+            pin.array[:] = host[0]
+            pin_t = torch.from_numpy(pin.array.view(np.float32).reshape(BLOCK, 2))
+
+        def step_e2e(i):
+            buf = d_stage[i % 2]
+            if rank == 0:
+                buf.copy_(pin_t, non_blocking=True)
+            dist.broadcast(buf, src=0)
+            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream()); st.wait_event(ev)
+            fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
+            fe.wait()
+            ev2 = torch.cuda.Event(); ev2.record(st); torch.cuda.current_stream().wait_event(ev2)
+
+        for i in range(args.warmup):
+            step_e2e(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step_e2e(i)
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        d2h = sum(len(fe.vfo_output(vid, copy=False)[0]) * 12 for vid in ids)
+        dd = torch.tensor([d2h], dtype=torch.int64, device=dev)
+        dist.all_reduce(dd, op=dist.ReduceOp.SUM)
+        e2e = {"value": args.steps * BLOCK / float(t.item()) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": BLOCK * 8,
+               "d2h_bytes_per_step": int(dd.item()) + int(FFT_N * 4 * BLOCK / FFT_N),
+               "note": "rank 0 pinned host block -> H2D -> NCCL broadcast -> sharded path -> per-rank D2H; wall clock, max over ranks"}
+
+    # ---- roofline + baseline objects (rank 0) -------------------------------------------------------------
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        model = algorithmic_model(mine)
+        s1_ms, fft_ms, tail_ms, ingest_ms = fam[2], fam[1], fam[3], fam[0]
+        chan_bytes = model["chan_bytes_per_sample"] * BLOCK
+        roof = {"bound": "hbm", "kernel": "stage1_kernel (NCO folded into the first decimating FIR; both VFO-class launches of a step)",
+                "achieved": chan_bytes / (s1_ms * 1e-3) / 1e9 if s1_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                "frac": (chan_bytes / (s1_ms * 1e-3) / 1e9 / hbm_peak) if s1_ms > 0 else None, "traffic": None,
+                "peak_source": peak_src, "ms_per_step": float(s1_ms),
+                "algorithmic_bytes_per_step": chan_bytes,
+                "note": "minimal-bytes accounting (8 B/sample in + outputs, SURVEY 8d); this kernel is FP32-FMA-bound, see fp32"}
+        sm_clk = (clk or {}).get("sm_mhz") or 1965.0
+        fma_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
+        s1_flops = model["stage1_flops_per_sample"] * BLOCK
+        roof["fp32"] = {"achieved": s1_flops / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None, "peak": fma_peak, "unit": "TFLOP/s",
+                        "frac": (s1_flops / (s1_ms * 1e-3) / 1e12 / fma_peak) if s1_ms > 0 else None,
+                        "peak_source": f"148 SM x 128 FMA lanes x 2 x {sm_clk:.0f} MHz (median SM clock sampled under load)",
+                        "algorithmic_flops_per_sample": model["stage1_flops_per_sample"]}
+        fft_bytes = 12.0 * BLOCK
+        roof_fft = {"bound": "hbm", "kernel": "fft_cols_kernel + fft_rows_kernel (window + 1M-pt FFT + dB row)",
+                    "achieved": fft_bytes / (fft_ms * 1e-3) / 1e9 if fft_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": (fft_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak) if fft_ms > 0 else None, "traffic": None,
+                    "ms_per_step": float(fft_ms), "algorithmic_bytes_per_step": fft_bytes,
+                    "msps": BLOCK / (fft_ms * 1e-3) / 1e6 if fft_ms > 0 else None}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, info = cpu_reference(nblocks=2)
+            cpu = {"value": v, "unit": "MS/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                   "channelizer_msps": info["channelizer_msps"], "spectrum_msps": info["spectrum_msps"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "block": BLOCK, "vfos": NVFO, "fft": FFT_N, "vfos_per_gpu": len(mine),
+                       "l2": f"inputs cycle through {NB} distinct blocks = {NB * BLOCK * 8 / 1e6:.0f} MB (> 126 MB L2)",
+                       "parallelism": f"vfo-shard x{world} + NCCL broadcast" if world > 1 else "1 GPU"},
+            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roof, "roofline_spectrum": roof_fft,
+            "kernel_ms_per_step": {"ingest": float(ingest_ms), "spectrum": float(fft_ms), "channelizer_stage1": float(s1_ms), "channelizer_tail": float(tail_ms)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    fe.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--input-blocks", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -46,7 +46,8 @@ class _Obj:
     def process(self, x, out_cap=None):
         x = _c64(x)
         n = len(x)
-        out = np.zeros(max(out_cap or n, n, 1) + 16, dtype=self._odt)
+        # room for interpolating resamplers (outSR > inSR): the reference writes count*interp/decim samples
+        out = np.zeros(max(out_cap or 0, 4 * n, 1) + 64, dtype=self._odt)
         fn = getattr(self._lib, f"{self._p}_process")
         fn.restype = _i
         fn.argtypes = [_vp, _i, _vp, _vp]

@@ -1,0 +1,218 @@
+"""GPU parity: the multi-VFO channelizer + demod front ends against the oracle.
+
+Protocol: integer index arithmetic (per-block output counts) is exact;
+everything after the NCO is checked stage-isolated with offset 0 (NCO = identity) to <= 1e-5
+relative RMS; NCO-containing outputs are checked (a) directly over a short window after reset and
+(b) per block after fitting one complex scalar (the slow fp32 phase walk of the reference
+rotator factors out of the linear stages)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from sdrpp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+# (inSR, outSR, bw, block) -- SURVEY App. B rows
+PLANS = [
+    (2.4e6, 250e3, 200e3, 12000),
+    (2.4e6, 240e3, 200e3, 12000),
+    (3.2e6, 48e3, 12.5e3, 7936),
+    (20e6, 250e3, 200e3, 100000),
+    (15.36e6, 48e3, 2.7e3, 76800),
+    (15.36e6, 24e3, 12e3, 76800),
+    (122.88e6, 48e3, 12.5e3, 614400),
+    (122.88e6, 24e3, 12e3, 614400),
+]
+
+
+def run_gpu(gpu, sr, vfos, blocks, fmt=po.FMT_CF32, max_block=None, **kw):
+    """vfos: list of (outSR, bw, offset, demod). Returns per VFO lists of per-block (iq, demod)."""
+    mb = max_block or max(len(b) if fmt == po.FMT_CF32 else len(b) // 2 for b in blocks)
+    out = [[] for _ in vfos]
+    with gpu.Frontend(sr, max_block=mb, **kw) as fe:
+        ids = [fe.add_vfo(*v) for v in vfos]
+        for b in blocks:
+            fe.process(fmt, b)
+            for i, vid in enumerate(ids):
+                out[i].append(fe.vfo_output(vid))
+    return out
+
+
+def run_oracle(orc, sr, vfo, blocks):
+    o = orc.rxvfo(sr, vfo[0], vfo[1], vfo[2])
+    d = orc.demod(vfo[3], vfo[1], vfo[0])
+    res = []
+    for b in blocks:
+        y = o.process(b)
+        res.append((y, d.process(y) if d is not None and len(y) else (np.zeros(0, np.float32) if d is not None else None)))
+    return res
+
+
+@pytest.mark.parametrize("inSR,outSR,bw,blk", PLANS)
+def test_stage_isolated_offset0(gpu, port, inSR, outSR, bw, blk):
+    nblocks = 3
+    x = synth.baseband(blk * nblocks, inSR, 7, carriers=[(0.0, "fm"), (bw, "am")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    g = run_gpu(gpu, inSR, [(outSR, bw, 0.0, po.DEMOD_NONE)], blocks)[0]
+    r = run_oracle(port, inSR, (outSR, bw, 0.0, po.DEMOD_NONE), blocks)
+    for b in range(nblocks):
+        assert len(g[b][0]) == len(r[b][0]), f"block {b}: count {len(g[b][0])} != {len(r[b][0])}"
+    ga = np.concatenate([a for a, _ in g]); ra = np.concatenate([a for a, _ in r])
+    err = po.rel_rms(ga, ra)
+    assert err <= TOL, f"rel-RMS {err:.3e}"
+
+
+@pytest.mark.parametrize("inSR,outSR,bw,blk", PLANS)
+def test_plan_info_matches_oracle(gpu, port, inSR, outSR, bw, blk):
+    with gpu.Frontend(inSR, max_block=blk) as fe:
+        vid = fe.add_vfo(outSR, bw, 1000.0)
+        gi = fe.vfo_info(vid)
+    oi = port.rxvfo(inSR, outSR, bw, 1000.0).info()
+    for k in ("mode", "predec", "interp", "decim", "rtaps", "tpp", "ftaps"):
+        assert gi[k] == oi[k], (k, gi, oi)
+
+
+@pytest.mark.parametrize("inSR,outSR,bw,blk", PLANS[:4] + PLANS[6:7])
+def test_with_nco_short_window_and_aligned(gpu, port, inSR, outSR, bw, blk):
+    off = 0.2137 * inSR / 2.4
+    nblocks = 4
+    x = synth.baseband(blk * nblocks, inSR, 8, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    g = run_gpu(gpu, inSR, [(outSR, bw, off, po.DEMOD_NONE)], blocks)[0]
+    r = run_oracle(port, inSR, (outSR, bw, off, po.DEMOD_NONE), blocks)
+    # (a) direct comparison over the first <= 4096 input samples after reset
+    n_short = max(8, int(4096 * outSR / inSR))
+    ga = np.concatenate([a for a, _ in g]); ra = np.concatenate([a for a, _ in r])
+    assert len(ga) == len(ra)
+    e0 = po.rel_rms(ga[:n_short], ra[:n_short]) if np.any(ra[:n_short]) else 0.0
+    assert e0 <= 3e-5, f"short-window rel-RMS {e0:.3e}"
+    # (b) per block, after fitting one complex scalar
+    for b in range(nblocks):
+        if len(r[b][0]) < 8:
+            continue
+        res, c = po.aligned_rel_rms(g[b][0], r[b][0])
+        assert res <= 3e-5, f"block {b}: aligned residual {res:.3e} (c={c})"
+        assert abs(abs(c) - 1.0) < 1e-3 and abs(np.angle(c)) < 2e-2
+
+
+def test_counts_ragged_blocks(gpu, port):
+    """Odd and tiny block sizes: output counts and values follow the reference's carried offsets."""
+    inSR, outSR, bw = 3.2e6, 48e3, 12.5e3
+    sizes = [7936, 1, 7, 513, 7935, 64, 7936, 1000, 3, 7936]
+    x = synth.baseband(sum(sizes), inSR, 9, noise_dbfs=-30.0).astype(np.complex64)
+    blocks, p = [], 0
+    for s in sizes:
+        blocks.append(x[p:p + s]); p += s
+    g = run_gpu(gpu, inSR, [(outSR, bw, 0.0, po.DEMOD_NONE)], blocks, max_block=8000)[0]
+    r = run_oracle(port, inSR, (outSR, bw, 0.0, po.DEMOD_NONE), blocks)
+    assert [len(a) for a, _ in g] == [len(a) for a, _ in r]
+    err = po.rel_rms(np.concatenate([a for a, _ in g]), np.concatenate([a for a, _ in r]))
+    assert err <= TOL
+
+
+@pytest.mark.parametrize("demod,outSR,bw", [(po.DEMOD_QUAD, 250e3, 200e3), (po.DEMOD_QUAD, 48e3, 12.5e3),
+                                            (po.DEMOD_AM, 24e3, 12e3), (po.DEMOD_USB, 48e3, 2.7e3),
+                                            (po.DEMOD_LSB, 48e3, 2.7e3), (po.DEMOD_DSB, 48e3, 4.6e3)])
+def test_demod_front_ends(gpu, port, demod, outSR, bw):
+    inSR, blk, nblocks = 2.4e6, 12000, 6
+    kind = {po.DEMOD_QUAD: "fm", po.DEMOD_AM: "am"}.get(demod, "cw")
+    x = synth.baseband(blk * nblocks, inSR, 10, carriers=[(0.0 if kind != "cw" else 700.0, kind)], tones=0, noise_dbfs=-60.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    g = run_gpu(gpu, inSR, [(outSR, bw, 0.0, demod)], blocks)[0]
+    r = run_oracle(port, inSR, (outSR, bw, 0.0, demod), blocks)
+    gd = np.concatenate([d for _, d in g]); rd = np.concatenate([d for _, d in r])
+    assert len(gd) == len(rd) and len(gd) > 100
+    # skip the filter transient (and the first Quadrature sample)
+    s = len(gd) // 3
+    if demod == po.DEMOD_QUAD:
+        # compare as phase increments: atan2 is ill-conditioned only where |y| ~ 0 (not here)
+        err = np.sqrt(np.mean((gd[s:] - rd[s:]) ** 2)) / max(np.sqrt(np.mean(rd[s:] ** 2)), 1e-3)
+        assert err <= 2e-4, f"quadrature rel err {err:.3e}"
+    else:
+        err = po.rel_rms(gd[s:], rd[s:])
+        assert err <= 3e-5, f"demod {demod} rel-RMS {err:.3e}"
+
+
+def test_many_vfos_two_classes(gpu, port):
+    """70 VFOs (NFM/AM alternating) share one IQ block; spot-check members against the oracle."""
+    inSR, blk, nblocks = 20e6, 100000, 2
+    offs = synth.vfo_grid(70, inSR)
+    vfos = []
+    for i, o in enumerate(offs):
+        vfos.append((48e3, 12.5e3, float(o), po.DEMOD_QUAD) if i % 2 == 0 else (24e3, 12e3, float(o), po.DEMOD_AM))
+    x = synth.baseband(blk * nblocks, inSR, 11, carriers=[(float(offs[i]), "fm" if i % 2 == 0 else "am") for i in (0, 1, 33, 34, 68, 69)],
+                       noise_dbfs=-50.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    x_rms = float(np.sqrt(np.mean(np.abs(x) ** 2)))
+    g = run_gpu(gpu, inSR, vfos, blocks)
+    for i in (0, 1, 31, 32, 33, 34, 63, 64, 68, 69):
+        r = run_oracle(port, inSR, vfos[i], blocks)
+        for b in range(nblocks):
+            assert len(g[i][b][0]) == len(r[b][0])
+            res, c = po.aligned_rel_rms(g[i][b][0], r[b][0])
+            # Channels without a carrier hold only noise ~-80 dBFS while the reference rotator's own fp32
+            # rounding is relative to the full-band signal (~-6 dBFS): gate those on absolute error.
+            ref_rms = float(np.sqrt(np.mean(np.abs(r[b][0]) ** 2)))
+            assert res * ref_rms <= 3e-5 * ref_rms + 3e-7 * x_rms, f"vfo {i} block {b}: {res:.3e}"
+
+
+def test_retune_reset_add_remove(gpu, port):
+    inSR, outSR, bw, blk = 2.4e6, 240e3, 200e3, 12000
+    x = synth.baseband(blk * 6, inSR, 12, carriers=[(100e3, "fm"), (-300e3, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(6)]
+    with gpu.Frontend(inSR, max_block=blk) as fe:
+        a = fe.add_vfo(outSR, bw, 100e3)
+        oa = port.rxvfo(inSR, outSR, bw, 100e3)
+        ob = None
+        for b in range(6):
+            if b == 2:
+                fe.vfo_set_offset(a, -300e3); oa.set_offset(-300e3)
+                vb = fe.add_vfo(outSR, bw, 100e3); ob = port.rxvfo(inSR, outSR, bw, 100e3)
+            if b == 4:
+                fe.vfo_reset(a); oa.reset()
+                fe.remove_vfo(vb); ob = None
+            fe.process(po.FMT_CF32, blocks[b])
+            ya, _ = fe.vfo_output(a)
+            ra = oa.process(blocks[b])
+            assert len(ya) == len(ra)
+            # Known deviation: in the retune block the folded taps apply the NEW frequency to the T-1
+            # history samples of stage 1 (26 input samples), a transient that rings through the later
+            # filters; compare after it has died out.
+            s = 500 if b == 2 else 0
+            res, _ = po.aligned_rel_rms(ya[s:], ra[s:])
+            assert res <= 3e-5, f"vfo a block {b}: {res:.3e}"
+            if ob is not None:
+                yb, _ = fe.vfo_output(vb)
+                rb = ob.process(blocks[b])
+                assert len(yb) == len(rb)
+                res, _ = po.aligned_rel_rms(yb, rb)
+                assert res <= 3e-5, f"vfo b block {b}: {res:.3e}"
+
+
+def test_frontend_decimation_int16_dc_conj(gpu, port):
+    """cfg4-style front end: int16 -> PowerDecimator x4 -> (DC block) -> (conjugate) -> VFO."""
+    sr, blk, nblocks = 61.44e6, 30720, 4
+    xq = [synth.quantise(synth.baseband(blk, sr, 13 + i, n0=i * blk, noise_dbfs=-40.0) + 0.05, po.FMT_I16_FILE) for i in range(nblocks)]
+    for dc, inv in [(False, False), (True, True)]:
+        with gpu.Frontend(sr, decim_ratio=4, dc_blocking=dc, invert_iq=inv, max_block=blk) as fe:
+            assert fe.effective_samplerate == sr / 4
+            vid = fe.add_vfo(48e3, 2.7e3, 0.0)
+            pd = port.powerdecim(4); dcb = port.dcblock(50.0 / (sr / 4)); vf = port.rxvfo(sr / 4, 48e3, 2.7e3, 0.0)
+            for b in range(nblocks):
+                fe.process(po.FMT_I16_FILE, xq[b])
+                y = pd.process(port.convert(po.FMT_I16_FILE, xq[b]))
+                if dc:
+                    y = dcb.process(y)
+                if inv:
+                    y = port.conjugate(y)
+                iq = fe.read_iq(len(y) + 8)
+                assert len(iq) == len(y)
+                assert po.rel_rms(iq, y) <= TOL, f"front end block {b} dc={dc}"
+                g, _ = fe.vfo_output(vid)
+                r = vf.process(y)
+                assert len(g) == len(r)
+                if b > 1 and len(r):
+                    assert po.rel_rms(g, r) <= 3e-5

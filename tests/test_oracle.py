@@ -1,0 +1,143 @@
+"""Pins the oracle. The reference has no tests or golden vectors for this path, so
+the plain-C port (oracle/port/oracle.c) is pinned (a) bit-exactly against the reference's own dsp/
+headers compiled in oracle/_ref (when present: this container) and (b) against golden vectors
+generated from that build and committed under tests/golden/ (tools/make_golden.py), which is what
+travels to the GPU box. Known answers from SURVEY 8c are checked too."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from sdrpp_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _noise(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64) * np.float32(0.25)
+
+
+# ---- known answers ---------------------------------------------------------------------
+def test_conversion_known_answers(port):
+    t = port.convert(po.FMT_U8_RTL, np.repeat(np.arange(256, dtype=np.uint8), 2)).view(np.float32)[0::2]
+    assert t[0] == np.float32(-1.0) and t[255] == np.float32(1.0) and t[128] == np.float32(0.00392156886)
+    assert po.fnv1a_words(t) == 0xb8121cc5
+    t16 = port.convert(po.FMT_I16_FILE, np.repeat(np.arange(-32768, 32768, dtype=np.int32).astype(np.int16), 2)).view(np.float32)[0::2]
+    assert po.fnv1a_words(t16) == 0x4fdefa45
+
+
+def test_unity_gain_tone(port):
+    N, k = 65536, 321
+    x = np.exp(2j * np.pi * k * np.arange(N) / N).astype(np.complex64)
+    row32, _, row64 = port.spectrum(N, x, port.window(po.WIN_BH7, N))
+    assert int(np.argmax(row64)) == N // 2 + k and abs(row64[N // 2 + k]) < 1e-3 and abs(row32[N // 2 + k]) < 2e-3
+
+
+def test_rxvfo_known_answer(port):
+    n = np.arange(12000)
+    x = np.exp(2j * np.pi * 100e3 * n / 2.4e6).astype(np.complex64)
+    v = port.rxvfo(2.4e6, 240e3, 200e3, 100e3)
+    y = v.process(x)
+    assert len(y) == 1200
+    assert abs(y[-1].real - 0.996594) < 2e-4 and abs(y[-1].imag) < 1e-4
+    q = port.quadrature(100e3, 240e3).process(y)
+    assert abs(q[-1]) < 1e-4
+
+
+def test_block_counts(port):
+    v = port.rxvfo(3.2e6, 48e3, 12.5e3, 0.0)
+    counts = [len(v.process(_noise(7936, i))) for i in range(40)]
+    assert counts[:3] == [120, 119, 119] and sum(counts) == 4762
+
+
+# ---- port vs the compiled reference (this container only) -----------------------------------------------
+@pytest.mark.parametrize("cfg", [(2.4e6, 250e3, 200e3, 100e3, 12000), (3.2e6, 48e3, 12.5e3, -400e3, 7936),
+                                 (20e6, 240e3, 200e3, 3.1e6, 100000), (15.36e6, 48e3, 2.7e3, 1e6, 76800), (48e3, 96e3, 96e3, 1e3, 480)])
+def test_port_matches_reference_rxvfo(port, ref, cfg):
+    inSR, outSR, bw, off, blk = cfg
+    a, b = port.rxvfo(inSR, outSR, bw, off), ref.rxvfo(inSR, outSR, bw, off)
+    assert a.info() == b.info()
+    for i in range(3):
+        x = _noise(blk if i != 1 else blk - 37, 100 + i)
+        ya, yb = a.process(x), b.process(x)
+        assert len(ya) == len(yb) and np.array_equal(_bits(ya), _bits(yb))
+
+
+def test_port_matches_reference_pieces(port, ref):
+    x = _noise(30000, 1)
+    for ratio in (2, 4, 64, 2048):
+        a, b = port.powerdecim(ratio), ref.powerdecim(ratio)
+        for i in range(3):
+            xs = x[i * 9001:(i + 1) * 9001]
+            assert np.array_equal(_bits(a.process(xs)), _bits(b.process(xs)))
+            assert a.offsets() == b.offsets()
+    taps = port.lowpass_taps(12e3, 1.2e3, 5 * 48e3) * np.float32(5)
+    a, b = port.polyphase(5, 6, taps), ref.polyphase(5, 6, taps)
+    for i in range(3):
+        xs = x[i * 777:(i + 1) * 777 + i]
+        assert np.array_equal(_bits(a.process(xs)), _bits(b.process(xs))) and a.state() == b.state()
+    a, b = port.dcblock(50.0 / 2.4e6), ref.dcblock(50.0 / 2.4e6)
+    assert np.array_equal(_bits(a.process(x + 0.1)), _bits(b.process(x + 0.1)))
+    for dem in (po.DEMOD_QUAD, po.DEMOD_AM, po.DEMOD_USB, po.DEMOD_LSB):
+        a, b = port.demod(dem, 12.5e3, 48e3), ref.demod(dem, 12.5e3, 48e3)
+        assert np.array_equal(_bits(a.process(x[:4000])), _bits(b.process(x[:4000])))
+    w = port.window(po.WIN_BH4, 4096)
+    ra, rb = port.spectrum(4096, x, w), ref.spectrum(4096, x, w)
+    assert np.array_equal(_bits(ra[0]), _bits(rb[0])) and np.array_equal(ra[1], rb[1])
+
+
+# ---- golden vectors generated from the compiled reference (travel to the GPU box) -----------------------------
+def _golden_cases():
+    p = os.path.join(GOLD, "manifest.json")
+    return json.load(open(p))["cases"] if os.path.exists(p) else []
+
+
+@pytest.mark.parametrize("case", _golden_cases(), ids=lambda c: c["name"])
+def test_port_matches_golden(port, case):
+    data = np.load(os.path.join(GOLD, case["file"]))
+    kind = case["kind"]
+    if kind == "rxvfo":
+        inSR, outSR, bw, off, demod = case["args"]
+        x = synth.baseband(case["n"], inSR, case["seed"], carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+        v = port.rxvfo(inSR, outSR, bw, off)
+        d = port.demod(demod, bw, outSR)
+        ys, ds, p = [], [], 0
+        for s in case["blocks"]:
+            y = v.process(x[p:p + s]); p += s
+            ys.append(y)
+            if d is not None:
+                ds.append(d.process(y))
+        assert [len(y) for y in ys] == case["counts"]
+        assert np.array_equal(_bits(np.concatenate(ys)), _bits(data["iq"]))
+        if d is not None:
+            assert np.array_equal(_bits(np.concatenate(ds)), _bits(data["demod"]))
+    elif kind == "spectrum":
+        N, nz, wtype = case["args"]
+        x = synth.baseband(nz, 2.4e6, case["seed"], noise_dbfs=-40.0).astype(np.complex64)
+        w = port.window(wtype, nz)
+        assert np.array_equal(_bits(w), _bits(data["window"]))
+        row32, _, row64 = port.spectrum(N, x, w)
+        assert np.array_equal(_bits(row32), _bits(data["row32"]))
+        assert np.allclose(row64, data["row64"], rtol=0, atol=1e-9)
+    elif kind == "convert":
+        raw = data["raw"]
+        assert np.array_equal(_bits(port.convert(case["args"][0], raw)), _bits(data["out"]))
+    elif kind == "frontend":
+        ratio, = case["args"]
+        x = synth.baseband(case["n"], 61.44e6, case["seed"], noise_dbfs=-40.0).astype(np.complex64)
+        pd, dc = port.powerdecim(ratio), port.dcblock(50.0 / (61.44e6 / ratio))
+        y = port.conjugate(dc.process(pd.process(x)))
+        assert np.array_equal(_bits(y), _bits(data["out"]))
+    else:
+        pytest.fail("unknown golden kind " + kind)
+
+
+def test_golden_present():
+    assert len(_golden_cases()) >= 8, "tests/golden is empty: run tools/make_golden.py where /root/reference exists"

@@ -1,0 +1,76 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/ from the REFERENCE's own dsp/ headers (oracle/_ref/libsdrpp_ref.so, built by
+`make -C oracle ref` from /root/reference where it lies). Run in the build container only; the vectors
+are committed so the oracle port can be pinned on the GPU box, where /root/reference does not exist.
+Inputs are regenerated from seeds (sdrpp_b200/synth.py); only outputs are stored."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import pyoracle as po  # noqa: E402
+from sdrpp_b200 import synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref = po.Ref()
+    cases = []
+
+    def add(name, kind, args, arrays, **extra):
+        f = name + ".npz"
+        np.savez_compressed(os.path.join(GOLD, f), **arrays)
+        cases.append(dict(name=name, kind=kind, args=list(args), file=f, **extra))
+
+    rx = [("cfg1_wfm250", 2.4e6, 250e3, 200e3, 100e3, po.DEMOD_QUAD, [12000] * 3, 1),
+          ("cfg1_wfm240", 2.4e6, 240e3, 200e3, -300e3, po.DEMOD_QUAD, [12000, 11999, 1, 12000], 1),
+          ("cfg2_nfm", 3.2e6, 48e3, 12.5e3, 400e3, po.DEMOD_QUAD, [7936] * 5, 2),
+          ("cfg3_wfm", 20e6, 250e3, 200e3, 3.1e6, po.DEMOD_QUAD, [100000] * 2, 3),
+          ("cfg4_usb", 15.36e6, 48e3, 2.7e3, 1.0e6, po.DEMOD_USB, [76800] * 3, 4),
+          ("cfg4_am", 15.36e6, 24e3, 12e3, -2.0e6, po.DEMOD_AM, [76800] * 3, 4),
+          ("cfg5_nfm", 122.88e6, 48e3, 12.5e3, 30e6, po.DEMOD_QUAD, [614400], 5),
+          ("cfg5_am", 122.88e6, 24e3, 12e3, -41e6, po.DEMOD_AM, [614400], 5),
+          ("upsample", 48e3, 96e3, 96e3, 1e3, po.DEMOD_NONE, [480, 481], 6)]
+    for name, inSR, outSR, bw, off, demod, blocks, seed in rx:
+        n = sum(blocks)
+        x = synth.baseband(n, inSR, seed, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+        v = ref.rxvfo(inSR, outSR, bw, off)
+        d = ref.demod(demod, bw, outSR)
+        ys, ds, p = [], [], 0
+        for s in blocks:
+            y = v.process(x[p:p + s]); p += s
+            ys.append(y)
+            if d is not None:
+                ds.append(d.process(y))
+        arrays = {"iq": np.concatenate(ys)}
+        if d is not None:
+            arrays["demod"] = np.concatenate(ds)
+        add("rxvfo_" + name, "rxvfo", (inSR, outSR, bw, off, demod), arrays, n=n, seed=seed, blocks=blocks, counts=[len(y) for y in ys])
+
+    for name, N, nz, wtype, seed in [("bh7_64k", 65536, 65536, po.WIN_BH7, 1), ("hann_8k_pad", 8192, 6000, po.WIN_HANN, 2),
+                                     ("bh4_1k", 1024, 1024, po.WIN_BH4, 3)]:
+        x = synth.baseband(nz, 2.4e6, seed, noise_dbfs=-40.0).astype(np.complex64)
+        w = ref.window(wtype, nz)
+        row32, _, row64 = ref.spectrum(N, x, w)
+        add("spectrum_" + name, "spectrum", (N, nz, wtype), {"window": w, "row32": row32, "row64": row64}, seed=seed)
+
+    # conversions: the reference does these inside its source modules, which cannot be compiled
+    # here (vendor SDKs); the port's formulas are pinned by the SURVEY 8c hashes instead. The VOLK-based variants
+    # go through the shim's (float)x/scale.
+    x = synth.baseband(4 * 30720, 61.44e6, 7, noise_dbfs=-40.0).astype(np.complex64)
+    pd, dc = ref.powerdecim(4), ref.dcblock(50.0 / (61.44e6 / 4))
+    y = ref.conjugate(dc.process(pd.process(x)))
+    add("frontend_x4_dc_conj", "frontend", (4,), {"out": y}, n=len(x), seed=7)
+
+    json.dump({"generator": "tools/make_golden.py", "source": ref.lib.ref_build_info.restype and "oracle/_ref/libsdrpp_ref.so (reference dsp/ headers, IEEE flags)",
+               "cases": cases}, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
+    print("wrote", len(cases), "cases;", sum(os.path.getsize(os.path.join(GOLD, c["file"])) for c in cases) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
