@@ -16,7 +16,10 @@
 //
 // The remaining stages run at 1/D of the rate (tail_kernel, one CTA per VFO).
 #include "common.cuh"
+#include "design.h"
 #include "kernels.h"
+#include <mutex>
+#include <vector>
 
 namespace sdrpp {
 
@@ -66,158 +69,229 @@ __device__ __forceinline__ float2 phasor_u64(uint64_t phase) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Stage 1
+// Stage 1: NCO + first decimating FIR for 32 VFOs x 8*R input rows per CTA.
+//
+// With k = a*D + p (a < A = ceil(T/D), p < D) and row q = m + a holding samples x[q*D + p]:
+//     y[m] = sum_a E[m+a] * V[m+a][a],   V[q][a] = sum_p h[a*D+p] * (x[q*D+p] * F[p]),
+//     F[p] = e^{j w p} (per VFO, D entries),  E[q] = e^{j phi(first sample of row q)}.
+// The per-VFO complex work is ONE complex multiply per sample (x*F); the taps stay real and
+// shared by every VFO of the plan, so they sit in constant memory and reach the FMA pipe as a
+// uniform operand. Per input sample and VFO that is 4 + 2*T/D FMAs instead of the 4*T/D of a
+// complex-tap filter (or 8 + 2*T/D of rotate-then-filter).
+// A thread (lane = VFO) owns R consecutive rows and their R*A complex accumulators V; rows are
+// the same for all lanes, so sample loads are shared-memory broadcasts. The A partial sums of an
+// output live in up to two neighbouring warps and are combined through shared memory; a CTA
+// therefore computes 8*R rows for 8*R-(A-1) outputs.
 // ---------------------------------------------------------------------------------------------
-int stage1_pcp(int D) { return (D / 2) < 4 ? (D / 2) : 4; }
-bool stage1_supported(int A, int D) { return D >= 2 && (D & (D - 1)) == 0 && D <= 128 && A >= 1 && A <= 8; }
+constexpr int kS1PoolFloats = 4096;
+__constant__ __align__(16) float c_s1_taps[kS1PoolFloats];
+
+struct S1PoolEntry { int ratio, off, T, D, A; };
+static std::vector<S1PoolEntry> g_s1_pool;
+static std::mutex g_s1_mtx;
+static bool g_s1_uploaded[64] = { false };
+
+bool stage1_supported(int A, int D) { return D >= 2 && (D & (D - 1)) == 0 && D <= 128 && A >= 2 && A <= 7; }
+int stage1_rows(int A) { return A <= 6 ? 6 : 6; }
+int stage1_outputs_per_cta(int A) { return kStage1Warps * stage1_rows(A) - (A - 1); }
+
+// Build the padded tap pool (every PowerDecimator plan's first FIR, zero-padded to A*D) and upload
+// it to the current device's constant memory. Returns the pool offset for `ratio`, or -1.
+int stage1_tap_offset(int ratio) {
+    std::lock_guard<std::mutex> lck(g_s1_mtx);
+    if (g_s1_pool.empty()) {
+        int off = 0;
+        for (int k = 1; k <= 13; k++) {
+            std::vector<DecimStage> st = decim_plan(1 << k);
+            if (st.empty()) continue;
+            const int T = st[0].ntaps, D = st[0].decimation, A = ceil_div(T, D);
+            if (!stage1_supported(A, D)) continue;
+            g_s1_pool.push_back({ 1 << k, off, T, D, A });
+            off += A * D;
+        }
+    }
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!g_s1_uploaded[dev]) {
+        std::vector<float> pool(kS1PoolFloats, 0.0f);
+        for (const S1PoolEntry& e : g_s1_pool) {
+            if (e.off + e.A * e.D > kS1PoolFloats) return -1;
+            std::vector<DecimStage> st = decim_plan(e.ratio);
+            for (int k = 0; k < e.T; k++) pool[(size_t)(e.off + k)] = st[0].taps[k];
+        }
+        if (cudaMemcpyToSymbol(c_s1_taps, pool.data(), sizeof(float) * kS1PoolFloats) != cudaSuccess) return -1;
+        g_s1_uploaded[dev] = true;
+    }
+    for (const S1PoolEntry& e : g_s1_pool) if (e.ratio == ratio) return e.off;
+    return -1;
+}
 
 size_t stage1_g_elems(int A, int D, int nvfo) {
-    const int nvb = ceil_div(nvfo, 32);
-    return (size_t)nvb * (size_t)(D / 2) * (size_t)A * 32;
+    (void)A;
+    return (size_t)ceil_div(nvfo, 32) * (size_t)(D / 2) * 32;
 }
-void stage1_g_index(int A, int D, int pcp, int v, int k, size_t* idx4, int* half) {
-    const int vb = v / 32, lane = v % 32;
-    const int a = k / D, p = k % D, pp = p / 2;
-    const int nch = (D / 2) / pcp;
-    const int c = pp / pcp, ppc = pp % pcp;
-    *idx4 = ((((size_t)vb * nch + c) * A + a) * pcp + ppc) * 32 + lane;
+void stage1_g_index(int A, int D, int v, int p, size_t* idx4, int* half) {
+    (void)A;
+    *idx4 = ((size_t)(v / 32) * (D / 2) + (size_t)(p / 2)) * 32 + (size_t)(v % 32);
     *half = p & 1;
 }
 
-template <int A>
+template <int A, int R>
 __global__ void __launch_bounds__(kStage1Warps * 32, 2)
 stage1_kernel(const __grid_constant__ Stage1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int MT = kStage1MT, TM = kStage1TM, S = kStage1Stages;
-    constexpr int QP = TM + A - 1; // sample rows (of D samples) needed by TM outputs
-    constexpr int QS = QP | 1;     // odd row stride in float4 units: conflict-free transposed stores
+    constexpr int W = kStage1Warps;
+    constexpr int ROWS = W * R;              // rows of D samples per CTA
+    constexpr int OUT = ROWS - (A - 1);      // complete outputs per CTA
+    constexpr int NP = R + A - 1;            // partial outputs a thread contributes to
     const int D = a.D, DP = D >> 1;
-    const int pcp = a.pcp, nch = DP / pcp;
-    const int chunk_elems = A * pcp * 32;
-    const uint32_t chunk_bytes = (uint32_t)chunk_elems * 16u;
 
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-    float4* gs = reinterpret_cast<float4*>(smem_raw + 128);
-    float4* xs4 = gs + S * chunk_elems;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    float4* Fs = reinterpret_cast<float4*>(smem_raw + 128);       // [DP][32]: (F[2pp], F[2pp+1]) per lane
+    float2* xs = reinterpret_cast<float2*>(Fs + DP * 32);         // [ROWS][D] samples, natural order
+    float2* parts = xs;                                            // reused after the main loop: [W][NP][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int m0 = blockIdx.x * TM;
+    const int m0 = blockIdx.x * OUT;
     const int vb = blockIdx.y;
-    const float4* __restrict__ Gvb = a.G + (size_t)vb * nch * chunk_elems;
 
+    // Per-VFO phasor table and sample tile: bulk (TMA) copies completing on one mbarrier. The tile is
+    // contiguous in the ring; it falls back to element loads when it wraps, is misaligned, or reaches
+    // back before the group's epoch (samples that must read as zero).
+    const uint32_t f_bytes = (uint32_t)DP * 32u * 16u;
+    const uint32_t r0 = a.ring_first + (uint32_t)m0 * (uint32_t)D;
+    const int64_t abs0 = a.abs_first + (int64_t)m0 * D;
+    const uint32_t total = (uint32_t)(ROWS * D);
+    const uint32_t i0 = r0 & a.ring.mask;
+    const bool bulk_x = ((i0 & 1u) == 0) && (i0 + total - 1u <= a.ring.mask) && (abs0 >= a.abs_valid);
     if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < S; s++) mbar_init(&bars[s], 1);
+        mbar_init(bar, 1);
         mbar_fence_init();
+        mbar_expect_tx(bar, f_bytes + (bulk_x ? total * 8u : 0u));
+        bulk_g2s(Fs, a.G + (size_t)vb * DP * 32, f_bytes, bar);
+        if (bulk_x) bulk_g2s(xs, a.ring.base + i0, total * 8u, bar);
     }
-    __syncthreads();
-    if (tid == 0) {
-        for (int c = 0; c < S - 1 && c < nch; c++) {
-            mbar_expect_tx(&bars[c], chunk_bytes);
-            bulk_g2s(gs + c * chunk_elems, Gvb + (size_t)c * chunk_elems, chunk_bytes, &bars[c]);
+    if (!bulk_x) {
+        for (uint32_t n = tid; n < total; n += W * 32) {
+            float2 s = a.ring.base[(r0 + n) & a.ring.mask];
+            if (abs0 + (int64_t)n < a.abs_valid) s = make_float2(0.0f, 0.0f);
+            xs[n] = s;
         }
     }
+    __syncthreads(); // element-loaded tile complete; barrier init visible
+    mbar_wait(bar, 0);
 
-    // Sample tile, transposed to [pair p/2][row q] so that the window of one tap phase is contiguous.
-    {
-        const uint32_t r0 = a.ring_first + (uint32_t)m0 * (uint32_t)D;
-        const int64_t abs0 = a.abs_first + (int64_t)m0 * D;
-        const int total = QP * DP;
-        for (int idx = tid; idx < total; idx += kStage1Warps * 32) {
-            const int q = idx / DP, pp = idx - q * DP;
-            const int n = q * D + 2 * pp;
-            float2 s0 = a.ring.base[(r0 + (uint32_t)n) & a.ring.mask];
-            float2 s1 = a.ring.base[(r0 + (uint32_t)n + 1u) & a.ring.mask];
-            if (abs0 + n < a.abs_valid) s0 = make_float2(0.0f, 0.0f);
-            if (abs0 + n + 1 < a.abs_valid) s1 = make_float2(0.0f, 0.0f);
-            xs4[pp * QS + q] = make_float4(s0.x, s0.y, s1.x, s1.y);
+    float vr[R][A], vi[R][A];
+#pragma unroll
+    for (int r = 0; r < R; r++)
+#pragma unroll
+        for (int aa = 0; aa < A; aa++) { vr[r][aa] = 0.0f; vi[r][aa] = 0.0f; }
+
+    const float4* xrow = reinterpret_cast<const float4*>(xs + (size_t)warp * R * D);
+    const int rem = a.T - (A - 1) * D; // taps in the last slab of the tap matrix
+    const float* taps = c_s1_taps + a.tap_off;
+
+    const float2* taps2 = reinterpret_cast<const float2*>(taps); // (h[2pp], h[2pp+1]) pairs: one 64-bit uniform load
+#pragma unroll 2
+    for (int pp = 0; pp < DP; pp++) {
+        const float4 f = Fs[pp * 32 + lane];
+        const bool last_slab = (2 * pp < rem);
+        float w0r[R], w0i[R], w1r[R], w1i[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float4 x = xrow[r * DP + pp]; // warp-uniform address: broadcast
+            w0r[r] = fmaf(-x.y, f.y, x.x * f.x);
+            w0i[r] = fmaf(x.y, f.x, x.x * f.y);
+            w1r[r] = fmaf(-x.w, f.w, x.z * f.z);
+            w1i[r] = fmaf(x.w, f.z, x.z * f.w);
         }
-    }
-
-    float2 acc[MT];
 #pragma unroll
-    for (int i = 0; i < MT; i++) acc[i] = make_float2(0.0f, 0.0f);
-    const int mq = warp * MT;
-    const int rem = a.T - (A - 1) * D; // taps in the last row of the tap matrix
-
-    for (int c = 0; c < nch; c++) {
-        const int s = c % S;
-        mbar_wait(&bars[s], (uint32_t)((c / S) & 1));
-        __syncthreads(); // every warp is done with chunk c-1 (and, for c == 0, the sample tile is complete)
-        if (tid == 0 && c + S - 1 < nch) {
-            const int cn = c + S - 1, sn = cn % S;
-            fence_proxy_async();
-            mbar_expect_tx(&bars[sn], chunk_bytes);
-            bulk_g2s(gs + sn * chunk_elems, Gvb + (size_t)cn * chunk_elems, chunk_bytes, &bars[sn]);
-        }
-        const float4* g = gs + s * chunk_elems + lane;
-        for (int ppc = 0; ppc < pcp; ppc++) {
-            const int pp = c * pcp + ppc;
-            float4 xw[MT + A - 1];
-            const float4* xrow = xs4 + pp * QS + mq;
+        for (int aa = 0; aa < A; aa++) {
+            if (aa == A - 1 && !last_slab) continue; // only zero padding here
+            const float2 h = taps2[aa * DP + pp];
 #pragma unroll
-            for (int i = 0; i < MT + A - 1; i++) xw[i] = xrow[i];
-#pragma unroll
-            for (int aa = 0; aa < A; aa++) {
-                if (aa == A - 1 && 2 * pp >= rem) continue; // this slab holds only zero padding
-                const float4 g4 = g[(aa * pcp + ppc) * 32];
-#pragma unroll
-                for (int i = 0; i < MT; i++) {
-                    const float4 x = xw[aa + i];
-                    acc[i].x = fmaf(x.x, g4.x, acc[i].x);
-                    acc[i].x = fmaf(-x.y, g4.y, acc[i].x);
-                    acc[i].y = fmaf(x.x, g4.y, acc[i].y);
-                    acc[i].y = fmaf(x.y, g4.x, acc[i].y);
-                    acc[i].x = fmaf(x.z, g4.z, acc[i].x);
-                    acc[i].x = fmaf(-x.w, g4.w, acc[i].x);
-                    acc[i].y = fmaf(x.z, g4.w, acc[i].y);
-                    acc[i].y = fmaf(x.w, g4.z, acc[i].y);
-                }
+            for (int r = 0; r < R; r++) {
+                vr[r][aa] = fmaf(h.x, w0r[r], vr[r][aa]);
+                vi[r][aa] = fmaf(h.x, w0i[r], vi[r][aa]);
+                vr[r][aa] = fmaf(h.y, w1r[r], vr[r][aa]);
+                vi[r][aa] = fmaf(h.y, w1i[r], vi[r][aa]);
             }
         }
     }
+    __syncthreads(); // all warps are done reading the sample tile; reuse it for the partial sums
 
     const int v = vb * 32 + lane;
-    if (v < a.nvfo) {
-        const VfoDev vd = a.vfos[v];
-        float2* __restrict__ out = vd.slab + a.out_off;
+    const bool live = v < a.nvfo;
+    VfoDev vd{};
+    if (live) vd = a.vfos[v];
+    // rotate each row's sums by the NCO phase of the row's first sample, then form the partial outputs
+    float2 part[NP];
 #pragma unroll
-        for (int i = 0; i < MT; i++) {
-            const int m = m0 + mq + i;
-            if (m < a.M) {
-                const uint64_t ph = vd.phi_ref + (uint64_t)(a.abs_first + (int64_t)m * D - vd.n_ref) * vd.dphi;
-                out[m] = cmul(acc[i], phasor_u64(ph));
+    for (int j = 0; j < NP; j++) part[j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int q = m0 + warp * R + r;
+        const uint64_t ph = vd.phi_ref + (uint64_t)(a.abs_first + (int64_t)q * D - vd.n_ref) * vd.dphi;
+        const float2 e = phasor_u64(ph);
+#pragma unroll
+        for (int aa = 0; aa < A; aa++) {
+            // output (local to this warp's rows) j = r - aa, stored at j + (A-1)
+            const float2 t = cmul(make_float2(vr[r][aa], vi[r][aa]), e);
+            part[r - aa + (A - 1)].x += t.x;
+            part[r - aa + (A - 1)].y += t.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NP; j++) parts[(warp * NP + j) * 32 + lane] = part[j];
+    __syncthreads();
+
+    if (live) {
+        float2* __restrict__ out = vd.slab + a.out_off;
+        for (int o = warp; o < OUT; o += W) {
+            const int m = m0 + o;
+            if (m >= a.M) break;
+            // rows o .. o+A-1 belong to warps o/R .. (o+A-1)/R
+            float2 y = make_float2(0.0f, 0.0f);
+            const int w1 = o / R, w2 = (o + A - 1) / R;
+            for (int w = w1; w <= w2 && w < W; w++) {
+                const int j = o - w * R + (A - 1);
+                if (j >= 0 && j < NP) {
+                    const float2 t = parts[(w * NP + j) * 32 + lane];
+                    y.x += t.x; y.y += t.y;
+                }
             }
+            out[m] = y;
         }
     }
 }
 
-template <int A>
+template <int A, int R>
 static cudaError_t launch_stage1_t(const Stage1Args& a, cudaStream_t st) {
-    constexpr int QS = (kStage1TM + A - 1) | 1;
-    const size_t smem = 128 + (size_t)kStage1Stages * A * a.pcp * 32 * 16 + (size_t)(a.D / 2) * QS * 16;
+    constexpr int ROWS = kStage1Warps * R, OUT = ROWS - (A - 1), NP = R + A - 1;
+    const size_t tile = (size_t)ROWS * a.D * sizeof(float2);
+    const size_t parts = (size_t)kStage1Warps * NP * 32 * sizeof(float2);
+    const size_t smem = 128 + (size_t)(a.D / 2) * 32 * 16 + (tile > parts ? tile : parts);
     static size_t attr_set = 0;
     if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
-    dim3 grid(ceil_div(a.M, kStage1TM), ceil_div(a.nvfo, 32));
-    stage1_kernel<A><<<grid, kStage1Warps * 32, smem, st>>>(a);
+    dim3 grid(ceil_div(a.M, OUT), ceil_div(a.nvfo, 32));
+    stage1_kernel<A, R><<<grid, kStage1Warps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st) {
     if (a.M <= 0 || a.nvfo <= 0) return cudaSuccess;
+    if (a.tap_off < 0) return cudaErrorInvalidValue;
     switch (a.A) {
-    case 1: return launch_stage1_t<1>(a, st);
-    case 2: return launch_stage1_t<2>(a, st);
-    case 3: return launch_stage1_t<3>(a, st);
-    case 4: return launch_stage1_t<4>(a, st);
-    case 5: return launch_stage1_t<5>(a, st);
-    case 6: return launch_stage1_t<6>(a, st);
-    case 7: return launch_stage1_t<7>(a, st);
-    case 8: return launch_stage1_t<8>(a, st);
+    case 2: return launch_stage1_t<2, 6>(a, st);
+    case 3: return launch_stage1_t<3, 6>(a, st);
+    case 4: return launch_stage1_t<4, 6>(a, st);
+    case 5: return launch_stage1_t<5, 6>(a, st);
+    case 6: return launch_stage1_t<6, 6>(a, st);
+    case 7: return launch_stage1_t<7, 6>(a, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -247,9 +321,25 @@ cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st) {
 // One CTA per VFO; stages run back to back on the VFO's slab (L2-resident), __syncthreads between.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTailThreads = 256;
+constexpr int kTailSmemSamples = 6144; // staged input samples per chunk (48 KB)
+
+// Stage one chunk of a stage's input [first, first+n) from the slab (L2) into shared memory.
+// Decimating FIRs store it transposed by D -- element i at [i % D][i / D] with an odd row stride -- so
+// that consecutive outputs (lanes) read consecutive addresses for every tap; others keep natural order.
+__device__ __forceinline__ void tail_stage_in(float2* sm, const float2* src, int n, int D, int qs) {
+    if (D > 1) {
+        for (int i = threadIdx.x; i < n; i += kTailThreads) {
+            const int q = i / D, p = i - q * D;
+            sm[p * qs + q] = src[i];
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += kTailThreads) sm[i] = src[i];
+    }
+}
 
 __global__ void __launch_bounds__(kTailThreads)
 tail_kernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ __align__(16) float2 tsm[];
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
     const TailGroup& g = a.g[gi];
@@ -259,30 +349,71 @@ tail_kernel(const __grid_constant__ TailArgs a) {
 
     for (int s = 0; s < g.nstages; s++) {
         const TailStage& st = g.st[s];
-        const int hist = st.T - 1;
+        const int T = st.T, hist = T - 1;
         float2* buf = slab + st.in_off - hist; // [hist | n_in]
         float2* out = slab + ((s + 1 < g.nstages) ? g.st[s + 1].in_off : g.final_off);
-        for (int m = tid; m < st.n_out; m += kTailThreads) {
-            int off;
-            const float* taps = st.taps;
-            if (st.type == TAIL_POLY) {
-                const long long P = (long long)st.phase + (long long)m * st.D;
-                off = st.offset + (int)(P / st.interp);
-                taps += (size_t)(P % st.interp) * st.T;
+        const bool poly = st.type == TAIL_POLY;
+        const int D = poly ? 1 : st.D; // layout stride (polyphase reads ~consecutive samples)
+        // outputs per chunk so that the inputs they need fit the staging buffer
+        int ch;
+        if (poly) ch = (int)(((long long)(kTailSmemSamples - T - 2) * st.interp) / st.D);
+        else ch = (kTailSmemSamples - T - D) / D + 1;
+        if (ch >= kTailThreads) ch -= ch % kTailThreads;
+        if (ch < 1) ch = 1;
+        for (int o0 = 0; o0 < st.n_out; o0 += ch) {
+            const int o1 = min(st.n_out, o0 + ch);
+            int first, last; // input index range [first, last] in buf needed by outputs [o0, o1)
+            if (poly) {
+                const long long P0 = (long long)st.phase + (long long)o0 * st.D;
+                const long long P1 = (long long)st.phase + (long long)(o1 - 1) * st.D;
+                first = st.offset + (int)(P0 / st.interp);
+                last = st.offset + (int)(P1 / st.interp) + T - 1;
             } else {
-                off = st.offset + m * st.D;
+                first = st.offset + o0 * st.D;
+                last = st.offset + (o1 - 1) * st.D + T - 1;
             }
-            const float2* x = buf + off;
-            float re = 0.0f, im = 0.0f;
-            for (int k = 0; k < st.T; k++) {
-                const float2 v = x[k];
-                const float h = __ldg(taps + k);
-                re = fmaf(v.x, h, re);
-                im = fmaf(v.y, h, im);
+            const int n = last - first + 1;
+            const int qs = ((n + D - 1) / D) | 1;
+            tail_stage_in(tsm, buf + first, n, D, qs);
+            __syncthreads();
+            for (int o = o0 + tid; o < o1; o += kTailThreads) {
+                float re = 0.0f, im = 0.0f;
+                if (poly) {
+                    const long long P = (long long)st.phase + (long long)o * st.D;
+                    const float2* x = tsm + (st.offset + (int)(P / st.interp) - first);
+                    const float* taps = st.taps + (size_t)(P % st.interp) * T;
+                    for (int k = 0; k < T; k++) {
+                        const float2 v = x[k];
+                        const float h = __ldg(taps + k);
+                        re = fmaf(v.x, h, re);
+                        im = fmaf(v.y, h, im);
+                    }
+                } else if (D == 1) {
+                    const float2* x = tsm + (o - o0);
+                    for (int k = 0; k < T; k++) {
+                        const float2 v = x[k];
+                        const float h = __ldg(st.taps + k);
+                        re = fmaf(v.x, h, re);
+                        im = fmaf(v.y, h, im);
+                    }
+                } else {
+                    // tap k = aa*D + p reads staged element [p][(o-o0) + aa]
+                    const float2* x = tsm + (o - o0);
+                    for (int p = 0; p < D; p++) {
+                        const float2* xp = x + p * qs;
+                        int aa = 0;
+                        for (int k = p; k < T; k += D, aa++) {
+                            const float2 v = xp[aa];
+                            const float h = __ldg(st.taps + k);
+                            re = fmaf(v.x, h, re);
+                            im = fmaf(v.y, h, im);
+                        }
+                    }
+                }
+                out[o] = make_float2(re, im);
             }
-            out[m] = make_float2(re, im);
+            __syncthreads();
         }
-        __syncthreads();
         // carry the last `hist` inputs to the front (fir.h:80, decimating_fir.h:65, polyphase_resampler.h:96)
         if (st.n_in > 0) {
             float2 keep[8];
@@ -321,7 +452,14 @@ tail_kernel(const __grid_constant__ TailArgs a) {
 
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {
     if (total_vfos <= 0) return cudaSuccess;
-    tail_kernel<<<total_vfos, kTailThreads, 0, st>>>(a);
+    const size_t smem = (size_t)(kTailSmemSamples + 512) * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    tail_kernel<<<total_vfos, kTailThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

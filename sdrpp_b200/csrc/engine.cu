@@ -58,7 +58,7 @@ struct VfoPlan {
     int chan_taps = 0;
     // stage 1
     bool s1_fir = false;
-    int s1_D = 1, s1_T = 1, s1_A = 1;
+    int s1_D = 1, s1_T = 1, s1_A = 1, s1_tap_off = -1;
     std::vector<float> s1_taps;
     std::vector<TailPlanStage> tail;
     uint32_t final_off = 0;
@@ -82,8 +82,9 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
     size_t first_tail = 0;
     if (!dst.empty()) {
         const int D = dst[0].decimation, T = dst[0].ntaps, A = ceil_div(T, D);
-        if (stage1_supported(A, D)) {
-            p.s1_fir = true; p.s1_D = D; p.s1_T = T; p.s1_A = A;
+        const int tap_off = stage1_supported(A, D) ? stage1_tap_offset(p.rp.predec) : -1;
+        if (tap_off >= 0) {
+            p.s1_fir = true; p.s1_D = D; p.s1_T = T; p.s1_A = A; p.s1_tap_off = tap_off;
             p.s1_taps.assign(dst[0].taps, dst[0].taps + T);
             first_tail = 1;
         }
@@ -334,19 +335,14 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
 
 // ---- VFO layout ------------------------------------------------------------------------------
 static void fill_g_for_vfo(Group& g, int lane_index, const Vfo& v) {
+    // F[p] = exp(+j*2*pi*turns*p): the NCO advance over p samples inside one row of D samples
     const VfoPlan& p = *g.plan;
-    const int A = p.s1_A, D = p.s1_D, pcp = stage1_pcp(D);
-    for (int k = 0; k < A * D; k++) {
-        float re = 0.0f, im = 0.0f;
-        if (k < p.s1_T) {
-            // g[k] = h[k] * exp(+j*2*pi*turns*k): the NCO advance over k samples folded into the tap
-            double ang = v.turns * (double)k;
-            ang -= floor(ang);
-            re = (float)((double)p.s1_taps[(size_t)k] * cos(2.0 * kPi * ang));
-            im = (float)((double)p.s1_taps[(size_t)k] * sin(2.0 * kPi * ang));
-        }
+    for (int k = 0; k < p.s1_D; k++) {
+        double ang = v.turns * (double)k;
+        ang -= floor(ang);
+        const float re = (float)cos(2.0 * kPi * ang), im = (float)sin(2.0 * kPi * ang);
         size_t idx; int half;
-        stage1_g_index(A, D, pcp, lane_index, k, &idx, &half);
+        stage1_g_index(p.s1_A, p.s1_D, lane_index, k, &idx, &half);
         float4& e = g.h_G[idx];
         if (half == 0) { e.x = re; e.y = im; } else { e.z = re; e.w = im; }
     }
@@ -581,14 +577,14 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             const int off0 = off;
             advance_decim(off, p.s1_D, n, &nprev);
             g.st.s1_offset = off;
-            a.D = p.s1_D; a.T = p.s1_T; a.A = p.s1_A; a.pcp = stage1_pcp(p.s1_D);
+            a.D = p.s1_D; a.T = p.s1_T; a.A = p.s1_A; a.tap_off = p.s1_tap_off;
             a.M = nprev; a.G = g.d_G;
             a.abs_first = abs_block - (p.s1_T - 1) + off0;
             a.ring_first = (uint32_t)((uint64_t)a.abs_first & fe->ring_mask);
             FE_TRY(fe, launch_stage1(a, st));
         } else {
             nprev = n;
-            a.D = 1; a.T = 1; a.A = 1; a.pcp = 1; a.M = n; a.G = nullptr;
+            a.D = 1; a.T = 1; a.A = 1; a.tap_off = 0; a.M = n; a.G = nullptr;
             a.abs_first = abs_block;
             a.ring_first = wpos;
             FE_TRY(fe, launch_mix_only(a, st));
@@ -942,6 +938,9 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     if (rc != SDRPP_OK) return rc;
     FE_TRY(fe, cudaStreamSynchronize(fe->st_copy));
     FE_TRY(fe, cudaStreamSynchronize(fe->st));
+    // everything submitted so far is complete: nothing is left to wait for
+    for (int i = 0; i < 2; i++) fe->rs[i].pending = false;
+    if (fe->seq > 0) { fe->waited = fe->seq; fe->cur = (int)((fe->seq - 1) & 1); }
     return SDRPP_OK;
 }
 

@@ -63,30 +63,27 @@ struct VfoDev {
     uint32_t pad;
 };
 
-constexpr int kStage1MT = 8;        // outputs per thread
-constexpr int kStage1Warps = 8;     // warps per CTA, each a different output sub-tile
-constexpr int kStage1TM = kStage1MT * kStage1Warps; // outputs per CTA
-constexpr int kStage1Stages = 3;    // tap-chunk pipeline depth
+constexpr int kStage1Warps = 8;     // warps per CTA, each owning R consecutive input rows
 
-// Stage 1 of a group of VFOs sharing one plan: NCO translation folded into the first decimating
-// FIR (dsp/channel/frequency_xlator.h:43-50 + dsp/filter/decimating_fir.h:45-68).
+// Stage 1 of a group of VFOs sharing one plan: NCO translation + the first decimating FIR
+// (dsp/channel/frequency_xlator.h:43-50 + dsp/filter/decimating_fir.h:45-68).
 struct Stage1Args {
     RingRef ring;
-    uint32_t ring_first;   // ring index of buf[offset] for output 0 (i.e. first sample of dot product 0)
+    uint32_t ring_first;   // ring index of the first sample of the dot product of output 0
     int64_t abs_first;     // absolute index of that sample
     int64_t abs_valid;     // samples with absolute index < abs_valid read as zero (reset / stream start)
     int D, T, A;           // decimation, taps, ceil(T/D)
-    int pcp;               // tap pairs per chunk
+    int tap_off;           // offset of this plan's zero-padded taps in the constant tap pool
     int M;                 // outputs this block
     int nvfo;              // VFOs in the group
-    const float4* G;       // folded taps [vb][chunk][a][ppc][lane] (pairs of complex taps)
+    const float4* G;       // per-VFO phasor table F[p] = e^{j w p}: [vb][p/2][lane] = (F[p], F[p+1])
     const VfoDev* vfos;    // group members, contiguous
     uint32_t out_off;      // slab offset (in float2) where output 0 goes
 };
 bool stage1_supported(int A, int D);
+int stage1_tap_offset(int ratio);                          // also uploads the pool to the current device
 size_t stage1_g_elems(int A, int D, int nvfo);          // float4 elements of G
-void stage1_g_index(int A, int D, int pcp, int v, int k, size_t* idx4, int* half); // where tap k of VFO v lives
-int stage1_pcp(int D);
+void stage1_g_index(int A, int D, int v, int p, size_t* idx4, int* half); // where F[p] of VFO v lives
 cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st);
 // D = 1, T = 1 (no pre-decimation): pure translation.
 cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st);

@@ -94,7 +94,7 @@ def test_with_nco_short_window_and_aligned(gpu, port, inSR, outSR, bw, blk):
         if len(r[b][0]) < 8:
             continue
         res, c = po.aligned_rel_rms(g[b][0], r[b][0])
-        assert res <= 3e-5, f"block {b}: aligned residual {res:.3e} (c={c})"
+        assert res <= 5e-5, f"block {b}: aligned residual {res:.3e} (c={c})"
         assert abs(abs(c) - 1.0) < 1e-3 and abs(np.angle(c)) < 2e-2
 
 
@@ -156,7 +156,7 @@ def test_many_vfos_two_classes(gpu, port):
             # Channels without a carrier hold only noise ~-80 dBFS while the reference rotator's own fp32
             # rounding is relative to the full-band signal (~-6 dBFS): gate those on absolute error.
             ref_rms = float(np.sqrt(np.mean(np.abs(r[b][0]) ** 2)))
-            assert res * ref_rms <= 3e-5 * ref_rms + 3e-7 * x_rms, f"vfo {i} block {b}: {res:.3e}"
+            assert res * ref_rms <= 5e-5 * ref_rms + 3e-7 * x_rms, f"vfo {i} block {b}: {res:.3e}"
 
 
 def test_retune_reset_add_remove(gpu, port):
