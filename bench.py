@@ -241,8 +241,10 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     vf_all = vfo_list()
-    # shard VFOs round-robin (NFM/AM alternate, so every rank gets the same mix = balanced cost)
-    mine = [v for i, v in enumerate(vf_all) if (i // 2) % world == rank] if world > 1 else vf_all
+    # shard the VFO set across ranks, balanced by per-VFO cost (sdrpp_b200/shard.py); no data-path collective
+    from sdrpp_b200 import shard
+    costs = [shard.vfo_cost(SR, v[0], v[1], cuda.design_resampler, cuda.design_decim_plan) for v in vf_all]
+    mine = [vf_all[i] for i in shard.shard_vfos(costs, world)[rank]]
     with_fft = (rank == 0)
     fe = cuda.Frontend(SR, fft_size=FFT_N if with_fft else 0, fft_rate=SR / FFT_N, fft_window=cuda.WIN_BH4, max_block=BLOCK)
     ids = [fe.add_vfo(*v) for v in mine]
