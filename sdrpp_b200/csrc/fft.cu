@@ -11,6 +11,10 @@
 // 126 MB L2; HBM sees the 8 B/sample read and the 4 B/sample row write.
 #include "fft_core.cuh"
 #include "kernels.h"
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
 #include "../../include/sdrpp_cuda.h"
 
 namespace sdrpp {
@@ -23,13 +27,62 @@ __device__ __forceinline__ float power_db(float2 x) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Twiddle tables: exp(-2*pi*i*j/L) computed in double on the host, rounded once. One set per (device, N).
+// ---------------------------------------------------------------------------------------------
+struct SpectrumTables {
+    float2* tw1 = nullptr;  // L = N1 (cols transform; also the coarse factor of the four-step twiddle)
+    float2* tw2 = nullptr;  // L = N2 (rows transform)
+    float2* twlo = nullptr; // exp(-2*pi*i*j/N), j < N2 (fine factor of the four-step twiddle)
+};
+static std::mutex g_tab_mtx;
+static std::map<std::pair<int, int>, SpectrumTables> g_tabs;
+
+static cudaError_t upload_table(float2** dst, int count, double denom) {
+    std::vector<float2> h((size_t)count);
+    for (int j = 0; j < count; j++) {
+        const double a = -2.0 * 3.14159265358979323846 * (double)j / denom;
+        h[(size_t)j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    cudaError_t e = cudaMalloc((void**)dst, sizeof(float2) * (size_t)count);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, h.data(), sizeof(float2) * (size_t)count, cudaMemcpyHostToDevice);
+}
+
+static cudaError_t get_tables(int N, int N1, int N2, SpectrumTables* out) {
+    std::lock_guard<std::mutex> lck(g_tab_mtx);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    auto key = std::make_pair(dev, N);
+    auto it = g_tabs.find(key);
+    if (it == g_tabs.end()) {
+        SpectrumTables t;
+        if ((e = upload_table(&t.tw2, N2, (double)N2)) != cudaSuccess) return e;
+        if (N1 > 1) {
+            if ((e = upload_table(&t.tw1, N1, (double)N1)) != cudaSuccess) return e;
+            if ((e = upload_table(&t.twlo, N2, (double)N)) != cudaSuccess) return e;
+        }
+        it = g_tabs.emplace(key, t).first;
+    }
+    *out = it->second;
+    return cudaSuccess;
+}
+
+__device__ __forceinline__ void load_table(float2* dst, const float2* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+}
+
+// ---------------------------------------------------------------------------------------------
 // cols kernel: grid (N2/B, frames), block T*B, thread (t,b) with b fastest (coalesced columns)
 // ---------------------------------------------------------------------------------------------
 template <class P, int B>
 __global__ void __launch_bounds__(P::T* B)
-fft_cols_kernel(SpectrumArgs a, int N2, int log2N) {
+fft_cols_kernel(SpectrumArgs a, SpectrumTables tabs, int N2, int log2N, int log2N2) {
     extern __shared__ __align__(16) float2 sm[];
-    constexpr int E = P::E, T = P::T;
+    constexpr int E = P::E, T = P::T, L = P::L;
+    float2* tw = sm;              // [L]   exp(-2 pi i j / N1)
+    float2* twlo = sm + L;        // [N2]  exp(-2 pi i j / N)
+    float2* ex = twlo + N2;       // exchange buffer
     const int b = threadIdx.x % B, t = threadIdx.x / B;
     const int n2 = blockIdx.x * B + b;
     const int f = blockIdx.y;
@@ -48,33 +101,21 @@ fft_cols_kernel(SpectrumArgs a, int N2, int log2N) {
             v[e] = make_float2(0.0f, 0.0f);
         }
     }
-    block_fft<P, true, B>(v, sm, t, b);
+    load_table(tw, tabs.tw1, L);
+    load_table(twlo, tabs.twlo, N2);
+    block_fft<P, true, B>(v, ex, tw, t, b); // the first exchange's __syncthreads also publishes the tables
 
-    // four-step twiddle W_N^(n2*k1), k1 = t + T*e: base * step^e
-    const uint32_t nmask = (1u << log2N) - 1u;
-    float sn, cs;
-    sincospif(-2.0f * (float)(((uint32_t)n2 * (uint32_t)t) & nmask) / (float)(1u << log2N), &sn, &cs);
-    const float2 wbase = make_float2(cs, sn);
-    sincospif(-2.0f * (float)(((uint32_t)n2 * (uint32_t)T) & nmask) / (float)(1u << log2N), &sn, &cs);
-    const float2 wstep = make_float2(cs, sn);
-    float2 p[E];
-    p[0] = wbase;
-    p[1] = cmul(wbase, wstep);
-    // p[e] = wbase * wstep^e with a log-depth tree on the powers of wstep
-    {
-        float2 q[E];
-        q[0] = make_float2(1.0f, 0.0f);
-        q[1] = wstep;
-#pragma unroll
-        for (int e = 2; e < E; e++) q[e] = cmul(q[e / 2], q[e - e / 2]);
-#pragma unroll
-        for (int e = 2; e < E; e++) p[e] = cmul(wbase, q[e]);
-    }
+    // four-step twiddle W_N^m, m = n2*k1 < N: W_N^m = exp(-2 pi i (m >> log2N2) / N1) * exp(-2 pi i (m & (N2-1)) / N)
     float2* __restrict__ out = a.inter + (size_t)f * ((size_t)1 << log2N);
+    const uint32_t lomask = (uint32_t)N2 - 1u;
+    uint32_t m = (uint32_t)n2 * (uint32_t)t;
+    const uint32_t dm = (uint32_t)n2 * (uint32_t)T;
 #pragma unroll
     for (int e = 0; e < E; e++) {
         const int k1 = t + T * e;
-        out[(size_t)k1 * N2 + n2] = cmul(v[e], p[e]);
+        const float2 w = cmul(tw[m >> log2N2], twlo[m & lomask]);
+        out[(size_t)k1 * N2 + n2] = cmul(v[e], w);
+        m += dm;
     }
 }
 
@@ -84,9 +125,11 @@ fft_cols_kernel(SpectrumArgs a, int N2, int log2N) {
 // ---------------------------------------------------------------------------------------------
 template <class P, int B, bool FROM_SAMPLES>
 __global__ void __launch_bounds__(P::T* B)
-fft_rows_kernel(SpectrumArgs a, int N1, int log2N) {
+fft_rows_kernel(SpectrumArgs a, SpectrumTables tabs, int N1, int log2N) {
     extern __shared__ __align__(16) float2 sm[];
     constexpr int E = P::E, T = P::T, L = P::L;
+    float2* tw = sm;        // [L] exp(-2 pi i j / N2)
+    float2* ex = sm + L;    // exchange buffer, later the transposed dB tile
     const int t = threadIdx.x % T, b = threadIdx.x / T;
     float2 v[E];
 
@@ -106,7 +149,8 @@ fft_rows_kernel(SpectrumArgs a, int N1, int log2N) {
                 v[e] = make_float2(0.0f, 0.0f);
             }
         }
-        block_fft<P, false, B>(v, sm, t, b);
+        load_table(tw, tabs.tw2, L);
+        block_fft<P, false, B>(v, ex, tw, t, b);
         if (live) {
 #pragma unroll
             for (int e = 0; e < E; e++) {
@@ -122,14 +166,15 @@ fft_rows_kernel(SpectrumArgs a, int N1, int log2N) {
         const float2* __restrict__ A = a.inter + (size_t)f * N + (size_t)(k1_0 + b) * L;
 #pragma unroll
         for (int e = 0; e < E; e++) v[e] = A[t + T * e];
-        block_fft<P, false, B>(v, sm, t, b);
+        load_table(tw, tabs.tw2, L);
+        block_fft<P, false, B>(v, ex, tw, t, b);
         if (a.X) {
 #pragma unroll
             for (int e = 0; e < E; e++) a.X[(size_t)f * N + (size_t)(k1_0 + b) + (size_t)N1 * (t + T * e)] = v[e];
         }
         if (a.rows) {
             // transpose through shared memory so each k2 writes B contiguous floats
-            float* so = reinterpret_cast<float*>(sm);
+            float* so = reinterpret_cast<float*>(ex);
 #pragma unroll
             for (int e = 0; e < E; e++) so[(t + T * e) * (B + 1) + b] = power_db(v[e]);
             __syncthreads();
@@ -153,25 +198,27 @@ using P1024 = FftPlan<1024, 32, 32, 32, 1>;
 using P2048 = FftPlan<2048, 16, 16, 16, 8>;
 using P4096 = FftPlan<4096, 16, 16, 16, 16>;
 
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
 template <class P, int B>
-static cudaError_t launch_cols(const SpectrumArgs& a, int N2, int log2N, cudaStream_t st) {
-    constexpr size_t smem = fft_smem_bytes<P, true, B>();
-    static bool attr_done = false;
-    if (!attr_done) {
+static cudaError_t launch_cols(const SpectrumArgs& a, const SpectrumTables& tabs, int N2, int log2N, cudaStream_t st) {
+    const size_t smem = (P::L + (size_t)N2 + fft_exchange_elems<P, true, B>()) * sizeof(float2);
+    static size_t attr_set = 0;
+    if (smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(fft_cols_kernel<P, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_done = true;
+        attr_set = smem;
     }
     dim3 grid(N2 / B, a.frames);
-    fft_cols_kernel<P, B><<<grid, P::T * B, smem, st>>>(a, N2, log2N);
+    fft_cols_kernel<P, B><<<grid, P::T * B, smem, st>>>(a, tabs, N2, log2N, ilog2(N2));
     return cudaGetLastError();
 }
 
 template <class P, int B, bool FROM_SAMPLES>
-static cudaError_t launch_rows(const SpectrumArgs& a, int N1, int log2N, cudaStream_t st) {
-    constexpr size_t ex = fft_smem_bytes<P, false, B>();
+static cudaError_t launch_rows(const SpectrumArgs& a, const SpectrumTables& tabs, int N1, int log2N, cudaStream_t st) {
+    constexpr size_t ex = fft_exchange_elems<P, false, B>() * sizeof(float2);
     constexpr size_t tr = FROM_SAMPLES ? 0 : (size_t)P::L * (B + 1) * sizeof(float);
-    constexpr size_t smem = ex > tr ? ex : tr;
+    constexpr size_t smem = P::L * sizeof(float2) + (ex > tr ? ex : tr);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(fft_rows_kernel<P, B, FROM_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -179,7 +226,7 @@ static cudaError_t launch_rows(const SpectrumArgs& a, int N1, int log2N, cudaStr
         attr_done = true;
     }
     dim3 grid(FROM_SAMPLES ? ceil_div(a.frames, B) : N1 / B, FROM_SAMPLES ? 1 : a.frames);
-    fft_rows_kernel<P, B, FROM_SAMPLES><<<grid, P::T * B, smem, st>>>(a, N1, log2N);
+    fft_rows_kernel<P, B, FROM_SAMPLES><<<grid, P::T * B, smem, st>>>(a, tabs, N1, log2N);
     return cudaGetLastError();
 }
 
@@ -197,36 +244,38 @@ cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long 
     int N1, N2;
     const int lg = spectrum_split(N, &N1, &N2);
     if (lg < 0 || a.frames <= 0) return cudaErrorInvalidValue;
-    cudaError_t e = cudaSuccess;
+    SpectrumTables tabs;
+    cudaError_t e = get_tables(N, N1, N2, &tabs);
+    if (e != cudaSuccess) return e;
     if (N1 == 1) {
         switch (N) {
-        case 64: e = launch_rows<P64, 16, true>(a, 1, lg, st); break;
-        case 128: e = launch_rows<P128, 16, true>(a, 1, lg, st); break;
-        case 256: e = launch_rows<P256, 8, true>(a, 1, lg, st); break;
-        case 512: e = launch_rows<P512, 8, true>(a, 1, lg, st); break;
-        case 1024: e = launch_rows<P1024, 4, true>(a, 1, lg, st); break;
-        case 2048: e = launch_rows<P2048, 2, true>(a, 1, lg, st); break;
-        case 4096: e = launch_rows<P4096, 1, true>(a, 1, lg, st); break;
+        case 64: e = launch_rows<P64, 16, true>(a, tabs, 1, lg, st); break;
+        case 128: e = launch_rows<P128, 16, true>(a, tabs, 1, lg, st); break;
+        case 256: e = launch_rows<P256, 8, true>(a, tabs, 1, lg, st); break;
+        case 512: e = launch_rows<P512, 8, true>(a, tabs, 1, lg, st); break;
+        case 1024: e = launch_rows<P1024, 4, true>(a, tabs, 1, lg, st); break;
+        case 2048: e = launch_rows<P2048, 2, true>(a, tabs, 1, lg, st); break;
+        case 4096: e = launch_rows<P4096, 1, true>(a, tabs, 1, lg, st); break;
         }
         if (launches) *launches += 1;
         return e;
     }
     switch (N1) {
-    case 64: e = launch_cols<P64, 16>(a, N2, lg, st); break;
-    case 128: e = launch_cols<P128, 16>(a, N2, lg, st); break;
-    case 256: e = launch_cols<P256, 16>(a, N2, lg, st); break;
-    case 512: e = launch_cols<P512, 16>(a, N2, lg, st); break;
-    case 1024: e = launch_cols<P1024, 8>(a, N2, lg, st); break;
-    case 2048: e = launch_cols<P2048, 8>(a, N2, lg, st); break;
+    case 64: e = launch_cols<P64, 16>(a, tabs, N2, lg, st); break;
+    case 128: e = launch_cols<P128, 16>(a, tabs, N2, lg, st); break;
+    case 256: e = launch_cols<P256, 16>(a, tabs, N2, lg, st); break;
+    case 512: e = launch_cols<P512, 16>(a, tabs, N2, lg, st); break;
+    case 1024: e = launch_cols<P1024, 8>(a, tabs, N2, lg, st); break;
+    case 2048: e = launch_cols<P2048, 8>(a, tabs, N2, lg, st); break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
     switch (N2) {
-    case 128: e = launch_rows<P128, 16, false>(a, N1, lg, st); break;
-    case 256: e = launch_rows<P256, 16, false>(a, N1, lg, st); break;
-    case 512: e = launch_rows<P512, 16, false>(a, N1, lg, st); break;
-    case 1024: e = launch_rows<P1024, 16, false>(a, N1, lg, st); break;
-    case 2048: e = launch_rows<P2048, 8, false>(a, N1, lg, st); break;
+    case 128: e = launch_rows<P128, 16, false>(a, tabs, N1, lg, st); break;
+    case 256: e = launch_rows<P256, 16, false>(a, tabs, N1, lg, st); break;
+    case 512: e = launch_rows<P512, 16, false>(a, tabs, N1, lg, st); break;
+    case 1024: e = launch_rows<P1024, 8, false>(a, tabs, N1, lg, st); break;
+    case 2048: e = launch_rows<P2048, 8, false>(a, tabs, N1, lg, st); break;
     default: return cudaErrorInvalidValue;
     }
     if (launches) *launches += 2;

@@ -68,18 +68,6 @@ __device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
     }
 }
 
-// u[r] *= w^r, r = 1..R-1, powers formed in a log-depth product tree (error ~ log2(R) ulp).
-template <int R>
-__device__ __forceinline__ void apply_twiddle_powers(float2 (&u)[R], float2 w) {
-    float2 p[R];
-    p[0] = make_float2(1.0f, 0.0f);
-    if constexpr (R > 1) p[1] = w;
-#pragma unroll
-    for (int r = 2; r < R; r++) p[r] = cmul(p[r / 2], p[r - r / 2]);
-#pragma unroll
-    for (int r = 1; r < R; r++) u[r] = cmul(u[r], p[r]);
-}
-
 template <int L_, int E_, int R0_, int R1_, int R2_>
 struct FftPlan {
     static constexpr int L = L_, E = E_, R0 = R0_, R1 = R1_, R2 = R2_;
@@ -98,9 +86,11 @@ __device__ __forceinline__ int smem_index(int idx, int b) {
 }
 
 // One Stockham pass on the register tile. NS = product of the radices of earlier passes.
+// tw: shared-memory table exp(-2*pi*i*j/L), j < L (correctly rounded on the host) -- every twiddle is a
+// single table value, so round-off matches a table-driven CPU FFT instead of growing along a product chain.
 template <class P, int R, int NS, bool LAST, bool COLS, int B>
-__device__ __forceinline__ void fft_pass(float2 (&v)[P::E], float2* sm, int t, int b) {
-    constexpr int E = P::E, T = P::T, S = E / R;
+__device__ __forceinline__ void fft_pass(float2 (&v)[P::E], float2* sm, const float2* tw, int t, int b) {
+    constexpr int E = P::E, T = P::T, S = E / R, L = P::L;
 #pragma unroll
     for (int s = 0; s < S; s++) {
         float2 u[R];
@@ -109,9 +99,9 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[P::E], float2* sm, int t, i
         const int j = t + T * s;
         if constexpr (NS > 1) {
             const int k = j % NS;
-            float sn, cs;
-            sincospif(-2.0f * (float)k / (float)(NS * R), &sn, &cs);
-            apply_twiddle_powers<R>(u, make_float2(cs, sn));
+            constexpr int STRIDE = L / (NS * R);
+#pragma unroll
+            for (int r = 1; r < R; r++) u[r] = cmul(u[r], tw[(k * r * STRIDE) & (L - 1)]);
         }
         dft_reg<R>(u);
         if constexpr (LAST) {
@@ -133,15 +123,16 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[P::E], float2* sm, int t, i
 
 // Full length-L transform of the register tile (in: x[t+T*e], out: X[t+T*e]).
 template <class P, bool COLS, int B>
-__device__ __forceinline__ void block_fft(float2 (&v)[P::E], float2* sm, int t, int b) {
-    fft_pass<P, P::R0, 1, P::PASSES == 1, COLS, B>(v, sm, t, b);
-    if constexpr (P::PASSES >= 2) fft_pass<P, P::R1, P::R0, P::PASSES == 2, COLS, B>(v, sm, t, b);
-    if constexpr (P::PASSES >= 3) fft_pass<P, P::R2, P::R0 * P::R1, true, COLS, B>(v, sm, t, b);
+__device__ __forceinline__ void block_fft(float2 (&v)[P::E], float2* sm, const float2* tw, int t, int b) {
+    fft_pass<P, P::R0, 1, P::PASSES == 1, COLS, B>(v, sm, tw, t, b);
+    if constexpr (P::PASSES >= 2) fft_pass<P, P::R1, P::R0, P::PASSES == 2, COLS, B>(v, sm, tw, t, b);
+    if constexpr (P::PASSES >= 3) fft_pass<P, P::R2, P::R0 * P::R1, true, COLS, B>(v, sm, tw, t, b);
 }
 
+// exchange buffer elements (float2) for B transforms
 template <class P, bool COLS, int B>
-constexpr size_t fft_smem_bytes() {
-    return P::PASSES == 1 ? 0 : (COLS ? (size_t)P::L * B : (size_t)P::LP * B) * sizeof(float2);
+constexpr size_t fft_exchange_elems() {
+    return P::PASSES == 1 ? 0 : (COLS ? (size_t)P::L * B : (size_t)P::LP * B);
 }
 
 } // namespace sdrpp
