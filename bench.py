@@ -259,22 +259,27 @@ def run_gpu(args, rank, world, local_rank):
         d_stage = [torch.empty((BLOCK, 2), dtype=torch.float32, device=dev) for _ in range(2)]
     torch.cuda.synchronize()
 
+    consumed = [None, None]  # per staging buffer: event after which the front end no longer reads it
+
     def step_device(i):
         blk = d_blocks[i % NB]
         if world > 1:
-            # NVLink broadcast of the IQ block from the ingest GPU, then every rank channelizes its VFOs
-            buf = d_stage[i % 2]
+            # NVLink broadcast of the IQ block from the ingest GPU, then every rank channelizes its VFOs.
+            # Two staging buffers: the broadcast of block i+1 overlaps the kernels of block i.
+            k = i % 2
+            buf = d_stage[k]
+            cur = torch.cuda.current_stream()
+            if consumed[k] is not None:
+                cur.wait_event(consumed[k])
             if rank == 0:
                 buf.copy_(blk, non_blocking=True)
             dist.broadcast(buf, src=0)
             ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
+            ev.record(cur)
             st.wait_event(ev)
             fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
-            # the staging buffer is reused two steps later: make torch's stream wait for the front end
-            ev2 = torch.cuda.Event()
-            ev2.record(st)
-            torch.cuda.current_stream().wait_event(ev2)
+            consumed[k] = torch.cuda.Event()
+            consumed[k].record(st)
         else:
             fe.submit_device(cuda.FMT_CF32, blk.data_ptr(), BLOCK)
 

@@ -415,13 +415,16 @@ tail_kernel(const __grid_constant__ TailArgs a) {
             __syncthreads();
         }
         // carry the last `hist` inputs to the front (fir.h:80, decimating_fir.h:65, polyphase_resampler.h:96)
-        if (st.n_in > 0) {
+        // Stage 0 reads the double-buffered stage-1 region, so its history goes to the OTHER region (always, even
+        // for an empty block); later stages shift in place.
+        if (s == 0 || st.n_in > 0) {
+            float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : buf;
             float2 keep[8];
             int n = 0;
             for (int i = tid; i < hist && n < 8; i += kTailThreads, n++) keep[n] = buf[st.n_in + i];
             __syncthreads();
             n = 0;
-            for (int i = tid; i < hist && n < 8; i += kTailThreads, n++) buf[i] = keep[n];
+            for (int i = tid; i < hist && n < 8; i += kTailThreads, n++) dst[i] = keep[n];
             __syncthreads();
         }
     }
@@ -447,7 +450,12 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         }
     }
     __syncthreads();
-    if (tid == 0 && g.n_final > 0) fin[-1] = fin[g.n_final - 1];
+    if (tid == 0) {
+        // previous-sample state of the quadrature demod; with no tail stage the final output IS the stage-1 region
+        float2* nxt = (g.nstages == 0) ? (slab + g.carry0_off) : fin;
+        if (g.n_final > 0) nxt[-1] = fin[g.n_final - 1];
+        else if (g.nstages == 0) nxt[-1] = fin[-1];
+    }
 }
 
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {

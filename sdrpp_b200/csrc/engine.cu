@@ -61,6 +61,7 @@ struct VfoPlan {
     int s1_D = 1, s1_T = 1, s1_A = 1, s1_tap_off = -1;
     std::vector<float> s1_taps;
     std::vector<TailPlanStage> tail;
+    uint32_t s1_off[2] = { 0, 0 }; // the two stage-1 output regions (data areas)
     uint32_t final_off = 0;
     int cap_final = 0;
     size_t slab_elems = 0;
@@ -114,21 +115,42 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
         p.tail.push_back(std::move(s));
     }
     if ((int)p.tail.size() > kTailMaxStages) { *err = "too many stages"; return SDRPP_ERR_ARG; }
-    // capacities and slab layout
+    // capacities and slab layout. The stage-1 output (= input of the first tail stage, or the final output when
+    // there is no tail stage) is double-buffered so that the tail of block i can run concurrently with stage 1
+    // of block i+1; each region is [history pad | data].
     long long cap = p.s1_fir ? (max_block / p.s1_D + 2) : max_block;
     uint32_t off = 0;
-    for (auto& s : p.tail) {
+    {
+        const int hist0 = p.tail.empty() ? 1 : p.tail[0].T - 1;
+        if (hist0 > 2048) { *err = "filter longer than 2049 taps is not supported"; return SDRPP_ERR_ARG; }
+        const uint32_t hc = (uint32_t)((hist0 + 1) & ~1);
+        for (int r = 0; r < 2; r++) {
+            p.s1_off[r] = off + hc;
+            off = p.s1_off[r] + (uint32_t)((cap + 1) & ~1LL);
+        }
+    }
+    for (size_t i = 0; i < p.tail.size(); i++) {
+        TailPlanStage& s = p.tail[i];
         if (s.T - 1 > 2048) { *err = "filter longer than 2049 taps is not supported"; return SDRPP_ERR_ARG; }
-        const uint32_t hc = (uint32_t)((s.T - 1 + 1) & ~1);
-        s.in_off = off + hc;
+        if (i > 0) {
+            const uint32_t hc = (uint32_t)((s.T - 1 + 1) & ~1);
+            s.in_off = off + hc;
+            off = s.in_off + (uint32_t)((cap + 1) & ~1LL);
+        } else {
+            s.in_off = p.s1_off[0];
+        }
         s.cap_in = (int)cap;
-        off = s.in_off + (uint32_t)((cap + 1) & ~1LL);
         if (s.type == TAIL_DECFIR) cap = cap / s.D + 2;
         else if (s.type == TAIL_POLY) cap = cap * s.interp / s.D + 2;
     }
-    p.final_off = off + 2;
     p.cap_final = (int)cap;
-    p.slab_elems = (size_t)p.final_off + (size_t)((cap + 1) & ~1LL);
+    if (p.tail.empty()) {
+        p.final_off = p.s1_off[0];
+        p.slab_elems = off;
+    } else {
+        p.final_off = off + 2;
+        p.slab_elems = (size_t)p.final_off + (size_t)((cap + 1) & ~1LL);
+    }
     for (auto& s : p.tail) {
         if (dev_alloc(&s.d_taps, s.taps.size(), false) != cudaSuccess ||
             cudaMemcpy(s.d_taps, s.taps.data(), s.taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -192,7 +214,10 @@ struct sdrpp_cuda_frontend {
     int device = 0;
     sdrpp_cuda_frontend_cfg cfg{};
     double eff_sr = 0;
-    cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr;
+    cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft = nullptr, ev_tail[2] = { nullptr, nullptr };
+    bool ev_tail_valid[2] = { false, false };
+    long long blk = 0; // blocks processed (parity selects the stage-1 output region)
     long long launches = 0;
     std::string sticky;
 
@@ -534,6 +559,16 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     fe->abs_pos += n;
     fe->last_count = n;
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[1], st));
+    // Three consumers of the ring run concurrently (the reference's Splitter fan-out): the spectrum on st_fft,
+    // stage 1 on st, and the tail of the PREVIOUS block on st_tail. Profiling serialises everything on st so
+    // that per-family CUDA-event times are those of the kernels alone.
+    cudaStream_t sf = prof ? st : fe->st_fft;
+    cudaStream_t stl = prof ? st : fe->st_tail;
+    const int par = (int)(fe->blk & 1);
+    if (!prof) {
+        FE_TRY(fe, cudaEventRecord(fe->ev_ingest, st));
+        FE_TRY(fe, cudaStreamWaitEvent(sf, fe->ev_ingest, 0));
+    }
 
     // ---- spectrum frames completed by this block (reshaper.h:102-129 keep/skip + handler) --------
     rs.nrows = 0;
@@ -553,14 +588,18 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             a.nz = fe->nz; a.window = fe->d_window; a.inter = fe->d_inter;
             a.rows = fe->d_rows + (size_t)f0 * N; a.X = nullptr;
             a.frames = std::min(fe->inter_frames, frames - f0);
-            FE_TRY(fe, launch_spectrum(N, a, st, &fe->launches));
+            FE_TRY(fe, launch_spectrum(N, a, sf, &fe->launches));
         }
         rs.nrows = frames;
     }
+    if (fe->readback && rs.nrows > 0)
+        FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, sf));
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[2], st));
+    else FE_TRY(fe, cudaEventRecord(fe->ev_fft, sf));
 
     // ---- channelizer ----------------------------------------------------------------------------
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
+    if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
     std::vector<TailArgs> tails;
     std::vector<int> tail_totals;
     for (Group& g : fe->groups) {
@@ -570,7 +609,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         a.nvfo = (int)g.members.size();
         a.vfos = fe->d_vfos + g.first_dev;
         a.abs_valid = g.st.abs_valid;
-        a.out_off = p.tail.empty() ? p.final_off : p.tail[0].in_off;
+        a.out_off = p.s1_off[par];
         int nprev = 0;
         if (p.s1_fir) {
             int off = g.st.s1_offset;
@@ -604,7 +643,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         for (size_t s = 0; s < p.tail.size(); s++) {
             const TailPlanStage& ps = p.tail[s];
             TailStage& ts = tg.st[s];
-            ts.type = ps.type; ts.T = ps.T; ts.D = ps.D; ts.interp = ps.interp; ts.taps = ps.d_taps; ts.in_off = ps.in_off;
+            ts.type = ps.type; ts.T = ps.T; ts.D = ps.D; ts.interp = ps.interp; ts.taps = ps.d_taps;
+            ts.in_off = (s == 0) ? p.s1_off[par] : ps.in_off;
             ts.n_in = nprev; ts.offset = g.st.st_offset[s]; ts.phase = g.st.st_phase[s];
             int nout = 0;
             if (ps.type == TAIL_DECFIR) {
@@ -624,15 +664,21 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             ts.n_out = nout;
             nprev = nout;
         }
-        tg.final_off = p.final_off; tg.n_final = nprev; tg.demod = g.demod;
+        tg.final_off = p.tail.empty() ? p.s1_off[par] : p.final_off;
+        tg.carry0_off = p.s1_off[par ^ 1];
+        tg.n_final = nprev; tg.demod = g.demod;
         tg.inv_dev = (float)(1.0 / (2.0 * kPi * ((p.bw / 2.0) / p.outSR))); // quadrature.h:21-28 with dev = bw/2 (fm.h:31)
         tg.abs_out = g.st.abs_out;
         g.st.abs_out += nprev;
         g.last_n_final = nprev;
     }
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[3], st));
+    else {
+        FE_TRY(fe, cudaEventRecord(fe->ev_s1, st));
+        FE_TRY(fe, cudaStreamWaitEvent(stl, fe->ev_s1, 0));
+    }
     for (size_t i = 0; i < tails.size(); i++) {
-        FE_TRY(fe, launch_tail(tails[i], tail_totals[i], st));
+        FE_TRY(fe, launch_tail(tails[i], tail_totals[i], stl));
         if (tail_totals[i] > 0) fe->launches++;
     }
     if (prof) { FE_TRY(fe, cudaEventRecord(fe->pev[4], st)); fe->pev_valid = true; }
@@ -641,16 +687,20 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     rs.counts.assign(fe->vfos.size(), 0);
     for (const Group& g : fe->groups)
         for (int id : g.members) rs.counts[(size_t)id] = g.last_n_final;
-    if (fe->readback) {
-        if (fe->arena_used > 0) {
-            FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, st));
-            FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, st));
-        }
-        if (rs.nrows > 0)
-            FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (fe->readback && fe->arena_used > 0) {
+        FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, stl));
+        FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, stl));
     }
-    FE_TRY(fe, cudaEventRecord(rs.done, st));
+    if (!prof) {
+        FE_TRY(fe, cudaEventRecord(fe->ev_tail[par], stl));
+        fe->ev_tail_valid[par] = true;
+        FE_TRY(fe, cudaStreamWaitEvent(stl, fe->ev_fft, 0)); // the block is done when its rows are on the host too
+    } else {
+        fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;  // everything ran in order on st
+    }
+    FE_TRY(fe, cudaEventRecord(rs.done, stl));
     rs.pending = true;
+    fe->blk++;
     return SDRPP_OK;
 }
 
@@ -875,7 +925,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
     if (cudaSetDevice(fe->device) != cudaSuccess) return bail("cudaSetDevice failed");
     // ring: history for the longest filter + a whole spectrum frame + one block, rounded up
     {
-        long long need = (long long)fe->cfg.max_block * 2 + std::max(fe->cfg.fft_size, 0) * 2LL + 8192;
+        long long need = (long long)fe->cfg.max_block * 3 + std::max(fe->cfg.fft_size, 0) * 2LL + 8192;
         int lg = 16;
         while ((1LL << lg) < need) lg++;
         if (fe->cfg.ring_log2 > 0) lg = fe->cfg.ring_log2;
@@ -884,7 +934,14 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         fe->ring_mask = (uint32_t)((1u << lg) - 1u);
     }
     if (cudaStreamCreateWithFlags(&fe->st, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&fe->st_copy, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
+        cudaStreamCreateWithFlags(&fe->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_tail, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
+    if (cudaEventCreateWithFlags(&fe->ev_ingest, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_s1, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_fft, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
     if (dev_alloc(&fe->ring, (size_t)1 << fe->ring_log2) != cudaSuccess) return bail("ring allocation failed");
     fe->raw_cap = (size_t)fe->cfg.max_block * 8;
     for (int i = 0; i < 2; i++) {
@@ -907,6 +964,8 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     cudaSetDevice(fe->device);
     if (fe->st) cudaStreamSynchronize(fe->st);
     if (fe->st_copy) cudaStreamSynchronize(fe->st_copy);
+    if (fe->st_fft) cudaStreamSynchronize(fe->st_fft);
+    if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
     for (Vfo& v : fe->vfos) if (v.slab) cudaFree(v.slab);
     for (Group& g : fe->groups) if (g.d_G) cudaFree(g.d_G);
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
@@ -928,6 +987,9 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     for (int i = 0; i < 5; i++) if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
     if (fe->st) cudaStreamDestroy(fe->st);
     if (fe->st_copy) cudaStreamDestroy(fe->st_copy);
+    if (fe->st_fft) cudaStreamDestroy(fe->st_fft);
+    if (fe->st_tail) cudaStreamDestroy(fe->st_tail);
+    for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft, fe->ev_tail[0], fe->ev_tail[1] }) if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete fe;
     return SDRPP_OK;
@@ -938,6 +1000,9 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     if (rc != SDRPP_OK) return rc;
     FE_TRY(fe, cudaStreamSynchronize(fe->st_copy));
     FE_TRY(fe, cudaStreamSynchronize(fe->st));
+    FE_TRY(fe, cudaStreamSynchronize(fe->st_fft));
+    FE_TRY(fe, cudaStreamSynchronize(fe->st_tail));
+    fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;
     // everything submitted so far is complete: nothing is left to wait for
     for (int i = 0; i < 2; i++) fe->rs[i].pending = false;
     if (fe->seq > 0) { fe->waited = fe->seq; fe->cur = (int)((fe->seq - 1) & 1); }

@@ -106,6 +106,8 @@ struct TailGroup {
     int nstages;
     TailStage st[kTailMaxStages];
     uint32_t final_off;  // slab offset of the final output data area (one sample of history before it)
+    uint32_t carry0_off; // data-area offset of the OTHER stage-1 region: receives the history carry of stage 0
+                         // (or of the final output when there is no tail stage) for the next block
     int n_final;         // output samples this block
     int demod;
     float inv_dev;       // Quadrature: 1/(2*pi*dev/sr)
