@@ -83,20 +83,22 @@ __device__ __forceinline__ float2 phasor_u64(uint64_t phase) {
 // output live in up to two neighbouring warps and are combined through shared memory; a CTA
 // therefore computes 8*R rows for 8*R-(A-1) outputs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kS1PoolFloats = 4096;
+constexpr int kS1PoolFloats = 8192;
 __constant__ __align__(16) float c_s1_taps[kS1PoolFloats];
 
+// Pool entry: the plan's first FIR stored twice, zero-padded to A*D: at `off` as is, and at `off + A*D` with one
+// leading zero tap. The second form lets the filter window start one sample earlier, which keeps the sample
+// tile 16-byte aligned in the ring (a bulk-copy requirement) whatever the parity of the window start.
 struct S1PoolEntry { int ratio, off, T, D, A; };
 static std::vector<S1PoolEntry> g_s1_pool;
 static std::mutex g_s1_mtx;
 static bool g_s1_uploaded[64] = { false };
 
 bool stage1_supported(int A, int D) { return D >= 2 && (D & (D - 1)) == 0 && D <= 128 && A >= 2 && A <= 7; }
-int stage1_rows(int A) { return A <= 6 ? 6 : 6; }
-int stage1_outputs_per_cta(int A) { return kStage1Warps * stage1_rows(A) - (A - 1); }
+int stage1_A(int T, int D) { return ceil_div(T + 1, D); } // room for the optional leading zero tap
 
-// Build the padded tap pool (every PowerDecimator plan's first FIR, zero-padded to A*D) and upload
-// it to the current device's constant memory. Returns the pool offset for `ratio`, or -1.
+// Builds the tap pool (every PowerDecimator plan's first FIR) and uploads it to the current device's constant
+// memory. Returns the pool offset of the un-shifted taps for `ratio` (shifted form at +A*D), or -1.
 int stage1_tap_offset(int ratio) {
     std::lock_guard<std::mutex> lck(g_s1_mtx);
     if (g_s1_pool.empty()) {
@@ -104,10 +106,10 @@ int stage1_tap_offset(int ratio) {
         for (int k = 1; k <= 13; k++) {
             std::vector<DecimStage> st = decim_plan(1 << k);
             if (st.empty()) continue;
-            const int T = st[0].ntaps, D = st[0].decimation, A = ceil_div(T, D);
+            const int T = st[0].ntaps, D = st[0].decimation, A = stage1_A(T, D);
             if (!stage1_supported(A, D)) continue;
             g_s1_pool.push_back({ 1 << k, off, T, D, A });
-            off += A * D;
+            off += 2 * A * D;
         }
     }
     int dev = 0;
@@ -115,9 +117,12 @@ int stage1_tap_offset(int ratio) {
     if (!g_s1_uploaded[dev]) {
         std::vector<float> pool(kS1PoolFloats, 0.0f);
         for (const S1PoolEntry& e : g_s1_pool) {
-            if (e.off + e.A * e.D > kS1PoolFloats) return -1;
+            if (e.off + 2 * e.A * e.D > kS1PoolFloats) return -1;
             std::vector<DecimStage> st = decim_plan(e.ratio);
-            for (int k = 0; k < e.T; k++) pool[(size_t)(e.off + k)] = st[0].taps[k];
+            for (int k = 0; k < e.T; k++) {
+                pool[(size_t)(e.off + k)] = st[0].taps[k];
+                pool[(size_t)(e.off + e.A * e.D + 1 + k)] = st[0].taps[k];
+            }
         }
         if (cudaMemcpyToSymbol(c_s1_taps, pool.data(), sizeof(float) * kS1PoolFloats) != cudaSuccess) return -1;
         g_s1_uploaded[dev] = true;

@@ -82,7 +82,7 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
     }
     size_t first_tail = 0;
     if (!dst.empty()) {
-        const int D = dst[0].decimation, T = dst[0].ntaps, A = ceil_div(T, D);
+        const int D = dst[0].decimation, T = dst[0].ntaps, A = stage1_A(T, D);
         const int tap_off = stage1_supported(A, D) ? stage1_tap_offset(p.rp.predec) : -1;
         if (tap_off >= 0) {
             p.s1_fir = true; p.s1_D = D; p.s1_T = T; p.s1_A = A; p.s1_tap_off = tap_off;
@@ -616,9 +616,15 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             const int off0 = off;
             advance_decim(off, p.s1_D, n, &nprev);
             g.st.s1_offset = off;
-            a.D = p.s1_D; a.T = p.s1_T; a.A = p.s1_A; a.tap_off = p.s1_tap_off;
+            a.D = p.s1_D; a.A = p.s1_A;
             a.M = nprev; a.G = g.d_G;
             a.abs_first = abs_block - (p.s1_T - 1) + off0;
+            // keep the window start even (16-byte aligned in the ring): if it is odd, start one sample earlier
+            // and use the tap table with a leading zero
+            const int pad = (int)(a.abs_first & 1);
+            a.abs_first -= pad;
+            a.T = p.s1_T + pad;
+            a.tap_off = p.s1_tap_off + pad * p.s1_A * p.s1_D;
             a.ring_first = (uint32_t)((uint64_t)a.abs_first & fe->ring_mask);
             FE_TRY(fe, launch_stage1(a, st));
         } else {

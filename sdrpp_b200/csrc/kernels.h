@@ -72,15 +72,17 @@ struct Stage1Args {
     uint32_t ring_first;   // ring index of the first sample of the dot product of output 0
     int64_t abs_first;     // absolute index of that sample
     int64_t abs_valid;     // samples with absolute index < abs_valid read as zero (reset / stream start)
-    int D, T, A;           // decimation, taps, ceil(T/D)
-    int tap_off;           // offset of this plan's zero-padded taps in the constant tap pool
+    int D, T, A;           // decimation, taps (+1 when the shifted form is used), rows of the tap matrix
+    int tap_off;           // offset of this plan's zero-padded taps (plain or shifted form) in the constant tap pool
     int M;                 // outputs this block
+    int opc;               // outputs per CTA (set by the launcher)
     int nvfo;              // VFOs in the group
     const float4* G;       // per-VFO phasor table F[p] = e^{j w p}: [vb][p/2][lane] = (F[p], F[p+1])
     const VfoDev* vfos;    // group members, contiguous
     uint32_t out_off;      // slab offset (in float2) where output 0 goes
 };
 bool stage1_supported(int A, int D);
+int stage1_A(int T, int D);                                // rows of the tap matrix, ceil((T+1)/D)
 int stage1_tap_offset(int ratio);                          // also uploads the pool to the current device
 size_t stage1_g_elems(int A, int D, int nvfo);          // float4 elements of G
 void stage1_g_index(int A, int D, int v, int p, size_t* idx4, int* half); // where F[p] of VFO v lives
