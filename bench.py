@@ -238,6 +238,7 @@ def run_gpu(args, rank, world, local_rank):
     cuda.init(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     vf_all = vfo_list()
@@ -375,21 +376,35 @@ def run_gpu(args, rank, world, local_rank):
             pin_t = torch.from_numpy(pin.array.view(np.float32).reshape(BLOCK, 2))
 
         def step_e2e(i):
-            buf = d_stage[i % 2]
+            k = i % 2
+            buf = d_stage[k]
+            cur = torch.cuda.current_stream()
+            if consumed[k] is not None:
+                cur.wait_event(consumed[k])
             if rank == 0:
-                buf.copy_(pin_t, non_blocking=True)
+                buf.copy_(pin_t, non_blocking=True)   # H2D from pinned host memory, every step
             dist.broadcast(buf, src=0)
-            ev = torch.cuda.Event(); ev.record(torch.cuda.current_stream()); st.wait_event(ev)
+            ev = torch.cuda.Event(); ev.record(cur); st.wait_event(ev)
             fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
-            fe.wait()
-            ev2 = torch.cuda.Event(); ev2.record(st); torch.cuda.current_stream().wait_event(ev2)
+            consumed[k] = torch.cuda.Event(); consumed[k].record(st)
+
+        sink = 0.0
+
+        def consume():
+            nonlocal sink
+            fe.wait()                                  # results of the oldest outstanding block are on the host
+            iq, _ = fe.vfo_output(ids[0], copy=False)
+            sink += float(iq[0].real) if len(iq) else 0.0
 
         for i in range(args.warmup):
-            step_e2e(i)
+            step_e2e(i); consume()
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        step_e2e(0)
+        for i in range(1, args.steps):
             step_e2e(i)
+            consume()
+        consume()
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -412,11 +427,20 @@ def run_gpu(args, rank, world, local_rank):
         peak_src = "MEASURED_PEAKS.json (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         model = algorithmic_model(mine)
         s1_ms, fft_ms, tail_ms, ingest_ms = fam[2], fam[1], fam[3], fam[0]
-        chan_bytes = model["chan_bytes_per_sample"] * BLOCK
+        # per launch: the block read once (8 B/sample) + that group's outputs; a step has one launch per VFO class
+        n_s1_launches = len({(v[0], v[1], v[3]) for v in mine})
+        chan_bytes = (8.0 * n_s1_launches + (model["chan_bytes_per_sample"] - 8.0)) * BLOCK
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
+            traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for name, k in tj.items() if "stage1_kernel" in name)
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": "stage1_kernel (NCO folded into the first decimating FIR; both VFO-class launches of a step)",
                 "achieved": chan_bytes / (s1_ms * 1e-3) / 1e9 if s1_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (chan_bytes / (s1_ms * 1e-3) / 1e9 / hbm_peak) if s1_ms > 0 else None, "traffic": None,
-                "peak_source": peak_src, "ms_per_step": float(s1_ms),
+                "frac": (chan_bytes / (s1_ms * 1e-3) / 1e9 / hbm_peak) if s1_ms > 0 else None, "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write summed over the step's stage-1 launches, ncu --set full at N=1 (profiles/r1_traffic.json)",
+                "peak_source": peak_src, "ms_per_step": float(s1_ms), "launches_per_step": n_s1_launches,
                 "algorithmic_bytes_per_step": chan_bytes,
                 "note": "minimal-bytes accounting (8 B/sample in + outputs, SURVEY 8d); this kernel is FP32-FMA-bound, see fp32"}
         sm_clk = (clk or {}).get("sm_mhz") or 1965.0
