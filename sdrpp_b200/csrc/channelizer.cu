@@ -326,25 +326,54 @@ cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st) {
 // One CTA per VFO; stages run back to back on the VFO's slab (L2-resident), __syncthreads between.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTailThreads = 256;
-constexpr int kTailSmemSamples = 6144; // staged input samples per chunk (48 KB)
+// 36 KB samples + 4 KB slack + 12 KB taps = 52 KB: four CTAs per SM, so 512 VFOs are a single wave on 148 SMs
+constexpr int kTailSmemSamples = 4608; // staged input samples per chunk
+constexpr int kTailTapFloats = 3072;   // staged taps per stage
 
 // Stage one chunk of a stage's input [first, first+n) from the slab (L2) into shared memory.
 // Decimating FIRs store it transposed by D -- element i at [i % D][i / D] with an odd row stride -- so
 // that consecutive outputs (lanes) read consecutive addresses for every tap; others keep natural order.
 __device__ __forceinline__ void tail_stage_in(float2* sm, const float2* src, int n, int D, int qs) {
-    if (D > 1) {
-        for (int i = threadIdx.x; i < n; i += kTailThreads) {
-            const int q = i / D, p = i - q * D;
-            sm[p * qs + q] = src[i];
+    // 4 independent loads in flight per thread before the (transposing) stores: the loop is L2-latency-bound
+    constexpr int U = 4;
+    const int lg = 31 - __clz(D); // D is a power of two (every PowerDecimator stage decimates by 2, 4, 8, ...)
+    int i = threadIdx.x;
+    for (; i + (U - 1) * kTailThreads < n; i += U * kTailThreads) {
+        float2 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = src[i + u * kTailThreads];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int j = i + u * kTailThreads;
+            sm[(j & (D - 1)) * qs + (j >> lg)] = v[u];
         }
-    } else {
-        for (int i = threadIdx.x; i < n; i += kTailThreads) sm[i] = src[i];
+    }
+    for (; i < n; i += kTailThreads) sm[(i & (D - 1)) * qs + (i >> lg)] = src[i];
+}
+
+// dot product of n complex samples (stride 1) with n real taps; taps 16-byte aligned
+__device__ __forceinline__ void tail_dot(const float2* __restrict__ x, const float* __restrict__ h, int n, float& re, float& im) {
+    int k = 0;
+    for (; k + 4 <= n; k += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(h + k);
+        const float2 v0 = x[k], v1 = x[k + 1], v2 = x[k + 2], v3 = x[k + 3];
+        re = fmaf(v0.x, t.x, re); im = fmaf(v0.y, t.x, im);
+        re = fmaf(v1.x, t.y, re); im = fmaf(v1.y, t.y, im);
+        re = fmaf(v2.x, t.z, re); im = fmaf(v2.y, t.z, im);
+        re = fmaf(v3.x, t.w, re); im = fmaf(v3.y, t.w, im);
+    }
+    for (; k < n; k++) {
+        const float2 v = x[k];
+        const float t = h[k];
+        re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
     }
 }
 
 __global__ void __launch_bounds__(kTailThreads)
 tail_kernel(const __grid_constant__ TailArgs a) {
-    extern __shared__ __align__(16) float2 tsm[];
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    float* ttaps = reinterpret_cast<float*>(tail_smem);                           // [kTailTapFloats]
+    float2* tsm = reinterpret_cast<float2*>(tail_smem + kTailTapFloats * 4);      // staged samples
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
     const TailGroup& g = a.g[gi];
@@ -359,6 +388,25 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         float2* out = slab + ((s + 1 < g.nstages) ? g.st[s + 1].in_off : g.final_off);
         const bool poly = st.type == TAIL_POLY;
         const int D = poly ? 1 : st.D; // layout stride (polyphase reads ~consecutive samples)
+        // taps into shared memory: natural order (FIR), [p][aa] rows of AA4 floats (decimating FIR, so that the
+        // taps of one polyphase row are contiguous like the transposed samples), or the whole polyphase bank
+        const int AA = (T + D - 1) / D, AA4 = (AA + 3) & ~3;
+        bool taps_staged = true;
+        if (poly) {
+            taps_staged = (long long)st.interp * T <= kTailTapFloats;
+            if (taps_staged) for (int i = tid; i < st.interp * T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
+        } else if (D == 1) {
+            taps_staged = T <= kTailTapFloats;
+            if (taps_staged) for (int i = tid; i < T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
+        } else {
+            taps_staged = D * AA4 <= kTailTapFloats;
+            if (taps_staged) {
+                for (int i = tid; i < D * AA4; i += kTailThreads) {
+                    const int p = i / AA4, aa = i - p * AA4, k = aa * D + p;
+                    ttaps[i] = (aa < AA && k < T) ? __ldg(st.taps + k) : 0.0f;
+                }
+            }
+        }
         // outputs per chunk so that the inputs they need fit the staging buffer
         int ch;
         if (poly) ch = (int)(((long long)(kTailSmemSamples - T - 2) * st.interp) / st.D);
@@ -386,40 +434,42 @@ tail_kernel(const __grid_constant__ TailArgs a) {
                 if (poly) {
                     const long long P = (long long)st.phase + (long long)o * st.D;
                     const float2* x = tsm + (st.offset + (int)(P / st.interp) - first);
-                    const float* taps = st.taps + (size_t)(P % st.interp) * T;
-                    for (int k = 0; k < T; k++) {
-                        const float2 v = x[k];
-                        const float h = __ldg(taps + k);
-                        re = fmaf(v.x, h, re);
-                        im = fmaf(v.y, h, im);
-                    }
-                } else if (D == 1) {
-                    const float2* x = tsm + (o - o0);
-                    for (int k = 0; k < T; k++) {
-                        const float2 v = x[k];
-                        const float h = __ldg(st.taps + k);
-                        re = fmaf(v.x, h, re);
-                        im = fmaf(v.y, h, im);
-                    }
-                } else {
-                    // tap k = aa*D + p reads staged element [p][(o-o0) + aa]
-                    const float2* x = tsm + (o - o0);
-                    for (int p = 0; p < D; p++) {
-                        const float2* xp = x + p * qs;
-                        int aa = 0;
-                        for (int k = p; k < T; k += D, aa++) {
-                            const float2 v = xp[aa];
-                            const float h = __ldg(st.taps + k);
-                            re = fmaf(v.x, h, re);
-                            im = fmaf(v.y, h, im);
+                    const int ph = (int)(P % st.interp);
+                    if (taps_staged) {
+                        const float* h = ttaps + ph * T; // rows are not 16-byte aligned in general
+                        for (int k = 0; k < T; k++) {
+                            const float2 v = x[k];
+                            const float t = h[k];
+                            re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
+                        }
+                    } else {
+                        const float* h = st.taps + (size_t)ph * T;
+                        for (int k = 0; k < T; k++) {
+                            const float2 v = x[k];
+                            const float t = __ldg(h + k);
+                            re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
                         }
                     }
+                } else if (!taps_staged) {
+                    // very long filter: taps from L1/L2 (never the case for the reference's plans)
+                    const float2* x = tsm + (o - o0);
+                    for (int k = 0; k < T; k++) {
+                        const int q = k / D, p = k - q * D;
+                        const float2 v = (D == 1) ? x[k] : x[p * qs + q];
+                        const float t = __ldg(st.taps + k);
+                        re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
+                    }
+                } else if (D == 1) {
+                    tail_dot(tsm + (o - o0), ttaps, T, re, im);
+                } else {
+                    // tap k = aa*D + p reads staged element [p][(o-o0) + aa]; row p has ceil((T-p)/D) taps
+                    const float2* x = tsm + (o - o0);
+                    for (int p = 0; p < D; p++) tail_dot(x + p * qs, ttaps + p * AA4, (T - p + D - 1) / D, re, im);
                 }
                 out[o] = make_float2(re, im);
             }
             __syncthreads();
         }
-        // carry the last `hist` inputs to the front (fir.h:80, decimating_fir.h:65, polyphase_resampler.h:96)
         // Stage 0 reads the double-buffered stage-1 region, so its history goes to the OTHER region (always, even
         // for an empty block); later stages shift in place.
         if (s == 0 || st.n_in > 0) {
@@ -465,7 +515,7 @@ tail_kernel(const __grid_constant__ TailArgs a) {
 
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {
     if (total_vfos <= 0) return cudaSuccess;
-    const size_t smem = (size_t)(kTailSmemSamples + 512) * sizeof(float2);
+    const size_t smem = (size_t)kTailTapFloats * sizeof(float) + (size_t)(kTailSmemSamples + 512) * sizeof(float2);
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
