@@ -119,9 +119,15 @@ int stage1_tap_offset(int ratio) {
         for (const S1PoolEntry& e : g_s1_pool) {
             if (e.off + 2 * e.A * e.D > kS1PoolFloats) return -1;
             std::vector<DecimStage> st = decim_plan(e.ratio);
+            // stored pair-major: [pp][aa] = (h[aa*D+2pp], h[aa*D+2pp+1]), so the A tap pairs one sample pair needs
+            // are contiguous in the constant bank (one address computation, immediate offsets per tap)
+            auto put = [&](int base, int k, float v) {
+                const int aa = k / e.D, p = k % e.D;
+                pool[(size_t)(base + ((p >> 1) * e.A + aa) * 2 + (p & 1))] = v;
+            };
             for (int k = 0; k < e.T; k++) {
-                pool[(size_t)(e.off + k)] = st[0].taps[k];
-                pool[(size_t)(e.off + e.A * e.D + 1 + k)] = st[0].taps[k];
+                put(e.off, k, st[0].taps[k]);
+                put(e.off + e.A * e.D, k + 1, st[0].taps[k]);
             }
         }
         if (cudaMemcpyToSymbol(c_s1_taps, pool.data(), sizeof(float) * kS1PoolFloats) != cudaSuccess) return -1;
@@ -213,7 +219,7 @@ stage1_kernel(const __grid_constant__ Stage1Args a) {
 #pragma unroll
         for (int aa = 0; aa < A; aa++) {
             if (aa == A - 1 && !last_slab) continue; // only zero padding here
-            const float2 h = taps2[aa * DP + pp];
+            const float2 h = taps2[pp * A + aa];
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 vr[r][aa] = fmaf(h.x, w0r[r], vr[r][aa]);
