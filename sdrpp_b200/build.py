@@ -27,7 +27,7 @@ FLAGS = [
     "--expt-relaxed-constexpr",
     # device code may contract to FMA (fp32 tolerance applies); conversions use explicit _rn intrinsics
     "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("SDRPP_EXTRA_NVCC", "").split()  # experiment knob, e.g. "-DSDRPP_S1_R=4 -DSDRPP_S1_W=12"
 
 
 def _gen_blob_inc():

@@ -147,11 +147,10 @@ void stage1_g_index(int A, int D, int v, int p, size_t* idx4, int* half) {
     *half = p & 1;
 }
 
-template <int A, int R>
-__global__ void __launch_bounds__(kStage1Warps * 32, 2)
+template <int A, int R, int W>
+__global__ void __launch_bounds__(W * 32, 2)
 stage1_kernel(const __grid_constant__ Stage1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int W = kStage1Warps;
     constexpr int ROWS = W * R;              // rows of D samples per CTA
     constexpr int OUT = ROWS - (A - 1);      // complete outputs per CTA
     constexpr int NP = R + A - 1;            // partial outputs a thread contributes to
@@ -276,33 +275,38 @@ stage1_kernel(const __grid_constant__ Stage1Args a) {
     }
 }
 
-template <int A, int R>
+template <int A, int R, int W>
 static cudaError_t launch_stage1_t(const Stage1Args& a, cudaStream_t st) {
-    constexpr int ROWS = kStage1Warps * R, OUT = ROWS - (A - 1), NP = R + A - 1;
+    constexpr int ROWS = W * R, OUT = ROWS - (A - 1), NP = R + A - 1;
     const size_t tile = (size_t)ROWS * a.D * sizeof(float2);
-    const size_t parts = (size_t)kStage1Warps * NP * 32 * sizeof(float2);
+    const size_t parts = (size_t)W * NP * 32 * sizeof(float2);
     const size_t smem = 128 + (size_t)(a.D / 2) * 32 * 16 + (tile > parts ? tile : parts);
     static size_t attr_set = 0;
     if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A, R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
     dim3 grid(ceil_div(a.M, OUT), ceil_div(a.nvfo, 32));
-    stage1_kernel<A, R><<<grid, kStage1Warps * 32, smem, st>>>(a);
+    stage1_kernel<A, R, W><<<grid, W * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
+
+#ifndef SDRPP_S1_R
+#define SDRPP_S1_R 6
+#define SDRPP_S1_W 8
+#endif
 
 cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st) {
     if (a.M <= 0 || a.nvfo <= 0) return cudaSuccess;
     if (a.tap_off < 0) return cudaErrorInvalidValue;
     switch (a.A) {
-    case 2: return launch_stage1_t<2, 6>(a, st);
-    case 3: return launch_stage1_t<3, 6>(a, st);
-    case 4: return launch_stage1_t<4, 6>(a, st);
-    case 5: return launch_stage1_t<5, 6>(a, st);
-    case 6: return launch_stage1_t<6, 6>(a, st);
-    case 7: return launch_stage1_t<7, 6>(a, st);
+    case 2: return launch_stage1_t<2, SDRPP_S1_R, SDRPP_S1_W>(a, st);
+    case 3: return launch_stage1_t<3, SDRPP_S1_R, SDRPP_S1_W>(a, st);
+    case 4: return launch_stage1_t<4, SDRPP_S1_R, SDRPP_S1_W>(a, st);
+    case 5: return launch_stage1_t<5, SDRPP_S1_R, SDRPP_S1_W>(a, st);
+    case 6: return launch_stage1_t<6, SDRPP_S1_R, SDRPP_S1_W>(a, st);
+    case 7: return launch_stage1_t<7, SDRPP_S1_R, SDRPP_S1_W>(a, st);
     }
     return cudaErrorInvalidValue;
 }
