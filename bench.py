@@ -97,56 +97,73 @@ def algorithmic_model(vfos):
 # clocks sampling during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread
+    (the timed region is tens of milliseconds, too short for `nvidia-smi -lms`), nvidia-smi as a fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = False
+        self.th = None
+        self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.idx)
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for name, b in bits.items():
+                    if r & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._pump, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.nvml = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+        if self.nvml is not None and self.th is not None:
+            self.stop_flag = True
+            self.th.join(timeout=1.0)
+            if self.samples:
+                return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                        "samples": len(self.samples), "source": "nvml, 2 ms poll during the timed region"}
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().splitlines()[0]
+            p = [x.strip() for x in out.split(",")]
+            reasons = [nm for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]) if v.lower().startswith("active")]
+            return {"sm_mhz": float(p[1]), "sm_max_mhz": float(p[2]), "reasons": reasons, "samples": 1, "source": "nvidia-smi right after the timed region"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            p = [s.strip() for s in ln.split(",")]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 # ---------------------------------------------------------------------------------------------
 # CPU reference arm / baseline: the reference's own dsp/ headers (oracle/_ref, release flags)
 # ---------------------------------------------------------------------------------------------
+_CPU_CACHE = {}
+
+
 def cpu_reference(nblocks=2, sample_vfos=None, fft_frames=1):
     """Times the reference's CPU implementation of the path on a bounded sample of the workload:
     `sample_vfos` of the 512 VFOs (thread-per-VFO multiplexed on all host cores, as
@@ -165,7 +182,9 @@ def cpu_reference(nblocks=2, sample_vfos=None, fft_frames=1):
     if sample_vfos is None:
         sample_vfos = min(NVFO, 2 * cores)
     pick = [vf[(i * NVFO) // sample_vfos] for i in range(sample_vfos)]
-    blocks = make_blocks(2, seed=5).reshape(-1)  # 1,228,800 samples >= one spectrum frame
+    if "blocks" not in _CPU_CACHE:
+        _CPU_CACHE["blocks"] = make_blocks(2, seed=5).reshape(-1)  # 1,228,800 samples >= one spectrum frame
+    blocks = _CPU_CACHE["blocks"]
     if lib is not None:
         win = lib.window(po.WIN_BH4, FFT_N)
         # the block handed to every VFO thread is the first BLOCK samples; the spectrum thread reads FFT_N
@@ -483,8 +502,8 @@ def run_gpu(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--input-blocks", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
