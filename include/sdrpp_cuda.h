@@ -45,7 +45,10 @@ enum {
     SDRPP_FMT_I8 = 3,        /* volk_8i_s32f_convert_32f(..,128.0f): source_modules/hackrf_source/src/main.cpp:386 */
     SDRPP_FMT_I16_FILE = 4,  /* (i16+0.5f)/(32768.0f-0.5f): source_modules/file_source/src/main.cpp:506 */
     SDRPP_FMT_I16_VOLK = 5,  /* volk_16i_s32f_convert_32f(..,32768): bladerf_source/src/main.cpp:587, plutosdr_source/src/main.cpp:261-265 */
-    SDRPP_FMT_COUNT = 6
+    SDRPP_FMT_I24_FILE = 6,  /* packed LE 24-bit, (i24+0.5f)/(8388608.0f-0.5f): source_modules/file_source/src/main.cpp:525 */
+    SDRPP_FMT_I32_FILE = 7,  /* (float)((i32+0.5)/(2147483648.0-0.5)): source_modules/file_source/src/main.cpp:542 */
+    SDRPP_FMT_F64 = 8,       /* volk_64f_convert_32f: source_modules/file_source/src/main.cpp:475 */
+    SDRPP_FMT_COUNT = 9
 };
 
 /* dsp::window::windowType (dsp/window/window.h:28-36) -- persisted as an int in the config */

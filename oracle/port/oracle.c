@@ -39,6 +39,9 @@ enum {
     ORC_FMT_I8 = 3,       /* volk_8i_s32f_convert_32f(.., 128.0f): hackrf_source/src/main.cpp:386 */
     ORC_FMT_I16_FILE = 4, /* source_modules/file_source/src/main.cpp:506 */
     ORC_FMT_I16_VOLK = 5, /* volk_16i_s32f_convert_32f(.., 32768): bladerf main.cpp:587, plutosdr main.cpp:261-265 */
+    ORC_FMT_I24_FILE = 6, /* source_modules/file_source/src/main.cpp:521-527 (packed little-endian 24 bit) */
+    ORC_FMT_I32_FILE = 7, /* source_modules/file_source/src/main.cpp:538-544 */
+    ORC_FMT_F64 = 8,      /* volk_64f_convert_32f, source_modules/file_source/src/main.cpp:470-476 */
 };
 
 API int orc_convert(int fmt, const void* in, int nscalars, float* out) {
@@ -71,6 +74,24 @@ API int orc_convert(int fmt, const void* in, int nscalars, float* out) {
     case ORC_FMT_I16_VOLK: {
         const int16_t* p = (const int16_t*)in;
         for (i = 0; i < nscalars; i++) out[i] = (float)p[i] / 32768.0f;
+        return 0;
+    }
+    case ORC_FMT_I24_FILE: {
+        const uint8_t* p = (const uint8_t*)in;
+        for (i = 0; i < nscalars; i++, p += 3) {
+            int32_t i24 = (int32_t)(((uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16)) << 8) >> 8;
+            out[i] = (i24 + 0.5f) / (8388608.0f - 0.5f);
+        }
+        return 0;
+    }
+    case ORC_FMT_I32_FILE: {
+        const int32_t* p = (const int32_t*)in;
+        for (i = 0; i < nscalars; i++) out[i] = (float)((p[i] + 0.5) / (2147483648.0 - 0.5));
+        return 0;
+    }
+    case ORC_FMT_F64: {
+        const double* p = (const double*)in;
+        for (i = 0; i < nscalars; i++) out[i] = (float)p[i];
         return 0;
     }
     }

@@ -20,7 +20,7 @@ _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
 _fp = C.POINTER(C.c_float)
 
 # input sample formats (same numbering as include/sdrpp_cuda.h)
-FMT_CF32, FMT_U8_RTL, FMT_U8_TCP, FMT_I8, FMT_I16_FILE, FMT_I16_VOLK = range(6)
+FMT_CF32, FMT_U8_RTL, FMT_U8_TCP, FMT_I8, FMT_I16_FILE, FMT_I16_VOLK, FMT_I24_FILE, FMT_I32_FILE, FMT_F64 = range(9)
 # window types, dsp/window/window.h:28-36
 WIN_RECT, WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_NUTTALL, WIN_BH4, WIN_BH7 = range(7)
 # demod front ends
@@ -238,7 +238,7 @@ class Port(_Base):
 
     def convert(self, fmt, raw):
         raw = np.ascontiguousarray(raw)
-        n = raw.size if fmt != FMT_CF32 else raw.size * 2
+        n = raw.size * 2 if fmt == FMT_CF32 else (raw.size // 3 if fmt == FMT_I24_FILE else raw.size)
         out = np.zeros(n, dtype=np.float32)
         rc = self._f("convert", _i, _i, _vp, _i, _vp)(fmt, _ptr(raw), n, _ptr(out))
         if rc != 0:

@@ -35,6 +35,8 @@ __device__ __forceinline__ float cvt_i16_file(int v) {
     return __fdiv_rn(__fadd_rn((float)v, 0.5f), 32767.5f);
 }
 __device__ __forceinline__ float cvt_i16_volk(int v) { return __fdiv_rn((float)v, 32768.0f); }
+__device__ __forceinline__ float cvt_i24_file(int v) { return __fdiv_rn(__fadd_rn((float)v, 0.5f), 8388607.5f); }
+__device__ __forceinline__ float cvt_i32_file(int v) { return (float)__ddiv_rn(__dadd_rn((double)v, 0.5), 2147483647.5); }
 
 // Load one complex sample of input format FMT at sample index i and convert it.
 template <int FMT>
@@ -47,14 +49,26 @@ __device__ __forceinline__ float2 load_sample(const void* __restrict__ base, siz
     } else if constexpr (FMT == 3) {
         const char2 v = __ldg(reinterpret_cast<const char2*>(base) + i);
         return make_float2(cvt_i8(v.x), cvt_i8(v.y));
-    } else {
+    } else if constexpr (FMT == 4 || FMT == 5) {
         const short2 v = __ldg(reinterpret_cast<const short2*>(base) + i);
         return FMT == 4 ? make_float2(cvt_i16_file(v.x), cvt_i16_file(v.y)) : make_float2(cvt_i16_volk(v.x), cvt_i16_volk(v.y));
+    } else if constexpr (FMT == 6) {
+        // packed little-endian 24-bit, sign-extended like ((b0 | b1<<8 | b2<<16) << 8) >> 8
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(base) + 6 * i;
+        const int re = ((int)((unsigned)__ldg(b) | ((unsigned)__ldg(b + 1) << 8) | ((unsigned)__ldg(b + 2) << 16)) << 8) >> 8;
+        const int im = ((int)((unsigned)__ldg(b + 3) | ((unsigned)__ldg(b + 4) << 8) | ((unsigned)__ldg(b + 5) << 16)) << 8) >> 8;
+        return make_float2(cvt_i24_file(re), cvt_i24_file(im));
+    } else if constexpr (FMT == 7) {
+        const int2 v = __ldg(reinterpret_cast<const int2*>(base) + i);
+        return make_float2(cvt_i32_file(v.x), cvt_i32_file(v.y));
+    } else {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(base) + i);
+        return make_float2((float)v.x, (float)v.y);
     }
 }
 
 __host__ __device__ constexpr int fmt_bytes_per_sample(int fmt) {
-    return fmt == 0 ? 8 : (fmt == 1 || fmt == 2 || fmt == 3) ? 2 : 4;
+    return fmt == 0 ? 8 : (fmt == 1 || fmt == 2 || fmt == 3) ? 2 : (fmt == 4 || fmt == 5) ? 4 : fmt == 6 ? 6 : fmt == 7 ? 8 : 16;
 }
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {

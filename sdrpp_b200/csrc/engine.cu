@@ -949,7 +949,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
     if (dev_alloc(&fe->ring, (size_t)1 << fe->ring_log2) != cudaSuccess) return bail("ring allocation failed");
-    fe->raw_cap = (size_t)fe->cfg.max_block * 8;
+    fe->raw_cap = (size_t)fe->cfg.max_block * 16; // widest input format: complex f64
     for (int i = 0; i < 2; i++) {
         if (cudaMallocHost(&fe->h_stage[i], fe->raw_cap) != cudaSuccess) return bail("pinned staging allocation failed");
         if (cudaMalloc(&fe->d_raw[i], fe->raw_cap) != cudaSuccess) return bail("raw buffer allocation failed");

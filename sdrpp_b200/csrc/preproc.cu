@@ -23,7 +23,7 @@ ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos
     const int nquads = count >> 2;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
         float2 s[4];
-        if (vec_ok) {
+        if (vec_ok && FMT <= 5) {
             if constexpr (FMT == 0) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(raw) + 2 * q);
                 const float4 b = __ldg(reinterpret_cast<const float4*>(raw) + 2 * q + 1);
@@ -45,7 +45,7 @@ ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos
                                    (int)(signed char)((w.y >> 16) & 255u), (int)(signed char)(w.y >> 24) };
 #pragma unroll
                 for (int i = 0; i < 4; i++) s[i] = make_float2(cvt_i8(b[2 * i]), cvt_i8(b[2 * i + 1]));
-            } else {
+            } else if constexpr (FMT == 4 || FMT == 5) {
                 const uint4 w = __ldg(reinterpret_cast<const uint4*>(raw) + q);
                 const unsigned int u[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
@@ -63,7 +63,7 @@ ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos
             for (int i = 0; i < 4; i++) s[i].y = -s[i].y;
         }
         const uint32_t i0 = (pos + 4u * (uint32_t)q) & dst.mask;
-        if ((i0 & 1u) == 0 && i0 + 3u <= dst.mask && dst.mask != 0xFFFFFFFFu) {
+        if ((i0 & 1u) == 0 && i0 <= dst.mask - 3u) {
             float4* o = reinterpret_cast<float4*>(dst.base + i0);
             o[0] = make_float4(s[0].x, s[0].y, s[1].x, s[1].y);
             o[1] = make_float4(s[2].x, s[2].y, s[3].x, s[3].y);
@@ -95,6 +95,9 @@ cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint
     case 3: ingest_kernel<3><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
     case 4: ingest_kernel<4><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
     case 5: ingest_kernel<5><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
+    case 6: ingest_kernel<6><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false); break;
+    case 7: ingest_kernel<7><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false); break;
+    case 8: ingest_kernel<8><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();

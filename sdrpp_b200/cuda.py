@@ -11,13 +11,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsdrpp_cuda.so")
 
-FMT_CF32, FMT_U8_RTL, FMT_U8_TCP, FMT_I8, FMT_I16_FILE, FMT_I16_VOLK = range(6)
+FMT_CF32, FMT_U8_RTL, FMT_U8_TCP, FMT_I8, FMT_I16_FILE, FMT_I16_VOLK, FMT_I24_FILE, FMT_I32_FILE, FMT_F64 = range(9)
 WIN_RECT, WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_NUTTALL, WIN_BH4, WIN_BH7 = range(7)
 DEMOD_NONE, DEMOD_QUAD, DEMOD_AM, DEMOD_USB, DEMOD_LSB, DEMOD_DSB = range(6)
 
 FMT_DTYPE = {FMT_CF32: np.complex64, FMT_U8_RTL: np.uint8, FMT_U8_TCP: np.uint8, FMT_I8: np.int8,
-             FMT_I16_FILE: np.int16, FMT_I16_VOLK: np.int16}
-FMT_BYTES = {FMT_CF32: 8, FMT_U8_RTL: 2, FMT_U8_TCP: 2, FMT_I8: 2, FMT_I16_FILE: 4, FMT_I16_VOLK: 4}
+             FMT_I16_FILE: np.int16, FMT_I16_VOLK: np.int16, FMT_I24_FILE: np.uint8, FMT_I32_FILE: np.int32, FMT_F64: np.float64}
+FMT_BYTES = {FMT_CF32: 8, FMT_U8_RTL: 2, FMT_U8_TCP: 2, FMT_I8: 2, FMT_I16_FILE: 4, FMT_I16_VOLK: 4, FMT_I24_FILE: 6, FMT_I32_FILE: 8, FMT_F64: 16}
 
 # every symbol include/sdrpp_cuda.h declares (checked by tests/test_abi.py)
 SYMBOLS = """
@@ -164,7 +164,7 @@ def design_reshape(sr, size, rate):
 # ---- one-shot block operations -----------------------------------------------------------------
 def _raw(fmt, a):
     a = np.ascontiguousarray(a, dtype=FMT_DTYPE[fmt])
-    n = a.size if fmt == FMT_CF32 else a.size // 2
+    n = a.size if fmt == FMT_CF32 else (a.size // 6 if fmt == FMT_I24_FILE else a.size // 2)
     return a, n
 
 

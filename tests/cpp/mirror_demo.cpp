@@ -45,17 +45,23 @@ static int hostSelfTest() {
     d.start();
     d.start(); // idempotent
     double sum = 0;
+    std::atomic<int> consumed{0};
     std::thread reader([&] {
         for (int b = 0; b < 50; b++) {
             int n = d.out.read();
             if (n < 0) { return; }
             for (int i = 0; i < n; i++) { sum += d.out.readBuf[i]; }
             d.out.flush();
+            consumed++;
         }
     });
     for (int b = 0; b < 50; b++) {
         for (int i = 0; i < 100; i++) { src.writeBuf[i] = (float)(b + i); }
-        if (b == 20) { d.tempStop(); d.tempStop(); d.tempStart(); d.tempStart(); } // nested pause
+        if (b == 20) {
+            // nested pause while the pipeline is idle (a block in flight during a stop is dropped, as in the reference)
+            while (consumed.load() < b) { std::this_thread::yield(); }
+            d.tempStop(); d.tempStop(); d.tempStart(); d.tempStart();
+        }
         if (!src.swap(100)) { return 2; }
     }
     reader.join();

@@ -56,6 +56,39 @@ def test_random_blocks(gpu, port, fmt, n):
     assert np.array_equal(_bits(out), _bits(port.convert(fmt, raw)))
 
 
+def _raw_wide(fmt, n, rng):
+    if fmt == po.FMT_I24_FILE:
+        v = rng.integers(-(1 << 23), 1 << 23, 2 * n).astype(np.int32)
+        v[:4] = [-(1 << 23), (1 << 23) - 1, 0, -1]
+        return np.stack([(v & 255), (v >> 8) & 255, (v >> 16) & 255], axis=1).astype(np.uint8).reshape(-1)
+    if fmt == po.FMT_I32_FILE:
+        v = rng.integers(-(1 << 31), 1 << 31, 2 * n).astype(np.int32)
+        v[:4] = [-(1 << 31), (1 << 31) - 1, 0, -1]
+        return v
+    v = rng.standard_normal(2 * n) * 10.0 ** rng.uniform(-8, 2, 2 * n)
+    v[:4] = [0.0, -0.0, 1.0 + 2.0 ** -24, 3.4e38]
+    return v.astype(np.float64)
+
+
+@pytest.mark.parametrize("fmt", [po.FMT_I24_FILE, po.FMT_I32_FILE, po.FMT_F64])
+@pytest.mark.parametrize("n", [2, 5, 7936, 100003])
+def test_wide_file_formats(gpu, port, fmt, n):
+    """WAV i24 / i32 / f64 (file_source/src/main.cpp:470-545): SURVEY 8f rank 3."""
+    raw = _raw_wide(fmt, n, np.random.default_rng(7 * fmt + n))
+    out = gpu.convert(fmt, raw)
+    assert len(out) == n
+    assert np.array_equal(_bits(out), _bits(port.convert(fmt, raw)))
+
+
+def test_wide_format_through_frontend(gpu, port):
+    n = 4096
+    raw = _raw_wide(po.FMT_I24_FILE, n, np.random.default_rng(3))
+    with gpu.Frontend(2.4e6, max_block=n) as fe:
+        fe.process(po.FMT_I24_FILE, raw)
+        iq = fe.read_iq(n)
+    assert np.array_equal(_bits(iq), _bits(port.convert(po.FMT_I24_FILE, raw)))
+
+
 def test_empty_and_bad_args(gpu):
     assert len(gpu.convert(po.FMT_U8_RTL, np.zeros(0, np.uint8))) == 0
     with pytest.raises(gpu.SdrppCudaError):
