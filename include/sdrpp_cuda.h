@@ -107,6 +107,12 @@ SDRPP_API int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf
 SDRPP_API int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* window,
                                   float* row, sdrpp_cf32* X);
 
+/* Waterfall zoom / max-decimation of one dB row to outSize pixels: fft_scaler(viewOffset, viewBandwidth,
+ * wholeBandwidth, N, outSize).doZoom (gui/widgets/fft_scaler.h:28-64, used by WaterFall::pushFFT,
+ * gui/widgets/waterfall.cpp:900-904). idx (optional, outSize+1 ints) receives the bin boundaries. */
+SDRPP_API int sdrpp_cuda_fft_zoom(int N, const float* row, double viewOffset, double viewBandwidth,
+                                  double wholeBandwidth, int outSize, float* out, int* idx);
+
 /* ---------------------------------------------------------------------------------------------
  * Front end: the device-resident signal path (sigpath::iqFrontEnd + sigpath::vfoManager's
  * dsp::channel::RxVFO set + demod front ends) of one GPU.
@@ -172,6 +178,13 @@ SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrp
 /* Spectrum rows completed in this block (each fft_size floats, the buffer handed to
  * acquireFFTBuffer/releaseFFTBuffer in the reference): returns the row count. */
 SDRPP_API int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows);
+/* Zoomed rows on the device: every spectrum row is also reduced to outSize pixels for the given view
+ * (outSize = 0 disables). keep_raw = 0 stops the device->host copy of the full rows (4 B x fft_size per row),
+ * leaving 4 B x outSize per row -- what the waterfall widget draws and the scanner module reads. */
+SDRPP_API int sdrpp_cuda_frontend_set_fft_zoom(sdrpp_cuda_frontend* fe, double viewOffset, double viewBandwidth,
+                                               double wholeBandwidth, int outSize, int keep_raw);
+/* Zoomed rows completed in the last waited block (each outSize floats): returns the row count. */
+SDRPP_API int sdrpp_cuda_fft_zoomed_rows(sdrpp_cuda_frontend* fe, const float** rows);
 /* The post-preprocessing IQ block as the Splitter would hand it to bound streams
  * (IQFrontEnd::bindIQStream, signal_path/iq_frontend.cpp:114-116; recorder tap). Copies up to cap
  * samples of the last block to `out` (device->host); returns the count. */

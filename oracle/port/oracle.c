@@ -638,4 +638,44 @@ API int orc_spectrum(int N, int nz, const cf32* frame, const float* window, floa
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* 8f rank 2. Waterfall zoom / max-decimation: gui/widgets/fft_scaler.h:28-64                   */
+/* idx (optional, outSize+1 ints) receives the bin boundaries i0..i_outSize for index parity.   */
+/* ------------------------------------------------------------------------------------------ */
+API void orc_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandwidth, int fftSize, int outSize,
+                      const float* data, float* out, int* idx) {
+    const double offsetRatio = viewOffset / (wholeBandwidth / 2.0);
+    double width = (viewBandwidth / wholeBandwidth) * fftSize;
+    double offset = (((double)fftSize / 2.0) * (offsetRatio + 1)) - (width / 2);
+    double factor, f0;
+    int i, j;
+    if (offset < 0) offset = 0;
+    if (width > fftSize - offset) width = fftSize - offset;
+    factor = width / outSize;
+    f0 = offset;
+    if (factor <= 1.0) {
+        for (i = 0; i < outSize; i++) {
+            int i0 = (int)roundf((float)f0);
+            if (idx) idx[i] = i0;
+            if (out) out[i] = data[i0];
+            f0 = f0 + factor;
+        }
+        if (idx) idx[outSize] = -1; /* point sampling: no range */
+    } else {
+        int i0 = (int)roundf((float)f0);
+        for (i = 0; i < outSize; i++) {
+            double f1 = f0 + factor;
+            int i1 = (int)roundf((float)f1);
+            if (idx) idx[i] = i0;
+            if (out) {
+                float m = data[i0];
+                for (j = i0 + 1; j < i1; j++) m = (m < data[j]) ? data[j] : m; /* std::max(a,b) = (a<b)?b:a */
+                out[i] = m;
+            }
+            f0 = f1; i0 = i1;
+        }
+        if (idx) idx[outSize] = i0;
+    }
+}
+
 API const char* orc_build_info(void) { return "oracle port: plain-C restatement, IEEE fp32, generic-VOLK semantics"; }

@@ -223,6 +223,19 @@ class _Base:
         return row32, X64, row64
 
 
+def _zoom(fn, view_offset, view_bw, whole_bw, row, out_size, with_idx):
+    row = np.ascontiguousarray(row, dtype=np.float32)
+    n = len(row)
+    data = np.concatenate([row, np.zeros(1, np.float32)])   # doZoom may touch data[fftSize]
+    out = np.zeros(out_size, dtype=np.float32)
+    if with_idx:
+        idx = np.zeros(out_size + 1, dtype=np.int32)
+        fn(view_offset, view_bw, whole_bw, n, out_size, _ptr(data), _ptr(out), _ptr(idx))
+        return out, idx
+    fn(view_offset, view_bw, whole_bw, n, out_size, _ptr(data), _ptr(out))
+    return out
+
+
 class Port(_Base):
     """Plain-C restatement (oracle/port/oracle.c)."""
     prefix = "orc"
@@ -244,6 +257,10 @@ class Port(_Base):
         if rc != 0:
             raise ValueError("bad format")
         return out.view(cf32)
+
+    def fft_zoom(self, view_offset, view_bw, whole_bw, row, out_size):
+        """fft_scaler::doZoom; returns (pixels, bin boundaries)."""
+        return _zoom(self._f("fft_zoom", None, _d, _d, _d, _i, _i, _vp, _vp, _vp), view_offset, view_bw, whole_bw, row, out_size, True)
 
     def reshape_params(self, sr, size, rate):
         skip, nz = _i(), _i()
@@ -270,6 +287,9 @@ class Ref(_Base):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle ref` where /root/reference exists")
         self.lib = C.CDLL(path)
         self.flavour = flavour
+
+    def fft_zoom(self, view_offset, view_bw, whole_bw, row, out_size):
+        return _zoom(self._f("fft_zoom", None, _d, _d, _d, _i, _i, _vp, _vp), view_offset, view_bw, whole_bw, row, out_size, False)
 
     def resampler_info(self, obj):
         info = (_i * 6)()

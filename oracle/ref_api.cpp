@@ -23,6 +23,7 @@
 #include <dsp/demod/quadrature.h>
 #include <dsp/math/conjugate.h>
 #include <dsp/convert/complex_to_real.h>
+#include <gui/widgets/fft_scaler.h>
 
 #include <vector>
 #include <thread>
@@ -372,6 +373,14 @@ API double ref_bench_channelizer(double inSR, int nvfo, const double* outSR, con
         if (c.ssb) delete c.ssb;
     }
     return dt;
+}
+
+// fft_scaler (gui/widgets/fft_scaler.h:21-65): the waterfall's zoom / max-decimation of one raw row, as
+// WaterFall::pushFFT applies it (gui/widgets/waterfall.cpp:900-904). data must hold fftSize+1 floats.
+API void ref_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandwidth, int fftSize, int outSize,
+                      const float* data, float* out) {
+    fft_scaler sc(viewOffset, viewBandwidth, wholeBandwidth, (size_t)fftSize, (size_t)outSize);
+    sc.doZoom(data, out);
 }
 
 API const char* ref_build_info() {

@@ -180,6 +180,33 @@ void reshape_params(double sampleRate, int size, double rate, int* skip, int* nz
     *skip = interval - *nz;
 }
 
+bool zoom_indices(double viewOffset, double viewBandwidth, double wholeBandwidth, int fftSize, int outSize, std::vector<int>* idx) {
+    // the running sum f0 += factor is kept in double and rounded through float exactly as doZoom does, so the
+    // bin boundaries are the reference's own
+    const double offsetRatio = viewOffset / (wholeBandwidth / 2.0);
+    double width = (viewBandwidth / wholeBandwidth) * fftSize;
+    double offset = (((double)fftSize / 2.0) * (offsetRatio + 1)) - (width / 2);
+    if (offset < 0) offset = 0;
+    if (width > fftSize - offset) width = fftSize - offset;
+    const double factor = width / outSize;
+    idx->assign((size_t)outSize + 1, 0);
+    double f0 = offset;
+    if (factor <= 1.0) {
+        for (int i = 0; i < outSize; i++) { (*idx)[(size_t)i] = (int)roundf((float)f0); f0 = f0 + factor; }
+        (*idx)[(size_t)outSize] = -1;
+        return false;
+    }
+    int i0 = (int)roundf((float)f0);
+    for (int i = 0; i < outSize; i++) {
+        const double f1 = f0 + factor;
+        (*idx)[(size_t)i] = i0;
+        i0 = (int)roundf((float)f1);
+        f0 = f1;
+    }
+    (*idx)[(size_t)outSize] = i0;
+    return true;
+}
+
 void xlator_increment(double offsetHz, double sampleRate, float* inc_re, float* inc_im, double* turns_eff) {
     const double w = 2.0 * kPi * (offsetHz / sampleRate); // math/hz_to_rads.h:6-8
     const float re = (float)cos(w), im = (float)sin(w);   // frequency_xlator.h:17-19

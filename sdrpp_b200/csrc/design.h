@@ -43,6 +43,10 @@ std::vector<float> build_polyphase_bank(const std::vector<float>& taps, int inte
 // IQFrontEnd::genReshapeParams (signal_path/iq_frontend.h:56-60)
 void reshape_params(double sampleRate, int size, double rate, int* skip, int* nz);
 
+// fft_scaler (gui/widgets/fft_scaler.h:28-64): bin boundaries of the waterfall zoom / max-decimation.
+// idx has outSize+1 entries; pixel i covers bins [idx[i], max(idx[i]+1, idx[i+1])) when ranged, bin idx[i] otherwise.
+bool zoom_indices(double viewOffset, double viewBandwidth, double wholeBandwidth, int fftSize, int outSize, std::vector<int>* idx);
+
 // FrequencyXlator increment (dsp/channel/frequency_xlator.h:15-23): the fp32-quantised phasor
 // (cos w, sin w) and the frequency it actually realises, in turns per sample.
 void xlator_increment(double offsetHz, double sampleRate, float* inc_re, float* inc_im, double* turns_eff);

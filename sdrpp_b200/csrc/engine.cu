@@ -200,6 +200,7 @@ struct ResultSet {
     sdrpp_cf32* iq = nullptr;
     float* demod = nullptr;
     float* rows = nullptr;
+    float* zoom = nullptr;
     int nrows = 0;
     std::vector<int> counts; // per VFO id
     cudaEvent_t done = nullptr;
@@ -247,6 +248,10 @@ struct sdrpp_cuda_frontend {
     float2* d_inter = nullptr; int inter_frames = 0;
     float* d_rows = nullptr; int rows_cap = 0;
     int64_t fft_next = 0;
+    // waterfall zoom (fft_scaler): bin boundaries on the device, zoomed rows beside the raw rows
+    int zoom_out = 0; bool zoom_ranged = false, zoom_keep_raw = true;
+    double zoom_view[3] = { 0, 0, 0 };
+    int* d_zoom_idx = nullptr; float* d_zoom = nullptr;
 
     // VFOs
     std::vector<Vfo> vfos;
@@ -320,6 +325,20 @@ static int configure_preproc(sdrpp_cuda_frontend* fe) {
     return SDRPP_OK;
 }
 
+static int configure_zoom(sdrpp_cuda_frontend* fe) {
+    if (fe->d_zoom_idx) { cudaFree(fe->d_zoom_idx); fe->d_zoom_idx = nullptr; }
+    if (fe->d_zoom) { cudaFree(fe->d_zoom); fe->d_zoom = nullptr; }
+    for (int i = 0; i < 2; i++) if (fe->rs[i].zoom) { cudaFreeHost(fe->rs[i].zoom); fe->rs[i].zoom = nullptr; }
+    if (fe->zoom_out <= 0 || fe->cfg.fft_size <= 0 || fe->rows_cap <= 0) return SDRPP_OK;
+    std::vector<int> idx;
+    fe->zoom_ranged = zoom_indices(fe->zoom_view[0], fe->zoom_view[1], fe->zoom_view[2], fe->cfg.fft_size, fe->zoom_out, &idx);
+    FE_TRY(fe, dev_alloc(&fe->d_zoom_idx, idx.size(), false));
+    FE_TRY(fe, cudaMemcpy(fe->d_zoom_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    FE_TRY(fe, dev_alloc(&fe->d_zoom, (size_t)fe->rows_cap * fe->zoom_out, false));
+    for (int i = 0; i < 2; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].zoom, (size_t)fe->rows_cap * fe->zoom_out * sizeof(float)));
+    return SDRPP_OK;
+}
+
 // ---- spectrum configuration (IQFrontEnd::updateFFTPath / updateFFTSize) ------------------------
 static int configure_fft(sdrpp_cuda_frontend* fe) {
     if (fe->d_window) { cudaFree(fe->d_window); fe->d_window = nullptr; }
@@ -355,7 +374,7 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     for (int i = 0; i < 2; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].rows, (size_t)rows * N * sizeof(float)));
     fe->rs_rows_cap = rows;
     fe->fft_next = fe->abs_pos;
-    return SDRPP_OK;
+    return configure_zoom(fe);
 }
 
 // ---- VFO layout ------------------------------------------------------------------------------
@@ -592,7 +611,13 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         rs.nrows = frames;
     }
-    if (fe->readback && rs.nrows > 0)
+    if (rs.nrows > 0 && fe->zoom_out > 0) {
+        FE_TRY(fe, launch_fft_zoom(fe->d_rows, fe->cfg.fft_size, rs.nrows, fe->d_zoom_idx, fe->zoom_out, fe->zoom_ranged, fe->d_zoom, sf));
+        fe->launches++;
+        if (fe->readback)
+            FE_TRY(fe, cudaMemcpyAsync(rs.zoom, fe->d_zoom, (size_t)rs.nrows * fe->zoom_out * sizeof(float), cudaMemcpyDeviceToHost, sf));
+    }
+    if (fe->readback && rs.nrows > 0 && (fe->zoom_keep_raw || fe->zoom_out <= 0))
         FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, sf));
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[2], st));
     else FE_TRY(fe, cudaEventRecord(fe->ev_fft, sf));
@@ -910,6 +935,26 @@ int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* 
     return SDRPP_OK;
 }
 
+int sdrpp_cuda_fft_zoom(int N, const float* row, double viewOffset, double viewBandwidth, double wholeBandwidth, int outSize,
+                        float* out, int* idx_out) {
+    if (N < 1 || !row || outSize < 1 || !(viewBandwidth > 0) || !(wholeBandwidth > 0) || !out) return fail(SDRPP_ERR_ARG, "bad argument");
+    std::vector<int> idx;
+    const bool ranged = zoom_indices(viewOffset, viewBandwidth, wholeBandwidth, N, outSize, &idx);
+    if (idx_out) memcpy(idx_out, idx.data(), idx.size() * sizeof(int));
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, (size_t)N * 4));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, idx.size() * 4));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, (size_t)outSize * 4));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, row, (size_t)N * 4, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_b, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(launch_fft_zoom((const float*)g_os.d_a, N, 1, (const int*)g_os.d_b, outSize, ranged, (float*)g_os.d_c, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_c, (size_t)outSize * 4, cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    return SDRPP_OK;
+}
+
 // ---- front end ---------------------------------------------------------------------------------
 sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* cfg) {
     if (!cfg) { set_last_error("null cfg"); return nullptr; }
@@ -979,6 +1024,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     for (float2* b : fe->fe_buf) cudaFree(b);
     cudaFree(fe->dc_in); cudaFree(fe->dc_state); cudaFree(fe->dc_scratch);
     cudaFree(fe->ring); cudaFree(fe->d_window); cudaFree(fe->d_inter); cudaFree(fe->d_rows);
+    cudaFree(fe->d_zoom_idx); cudaFree(fe->d_zoom);
     cudaFree(fe->d_vfos); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod);
     for (int i = 0; i < 2; i++) {
         if (fe->h_stage[i]) cudaFreeHost(fe->h_stage[i]);
@@ -989,6 +1035,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
         if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
         if (fe->rs[i].rows) cudaFreeHost(fe->rs[i].rows);
+        if (fe->rs[i].zoom) cudaFreeHost(fe->rs[i].zoom);
     }
     for (int i = 0; i < 5; i++) if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
     if (fe->st) cudaStreamDestroy(fe->st);
@@ -1243,6 +1290,24 @@ int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows) {
     const ResultSet& rs = fe->rs[fe->cur];
     if (rows) *rows = rs.rows;
     return rs.nrows;
+}
+
+int sdrpp_cuda_frontend_set_fft_zoom(sdrpp_cuda_frontend* fe, double viewOffset, double viewBandwidth, double wholeBandwidth,
+                                     int outSize, int keep_raw) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (outSize < 0 || outSize > (1 << 20) || (outSize > 0 && (!(viewBandwidth > 0) || !(wholeBandwidth > 0)))) return fail(SDRPP_ERR_ARG, "bad zoom view");
+    fe->zoom_out = outSize; fe->zoom_keep_raw = keep_raw != 0;
+    fe->zoom_view[0] = viewOffset; fe->zoom_view[1] = viewBandwidth; fe->zoom_view[2] = wholeBandwidth;
+    return configure_zoom(fe);
+}
+
+int sdrpp_cuda_fft_zoomed_rows(sdrpp_cuda_frontend* fe, const float** rows) {
+    if (!fe) return fail(SDRPP_ERR_ARG, "null front end");
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    const ResultSet& rs = fe->rs[fe->cur];
+    if (rows) *rows = rs.zoom;
+    return (fe->zoom_out > 0 && rs.zoom) ? rs.nrows : 0;
 }
 
 int sdrpp_cuda_frontend_read_iq(sdrpp_cuda_frontend* fe, sdrpp_cf32* out, int cap) {

@@ -230,6 +230,35 @@ static cudaError_t launch_rows(const SpectrumArgs& a, const SpectrumTables& tabs
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Waterfall zoom: one warp per output pixel, lanes stride over the pixel's bin range, shuffle max.
+// std::max(a, b) = (a < b) ? b : a, so a NaN bin never replaces the running maximum (as in doZoom).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fft_zoom_kernel(const float* __restrict__ rows, int N, const int* __restrict__ idx, int outSize, bool ranged, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int px = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (px >= outSize) return;
+    const float* __restrict__ row = rows + (size_t)blockIdx.y * N;
+    int i0 = idx[px];
+    i0 = max(0, min(N - 1, i0));
+    float m = row[i0];
+    if (ranged) {
+        const int i1 = min(N, idx[px + 1]);
+        for (int j = i0 + 1 + lane; j < i1; j += 32) { const float v = row[j]; m = (m < v) ? v : m; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float v = __shfl_xor_sync(0xffffffffu, m, o); m = (m < v) ? v : m; }
+    }
+    if (lane == 0) out[(size_t)blockIdx.y * outSize + px] = m;
+}
+
+cudaError_t launch_fft_zoom(const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out, cudaStream_t st) {
+    if (nrows <= 0 || outSize <= 0) return cudaSuccess;
+    dim3 grid(ceil_div(outSize, 8), nrows);
+    fft_zoom_kernel<<<grid, 256, 0, st>>>(rows, N, idx, outSize, ranged, out);
+    return cudaGetLastError();
+}
+
 int spectrum_split(int N, int* N1, int* N2) {
     int lg = 0;
     while ((1 << lg) < N) lg++;

@@ -49,6 +49,10 @@ struct SpectrumArgs {
 int spectrum_split(int N, int* N1, int* N2);
 cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long long* launches);
 
+// Waterfall zoom / max-decimation of dB rows (gui/widgets/fft_scaler.h:41-64): out[r][i] = max over bins
+// [idx[i], idx[i+1]) (ranged) or rows[r][idx[i]] (point sampling). Reads are clamped to the row.
+cudaError_t launch_fft_zoom(const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // Channelizer (channelizer.cu)
 // ---------------------------------------------------------------------------------------------

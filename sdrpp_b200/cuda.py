@@ -32,7 +32,7 @@ sdrpp_cuda_vfo_set_bandwidth sdrpp_cuda_vfo_set_out_samplerate sdrpp_cuda_vfo_re
 sdrpp_cuda_frontend_submit sdrpp_cuda_frontend_submit_device sdrpp_cuda_frontend_wait
 sdrpp_cuda_frontend_set_readback sdrpp_cuda_vfo_output sdrpp_cuda_fft_rows sdrpp_cuda_frontend_read_iq
 sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_profiling
-sdrpp_cuda_frontend_kernel_ms
+sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -71,6 +71,9 @@ def lib():
         L.sdrpp_cuda_design_reshape.restype = None
         L.sdrpp_cuda_convert.argtypes = [_i, _vp, _i, _vp]
         L.sdrpp_cuda_spectrum.argtypes = [_i, _i, _i, _vp, _vp, _vp, _vp]
+        L.sdrpp_cuda_fft_zoom.argtypes = [_i, _vp, _d, _d, _d, _i, _vp, _vp]
+        L.sdrpp_cuda_frontend_set_fft_zoom.argtypes = [_vp, _d, _d, _d, _i, _i]
+        L.sdrpp_cuda_fft_zoomed_rows.argtypes = [_vp, C.POINTER(_vp)]
         L.sdrpp_cuda_frontend_create.restype = _vp
         L.sdrpp_cuda_frontend_create.argtypes = [C.POINTER(FrontendCfg)]
         L.sdrpp_cuda_frontend_destroy.argtypes = [_vp]
@@ -185,6 +188,15 @@ def spectrum(N, frame, window, fmt=FMT_CF32, want_X=False):
     _check(lib().sdrpp_cuda_spectrum(N, nz, fmt, _ptr(frame), _ptr(window), _ptr(row), _ptr(X) if want_X else None),
            "sdrpp_cuda_spectrum")
     return (row, X) if want_X else row
+
+
+def fft_zoom(row, view_offset, view_bw, whole_bw, out_size):
+    """fft_scaler::doZoom on the GPU; returns (pixels, bin boundaries)."""
+    row = np.ascontiguousarray(row, dtype=np.float32)
+    out = np.zeros(out_size, dtype=np.float32)
+    idx = np.zeros(out_size + 1, dtype=np.int32)
+    _check(lib().sdrpp_cuda_fft_zoom(len(row), _ptr(row), view_offset, view_bw, whole_bw, out_size, _ptr(out), _ptr(idx)), "sdrpp_cuda_fft_zoom")
+    return out, idx
 
 
 # ---- pinned host buffers -----------------------------------------------------------------------
@@ -322,6 +334,18 @@ class Frontend:
         if n == 0:
             return np.zeros((0, self.fft_size), np.float32)
         a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, self.fft_size))
+        return a.copy() if copy else a
+
+    def set_fft_zoom(self, view_offset, view_bw, whole_bw, out_size, keep_raw=True):
+        _check(lib().sdrpp_cuda_frontend_set_fft_zoom(self.h, view_offset, view_bw, whole_bw, out_size, int(keep_raw)), "set_fft_zoom")
+        self.zoom_out = out_size
+
+    def fft_zoomed_rows(self, copy=True):
+        p = _vp()
+        n = _check(lib().sdrpp_cuda_fft_zoomed_rows(self.h, C.byref(p)), "fft_zoomed_rows")
+        if n == 0:
+            return np.zeros((0, getattr(self, "zoom_out", 0)), np.float32)
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, self.zoom_out))
         return a.copy() if copy else a
 
     def read_iq(self, cap):

@@ -134,3 +134,34 @@ def test_low_noise_floor_scatter(gpu, port):
     g = np.abs(row.astype(np.float64) - row64); r = np.abs(row32.astype(np.float64) - row64)
     for q in (99.0, 99.9):
         assert np.percentile(g, q) <= max(SCATTER_X * np.percentile(r, q), TOL_DB), (q, np.percentile(g, q), np.percentile(r, q))
+
+
+ZOOM_CASES = [(65536, 1024, 0.0, 2.4e6, 2.4e6), (65536, 1600, 3e5, 4e5, 2.4e6), (1048576, 1917, -2e7, 3.3e7, 122.88e6),
+              (1024, 2000, 0.0, 2.4e6, 2.4e6), (8192, 777, 1.1e6, 2.4e5, 2.4e6), (8192, 500, -1.19e6, 1e5, 2.4e6)]
+
+
+@pytest.mark.parametrize("N,out,vo,vb,wb", ZOOM_CASES)
+def test_waterfall_zoom(gpu, port, N, out, vo, vb, wb):
+    """fft_scaler::doZoom (SURVEY 8f rank 2): bin boundaries and pixel values bit-exact."""
+    rng = np.random.default_rng(N + out)
+    row = (rng.standard_normal(N) * 10.0 - 80.0).astype(np.float32)
+    ref, ridx = port.fft_zoom(vo, vb, wb, row, out)
+    got, gidx = gpu.fft_zoom(row, vo, vb, wb, out)
+    assert np.array_equal(gidx, ridx)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+
+
+def test_frontend_zoomed_rows(gpu, port):
+    sr, N, blk, W = 2.4e6, 8192, 12000, 1000
+    x = _frame(blk * 3, 9)
+    with gpu.Frontend(sr, fft_size=N, fft_rate=sr / N, fft_window=po.WIN_BH4, max_block=blk) as fe:
+        fe.set_fft_zoom(2e5, 1.2e6, sr, W, keep_raw=True)
+        raw, zoomed = [], []
+        for b in range(3):
+            fe.process(po.FMT_CF32, x[b * blk:(b + 1) * blk])
+            raw.append(fe.fft_rows()); zoomed.append(fe.fft_zoomed_rows())
+        raw, zoomed = np.concatenate(raw), np.concatenate(zoomed)
+    assert raw.shape == (4, N) and zoomed.shape == (4, W)
+    for r in range(4):
+        ref, _ = port.fft_zoom(2e5, 1.2e6, sr, raw[r], W)
+        assert np.array_equal(zoomed[r].view(np.uint32), ref.view(np.uint32))

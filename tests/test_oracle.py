@@ -135,6 +135,12 @@ def test_port_matches_golden(port, case):
         pd, dc = port.powerdecim(ratio), port.dcblock(50.0 / (61.44e6 / ratio))
         y = port.conjugate(dc.process(pd.process(x)))
         assert np.array_equal(_bits(y), _bits(data["out"]))
+    elif kind == "zoom":
+        N, out, vo, vb, wb = case["args"]
+        rng = np.random.default_rng(case["seed"])
+        row = (rng.standard_normal(int(N)) * 10.0 - 80.0).astype(np.float32)
+        got, _ = port.fft_zoom(vo, vb, wb, row, int(out))
+        assert np.array_equal(_bits(got), _bits(data["out"]))
     else:
         pytest.fail("unknown golden kind " + kind)
 

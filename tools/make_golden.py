@@ -67,6 +67,12 @@ def main():
     y = ref.conjugate(dc.process(pd.process(x)))
     add("frontend_x4_dc_conj", "frontend", (4,), {"out": y}, n=len(x), seed=7)
 
+    # waterfall zoom (fft_scaler.h is self-contained, so the reference header itself generates these)
+    for name, N, out, vo, vb, wb, seed in [("zoom_1m_max", 1048576, 1917, -2e7, 3.3e7, 122.88e6, 8), ("zoom_1k_point", 1024, 2000, 0.0, 2.4e6, 2.4e6, 9)]:
+        rng = np.random.default_rng(seed)
+        row = (rng.standard_normal(N) * 10.0 - 80.0).astype(np.float32)
+        add("fft_" + name, "zoom", (N, out, vo, vb, wb), {"out": ref.fft_zoom(vo, vb, wb, row, out)}, seed=seed)
+
     json.dump({"generator": "tools/make_golden.py", "source": ref.lib.ref_build_info.restype and "oracle/_ref/libsdrpp_ref.so (reference dsp/ headers, IEEE flags)",
                "cases": cases}, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
     print("wrote", len(cases), "cases;", sum(os.path.getsize(os.path.join(GOLD, c["file"])) for c in cases) // 1024, "KiB")
