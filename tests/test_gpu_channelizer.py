@@ -216,3 +216,66 @@ def test_frontend_decimation_int16_dc_conj(gpu, port):
                 assert len(g) == len(r)
                 if b > 1 and len(r):
                     assert po.rel_rms(g, r) <= 3e-5
+
+
+# every PowerDecimator ratio as a first stage, the no-predecimation modes and an interpolating resampler
+EXTRA_PLANS = [
+    (48e3, 48e3, 48e3, 4800),        # NONE: translation only, no filter (bw == outSR)
+    (48e3, 48e3, 12.5e3, 4800),      # NONE + channel filter
+    (48e3, 96e3, 96e3, 4801),        # RESAMP_ONLY, interpolating
+    (1.0e6, 300e3, 200e3, 5000),     # ratio 2: first FIR 69 taps /2 is not a stage-1 shape -> translation + tail
+    (2.4e6, 500e3, 400e3, 12000),    # ratio 4: first FIR 12 taps /2
+    (4.0e6, 300e3, 250e3, 20000),    # ratio 8
+    (8.0e6, 300e3, 250e3, 40000),    # ratio 16
+    (10.0e6, 200e3, 150e3, 50000),   # ratio 32
+    (30.72e6, 200e3, 150e3, 153600), # ratio 128
+    (30.72e6, 100e3, 50e3, 153600),  # ratio 256
+    (61.44e6, 48e3, 12.5e3, 307200), # ratio 1024
+    (122.88e6, 12e3, 6e3, 614400),   # ratio 8192
+]
+
+
+@pytest.mark.parametrize("inSR,outSR,bw,blk", EXTRA_PLANS)
+def test_all_plan_shapes(gpu, port, inSR, outSR, bw, blk):
+    off = 0.0371 * inSR
+    nblocks = 3
+    x = synth.baseband(blk * nblocks, inSR, 17, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    for offset, aligned in ((0.0, False), (off, True)):
+        g = run_gpu(gpu, inSR, [(outSR, bw, offset, po.DEMOD_NONE)], blocks)[0]
+        r = run_oracle(port, inSR, (outSR, bw, offset, po.DEMOD_NONE), blocks)
+        assert [len(a) for a, _ in g] == [len(a) for a, _ in r]
+        ga = np.concatenate([a for a, _ in g]); ra = np.concatenate([a for a, _ in r])
+        if not aligned:
+            assert po.rel_rms(ga, ra) <= TOL, f"offset 0: {po.rel_rms(ga, ra):.3e}"
+        else:
+            for b in range(nblocks):
+                if len(r[b][0]) >= 8:
+                    res, _ = po.aligned_rel_rms(g[b][0], r[b][0])
+                    assert res <= 5e-5, f"block {b}: {res:.3e}"
+
+
+def test_max_block_and_cfg3_spectrum(gpu, port):
+    """1,000,000-sample blocks (the reference's stream buffer limit) and the cfg3 spectrum shape:
+    20 MS/s at 20 lines/s -> interval 1e6, nz = 1e6 < N = 1M (zero padded)."""
+    sr, blk, N = 20e6, 1000000, 1 << 20
+    x = synth.baseband(blk * 2, sr, 23, carriers=[(3.1e6, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    with gpu.Frontend(sr, fft_size=N, fft_rate=20.0, fft_window=po.WIN_BH7, max_block=blk) as fe:
+        vid = fe.add_vfo(250e3, 200e3, 3.1e6, po.DEMOD_QUAD)
+        orc = port.rxvfo(sr, 250e3, 200e3, 3.1e6)
+        rows = []
+        for b in range(2):
+            fe.process(po.FMT_CF32, x[b * blk:(b + 1) * blk])
+            rows.append(fe.fft_rows())
+            y, _ = fe.vfo_output(vid)
+            ref = orc.process(x[b * blk:(b + 1) * blk])
+            assert len(y) == len(ref) == 12500
+            res, _ = po.aligned_rel_rms(y, ref)
+            assert res <= 1e-4, res   # 1e6 input samples per block: the reference rotator's own walk (SURVEY C.2)
+        rows = np.concatenate(rows)
+    assert rows.shape == (2, N)
+    skip, nz = port.reshape_params(sr, N, 20.0)
+    assert (skip, nz) == (0, 1000000)
+    _, _, row64 = port.spectrum(N, x[:nz], port.window(po.WIN_BH7, nz))
+    mask = row64 >= row64.max() - 80.0
+    assert np.abs(rows[0] - row64)[mask].max() <= 0.01
