@@ -264,7 +264,10 @@ def run_gpu(args, rank, world, local_rank):
     # shard the VFO set across ranks, balanced by per-VFO cost (sdrpp_b200/shard.py); no data-path collective
     from sdrpp_b200 import shard
     costs = [shard.vfo_cost(SR, v[0], v[1], cuda.design_resampler, cuda.design_decim_plan) for v in vf_all]
-    mine = [vf_all[i] for i in shard.shard_vfos(costs, world)[rank]]
+    # rank 0 also ingests, broadcasts and runs the 1M-point spectrum (~25 us per step); at the measured
+    # ~32 ns per cost unit of stage 1 (0.256 ms for 512 VFOs x 15.4) that is ~770 units of VFO work it cannot take
+    base = [770.0] + [0.0] * (world - 1) if world > 1 else None
+    mine = [vf_all[i] for i in shard.shard_vfos(costs, world, base)[rank]]
     with_fft = (rank == 0)
     fe = cuda.Frontend(SR, fft_size=FFT_N if with_fft else 0, fft_rate=SR / FFT_N, fft_window=cuda.WIN_BH4, max_block=BLOCK)
     ids = [fe.add_vfo(*v) for v in mine]

@@ -43,6 +43,8 @@ static cudaError_t dev_alloc(T** p, size_t n, bool zero = true) {
 // ---------------------------------------------------------------------------------------------
 // VFO plan: the stage list RxVFO::init would build for (inSR, outSR, bw)
 // ---------------------------------------------------------------------------------------------
+constexpr int kChanHistPad = 2048; // history pad of a channel FIR stage (taps - 1 <= 2048)
+
 struct TailPlanStage {
     int type = TAIL_FIR, T = 1, D = 1, interp = 1;
     std::vector<float> taps; // FIR taps or polyphase bank
@@ -122,8 +124,9 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
     uint32_t off = 0;
     {
         const int hist0 = p.tail.empty() ? 1 : p.tail[0].T - 1;
-        if (hist0 > 2048) { *err = "filter longer than 2049 taps is not supported"; return SDRPP_ERR_ARG; }
-        const uint32_t hc = (uint32_t)((hist0 + 1) & ~1);
+        if (hist0 > kChanHistPad) { *err = "filter longer than 2049 taps is not supported"; return SDRPP_ERR_ARG; }
+        // the channel filter's pad does not depend on its length, so setBandwidth keeps the slab layout
+        const uint32_t hc = (!p.tail.empty() && p.tail[0].type == TAIL_FIR) ? (uint32_t)kChanHistPad : (uint32_t)((hist0 + 1) & ~1);
         for (int r = 0; r < 2; r++) {
             p.s1_off[r] = off + hc;
             off = p.s1_off[r] + (uint32_t)((cap + 1) & ~1LL);
@@ -133,7 +136,7 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
         TailPlanStage& s = p.tail[i];
         if (s.T - 1 > 2048) { *err = "filter longer than 2049 taps is not supported"; return SDRPP_ERR_ARG; }
         if (i > 0) {
-            const uint32_t hc = (uint32_t)((s.T - 1 + 1) & ~1);
+            const uint32_t hc = (s.type == TAIL_FIR) ? (uint32_t)kChanHistPad : (uint32_t)((s.T - 1 + 1) & ~1);
             s.in_off = off + hc;
             off = s.in_off + (uint32_t)((cap + 1) & ~1LL);
         } else {
@@ -481,6 +484,24 @@ static void join_group(sdrpp_cuda_frontend* fe, int id, int64_t epoch) {
     }
     Group g;
     g.plan = v.plan; g.demod = v.demod; g.st.abs_valid = epoch;
+    g.members.push_back(id);
+    fe->groups.push_back(std::move(g));
+    v.group = (int)fe->groups.size() - 1;
+    fe->layout_dirty = true;
+}
+
+// Put a VFO whose filter state continues (setBandwidth) into a group with exactly this integer state.
+static void join_group_with_state(sdrpp_cuda_frontend* fe, int id, const GroupState& st) {
+    Vfo& v = fe->vfos[(size_t)id];
+    for (size_t gi = 0; gi < fe->groups.size(); gi++) {
+        Group& g = fe->groups[gi];
+        if (g.plan == v.plan && g.demod == v.demod && memcmp(&g.st, &st, sizeof(GroupState)) == 0) {
+            g.members.push_back(id); g.g_dirty = true; v.group = (int)gi; fe->layout_dirty = true;
+            return;
+        }
+    }
+    Group g;
+    g.plan = v.plan; g.demod = v.demod; g.st = st;
     g.members.push_back(id);
     fe->groups.push_back(std::move(g));
     v.group = (int)fe->groups.size() - 1;
@@ -1205,7 +1226,28 @@ int sdrpp_cuda_vfo_set_bandwidth(sdrpp_cuda_frontend* fe, int id, double bw) {
     if (rc != SDRPP_OK) return rc;
     Vfo* v;
     if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
-    return vfo_replan(fe, id, v->outSR, bw, false);
+    // RxVFO::setBandwidth (rx_vfo.h:60-70) only swaps the channel filter's taps: xlator, resampler and the
+    // filter's history carry on (FIR::setTaps keeps the newest samples and zero-fills when the filter grows,
+    // fir.h:31-52). Possible in place when the filter exists before and after; otherwise the VFO restarts.
+    std::shared_ptr<VfoPlan> np;
+    if ((rc = get_plan(fe, v->outSR, bw, &np)) != SDRPP_OK) return rc;
+    const std::shared_ptr<VfoPlan> op = v->plan;
+    const bool in_place = op->filter_needed && np->filter_needed && op->tail.size() == np->tail.size() &&
+                          op->slab_elems == np->slab_elems && op->final_off == np->final_off && v->group >= 0;
+    if (!in_place) return vfo_replan(fe, id, v->outSR, bw, false);
+    const TailPlanStage& of = op->tail.back();
+    const TailPlanStage& nf = np->tail.back();
+    const uint32_t offs[2] = { op->tail.size() == 1 ? op->s1_off[0] : nf.in_off, op->tail.size() == 1 ? op->s1_off[1] : nf.in_off };
+    if (nf.T > of.T) {
+        for (int r = 0; r < (op->tail.size() == 1 ? 2 : 1); r++)
+            FE_TRY(fe, cudaMemset(v->slab + offs[r] - (nf.T - 1), 0, sizeof(float2) * (size_t)(nf.T - of.T)));
+    }
+    const GroupState st = fe->groups[(size_t)v->group].st;
+    remove_from_group(fe, id);
+    v->bw = bw; v->plan = np;
+    set_nco(fe, *v, v->offset, true); // SSB translation follows the bandwidth; NCO phase continues
+    join_group_with_state(fe, id, st);
+    return SDRPP_OK;
 }
 int sdrpp_cuda_vfo_set_out_samplerate(sdrpp_cuda_frontend* fe, int id, double outSR, double bw) {
     int rc = fe_quiesce(fe);

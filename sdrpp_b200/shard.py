@@ -18,11 +18,15 @@ def vfo_cost(in_sr, out_sr, bw, design_resampler, design_decim_plan):
     return cost
 
 
-def shard_vfos(costs, world):
+def shard_vfos(costs, world, base_load=None):
     """Greedy longest-processing-time partition: returns, per rank, the list of VFO indices it owns.
-    Deterministic (ties by index), every VFO in exactly one shard."""
+    Deterministic (ties by index), every VFO in exactly one shard. base_load: work a rank already has
+    (rank 0 ingests, broadcasts and computes the spectrum), in the same units as costs."""
     order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
     load = [0.0] * world
+    if base_load:
+        for r, b in enumerate(base_load[:world]):
+            load[r] = float(b)
     shards = [[] for _ in range(world)]
     for i in order:
         r = min(range(world), key=lambda k: (load[k], k))

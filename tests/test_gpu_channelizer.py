@@ -279,3 +279,26 @@ def test_max_block_and_cfg3_spectrum(gpu, port):
     _, _, row64 = port.spectrum(N, x[:nz], port.window(po.WIN_BH7, nz))
     mask = row64 >= row64.max() - 80.0
     assert np.abs(rows[0] - row64)[mask].max() <= 0.01
+
+
+def test_set_bandwidth_keeps_state(gpu, port):
+    """RxVFO::setBandwidth mid-stream: only the channel filter taps change (rx_vfo.h:60-70, fir.h:31-52)."""
+    inSR, outSR, blk = 3.2e6, 48e3, 7936
+    x = synth.baseband(blk * 9, inSR, 29, carriers=[(0.0, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    with gpu.Frontend(inSR, max_block=blk) as fe:
+        vid = fe.add_vfo(outSR, 12.5e3, 0.0)
+        orc_lib = po.Ref() if po.have_ref() else None
+        if orc_lib is None:
+            pytest.skip("needs oracle/_ref (reference RxVFO::setBandwidth)")
+        o = orc_lib.rxvfo(inSR, outSR, 12.5e3, 0.0)
+        set_bw = orc_lib._f("rxvfo_set_bandwidth", None, po._vp, po._d)
+        for b in range(9):
+            if b == 3:
+                fe.vfo_set_bandwidth(vid, 6.25e3); set_bw(o.h, 6.25e3)     # longer filter (581 taps)
+            if b == 6:
+                fe.vfo_set_bandwidth(vid, 25e3); set_bw(o.h, 25e3)         # shorter filter (145 taps)
+            fe.process(po.FMT_CF32, x[b * blk:(b + 1) * blk])
+            y, _ = fe.vfo_output(vid)
+            r = o.process(x[b * blk:(b + 1) * blk])
+            assert len(y) == len(r), f"block {b}: {len(y)} vs {len(r)}"
+            assert po.rel_rms(y, r) <= TOL, f"block {b}: {po.rel_rms(y, r):.3e}"

@@ -21,6 +21,8 @@ def test_shard_partition_properties(cuda_lib):
         assert allv == list(range(512))
         loads = [sum(costs[i] for i in s) for s in sh]
         assert max(loads) - min(loads) <= max(costs) + 1e-9
+    sh = shard.shard_vfos(costs, 8, base_load=[770.0])
+    assert sorted(i for s in sh for i in s) == list(range(512)) and len(sh[0]) < len(sh[1])
     assert shard.shard_vfos([], 2) == [[], []]
     assert shard.shard_vfos([1.0], 4) == [[0], [], [], []]
 
