@@ -257,7 +257,7 @@ def run_gpu(args, rank, world, local_rank):
     cuda.init(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.pop("NCCL_DEBUG", None)  # any level >= VERSION makes NCCL print a banner on stdout; rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     vf_all = vfo_list()
