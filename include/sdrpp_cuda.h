@@ -107,6 +107,14 @@ SDRPP_API int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf
 SDRPP_API int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* window,
                                   float* row, sdrpp_cf32* X);
 
+/* Same transform on DEVICE buffers, for callers whose samples already live on the GPU: `frames` frames of nz
+ * cf32 samples, frame f starting at dev_in + f*frame_stride; window: nz floats in HOST memory, or NULL to reuse
+ * the table of the previous call with the same N and nz (skips the comparison of a large table); dev_rows:
+ * frames*N floats in device memory. Asynchronous on `stream` (a cudaStream_t, NULL = the library's own stream,
+ * in which case the call synchronises before returning). */
+SDRPP_API int sdrpp_cuda_spectrum_device(int N, int nz, int frames, long long frame_stride, const sdrpp_cf32* dev_in,
+                                         const float* window, float* dev_rows, void* stream);
+
 /* Waterfall zoom / max-decimation of one dB row to outSize pixels: fft_scaler(viewOffset, viewBandwidth,
  * wholeBandwidth, N, outSize).doZoom (gui/widgets/fft_scaler.h:28-64, used by WaterFall::pushFFT,
  * gui/widgets/waterfall.cpp:900-904). idx (optional, outSize+1 ints) receives the bin boundaries. */

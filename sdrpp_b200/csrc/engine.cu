@@ -812,6 +812,8 @@ struct OneShot {
     void* d_b = nullptr; size_t cap_b = 0;
     void* d_c = nullptr; size_t cap_c = 0;
     void* d_d = nullptr; size_t cap_d = 0;
+    void* d_w = nullptr; size_t cap_w = 0;   // spectrum_device: cached window (natural order)
+    std::vector<float> win_host; int win_n = 0;
     int device = -1;
 };
 static OneShot g_os;
@@ -829,8 +831,9 @@ static int os_prepare() {
     SDRPP_CUDA_TRY(cudaSetDevice(g_device));
     if (g_os.device != g_device) {
         if (g_os.st) { cudaStreamDestroy(g_os.st); g_os.st = nullptr; }
-        g_os.d_a = g_os.d_b = g_os.d_c = g_os.d_d = nullptr;
-        g_os.cap_a = g_os.cap_b = g_os.cap_c = g_os.cap_d = 0;
+        g_os.d_a = g_os.d_b = g_os.d_c = g_os.d_d = g_os.d_w = nullptr;
+        g_os.cap_a = g_os.cap_b = g_os.cap_c = g_os.cap_d = g_os.cap_w = 0;
+        g_os.win_host.clear(); g_os.win_n = 0;
         g_os.device = g_device;
     }
     if (!g_os.st) SDRPP_CUDA_TRY(cudaStreamCreateWithFlags(&g_os.st, cudaStreamNonBlocking));
@@ -953,6 +956,44 @@ int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* 
     if (row) SDRPP_CUDA_TRY(cudaMemcpyAsync(row, a.rows, (size_t)N * 4, cudaMemcpyDeviceToHost, g_os.st));
     if (X) SDRPP_CUDA_TRY(cudaMemcpyAsync(X, a.X, (size_t)N * 8, cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_spectrum_device(int N, int nz, int frames, long long frame_stride, const sdrpp_cf32* dev_in, const float* window,
+                               float* dev_rows, void* stream) {
+    int N1, N2;
+    if (spectrum_split(N, &N1, &N2) < 0) return fail(SDRPP_ERR_ARG, "N must be a power of two in 64..4194304");
+    if (nz < 1 || nz > N || frames < 1 || frame_stride < 0 || !dev_in || !dev_rows) return fail(SDRPP_ERR_ARG, "bad argument");
+    if ((long long)(frames - 1) * frame_stride + nz > 0x7FFFFFFFLL) return fail(SDRPP_ERR_ARG, "input span exceeds 2^31 samples");
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : g_os.st;
+    // window table (re-uploaded only when it changes) and an L2-sized four-step intermediate
+    if (!window && (g_os.win_n != N || g_os.win_host.size() != (size_t)nz)) return fail(SDRPP_ERR_STATE, "no cached window of this size: pass the window table");
+    if (window && (g_os.win_n != N || g_os.win_host.size() != (size_t)nz || memcmp(g_os.win_host.data(), window, (size_t)nz * 4) != 0)) {
+        SDRPP_CUDA_TRY(cudaStreamSynchronize(st));
+        SDRPP_CUDA_TRY(os_reserve(&g_os.d_w, &g_os.cap_w, (size_t)nz * 4));
+        SDRPP_CUDA_TRY(cudaMemcpy(g_os.d_w, window, (size_t)nz * 4, cudaMemcpyHostToDevice));
+        g_os.win_host.assign(window, window + nz);
+        g_os.win_n = N;
+    }
+    // frames per launch: enough CTAs for several waves (the kernels' load and compute phases only overlap once
+    // CTAs are out of step); the intermediate need not stay in L2 for that to pay (profiles/README.md)
+    const size_t inter_cap = getenv("SDRPP_FFT_INTER_MB") ? (size_t)atoi(getenv("SDRPP_FFT_INTER_MB")) << 20 : ((size_t)256 << 20);
+    const int group = N1 > 1 ? std::max(1, std::min(frames, (int)(inter_cap / ((size_t)N * 8)))) : frames;
+    if (N1 > 1 && g_os.cap_c < (size_t)group * N * 8) {
+        SDRPP_CUDA_TRY(cudaStreamSynchronize(st));
+        SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, (size_t)group * N * 8));
+    }
+    for (int f0 = 0; f0 < frames; f0 += group) {
+        SpectrumArgs a{};
+        a.in = dev_in + (size_t)f0 * (size_t)frame_stride; a.ring_mask = 0xFFFFFFFFu; a.start = 0; a.frame_stride = (uint32_t)frame_stride;
+        a.nz = nz; a.window = (const float*)g_os.d_w; a.inter = (float2*)g_os.d_c;
+        a.rows = dev_rows + (size_t)f0 * N; a.X = nullptr; a.frames = std::min(group, frames - f0);
+        SDRPP_CUDA_TRY(launch_spectrum(N, a, st, nullptr));
+    }
+    if (!stream) SDRPP_CUDA_TRY(cudaStreamSynchronize(st));
     return SDRPP_OK;
 }
 

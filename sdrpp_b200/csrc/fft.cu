@@ -17,6 +17,13 @@
 #include <vector>
 #include "../../include/sdrpp_cuda.h"
 
+#ifndef SDRPP_FFT_CB
+#define SDRPP_FFT_CB 8
+#endif
+#ifndef SDRPP_FFT_RB
+#define SDRPP_FFT_RB 8
+#endif
+
 namespace sdrpp {
 
 __device__ __forceinline__ float power_db(float2 x) {
@@ -194,7 +201,11 @@ using P64 = FftPlan<64, 8, 8, 8, 1>;
 using P128 = FftPlan<128, 16, 16, 8, 1>;
 using P256 = FftPlan<256, 16, 16, 16, 1>;
 using P512 = FftPlan<512, 32, 32, 16, 1>;
+#ifdef SDRPP_FFT1024_E16
+using P1024 = FftPlan<1024, 16, 16, 16, 4>;
+#else
 using P1024 = FftPlan<1024, 32, 32, 32, 1>;
+#endif
 using P2048 = FftPlan<2048, 16, 16, 16, 8>;
 using P4096 = FftPlan<4096, 16, 16, 16, 16>;
 
@@ -294,7 +305,7 @@ cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long 
     case 128: e = launch_cols<P128, 16>(a, tabs, N2, lg, st); break;
     case 256: e = launch_cols<P256, 16>(a, tabs, N2, lg, st); break;
     case 512: e = launch_cols<P512, 16>(a, tabs, N2, lg, st); break;
-    case 1024: e = launch_cols<P1024, 8>(a, tabs, N2, lg, st); break;
+    case 1024: e = launch_cols<P1024, SDRPP_FFT_CB>(a, tabs, N2, lg, st); break;
     case 2048: e = launch_cols<P2048, 8>(a, tabs, N2, lg, st); break;
     default: return cudaErrorInvalidValue;
     }
@@ -303,7 +314,7 @@ cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long 
     case 128: e = launch_rows<P128, 16, false>(a, tabs, N1, lg, st); break;
     case 256: e = launch_rows<P256, 16, false>(a, tabs, N1, lg, st); break;
     case 512: e = launch_rows<P512, 16, false>(a, tabs, N1, lg, st); break;
-    case 1024: e = launch_rows<P1024, 8, false>(a, tabs, N1, lg, st); break;
+    case 1024: e = launch_rows<P1024, SDRPP_FFT_RB, false>(a, tabs, N1, lg, st); break;
     case 2048: e = launch_rows<P2048, 8, false>(a, tabs, N1, lg, st); break;
     default: return cudaErrorInvalidValue;
     }

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsdrpp_cuda.so")
+LIB_PATH = os.environ.get("SDRPP_CUDA_LIB") or os.path.join(HERE, "libsdrpp_cuda.so")  # override: experiment builds
 
 FMT_CF32, FMT_U8_RTL, FMT_U8_TCP, FMT_I8, FMT_I16_FILE, FMT_I16_VOLK, FMT_I24_FILE, FMT_I32_FILE, FMT_F64 = range(9)
 WIN_RECT, WIN_HAMMING, WIN_HANN, WIN_BLACKMAN, WIN_NUTTALL, WIN_BH4, WIN_BH7 = range(7)
@@ -32,7 +32,7 @@ sdrpp_cuda_vfo_set_bandwidth sdrpp_cuda_vfo_set_out_samplerate sdrpp_cuda_vfo_re
 sdrpp_cuda_frontend_submit sdrpp_cuda_frontend_submit_device sdrpp_cuda_frontend_wait
 sdrpp_cuda_frontend_set_readback sdrpp_cuda_vfo_output sdrpp_cuda_fft_rows sdrpp_cuda_frontend_read_iq
 sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_profiling
-sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows
+sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -71,6 +71,7 @@ def lib():
         L.sdrpp_cuda_design_reshape.restype = None
         L.sdrpp_cuda_convert.argtypes = [_i, _vp, _i, _vp]
         L.sdrpp_cuda_spectrum.argtypes = [_i, _i, _i, _vp, _vp, _vp, _vp]
+        L.sdrpp_cuda_spectrum_device.argtypes = [_i, _i, _i, C.c_longlong, _vp, _vp, _vp, _vp]
         L.sdrpp_cuda_fft_zoom.argtypes = [_i, _vp, _d, _d, _d, _i, _vp, _vp]
         L.sdrpp_cuda_frontend_set_fft_zoom.argtypes = [_vp, _d, _d, _d, _i, _i]
         L.sdrpp_cuda_fft_zoomed_rows.argtypes = [_vp, C.POINTER(_vp)]
@@ -188,6 +189,14 @@ def spectrum(N, frame, window, fmt=FMT_CF32, want_X=False):
     _check(lib().sdrpp_cuda_spectrum(N, nz, fmt, _ptr(frame), _ptr(window), _ptr(row), _ptr(X) if want_X else None),
            "sdrpp_cuda_spectrum")
     return (row, X) if want_X else row
+
+
+def spectrum_device(N, nz, frames, frame_stride, dev_in, window, dev_rows, stream=None):
+    """Spectrum rows for frames already in device memory (raw device pointers as ints)."""
+    if window is not None:
+        window = np.ascontiguousarray(window, dtype=np.float32)
+    _check(lib().sdrpp_cuda_spectrum_device(N, nz, frames, frame_stride, C.c_void_p(dev_in), _ptr(window) if window is not None else None, C.c_void_p(dev_rows),
+                                            C.c_void_p(stream) if stream else None), "sdrpp_cuda_spectrum_device")
 
 
 def fft_zoom(row, view_offset, view_bw, whole_bw, out_size):

@@ -165,3 +165,19 @@ def test_frontend_zoomed_rows(gpu, port):
     for r in range(4):
         ref, _ = port.fft_zoom(2e5, 1.2e6, sr, raw[r], W)
         assert np.array_equal(zoomed[r].view(np.uint32), ref.view(np.uint32))
+
+
+def test_spectrum_device_batched(gpu, port):
+    """sdrpp_cuda_spectrum_device: frames already on the GPU, several per call, equal to the one-shot rows."""
+    import torch
+    N, F = 65536, 5
+    x = _frame(N * F, 41)
+    xd = torch.from_numpy(x.view(np.float32).reshape(-1, 2).copy()).cuda()
+    rows = torch.empty((F, N), dtype=torch.float32, device="cuda")
+    w = port.window(po.WIN_BH7, N)
+    gpu.spectrum_device(N, N, F, N, xd.data_ptr(), w, rows.data_ptr())
+    torch.cuda.synchronize()
+    got = rows.cpu().numpy()
+    for f in range(F):
+        one = gpu.spectrum(N, x[f * N:(f + 1) * N], w)
+        assert np.array_equal(one.view(np.uint32), got[f].view(np.uint32))
