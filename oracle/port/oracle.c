@@ -639,6 +639,153 @@ API int orc_spectrum(int N, int nz, const cf32* frame, const float* window, floa
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* 8f rank 1. Post-detector stages: loop/agc.h:87-147, correction/dc_blocker.h:54-60 (float),  */
+/* filter/fir.h:62-83 (float), demod/fm.h:86-103, demod/am.h:114-146, demod/ssb.h:90-101        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { float setPoint, attack, invAttack, decay, invDecay, maxGain, maxOut, gain, amp; int enabled; } orc_agc;
+static void agc_init(orc_agc* a, double attack, double decay) {
+    /* AGC::init(NULL, 1.0, attack, decay, 10e6, 10.0, INFINITY) as AM/SSB call it (am.h:32-33, ssb.h:27) */
+    float initGain = INFINITY;
+    a->setPoint = 1.0f; a->attack = (float)attack; a->invAttack = 1.0f - a->attack;
+    a->decay = (float)decay; a->invDecay = 1.0f - a->decay;
+    a->maxGain = (float)10e6; a->maxOut = 10.0f;
+    a->amp = a->setPoint / initGain;
+    a->gain = initGain < a->maxGain ? initGain : a->maxGain;
+    a->enabled = 1;
+}
+static void agc_float(orc_agc* a, int count, const float* in, float* out) {
+    int i, j;
+    for (i = 0; i < count; i++) {
+        if (a->enabled) {
+            float inAmp = fabsf(in[i]);
+            if (inAmp != 0.0f) {
+                a->amp = (inAmp > a->amp) ? ((a->amp * a->invAttack) + (inAmp * a->attack)) : ((a->amp * a->invDecay) + (inAmp * a->decay));
+                { float g = a->setPoint / a->amp; a->gain = g < a->maxGain ? g : a->maxGain; }
+            } else a->gain = 1.0f;
+            if (inAmp * a->gain > a->maxOut) {
+                float maxAmp = 0;
+                for (j = i; j < count; j++) { float v = fabsf(in[j]); if (v > maxAmp) maxAmp = v; }
+                a->amp = maxAmp;
+                { float g = a->setPoint / a->amp; a->gain = g < a->maxGain ? g : a->maxGain; }
+            }
+            out[i] = in[i] * a->gain;
+        } else {
+            float inAmp = fabsf(in[i]);
+            float gainAmp = inAmp * a->gain;
+            out[i] = (gainAmp > a->maxOut) ? in[i] * (a->maxOut / inAmp) : in[i] * a->gain;
+        }
+    }
+}
+static void agc_complex(orc_agc* a, int count, const cf32* in, cf32* out) {
+    int i, j;
+    for (i = 0; i < count; i++) { /* carrier AGC is always enabled (am.h:38) */
+        float inAmp = sqrtf(in[i].re * in[i].re + in[i].im * in[i].im); /* complex_t::amplitude(), types.h */
+        if (inAmp != 0.0f) {
+            a->amp = (inAmp > a->amp) ? ((a->amp * a->invAttack) + (inAmp * a->attack)) : ((a->amp * a->invDecay) + (inAmp * a->decay));
+            { float g = a->setPoint / a->amp; a->gain = g < a->maxGain ? g : a->maxGain; }
+        } else a->gain = 1.0f;
+        if (inAmp * a->gain > a->maxOut) {
+            float maxAmp = 0;
+            for (j = i; j < count; j++) { float v = sqrtf(in[j].re * in[j].re + in[j].im * in[j].im); if (v > maxAmp) maxAmp = v; }
+            a->amp = maxAmp;
+            { float g = a->setPoint / a->amp; a->gain = g < a->maxGain ? g : a->maxGain; }
+        }
+        out[i].re = in[i].re * a->gain; out[i].im = in[i].im * a->gain;
+    }
+}
+typedef struct { int ntaps; float* taps; float* buf; int cap; } orc_ffir;
+static void ffir_init(orc_ffir* f, const float* taps, int n) {
+    f->ntaps = n; f->taps = (float*)malloc(sizeof(float) * (size_t)n); memcpy(f->taps, taps, sizeof(float) * (size_t)n);
+    f->buf = NULL; f->cap = 0;
+}
+static void ffir_process(orc_ffir* f, int count, const float* in, float* out) {
+    int need = f->ntaps - 1 + count, i, k;
+    if (need > f->cap) {
+        float* nb = (float*)calloc((size_t)need + 16, sizeof(float));
+        if (f->buf) { memcpy(nb, f->buf, sizeof(float) * (size_t)(f->ntaps - 1)); free(f->buf); }
+        f->buf = nb; f->cap = need;
+    }
+    memcpy(f->buf + (f->ntaps - 1), in, sizeof(float) * (size_t)count);
+    for (i = 0; i < count; i++) { /* volk_32f_x2_dot_prod_32f generic: sequential fp32 */
+        float acc = 0.0f;
+        for (k = 0; k < f->ntaps; k++) acc += f->buf[i + k] * f->taps[k];
+        out[i] = acc;
+    }
+    memmove(f->buf, f->buf + count, sizeof(float) * (size_t)(f->ntaps - 1));
+}
+static void ffir_free(orc_ffir* f) { free(f->taps); free(f->buf); }
+
+typedef struct {
+    int kind;                 /* 1 FM, 2 AM, 3 SSB */
+    orc_quad* quad; orc_ssb* ssb;
+    int lowpass, agc_mode;    /* AM: 0 OFF 1 CARRIER 2 AUDIO */
+    orc_agc audio, carrier; float dc_rate, dc_off;
+    orc_ffir lpf; int has_lpf;
+    cf32* ctmp; float* ftmp; int cap;
+} orc_post;
+static void post_reserve(orc_post* p, int n) {
+    if (n > p->cap) { free(p->ctmp); free(p->ftmp); p->ctmp = (cf32*)malloc(sizeof(cf32) * (size_t)(n + 16)); p->ftmp = (float*)malloc(sizeof(float) * (size_t)(n + 16)); p->cap = n; }
+}
+static void post_lpf(orc_post* p, double bandwidth, double samplerate) {
+    int n = orc_lowpass_taps(bandwidth / 2.0, (bandwidth / 2.0) * 0.1, samplerate, NULL, 0);
+    float* t = (float*)malloc(sizeof(float) * (size_t)n);
+    orc_lowpass_taps(bandwidth / 2.0, (bandwidth / 2.0) * 0.1, samplerate, t, n);
+    ffir_init(&p->lpf, t, n); p->has_lpf = 1;
+    free(t);
+}
+/* dsp::demod::FM<float>::init(in, samplerate, bandwidth, lowPass, highPass=false), fm.h:25-44,117-145 */
+API orc_post* orc_fm_create(double samplerate, double bandwidth, int lowPass) {
+    orc_post* p = (orc_post*)calloc(1, sizeof(orc_post));
+    p->kind = 1; p->quad = orc_quadrature_create(bandwidth / 2.0, samplerate); p->lowpass = lowPass;
+    if (lowPass) post_lpf(p, bandwidth, samplerate);
+    return p;
+}
+/* dsp::demod::AM<float>::init, am.h:27-44 */
+API orc_post* orc_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate, float agcGain) {
+    orc_post* p = (orc_post*)calloc(1, sizeof(orc_post));
+    p->kind = 2; p->agc_mode = agcMode;
+    agc_init(&p->carrier, agcAttack, agcDecay); agc_init(&p->audio, agcAttack, agcDecay);
+    p->audio.enabled = (agcMode == 2);
+    if (agcGain > 0) p->audio.gain = agcGain;     /* setAGCGain */
+    p->dc_rate = (float)dcBlockRate; p->dc_off = 0.0f;
+    post_lpf(p, bandwidth, samplerate);
+    return p;
+}
+/* dsp::demod::SSB<float>::init, ssb.h:21-36 */
+API orc_post* orc_ssbfull_create(int mode, double bandwidth, double samplerate, int agcEnabled, double agcAttack, double agcDecay) {
+    orc_post* p = (orc_post*)calloc(1, sizeof(orc_post));
+    p->kind = 3; p->ssb = orc_ssb_create(mode, bandwidth, samplerate);
+    agc_init(&p->audio, agcAttack, agcDecay); p->audio.enabled = agcEnabled;
+    return p;
+}
+API int orc_post_process(orc_post* p, int count, const cf32* in, float* out) {
+    int i;
+    post_reserve(p, count);
+    if (p->kind == 1) {
+        orc_quadrature_process(p->quad, count, in, out);
+        if (p->has_lpf) ffir_process(&p->lpf, count, out, out);
+    } else if (p->kind == 2) {
+        const cf32* src = in;
+        if (p->agc_mode == 1) { agc_complex(&p->carrier, count, in, p->ctmp); src = p->ctmp; }
+        orc_am_magnitude(count, src, out);
+        for (i = 0; i < count; i++) { float o = out[i] - p->dc_off; out[i] = o; p->dc_off += o * p->dc_rate; } /* dc_blocker.h:54-60 */
+        if (p->agc_mode != 1) agc_float(&p->audio, count, out, out);
+        ffir_process(&p->lpf, count, out, out);
+    } else {
+        orc_ssb_process(p->ssb, count, in, out);
+        agc_float(&p->audio, count, out, out);
+    }
+    return count;
+}
+API void orc_post_destroy(orc_post* p) {
+    if (!p) return;
+    if (p->quad) orc_quadrature_destroy(p->quad);
+    if (p->ssb) orc_ssb_destroy(p->ssb);
+    if (p->has_lpf) ffir_free(&p->lpf);
+    free(p->ctmp); free(p->ftmp); free(p);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* 8f rank 2. Waterfall zoom / max-decimation: gui/widgets/fft_scaler.h:28-64                   */
 /* idx (optional, outSize+1 ints) receives the bin boundaries i0..i_outSize for index parity.   */
 /* ------------------------------------------------------------------------------------------ */

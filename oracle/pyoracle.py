@@ -194,6 +194,22 @@ class _Base:
         self._f("conjugate", _i, _i, _vp, _vp)(len(x), _ptr(x), _ptr(out))
         return out
 
+    # ---- complete demodulators -----------------------------------------------------
+    def _post_obj(self, h, name):
+        lib, pre = self.lib, self.prefix
+        proc = f"{pre}_{name}" if pre == "ref" else "orc_post"
+        o = _Obj(lib, proc, h, out_dtype=np.float32)
+        return o
+
+    def fm_full(self, sr, bw, low_pass=True):
+        return self._post_obj(self._f("fm_create", _vp, _d, _d, _i)(sr, bw, int(low_pass)), "fm")
+
+    def am_full(self, agc_mode, bw, attack, decay, dc_rate, sr, agc_gain=0.0):
+        return self._post_obj(self._f("am_create", _vp, _i, _d, _d, _d, _d, _d, C.c_float)(agc_mode, bw, attack, decay, dc_rate, sr, agc_gain), "am")
+
+    def ssb_full(self, mode, bw, sr, agc_enabled, attack, decay):
+        return self._post_obj(self._f("ssbfull_create", _vp, _i, _d, _d, _i, _d, _d)(mode, bw, sr, int(agc_enabled), attack, decay), "ssbfull")
+
     def demod(self, kind, bw, sr):
         """Demod front end object for a VFO output stream (kind = DEMOD_*), or None."""
         if kind == DEMOD_QUAD:

@@ -24,6 +24,9 @@
 #include <dsp/math/conjugate.h>
 #include <dsp/convert/complex_to_real.h>
 #include <gui/widgets/fft_scaler.h>
+#include <dsp/demod/fm.h>
+#include <dsp/demod/am.h>
+#include <dsp/demod/ssb.h>
 
 #include <vector>
 #include <thread>
@@ -382,6 +385,38 @@ API void ref_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandw
     fft_scaler sc(viewOffset, viewBandwidth, wholeBandwidth, (size_t)fftSize, (size_t)outSize);
     sc.doZoom(data, out);
 }
+
+// ---------------------------------------------------------------------------------------------
+// the complete demodulators (front end + post-detector stages), float output
+// ---------------------------------------------------------------------------------------------
+// dsp::demod::FM<float> (dsp/demod/fm.h): Quadrature + optional low-pass FIR
+API void* ref_fm_create(double samplerate, double bandwidth, int lowPass) {
+    auto* d = new dsp::demod::FM<float>();
+    d->init(NULL, samplerate, bandwidth, lowPass != 0, false);
+    d->reset();
+    return d;
+}
+API int ref_fm_process(void* h, int count, complex_t* in, float* out) { return ((dsp::demod::FM<float>*)h)->process(count, in, out); }
+API void ref_fm_destroy(void* h) { delete (dsp::demod::FM<float>*)h; }
+
+// dsp::demod::AM<float> (dsp/demod/am.h): [carrier AGC] -> magnitude -> DC block -> [audio AGC] -> low-pass FIR
+API void* ref_am_create(int agcMode, double bandwidth, double agcAttack, double agcDecay, double dcBlockRate, double samplerate, float agcGain) {
+    auto* d = new dsp::demod::AM<float>();
+    d->init(NULL, (dsp::demod::AM<float>::AGCMode)agcMode, bandwidth, agcAttack, agcDecay, dcBlockRate, samplerate);
+    if (agcGain > 0) d->setAGCGain(agcGain);
+    return d;
+}
+API int ref_am_process(void* h, int count, complex_t* in, float* out) { return ((dsp::demod::AM<float>*)h)->process(count, in, out); }
+API void ref_am_destroy(void* h) { delete (dsp::demod::AM<float>*)h; }
+
+// dsp::demod::SSB<float> (dsp/demod/ssb.h): xlate -> real -> AGC. mode 0 USB, 1 LSB, 2 DSB
+API void* ref_ssbfull_create(int mode, double bandwidth, double samplerate, int agcEnabled, double agcAttack, double agcDecay) {
+    auto* d = new dsp::demod::SSB<float>();
+    d->init(NULL, (dsp::demod::SSB<float>::Mode)mode, bandwidth, samplerate, agcEnabled != 0, agcAttack, agcDecay);
+    return d;
+}
+API int ref_ssbfull_process(void* h, int count, const complex_t* in, float* out) { return ((dsp::demod::SSB<float>*)h)->process(count, in, out); }
+API void ref_ssbfull_destroy(void* h) { delete (dsp::demod::SSB<float>*)h; }
 
 API const char* ref_build_info() {
 #ifdef __FAST_MATH__
