@@ -6,20 +6,24 @@
 // ssb.h:90-101).
 //
 // Stage 1 (stage1_kernel) carries ~95 % of the arithmetic at high decimation: the NCO and the
-// first decimating FIR, which both run at the full input rate. The translation is folded into the
-// taps: with z[n] = x[n] e^{j phi(n)} and phi(n0+k) = phi(n0) + w k,
-//     y[m] = sum_k z[n0+k] h[k] = e^{j phi(n0)} sum_k x[n0+k] g[k],   g[k] = h[k] e^{j w k},
-// so every VFO of a group reads the SAME untranslated samples from one shared-memory tile and
-// only its taps differ. A warp holds 32 VFOs (one per lane) x 8 consecutive outputs; the sample
-// window is a shared-memory broadcast, the per-VFO taps stream through a 3-stage
-// cp.async.bulk (TMA) + mbarrier pipeline, and the inner loop is register-blocked FP32 FMA.
+// first decimating FIR, which both run at the full input rate. Every VFO of a group reads the SAME
+// untranslated samples from one shared-memory tile (one bulk/TMA copy per CTA); the per-VFO work is
+// one complex multiply per sample by a short phasor table, the taps stay real and shared (constant
+// memory, uniform operands), and the inner loop is register-blocked packed FP32 FMA (FFMA2).
 //
 // The remaining stages run at 1/D of the rate (tail_kernel, one CTA per VFO).
 #include "common.cuh"
 #include "design.h"
 #include "kernels.h"
+#include <cstdlib>
 #include <mutex>
+#include <type_traits>
 #include <vector>
+
+#ifndef SDRPP_S1_R
+#define SDRPP_S1_R 6
+#define SDRPP_S1_W 8
+#endif
 
 namespace sdrpp {
 
@@ -36,6 +40,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -147,27 +154,62 @@ void stage1_g_index(int A, int D, int v, int p, size_t* idx4, int* half) {
     *half = p & 1;
 }
 
-template <int A, int R, int W>
+// ---------------------------------------------------------------------------------------------
+// The kernel runs on FFMA2 (fma.rn.f32x2, sm_100): one instruction updates the (re, im) pair of an
+// accumulator. FFMA2 takes a scalar (register or uniform register) broadcast to both halves as an
+// operand, so
+//     (w.re, w.im) = x.re * (F.re, F.im) + x.im * (-F.im, F.re),    acc += h * (w.re, w.im)
+// need no operand shuffling: x.re / x.im are the halves of the broadcast sample load and h is the
+// uniform tap (FFMA2 R, R.F32x2, UR.F32, R.F32x2 in SASS). Measured on B200 (tools/_mb microbenchmarks,
+// profiles/README.md): FFMA2 does not raise the FMA peak (128 FMA/clk/SM either way) and every non-FMA
+// instruction in an FFMA2 stream costs about one FFMA2 slot, so the inner loop is kept to the sample,
+// phasor and tap loads: the decimation is a template parameter for the plan shapes that matter (row
+// strides become immediates) and the partially filled last tap slab has its own loop (no branches).
+// ---------------------------------------------------------------------------------------------
+#ifdef SDRPP_S1_TRACE
+// Debug build only (-DSDRPP_S1_TRACE): per-CTA phase timestamps (globaltimer ns) of the packed kernel.
+constexpr int kS1TraceCap = 8192;
+__device__ long long g_s1_trace[kS1TraceCap][6];
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define S1_TRACE(slot)                                                                            \
+    do {                                                                                          \
+        if (threadIdx.x == 0) {                                                                   \
+            const unsigned lin_ = blockIdx.y * gridDim.x + blockIdx.x;                            \
+            if (lin_ < (unsigned)kS1TraceCap) g_s1_trace[lin_][slot] = gtime();                   \
+        }                                                                                         \
+    } while (0)
+#else
+#define S1_TRACE(slot) do {} while (0)
+#endif
+
+// DT: decimation as a compile-time constant (row strides become immediates), or 0 to take it from the arguments.
+template <int A, int R, int W, int DT>
 __global__ void __launch_bounds__(W * 32, 2)
 stage1_kernel(const __grid_constant__ Stage1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int ROWS = W * R;              // rows of D samples per CTA
-    constexpr int OUT = ROWS - (A - 1);      // complete outputs per CTA
-    constexpr int NP = R + A - 1;            // partial outputs a thread contributes to
-    const int D = a.D, DP = D >> 1;
+    constexpr int ROWS = W * R;
+    constexpr int OUT = ROWS - (A - 1);
+    constexpr int NP = R + A - 1;
+    constexpr int NT = W * 32;
+    const int D = DT > 0 ? DT : a.D, DP = D >> 1;
 
+    S1_TRACE(0);
+#ifdef SDRPP_S1_TRACE
+    if (threadIdx.x == 0) {
+        unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+        const unsigned lin_ = blockIdx.y * gridDim.x + blockIdx.x;
+        if (lin_ < (unsigned)kS1TraceCap) g_s1_trace[lin_][5] = sm_;
+    }
+#endif
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-    float4* Fs = reinterpret_cast<float4*>(smem_raw + 128);       // [DP][32]: (F[2pp], F[2pp+1]) per lane
+    float2* parts = reinterpret_cast<float2*>(smem_raw + 128);    // [W][NP][32] partial outputs (epilogue)
+    float4* Fs = reinterpret_cast<float4*>(parts + W * NP * 32);  // [DP][32]: (F[2pp], F[2pp+1]) per lane
     float2* xs = reinterpret_cast<float2*>(Fs + DP * 32);         // [ROWS][D] samples, natural order
-    float2* parts = xs;                                            // reused after the main loop: [W][NP][32]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * OUT;
     const int vb = blockIdx.y;
 
-    // Per-VFO phasor table and sample tile: bulk (TMA) copies completing on one mbarrier. The tile is
-    // contiguous in the ring; it falls back to element loads when it wraps, is misaligned, or reaches
-    // back before the group's epoch (samples that must read as zero).
     const uint32_t f_bytes = (uint32_t)DP * 32u * 16u;
     const uint32_t r0 = a.ring_first + (uint32_t)m0 * (uint32_t)D;
     const int64_t abs0 = a.abs_first + (int64_t)m0 * D;
@@ -182,7 +224,7 @@ stage1_kernel(const __grid_constant__ Stage1Args a) {
         if (bulk_x) bulk_g2s(xs, a.ring.base + i0, total * 8u, bar);
     }
     if (!bulk_x) {
-        for (uint32_t n = tid; n < total; n += W * 32) {
+        for (uint32_t n = tid; n < total; n += NT) {
             float2 s = a.ring.base[(r0 + n) & a.ring.mask];
             if (abs0 + (int64_t)n < a.abs_valid) s = make_float2(0.0f, 0.0f);
             xs[n] = s;
@@ -190,70 +232,83 @@ stage1_kernel(const __grid_constant__ Stage1Args a) {
     }
     __syncthreads(); // element-loaded tile complete; barrier init visible
     mbar_wait(bar, 0);
+    S1_TRACE(1);
 
-    float vr[R][A], vi[R][A];
+    float2 acc[R][A];
 #pragma unroll
     for (int r = 0; r < R; r++)
 #pragma unroll
-        for (int aa = 0; aa < A; aa++) { vr[r][aa] = 0.0f; vi[r][aa] = 0.0f; }
+        for (int aa = 0; aa < A; aa++) acc[r][aa] = make_float2(0.0f, 0.0f);
 
     const float4* xrow = reinterpret_cast<const float4*>(xs + (size_t)warp * R * D);
-    const int rem = a.T - (A - 1) * D; // taps in the last slab of the tap matrix
-    const float* taps = c_s1_taps + a.tap_off;
+    const int rem = a.T - (A - 1) * D;  // taps in the last slab of the tap matrix
+    const int pl = (rem + 1) >> 1;      // sample pairs that reach into the last slab; the others use A-1 slabs
+    const float2* taps2 = reinterpret_cast<const float2*>(c_s1_taps + a.tap_off); // pair-major [pp][aa] (h[aa*D+2pp], h[aa*D+2pp+1])
 
-    const float2* taps2 = reinterpret_cast<const float2*>(taps); // (h[2pp], h[2pp+1]) pairs: one 64-bit uniform load
-#pragma unroll 2
-    for (int pp = 0; pp < DP; pp++) {
+    // one sample pair of every row of the warp against NA slabs of the tap matrix
+    auto pair_step = [&](int pp, auto na_tag) {
+        constexpr int NA = decltype(na_tag)::value;
         const float4 f = Fs[pp * 32 + lane];
-        const bool last_slab = (2 * pp < rem);
-        float w0r[R], w0i[R], w1r[R], w1i[R];
+        const float2 f0 = make_float2(f.x, f.y), g0 = make_float2(-f.y, f.x); // F[2pp], j*F[2pp]
+        const float2 f1 = make_float2(f.z, f.w), g1 = make_float2(-f.w, f.z);
+        float2 w0[R], w1[R];
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const float4 x = xrow[r * DP + pp]; // warp-uniform address: broadcast
-            w0r[r] = fmaf(-x.y, f.y, x.x * f.x);
-            w0i[r] = fmaf(x.y, f.x, x.x * f.y);
-            w1r[r] = fmaf(-x.w, f.w, x.z * f.z);
-            w1i[r] = fmaf(x.w, f.z, x.z * f.w);
+            w0[r] = __ffma2_rn(make_float2(x.x, x.x), f0, __fmul2_rn(make_float2(x.y, x.y), g0));
+            w1[r] = __ffma2_rn(make_float2(x.z, x.z), f1, __fmul2_rn(make_float2(x.w, x.w), g1));
         }
+        const float2* tp = taps2 + pp * A;
 #pragma unroll
-        for (int aa = 0; aa < A; aa++) {
-            if (aa == A - 1 && !last_slab) continue; // only zero padding here
-            const float2 h = taps2[pp * A + aa];
+        for (int aa = 0; aa < NA; aa++) {
+            const float2 h = tp[aa]; // uniform constant load; FFMA2 broadcasts the scalar to both halves
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                vr[r][aa] = fmaf(h.x, w0r[r], vr[r][aa]);
-                vi[r][aa] = fmaf(h.x, w0i[r], vi[r][aa]);
-                vr[r][aa] = fmaf(h.y, w1r[r], vr[r][aa]);
-                vi[r][aa] = fmaf(h.y, w1i[r], vi[r][aa]);
+                acc[r][aa] = __ffma2_rn(make_float2(h.x, h.x), w0[r], acc[r][aa]);
+                acc[r][aa] = __ffma2_rn(make_float2(h.y, h.y), w1[r], acc[r][aa]);
             }
         }
+    };
+    {
+        int pp = 0;
+#pragma unroll 1
+        for (; pp < pl; pp++) pair_step(pp, std::integral_constant<int, A>());
+#pragma unroll 1
+        for (; pp < DP; pp++) pair_step(pp, std::integral_constant<int, A - 1>());
     }
-    __syncthreads(); // all warps are done reading the sample tile; reuse it for the partial sums
 
+    S1_TRACE(2);
     const int v = vb * 32 + lane;
     const bool live = v < a.nvfo;
     VfoDev vd{};
     if (live) vd = a.vfos[v];
-    // rotate each row's sums by the NCO phase of the row's first sample, then form the partial outputs
+    // Rotate each row's sums by the NCO phase E[q] of the row's first sample and add them into the partial outputs
+    // (output j = r - aa of this warp's rows, stored at j + A - 1). E comes from the 64-bit phase accumulator for the
+    // warp's first row and advances by one row (D samples) per step: acc*E = acc.re*(E.re, E.im) + acc.im*(-E.im, E.re).
     float2 part[NP];
 #pragma unroll
     for (int j = 0; j < NP; j++) part[j] = make_float2(0.0f, 0.0f);
+    {
+        const int q0 = m0 + warp * R;
+        const uint64_t ph0 = vd.phi_ref + (uint64_t)(a.abs_first + (int64_t)q0 * D - vd.n_ref) * vd.dphi;
+        float2 e = phasor_u64(ph0);
+        const float2 step = phasor_u64((uint64_t)D * vd.dphi);
 #pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int q = m0 + warp * R + r;
-        const uint64_t ph = vd.phi_ref + (uint64_t)(a.abs_first + (int64_t)q * D - vd.n_ref) * vd.dphi;
-        const float2 e = phasor_u64(ph);
+        for (int r = 0; r < R; r++) {
+            if (r > 0) e = cmul(e, step);
+            const float2 ej = make_float2(-e.y, e.x);
 #pragma unroll
-        for (int aa = 0; aa < A; aa++) {
-            // output (local to this warp's rows) j = r - aa, stored at j + (A-1)
-            const float2 t = cmul(make_float2(vr[r][aa], vi[r][aa]), e);
-            part[r - aa + (A - 1)].x += t.x;
-            part[r - aa + (A - 1)].y += t.y;
+            for (int aa = 0; aa < A; aa++) {
+                float2& pj = part[r - aa + (A - 1)];
+                pj = __ffma2_rn(make_float2(acc[r][aa].x, acc[r][aa].x), e, pj);
+                pj = __ffma2_rn(make_float2(acc[r][aa].y, acc[r][aa].y), ej, pj);
+            }
         }
     }
 #pragma unroll
     for (int j = 0; j < NP; j++) parts[(warp * NP + j) * 32 + lane] = part[j];
     __syncthreads();
+    S1_TRACE(3);
 
     if (live) {
         float2* __restrict__ out = vd.slab + a.out_off;
@@ -273,40 +328,44 @@ stage1_kernel(const __grid_constant__ Stage1Args a) {
             out[m] = y;
         }
     }
+    S1_TRACE(4);
 }
 
-template <int A, int R, int W>
+template <int A, int R, int W, int DT>
 static cudaError_t launch_stage1_t(const Stage1Args& a, cudaStream_t st) {
     constexpr int ROWS = W * R, OUT = ROWS - (A - 1), NP = R + A - 1;
     const size_t tile = (size_t)ROWS * a.D * sizeof(float2);
     const size_t parts = (size_t)W * NP * 32 * sizeof(float2);
-    const size_t smem = 128 + (size_t)(a.D / 2) * 32 * 16 + (tile > parts ? tile : parts);
+    const size_t smem = 128 + parts + (size_t)(a.D / 2) * 32 * 16 + tile;
     static size_t attr_set = 0;
     if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A, R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A, R, W, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = smem;
     }
     dim3 grid(ceil_div(a.M, OUT), ceil_div(a.nvfo, 32));
-    stage1_kernel<A, R, W><<<grid, W * 32, smem, st>>>(a);
+    stage1_kernel<A, R, W, DT><<<grid, W * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
-
-#ifndef SDRPP_S1_R
-#define SDRPP_S1_R 6
-#define SDRPP_S1_W 8
-#endif
 
 cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st) {
     if (a.M <= 0 || a.nvfo <= 0) return cudaSuccess;
     if (a.tap_off < 0) return cudaErrorInvalidValue;
+    // the shapes the PowerDecimator plans produce at high ratios get the decimation as a compile-time constant
+#define SDRPP_S1P_CASE(AA, DD) if (a.A == AA && a.D == DD) return launch_stage1_t<AA, SDRPP_S1_R, SDRPP_S1_W, DD>(a, st);
+    SDRPP_S1P_CASE(5, 32)
+    SDRPP_S1P_CASE(5, 64)
+    SDRPP_S1P_CASE(6, 64)
+    SDRPP_S1P_CASE(7, 64)
+    SDRPP_S1P_CASE(6, 128)
+#undef SDRPP_S1P_CASE
     switch (a.A) {
-    case 2: return launch_stage1_t<2, SDRPP_S1_R, SDRPP_S1_W>(a, st);
-    case 3: return launch_stage1_t<3, SDRPP_S1_R, SDRPP_S1_W>(a, st);
-    case 4: return launch_stage1_t<4, SDRPP_S1_R, SDRPP_S1_W>(a, st);
-    case 5: return launch_stage1_t<5, SDRPP_S1_R, SDRPP_S1_W>(a, st);
-    case 6: return launch_stage1_t<6, SDRPP_S1_R, SDRPP_S1_W>(a, st);
-    case 7: return launch_stage1_t<7, SDRPP_S1_R, SDRPP_S1_W>(a, st);
+    case 2: return launch_stage1_t<2, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
+    case 3: return launch_stage1_t<3, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
+    case 4: return launch_stage1_t<4, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
+    case 5: return launch_stage1_t<5, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
+    case 6: return launch_stage1_t<6, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
+    case 7: return launch_stage1_t<7, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -537,3 +596,10 @@ cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {
 }
 
 } // namespace sdrpp
+
+#ifdef SDRPP_S1_TRACE
+extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_s1_trace(long long* out, int rows) {
+    if (rows > sdrpp::kS1TraceCap) rows = sdrpp::kS1TraceCap;
+    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1_trace, sizeof(long long) * 6 * (size_t)rows);
+}
+#endif

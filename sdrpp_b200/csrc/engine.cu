@@ -218,8 +218,9 @@ struct sdrpp_cuda_frontend {
     int device = 0;
     sdrpp_cuda_frontend_cfg cfg{};
     double eff_sr = 0;
-    cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr, st_s1b = nullptr;
     cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft = nullptr, ev_tail[2] = { nullptr, nullptr };
+    cudaEvent_t ev_s1_fork = nullptr, ev_s1_join = nullptr;
     bool ev_tail_valid[2] = { false, false };
     long long blk = 0; // blocks processed (parity selects the stage-1 output region)
     long long launches = 0;
@@ -648,8 +649,17 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
     std::vector<TailArgs> tails;
     std::vector<int> tail_totals;
+    // Stage-1 launches of different groups are independent: alternate them between two streams so that the
+    // partially filled last wave of one grid is topped up by the next grid's CTAs.
+    const bool fork = fe->groups.size() > 1;
+    if (fork) {
+        FE_TRY(fe, cudaEventRecord(fe->ev_s1_fork, st));
+        FE_TRY(fe, cudaStreamWaitEvent(fe->st_s1b, fe->ev_s1_fork, 0));
+    }
+    int s1_launch = 0;
     for (Group& g : fe->groups) {
         const VfoPlan& p = *g.plan;
+        cudaStream_t s1s = (fork && (s1_launch & 1)) ? fe->st_s1b : st;
         Stage1Args a{};
         a.ring = ring;
         a.nvfo = (int)g.members.size();
@@ -672,15 +682,15 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             a.T = p.s1_T + pad;
             a.tap_off = p.s1_tap_off + pad * p.s1_A * p.s1_D;
             a.ring_first = (uint32_t)((uint64_t)a.abs_first & fe->ring_mask);
-            FE_TRY(fe, launch_stage1(a, st));
+            FE_TRY(fe, launch_stage1(a, s1s));
         } else {
             nprev = n;
             a.D = 1; a.T = 1; a.A = 1; a.tap_off = 0; a.M = n; a.G = nullptr;
             a.abs_first = abs_block;
             a.ring_first = wpos;
-            FE_TRY(fe, launch_mix_only(a, st));
+            FE_TRY(fe, launch_mix_only(a, s1s));
         }
-        if (nprev > 0) fe->launches++;
+        if (nprev > 0) { fe->launches++; s1_launch++; }
 
         if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
             TailArgs t{};
@@ -723,6 +733,10 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         tg.abs_out = g.st.abs_out;
         g.st.abs_out += nprev;
         g.last_n_final = nprev;
+    }
+    if (fork) {
+        FE_TRY(fe, cudaEventRecord(fe->ev_s1_join, fe->st_s1b));
+        FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_s1_join, 0));
     }
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[3], st));
     else {
@@ -1049,10 +1063,13 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
     if (cudaStreamCreateWithFlags(&fe->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&fe->st_tail, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
+        cudaStreamCreateWithFlags(&fe->st_tail, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_s1b, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
     if (cudaEventCreateWithFlags(&fe->ev_ingest, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_fft, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_s1_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_s1_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
     if (dev_alloc(&fe->ring, (size_t)1 << fe->ring_log2) != cudaSuccess) return bail("ring allocation failed");
@@ -1079,6 +1096,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_copy) cudaStreamSynchronize(fe->st_copy);
     if (fe->st_fft) cudaStreamSynchronize(fe->st_fft);
     if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
+    if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
     for (Vfo& v : fe->vfos) if (v.slab) cudaFree(v.slab);
     for (Group& g : fe->groups) if (g.d_G) cudaFree(g.d_G);
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
@@ -1104,7 +1122,8 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_copy) cudaStreamDestroy(fe->st_copy);
     if (fe->st_fft) cudaStreamDestroy(fe->st_fft);
     if (fe->st_tail) cudaStreamDestroy(fe->st_tail);
-    for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft, fe->ev_tail[0], fe->ev_tail[1] }) if (e) cudaEventDestroy(e);
+    if (fe->st_s1b) cudaStreamDestroy(fe->st_s1b);
+    for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft, fe->ev_tail[0], fe->ev_tail[1], fe->ev_s1_fork, fe->ev_s1_join }) if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete fe;
     return SDRPP_OK;
@@ -1117,6 +1136,7 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, cudaStreamSynchronize(fe->st));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_fft));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_tail));
+    FE_TRY(fe, cudaStreamSynchronize(fe->st_s1b));
     fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;
     // everything submitted so far is complete: nothing is left to wait for
     for (int i = 0; i < 2; i++) fe->rs[i].pending = false;
