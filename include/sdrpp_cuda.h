@@ -183,6 +183,28 @@ SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enab
 /* RxVFO::out for this block: returns the output sample count; *iq -> cf32[count];
  * *demod -> float[count] (NULL when demod == NONE). */
 SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cf32** iq, const float** demod);
+/* Post-detector stages of the demodulator behind a VFO, run on the device after the front end:
+ *   QUADRATURE: dsp::demod::FM<float>  -- optional low-pass FIR lowPass(bw/2, bw/20, outSR) (dsp/demod/fm.h:86-103,117-145)
+ *   AM:         dsp::demod::AM<float>  -- [carrier AGC] -> magnitude -> DC block -> [audio AGC] -> low-pass (dsp/demod/am.h:27-44,114-146)
+ *   USB/LSB/DSB: dsp::demod::SSB<float> -- AGC on the real output (dsp/demod/ssb.h:21-36,90-101)
+ * with dsp::loop::AGC (dsp/loop/agc.h:87-147: setPoint 1, maxGain 10e6, maxOutputAmp 10, initGain INFINITY) and
+ * dsp::correction::DCBlocker<float> (dsp/correction/dc_blocker.h:54-60). The radio module passes attack/decay/rate
+ * already divided by the IF sample rate (decoder_modules/radio/src/demodulators/am.h:38, usb.h:40). */
+typedef struct {
+    int enabled;           /* 0: front end only (sdrpp_cuda_vfo_audio is then an error) */
+    int fm_lowpass;        /* FM: _lowPass */
+    int am_agc_mode;       /* AM: dsp::demod::AM::AGCMode 0 OFF, 1 CARRIER, 2 AUDIO */
+    int ssb_agc;           /* SSB: agcEnabled */
+    double agc_attack;     /* per-sample attack coefficient */
+    double agc_decay;      /* per-sample decay coefficient */
+    double dc_block_rate;  /* AM: dcBlockRate */
+    float agc_gain;        /* > 0: setAGCGain(agc_gain) after init (the fixed gain when the audio AGC is off) */
+} sdrpp_cuda_post_cfg;
+/* (Re)initialises the VFO's post-detector objects; also redone when the VFO's bandwidth or rate changes. */
+SDRPP_API int sdrpp_cuda_vfo_set_post(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cuda_post_cfg* cfg);
+/* Demodulated audio of the last waited block: returns the sample count; *audio -> float[count]. */
+SDRPP_API int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int vfo, const float** audio);
+
 /* Spectrum rows completed in this block (each fft_size floats, the buffer handed to
  * acquireFFTBuffer/releaseFFTBuffer in the reference): returns the row count. */
 SDRPP_API int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows);

@@ -595,6 +595,148 @@ cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Post-detector stages. The AGC and the DC blocker are sequential recurrences with data-dependent
+// control flow (clip look-ahead, agc.h:106-121): thread 0 runs them with the reference's operation
+// order (_rn intrinsics: no contraction), everything else is parallel over the block's samples.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPostThreads = 128;
+constexpr int kPostTapFloats = 2048;
+
+struct AgcCoef { float attack, inv_attack, decay, inv_decay, set_point, max_gain, max_out; };
+
+// dsp::loop::AGC<T>::process (agc.h:87-147), enabled branch. amp_of(i) = |in[i]|; apply(i, gain) writes the output.
+template <class AmpFn, class ApplyFn>
+__device__ __forceinline__ void agc_run(const AgcCoef& c, float& amp, float& gain, int count, AmpFn amp_of, ApplyFn apply) {
+    for (int i = 0; i < count; i++) {
+        const float in_amp = amp_of(i);
+        if (in_amp != 0.0f) {
+            amp = (in_amp > amp) ? __fadd_rn(__fmul_rn(amp, c.inv_attack), __fmul_rn(in_amp, c.attack))
+                                 : __fadd_rn(__fmul_rn(amp, c.inv_decay), __fmul_rn(in_amp, c.decay));
+            gain = fminf(__fdiv_rn(c.set_point, amp), c.max_gain);
+        } else {
+            gain = 1.0f;
+        }
+        if (__fmul_rn(in_amp, gain) > c.max_out) { // clipping ahead: restart from the largest amplitude left in the block
+            float max_amp = 0.0f;
+            for (int j = i; j < count; j++) { const float v = amp_of(j); if (v > max_amp) max_amp = v; }
+            amp = max_amp;
+            gain = fminf(__fdiv_rn(c.set_point, amp), c.max_gain);
+        }
+        apply(i, gain);
+    }
+}
+
+// FIR<float,float>::process (fir.h:62-83) on buf = [ntaps-1 history | n samples] (history directly in front of
+// `work`), result to out; then the last ntaps-1 samples become the history.
+__device__ __forceinline__ void post_fir(float* work, int n, const float* __restrict__ staps, int ntaps, float* __restrict__ out) {
+    const float* buf = work - (ntaps - 1);
+    for (int i = threadIdx.x; i < n; i += kPostThreads) {
+        float acc = 0.0f;
+        for (int k = 0; k < ntaps; k++) acc = fmaf(buf[i + k], staps[k], acc);
+        out[i] = acc;
+    }
+    __syncthreads();
+    const int hist = ntaps - 1;
+    float keep[kPostTapFloats / kPostThreads];
+    int c = 0;
+    for (int j = threadIdx.x; j < hist; j += kPostThreads, c++) keep[c] = buf[n + j];
+    __syncthreads();
+    c = 0;
+    for (int j = threadIdx.x; j < hist; j += kPostThreads, c++) work[j - hist] = keep[c];
+}
+
+__global__ void __launch_bounds__(kPostThreads)
+post_kernel(const __grid_constant__ PostArgs a) {
+    __shared__ float staps[kPostTapFloats];
+    int vi = blockIdx.x, gi = 0;
+    while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
+    const int n = a.g[gi].n;
+    const PostDev pd = a.post[a.g[gi].first_vfo + vi];
+    if (pd.kind == POST_NONE || n <= 0) return;
+    const int tid = threadIdx.x;
+    const float2* __restrict__ iq = a.arena_iq + pd.out_off;
+    const float* __restrict__ dm = a.arena_demod + pd.out_off;
+    float* __restrict__ out = a.arena_audio + pd.out_off;
+    float* st = pd.state;
+    float* work = st + 16 + pd.hist_pad;
+    const AgcCoef c{ pd.attack, pd.inv_attack, pd.decay, pd.inv_decay, pd.set_point, pd.max_gain, pd.max_out };
+    for (int i = tid; i < pd.ntaps; i += kPostThreads) staps[i] = pd.taps[i];
+
+    if (pd.kind == POST_FM) {
+        if (pd.ntaps > 0) {
+            for (int i = tid; i < n; i += kPostThreads) work[i] = dm[i];
+            __syncthreads();
+            post_fir(work, n, staps, pd.ntaps, out);
+        } else {
+            for (int i = tid; i < n; i += kPostThreads) out[i] = dm[i];
+        }
+    } else if (pd.kind == POST_AM) {
+        if (pd.mode == 1) {
+            // carrier AGC on the complex samples (always enabled, am.h:38), then the magnitude of the scaled sample
+            if (tid == 0) {
+                float amp = st[2], gain = st[3];
+                agc_run(c, amp, gain, n,
+                        [&](int i) { const float2 v = iq[i]; return __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))); },
+                        [&](int i, float g) {
+                            const float2 v = iq[i];
+                            const float re = __fmul_rn(v.x, g), im = __fmul_rn(v.y, g);
+                            work[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+                        });
+                st[2] = amp; st[3] = gain;
+            }
+        } else {
+            for (int i = tid; i < n; i += kPostThreads) work[i] = dm[i];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // DCBlocker<float> (dc_blocker.h:54-60), then the audio AGC unless the carrier AGC is in use
+            float off = st[4];
+            for (int i = 0; i < n; i++) {
+                const float o = __fadd_rn(work[i], -off);
+                work[i] = o;
+                off = __fadd_rn(off, __fmul_rn(o, pd.dc_rate));
+            }
+            st[4] = off;
+            if (pd.mode != 1) {
+                float amp = st[0], gain = st[1];
+                if (pd.mode == 2) {
+                    agc_run(c, amp, gain, n, [&](int i) { return fabsf(work[i]); }, [&](int i, float g) { work[i] = __fmul_rn(work[i], g); });
+                } else {
+                    // disabled AGC: fixed gain with clipping to max_out (agc.h:126-143)
+                    for (int i = 0; i < n; i++) {
+                        const float v = work[i], in_amp = fabsf(v);
+                        work[i] = (__fmul_rn(in_amp, gain) > c.max_out) ? __fmul_rn(v, __fdiv_rn(c.max_out, in_amp)) : __fmul_rn(v, gain);
+                    }
+                }
+                st[0] = amp; st[1] = gain;
+            }
+        }
+        __syncthreads();
+        post_fir(work, n, staps, pd.ntaps, out);
+    } else {
+        if (tid == 0) {
+            float amp = st[0], gain = st[1];
+            if (pd.mode == 1) {
+                agc_run(c, amp, gain, n, [&](int i) { return fabsf(dm[i]); }, [&](int i, float g) { out[i] = __fmul_rn(dm[i], g); });
+            } else {
+                for (int i = 0; i < n; i++) {
+                    const float v = dm[i], in_amp = fabsf(v);
+                    out[i] = (__fmul_rn(in_amp, gain) > c.max_out) ? __fmul_rn(v, __fdiv_rn(c.max_out, in_amp)) : __fmul_rn(v, gain);
+                }
+            }
+            st[0] = amp; st[1] = gain;
+        }
+    }
+}
+
+cudaError_t launch_post(const PostArgs& a, int total_vfos, cudaStream_t st) {
+    if (total_vfos <= 0) return cudaSuccess;
+    post_kernel<<<total_vfos, kPostThreads, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 } // namespace sdrpp
 
 #ifdef SDRPP_S1_TRACE

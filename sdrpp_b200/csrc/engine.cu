@@ -185,6 +185,11 @@ struct Vfo {
     float2* slab = nullptr;
     uint32_t out_off = 0;
     int dev_index = -1;
+    // post-detector stages
+    sdrpp_cuda_post_cfg post{};
+    float* post_state = nullptr;   // device: scalars | FIR history | work area
+    float* post_taps = nullptr;    // device
+    int post_ntaps = 0, post_hist_pad = 0;
 };
 
 struct Group {
@@ -202,6 +207,7 @@ struct Group {
 struct ResultSet {
     sdrpp_cf32* iq = nullptr;
     float* demod = nullptr;
+    float* audio = nullptr;
     float* rows = nullptr;
     float* zoom = nullptr;
     int nrows = 0;
@@ -263,7 +269,8 @@ struct sdrpp_cuda_frontend {
     std::map<std::tuple<double, double, double>, std::weak_ptr<VfoPlan>> plan_cache;
     bool layout_dirty = true;
     VfoDev* d_vfos = nullptr; int d_vfos_cap = 0;
-    float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; size_t arena_cap = 0, arena_used = 0;
+    PostDev* d_post = nullptr; int post_active = 0; // per-VFO post-detector records (same indexing as d_vfos)
+    float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; float* d_arena_audio = nullptr; size_t arena_cap = 0, arena_used = 0;
 
     // results
     ResultSet rs[2];
@@ -402,6 +409,8 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
     size_t arena = 0;
     for (Group& g : fe->groups) { g.first_dev = total; total += (int)g.members.size(); }
     std::vector<VfoDev> h((size_t)std::max(total, 1));
+    std::vector<PostDev> hp((size_t)std::max(total, 1));
+    fe->post_active = 0;
     for (Group& g : fe->groups) {
         for (size_t i = 0; i < g.members.size(); i++) {
             Vfo& v = fe->vfos[(size_t)g.members[i]];
@@ -411,6 +420,19 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
             VfoDev& d = h[(size_t)v.dev_index];
             d.slab = v.slab; d.phi_ref = v.phi_ref; d.n_ref = v.n_ref; d.dphi = v.dphi; d.dphi2 = v.dphi2;
             d.out_off = v.out_off; d.pad = 0;
+            PostDev& pd = hp[(size_t)v.dev_index];
+            pd = PostDev{};
+            if (v.post.enabled && v.post_state) {
+                pd.kind = v.demod == SDRPP_DEMOD_QUADRATURE ? POST_FM : v.demod == SDRPP_DEMOD_AM ? POST_AM : POST_SSB;
+                pd.mode = pd.kind == POST_FM ? (v.post.fm_lowpass != 0) : pd.kind == POST_AM ? v.post.am_agc_mode : (v.post.ssb_agc != 0);
+                pd.ntaps = v.post_ntaps; pd.hist_pad = v.post_hist_pad; pd.taps = v.post_taps; pd.state = v.post_state;
+                pd.out_off = v.out_off;
+                // AGC::init(NULL, 1.0, attack, decay, 10e6, 10.0, INFINITY) (am.h:32-33, ssb.h:27); coefficients as floats (agc.h:22-33)
+                pd.attack = (float)v.post.agc_attack; pd.inv_attack = 1.0f - pd.attack;
+                pd.decay = (float)v.post.agc_decay; pd.inv_decay = 1.0f - pd.decay;
+                pd.dc_rate = (float)v.post.dc_block_rate; pd.set_point = 1.0f; pd.max_gain = (float)10e6; pd.max_out = 10.0f;
+                fe->post_active++;
+            }
         }
         if (g.plan->s1_fir && g.g_dirty) {
             const size_t n = stage1_g_elems(g.plan->s1_A, g.plan->s1_D, (int)g.members.size());
@@ -424,12 +446,14 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         }
     }
     if (total > fe->d_vfos_cap) {
-        if (fe->d_vfos) { FE_TRY(fe, cudaStreamSynchronize(fe->st)); cudaFree(fe->d_vfos); }
+        if (fe->d_vfos) { FE_TRY(fe, cudaStreamSynchronize(fe->st)); cudaFree(fe->d_vfos); cudaFree(fe->d_post); }
         fe->d_vfos_cap = std::max(total, 64);
         FE_TRY(fe, dev_alloc(&fe->d_vfos, (size_t)fe->d_vfos_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_post, (size_t)fe->d_vfos_cap));
     }
     if (total > 0) {
         FE_TRY(fe, cudaMemcpyAsync(fe->d_vfos, h.data(), sizeof(VfoDev) * (size_t)total, cudaMemcpyHostToDevice, fe->st));
+        FE_TRY(fe, cudaMemcpyAsync(fe->d_post, hp.data(), sizeof(PostDev) * (size_t)total, cudaMemcpyHostToDevice, fe->st));
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
     }
     fe->arena_used = arena;
@@ -437,17 +461,21 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
         if (fe->d_arena_iq) cudaFree(fe->d_arena_iq);
         if (fe->d_arena_demod) cudaFree(fe->d_arena_demod);
+        if (fe->d_arena_audio) cudaFree(fe->d_arena_audio);
         fe->arena_cap = arena + arena / 2 + 1024;
         FE_TRY(fe, dev_alloc(&fe->d_arena_iq, fe->arena_cap));
         FE_TRY(fe, dev_alloc(&fe->d_arena_demod, fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_audio, fe->arena_cap));
     }
     if (arena > fe->rs_arena_cap) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
         for (int i = 0; i < 2; i++) {
             if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
             if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
+            if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
             FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].iq, fe->arena_cap * sizeof(sdrpp_cf32)));
             FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].demod, fe->arena_cap * sizeof(float)));
+            FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].audio, fe->arena_cap * sizeof(float)));
         }
         fe->rs_arena_cap = fe->arena_cap;
     }
@@ -541,6 +569,37 @@ static int get_plan(sdrpp_cuda_frontend* fe, double outSR, double bw, std::share
     if (rc != SDRPP_OK) return fail(rc, err);
     fe->plan_cache[key] = sp;
     *out = sp;
+    return SDRPP_OK;
+}
+
+// (Re)build the post-detector objects of a VFO for its current (demod, outSR, bw): the demodulators' init()
+// (fm.h:25-44, am.h:27-44, ssb.h:21-36). Filter and AGC state start from reset.
+static int apply_post(sdrpp_cuda_frontend* fe, Vfo& v) {
+    cudaFree(v.post_state); cudaFree(v.post_taps);
+    v.post_state = nullptr; v.post_taps = nullptr; v.post_ntaps = 0; v.post_hist_pad = 0;
+    fe->layout_dirty = true;
+    if (!v.post.enabled) return SDRPP_OK;
+    if (v.demod == SDRPP_DEMOD_NONE) return fail(SDRPP_ERR_STATE, "post-detector stages need a demodulator front end");
+    std::vector<float> taps;
+    const bool fm = v.demod == SDRPP_DEMOD_QUADRATURE, am = v.demod == SDRPP_DEMOD_AM;
+    if ((fm && v.post.fm_lowpass) || am) {
+        const double fw = v.bw / 2.0; // lowPass(bandwidth / 2, (bandwidth / 2) * 0.1, samplerate): fm.h:121-123, am.h:35
+        taps = design_lowpass(fw, fw * 0.1, v.outSR);
+        if (taps.empty() || taps.size() > 2048) return fail(SDRPP_ERR_ARG, "post-detector low-pass must have 1..2048 taps");
+    }
+    if (am && (v.post.am_agc_mode < 0 || v.post.am_agc_mode > 2)) return fail(SDRPP_ERR_ARG, "am_agc_mode must be 0 (off), 1 (carrier) or 2 (audio)");
+    v.post_ntaps = (int)taps.size();
+    v.post_hist_pad = (std::max(v.post_ntaps - 1, 0) + 3) & ~3;
+    const size_t n = 16 + (size_t)v.post_hist_pad + (size_t)v.plan->cap_final + 8;
+    FE_TRY(fe, dev_alloc(&v.post_state, n));
+    if (!taps.empty()) {
+        FE_TRY(fe, dev_alloc(&v.post_taps, taps.size(), false));
+        FE_TRY(fe, cudaMemcpy(v.post_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    // AGC::init(.., maxGain = 10e6, .., initGain = INFINITY): amp = setPoint / initGain = 0, gain = min(initGain, maxGain)
+    float init[5] = { 0.0f, (float)10e6, 0.0f, (float)10e6, 0.0f };
+    if (v.post.agc_gain > 0.0f) init[1] = v.post.agc_gain; // setAGCGain (am.h:69-73, ssb.h)
+    FE_TRY(fe, cudaMemcpy(v.post_state, init, sizeof(init), cudaMemcpyHostToDevice));
     return SDRPP_OK;
 }
 
@@ -747,6 +806,20 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         FE_TRY(fe, launch_tail(tails[i], tail_totals[i], stl));
         if (tail_totals[i] > 0) fe->launches++;
     }
+    if (fe->post_active > 0) {
+        // post-detector stages of the VFOs that have them, on the outputs the tail just wrote
+        for (size_t i = 0; i < tails.size(); i++) {
+            PostArgs pa{};
+            pa.ngroups = tails[i].ngroups;
+            bool any = false;
+            for (int k = 0; k < pa.ngroups; k++) {
+                pa.g[k].first_vfo = tails[i].g[k].first_vfo; pa.g[k].nvfo = tails[i].g[k].nvfo; pa.g[k].n = tails[i].g[k].n_final;
+                any = any || pa.g[k].n > 0;
+            }
+            pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq; pa.arena_demod = fe->d_arena_demod; pa.arena_audio = fe->d_arena_audio;
+            if (any && tail_totals[i] > 0) { FE_TRY(fe, launch_post(pa, tail_totals[i], stl)); fe->launches++; }
+        }
+    }
     if (prof) { FE_TRY(fe, cudaEventRecord(fe->pev[4], st)); fe->pev_valid = true; }
 
     // ---- results to pinned host memory --------------------------------------------------------------
@@ -756,6 +829,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     if (fe->readback && fe->arena_used > 0) {
         FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, stl));
         FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, stl));
+        if (fe->post_active > 0)
+            FE_TRY(fe, cudaMemcpyAsync(rs.audio, fe->d_arena_audio, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, stl));
     }
     if (!prof) {
         FE_TRY(fe, cudaEventRecord(fe->ev_tail[par], stl));
@@ -1097,7 +1172,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_fft) cudaStreamSynchronize(fe->st_fft);
     if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
-    for (Vfo& v : fe->vfos) if (v.slab) cudaFree(v.slab);
+    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); }
     for (Group& g : fe->groups) if (g.d_G) cudaFree(g.d_G);
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
     for (float* t : fe->fe_taps) cudaFree(t);
@@ -1105,7 +1180,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     cudaFree(fe->dc_in); cudaFree(fe->dc_state); cudaFree(fe->dc_scratch);
     cudaFree(fe->ring); cudaFree(fe->d_window); cudaFree(fe->d_inter); cudaFree(fe->d_rows);
     cudaFree(fe->d_zoom_idx); cudaFree(fe->d_zoom);
-    cudaFree(fe->d_vfos); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod);
+    cudaFree(fe->d_vfos); cudaFree(fe->d_post); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod); cudaFree(fe->d_arena_audio);
     for (int i = 0; i < 2; i++) {
         if (fe->h_stage[i]) cudaFreeHost(fe->h_stage[i]);
         if (fe->d_raw[i]) cudaFree(fe->d_raw[i]);
@@ -1114,6 +1189,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->rs[i].done) cudaEventDestroy(fe->rs[i].done);
         if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
         if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
+        if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
         if (fe->rs[i].rows) cudaFreeHost(fe->rs[i].rows);
         if (fe->rs[i].zoom) cudaFreeHost(fe->rs[i].zoom);
     }
@@ -1159,6 +1235,7 @@ static int replan_all(sdrpp_cuda_frontend* fe) {
         FE_TRY(fe, dev_alloc(&v.slab, plan->slab_elems));
         set_nco(fe, v, v.offset, true);
         join_group(fe, (int)id, fe->abs_pos);
+        if (v.post.enabled && (rc = apply_post(fe, v)) != SDRPP_OK) return rc;
     }
     return SDRPP_OK;
 }
@@ -1250,6 +1327,7 @@ int sdrpp_cuda_vfo_destroy(sdrpp_cuda_frontend* fe, int id) {
     if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
     remove_from_group(fe, id);
     if (v->slab) cudaFree(v->slab);
+    cudaFree(v->post_state); cudaFree(v->post_taps);
     *v = Vfo();
     return SDRPP_OK;
 }
@@ -1279,6 +1357,7 @@ static int vfo_replan(sdrpp_cuda_frontend* fe, int id, double outSR, double bw, 
     set_nco(fe, *v, v->offset, true);
     (void)new_epoch;
     join_group(fe, id, fe->abs_pos);
+    if (v->post.enabled) return apply_post(fe, *v); // the demodulator's filter follows the bandwidth / rate
     return SDRPP_OK;
 }
 
@@ -1308,6 +1387,7 @@ int sdrpp_cuda_vfo_set_bandwidth(sdrpp_cuda_frontend* fe, int id, double bw) {
     v->bw = bw; v->plan = np;
     set_nco(fe, *v, v->offset, true); // SSB translation follows the bandwidth; NCO phase continues
     join_group_with_state(fe, id, st);
+    if (v->post.enabled) return apply_post(fe, *v);
     return SDRPP_OK;
 }
 int sdrpp_cuda_vfo_set_out_samplerate(sdrpp_cuda_frontend* fe, int id, double outSR, double bw) {
@@ -1385,6 +1465,30 @@ int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int id, const sdrpp_cf32** iq
     if (iq) *iq = rs.iq ? rs.iq + v->out_off : nullptr;
     if (demod) *demod = (v->demod != SDRPP_DEMOD_NONE && rs.demod) ? rs.demod + v->out_off : nullptr;
     return n;
+}
+
+int sdrpp_cuda_vfo_set_post(sdrpp_cuda_frontend* fe, int id, const sdrpp_cuda_post_cfg* cfg) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    if (!cfg) return fail(SDRPP_ERR_ARG, "null cfg");
+    if (cfg->enabled && (!(cfg->agc_attack >= 0) || !(cfg->agc_decay >= 0) || !(cfg->dc_block_rate >= 0))) return fail(SDRPP_ERR_ARG, "negative coefficient");
+    const sdrpp_cuda_post_cfg old = v->post;
+    v->post = *cfg;
+    if ((rc = apply_post(fe, *v)) != SDRPP_OK) { v->post = old; v->post.enabled = 0; apply_post(fe, *v); return rc; }
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int id, const float** audio) {
+    Vfo* v;
+    int rc = vfo_get(fe, id, &v);
+    if (rc != SDRPP_OK) return rc;
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    if (!v->post.enabled) return fail(SDRPP_ERR_STATE, "post-detector stages are not enabled for this VFO");
+    const ResultSet& rs = fe->rs[fe->cur];
+    if (audio) *audio = rs.audio ? rs.audio + v->out_off : nullptr;
+    return (size_t)id < rs.counts.size() ? rs.counts[(size_t)id] : 0;
 }
 
 int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows) {

@@ -128,4 +128,29 @@ struct TailArgs {
 };
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st);
 
+// Post-detector stages of the three demodulators: FM low-pass (dsp/demod/fm.h:86-103), AM
+// [carrier AGC] -> magnitude -> DC block -> [audio AGC] -> low-pass (dsp/demod/am.h:114-146), SSB AGC
+// (dsp/demod/ssb.h:90-101); dsp::loop::AGC (dsp/loop/agc.h:87-147). One CTA per VFO, after the tail.
+enum { POST_NONE = 0, POST_FM = 1, POST_AM = 2, POST_SSB = 3 };
+struct PostDev {
+    int kind;            // POST_*
+    int mode;            // FM: 1 = low-pass; AM: AGCMode (0 OFF, 1 CARRIER, 2 AUDIO); SSB: 1 = AGC enabled
+    int ntaps;           // float FIR taps (0: no filter)
+    int hist_pad;        // floats reserved for the FIR history in front of the work area (>= ntaps - 1)
+    const float* taps;
+    float* state;        // [0] audio amp [1] audio gain [2] carrier amp [3] carrier gain [4] dc offset, ... [16 ..] history | work
+    uint32_t out_off;    // offset of this VFO's rows in the output arenas (samples)
+    float attack, inv_attack, decay, inv_decay;
+    float dc_rate, set_point, max_gain, max_out;
+};
+struct PostArgs {
+    int ngroups;
+    struct { int first_vfo, nvfo, n; } g[kTailMaxGroups];
+    const PostDev* post;          // indexed like the VfoDev table
+    const float2* arena_iq;
+    const float* arena_demod;
+    float* arena_audio;
+};
+cudaError_t launch_post(const PostArgs& a, int total_vfos, cudaStream_t st);
+
 } // namespace sdrpp

@@ -33,6 +33,7 @@ sdrpp_cuda_frontend_submit sdrpp_cuda_frontend_submit_device sdrpp_cuda_frontend
 sdrpp_cuda_frontend_set_readback sdrpp_cuda_vfo_output sdrpp_cuda_fft_rows sdrpp_cuda_frontend_read_iq
 sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_profiling
 sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
+sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -42,6 +43,11 @@ class FrontendCfg(C.Structure):
     _fields_ = [("sample_rate", _d), ("decim_ratio", _i), ("dc_blocking", _i), ("invert_iq", _i),
                 ("fft_size", _i), ("fft_rate", _d), ("fft_window", _i), ("max_block", _i),
                 ("ring_log2", _i), ("max_fft_rows", _i)]
+
+
+class PostCfg(C.Structure):
+    _fields_ = [("enabled", _i), ("fm_lowpass", _i), ("am_agc_mode", _i), ("ssb_agc", _i),
+                ("agc_attack", _d), ("agc_decay", _d), ("dc_block_rate", _d), ("agc_gain", C.c_float)]
 
 
 class SdrppCudaError(RuntimeError):
@@ -97,6 +103,8 @@ def lib():
         L.sdrpp_cuda_frontend_wait.argtypes = [_vp]
         L.sdrpp_cuda_vfo_output.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]
         L.sdrpp_cuda_fft_rows.argtypes = [_vp, C.POINTER(_vp)]
+        L.sdrpp_cuda_vfo_set_post.argtypes = [_vp, _i, C.POINTER(PostCfg)]
+        L.sdrpp_cuda_vfo_audio.argtypes = [_vp, _i, C.POINTER(_vp)]
         L.sdrpp_cuda_frontend_read_iq.argtypes = [_vp, _vp, _i]
         L.sdrpp_cuda_frontend_launches.restype = C.c_longlong
         L.sdrpp_cuda_frontend_launches.argtypes = [_vp]
@@ -336,6 +344,19 @@ class Frontend:
         if dm.value:
             d = np.ctypeslib.as_array(C.cast(dm, C.POINTER(C.c_float)), shape=(n,))
         return (a.copy(), d.copy() if d is not None else None) if copy else (a, d)
+
+    def set_post(self, vid, enabled=True, fm_lowpass=True, am_agc_mode=0, ssb_agc=True, agc_attack=0.0, agc_decay=0.0,
+                 dc_block_rate=0.0, agc_gain=0.0):
+        """Post-detector stages of the demodulator behind the VFO (dsp::demod::FM / AM / SSB)."""
+        cfg = PostCfg(int(enabled), int(fm_lowpass), int(am_agc_mode), int(ssb_agc), agc_attack, agc_decay, dc_block_rate, agc_gain)
+        _check(lib().sdrpp_cuda_vfo_set_post(self.h, vid, C.byref(cfg)), "vfo_set_post")
+
+    def vfo_audio(self, vid):
+        p = _vp()
+        n = _check(lib().sdrpp_cuda_vfo_audio(self.h, vid, C.byref(p)), "vfo_audio")
+        if n == 0:
+            return np.zeros(0, np.float32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).copy()
 
     def fft_rows(self, copy=True):
         p = _vp()

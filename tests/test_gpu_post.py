@@ -1,0 +1,136 @@
+"""GPU parity: post-detector stages of the three demodulators -- dsp::demod::FM<float> low-pass,
+dsp::demod::AM<float> carrier/audio AGC + DC blocker + low-pass, dsp::demod::SSB<float> AGC -- through the C ABI.
+
+The stages are checked in isolation: the oracle's complete demodulator is fed the GPU's own VFO output (cf32), so
+the only differences left are those of the stages under test (the VFO itself is gated in test_gpu_channelizer.py).
+The AGC and DC blocker recurrences use the reference's operation order, so their gate is 1e-5 relative RMS; the FM
+branch inherits the discriminator's 2e-4 gate (atan2f implementations differ by ~1 ulp)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+IN_SR, BLK = 2.4e6, 12000
+
+
+def stream(nblocks, offset, seed):
+    """A carrier at `offset` with AM + FM modulation and level steps (AGC attack, decay and clip look-ahead fire)."""
+    rng = np.random.default_rng(seed)
+    n = nblocks * BLK
+    t = np.arange(n) / IN_SR
+    m = 0.5 * np.sin(2 * np.pi * 700.0 * t) + 0.3 * np.sin(2 * np.pi * 1900.0 * t)
+    level = np.where(t < 0.3 * t[-1], 0.02, np.where(t < 0.6 * t[-1], 0.5, 0.0005))
+    ph = 2 * np.pi * ((offset * t) % 1.0) + 2 * np.pi * 1500.0 * np.cumsum(m) / IN_SR
+    x = level * (1.0 + 0.8 * m) * np.exp(1j * ph) + 1e-5 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    x = x.astype(np.complex64)
+    return [x[i * BLK:(i + 1) * BLK] for i in range(nblocks)]
+
+
+def run(gpu, vfo, post, blocks, sizes=None):
+    iq, audio = [], []
+    with gpu.Frontend(IN_SR, max_block=BLK) as fe:
+        vid = fe.add_vfo(*vfo)
+        fe.set_post(vid, **post)
+        for b in blocks:
+            fe.process(po.FMT_CF32, b)
+            y, _ = fe.vfo_output(vid)
+            a = fe.vfo_audio(vid)
+            assert len(a) == len(y)
+            iq.append(y); audio.append(a)
+    return iq, audio
+
+
+CASES = [
+    ("fm_nfm_lp", (48e3, 12.5e3, 100e3, po.DEMOD_QUAD), dict(fm_lowpass=True), lambda o: o.fm_full(48e3, 12.5e3, True), 2e-4),
+    ("fm_wfm_lp", (250e3, 200e3, -300e3, po.DEMOD_QUAD), dict(fm_lowpass=True), lambda o: o.fm_full(250e3, 200e3, True), 2e-4),
+    ("fm_nolp", (48e3, 12.5e3, 100e3, po.DEMOD_QUAD), dict(fm_lowpass=False), lambda o: o.fm_full(48e3, 12.5e3, False), 2e-4),
+    ("am_off", (24e3, 12e3, 100e3, po.DEMOD_AM), dict(am_agc_mode=0, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3, agc_gain=3.0),
+     lambda o: o.am_full(0, 12e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3, 3.0), 1e-5),
+    ("am_carrier", (24e3, 12e3, 100e3, po.DEMOD_AM), dict(am_agc_mode=1, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3),
+     lambda o: o.am_full(1, 12e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3), 1e-5),
+    ("am_audio", (24e3, 12e3, 100e3, po.DEMOD_AM), dict(am_agc_mode=2, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3),
+     lambda o: o.am_full(2, 12e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3), 1e-5),
+    ("usb_agc", (48e3, 2.7e3, 100e3, po.DEMOD_USB), dict(ssb_agc=True, agc_attack=50 / 48e3, agc_decay=5 / 48e3),
+     lambda o: o.ssb_full(0, 2.7e3, 48e3, True, 50 / 48e3, 5 / 48e3), 3e-5),
+    ("lsb_fixed", (48e3, 2.7e3, 100e3, po.DEMOD_LSB), dict(ssb_agc=False, agc_attack=50 / 48e3, agc_decay=5 / 48e3, agc_gain=2.0),
+     None, 3e-5),
+]
+
+
+@pytest.mark.parametrize("name,vfo,post,make,tol", CASES, ids=[c[0] for c in CASES])
+def test_post_detector_stage(gpu, port, name, vfo, post, make, tol):
+    blocks = stream(10, vfo[2], 21)
+    iq, audio = run(gpu, vfo, post, blocks)
+    if make is None:
+        # SSB with the AGC off: fixed gain with clipping (agc.h:126-143) on the GPU's own front-end output
+        with gpu.Frontend(IN_SR, max_block=BLK) as fe:
+            vid = fe.add_vfo(*vfo)
+            ref = []
+            for b in blocks:
+                fe.process(po.FMT_CF32, b)
+                d = fe.vfo_output(vid)[1].astype(np.float32)
+                g = np.float32(post["agc_gain"])
+                amp = np.abs(d)
+                with np.errstate(divide="ignore", invalid="ignore"):
+                    ref.append(np.where(amp * g > np.float32(10.0), d * (np.float32(10.0) / amp), d * g).astype(np.float32))
+    else:
+        o = make(port)
+        ref = [o.process(y) if len(y) else np.zeros(0, np.float32) for y in iq]
+    ga, ra = np.concatenate(audio), np.concatenate(ref)
+    assert len(ga) == len(ra) and len(ga) > 500
+    assert np.all(np.isfinite(ga))
+    if vfo[3] == po.DEMOD_QUAD:
+        err = np.sqrt(np.mean((ga - ra) ** 2)) / max(np.sqrt(np.mean(ra ** 2)), 1e-3)
+    else:
+        err = po.rel_rms(ga, ra)
+    assert err <= tol, f"{name}: rel-RMS {err:.3e}"
+
+
+def test_post_follows_bandwidth_and_disable(gpu, port):
+    """setBandwidth re-designs the demodulator's low-pass (am.h:46-55); disabling removes the audio output."""
+    blocks = stream(6, 50e3, 22)
+    with gpu.Frontend(IN_SR, max_block=BLK) as fe:
+        vid = fe.add_vfo(24e3, 12e3, 50e3, po.DEMOD_AM)
+        fe.set_post(vid, am_agc_mode=2, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3)
+        for b in blocks[:2]:
+            fe.process(po.FMT_CF32, b)
+        fe.vfo_set_bandwidth(vid, 8e3)
+        o = port.am_full(2, 8e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3)
+        got, want = [], []
+        for b in blocks[2:]:
+            fe.process(po.FMT_CF32, b)
+            y, _ = fe.vfo_output(vid)
+            got.append(fe.vfo_audio(vid)); want.append(o.process(y))
+        assert po.rel_rms(np.concatenate(got), np.concatenate(want)) <= 1e-5
+        fe.set_post(vid, enabled=False)
+        fe.process(po.FMT_CF32, blocks[0])
+        with pytest.raises(gpu.SdrppCudaError):
+            fe.vfo_audio(vid)
+
+
+def test_post_many_vfos_mixed(gpu, port):
+    """Post stages on a subset of a mixed VFO set: only those VFOs get audio, the others are untouched."""
+    blocks = stream(4, 100e3, 23)
+    vf = [(48e3, 12.5e3, 100e3, po.DEMOD_QUAD), (24e3, 12e3, 100e3, po.DEMOD_AM), (48e3, 2.7e3, 100e3, po.DEMOD_USB),
+          (48e3, 12.5e3, -200e3, po.DEMOD_QUAD), (24e3, 12e3, 100e3, po.DEMOD_AM)]
+    with gpu.Frontend(IN_SR, max_block=BLK) as fe:
+        ids = [fe.add_vfo(*v) for v in vf]
+        fe.set_post(ids[0], fm_lowpass=True)
+        fe.set_post(ids[1], am_agc_mode=1, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3)
+        fe.set_post(ids[2], ssb_agc=True, agc_attack=50 / 48e3, agc_decay=5 / 48e3)
+        os_ = [port.fm_full(48e3, 12.5e3, True), port.am_full(1, 12e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3),
+               port.ssb_full(0, 2.7e3, 48e3, True, 50 / 48e3, 5 / 48e3)]
+        got, want = [[], [], []], [[], [], []]
+        for b in blocks:
+            fe.process(po.FMT_CF32, b)
+            for k in range(3):
+                y, _ = fe.vfo_output(ids[k])
+                got[k].append(fe.vfo_audio(ids[k])); want[k].append(os_[k].process(y))
+            with pytest.raises(gpu.SdrppCudaError):
+                fe.vfo_audio(ids[3])
+        for k, tol in ((0, 2e-4), (1, 1e-5), (2, 3e-5)):
+            g, w = np.concatenate(got[k]), np.concatenate(want[k])
+            err = np.sqrt(np.mean((g - w) ** 2)) / max(np.sqrt(np.mean(w ** 2)), 1e-3)
+            assert err <= tol, (k, err)

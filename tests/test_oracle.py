@@ -93,6 +93,15 @@ def test_port_matches_reference_pieces(port, ref):
     assert np.array_equal(_bits(ra[0]), _bits(rb[0])) and np.array_equal(ra[1], rb[1])
 
 
+def test_port_matches_reference_full_demods(port, ref):
+    """dsp::demod::FM/AM/SSB<float> including AGC (clip look-ahead), DC blocker and the audio low-pass."""
+    from tools.make_golden import POST_CASES, make_post, post_input
+    for name, kind, a in POST_CASES:
+        da, db = make_post(port, kind, a), make_post(ref, kind, a)
+        for blk in post_input(a["sr"], a["seed"] + 100):
+            assert np.array_equal(_bits(da.process(blk)), _bits(db.process(blk))), name
+
+
 # ---- golden vectors generated from the compiled reference (travel to the GPU box) -----------------------------
 def _golden_cases():
     p = os.path.join(GOLD, "manifest.json")
@@ -140,6 +149,12 @@ def test_port_matches_golden(port, case):
         rng = np.random.default_rng(case["seed"])
         row = (rng.standard_normal(int(N)) * 10.0 - 80.0).astype(np.float32)
         got, _ = port.fft_zoom(vo, vb, wb, row, int(out))
+        assert np.array_equal(_bits(got), _bits(data["out"]))
+    elif kind == "post":
+        from tools.make_golden import make_post, post_input
+        a = case["params"]
+        d = make_post(port, case["args"][0], a)
+        got = np.concatenate([d.process(b) for b in post_input(a["sr"], a["seed"])])
         assert np.array_equal(_bits(got), _bits(data["out"]))
     else:
         pytest.fail("unknown golden kind " + kind)

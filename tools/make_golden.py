@@ -17,6 +17,43 @@ from sdrpp_b200 import synth  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 
+POST_CASES = [
+    ("fm_nfm_lp", "fm", dict(sr=48e3, bw=12.5e3, low_pass=1, seed=11)),
+    ("fm_wfm_nolp", "fm", dict(sr=250e3, bw=200e3, low_pass=0, seed=12)),
+    ("am_off_gain", "am", dict(sr=24e3, bw=12e3, mode=0, attack=50.0 / 24e3, decay=5.0 / 24e3, dc=100.0 / 24e3, gain=3.0, seed=13)),
+    ("am_carrier", "am", dict(sr=24e3, bw=12e3, mode=1, attack=50.0 / 24e3, decay=5.0 / 24e3, dc=100.0 / 24e3, gain=0.0, seed=14)),
+    ("am_audio", "am", dict(sr=24e3, bw=12e3, mode=2, attack=50.0 / 24e3, decay=5.0 / 24e3, dc=100.0 / 24e3, gain=0.0, seed=15)),
+    ("usb_agc", "ssb", dict(sr=48e3, bw=2.7e3, mode=0, agc=1, attack=50.0 / 48e3, decay=5.0 / 48e3, seed=16)),
+    ("lsb_noagc", "ssb", dict(sr=48e3, bw=2.7e3, mode=1, agc=0, attack=50.0 / 48e3, decay=5.0 / 48e3, seed=17)),
+]
+
+
+def post_input(sr, seed):
+    """VFO-rate test stream in ragged blocks: AM+FM modulated carrier with level steps (AGC attack, decay and the
+    clip look-ahead all fire), plus noise."""
+    rng = np.random.default_rng(seed)
+    sizes = [int(sr / 200), 1, 777, int(sr / 200), int(sr / 100), 313]
+    n = sum(sizes)
+    t = np.arange(n) / sr
+    m = 0.5 * np.sin(2 * np.pi * 700.0 * t) + 0.3 * np.sin(2 * np.pi * 1900.0 * t)
+    level = np.where(t < 0.3 * t[-1], 0.3, np.where(t < 0.6 * t[-1], 6.0, 0.002))
+    x = level * (1.0 + 0.8 * m) * np.exp(1j * (2 * np.pi * 300.0 * t + 2 * np.pi * 1500.0 * np.cumsum(m) / sr))
+    x = x + 1e-3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    x = x.astype(np.complex64)
+    out, p = [], 0
+    for s in sizes:
+        out.append(x[p:p + s]); p += s
+    return out
+
+
+def make_post(lib, kind, a):
+    if kind == "fm":
+        return lib.fm_full(a["sr"], a["bw"], bool(a["low_pass"]))
+    if kind == "am":
+        return lib.am_full(a["mode"], a["bw"], a["attack"], a["decay"], a["dc"], a["sr"], a["gain"])
+    return lib.ssb_full(a["mode"], a["bw"], a["sr"], bool(a["agc"]), a["attack"], a["decay"])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = po.Ref()
@@ -66,6 +103,13 @@ def main():
     pd, dc = ref.powerdecim(4), ref.dcblock(50.0 / (61.44e6 / 4))
     y = ref.conjugate(dc.process(pd.process(x)))
     add("frontend_x4_dc_conj", "frontend", (4,), {"out": y}, n=len(x), seed=7)
+
+    # complete demodulators: dsp::demod::FM/AM/SSB<float> on a seeded VFO-rate stream
+    for name, kind, args in POST_CASES:
+        x = post_input(args["sr"], args["seed"])
+        d = make_post(ref, kind, args)
+        out = np.concatenate([d.process(b) for b in x])
+        add("post_" + name, "post", (kind,), {"out": out}, params=args)
 
     # waterfall zoom (fft_scaler.h is self-contained, so the reference header itself generates these)
     for name, N, out, vo, vb, wb, seed in [("zoom_1m_max", 1048576, 1917, -2e7, 3.3e7, 122.88e6, 8), ("zoom_1k_point", 1024, 2000, 0.0, 2.4e6, 2.4e6, 9)]:
