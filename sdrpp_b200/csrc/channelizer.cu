@@ -67,6 +67,12 @@ __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// 8-byte asynchronous global -> shared copy (LDGSTS): many in flight per thread without holding registers
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float2 phasor_u64(uint64_t phase) {
     // phase in turns * 2^64 -> (cos, sin). The top 32 bits as a signed fraction of a half turn.
     const float x = (float)(int32_t)(phase >> 32) * 4.656612873077393e-10f; // * 2^-31
@@ -403,42 +409,113 @@ constexpr int kTailTapFloats = 3072;   // staged taps per stage
 // Decimating FIRs store it transposed by D -- element i at [i % D][i / D] with an odd row stride -- so
 // that consecutive outputs (lanes) read consecutive addresses for every tap; others keep natural order.
 __device__ __forceinline__ void tail_stage_in(float2* sm, const float2* src, int n, int D, int qs) {
-    // 4 independent loads in flight per thread before the (transposing) stores: the loop is L2-latency-bound
-    constexpr int U = 4;
     const int lg = 31 - __clz(D); // D is a power of two (every PowerDecimator stage decimates by 2, 4, 8, ...)
-    int i = threadIdx.x;
-    for (; i + (U - 1) * kTailThreads < n; i += U * kTailThreads) {
-        float2 v[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) v[u] = src[i + u * kTailThreads];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int j = i + u * kTailThreads;
-            sm[(j & (D - 1)) * qs + (j >> lg)] = v[u];
+    for (int i = threadIdx.x; i < n; i += kTailThreads) cp_async8(sm + (i & (D - 1)) * qs + (i >> lg), src + i);
+    cp_async_wait_all();
+}
+
+// FIR / decimating FIR stage, register-blocked: a thread owns OB = 4 consecutive outputs, so a staged sample is
+// loaded once for up to four taps (the stage was shared-memory-bandwidth-bound at one load per tap and output,
+// profiles/r1d). With M = OB*D, input element i of the chunk sits at plane i % M, position i / M; output 4t+r, tap k
+// reads element M*t + s with s = r*D + k, so for every s the threads of a warp read consecutive positions of one
+// plane, and the four taps that meet that sample, (h[s], h[s-D], h[s-2D], h[s-3D]), come from one broadcast load of
+// a table built per stage. Few outputs and many taps (the channel filter): the s range is split over KS thread groups
+// and reduced through shared memory. out[o] = sum_k buf[offset + o*D + k] * h[k] (decimating_fir.h:45-68, fir.h:62-83).
+__device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, const float2* __restrict__ buf, float2* __restrict__ out,
+                                                 float2* tsm, float4* tt) {
+    constexpr int OB = 4;
+    constexpr int kTabEntries = kTailTapFloats / 4;
+    const int tid = threadIdx.x;
+    const int T = st.T, M = OB * D, lgM = 31 - __clz(M);
+    const int S = (OB - 1) * D + T, SQ = (S + M - 1) >> lgM;
+    int ch = min(OB * kTailThreads, (kTailSmemSamples - T - 16 * D) / D) & ~(OB - 1);
+    if (ch < OB) ch = OB;
+    for (int o0 = 0; o0 < st.n_out; o0 += ch) {
+        const int co = min(ch, st.n_out - o0);
+        const int nthr = (co + OB - 1) / OB;
+        const int qs = (nthr + SQ) | 1;
+        const int n = (co - 1) * D + T; // staged samples that exist
+        const float2* __restrict__ src = buf + st.offset + o0 * D;
+        {
+            // asynchronous element copies (the copy is L2-latency-bound: everything a thread moves is in flight at once)
+            const int total = M * qs;
+            for (int i = tid; i < total; i += kTailThreads) {
+                float2* dst = tsm + (i & (M - 1)) * qs + (i >> lgM);
+                if (i < n) cp_async8(dst, src + i);
+                else *dst = make_float2(0.0f, 0.0f);
+            }
+            cp_async_wait_all();
         }
+        int KS = 1;
+        while (KS < 8 && nthr * KS * 2 <= kTailThreads && SQ >= 8 * KS * 2) KS *= 2;
+        const int Sk = (SQ + KS - 1) / KS;                  // rows of M s-values per thread group
+        const int SEGq = max(1, min(Sk, kTabEntries / (KS * M)));
+        const int t_out = tid % nthr, ks = tid / nthr;
+        const bool active = ks < KS;
+        float2 acc[OB];
+#pragma unroll
+        for (int r = 0; r < OB; r++) acc[r] = make_float2(0.0f, 0.0f);
+        for (int q0 = 0; q0 < Sk; q0 += SEGq) {
+            // tap table of this step: for each group, rows [ks*Sk + q0, +SEGq)
+            for (int e = tid; e < KS * SEGq * M; e += kTailThreads) {
+                const int g = e / (SEGq * M), loc = e - g * (SEGq * M);
+                const int row = g * Sk + q0 + (loc >> lgM);
+                float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (row < min((g + 1) * Sk, SQ) && (loc >> lgM) < Sk - q0) {
+                    const int sv = (row << lgM) + (loc & (M - 1));
+                    h.x = (sv < T) ? __ldg(st.taps + sv) : 0.0f;
+                    h.y = (sv - D >= 0 && sv - D < T) ? __ldg(st.taps + sv - D) : 0.0f;
+                    h.z = (sv - 2 * D >= 0 && sv - 2 * D < T) ? __ldg(st.taps + sv - 2 * D) : 0.0f;
+                    h.w = (sv - 3 * D >= 0 && sv - 3 * D < T) ? __ldg(st.taps + sv - 3 * D) : 0.0f;
+                }
+                tt[e] = h;
+            }
+            __syncthreads(); // samples (first step) and the table are staged
+            if (active) {
+                const int r0 = ks * Sk + q0;
+                const int r1 = min(min(r0 + SEGq, (ks + 1) * Sk), SQ);
+                for (int row = r0; row < r1; row++) {
+                    const float2* __restrict__ xp = tsm + t_out + row;
+                    const float4* __restrict__ tp = tt + ((ks * SEGq + (row - r0)) << lgM);
+#pragma unroll 4
+                    for (int sp = 0; sp < M; sp++) {
+                        const float2 v = xp[sp * qs];
+                        const float4 h = tp[sp];
+                        acc[0].x = fmaf(v.x, h.x, acc[0].x); acc[0].y = fmaf(v.y, h.x, acc[0].y);
+                        acc[1].x = fmaf(v.x, h.y, acc[1].x); acc[1].y = fmaf(v.y, h.y, acc[1].y);
+                        acc[2].x = fmaf(v.x, h.z, acc[2].x); acc[2].y = fmaf(v.y, h.z, acc[2].y);
+                        acc[3].x = fmaf(v.x, h.w, acc[3].x); acc[3].y = fmaf(v.y, h.w, acc[3].y);
+                    }
+                }
+            }
+            __syncthreads(); // table (and after the last step the samples) may be overwritten
+        }
+        if (KS > 1) {
+            float2* red = tsm; // [ks][t_out][OB]
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < OB; r++) red[(ks * nthr + t_out) * OB + r] = acc[r];
+            }
+            __syncthreads();
+            if (ks == 0) {
+                for (int g = 1; g < KS; g++) {
+#pragma unroll
+                    for (int r = 0; r < OB; r++) { const float2 v = red[(g * nthr + t_out) * OB + r]; acc[r].x += v.x; acc[r].y += v.y; }
+                }
+            }
+        }
+        if (ks == 0) {
+#pragma unroll
+            for (int r = 0; r < OB; r++) {
+                const int o = OB * t_out + r;
+                if (o < co) out[o0 + o] = acc[r];
+            }
+        }
+        __syncthreads();
     }
-    for (; i < n; i += kTailThreads) sm[(i & (D - 1)) * qs + (i >> lg)] = src[i];
 }
 
-// dot product of n complex samples (stride 1) with n real taps; taps 16-byte aligned
-__device__ __forceinline__ void tail_dot(const float2* __restrict__ x, const float* __restrict__ h, int n, float& re, float& im) {
-    int k = 0;
-    for (; k + 4 <= n; k += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(h + k);
-        const float2 v0 = x[k], v1 = x[k + 1], v2 = x[k + 2], v3 = x[k + 3];
-        re = fmaf(v0.x, t.x, re); im = fmaf(v0.y, t.x, im);
-        re = fmaf(v1.x, t.y, re); im = fmaf(v1.y, t.y, im);
-        re = fmaf(v2.x, t.z, re); im = fmaf(v2.y, t.z, im);
-        re = fmaf(v3.x, t.w, re); im = fmaf(v3.y, t.w, im);
-    }
-    for (; k < n; k++) {
-        const float2 v = x[k];
-        const float t = h[k];
-        re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
-    }
-}
-
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailThreads, 4)
 tail_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* ttaps = reinterpret_cast<float*>(tail_smem);                           // [kTailTapFloats]
@@ -455,89 +532,42 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         const int T = st.T, hist = T - 1;
         float2* buf = slab + st.in_off - hist; // [hist | n_in]
         float2* out = slab + ((s + 1 < g.nstages) ? g.st[s + 1].in_off : g.final_off);
-        const bool poly = st.type == TAIL_POLY;
-        const int D = poly ? 1 : st.D; // layout stride (polyphase reads ~consecutive samples)
-        // taps into shared memory: natural order (FIR), [p][aa] rows of AA4 floats (decimating FIR, so that the
-        // taps of one polyphase row are contiguous like the transposed samples), or the whole polyphase bank
-        const int AA = (T + D - 1) / D, AA4 = (AA + 3) & ~3;
-        bool taps_staged = true;
-        if (poly) {
-            taps_staged = (long long)st.interp * T <= kTailTapFloats;
-            if (taps_staged) for (int i = tid; i < st.interp * T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
-        } else if (D == 1) {
-            taps_staged = T <= kTailTapFloats;
-            if (taps_staged) for (int i = tid; i < T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
+        if (st.type != TAIL_POLY) {
+            tail_fir_blocked(st, st.type == TAIL_DECFIR ? st.D : 1, buf, out, tsm, reinterpret_cast<float4*>(ttaps));
         } else {
-            taps_staged = D * AA4 <= kTailTapFloats;
-            if (taps_staged) {
-                for (int i = tid; i < D * AA4; i += kTailThreads) {
-                    const int p = i / AA4, aa = i - p * AA4, k = aa * D + p;
-                    ttaps[i] = (aa < AA && k < T) ? __ldg(st.taps + k) : 0.0f;
-                }
-            }
-        }
-        // outputs per chunk so that the inputs they need fit the staging buffer
-        int ch;
-        if (poly) ch = (int)(((long long)(kTailSmemSamples - T - 2) * st.interp) / st.D);
-        else ch = (kTailSmemSamples - T - D) / D + 1;
-        if (ch >= kTailThreads) ch -= ch % kTailThreads;
-        if (ch < 1) ch = 1;
-        for (int o0 = 0; o0 < st.n_out; o0 += ch) {
-            const int o1 = min(st.n_out, o0 + ch);
-            int first, last; // input index range [first, last] in buf needed by outputs [o0, o1)
-            if (poly) {
+            // polyphase resampler: consecutive outputs use different tap phases and input strides; one output per thread
+            const bool taps_staged = (long long)st.interp * T <= kTailTapFloats;
+            if (taps_staged) for (int i = tid; i < st.interp * T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
+            int ch = (int)(((long long)(kTailSmemSamples - T - 2) * st.interp) / st.D);
+            if (ch >= kTailThreads) ch -= ch % kTailThreads;
+            if (ch < 1) ch = 1;
+            for (int o0 = 0; o0 < st.n_out; o0 += ch) {
+                const int o1 = min(st.n_out, o0 + ch);
                 const long long P0 = (long long)st.phase + (long long)o0 * st.D;
                 const long long P1 = (long long)st.phase + (long long)(o1 - 1) * st.D;
-                first = st.offset + (int)(P0 / st.interp);
-                last = st.offset + (int)(P1 / st.interp) + T - 1;
-            } else {
-                first = st.offset + o0 * st.D;
-                last = st.offset + (o1 - 1) * st.D + T - 1;
-            }
-            const int n = last - first + 1;
-            const int qs = ((n + D - 1) / D) | 1;
-            tail_stage_in(tsm, buf + first, n, D, qs);
-            __syncthreads();
-            for (int o = o0 + tid; o < o1; o += kTailThreads) {
-                float re = 0.0f, im = 0.0f;
-                if (poly) {
+                const int first = st.offset + (int)(P0 / st.interp);
+                const int last = st.offset + (int)(P1 / st.interp) + T - 1;
+                tail_stage_in(tsm, buf + first, last - first + 1, 1, 0);
+                __syncthreads();
+                for (int o = o0 + tid; o < o1; o += kTailThreads) {
+                    // closed form of polyphase_resampler.h:75-93
                     const long long P = (long long)st.phase + (long long)o * st.D;
                     const float2* x = tsm + (st.offset + (int)(P / st.interp) - first);
                     const int ph = (int)(P % st.interp);
-                    if (taps_staged) {
-                        const float* h = ttaps + ph * T; // rows are not 16-byte aligned in general
-                        for (int k = 0; k < T; k++) {
-                            const float2 v = x[k];
-                            const float t = h[k];
-                            re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
-                        }
-                    } else {
-                        const float* h = st.taps + (size_t)ph * T;
-                        for (int k = 0; k < T; k++) {
-                            const float2 v = x[k];
-                            const float t = __ldg(h + k);
-                            re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
-                        }
+                    const float* h = taps_staged ? ttaps + ph * T : st.taps + (size_t)ph * T; // rows are not 16-byte aligned in general
+                    float re0 = 0.0f, im0 = 0.0f, re1 = 0.0f, im1 = 0.0f;
+                    int k = 0;
+                    for (; k + 2 <= T; k += 2) {
+                        const float2 v0 = x[k], v1 = x[k + 1];
+                        const float t0 = h[k], t1 = h[k + 1];
+                        re0 = fmaf(v0.x, t0, re0); im0 = fmaf(v0.y, t0, im0);
+                        re1 = fmaf(v1.x, t1, re1); im1 = fmaf(v1.y, t1, im1);
                     }
-                } else if (!taps_staged) {
-                    // very long filter: taps from L1/L2 (never the case for the reference's plans)
-                    const float2* x = tsm + (o - o0);
-                    for (int k = 0; k < T; k++) {
-                        const int q = k / D, p = k - q * D;
-                        const float2 v = (D == 1) ? x[k] : x[p * qs + q];
-                        const float t = __ldg(st.taps + k);
-                        re = fmaf(v.x, t, re); im = fmaf(v.y, t, im);
-                    }
-                } else if (D == 1) {
-                    tail_dot(tsm + (o - o0), ttaps, T, re, im);
-                } else {
-                    // tap k = aa*D + p reads staged element [p][(o-o0) + aa]; row p has ceil((T-p)/D) taps
-                    const float2* x = tsm + (o - o0);
-                    for (int p = 0; p < D; p++) tail_dot(x + p * qs, ttaps + p * AA4, (T - p + D - 1) / D, re, im);
+                    if (k < T) { const float2 v = x[k]; const float t = h[k]; re0 = fmaf(v.x, t, re0); im0 = fmaf(v.y, t, im0); }
+                    out[o] = make_float2(re0 + re1, im0 + im1);
                 }
-                out[o] = make_float2(re, im);
+                __syncthreads();
             }
-            __syncthreads();
         }
         // Stage 0 reads the double-buffered stage-1 region, so its history goes to the OTHER region (always, even
         // for an empty block); later stages shift in place.
