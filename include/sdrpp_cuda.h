@@ -229,6 +229,13 @@ SDRPP_API void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe);
  * 1 spectrum, 2 channelizer stage 1, 3 channelizer tail. */
 SDRPP_API int sdrpp_cuda_frontend_set_profiling(sdrpp_cuda_frontend* fe, int enabled);
 SDRPP_API float sdrpp_cuda_frontend_kernel_ms(sdrpp_cuda_frontend* fe, int idx);
+/* Channelizer stage 1 (FrequencyXlator + first DecimatingFIR, frequency_xlator.h:43-50 + decimating_fir.h:45-68)
+ * has two device implementations with the same results contract: mode 0 (default) runs it on the tensor cores
+ * (tcgen05, fp16 hi/lo split operands, fp32 accumulate) for first-stage decimations of 32 and 64 and on the FP32
+ * FMA kernel otherwise; mode 1 uses the FP32 FMA kernel only. The environment variable SDRPP_S1_MODE=fp32 sets
+ * mode 1 at creation. _stage1_tensor_launches counts the tensor-core stage-1 launches since creation. */
+SDRPP_API int sdrpp_cuda_frontend_set_stage1_mode(sdrpp_cuda_frontend* fe, int mode);
+SDRPP_API long long sdrpp_cuda_frontend_stage1_tensor_launches(sdrpp_cuda_frontend* fe);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libsdrpp_cuda.so")
 BLOB = os.path.join(HERE, "data", "decim_plans.bin")
 
-SOURCES = ["design.cpp", "preproc.cu", "fft.cu", "channelizer.cu", "engine.cu"]
+SOURCES = ["design.cpp", "preproc.cu", "fft.cu", "channelizer.cu", "channelizer_tc.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

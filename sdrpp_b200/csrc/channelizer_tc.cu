@@ -1,0 +1,541 @@
+// Channelizer stage 1 on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Replaces, for every VFO of a group at once, FrequencyXlator::process (dsp/channel/frequency_xlator.h:43-50)
+// followed by the first DecimatingFIR of the PowerDecimator cascade (dsp/filter/decimating_fir.h:45-68,
+// dsp/multirate/power_decimator.h:51-67), like stage1_kernel in channelizer.cu -- which stays as the path for
+// plan shapes and blocks this one does not take (small first-stage decimation, windows that reach before a
+// VFO's epoch). Same results contract (<= 1e-5 relative RMS against the reference's fp32 blocks).
+//
+// The sum as a matrix product. Cut the input into rows of D samples aligned to absolute multiples of D.
+// An output's window starts s = n0 mod D samples into a row, so with the taps shifted by s (h'[k] = h[k-s])
+// and k = a*D + p (a < A = ceil((T+s)/D), p < D):
+//     y[m] = e^{j phi(row R_m)} * sum_a V[R_m + a][a],
+//     V[R][a] = sum_p x[R*D + p] * ( h'[a*D+p] * e^{j w (a*D+p)} )            (complex * complex)
+// V = X * B with X[R][p] the untranslated samples (shared by EVERY VFO and plan of the same D) and
+// B[p][(vfo, a)] a per-VFO constant table: a complex GEMM with M = rows, K = D, N = A * VFOs, written as a
+// real one with K = 2D (re, im interleaved exactly as the samples lie in memory) and N = 2*A per VFO.
+// fp32 accuracy on fp16 tensor cores: both operands are split into two fp16 halves (hi + lo, 22 significant
+// bits, block-scaled by a power of two per 8 rows of X and per group for B) and three products are
+// accumulated in fp32: Xhi*Bhi + Xhi*Blo + Xlo*Bhi (the dropped Xlo*Blo term is 2^-22 relative).
+//
+//  s1t_split_kernel   cf32 ring -> fp16 hi/lo planes stored directly in the UMMA K-major SWIZZLE_128B
+//                     shared-memory image (an A tile of 128 rows x 64 K is one contiguous 16 KB bulk copy)
+//  s1t_build_b_kernel per VFO tile of 16 VFOs: the B image (hi/lo, shifted taps x phasors), rebuilt on retune
+//  s1t_kernel         persistent, one CTA per SM, warp-specialised: bulk-copy producer | MMA issuer |
+//                     8 epilogue warps (TMEM -> registers, sum over a across rows by warp shuffles,
+//                     rotate by the row phase, store to the VFO slabs); TMEM accumulator double-buffered.
+#include "common.cuh"
+#include "kernels.h"
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace sdrpp {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// A wait that never completes traps (the launch fails with an error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+        if (spins > (1u << 22)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 operands, fp32 accumulate; issued by ONE thread for the CTA
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 B stacked every 1024 B
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
+// [46,48), layout type [61,64) with SWIZZLE_128B = 2).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// Instruction descriptor (InstrDescriptor): D = F32 [4,6), A/B = F16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float2 phasor64(uint64_t phase) {
+    const float x = (float)(int32_t)(phase >> 32) * 4.656612873077393e-10f; // turns*2^64 -> half turns in [-1, 1)
+    float s, c;
+    sincospif(x, &s, &c);
+    return make_float2(c, s);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+constexpr int kRowsPerTile = 128;   // MMA M
+constexpr int kOutPerTile = 120;    // outputs per time tile: 128 - (A-1) rounded down to whole 8-row atoms
+constexpr int kNV = kS1TVfosPerTile;
+constexpr int kChunkBytes = 16384;  // one A-operand chunk: 128 rows x 64 fp16
+constexpr int kMaxChunks = 8;
+constexpr int kThreads = 320;       // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+constexpr int kXchFloats = 2 /*buffers*/ * 2 /*halves*/ * 4 /*quadrants*/ * 7 /*lanes*/ * (kNV / 2) * 2;
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// cf32 ring -> fp16 hi/lo planes in the UMMA shared-memory image.
+// One CTA per 8-row group (8*D samples): block scale 2^e from the group's largest component, then
+// hi = fp16(x*2^e), lo = fp16(x*2^e - hi). A thread converts 4 consecutive samples = one 16-byte chunk
+// (8 fp16: re0 im0 .. re3 im3) of the row and stores it at the swizzled chunk position (chunk ^ row).
+// Samples at or beyond abs_end (not written yet) are stored as zeros.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+s1t_split_kernel(RingRef ring, S1TPlanes pl, int64_t g_first, int64_t abs_end) {
+    __shared__ float red[8];
+    const int D = pl.D;
+    const int t = threadIdx.x;
+    const int64_t g = g_first + blockIdx.x;
+    const int cpr = D >> 2;               // 16-byte chunks per row and plane
+    const int r = t / cpr, c16 = t - r * cpr;
+    const int64_t n0 = g * (int64_t)(8 * D) + (int64_t)r * D + (int64_t)c16 * 4;
+    float v[8];
+    {
+        const uint32_t i0 = (uint32_t)((uint64_t)n0 & ring.mask);
+        const float4 a = *reinterpret_cast<const float4*>(ring.base + i0);
+        const float4 b = *reinterpret_cast<const float4*>(ring.base + i0 + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    float m = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (n0 + i >= abs_end || n0 + i < 0) { v[2 * i] = 0.0f; v[2 * i + 1] = 0.0f; }
+        m = fmaxf(m, fmaxf(fabsf(v[2 * i]), fabsf(v[2 * i + 1])));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((t & 31) == 0) red[t >> 5] = m;
+    __syncthreads();
+    const int nw = (int)blockDim.x >> 5;
+    m = red[0];
+    for (int w = 1; w < nw; w++) m = fmaxf(m, red[w]);
+    // largest component scaled into [2^13, 2^14): fp16 keeps 11 bits down to 2^-14 and loses range above 2^16
+    int e = 0;
+    if (m > 0.0f && m < 3.0e38f) {
+        const int ex = (int)((__float_as_uint(m) >> 23) & 0xffu) - 126; // m = f * 2^ex, f in [0.5, 1)
+        e = 14 - ex;
+        e = e > 60 ? 60 : (e < -40 ? -40 : e);
+    }
+    const float sc = __uint_as_float((uint32_t)(127 + e) << 23);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const float a = v[2 * i] * sc, b = v[2 * i + 1] * sc;
+        const __half2 h = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(h);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = pack_half2(a - hf.x, b - hf.y);
+    }
+    const uint32_t slot = (uint32_t)((uint64_t)g & pl.group_mask);
+    const int kh = c16 >> 3, ch = c16 & 7;
+    const size_t off = ((size_t)kh * ((size_t)pl.group_mask + 1) + slot) * 1024 + (size_t)r * 128 + (size_t)((ch ^ r) << 4);
+    *reinterpret_cast<uint4*>(pl.hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(pl.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (t == 0) pl.sinv[slot] = __uint_as_float((uint32_t)(127 - e) << 23);
+}
+
+cudaError_t launch_s1t_split(RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end, cudaStream_t st) {
+    if (abs_end <= abs_begin) return cudaSuccess;
+    const int gs = 8 * pl.D;
+    const int64_t g0 = abs_begin / gs, g1 = (abs_end - 1) / gs;
+    s1t_split_kernel<<<(unsigned)(g1 - g0 + 1), 2 * pl.D, 0, st>>>(ring, pl, g0, abs_end);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// B image of one group: for every tile of 16 VFOs, planes (hi, lo) x k-halves x N rows of 128 bytes,
+// row n = (vfo_local, a, c) with c = 0 the real and c = 1 the imaginary output column, K index 2p + ci
+// multiplying (ci = 0) x.re or (ci = 1) x.im of sample p of the row:
+//     w = h'[a*D+p] * e^{j*dphi*(a*D+p)}:   c=0: (+w.re, -w.im)    c=1: (+w.im, +w.re)
+// One thread per 16-byte chunk (4 samples x 2).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+s1t_build_b_kernel(uint8_t* blob, const VfoDev* vfos, int nvfo, const float* taps, int T, int D, int shift, int A, int escale) {
+    const int N = 2 * A * kNV, NKH = D >> 5;
+    const int chunks_per_tile = NKH * N * 8;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int vt = blockIdx.y;
+    if (idx >= chunks_per_tile) return;
+    const int ch = idx & 7, n = (idx >> 3) % N, kh = idx / (8 * N);
+    const int vl = n / (2 * A), a = (n - vl * 2 * A) >> 1, c = n & 1;
+    const int v = vt * kNV + vl;
+    const float sc = __uint_as_float((uint32_t)(127 + escale) << 23);
+    float val[8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int p = kh * 32 + ch * 4 + i;
+        const int k = a * D + p, kt = k - shift;
+        float wr = 0.0f, wi = 0.0f;
+        if (v < nvfo && kt >= 0 && kt < T) {
+            const float2 e = phasor64((uint64_t)k * vfos[v].dphi);
+            const float h = taps[kt] * sc;
+            wr = h * e.x; wi = h * e.y;
+        }
+        val[2 * i] = c == 0 ? wr : wi;
+        val[2 * i + 1] = c == 0 ? -wi : wr;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const __half2 h = __floats2half2_rn(val[2 * i], val[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = pack_half2(val[2 * i] - hf.x, val[2 * i + 1] - hf.y);
+    }
+    const size_t plane = (size_t)NKH * N * 128;
+    uint8_t* tile = blob + (size_t)vt * 2 * plane;
+    const size_t off = ((size_t)kh * N + n) * 128 + (size_t)((ch ^ (n & 7)) << 4);
+    *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(tile + plane + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+size_t s1t_b_bytes(int A, int D, int nvfo) {
+    return (size_t)ceil_div(nvfo, kNV) * 2 * (size_t)(D >> 5) * (size_t)(2 * A * kNV) * 128;
+}
+bool s1t_supported(int T, int D) { return (D == 32 || D == 64) && ceil_div(T + D - 1, D) <= 8 && T >= D; }
+int s1t_A(int T, int D, int shift) { return ceil_div(T + shift, D); }
+// exponent that puts the largest tap into [2^13, 2^14) (the phasor has unit modulus)
+int s1t_b_exponent(const float* taps, int T) {
+    float m = 0.0f;
+    for (int i = 0; i < T; i++) m = std::max(m, std::fabs(taps[i]));
+    if (!(m > 0.0f)) return 0;
+    int ex = 0;
+    std::frexp(m, &ex);
+    return std::max(-40, std::min(60, 14 - ex));
+}
+
+cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift, int A,
+                               int escale, cudaStream_t st) {
+    const int N = 2 * A * kNV, NKH = D >> 5;
+    dim3 grid(ceil_div(NKH * N * 8, 256), ceil_div(nvfo, kNV));
+    s1t_build_b_kernel<<<grid, 256, 0, st>>>(blob, vfos, nvfo, d_taps, T, D, shift, A, escale);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one time tile for one epilogue warp: quadrant q (TMEM lanes 32q..32q+31 = tile rows), half hf
+// (VFOs 8hf..8hf+7 of the tile). Thread = one row R. Per VFO: load the 2A accumulator columns, bring them to
+// the row's block scale, and sum V[R+a][a] over a with warp shuffles; the part that reaches into the next
+// warp's rows is handed over through shared memory (written by the lanes it wraps onto).
+// ---------------------------------------------------------------------------------------------
+template <int A>
+__device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S1TPlanes& pl, uint32_t tmem_acc, int q, int hf, int lane,
+                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar) {
+    const int row = q * 32 + lane;
+    const int64_t R = row_t + row;
+    const float sc = pl.sinv[(uint32_t)((uint64_t)(R >> 3) & pl.group_mask)] * G.b_scale_inv;
+    const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * (kNV / 2) * 2 * A);
+    float yre[kNV / 2], yim[kNV / 2];
+    float* xw = xch + ((hf * 4 + q) * 7) * (kNV / 2) * 2;
+#pragma unroll
+    for (int vb = 0; vb < kNV / 2; vb += 4) {
+        uint32_t r[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; j++) tc_ld16(t0 + (uint32_t)((vb + j) * 2 * A), r[j]);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float sre = 0.0f, sim = 0.0f, wre = 0.0f, wim = 0.0f;
+#pragma unroll
+            for (int a = 0; a < A; a++) {
+                float tre = __uint_as_float(r[j][2 * a]) * sc, tim = __uint_as_float(r[j][2 * a + 1]) * sc;
+                if (a > 0) {
+                    tre = __shfl_sync(0xffffffffu, tre, (lane + a) & 31);
+                    tim = __shfl_sync(0xffffffffu, tim, (lane + a) & 31);
+                }
+                const bool wrapped = lane + a >= 32;
+                sre += wrapped ? 0.0f : tre; sim += wrapped ? 0.0f : tim;
+                wre += wrapped ? tre : 0.0f; wim += wrapped ? tim : 0.0f;
+            }
+            yre[vb + j] = sre; yim[vb + j] = sim;
+            // lanes 25..31 hold the sums that belong to rows 25..31 of the PREVIOUS quadrant
+            if (lane >= 25) {
+                xw[((lane - 25) * (kNV / 2) + vb + j) * 2] = wre;
+                xw[((lane - 25) * (kNV / 2) + vb + j) * 2 + 1] = wim;
+            }
+        }
+    }
+    // accumulator stage drained: hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty_bar);
+    asm volatile("bar.sync 1, 256;" ::: "memory"); // the 8 epilogue warps: wrapped sums visible
+    const int64_t m = R - G.row_first;
+    const bool out_row = row < kOutPerTile && m >= 0 && m < (int64_t)G.M;
+    const float* xr = xch + ((hf * 4 + q + 1) * 7) * (kNV / 2) * 2; // next quadrant's hand-over (q < 3 only)
+#pragma unroll
+    for (int j = 0; j < kNV / 2; j++) {
+        float re = yre[j], im = yim[j];
+        if (q < 3 && lane >= 25) {
+            re += xr[((lane - 25) * (kNV / 2) + j) * 2];
+            im += xr[((lane - 25) * (kNV / 2) + j) * 2 + 1];
+        }
+        const int v = vt * kNV + hf * (kNV / 2) + j;
+        if (out_row && v < G.nvfo) {
+            const VfoDev* vd = G.vfos + v;
+            const uint64_t ph = vd->phi_ref + (uint64_t)(R * (int64_t)pl.D - vd->n_ref) * vd->dphi;
+            const float2 e = phasor64(ph);
+            vd->slab[G.out_off + (uint32_t)m] = make_float2(re * e.x - im * e.y, re * e.y + im * e.x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Persistent warp-specialised kernel. CTA b serves one VFO tile (its B image stays in shared memory) of one
+// group over a contiguous range of time tiles.
+// ---------------------------------------------------------------------------------------------
+template <int NKH>
+__global__ void __launch_bounds__(kThreads, 1)
+s1t_kernel(const __grid_constant__ S1TArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    int gi = 0;
+    while (gi + 1 < a.ngroups && (int)blockIdx.x >= a.g[gi + 1].cta_begin) gi++;
+    const S1TGroupArgs& G = a.g[gi];
+    const int local = (int)blockIdx.x - G.cta_begin;
+    const int vt = local / G.cta_per_vtile, ts = local - vt * G.cta_per_vtile;
+    const int tt0 = (int)((int64_t)G.n_ttiles * ts / G.cta_per_vtile);
+    const int tt1 = (int)((int64_t)G.n_ttiles * (ts + 1) / G.cta_per_vtile);
+    const int A = G.A, N = 2 * A * kNV;
+    const int nch = a.nchunks;
+    const uint32_t b_plane = (uint32_t)NKH * (uint32_t)N * 128u;   // bytes of one B plane (hi or lo)
+
+    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smB = base;                                  // [hi|lo][kh][N][128]
+    uint8_t* smA = smB + 2 * b_plane;                     // nch chunks of 16 KB (multiple of 1024: N % 8 == 0)
+    float* xch = reinterpret_cast<float*>(smA + (size_t)nch * kChunkBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kXchFloats);
+    uint64_t* full = bars;                 // [kMaxChunks]
+    uint64_t* empty = bars + kMaxChunks;   // [kMaxChunks]
+    uint64_t* bfull = bars + 2 * kMaxChunks;
+    uint64_t* tfull = bfull + 1;           // [2]
+    uint64_t* tempty = tfull + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kMaxChunks; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+        mbar_init(bfull, 1);
+        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 8); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== producer: B image once, then the A chunks of every time tile (hi, lo per k-half) =====
+        if (lane == 0 && tt1 > tt0) {
+            const uint8_t* bsrc = G.bblob + (size_t)vt * 2 * b_plane;
+            const uint32_t piece = (uint32_t)N * 128u;
+            mbar_expect_tx(bfull, 2 * b_plane);
+            for (int i = 0; i < 2 * NKH; i++) bulk_g2s(smB + (size_t)i * piece, bsrc + (size_t)i * piece, piece, bfull);
+            const uint32_t ng = a.pl.group_mask + 1;
+            uint32_t it = 0;
+            for (int tt = tt0; tt < tt1; tt++) {
+                const int64_t row_t = G.row0 + (int64_t)kOutPerTile * tt;
+                const uint32_t gs = (uint32_t)((uint64_t)(row_t >> 3) & a.pl.group_mask);
+                const uint32_t n1 = min(16u, ng - gs);   // groups before the ring wraps
+#pragma unroll 1
+                for (int c = 0; c < 2 * NKH; c++, it++) {
+                    const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                    mbar_wait(empty + slot, ph ^ 1u);
+                    const uint8_t* plane = ((c & 1) ? a.pl.lo : a.pl.hi) + (size_t)(c >> 1) * ng * 1024;
+                    uint8_t* dst = smA + (size_t)slot * kChunkBytes;
+                    mbar_expect_tx(full + slot, (uint32_t)kChunkBytes);
+                    bulk_g2s(dst, plane + (size_t)gs * 1024, n1 * 1024u, full + slot);
+                    if (n1 < 16u) bulk_g2s(dst + (size_t)n1 * 1024, plane, (16u - n1) * 1024u, full + slot);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: Xhi*Bhi + Xhi*Blo + Xlo*Bhi per k-half, fp32 accumulate in TMEM =====
+        if (lane == 0 && tt1 > tt0) {
+            const uint32_t idesc = umma_idesc_f16(kRowsPerTile, N);
+            mbar_wait(bfull, 0);
+            tc_fence_after();
+            const uint32_t sB = smem_addr(smB), sA = smem_addr(smA);
+            uint32_t it = 0;
+            for (int tt = tt0; tt < tt1; tt++) {
+                const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
+                mbar_wait(tempty + as, aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256u;
+#pragma unroll 1
+                for (int kh = 0; kh < NKH; kh++) {
+                    const uint64_t bh = umma_desc_sw128(sB + (uint32_t)kh * (uint32_t)N * 128u);
+                    const uint64_t bl = umma_desc_sw128(sB + b_plane + (uint32_t)kh * (uint32_t)N * 128u);
+                    {
+                        const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                        mbar_wait(full + slot, ph);
+                        tc_fence_after();
+                        const uint64_t xh = umma_desc_sw128(sA + slot * (uint32_t)kChunkBytes);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            tc_mma_f16(d_tmem, xh + 2u * ks, bh + 2u * ks, idesc, (kh | ks) ? 1u : 0u);
+                            tc_mma_f16(d_tmem, xh + 2u * ks, bl + 2u * ks, idesc, 1u);
+                        }
+                        tc_commit(empty + slot);
+                        it++;
+                    }
+                    {
+                        const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                        mbar_wait(full + slot, ph);
+                        tc_fence_after();
+                        const uint64_t xl = umma_desc_sw128(sA + slot * (uint32_t)kChunkBytes);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) tc_mma_f16(d_tmem, xl + 2u * ks, bh + 2u * ks, idesc, 1u);
+                        tc_commit(empty + slot);
+                        it++;
+                    }
+                }
+                tc_commit(tfull + as);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3, hf = (warp - 2) >> 2;
+        for (int tt = tt0; tt < tt1; tt++) {
+            const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
+            mbar_wait(tfull + as, aph);
+            tc_fence_after();
+            const int64_t row_t = G.row0 + (int64_t)kOutPerTile * tt;
+            float* xb = xch + (k & 1u) * (kXchFloats / 2);
+            const uint32_t acc = tmem_base + as * 256u;
+            switch (A) {
+            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
+            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
+            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
+            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
+            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+static size_t s1t_smem_bytes(int NKH, int A, int nchunks) {
+    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) + 256;
+}
+
+// Fills in cta_begin / cta_per_vtile (time tiles of a VFO tile are split between CTAs so that every SM gets
+// about the same number of MMA cycles) and launches one persistent grid for all groups.
+cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
+    if (a.ngroups <= 0) return cudaSuccess;
+    const int NKH = a.pl.D >> 5;
+    if (NKH != 1 && NKH != 2) return cudaErrorInvalidValue;
+    int maxA = 0;
+    double total = 0.0;
+    for (int i = 0; i < a.ngroups; i++) {
+        S1TGroupArgs& g = a.g[i];
+        if (g.A < 4 || g.A > 8 || g.n_ttiles <= 0 || g.nvfo <= 0) return cudaErrorInvalidValue;
+        g.n_vtiles = ceil_div(g.nvfo, kNV);
+        maxA = std::max(maxA, g.A);
+        total += (double)g.n_vtiles * g.n_ttiles * g.A;
+    }
+    // CTAs per VFO tile: proportional share of the SMs, at least 1, at most one per time tile
+    int used = 0;
+    for (int i = 0; i < a.ngroups; i++) {
+        S1TGroupArgs& g = a.g[i];
+        const double share = (double)num_sms * ((double)g.n_vtiles * g.n_ttiles * g.A) / total;
+        g.cta_per_vtile = std::max(1, std::min(g.n_ttiles, (int)(share / g.n_vtiles)));
+        used += g.cta_per_vtile * g.n_vtiles;
+    }
+    for (;;) { // hand the remaining SMs to the group with the longest per-CTA run
+        int best = -1;
+        double best_load = 0.0;
+        for (int i = 0; i < a.ngroups; i++) {
+            const S1TGroupArgs& g = a.g[i];
+            if (g.cta_per_vtile >= g.n_ttiles || used + g.n_vtiles > num_sms) continue;
+            const double load = (double)ceil_div(g.n_ttiles, g.cta_per_vtile) * g.A;
+            if (load > best_load) { best_load = load; best = i; }
+        }
+        if (best < 0) break;
+        a.g[best].cta_per_vtile++;
+        used += a.g[best].n_vtiles;
+    }
+    int ctas = 0;
+    for (int i = 0; i < a.ngroups; i++) { a.g[i].cta_begin = ctas; ctas += a.g[i].cta_per_vtile * a.g[i].n_vtiles; }
+    // A-operand ring: as many 16 KB chunks as fit beside the largest B image
+    const size_t cap = 232448;
+    int nch = kMaxChunks;
+    while (nch > 2 * NKH && s1t_smem_bytes(NKH, maxA, nch) > cap) nch--;
+    if (s1t_smem_bytes(NKH, maxA, nch) > cap) return cudaErrorInvalidValue;
+    a.nchunks = nch;
+    const size_t smem = s1t_smem_bytes(NKH, maxA, nch);
+    static size_t attr_set[3] = { 0, 0, 0 };
+    if (smem > attr_set[NKH]) {
+        cudaError_t e = NKH == 1 ? cudaFuncSetAttribute(s1t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                 : cudaFuncSetAttribute(s1t_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set[NKH] = smem;
+    }
+    if (NKH == 1) s1t_kernel<1><<<ctas, kThreads, smem, st>>>(a);
+    else s1t_kernel<2><<<ctas, kThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+} // namespace sdrpp

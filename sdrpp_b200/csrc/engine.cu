@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -62,6 +63,10 @@ struct VfoPlan {
     bool s1_fir = false;
     int s1_D = 1, s1_T = 1, s1_A = 1, s1_tap_off = -1;
     std::vector<float> s1_taps;
+    // tensor-core stage 1 (channelizer_tc.cu): device copy of the first FIR, block exponent of the B image
+    bool tc_ok = false;
+    float* d_s1_taps = nullptr;
+    int tc_escale = 0;
     std::vector<TailPlanStage> tail;
     uint32_t s1_off[2] = { 0, 0 }; // the two stage-1 output regions (data areas)
     uint32_t final_off = 0;
@@ -69,7 +74,7 @@ struct VfoPlan {
     size_t slab_elems = 0;
     int max_block = 0;
 
-    ~VfoPlan() { for (auto& s : tail) if (s.d_taps) cudaFree(s.d_taps); }
+    ~VfoPlan() { for (auto& s : tail) if (s.d_taps) cudaFree(s.d_taps); if (d_s1_taps) cudaFree(d_s1_taps); }
 };
 
 static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_block, std::string* err) {
@@ -154,6 +159,15 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
         p.final_off = off + 2;
         p.slab_elems = (size_t)p.final_off + (size_t)((cap + 1) & ~1LL);
     }
+    if (p.s1_fir && s1t_supported(p.s1_T, p.s1_D)) {
+        if (dev_alloc(&p.d_s1_taps, p.s1_taps.size(), false) != cudaSuccess ||
+            cudaMemcpy(p.d_s1_taps, p.s1_taps.data(), p.s1_taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            *err = std::string("tap upload: ") + cudaGetErrorString(cudaGetLastError());
+            return SDRPP_ERR_CUDA;
+        }
+        p.tc_escale = s1t_b_exponent(p.s1_taps.data(), p.s1_T);
+        p.tc_ok = true;
+    }
     for (auto& s : p.tail) {
         if (dev_alloc(&s.d_taps, s.taps.size(), false) != cudaSuccess ||
             cudaMemcpy(s.d_taps, s.taps.data(), s.taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -202,6 +216,10 @@ struct Group {
     std::vector<float4> h_G;
     bool g_dirty = true;
     int last_n_final = 0;
+    // tensor-core stage 1: B image (shifted taps x member phasors), rebuilt when a member retunes
+    uint8_t* d_B = nullptr; size_t b_cap = 0;
+    int tc_shift = -1, tc_A = 0;
+    bool tc_dirty = true;
 };
 
 struct ResultSet {
@@ -278,6 +296,12 @@ struct sdrpp_cuda_frontend {
     int cur = -1; // result set of the last waited block
     long long waited = 0;
     bool readback = true;
+
+    // tensor-core stage 1: fp16 hi/lo planes of the ring per first-stage decimation (index D / 64: 32 -> 0, 64 -> 1)
+    int s1_mode = 0;        // 0: tensor cores where the plan allows, 1: FP32 FMA kernel only
+    int num_sms = 148;
+    S1TPlanes tc_planes[2] = {};
+    long long s1t_launches = 0;
 
     // profiling
     bool profiling = false;
@@ -434,6 +458,7 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
                 fe->post_active++;
             }
         }
+        if (g.g_dirty) g.tc_dirty = true;
         if (g.plan->s1_fir && g.g_dirty) {
             const size_t n = stage1_g_elems(g.plan->s1_A, g.plan->s1_D, (int)g.members.size());
             g.h_G.assign(n, make_float4(0.f, 0.f, 0.f, 0.f));
@@ -494,6 +519,7 @@ static void remove_from_group(sdrpp_cuda_frontend* fe, int id) {
     for (size_t gi = 0; gi < fe->groups.size();) {
         if (fe->groups[gi].members.empty()) {
             if (fe->groups[gi].d_G) { cudaStreamSynchronize(fe->st); cudaFree(fe->groups[gi].d_G); }
+            if (fe->groups[gi].d_B) { cudaStreamSynchronize(fe->st); cudaFree(fe->groups[gi].d_B); }
             fe->groups.erase(fe->groups.begin() + (long)gi);
             for (Vfo& o : fe->vfos) if (o.alive && o.group > (int)gi) o.group--;
         } else gi++;
@@ -708,6 +734,38 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
     std::vector<TailArgs> tails;
     std::vector<int> tail_totals;
+    // Tensor-core stage 1: refresh the fp16 hi/lo planes of the ring for every first-stage decimation in use
+    // (one conversion serves all VFOs and plans of that decimation), then collect the eligible groups per plane set.
+    S1TArgs tc_args[2] = {};
+    if (fe->s1_mode == 0 && n > 0) {
+        for (Group& g : fe->groups) {
+            const VfoPlan& p = *g.plan;
+            if (!p.tc_ok) continue;
+            const int pi = p.s1_D >> 6;
+            S1TPlanes& pl = fe->tc_planes[pi];
+            const uint32_t ngroups = (uint32_t)(((uint64_t)fe->ring_mask + 1) / (uint64_t)(8 * p.s1_D));
+            if (ngroups < 64) continue;
+            if (!pl.hi) {
+                const size_t bytes = ((size_t)fe->ring_mask + 1) * 4;
+                FE_TRY(fe, dev_alloc(&pl.hi, bytes));
+                FE_TRY(fe, dev_alloc(&pl.lo, bytes));
+                FE_TRY(fe, dev_alloc(&pl.sinv, (size_t)ngroups));
+                pl.D = p.s1_D; pl.group_mask = ngroups - 1;
+            }
+            if (tc_args[pi].pl.hi == nullptr) {
+                tc_args[pi].pl = pl;
+                FE_TRY(fe, launch_s1t_split(ring, pl, abs_block, abs_block + n, st));
+                fe->launches++;
+            }
+        }
+    }
+    auto flush_tc = [&](int pi) -> int {
+        if (tc_args[pi].ngroups == 0) return SDRPP_OK;
+        FE_TRY(fe, launch_s1t(tc_args[pi], fe->num_sms, st));
+        fe->launches++; fe->s1t_launches++;
+        tc_args[pi].ngroups = 0;
+        return SDRPP_OK;
+    };
     // Stage-1 launches of different groups are independent: alternate them between two streams so that the
     // partially filled last wave of one grid is topped up by the next grid's CTAs.
     const bool fork = fe->groups.size() > 1;
@@ -734,6 +792,34 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             a.D = p.s1_D; a.A = p.s1_A;
             a.M = nprev; a.G = g.d_G;
             a.abs_first = abs_block - (p.s1_T - 1) + off0;
+            // tensor cores when the whole window lies after the group's epoch (history before it reads as zero,
+            // which only the FP32 kernel does)
+            const int pi = p.s1_D >> 6;
+            if (p.tc_ok && tc_args[pi].pl.hi && nprev > 0 && a.abs_first >= g.st.abs_valid && a.abs_first >= 0) {
+                const int shift = (int)(a.abs_first % p.s1_D);
+                const int A = s1t_A(p.s1_T, p.s1_D, shift);
+                const size_t need = s1t_b_bytes(A, p.s1_D, a.nvfo);
+                if (need > g.b_cap) {
+                    if (g.d_B) { FE_TRY(fe, cudaStreamSynchronize(st)); cudaFree(g.d_B); g.d_B = nullptr; }
+                    FE_TRY(fe, dev_alloc(&g.d_B, need, false));
+                    g.b_cap = need; g.tc_dirty = true;
+                }
+                if (g.tc_dirty || shift != g.tc_shift || A != g.tc_A) {
+                    FE_TRY(fe, launch_s1t_build_b(g.d_B, a.vfos, a.nvfo, p.d_s1_taps, p.s1_T, p.s1_D, shift, A, p.tc_escale, st));
+                    fe->launches++;
+                    g.tc_shift = shift; g.tc_A = A; g.tc_dirty = false;
+                }
+                if (tc_args[pi].ngroups == kS1TMaxGroups) { int rc = flush_tc(pi); if (rc != SDRPP_OK) return rc; }
+                S1TGroupArgs& tg = tc_args[pi].g[tc_args[pi].ngroups++];
+                tg = S1TGroupArgs{};
+                tg.bblob = g.d_B; tg.vfos = a.vfos; tg.nvfo = a.nvfo; tg.A = A; tg.M = nprev;
+                tg.row_first = a.abs_first / p.s1_D;
+                tg.row0 = tg.row_first & ~(int64_t)7;
+                tg.n_ttiles = (int)((tg.row_first - tg.row0 + nprev + 119) / 120);
+                tg.out_off = a.out_off;
+                tg.b_scale_inv = (float)std::ldexp(1.0, -p.tc_escale);
+                goto stage1_done;
+            }
             // keep the window start even (16-byte aligned in the ring): if it is odd, start one sample earlier
             // and use the tap table with a leading zero
             const int pad = (int)(a.abs_first & 1);
@@ -750,6 +836,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             FE_TRY(fe, launch_mix_only(a, s1s));
         }
         if (nprev > 0) { fe->launches++; s1_launch++; }
+    stage1_done:
 
         if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
             TailArgs t{};
@@ -793,6 +880,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         g.st.abs_out += nprev;
         g.last_n_final = nprev;
     }
+    for (int pi = 0; pi < 2; pi++) { int rc = flush_tc(pi); if (rc != SDRPP_OK) return rc; }
     if (fork) {
         FE_TRY(fe, cudaEventRecord(fe->ev_s1_join, fe->st_s1b));
         FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_s1_join, 0));
@@ -1125,6 +1213,12 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         return nullptr;
     };
     if (cudaSetDevice(fe->device) != cudaSuccess) return bail("cudaSetDevice failed");
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, fe->device) == cudaSuccess && sms > 0) fe->num_sms = sms;
+        const char* m = getenv("SDRPP_S1_MODE");
+        fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
+    }
     // ring: history for the longest filter + a whole spectrum frame + one block, rounded up
     {
         long long need = (long long)fe->cfg.max_block * 3 + std::max(fe->cfg.fft_size, 0) * 2LL + 8192;
@@ -1173,7 +1267,8 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
     for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); }
-    for (Group& g : fe->groups) if (g.d_G) cudaFree(g.d_G);
+    for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
+    for (int i = 0; i < 2; i++) { cudaFree(fe->tc_planes[i].hi); cudaFree(fe->tc_planes[i].lo); cudaFree(fe->tc_planes[i].sinv); }
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
     for (float* t : fe->fe_taps) cudaFree(t);
     for (float2* b : fe->fe_buf) cudaFree(b);
@@ -1531,6 +1626,14 @@ int sdrpp_cuda_frontend_read_iq(sdrpp_cuda_frontend* fe, sdrpp_cf32* out, int ca
 }
 
 long long sdrpp_cuda_frontend_launches(sdrpp_cuda_frontend* fe) { return fe ? fe->launches : 0; }
+long long sdrpp_cuda_frontend_stage1_tensor_launches(sdrpp_cuda_frontend* fe) { return fe ? fe->s1t_launches : 0; }
+int sdrpp_cuda_frontend_set_stage1_mode(sdrpp_cuda_frontend* fe, int mode) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (mode != 0 && mode != 1) return fail(SDRPP_ERR_ARG, "stage-1 mode must be 0 (tensor cores where possible) or 1 (FP32 only)");
+    fe->s1_mode = mode;
+    return SDRPP_OK;
+}
 void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe) { return fe ? (void*)fe->st : nullptr; }
 int sdrpp_cuda_frontend_set_profiling(sdrpp_cuda_frontend* fe, int enabled) {
     int rc = fe_quiesce(fe);

@@ -94,6 +94,50 @@ cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st);
 // D = 1, T = 1 (no pre-decimation): pure translation.
 cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------
+// Stage 1 on the tensor cores (channelizer_tc.cu): same result as launch_stage1 for first-stage decimations of
+// 32 and 64, computed as X (samples, fp16 hi/lo) * B (shifted taps x per-VFO phasors, fp16 hi/lo) with tcgen05.
+// ---------------------------------------------------------------------------------------------
+constexpr int kS1TVfosPerTile = 16;
+constexpr int kS1TMaxGroups = 6;
+// fp16 hi/lo copies of the IQ ring in the UMMA shared-memory image: [k-half][group of 8 rows][1024 B] per plane,
+// row = D consecutive samples starting at an absolute multiple of D; sinv[group] = 2^-e of the group's block scale.
+struct S1TPlanes {
+    int D;
+    uint32_t group_mask;   // groups in the ring - 1
+    uint8_t* hi;
+    uint8_t* lo;
+    float* sinv;
+};
+struct S1TGroupArgs {
+    const uint8_t* bblob;  // B images of the group's VFO tiles (s1t_b_bytes)
+    const VfoDev* vfos;    // group members, contiguous
+    int nvfo;
+    int A;                 // rows of the shifted tap matrix, ceil((T + shift) / D)
+    int n_ttiles;          // time tiles (120 outputs each) of this block
+    int M;                 // outputs this block
+    int64_t row0;          // absolute row of time tile 0's first row (multiple of 8)
+    int64_t row_first;     // absolute row in which the window of output 0 starts
+    uint32_t out_off;      // slab offset (in float2) where output 0 goes
+    float b_scale_inv;     // 2^-(B block exponent)
+    int n_vtiles, cta_per_vtile, cta_begin; // set by the launcher
+};
+struct S1TArgs {
+    S1TPlanes pl;
+    int ngroups;
+    int nchunks;           // set by the launcher
+    S1TGroupArgs g[kS1TMaxGroups];
+};
+bool s1t_supported(int T, int D);
+int s1t_A(int T, int D, int shift);
+int s1t_b_exponent(const float* taps, int T);
+size_t s1t_b_bytes(int A, int D, int nvfo);
+// samples [abs_begin, abs_end) were just written to the ring: (re)build the 8-row groups they touch
+cudaError_t launch_s1t_split(RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end, cudaStream_t st);
+cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift, int A,
+                               int escale, cudaStream_t st);
+cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st);
+
 enum { TAIL_DECFIR = 0, TAIL_POLY = 1, TAIL_FIR = 2 };
 struct TailStage {
     int type;

@@ -34,6 +34,7 @@ sdrpp_cuda_frontend_set_readback sdrpp_cuda_vfo_output sdrpp_cuda_fft_rows sdrpp
 sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_profiling
 sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
 sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio
+sdrpp_cuda_frontend_set_stage1_mode sdrpp_cuda_frontend_stage1_tensor_launches
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -108,6 +109,9 @@ def lib():
         L.sdrpp_cuda_frontend_read_iq.argtypes = [_vp, _vp, _i]
         L.sdrpp_cuda_frontend_launches.restype = C.c_longlong
         L.sdrpp_cuda_frontend_launches.argtypes = [_vp]
+        L.sdrpp_cuda_frontend_stage1_tensor_launches.restype = C.c_longlong
+        L.sdrpp_cuda_frontend_stage1_tensor_launches.argtypes = [_vp]
+        L.sdrpp_cuda_frontend_set_stage1_mode.argtypes = [_vp, _i]
         L.sdrpp_cuda_frontend_stream.restype = _vp
         L.sdrpp_cuda_frontend_stream.argtypes = [_vp]
         L.sdrpp_cuda_frontend_kernel_ms.restype = C.c_float
@@ -386,6 +390,14 @@ class Frontend:
     @property
     def launches(self):
         return lib().sdrpp_cuda_frontend_launches(self.h)
+
+    @property
+    def stage1_tensor_launches(self):
+        return lib().sdrpp_cuda_frontend_stage1_tensor_launches(self.h)
+
+    def set_stage1_mode(self, mode):
+        """0: tensor cores where the plan allows (default), 1: FP32 FMA kernel only."""
+        _check(lib().sdrpp_cuda_frontend_set_stage1_mode(self.h, int(mode)), "set_stage1_mode")
 
     @property
     def stream(self):

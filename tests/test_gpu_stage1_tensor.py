@@ -1,0 +1,134 @@
+"""GPU parity of the tensor-core stage 1 (channelizer_tc.cu): FrequencyXlator + first DecimatingFIR as a
+tcgen05 matrix product with fp16 hi/lo split operands.
+
+Checked three ways, all through the C ABI: (1) against the oracle with offset 0 (NCO = identity) at the
+1e-5 gate of SURVEY 8d; (2) against the library's own FP32 FMA stage 1 (mode 1) on identical inputs -- both
+evaluate the same ideal NCO, so they must agree far inside the gate, whatever the VFO offsets; (3) with the
+NCO against the oracle after fitting one complex scalar per block. Every test asserts that the
+tensor-core kernel actually ran."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from sdrpp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+# (inSR, outSR, bw, block): PowerDecimator ratios 256, 512 (first stage /32) and 1024, 2048, 4096 (first stage /64)
+TC_PLANS = [
+    (15.36e6, 48e3, 2.7e3, 76800),
+    (15.36e6, 24e3, 12e3, 76800),
+    (61.44e6, 48e3, 12.5e3, 307200),
+    (122.88e6, 48e3, 12.5e3, 614400),
+    (122.88e6, 24e3, 12e3, 614400),
+]
+
+
+def run(gpu, sr, vfos, blocks, mode, max_block=None, retune=None, **kw):
+    """Per VFO the concatenated cf32 output and the per-block counts; retune = (block index, vfo index, offset)."""
+    mb = max_block or max(len(b) for b in blocks)
+    out = [[] for _ in vfos]
+    with gpu.Frontend(sr, max_block=mb, **kw) as fe:
+        fe.set_stage1_mode(mode)
+        ids = [fe.add_vfo(*v) for v in vfos]
+        for bi, b in enumerate(blocks):
+            if retune is not None and retune[0] == bi:
+                fe.vfo_set_offset(ids[retune[1]], retune[2])
+            fe.process(po.FMT_CF32, b)
+            for i, vid in enumerate(ids):
+                out[i].append(fe.vfo_output(vid)[0].copy())
+        tl = fe.stage1_tensor_launches
+    return [np.concatenate(o) for o in out], [[len(a) for a in o] for o in out], tl
+
+
+@pytest.mark.parametrize("inSR,outSR,bw,blk", TC_PLANS)
+def test_offset0_against_oracle(gpu, port, inSR, outSR, bw, blk):
+    nblocks = 4
+    x = synth.baseband(blk * nblocks, inSR, 21, carriers=[(0.0, "fm"), (bw, "am")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    g, counts, tl = run(gpu, inSR, [(outSR, bw, 0.0, po.DEMOD_NONE)], blocks, 0)
+    assert tl >= nblocks - 1, "tensor-core stage 1 did not run"
+    o = port.rxvfo(inSR, outSR, bw, 0.0)
+    r = [o.process(b) for b in blocks]
+    assert counts[0] == [len(a) for a in r]
+    err = po.rel_rms(g[0], np.concatenate(r))
+    assert err <= 1e-5, f"rel-RMS {err:.3e}"
+
+
+@pytest.mark.parametrize("inSR,outSR,bw,blk", TC_PLANS)
+def test_matches_fp32_kernel_many_vfos(gpu, inSR, outSR, bw, blk):
+    """37 VFOs (three tiles, the last one partial) at arbitrary offsets, ragged blocks."""
+    sizes = [blk, blk // 3 + 1, 7, blk - 5, 513, blk]
+    offs = synth.vfo_grid(37, inSR)
+    x = synth.baseband(sum(sizes), inSR, 22, carriers=[(float(o), "fm") for o in offs[::4]], noise_dbfs=-50.0).astype(np.complex64)
+    blocks, p = [], 0
+    for s in sizes:
+        blocks.append(x[p:p + s]); p += s
+    vfos = [(outSR, bw, float(o), po.DEMOD_NONE) for o in offs]
+    gt, ct, tl = run(gpu, inSR, vfos, blocks, 0, max_block=blk)
+    gf, cf, tl0 = run(gpu, inSR, vfos, blocks, 1, max_block=blk)
+    assert tl > 0 and tl0 == 0
+    assert ct == cf
+    x_rms = float(np.sqrt(np.mean(np.abs(x) ** 2)))
+    worst = 0.0
+    for i in range(len(vfos)):
+        ref_rms = float(np.sqrt(np.mean(np.abs(gf[i]) ** 2)))
+        d = float(np.sqrt(np.mean(np.abs(gt[i] - gf[i]) ** 2)))
+        # channels without a carrier hold only noise: absolute gate relative to the full-band signal there
+        assert d <= 3e-6 * ref_rms + 1e-7 * x_rms, f"vfo {i}: diff {d:.3e} ref {ref_rms:.3e}"
+        worst = max(worst, d / max(ref_rms, 1e-12))
+    print(f"worst tensor-vs-fp32 relative difference {worst:.3e}")
+
+
+def test_nco_against_oracle_aligned(gpu, port):
+    inSR, outSR, bw, blk = 122.88e6, 48e3, 12.5e3, 614400
+    off = 0.2137 * inSR / 2.4
+    nblocks = 3
+    x = synth.baseband(blk * nblocks, inSR, 23, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    g, counts, tl = run(gpu, inSR, [(outSR, bw, off, po.DEMOD_NONE)], blocks, 0)
+    assert tl >= nblocks - 1
+    o = port.rxvfo(inSR, outSR, bw, off)
+    p = 0
+    for b in range(nblocks):
+        r = o.process(blocks[b])
+        assert counts[0][b] == len(r)
+        res, c = po.aligned_rel_rms(g[0][p:p + len(r)], r)
+        p += len(r)
+        assert res <= 5e-5, f"block {b}: aligned residual {res:.3e}"
+        assert abs(abs(c) - 1.0) < 1e-3 and abs(np.angle(c)) < 2e-2
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1.0, 3000.0])
+def test_block_scaling_and_ring_wrap(gpu, scale):
+    """Input amplitude far from full scale (the fp16 split is block-scaled per 8 rows) on a ring that wraps
+    several times during the run."""
+    inSR, outSR, bw, blk = 15.36e6, 24e3, 12e3, 76800
+    nblocks = 9
+    offs = synth.vfo_grid(5, inSR)
+    x = (synth.baseband(blk * nblocks, inSR, 24, carriers=[(float(o), "am") for o in offs], noise_dbfs=-50.0) * scale).astype(np.complex64)
+    # a quiet stretch and a loud burst inside one block: neighbouring row groups get different exponents
+    x[blk * 4 + 1000: blk * 4 + 20000] *= 1e-3
+    x[blk * 5 + 7: blk * 5 + 3000] *= 30.0
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    vfos = [(outSR, bw, float(o), po.DEMOD_NONE) for o in offs]
+    gt, ct, tl = run(gpu, inSR, vfos, blocks, 0, ring_log2=18)
+    gf, cf, _ = run(gpu, inSR, vfos, blocks, 1, ring_log2=18)
+    assert tl > 0 and ct == cf
+    for i in range(len(vfos)):
+        err = po.rel_rms(gt[i], gf[i])
+        assert err <= 3e-6, f"vfo {i}: {err:.3e}"
+
+
+def test_retune_midstream(gpu):
+    inSR, outSR, bw, blk = 61.44e6, 48e3, 12.5e3, 307200
+    nblocks = 5
+    x = synth.baseband(blk * nblocks, inSR, 25, carriers=[(1.0e6, "fm"), (-7.3e6, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
+    vfos = [(outSR, bw, 1.0e6, po.DEMOD_NONE), (outSR, bw, 3.0e6, po.DEMOD_NONE)]
+    gt, ct, tl = run(gpu, inSR, vfos, blocks, 0, retune=(2, 1, -7.3e6))
+    gf, cf, _ = run(gpu, inSR, vfos, blocks, 1, retune=(2, 1, -7.3e6))
+    assert tl > 0 and ct == cf
+    for i in range(2):
+        err = po.rel_rms(gt[i], gf[i])
+        assert err <= 3e-6, f"vfo {i}: {err:.3e}"
