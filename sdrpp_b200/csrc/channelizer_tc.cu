@@ -69,6 +69,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -115,13 +126,28 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+#ifdef SDRPP_S1T_TRACE
+// Debug build only (-DSDRPP_S1T_TRACE): per-CTA cycle counters of the three roles (tools/s1t_trace.py)
+__device__ long long g_s1t_trace[256][16];
+#define S1T_T0(var) const long long var = clock64()
+#define S1T_ACC(slot, var) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] += clock64() - (var); } while (0)
+#define S1T_SET(slot, val) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = (val); } while (0)
+#else
+#define S1T_T0(var) do {} while (0)
+#define S1T_ACC(slot, var) do {} while (0)
+#define S1T_SET(slot, val) do {} while (0)
+#endif
+
 constexpr int kRowsPerTile = 128;   // MMA M
 constexpr int kOutPerTile = 120;    // outputs per time tile: 128 - (A-1) rounded down to whole 8-row atoms
 constexpr int kNV = kS1TVfosPerTile;
 constexpr int kChunkBytes = 16384;  // one A-operand chunk: 128 rows x 64 fp16
 constexpr int kMaxChunks = 8;
-constexpr int kThreads = 320;       // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
-constexpr int kXchFloats = 2 /*buffers*/ * 2 /*halves*/ * 4 /*quadrants*/ * 7 /*lanes*/ * (kNV / 2) * 2;
+constexpr int kEpiWarps = 16;       // 4 per TMEM lane quadrant, each with kNV/4 VFOs of the tile
+constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
+constexpr int kNVW = kNV / (kEpiWarps / 4); // VFOs per epilogue warp
+constexpr int kEpiBatch = 2;         // VFOs per TMEM load batch in the epilogue
+constexpr int kXchFloats = 2 /*buffers*/ * 4 /*quadrants*/ * 7 /*lanes*/ * kNV * 2;
 
 } // namespace
 
@@ -140,7 +166,7 @@ s1t_split_kernel(RingRef ring, S1TPlanes pl, int64_t g_first, int64_t abs_end) {
     const int64_t g = g_first + blockIdx.x;
     const int cpr = D >> 2;               // 16-byte chunks per row and plane
     const int r = t / cpr, c16 = t - r * cpr;
-    const int64_t n0 = g * (int64_t)(8 * D) + (int64_t)r * D + (int64_t)c16 * 4;
+    const int64_t n0 = g * (int64_t)(8 * D) + (int64_t)r * D + (int64_t)c16 * 4 + pl.origin;
     float v[8];
     {
         const uint32_t i0 = (uint32_t)((uint64_t)n0 & ring.mask);
@@ -189,7 +215,8 @@ s1t_split_kernel(RingRef ring, S1TPlanes pl, int64_t g_first, int64_t abs_end) {
 cudaError_t launch_s1t_split(RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end, cudaStream_t st) {
     if (abs_end <= abs_begin) return cudaSuccess;
     const int gs = 8 * pl.D;
-    const int64_t g0 = abs_begin / gs, g1 = (abs_end - 1) / gs;
+    if (abs_end <= pl.origin) return cudaSuccess;
+    const int64_t g0 = std::max<int64_t>(abs_begin - pl.origin, 0) / gs, g1 = (abs_end - 1 - pl.origin) / gs;
     s1t_split_kernel<<<(unsigned)(g1 - g0 + 1), 2 * pl.D, 0, st>>>(ring, pl, g0, abs_end);
     return cudaGetLastError();
 }
@@ -265,69 +292,84 @@ cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue of one time tile for one epilogue warp: quadrant q (TMEM lanes 32q..32q+31 = tile rows), half hf
-// (VFOs 8hf..8hf+7 of the tile). Thread = one row R. Per VFO: load the 2A accumulator columns, bring them to
-// the row's block scale, and sum V[R+a][a] over a with warp shuffles; the part that reaches into the next
-// warp's rows is handed over through shared memory (written by the lanes it wraps onto).
+// Epilogue of one time tile for one epilogue warp: quadrant q (TMEM lanes 32q..32q+31 = tile rows), part hf
+// (VFOs kNVW*hf .. of the tile). Thread = one row R. Per VFO: load the 2A accumulator columns and sum
+// V[R+a][a] over a with warp shuffles, each term weighted by the block scale of the row it comes from; the part
+// that reaches into the next warp's rows is handed over through shared memory (written by the lanes it wraps
+// onto). cur[j] = e^{j phi(R)} of the thread's row for VFO j, advanced by the caller from tile to tile.
 // ---------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S1TPlanes& pl, uint32_t tmem_acc, int q, int hf, int lane,
-                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar) {
+                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur) {
+    constexpr int NVH = kNVW;
+#ifdef SDRPP_S1T_TRACE
+    const long long tl0_ = clock64();
+#endif
     const int row = q * 32 + lane;
     const int64_t R = row_t + row;
     const float sc = pl.sinv[(uint32_t)((uint64_t)(R >> 3) & pl.group_mask)] * G.b_scale_inv;
-    const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * (kNV / 2) * 2 * A);
-    float yre[kNV / 2], yim[kNV / 2];
-    float* xw = xch + ((hf * 4 + q) * 7) * (kNV / 2) * 2;
+    // weight of the term taken from lane (lane + a) & 31: its row's scale, routed to the in-warp sum (scA) or to
+    // the sum that belongs to the previous quadrant's row (scW)
+    float scA[A], scW[A];
 #pragma unroll
-    for (int vb = 0; vb < kNV / 2; vb += 4) {
-        uint32_t r[4][16];
+    for (int a = 0; a < A; a++) {
+        const float s = a ? __shfl_sync(0xffffffffu, sc, (lane + a) & 31) : sc;
+        const bool wrapped = lane + a >= 32;
+        scA[a] = wrapped ? 0.0f : s;
+        scW[a] = wrapped ? s : 0.0f;
+    }
+    const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * NVH * 2 * A);
+    float2 y[NVH];
+    float2* xw = reinterpret_cast<float2*>(xch) + ((hf * 4 + q) * 7) * NVH;
 #pragma unroll
-        for (int j = 0; j < 4; j++) tc_ld16(t0 + (uint32_t)((vb + j) * 2 * A), r[j]);
+    for (int vb = 0; vb < NVH; vb += kEpiBatch) {
+        uint32_t r[kEpiBatch][16];
+#pragma unroll
+        for (int j = 0; j < kEpiBatch; j++) tc_ld16(t0 + (uint32_t)((vb + j) * 2 * A), r[j]);
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float sre = 0.0f, sim = 0.0f, wre = 0.0f, wim = 0.0f;
+        for (int j = 0; j < kEpiBatch; j++) {
+            float sre = __uint_as_float(r[j][0]) * scA[0], sim = __uint_as_float(r[j][1]) * scA[0];
+            float wre = 0.0f, wim = 0.0f;
 #pragma unroll
-            for (int a = 0; a < A; a++) {
-                float tre = __uint_as_float(r[j][2 * a]) * sc, tim = __uint_as_float(r[j][2 * a + 1]) * sc;
-                if (a > 0) {
-                    tre = __shfl_sync(0xffffffffu, tre, (lane + a) & 31);
-                    tim = __shfl_sync(0xffffffffu, tim, (lane + a) & 31);
-                }
-                const bool wrapped = lane + a >= 32;
-                sre += wrapped ? 0.0f : tre; sim += wrapped ? 0.0f : tim;
-                wre += wrapped ? tre : 0.0f; wim += wrapped ? tim : 0.0f;
+            for (int a = 1; a < A; a++) {
+                const float tre = __shfl_sync(0xffffffffu, __uint_as_float(r[j][2 * a]), (lane + a) & 31);
+                const float tim = __shfl_sync(0xffffffffu, __uint_as_float(r[j][2 * a + 1]), (lane + a) & 31);
+                sre = fmaf(tre, scA[a], sre); sim = fmaf(tim, scA[a], sim);
+                wre = fmaf(tre, scW[a], wre); wim = fmaf(tim, scW[a], wim);
             }
-            yre[vb + j] = sre; yim[vb + j] = sim;
+            y[vb + j] = make_float2(sre, sim);
             // lanes 25..31 hold the sums that belong to rows 25..31 of the PREVIOUS quadrant
-            if (lane >= 25) {
-                xw[((lane - 25) * (kNV / 2) + vb + j) * 2] = wre;
-                xw[((lane - 25) * (kNV / 2) + vb + j) * 2 + 1] = wim;
-            }
+            if (lane >= 25) xw[(lane - 25) * NVH + vb + j] = make_float2(wre, wim);
         }
     }
     // accumulator stage drained: hand it back to the MMA issuer
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty_bar);
-    asm volatile("bar.sync 1, 256;" ::: "memory"); // the 8 epilogue warps: wrapped sums visible
+#ifdef SDRPP_S1T_TRACE
+    const long long tb_ = clock64();
+    if (q == 2 && hf == 0 && lane == 0) { S1T_ACC(6, tl0_); }
+#endif
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); // the epilogue warps: wrapped sums visible
+#ifdef SDRPP_S1T_TRACE
+    if (q == 2 && hf == 0 && lane == 0) { S1T_ACC(7, tb_); }
+#endif
     const int64_t m = R - G.row_first;
     const bool out_row = row < kOutPerTile && m >= 0 && m < (int64_t)G.M;
-    const float* xr = xch + ((hf * 4 + q + 1) * 7) * (kNV / 2) * 2; // next quadrant's hand-over (q < 3 only)
+    const bool take = q < 3 && lane >= 25;
+    const float2* xr = reinterpret_cast<const float2*>(xch) + ((hf * 4 + q + 1) * 7) * NVH; // next quadrant's hand-over
 #pragma unroll
-    for (int j = 0; j < kNV / 2; j++) {
-        float re = yre[j], im = yim[j];
-        if (q < 3 && lane >= 25) {
-            re += xr[((lane - 25) * (kNV / 2) + j) * 2];
-            im += xr[((lane - 25) * (kNV / 2) + j) * 2 + 1];
+    for (int j = 0; j < NVH; j++) {
+        float2 t = y[j];
+        if (take) {
+            const float2 w = xr[(lane - 25) * NVH + j];
+            t.x += w.x; t.y += w.y;
         }
-        const int v = vt * kNV + hf * (kNV / 2) + j;
+        const int v = vt * kNV + hf * NVH + j;
         if (out_row && v < G.nvfo) {
-            const VfoDev* vd = G.vfos + v;
-            const uint64_t ph = vd->phi_ref + (uint64_t)(R * (int64_t)pl.D - vd->n_ref) * vd->dphi;
-            const float2 e = phasor64(ph);
-            vd->slab[G.out_off + (uint32_t)m] = make_float2(re * e.x - im * e.y, re * e.y + im * e.x);
+            const float2 e = cur[j];
+            G.vfos[v].slab[G.out_off + (uint32_t)m] = make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x);
         }
     }
 }
@@ -364,10 +406,15 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef SDRPP_S1T_TRACE
+    const long long tk0_ = clock64();
+    if (tid == 0 && blockIdx.x < 256) { for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0; g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A; }
+    __syncthreads();
+#endif
     if (tid == 0) {
         for (int i = 0; i < kMaxChunks; i++) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
         mbar_init(bfull, 1);
-        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, 8); }
+        for (int i = 0; i < 2; i++) { mbar_init(tfull + i, 1); mbar_init(tempty + i, kEpiWarps); }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -379,13 +426,19 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The producer and MMA warps run their loops convergently (all 32 lanes wait on the barriers) and elect one lane
+    // only for the issuing instructions: bulk copies and tcgen05.mma take their operands from uniform registers, and
+    // in divergent code every one of them costs a register-to-uniform broadcast loop.
     if (warp == 0) {
         // ===== producer: B image once, then the A chunks of every time tile (hi, lo per k-half) =====
-        if (lane == 0 && tt1 > tt0) {
+        if (tt1 > tt0) {
             const uint8_t* bsrc = G.bblob + (size_t)vt * 2 * b_plane;
             const uint32_t piece = (uint32_t)N * 128u;
-            mbar_expect_tx(bfull, 2 * b_plane);
-            for (int i = 0; i < 2 * NKH; i++) bulk_g2s(smB + (size_t)i * piece, bsrc + (size_t)i * piece, piece, bfull);
+            if (elect_one()) {
+                mbar_expect_tx(bfull, 2 * b_plane);
+                for (int i = 0; i < 2 * NKH; i++) bulk_g2s(smB + (size_t)i * piece, bsrc + (size_t)i * piece, piece, bfull);
+            }
+            __syncwarp();
             const uint32_t ng = a.pl.group_mask + 1;
             uint32_t it = 0;
             for (int tt = tt0; tt < tt1; tt++) {
@@ -395,27 +448,36 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #pragma unroll 1
                 for (int c = 0; c < 2 * NKH; c++, it++) {
                     const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                    S1T_T0(tw_);
                     mbar_wait(empty + slot, ph ^ 1u);
+                    S1T_ACC(10, tw_);
                     const uint8_t* plane = ((c & 1) ? a.pl.lo : a.pl.hi) + (size_t)(c >> 1) * ng * 1024;
                     uint8_t* dst = smA + (size_t)slot * kChunkBytes;
-                    mbar_expect_tx(full + slot, (uint32_t)kChunkBytes);
-                    bulk_g2s(dst, plane + (size_t)gs * 1024, n1 * 1024u, full + slot);
-                    if (n1 < 16u) bulk_g2s(dst + (size_t)n1 * 1024, plane, (16u - n1) * 1024u, full + slot);
+                    if (elect_one()) {
+                        mbar_expect_tx(full + slot, (uint32_t)kChunkBytes);
+                        bulk_g2s(dst, plane + (size_t)gs * 1024, n1 * 1024u, full + slot);
+                        if (n1 < 16u) bulk_g2s(dst + (size_t)n1 * 1024, plane, (16u - n1) * 1024u, full + slot);
+                    }
+                    __syncwarp();
                 }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer: Xhi*Bhi + Xhi*Blo + Xlo*Bhi per k-half, fp32 accumulate in TMEM =====
-        if (lane == 0 && tt1 > tt0) {
+        if (tt1 > tt0) {
             const uint32_t idesc = umma_idesc_f16(kRowsPerTile, N);
             mbar_wait(bfull, 0);
+#ifdef SDRPP_S1T_TRACE
+            if (lane == 0) { S1T_ACC(14, tk0_); }
+#endif
             tc_fence_after();
             const uint32_t sB = smem_addr(smB), sA = smem_addr(smA);
             uint32_t it = 0;
             for (int tt = tt0; tt < tt1; tt++) {
                 const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
+                S1T_T0(tw_);
                 mbar_wait(tempty + as, aph ^ 1u);
+                S1T_ACC(2, tw_);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256u;
 #pragma unroll 1
@@ -424,53 +486,100 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                     const uint64_t bl = umma_desc_sw128(sB + b_plane + (uint32_t)kh * (uint32_t)N * 128u);
                     {
                         const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                        S1T_T0(tf_);
                         mbar_wait(full + slot, ph);
+                        S1T_ACC(3, tf_);
                         tc_fence_after();
                         const uint64_t xh = umma_desc_sw128(sA + slot * (uint32_t)kChunkBytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            tc_mma_f16(d_tmem, xh + 2u * ks, bh + 2u * ks, idesc, (kh | ks) ? 1u : 0u);
-                            tc_mma_f16(d_tmem, xh + 2u * ks, bl + 2u * ks, idesc, 1u);
+                            for (int ks = 0; ks < 4; ks++) {
+                                tc_mma_f16(d_tmem, xh + 2u * ks, bh + 2u * ks, idesc, (kh | ks) ? 1u : 0u);
+                                tc_mma_f16(d_tmem, xh + 2u * ks, bl + 2u * ks, idesc, 1u);
+                            }
+                            tc_commit(empty + slot);
                         }
-                        tc_commit(empty + slot);
+                        __syncwarp();
                         it++;
                     }
                     {
                         const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                        S1T_T0(tf_);
                         mbar_wait(full + slot, ph);
+                        S1T_ACC(3, tf_);
                         tc_fence_after();
                         const uint64_t xl = umma_desc_sw128(sA + slot * (uint32_t)kChunkBytes);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) tc_mma_f16(d_tmem, xl + 2u * ks, bh + 2u * ks, idesc, 1u);
-                        tc_commit(empty + slot);
+                            for (int ks = 0; ks < 4; ks++) tc_mma_f16(d_tmem, xl + 2u * ks, bh + 2u * ks, idesc, 1u);
+                            tc_commit(empty + slot);
+                            if (kh == NKH - 1) tc_commit(tfull + as);
+                        }
+                        __syncwarp();
                         it++;
                     }
                 }
-                tc_commit(tfull + as);
             }
         }
-        __syncwarp();
     } else {
         // ===== epilogue warps =====
         const int q = warp & 3, hf = (warp - 2) >> 2;
+        constexpr int NVH = kNVW;
+        // NCO phase of this thread's row per VFO: exact (64-bit accumulator) every 8 tiles, advanced by the
+        // constant tile step in between
+        float2 cur[NVH], stp[NVH];
+        auto exact_phase = [&](int tt) {
+            const int64_t R = G.row0 + (int64_t)kOutPerTile * tt + q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < NVH; j++) {
+                const int v = vt * kNV + hf * NVH + j;
+                if (v < G.nvfo) {
+                    const VfoDev* vd = G.vfos + v;
+                    cur[j] = phasor64(vd->phi_ref + (uint64_t)(R * (int64_t)a.pl.D + a.pl.origin - vd->n_ref) * vd->dphi);
+                } else cur[j] = make_float2(1.0f, 0.0f);
+            }
+        };
+#pragma unroll
+        for (int j = 0; j < NVH; j++) {
+            const int v = vt * kNV + hf * NVH + j;
+            stp[j] = v < G.nvfo ? phasor64((uint64_t)(kOutPerTile * a.pl.D) * G.vfos[v].dphi) : make_float2(1.0f, 0.0f);
+        }
         for (int tt = tt0; tt < tt1; tt++) {
             const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
+            if ((k & 7u) == 0u) exact_phase(tt);
+#ifdef SDRPP_S1T_TRACE
+            const bool tr_ = warp == 2 && lane == 0;
+            const long long te_ = clock64();
+#endif
             mbar_wait(tfull + as, aph);
+#ifdef SDRPP_S1T_TRACE
+            if (tr_ && k == 0) { S1T_ACC(15, tk0_); }
+            if (tr_) { S1T_ACC(5, te_); }
+            const long long tl_ = clock64();
+#endif
             tc_fence_after();
             const int64_t row_t = G.row0 + (int64_t)kOutPerTile * tt;
             float* xb = xch + (k & 1u) * (kXchFloats / 2);
             const uint32_t acc = tmem_base + as * 256u;
             switch (A) {
-            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
-            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
-            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
-            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
-            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as); break;
+            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
+            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
+            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
+            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
+            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
             }
+#pragma unroll
+            for (int j = 0; j < NVH; j++) cur[j] = cmul(cur[j], stp[j]);
+#ifdef SDRPP_S1T_TRACE
+            if (tr_) { S1T_ACC(9, tl_); }
+#endif
         }
     }
     tc_fence_before();
     __syncthreads();
+#ifdef SDRPP_S1T_TRACE
+    if (tid == 0) { S1T_ACC(1, tk0_); }
+#endif
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -539,3 +648,10 @@ cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
 }
 
 } // namespace sdrpp
+
+#ifdef SDRPP_S1T_TRACE
+extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_s1t_trace(long long* out, int rows) {
+    if (rows > 256) rows = 256;
+    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 16 * (size_t)rows);
+}
+#endif

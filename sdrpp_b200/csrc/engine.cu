@@ -738,25 +738,44 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     // (one conversion serves all VFOs and plans of that decimation), then collect the eligible groups per plane set.
     S1TArgs tc_args[2] = {};
     if (fe->s1_mode == 0 && n > 0) {
-        for (Group& g : fe->groups) {
-            const VfoPlan& p = *g.plan;
-            if (!p.tc_ok) continue;
-            const int pi = p.s1_D >> 6;
-            S1TPlanes& pl = fe->tc_planes[pi];
-            const uint32_t ngroups = (uint32_t)(((uint64_t)fe->ring_mask + 1) / (uint64_t)(8 * p.s1_D));
+        for (int pi = 0; pi < 2; pi++) {
+            const int D = pi ? 64 : 32;
+            const uint32_t ngroups = (uint32_t)(((uint64_t)fe->ring_mask + 1) / (uint64_t)(8 * D));
             if (ngroups < 64) continue;
+            // Row origin: every group's windows start on its own lattice n0 + m*D; rows aligned so that the starts
+            // fall early in a row keep the shifted tap matrix at ceil(T/D) rows instead of one more.
+            S1TPlanes& pl = fe->tc_planes[pi];
+            long long best_cost = -1, cur_cost = -1; int best = 0; bool any = false;
+            for (int o = 0; o < D; o += 4) {
+                long long cost = 0;
+                for (const Group& g : fe->groups) {
+                    const VfoPlan& p = *g.plan;
+                    if (!p.tc_ok || p.s1_D != D) continue;
+                    any = true;
+                    const int64_t first = abs_block - (p.s1_T - 1) + g.st.s1_offset;
+                    const int sh = (int)(((first - o) % D + D) % D);
+                    cost += (long long)g.members.size() * s1t_A(p.s1_T, D, sh);
+                }
+                if (!any) break;
+                if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = o; }
+                if (pl.hi && o == pl.origin) cur_cost = cost;
+            }
+            if (!any) continue;
+            int64_t split_from = abs_block;
             if (!pl.hi) {
                 const size_t bytes = ((size_t)fe->ring_mask + 1) * 4;
                 FE_TRY(fe, dev_alloc(&pl.hi, bytes));
                 FE_TRY(fe, dev_alloc(&pl.lo, bytes));
                 FE_TRY(fe, dev_alloc(&pl.sinv, (size_t)ngroups));
-                pl.D = p.s1_D; pl.group_mask = ngroups - 1;
+                pl.D = D; pl.group_mask = ngroups - 1; pl.origin = best;
+            } else if (best_cost < cur_cost) {
+                // new origin: the history the next windows reach back into has to be converted again
+                pl.origin = best;
+                split_from = std::max<int64_t>(0, abs_block - 4096);
             }
-            if (tc_args[pi].pl.hi == nullptr) {
-                tc_args[pi].pl = pl;
-                FE_TRY(fe, launch_s1t_split(ring, pl, abs_block, abs_block + n, st));
-                fe->launches++;
-            }
+            tc_args[pi].pl = pl;
+            FE_TRY(fe, launch_s1t_split(ring, pl, split_from, abs_block + n, st));
+            fe->launches++;
         }
     }
     auto flush_tc = [&](int pi) -> int {
@@ -795,8 +814,9 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             // tensor cores when the whole window lies after the group's epoch (history before it reads as zero,
             // which only the FP32 kernel does)
             const int pi = p.s1_D >> 6;
-            if (p.tc_ok && tc_args[pi].pl.hi && nprev > 0 && a.abs_first >= g.st.abs_valid && a.abs_first >= 0) {
-                const int shift = (int)(a.abs_first % p.s1_D);
+            if (p.tc_ok && tc_args[pi].pl.hi && nprev > 0 && a.abs_first >= g.st.abs_valid && a.abs_first >= tc_args[pi].pl.origin) {
+                const int64_t rel_first = a.abs_first - tc_args[pi].pl.origin;
+                const int shift = (int)(rel_first % p.s1_D);
                 const int A = s1t_A(p.s1_T, p.s1_D, shift);
                 const size_t need = s1t_b_bytes(A, p.s1_D, a.nvfo);
                 if (need > g.b_cap) {
@@ -813,7 +833,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 S1TGroupArgs& tg = tc_args[pi].g[tc_args[pi].ngroups++];
                 tg = S1TGroupArgs{};
                 tg.bblob = g.d_B; tg.vfos = a.vfos; tg.nvfo = a.nvfo; tg.A = A; tg.M = nprev;
-                tg.row_first = a.abs_first / p.s1_D;
+                tg.row_first = rel_first / p.s1_D;
                 tg.row0 = tg.row_first & ~(int64_t)7;
                 tg.n_ttiles = (int)((tg.row_first - tg.row0 + nprev + 119) / 120);
                 tg.out_off = a.out_off;

@@ -101,9 +101,10 @@ cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st);
 constexpr int kS1TVfosPerTile = 16;
 constexpr int kS1TMaxGroups = 6;
 // fp16 hi/lo copies of the IQ ring in the UMMA shared-memory image: [k-half][group of 8 rows][1024 B] per plane,
-// row = D consecutive samples starting at an absolute multiple of D; sinv[group] = 2^-e of the group's block scale.
+// row = D consecutive samples starting at an absolute index == origin (mod D); sinv[group] = 2^-e of the group's block scale.
 struct S1TPlanes {
     int D;
+    int origin;            // rows start at absolute sample indices == origin (mod D); multiple of 4, < D
     uint32_t group_mask;   // groups in the ring - 1
     uint8_t* hi;
     uint8_t* lo;

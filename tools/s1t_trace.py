@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Per-CTA cycle counters of the tensor-core stage-1 kernel (debug build: SDRPP_EXTRA_NVCC=-DSDRPP_S1T_TRACE).
+Prints, for the last block, how long each role waited on each barrier."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from sdrpp_b200 import cuda  # noqa: E402
+
+cuda.init(0)
+fe = cuda.Frontend(bench.SR, fft_size=0, fft_rate=bench.SR / bench.FFT_N, fft_window=cuda.WIN_BH4, max_block=bench.BLOCK)
+for v in bench.vfo_list():
+    fe.add_vfo(*v)
+blocks = bench.make_blocks(4)
+fe.set_readback(False)
+for i in range(6):
+    fe.submit(cuda.FMT_CF32, blocks[i % 4])
+    fe.wait()
+L = cuda.lib()
+buf = np.zeros((256, 16), dtype=np.int64)
+L.sdrpp_cuda_debug_s1t_trace.argtypes = [C.c_void_p, C.c_int]
+assert L.sdrpp_cuda_debug_s1t_trace(buf.ctypes.data, 256) == 0
+t = buf[buf[:, 12] > 0]
+names = {1: "kernel total", 2: "mma: wait tmem empty", 3: "mma: wait smem full", 5: "epi: wait tmem full", 6: "epi: load+sum phase",
+         7: "epi: bar.sync", 9: "epi: tile total (after wait)", 10: "producer: wait smem empty", 14: "start -> B image landed", 15: "start -> first accumulator ready"}
+for A in sorted(set(t[:, 13])):
+    c = t[t[:, 13] == A]
+    print(f"A={A}: {len(c)} CTAs, tiles per CTA {c[:, 12].min()}..{c[:, 12].max()}")
+    for k, n in names.items():
+        per = c[:, k] / c[:, 12]
+        print(f"   {n:32s} total {c[:, k].mean():10.0f} cyc   per tile {per.mean():8.0f}")
