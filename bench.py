@@ -13,6 +13,7 @@ N > 1 (torchrun, one rank per GPU): the VFO set is sharded across ranks, every s
 broadcast from rank 0 over NCCL (NVLink) and the spectrum stays on rank 0.
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -386,8 +387,23 @@ def run_gpu(args, rank, world, local_rank):
             n = len(fe.vfo_output(vid, copy=False)[0])
             d2h += n * (8 + 4)
         d2h += int(FFT_N * 4 * BLOCK / FFT_N)
+        # the host link on its own: the same pinned block copied host -> device back to back (what bounds e2e for cf32 input)
+        hsrc = torch.from_numpy(pin[0].array.view(np.float32))
+        hdst = torch.empty_like(d_blocks[0].view(-1))
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            hdst.copy_(hsrc, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(20):
+            hdst.copy_(hsrc, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 20 * BLOCK * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
         e2e = {"value": args.steps * BLOCK / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
-               "note": "pinned host block -> cudaMemcpyAsync H2D -> full path -> D2H of all VFO outputs + spectrum rows; wall clock"}
+               "h2d_link_gbs": h2d_gbs, "h2d_link_bound_msps": h2d_gbs * 1e9 / 8 / 1e6,
+               "note": "pinned host block -> cudaMemcpyAsync H2D -> full path -> D2H of all VFO outputs + spectrum rows; wall clock. "
+                       "h2d_link_gbs: the same 4.9 MB pinned block copied back to back with nothing else running = the ceiling of any cf32 e2e number on this host link"}
         for p in pin:
             p.free()
     else:
@@ -482,7 +498,8 @@ def run_gpu(args, rank, world, local_rank):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
-            traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for name, k in tj.items() if "stage1_kernel" in name)
+            want = "s1t_" if fe.stage1_tensor_launches > 0 else "stage1_kernel"
+            traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for name, k in tj.items() if want in name) or None
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": "stage1_kernel (NCO folded into the first decimating FIR; both VFO-class launches of a step)",
@@ -495,10 +512,43 @@ def run_gpu(args, rank, world, local_rank):
         sm_clk = (clk or {}).get("sm_mhz") or 1965.0
         fma_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
         s1_flops = model["stage1_flops_per_sample"] * BLOCK
-        roof["fp32"] = {"achieved": s1_flops / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None, "peak": fma_peak, "unit": "TFLOP/s",
-                        "frac": (s1_flops / (s1_ms * 1e-3) / 1e12 / fma_peak) if s1_ms > 0 else None,
-                        "peak_source": f"148 SM x 128 FMA lanes x 2 x {sm_clk:.0f} MHz (median SM clock sampled under load)",
-                        "algorithmic_flops_per_sample": model["stage1_flops_per_sample"]}
+        fp32 = {"achieved": s1_flops / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None, "peak": fma_peak, "unit": "TFLOP/s",
+                "frac": (s1_flops / (s1_ms * 1e-3) / 1e12 / fma_peak) if s1_ms > 0 else None,
+                "peak_source": f"148 SM x 128 FMA lanes x 2 x {sm_clk:.0f} MHz (median SM clock sampled under load)",
+                "algorithmic_flops_per_sample": model["stage1_flops_per_sample"]}
+        if fe.stage1_tensor_launches > 0:
+            # Stage 1 ran on the tensor cores (channelizer_tc.cu). Algorithmic flops stay the reference's own count for
+            # NCO + first decimating FIR; the kernel executes more: complex x complex products, three fp16
+            # products per fp32 product, tap matrix padded to whole rows, 128-row tiles for 120 outputs.
+            tens_peak = float(peaks.get("bf16_tflops", 2250.0))
+            tens_src = ("MEASURED_PEAKS.json bf16_tflops (cuBLAS dense, burst; fp16 runs at the same rate)" if "bf16_tflops" in peaks
+                        else "fallback 2250 TFLOP/s nominal dense fp16 (B200_PROFILING.md)")
+            executed = 0.0
+            for (osr, bw, dm), cnt in collections.Counter((v[0], v[1], v[3]) for v in mine).items():
+                plan = cuda.design_resampler(SR, osr)[0]
+                st1 = cuda.design_decim_plan(plan["predec"])[0] if plan["predec"] > 1 else None
+                if st1 is None or st1[0] not in (32, 64):
+                    continue
+                D, T = int(st1[0]), len(st1[1])
+                A = -(-T // D)
+                executed += (-(-cnt // 16)) * (-(-(BLOCK // D) // 120)) * 3 * (2 * D // 16) * 2.0 * 128 * (32 * A) * 16
+            hbm_view = {k: roof[k] for k in ("achieved", "peak", "unit", "frac", "algorithmic_bytes_per_step", "note")}
+            hbm_view["note"] = "minimal-bytes accounting (8 B/sample in + outputs, SURVEY 8d)"
+            roof = {"bound": "tensor",
+                    "kernel": "s1t_split_kernel + s1t_kernel (tcgen05: NCO + first decimating FIR of every VFO as one split-fp16 matrix product per step)",
+                    "achieved": fp32["achieved"], "peak": tens_peak, "unit": "TFLOP/s",
+                    "frac": fp32["achieved"] / tens_peak if fp32["achieved"] else None,
+                    "traffic": traffic, "traffic_note": roof["traffic_note"], "peak_source": tens_src,
+                    "ms_per_step": float(s1_ms), "launches_per_step": 2,
+                    "algorithmic_flops_per_step": s1_flops, "algorithmic_flops_per_sample": model["stage1_flops_per_sample"],
+                    "executed": {"tflops": executed / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None,
+                                 "frac_of_peak": executed / (s1_ms * 1e-3) / 1e12 / tens_peak if s1_ms > 0 else None,
+                                 "flops_per_step": executed,
+                                 "note": "tensor-core flops issued: 3 fp16 products x complex x (tap matrix padded to ceil(T/D) rows) x 128-row tiles per 120 outputs"},
+                    "hbm": hbm_view, "fp32_equivalent": fp32,
+                    "note": "algorithmic flops = the reference's count for NCO + first FIR (what the FP32 kernel of mode 1 executes); ms_per_step covers the fp16 split of the block and the matrix-product kernel"}
+        else:
+            roof["fp32"] = fp32
         fft_bytes = 12.0 * BLOCK
         roof_fft = {"bound": "hbm", "kernel": "fft_cols_kernel + fft_rows_kernel (window + 1M-pt FFT + dB row)",
                     "achieved": fft_bytes / (fft_ms * 1e-3) / 1e9 if fft_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",

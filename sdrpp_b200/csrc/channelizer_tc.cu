@@ -130,11 +130,17 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // Debug build only (-DSDRPP_S1T_TRACE): per-CTA cycle counters of the three roles (tools/s1t_trace.py)
 __device__ long long g_s1t_trace[256][16];
 #define S1T_T0(var) const long long var = clock64()
-#define S1T_ACC(slot, var) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] += clock64() - (var); } while (0)
+#define S1T_ACC(slot, var) do { s1t_acc_[slot] += clock64() - (var); } while (0)
+#define S1T_DECL long long s1t_acc_[16] = { 0 }
+#define S1T_ARG , s1t_acc_
+#define S1T_FLUSH(slot) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = s1t_acc_[slot]; } while (0)
 #define S1T_SET(slot, val) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = (val); } while (0)
 #else
 #define S1T_T0(var) do {} while (0)
 #define S1T_ACC(slot, var) do {} while (0)
+#define S1T_DECL do {} while (0)
+#define S1T_ARG
+#define S1T_FLUSH(slot) do {} while (0)
 #define S1T_SET(slot, val) do {} while (0)
 #endif
 
@@ -300,7 +306,11 @@ cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, cons
 // ---------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S1TPlanes& pl, uint32_t tmem_acc, int q, int hf, int lane,
-                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur) {
+                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur
+#ifdef SDRPP_S1T_TRACE
+                                                  , long long* s1t_acc_
+#endif
+                                                  ) {
     constexpr int NVH = kNVW;
 #ifdef SDRPP_S1T_TRACE
     const long long tl0_ = clock64();
@@ -406,6 +416,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    S1T_DECL;
 #ifdef SDRPP_S1T_TRACE
     const long long tk0_ = clock64();
     if (tid == 0 && blockIdx.x < 256) { for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0; g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A; }
@@ -491,6 +502,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                         S1T_ACC(3, tf_);
                         tc_fence_after();
                         const uint64_t xh = umma_desc_sw128(sA + slot * (uint32_t)kChunkBytes);
+                        S1T_T0(ti_);
                         if (elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {
@@ -500,6 +512,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                             tc_commit(empty + slot);
                         }
                         __syncwarp();
+                        S1T_ACC(4, ti_);
                         it++;
                     }
                     {
@@ -509,6 +522,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                         S1T_ACC(3, tf_);
                         tc_fence_after();
                         const uint64_t xl = umma_desc_sw128(sA + slot * (uint32_t)kChunkBytes);
+                        S1T_T0(ti_);
                         if (elect_one()) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) tc_mma_f16(d_tmem, xl + 2u * ks, bh + 2u * ks, idesc, 1u);
@@ -516,6 +530,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                             if (kh == NKH - 1) tc_commit(tfull + as);
                         }
                         __syncwarp();
+                        S1T_ACC(8, ti_);
                         it++;
                     }
                 }
@@ -562,11 +577,11 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             float* xb = xch + (k & 1u) * (kXchFloats / 2);
             const uint32_t acc = tmem_base + as * 256u;
             switch (A) {
-            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
-            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
-            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
-            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
-            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur); break;
+            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
             }
 #pragma unroll
             for (int j = 0; j < NVH; j++) cur[j] = cmul(cur[j], stp[j]);
@@ -575,10 +590,15 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #endif
         }
     }
+#ifdef SDRPP_S1T_TRACE
+    if (warp == 0) { S1T_FLUSH(10); }
+    if (warp == 1) { S1T_FLUSH(2); S1T_FLUSH(3); S1T_FLUSH(4); S1T_FLUSH(8); S1T_FLUSH(14); }
+    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); }
+#endif
     tc_fence_before();
     __syncthreads();
 #ifdef SDRPP_S1T_TRACE
-    if (tid == 0) { S1T_ACC(1, tk0_); }
+    if (tid == 0) { S1T_ACC(1, tk0_); S1T_FLUSH(1); }
 #endif
     if (warp == 1) {
         tc_fence_after();

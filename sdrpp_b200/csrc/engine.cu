@@ -242,7 +242,7 @@ struct sdrpp_cuda_frontend {
     int device = 0;
     sdrpp_cuda_frontend_cfg cfg{};
     double eff_sr = 0;
-    cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr, st_s1b = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr, st_s1b = nullptr, st_d2h = nullptr;
     cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft = nullptr, ev_tail[2] = { nullptr, nullptr };
     cudaEvent_t ev_s1_fork = nullptr, ev_s1_join = nullptr;
     bool ev_tail_valid[2] = { false, false };
@@ -488,9 +488,10 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         if (fe->d_arena_demod) cudaFree(fe->d_arena_demod);
         if (fe->d_arena_audio) cudaFree(fe->d_arena_audio);
         fe->arena_cap = arena + arena / 2 + 1024;
-        FE_TRY(fe, dev_alloc(&fe->d_arena_iq, fe->arena_cap));
-        FE_TRY(fe, dev_alloc(&fe->d_arena_demod, fe->arena_cap));
-        FE_TRY(fe, dev_alloc(&fe->d_arena_audio, fe->arena_cap));
+        // two result arenas (block parity): the device-to-host copy of block i runs beside the tail of block i+1
+        FE_TRY(fe, dev_alloc(&fe->d_arena_iq, 2 * fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_demod, 2 * fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_audio, 2 * fe->arena_cap));
     }
     if (arena > fe->rs_arena_cap) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
@@ -860,7 +861,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
 
         if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
             TailArgs t{};
-            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq; t.arena_demod = fe->d_arena_demod;
+            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq + (size_t)par * fe->arena_cap; t.arena_demod = fe->d_arena_demod + (size_t)par * fe->arena_cap;
             tails.push_back(t); tail_totals.push_back(0);
         }
         TailArgs& t = tails.back();
@@ -924,7 +925,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 pa.g[k].first_vfo = tails[i].g[k].first_vfo; pa.g[k].nvfo = tails[i].g[k].nvfo; pa.g[k].n = tails[i].g[k].n_final;
                 any = any || pa.g[k].n > 0;
             }
-            pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq; pa.arena_demod = fe->d_arena_demod; pa.arena_audio = fe->d_arena_audio;
+            pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq + (size_t)par * fe->arena_cap; pa.arena_demod = fe->d_arena_demod + (size_t)par * fe->arena_cap;
+            pa.arena_audio = fe->d_arena_audio + (size_t)par * fe->arena_cap;
             if (any && tail_totals[i] > 0) { FE_TRY(fe, launch_post(pa, tail_totals[i], stl)); fe->launches++; }
         }
     }
@@ -934,20 +936,26 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     rs.counts.assign(fe->vfos.size(), 0);
     for (const Group& g : fe->groups)
         for (int id : g.members) rs.counts[(size_t)id] = g.last_n_final;
-    if (fe->readback && fe->arena_used > 0) {
-        FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, stl));
-        FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, stl));
-        if (fe->post_active > 0)
-            FE_TRY(fe, cudaMemcpyAsync(rs.audio, fe->d_arena_audio, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, stl));
-    }
+    // The copies run on their own stream behind the tail, so the tail of the next block does not queue up behind
+    // them; the pinned result set and the arena of this parity are free again once the caller has waited for
+    // block i (it must, before submitting block i+2).
+    cudaStream_t sd = prof ? st : fe->st_d2h;
     if (!prof) {
         FE_TRY(fe, cudaEventRecord(fe->ev_tail[par], stl));
         fe->ev_tail_valid[par] = true;
-        FE_TRY(fe, cudaStreamWaitEvent(stl, fe->ev_fft, 0)); // the block is done when its rows are on the host too
+        FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_tail[par], 0));
     } else {
         fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;  // everything ran in order on st
     }
-    FE_TRY(fe, cudaEventRecord(rs.done, stl));
+    if (fe->readback && fe->arena_used > 0) {
+        const size_t ao = (size_t)par * fe->arena_cap;
+        FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq + ao, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, sd));
+        FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
+        if (fe->post_active > 0)
+            FE_TRY(fe, cudaMemcpyAsync(rs.audio, fe->d_arena_audio + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
+    }
+    if (!prof) FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_fft, 0)); // the block is done when its rows are on the host too
+    FE_TRY(fe, cudaEventRecord(rs.done, sd));
     rs.pending = true;
     fe->blk++;
     return SDRPP_OK;
@@ -1253,6 +1261,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaStreamCreateWithFlags(&fe->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_tail, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_d2h, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_s1b, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
     if (cudaEventCreateWithFlags(&fe->ev_ingest, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1, cudaEventDisableTiming) != cudaSuccess ||
@@ -1285,6 +1294,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_copy) cudaStreamSynchronize(fe->st_copy);
     if (fe->st_fft) cudaStreamSynchronize(fe->st_fft);
     if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
+    if (fe->st_d2h) cudaStreamSynchronize(fe->st_d2h);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
     for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); }
     for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
@@ -1313,6 +1323,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_copy) cudaStreamDestroy(fe->st_copy);
     if (fe->st_fft) cudaStreamDestroy(fe->st_fft);
     if (fe->st_tail) cudaStreamDestroy(fe->st_tail);
+    if (fe->st_d2h) cudaStreamDestroy(fe->st_d2h);
     if (fe->st_s1b) cudaStreamDestroy(fe->st_s1b);
     for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft, fe->ev_tail[0], fe->ev_tail[1], fe->ev_s1_fork, fe->ev_s1_join }) if (e) cudaEventDestroy(e);
     cudaGetLastError();
@@ -1327,6 +1338,7 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, cudaStreamSynchronize(fe->st));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_fft));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_tail));
+    FE_TRY(fe, cudaStreamSynchronize(fe->st_d2h));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_s1b));
     fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;
     // everything submitted so far is complete: nothing is left to wait for

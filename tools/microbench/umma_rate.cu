@@ -1,6 +1,7 @@
 // tcgen05.mma issue/execute rate on one SM per N (M = 128, K = 16, fp16 -> fp32, both operands in shared memory,
 // K-major SWIZZLE_128B): cycles per MMA for N = 64..256, with the A/B descriptors (a) fixed and (b) walking over a
-// 96 KB + 128 KB operand area like the channelizer's stage-1 kernel does.
+// 96 KB + 128 KB operand area like the channelizer's stage-1 kernel does, alone and with the stage-1 kernel's other
+// traffic running beside it: tcgen05.ld of the second accumulator stage, bulk copies into shared memory.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o umma_rate umma_rate.cu && ./umma_rate
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -19,15 +20,18 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-__global__ void __launch_bounds__(128, 1) k(int N, int iters, int walk, int two_acc, long long* out) {
+__global__ void __launch_bounds__(256, 1) k(int N, int iters, int walk, int two_acc, int ldtm_warps, int tma, const uint8_t* gsrc, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, cbar;
+    __shared__ volatile int done;
     __shared__ uint32_t tslot;
     uint8_t* base = (uint8_t*)(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
     for (int i = threadIdx.x; i < 220 * 1024 / 4; i += blockDim.x) ((uint32_t*)base)[i] = 0;
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&cbar)));
+        done = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (warp == 0) {
@@ -60,7 +64,37 @@ __global__ void __launch_bounds__(128, 1) k(int N, int iters, int walk, int two_
         uint32_t ok = 0;
         while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_addr(&bar)) : "memory");
         const long long t1 = clock64();
-        if ((threadIdx.x & 31) == 0) out[blockIdx.x] = t1 - t0;
+        if ((threadIdx.x & 31) == 0) { out[blockIdx.x] = t1 - t0; done = 1; }
+    } else if (warp >= 4 && warp < 4 + ldtm_warps) {
+        // concurrent TMEM reads (the epilogue's tcgen05.ld of the OTHER accumulator stage)
+        uint32_t r[16], acc = 0;
+        while (!done) {
+            const uint32_t ta = tm + ((uint32_t)((warp & 3) * 32) << 16) + 256u;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                             : "r"(ta + 16u * j) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                acc += r[0] + r[15];
+            }
+        }
+        if (acc == 0x12345678u) out[0] = 0;
+    } else if (warp == 2 && tma) {
+        // concurrent bulk copies into an unused part of shared memory (the producer's A chunks)
+        uint32_t ph = 0;
+        while (!done) {
+            if (elect_one()) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&cbar)), "r"(16384u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(smem_addr(base + 200 * 1024)), "l"(gsrc + (size_t)blockIdx.x * 16384), "r"(16384u), "r"(smem_addr(&cbar)) : "memory");
+            }
+            __syncwarp();
+            uint32_t ok = 0;
+            while (!ok) asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_addr(&cbar)), "r"(ph) : "memory");
+            ph ^= 1;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
@@ -70,14 +104,17 @@ __global__ void __launch_bounds__(128, 1) k(int N, int iters, int walk, int two_
 int main() {
     long long* d;
     cudaMalloc(&d, 148 * sizeof(long long));
+    uint8_t* gsrc;
+    cudaMalloc(&gsrc, 148 * 16384);
+    cudaMemset(gsrc, 0, 148 * 16384);
     const size_t smem = 226 * 1024;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int iters = 2000;
-    for (int ctas : { 1, 148 })
-        for (int walk = 0; walk < 2; walk++)
-            for (int two = 0; two < 2; two++)
-                for (int N : { 64, 128, 192, 224, 256 }) {
-                    k<<<ctas, 128, smem>>>(N, iters, walk, two, d);
+    const int ctas = 148, walk = 1, two = 0;
+    for (int tma = 0; tma < 2; tma++)
+        for (int lw : { 0, 1, 4 })
+                for (int N : { 128, 192, 224, 256 }) {
+                    k<<<ctas, 256, smem>>>(N, iters, walk, two, lw, tma, gsrc, d);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
                     long long h[148];
@@ -85,7 +122,7 @@ int main() {
                     double s = 0;
                     for (int i = 0; i < ctas; i++) s += (double)h[i];
                     s /= ctas;
-                    printf("ctas %3d walk %d two_acc %d N %3d: %.1f cycles per MMA (floor %d), %.0f FMA/clk/SM\n", ctas, walk, two, N,
+                    printf("bulk copies %d, tcgen05.ld warps %d, N %3d: %.1f cycles per MMA (floor %d), %.0f FMA/clk/SM\n", tma, lw, N,
                            s / (iters * 4.0), N / 2, 128.0 * N * 16 * iters * 4 / s);
                 }
     return 0;
