@@ -376,9 +376,11 @@ def run_gpu(args, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         step_host(0)
-        for i in range(1, args.steps):
-            step_host(i)      # block i is copied in while block i-1 is still computing
-            consume()         # results of block i-1
+        step_host(1)
+        for i in range(2, args.steps):
+            step_host(i)      # block i is copied in while blocks i-2 and i-1 are still in flight (three result sets)
+            consume()         # results of block i-2
+        consume()
         consume()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0

@@ -173,13 +173,15 @@ SDRPP_API int sdrpp_cuda_vfo_info(sdrpp_cuda_frontend* fe, int vfo, int* info);
 SDRPP_API int sdrpp_cuda_frontend_submit(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count);
 /* Same, with `in` already in device memory on this GPU (e.g. the target of an NCCL broadcast). */
 SDRPP_API int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt, const void* dev_in, int count);
-/* Block until the last submitted block's results are on the host. */
+/* Block until the OLDEST block not yet waited for has its results on the host. Up to three blocks may be in flight
+ * (submit, submit, submit, wait, submit, wait, ...): with two or more submitted ahead, the host-to-device copy of a
+ * block never waits for an earlier block's results to reach the host. */
 SDRPP_API int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe);
 /* Skip the device->host copies of results (kernel-only timing); default 1 = copy. */
 SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled);
 
 /* Results of the last waited block. Pointers are into pinned host memory owned by the front end
- * and stay valid until the next submit. */
+ * and stay valid until the next submit (with blocks submitted ahead: until the third submit after the block's own). */
 /* RxVFO::out for this block: returns the output sample count; *iq -> cf32[count];
  * *demod -> float[count] (NULL when demod == NONE). */
 SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cf32** iq, const float** demod);

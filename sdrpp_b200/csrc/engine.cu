@@ -238,6 +238,8 @@ struct ResultSet {
 
 using namespace sdrpp;
 
+constexpr int kSets = 3; // result sets / raw staging buffers / result arenas
+
 struct sdrpp_cuda_frontend {
     int device = 0;
     sdrpp_cuda_frontend_cfg cfg{};
@@ -251,10 +253,12 @@ struct sdrpp_cuda_frontend {
     std::string sticky;
 
     // input staging
-    void* h_stage[2] = { nullptr, nullptr };
-    void* d_raw[2] = { nullptr, nullptr };
-    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_consumed[2] = { nullptr, nullptr };
-    bool consumed_valid[2] = { false, false };
+    // kSets blocks may be in flight: the caller can submit block i+2 before waiting for block i, so that the
+    // host-to-device copy of a block never waits for the results of an earlier one to reach the host
+    void* h_stage[kSets] = { nullptr };
+    void* d_raw[kSets] = { nullptr };
+    cudaEvent_t ev_h2d[kSets] = { nullptr }, ev_consumed[kSets] = { nullptr };
+    bool consumed_valid[kSets] = { false };
     size_t raw_cap = 0;
     long long seq = 0;
 
@@ -291,7 +295,7 @@ struct sdrpp_cuda_frontend {
     float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; float* d_arena_audio = nullptr; size_t arena_cap = 0, arena_used = 0;
 
     // results
-    ResultSet rs[2];
+    ResultSet rs[kSets];
     size_t rs_arena_cap = 0; int rs_rows_cap = 0; int rs_rows_n = 0;
     int cur = -1; // result set of the last waited block
     long long waited = 0;
@@ -363,14 +367,14 @@ static int configure_preproc(sdrpp_cuda_frontend* fe) {
 static int configure_zoom(sdrpp_cuda_frontend* fe) {
     if (fe->d_zoom_idx) { cudaFree(fe->d_zoom_idx); fe->d_zoom_idx = nullptr; }
     if (fe->d_zoom) { cudaFree(fe->d_zoom); fe->d_zoom = nullptr; }
-    for (int i = 0; i < 2; i++) if (fe->rs[i].zoom) { cudaFreeHost(fe->rs[i].zoom); fe->rs[i].zoom = nullptr; }
+    for (int i = 0; i < kSets; i++) if (fe->rs[i].zoom) { cudaFreeHost(fe->rs[i].zoom); fe->rs[i].zoom = nullptr; }
     if (fe->zoom_out <= 0 || fe->cfg.fft_size <= 0 || fe->rows_cap <= 0) return SDRPP_OK;
     std::vector<int> idx;
     fe->zoom_ranged = zoom_indices(fe->zoom_view[0], fe->zoom_view[1], fe->zoom_view[2], fe->cfg.fft_size, fe->zoom_out, &idx);
     FE_TRY(fe, dev_alloc(&fe->d_zoom_idx, idx.size(), false));
     FE_TRY(fe, cudaMemcpy(fe->d_zoom_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
     FE_TRY(fe, dev_alloc(&fe->d_zoom, (size_t)fe->rows_cap * fe->zoom_out, false));
-    for (int i = 0; i < 2; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].zoom, (size_t)fe->rows_cap * fe->zoom_out * sizeof(float)));
+    for (int i = 0; i < kSets; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].zoom, (size_t)fe->rows_cap * fe->zoom_out * sizeof(float)));
     return SDRPP_OK;
 }
 
@@ -379,7 +383,7 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     if (fe->d_window) { cudaFree(fe->d_window); fe->d_window = nullptr; }
     if (fe->d_inter) { cudaFree(fe->d_inter); fe->d_inter = nullptr; }
     if (fe->d_rows) { cudaFree(fe->d_rows); fe->d_rows = nullptr; }
-    for (int i = 0; i < 2; i++) if (fe->rs[i].rows) { cudaFreeHost(fe->rs[i].rows); fe->rs[i].rows = nullptr; }
+    for (int i = 0; i < kSets; i++) if (fe->rs[i].rows) { cudaFreeHost(fe->rs[i].rows); fe->rs[i].rows = nullptr; }
     fe->rows_cap = 0; fe->rs_rows_cap = 0;
     const int N = fe->cfg.fft_size;
     if (N == 0) return SDRPP_OK;
@@ -406,7 +410,7 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     } else {
         fe->inter_frames = rows;
     }
-    for (int i = 0; i < 2; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].rows, (size_t)rows * N * sizeof(float)));
+    for (int i = 0; i < kSets; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].rows, (size_t)rows * N * sizeof(float)));
     fe->rs_rows_cap = rows;
     fe->fft_next = fe->abs_pos;
     return configure_zoom(fe);
@@ -488,14 +492,14 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         if (fe->d_arena_demod) cudaFree(fe->d_arena_demod);
         if (fe->d_arena_audio) cudaFree(fe->d_arena_audio);
         fe->arena_cap = arena + arena / 2 + 1024;
-        // two result arenas (block parity): the device-to-host copy of block i runs beside the tail of block i+1
-        FE_TRY(fe, dev_alloc(&fe->d_arena_iq, 2 * fe->arena_cap));
-        FE_TRY(fe, dev_alloc(&fe->d_arena_demod, 2 * fe->arena_cap));
-        FE_TRY(fe, dev_alloc(&fe->d_arena_audio, 2 * fe->arena_cap));
+        // one result arena per result set: the device-to-host copy of block i runs beside the tail of block i+1
+        FE_TRY(fe, dev_alloc(&fe->d_arena_iq, kSets * fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_demod, kSets * fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_audio, kSets * fe->arena_cap));
     }
     if (arena > fe->rs_arena_cap) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kSets; i++) {
             if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
             if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
             if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
@@ -692,6 +696,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     cudaStream_t sf = prof ? st : fe->st_fft;
     cudaStream_t stl = prof ? st : fe->st_tail;
     const int par = (int)(fe->blk & 1);
+    const int aset = (int)(&rs - fe->rs); // result set (and result arena) of this block
     if (!prof) {
         FE_TRY(fe, cudaEventRecord(fe->ev_ingest, st));
         FE_TRY(fe, cudaStreamWaitEvent(sf, fe->ev_ingest, 0));
@@ -861,7 +866,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
 
         if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
             TailArgs t{};
-            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq + (size_t)par * fe->arena_cap; t.arena_demod = fe->d_arena_demod + (size_t)par * fe->arena_cap;
+            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq + (size_t)aset * fe->arena_cap; t.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
             tails.push_back(t); tail_totals.push_back(0);
         }
         TailArgs& t = tails.back();
@@ -925,8 +930,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 pa.g[k].first_vfo = tails[i].g[k].first_vfo; pa.g[k].nvfo = tails[i].g[k].nvfo; pa.g[k].n = tails[i].g[k].n_final;
                 any = any || pa.g[k].n > 0;
             }
-            pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq + (size_t)par * fe->arena_cap; pa.arena_demod = fe->d_arena_demod + (size_t)par * fe->arena_cap;
-            pa.arena_audio = fe->d_arena_audio + (size_t)par * fe->arena_cap;
+            pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq + (size_t)aset * fe->arena_cap; pa.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
+            pa.arena_audio = fe->d_arena_audio + (size_t)aset * fe->arena_cap;
             if (any && tail_totals[i] > 0) { FE_TRY(fe, launch_post(pa, tail_totals[i], stl)); fe->launches++; }
         }
     }
@@ -948,7 +953,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;  // everything ran in order on st
     }
     if (fe->readback && fe->arena_used > 0) {
-        const size_t ao = (size_t)par * fe->arena_cap;
+        const size_t ao = (size_t)aset * fe->arena_cap;
         FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq + ao, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, sd));
         FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
         if (fe->post_active > 0)
@@ -975,9 +980,9 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
     if (rc != SDRPP_OK) return rc;
     if (fmt < 0 || fmt >= SDRPP_FMT_COUNT) return fail(SDRPP_ERR_ARG, "unknown sample format");
     if (!in || count <= 0 || count > fe->cfg.max_block) return fail(SDRPP_ERR_ARG, "count must be in 1..max_block");
-    const int slot = (int)(fe->seq & 1);
+    const int slot = (int)(fe->seq % kSets);
     ResultSet& rs = fe->rs[slot];
-    rc = wait_set(fe, slot); // the block that used this result set two submits ago must be done
+    rc = wait_set(fe, slot); // the block that used this result set kSets submits ago must be done
     if (rc != SDRPP_OK) return rc;
     const void* d_in = in;
     if (!device_src) {
@@ -1272,7 +1277,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
     if (dev_alloc(&fe->ring, (size_t)1 << fe->ring_log2) != cudaSuccess) return bail("ring allocation failed");
     fe->raw_cap = (size_t)fe->cfg.max_block * 16; // widest input format: complex f64
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kSets; i++) {
         if (cudaMallocHost(&fe->h_stage[i], fe->raw_cap) != cudaSuccess) return bail("pinned staging allocation failed");
         if (cudaMalloc(&fe->d_raw[i], fe->raw_cap) != cudaSuccess) return bail("raw buffer allocation failed");
         if (cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
@@ -1306,7 +1311,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     cudaFree(fe->ring); cudaFree(fe->d_window); cudaFree(fe->d_inter); cudaFree(fe->d_rows);
     cudaFree(fe->d_zoom_idx); cudaFree(fe->d_zoom);
     cudaFree(fe->d_vfos); cudaFree(fe->d_post); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod); cudaFree(fe->d_arena_audio);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kSets; i++) {
         if (fe->h_stage[i]) cudaFreeHost(fe->h_stage[i]);
         if (fe->d_raw[i]) cudaFree(fe->d_raw[i]);
         if (fe->ev_h2d[i]) cudaEventDestroy(fe->ev_h2d[i]);
@@ -1342,8 +1347,8 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, cudaStreamSynchronize(fe->st_s1b));
     fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;
     // everything submitted so far is complete: nothing is left to wait for
-    for (int i = 0; i < 2; i++) fe->rs[i].pending = false;
-    if (fe->seq > 0) { fe->waited = fe->seq; fe->cur = (int)((fe->seq - 1) & 1); }
+    for (int i = 0; i < kSets; i++) fe->rs[i].pending = false;
+    if (fe->seq > 0) { fe->waited = fe->seq; fe->cur = (int)((fe->seq - 1) % kSets); }
     return SDRPP_OK;
 }
 
@@ -1559,9 +1564,9 @@ int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe) {
     if (rc != SDRPP_OK) return rc;
     if (fe->seq == 0) return fail(SDRPP_ERR_STATE, "nothing submitted");
     // oldest block not yet waited for
-    if (fe->waited < fe->seq - 2) fe->waited = fe->seq - 2;
+    if (fe->waited < fe->seq - kSets) fe->waited = fe->seq - kSets;
     if (fe->waited >= fe->seq) fe->waited = fe->seq - 1;
-    const int slot = (int)(fe->waited & 1);
+    const int slot = (int)(fe->waited % kSets);
     if ((rc = wait_set(fe, slot)) != SDRPP_OK) return rc;
     fe->cur = slot;
     fe->waited++;
