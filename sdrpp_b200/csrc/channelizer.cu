@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "design.h"
 #include "kernels.h"
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <type_traits>
@@ -421,6 +422,7 @@ __device__ __forceinline__ void tail_stage_in(float2* sm, const float2* src, int
 // plane, and the four taps that meet that sample, (h[s], h[s-D], h[s-2D], h[s-3D]), come from one broadcast load of
 // a table built per stage. Few outputs and many taps (the channel filter): the s range is split over KS thread groups
 // and reduced through shared memory. out[o] = sum_k buf[offset + o*D + k] * h[k] (decimating_fir.h:45-68, fir.h:62-83).
+template <int NT>
 __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, const float2* __restrict__ buf, float2* __restrict__ out,
                                                  float2* tsm, float4* tt) {
     constexpr int OB = 4;
@@ -428,7 +430,7 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
     const int tid = threadIdx.x;
     const int T = st.T, M = OB * D, lgM = 31 - __clz(M);
     const int S = (OB - 1) * D + T, SQ = (S + M - 1) >> lgM;
-    int ch = min(OB * kTailThreads, (kTailSmemSamples - T - 16 * D) / D) & ~(OB - 1);
+    int ch = min(OB * NT, (kTailSmemSamples - T - 16 * D) / D) & ~(OB - 1);
     if (ch < OB) ch = OB;
     for (int o0 = 0; o0 < st.n_out; o0 += ch) {
         const int co = min(ch, st.n_out - o0);
@@ -439,7 +441,7 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
         {
             // asynchronous element copies (the copy is L2-latency-bound: everything a thread moves is in flight at once)
             const int total = M * qs;
-            for (int i = tid; i < total; i += kTailThreads) {
+            for (int i = tid; i < total; i += NT) {
                 float2* dst = tsm + (i & (M - 1)) * qs + (i >> lgM);
                 if (i < n) cp_async8(dst, src + i);
                 else *dst = make_float2(0.0f, 0.0f);
@@ -447,7 +449,7 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
             cp_async_wait_all();
         }
         int KS = 1;
-        while (KS < 8 && nthr * KS * 2 <= kTailThreads && SQ >= 8 * KS * 2) KS *= 2;
+        while (KS < 8 && nthr * KS * 2 <= NT && SQ >= 8 * KS * 2) KS *= 2;
         const int Sk = (SQ + KS - 1) / KS;                  // rows of M s-values per thread group
         const int SEGq = max(1, min(Sk, kTabEntries / (KS * M)));
         const int t_out = tid % nthr, ks = tid / nthr;
@@ -457,7 +459,7 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
         for (int r = 0; r < OB; r++) acc[r] = make_float2(0.0f, 0.0f);
         for (int q0 = 0; q0 < Sk; q0 += SEGq) {
             // tap table of this step: for each group, rows [ks*Sk + q0, +SEGq)
-            for (int e = tid; e < KS * SEGq * M; e += kTailThreads) {
+            for (int e = tid; e < KS * SEGq * M; e += NT) {
                 const int g = e / (SEGq * M), loc = e - g * (SEGq * M);
                 const int row = g * Sk + q0 + (loc >> lgM);
                 float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -481,10 +483,11 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
                     for (int sp = 0; sp < M; sp++) {
                         const float2 v = xp[sp * qs];
                         const float4 h = tp[sp];
-                        acc[0].x = fmaf(v.x, h.x, acc[0].x); acc[0].y = fmaf(v.y, h.x, acc[0].y);
-                        acc[1].x = fmaf(v.x, h.y, acc[1].x); acc[1].y = fmaf(v.y, h.y, acc[1].y);
-                        acc[2].x = fmaf(v.x, h.z, acc[2].x); acc[2].y = fmaf(v.y, h.z, acc[2].y);
-                        acc[3].x = fmaf(v.x, h.w, acc[3].x); acc[3].y = fmaf(v.y, h.w, acc[3].y);
+                        // packed FMA: (re, im) of one accumulator per instruction, the tap broadcast to both halves
+                        acc[0] = __ffma2_rn(make_float2(h.x, h.x), v, acc[0]);
+                        acc[1] = __ffma2_rn(make_float2(h.y, h.y), v, acc[1]);
+                        acc[2] = __ffma2_rn(make_float2(h.z, h.z), v, acc[2]);
+                        acc[3] = __ffma2_rn(make_float2(h.w, h.w), v, acc[3]);
                     }
                 }
             }
@@ -527,13 +530,13 @@ tail_kernel(const __grid_constant__ TailArgs a) {
     float2* slab = vd.slab;
     const int tid = threadIdx.x;
 
-    for (int s = 0; s < g.nstages; s++) {
+    for (int s = g.s_begin; s < g.nstages; s++) { // stage 0 may already have run in tail_stage0_wide_kernel
         const TailStage& st = g.st[s];
         const int T = st.T, hist = T - 1;
         float2* buf = slab + st.in_off - hist; // [hist | n_in]
         float2* out = slab + ((s + 1 < g.nstages) ? g.st[s + 1].in_off : g.final_off);
         if (st.type != TAIL_POLY) {
-            tail_fir_blocked(st, st.type == TAIL_DECFIR ? st.D : 1, buf, out, tsm, reinterpret_cast<float4*>(ttaps));
+            tail_fir_blocked<kTailThreads>(st, st.type == TAIL_DECFIR ? st.D : 1, buf, out, tsm, reinterpret_cast<float4*>(ttaps));
         } else {
             // polyphase resampler: consecutive outputs use different tap phases and input strides; one output per thread
             const bool taps_staged = (long long)st.interp * T <= kTailTapFloats;
@@ -555,16 +558,16 @@ tail_kernel(const __grid_constant__ TailArgs a) {
                     const float2* x = tsm + (st.offset + (int)(P / st.interp) - first);
                     const int ph = (int)(P % st.interp);
                     const float* h = taps_staged ? ttaps + ph * T : st.taps + (size_t)ph * T; // rows are not 16-byte aligned in general
-                    float re0 = 0.0f, im0 = 0.0f, re1 = 0.0f, im1 = 0.0f;
+                    float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
                     int k = 0;
                     for (; k + 2 <= T; k += 2) {
                         const float2 v0 = x[k], v1 = x[k + 1];
                         const float t0 = h[k], t1 = h[k + 1];
-                        re0 = fmaf(v0.x, t0, re0); im0 = fmaf(v0.y, t0, im0);
-                        re1 = fmaf(v1.x, t1, re1); im1 = fmaf(v1.y, t1, im1);
+                        a0 = __ffma2_rn(make_float2(t0, t0), v0, a0);
+                        a1 = __ffma2_rn(make_float2(t1, t1), v1, a1);
                     }
-                    if (k < T) { const float2 v = x[k]; const float t = h[k]; re0 = fmaf(v.x, t, re0); im0 = fmaf(v.y, t, im0); }
-                    out[o] = make_float2(re0 + re1, im0 + im1);
+                    if (k < T) { const float2 v = x[k]; const float t = h[k]; a0 = __ffma2_rn(make_float2(t, t), v, a0); }
+                    out[o] = make_float2(a0.x + a1.x, a0.y + a1.y);
                 }
                 __syncthreads();
             }
@@ -610,6 +613,109 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         if (g.n_final > 0) nxt[-1] = fin[g.n_final - 1];
         else if (g.nstages == 0) nxt[-1] = fin[-1];
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The first tail stage (the second decimating FIR of the PowerDecimator cascade) on its own, wide grid: it still
+// runs at 1/D of the input rate for every VFO (e.g. 9600 samples per VFO and block), which one CTA per VFO can only
+// walk in three sequential load-compute rounds. Here a CTA of 128 threads owns a range of outputs of one VFO, so the
+// stage is spread over the whole machine; the tail kernel then starts from the second stage. CTA 0 of a VFO also
+// carries the stage's history to the other stage-1 region (fir.h:80), like the tail kernel does for its stage 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWideThreads = 128;
+constexpr int kWideR = 2;                        // outputs per thread: tid + 128 r
+constexpr int kWideOut = kWideR * kWideThreads;  // outputs per CTA at most
+constexpr int kWideMaxTaps = 128;
+
+// Samples of the CTA's window are staged transposed by D (element i at plane i % D, position i / D, odd plane
+// stride): for every tap the threads of a warp (consecutive outputs) read consecutive positions of one plane.
+// A tap load serves the thread's four outputs; accumulation is packed FMA on (re, im).
+template <int D>
+__global__ void __launch_bounds__(kWideThreads, 10)
+tail_stage0_wide_kernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    float* taps = reinterpret_cast<float*>(tail_smem);                            // [kWideMaxTaps + 16], zero padded
+    float2* xs = reinterpret_cast<float2*>(tail_smem + (kWideMaxTaps + 16) * 4);  // transposed window
+    int vi = blockIdx.y, gi = 0;
+    while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
+    const TailGroup& g = a.g[gi];
+    if (g.s_begin == 0 || g.nstages == 0 || g.st[0].D != D) return; // not this instantiation's (or the tail kernel's) stage
+    const TailStage& st = g.st[0];
+    float2* slab = a.vfos[g.first_vfo + vi].slab;
+    constexpr int lg = D == 2 ? 1 : D == 4 ? 2 : D == 8 ? 3 : 4;
+    constexpr int qs = (kWideOut + (kWideMaxTaps >> lg) + 2) | 1;
+    const int T = st.T, hist = T - 1;
+    const float2* __restrict__ buf = slab + st.in_off - hist;
+    float2* __restrict__ out = slab + ((g.nstages > 1) ? g.st[1].in_off : g.final_off);
+    const int tid = threadIdx.x;
+    // equal ranges of outputs over the CTAs of this VFO
+    const int nct = max(1, (st.n_out + kWideOut - 1) / kWideOut);
+    const int per = (st.n_out + nct - 1) / nct;
+    const int o0 = (int)blockIdx.x * per;
+    if ((int)blockIdx.x < nct && o0 < st.n_out) {
+        const int co = min(per, st.n_out - o0);
+        const int n = (co - 1) * D + T;                 // samples of the window that exist
+        const float2* __restrict__ src = buf + st.offset + o0 * D;
+        for (int i = tid; i < n; i += kWideThreads) cp_async8(xs + (i & (D - 1)) * qs + (i >> lg), src + i);
+        // the last tap group is zero padded to D taps: the samples it meets must be finite
+        for (int i = n + tid; i < n + D; i += kWideThreads) xs[(i & (D - 1)) * qs + (i >> lg)] = make_float2(0.0f, 0.0f);
+        for (int i = tid; i < kWideMaxTaps + 16; i += kWideThreads) taps[i] = i < T ? __ldg(st.taps + i) : 0.0f;
+        cp_async_wait_all();
+        __syncthreads();
+        float2 acc[kWideR];
+#pragma unroll
+        for (int r = 0; r < kWideR; r++) acc[r] = make_float2(0.0f, 0.0f);
+        // positions past the staged window are only read for outputs >= co (not stored)
+        for (int k0 = 0; k0 < T; k0 += D) {
+            const float2* __restrict__ xp = xs + (k0 >> lg) + tid;
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+                const float h = taps[k0 + c];
+#pragma unroll
+                for (int r = 0; r < kWideR; r++) acc[r] = __ffma2_rn(make_float2(h, h), xp[c * qs + r * kWideThreads], acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kWideR; r++)
+            if (tid + r * kWideThreads < co) out[o0 + tid + r * kWideThreads] = acc[r];
+    }
+    if (blockIdx.x == 0) {
+        float2* dst = slab + g.carry0_off - hist;
+        for (int i = tid; i < hist; i += kWideThreads) dst[i] = buf[st.n_in + i];
+    }
+}
+
+template <int D>
+static cudaError_t launch_wide_t(const TailArgs& a, int total_vfos, int max_out, cudaStream_t st) {
+    constexpr int lg = D == 2 ? 1 : D == 4 ? 2 : D == 8 ? 3 : 4;
+    constexpr int qs = (kWideOut + (kWideMaxTaps >> lg) + 2) | 1;
+    const size_t smem = (size_t)(kWideMaxTaps + 16) * sizeof(float) + (size_t)D * qs * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tail_stage0_wide_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    dim3 grid((unsigned)std::max(1, ceil_div(max_out, kWideOut)), (unsigned)total_vfos);
+    tail_stage0_wide_kernel<D><<<grid, kWideThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+bool tail_stage0_wide_supported(int T, int D) { return T <= kWideMaxTaps && (D == 2 || D == 4 || D == 8 || D == 16); }
+
+cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStream_t st) {
+    if (total_vfos <= 0) return cudaSuccess;
+    for (int D : { 2, 4, 8, 16 }) {
+        int max_out = 0;
+        bool any = false;
+        for (int i = 0; i < a.ngroups; i++)
+            if (a.g[i].s_begin == 1 && a.g[i].nstages > 0 && a.g[i].st[0].D == D) { any = true; max_out = std::max(max_out, a.g[i].st[0].n_out); }
+        if (!any) continue;
+        cudaError_t e = D == 2 ? launch_wide_t<2>(a, total_vfos, max_out, st) : D == 4 ? launch_wide_t<4>(a, total_vfos, max_out, st)
+                      : D == 8 ? launch_wide_t<8>(a, total_vfos, max_out, st) : launch_wide_t<16>(a, total_vfos, max_out, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {

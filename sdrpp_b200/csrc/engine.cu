@@ -874,6 +874,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         tail_totals.back() += (int)g.members.size();
         tg.first_vfo = g.first_dev; tg.nvfo = (int)g.members.size();
         tg.nstages = (int)p.tail.size();
+        // a leading decimating FIR still sees 1/D of the input rate per VFO: it gets its own wide launch
+        tg.s_begin = (!p.tail.empty() && p.tail[0].type == TAIL_DECFIR && tail_stage0_wide_supported(p.tail[0].T, p.tail[0].D)) ? 1 : 0;
         for (size_t s = 0; s < p.tail.size(); s++) {
             const TailPlanStage& ps = p.tail[s];
             TailStage& ts = tg.st[s];
@@ -917,6 +919,9 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         FE_TRY(fe, cudaStreamWaitEvent(stl, fe->ev_s1, 0));
     }
     for (size_t i = 0; i < tails.size(); i++) {
+        bool wide = false;
+        for (int k = 0; k < tails[i].ngroups; k++) wide = wide || tails[i].g[k].s_begin == 1;
+        if (wide && tail_totals[i] > 0) { FE_TRY(fe, launch_tail_stage0_wide(tails[i], tail_totals[i], stl)); fe->launches++; }
         FE_TRY(fe, launch_tail(tails[i], tail_totals[i], stl));
         if (tail_totals[i] > 0) fe->launches++;
     }

@@ -155,6 +155,7 @@ constexpr int kTailMaxGroups = 6;
 struct TailGroup {
     int first_vfo, nvfo;
     int nstages;
+    int s_begin;         // first stage the tail kernel runs: 1 when stage 0 ran in tail_stage0_wide_kernel
     TailStage st[kTailMaxStages];
     uint32_t final_off;  // slab offset of the final output data area (one sample of history before it)
     uint32_t carry0_off; // data-area offset of the OTHER stage-1 region: receives the history carry of stage 0
@@ -172,6 +173,9 @@ struct TailArgs {
     float* arena_demod;
 };
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st);
+// stage 0 of the groups with s_begin == 1 on a wide grid (a decimating FIR); launch before launch_tail
+cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStream_t st);
+bool tail_stage0_wide_supported(int T, int D);
 
 // Post-detector stages of the three demodulators: FM low-pass (dsp/demod/fm.h:86-103), AM
 // [carrier AGC] -> magnitude -> DC block -> [audio AGC] -> low-pass (dsp/demod/am.h:114-146), SSB AGC
