@@ -419,7 +419,12 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     S1T_DECL;
 #ifdef SDRPP_S1T_TRACE
     const long long tk0_ = clock64();
-    if (tid == 0 && blockIdx.x < 256) { for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0; g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A; }
+    if (tid == 0 && blockIdx.x < 256) {
+        for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0;
+        g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A;
+        long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
+        g_s1t_trace[blockIdx.x][11] = gt_;
+    }
     __syncthreads();
 #endif
     if (tid == 0) {
@@ -598,7 +603,11 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     tc_fence_before();
     __syncthreads();
 #ifdef SDRPP_S1T_TRACE
-    if (tid == 0) { S1T_ACC(1, tk0_); S1T_FLUSH(1); }
+    if (tid == 0) {
+        S1T_ACC(1, tk0_); S1T_FLUSH(1);
+        long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
+        if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][0] = gt_;
+    }
 #endif
     if (warp == 1) {
         tc_fence_after();

@@ -25,6 +25,12 @@ buf = np.zeros((256, 16), dtype=np.int64)
 L.sdrpp_cuda_debug_s1t_trace.argtypes = [C.c_void_p, C.c_int]
 assert L.sdrpp_cuda_debug_s1t_trace(buf.ctypes.data, 256) == 0
 t = buf[buf[:, 12] > 0]
+print(f"kernel span (globaltimer, first CTA start -> last CTA end): {(t[:, 0].max() - t[:, 11].min()) / 1e3:.1f} us; "
+      f"CTA starts spread over {(t[:, 11].max() - t[:, 11].min()) / 1e3:.1f} us; CTA ends spread over {(t[:, 0].max() - t[:, 0].min()) / 1e3:.1f} us")
+fe.set_profiling(True)
+for i in range(4):
+    fe.submit(cuda.FMT_CF32, blocks[i % 4]); fe.wait()
+print("family brackets (ms): ingest, spectrum, stage1, tail =", fe.kernel_ms())
 names = {1: "kernel total", 2: "mma: wait tmem empty", 3: "mma: wait smem full", 4: "mma: issue hi chunks (16 MMA)", 8: "mma: issue lo chunks (8 MMA)", 5: "epi: wait tmem full", 6: "epi: load+sum phase",
          7: "epi: bar.sync", 9: "epi: tile total (after wait)", 10: "producer: wait smem empty", 14: "start -> B image landed", 15: "start -> first accumulator ready"}
 for A in sorted(set(t[:, 13])):
