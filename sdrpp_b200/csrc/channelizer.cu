@@ -574,8 +574,9 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         }
         // Stage 0 reads the double-buffered stage-1 region, so its history goes to the OTHER region (always, even
         // for an empty block); later stages shift in place.
-        if (s == 0 || st.n_in > 0) {
-            float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : buf;
+        const bool other = s == 0 || (s == 1 && g.z2); // this stage's input region alternates block by block
+        if (other || st.n_in > 0) {
+            float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : (s == 1 && g.z2) ? (slab + g.carry1_off - hist) : buf;
             float2 keep[8];
             int n = 0;
             for (int i = tid; i < hist && n < 8; i += kTailThreads, n++) keep[n] = buf[st.n_in + i];

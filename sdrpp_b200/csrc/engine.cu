@@ -69,6 +69,10 @@ struct VfoPlan {
     int tc_escale = 0;
     std::vector<TailPlanStage> tail;
     uint32_t s1_off[2] = { 0, 0 }; // the two stage-1 output regions (data areas)
+    // the first tail stage runs apart from the tail kernel (wide kernel, or fused into the tensor-core stage 1 on the
+    // stage-1 stream): its output = input of the second tail stage is double-buffered too, like the stage-1 regions
+    bool z2 = false;
+    uint32_t z_off[2] = { 0, 0 };
     uint32_t final_off = 0;
     int cap_final = 0;
     size_t slab_elems = 0;
@@ -158,6 +162,14 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
     } else {
         p.final_off = off + 2;
         p.slab_elems = (size_t)p.final_off + (size_t)((cap + 1) & ~1LL);
+    }
+    if (p.tail.size() >= 2 && p.tail[0].type == TAIL_DECFIR && p.tail[1].type == TAIL_DECFIR &&
+        tail_stage0_wide_supported(p.tail[0].T, p.tail[0].D)) {
+        const uint32_t hc = (uint32_t)((p.tail[1].T - 1 + 1) & ~1);
+        p.z2 = true;
+        p.z_off[0] = p.tail[1].in_off;
+        p.z_off[1] = (uint32_t)((p.slab_elems + 1) & ~(size_t)1) + hc;
+        p.slab_elems = (size_t)p.z_off[1] + (size_t)((p.tail[1].cap_in + 1) & ~1);
     }
     if (p.s1_fir && s1t_supported(p.s1_T, p.s1_D)) {
         if (dev_alloc(&p.d_s1_taps, p.s1_taps.size(), false) != cudaSuccess ||
@@ -880,7 +892,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             const TailPlanStage& ps = p.tail[s];
             TailStage& ts = tg.st[s];
             ts.type = ps.type; ts.T = ps.T; ts.D = ps.D; ts.interp = ps.interp; ts.taps = ps.d_taps;
-            ts.in_off = (s == 0) ? p.s1_off[par] : ps.in_off;
+            ts.in_off = (s == 0) ? p.s1_off[par] : (s == 1 && p.z2) ? p.z_off[par] : ps.in_off;
             ts.n_in = nprev; ts.offset = g.st.st_offset[s]; ts.phase = g.st.st_phase[s];
             int nout = 0;
             if (ps.type == TAIL_DECFIR) {
@@ -902,6 +914,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         tg.final_off = p.tail.empty() ? p.s1_off[par] : p.final_off;
         tg.carry0_off = p.s1_off[par ^ 1];
+        tg.z2 = (p.z2 && tg.s_begin == 1) ? 1 : 0;
+        tg.carry1_off = p.z_off[par ^ 1];
         tg.n_final = nprev; tg.demod = g.demod;
         tg.inv_dev = (float)(1.0 / (2.0 * kPi * ((p.bw / 2.0) / p.outSR))); // quadrature.h:21-28 with dev = bw/2 (fm.h:31)
         tg.abs_out = g.st.abs_out;

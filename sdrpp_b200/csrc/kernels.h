@@ -158,6 +158,8 @@ struct TailGroup {
     int s_begin;         // first stage the tail kernel runs: 1 when stage 0 ran in tail_stage0_wide_kernel
     TailStage st[kTailMaxStages];
     uint32_t final_off;  // slab offset of the final output data area (one sample of history before it)
+    int z2;              // stage 1 reads a double-buffered region too: its history goes to carry1_off's region
+    uint32_t carry1_off; // data-area offset of the OTHER input region of stage 1
     uint32_t carry0_off; // data-area offset of the OTHER stage-1 region: receives the history carry of stage 0
                          // (or of the final output when there is no tail stage) for the next block
     int n_final;         // output samples this block
