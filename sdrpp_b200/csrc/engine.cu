@@ -232,6 +232,7 @@ struct Group {
     uint8_t* d_B = nullptr; size_t b_cap = 0;
     int tc_shift = -1, tc_A = 0;
     bool tc_dirty = true;
+    bool fused_now = false, was_fused = false; // first tail stage fused into the tensor-core stage 1 (this / previous block)
 };
 
 struct ResultSet {
@@ -315,6 +316,7 @@ struct sdrpp_cuda_frontend {
 
     // tensor-core stage 1: fp16 hi/lo planes of the ring per first-stage decimation (index D / 64: 32 -> 0, 64 -> 1)
     int s1_mode = 0;        // 0: tensor cores where the plan allows, 1: FP32 FMA kernel only
+    bool s1_fuse = true;    // tensor-core stage 1 also runs the second decimating FIR (SDRPP_S1_FUSE=0 turns it off)
     int num_sms = 148;
     S1TPlanes tc_planes[2] = {};
     long long s1t_launches = 0;
@@ -800,6 +802,9 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         if (tc_args[pi].ngroups == 0) return SDRPP_OK;
         FE_TRY(fe, launch_s1t(tc_args[pi], fe->num_sms, st));
         fe->launches++; fe->s1t_launches++;
+        bool any_fused = false;
+        for (int i = 0; i < tc_args[pi].ngroups; i++) any_fused = any_fused || tc_args[pi].g[i].fuse;
+        if (any_fused) { FE_TRY(fe, launch_s1t_boundary(tc_args[pi], st)); fe->launches++; }
         tc_args[pi].ngroups = 0;
         return SDRPP_OK;
     };
@@ -815,6 +820,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         const VfoPlan& p = *g.plan;
         cudaStream_t s1s = (fork && (s1_launch & 1)) ? fe->st_s1b : st;
         Stage1Args a{};
+        g.fused_now = false;
         a.ring = ring;
         a.nvfo = (int)g.members.size();
         a.vfos = fe->d_vfos + g.first_dev;
@@ -856,6 +862,14 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 tg.n_ttiles = (int)((tg.row_first - tg.row0 + nprev + 119) / 120);
                 tg.out_off = a.out_off;
                 tg.b_scale_inv = (float)std::ldexp(1.0, -p.tc_escale);
+                if (p.z2 && fe->s1_fuse && s1t_fuse_supported(p.tail[0].T, p.tail[0].D)) {
+                    // the second decimating FIR rides in the epilogue: its decimation phase is the tail's stage-0 state
+                    tg.fuse = 1; tg.T2 = p.tail[0].T; tg.D2 = p.tail[0].D; tg.off2 = g.st.st_offset[0];
+                    tg.taps2 = p.tail[0].d_taps; tg.z_off = p.z_off[par]; tg.carry0_off = p.s1_off[par ^ 1];
+                    g.fused_now = true;
+                    // the history pad this block reads was written by the previous block's wide kernel on the tail stream
+                    if (!g.was_fused && !prof && fe->ev_tail_valid[par ^ 1]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par ^ 1], 0));
+                }
                 goto stage1_done;
             }
             // keep the window start even (16-byte aligned in the ring): if it is odd, start one sample earlier
@@ -875,6 +889,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         if (nprev > 0) { fe->launches++; s1_launch++; }
     stage1_done:
+        g.was_fused = g.fused_now;
 
         if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
             TailArgs t{};
@@ -915,6 +930,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         tg.final_off = p.tail.empty() ? p.s1_off[par] : p.final_off;
         tg.carry0_off = p.s1_off[par ^ 1];
         tg.z2 = (p.z2 && tg.s_begin == 1) ? 1 : 0;
+        tg.fused0 = g.fused_now ? 1 : 0;
         tg.carry1_off = p.z_off[par ^ 1];
         tg.n_final = nprev; tg.demod = g.demod;
         tg.inv_dev = (float)(1.0 / (2.0 * kPi * ((p.bw / 2.0) / p.outSR))); // quadrature.h:21-28 with dev = bw/2 (fm.h:31)
@@ -1270,6 +1286,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, fe->device) == cudaSuccess && sms > 0) fe->num_sms = sms;
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
+        const char* f = getenv("SDRPP_S1_FUSE");
+        fe->s1_fuse = !(f && !strcmp(f, "0"));
     }
     // ring: history for the longest filter + a whole spectrum frame + one block, rounded up
     {
