@@ -128,10 +128,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 #ifdef SDRPP_S1T_TRACE
 // Debug build only (-DSDRPP_S1T_TRACE): per-CTA cycle counters of the three roles (tools/s1t_trace.py)
-__device__ long long g_s1t_trace[256][16];
+__device__ long long g_s1t_trace[256][24];
 #define S1T_T0(var) const long long var = clock64()
 #define S1T_ACC(slot, var) do { s1t_acc_[slot] += clock64() - (var); } while (0)
-#define S1T_DECL long long s1t_acc_[16] = { 0 }
+#define S1T_DECL long long s1t_acc_[24] = { 0 }
 #define S1T_ARG , s1t_acc_
 #define S1T_FLUSH(slot) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = s1t_acc_[slot]; } while (0)
 #define S1T_SET(slot, val) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = (val); } while (0)
@@ -153,6 +153,7 @@ constexpr int kEpiWarps = 16;       // 4 per TMEM lane quadrant, each with kNV/4
 constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
 constexpr int kNVW = kNV / (kEpiWarps / 4); // VFOs per epilogue warp
 constexpr int kYRing = 176;         // fused second FIR: ring of y per VFO (120 new per tile + >= 56 of history)
+constexpr int kYPerVfo = kYRing + 64; // each of the D2 planes is extended by 8 mirrored positions: windows read linearly
 constexpr int kEpiBatch = 2;         // VFOs per TMEM load batch in the epilogue
 constexpr int kXchFloats = 2 /*buffers*/ * 4 /*quadrants*/ * 7 /*lanes*/ * kNV * 2;
 
@@ -369,6 +370,16 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
     const int64_t m = R - G.row_first;
     const bool out_row = row < kOutPerTile && m >= 0 && m < (int64_t)G.M;
     const bool take = q < 3 && lane >= 25;
+    // ring position of this row in the fused second FIR's y buffer: transposed by D2 (plane = position mod D2), the first
+    // 8 positions of a plane mirrored behind its end
+    int ypos = 0, ymirror = 0;
+    if (G.fuse) {
+        const uint32_t P = (kt * (uint32_t)kOutPerTile + (uint32_t)row) % (uint32_t)kYRing;
+        const int lg2 = 31 - __clz(G.D2), Q = kYRing >> lg2;
+        const int qq = (int)(P >> lg2);
+        ypos = (int)(P & (uint32_t)(G.D2 - 1)) * (Q + 8) + qq;
+        ymirror = qq < 8 ? Q : 0;
+    }
     const float2* xr = reinterpret_cast<const float2*>(xch) + ((hf * 4 + q + 1) * 7) * NVH; // next quadrant's hand-over
 #pragma unroll
     for (int j = 0; j < NVH; j++) {
@@ -383,9 +394,9 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
         if (out_row && v < G.nvfo) G.vfos[v].slab[G.out_off + (uint32_t)m] = yv;
         if (G.fuse && row < kOutPerTile) {
             // ring position of this row, stored transposed by D2 (plane = position mod D2) for the z phase
-            const uint32_t P = (kt * (uint32_t)kOutPerTile + (uint32_t)row) % (uint32_t)kYRing;
-            const int lg2 = 31 - __clz(G.D2);
-            yb[(hf * NVH + j) * kYRing + (P & (uint32_t)(G.D2 - 1)) * (kYRing >> lg2) + (P >> lg2)] = yv;
+            float2* dst = yb + (hf * NVH + j) * kYPerVfo + ypos;
+            dst[0] = yv;
+            if (ymirror) dst[ymirror] = yv;
         }
     }
 }
@@ -409,12 +420,14 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     const int nch = a.nchunks;
     const uint32_t b_plane = (uint32_t)NKH * (uint32_t)N * 128u;   // bytes of one B plane (hi or lo)
 
-    uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smB = base;                                  // [hi|lo][kh][N][128]
+    // the dynamic shared memory base is 1024-byte aligned (SWIZZLE_128B atoms); pointers derived from smem_raw keep
+    // the shared address space, so the epilogue's accesses compile to LDS/STS with 32-bit addressing
+    if ((smem_addr(smem_raw) & 1023u) != 0u) __trap();
+    uint8_t* smB = smem_raw;                              // [hi|lo][kh][N][128]
     uint8_t* smA = smB + 2 * b_plane;                     // nch chunks of 16 KB (multiple of 1024: N % 8 == 0)
     float* xch = reinterpret_cast<float*>(smA + (size_t)nch * kChunkBytes);
-    float2* yb = reinterpret_cast<float2*>(xch + kXchFloats);          // [kNV][kYRing] (fused second FIR)
-    float* tp2 = reinterpret_cast<float*>(yb + kNV * kYRing);          // [D2][8] taps of the second FIR, by tap index mod D2
+    float2* yb = reinterpret_cast<float2*>(xch + kXchFloats);          // [kNV][kYPerVfo] (fused second FIR)
+    float* tp2 = reinterpret_cast<float*>(yb + kNV * kYPerVfo);          // [D2][8] taps of the second FIR, by tap index mod D2
     uint64_t* bars = reinterpret_cast<uint64_t*>(tp2 + 64);
     uint64_t* full = bars;                 // [kMaxChunks]
     uint64_t* empty = bars + kMaxChunks;   // [kMaxChunks]
@@ -428,7 +441,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #ifdef SDRPP_S1T_TRACE
     const long long tk0_ = clock64();
     if (tid == 0 && blockIdx.x < 256) {
-        for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0;
+        for (int i = 0; i < 24; i++) g_s1t_trace[blockIdx.x][i] = 0;
         g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A;
         long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
         g_s1t_trace[blockIdx.x][11] = gt_;
@@ -572,7 +585,11 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             const int v = vt * kNV + hf * NVH + j;
             stp[j] = v < G.nvfo ? phasor64((uint64_t)(kOutPerTile * a.pl.D) * G.vfos[v].dphi) : make_float2(1.0f, 0.0f);
         }
+        float2* zout = nullptr; // z[0] of this warp's VFO (warp = VFO in the second-FIR phase)
         if (G.fuse) {
+            if (vt * kNV + (warp - 2) < G.nvfo) zout = G.vfos[vt * kNV + (warp - 2)].slab + G.z_off;
+            // slots a window may touch beyond its newest sample meet zero taps: they have to hold finite values
+            for (int i = tid - 64; i < kNV * kYPerVfo; i += 32 * kEpiWarps) yb[i] = make_float2(0.0f, 0.0f);
             const int e = tid - 64; // tp2[kappa * 8 + t] = taps2[kappa + D2 * t]; visible after the first tile's barriers
             if (e < 64) { const int kk = (e >> 3) + G.D2 * (e & 7); tp2[e] = ((e >> 3) < G.D2 && kk < G.T2) ? __ldg(G.taps2 + kk) : 0.0f; }
         }
@@ -606,15 +623,23 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                 // Second decimating FIR on the y values of this CTA's tiles (decimating_fir.h:45-68): warp = VFO of the
                 // tile, lane = output. Only windows that lie inside this CTA's range of tiles; the rest (block start, range
                 // boundaries) is s1t_boundary_kernel's. The ring keeps the last 56 y of the previous tile.
+#ifdef SDRPP_S1T_TRACE
+                const long long tz0_ = clock64();
+#endif
                 asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
-                const int vl = warp - 2, v = vt * kNV + vl;
-                const int D2 = G.D2, T2 = G.T2, lg2 = 31 - __clz(D2), Q = kYRing >> lg2;
+#ifdef SDRPP_S1T_TRACE
+                if (tr_) { S1T_ACC(16, tz0_); }
+                const long long tz1_ = clock64();
+#endif
+                const int vl = warp - 2;
+                const int D2 = G.D2, T2 = G.T2, lg2 = 31 - __clz(D2), Q = kYRing >> lg2, QS = Q + 8;
+                const int ntm = (T2 + D2 - 1) >> lg2;     // taps per class k mod D2, at most (zero taps pad the classes)
                 const int mT = (int)(row_t - G.row_first);
                 const int mLo = max(0, (int)(G.row0 + (int64_t)kOutPerTile * tt0 - G.row_first));
                 const int mHi = min(G.M, mT + kOutPerTile);
                 const int mmin = max(mT, mLo + T2 - 1);
                 const int o_first = mmin <= G.off2 ? 0 : (mmin - G.off2 + D2 - 1) >> lg2;
-                const float2* ybv = yb + vl * kYRing;
+                const float2* ybv = yb + vl * kYPerVfo;
                 // two lanes per output (lane and lane + 16), each with half of the tap classes k mod D2
                 const int half = lane >> 4, l16 = lane & 15, kap0 = half * (D2 >> 1), kap1 = kap0 + (D2 >> 1);
                 for (int ob = o_first; ob * D2 + G.off2 < mHi; ob += 16) {
@@ -626,24 +651,23 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                     for (int kap = kap0; kap < kap1; kap++) {
                         uint32_t Pk = P0 + (uint32_t)kap;
                         if (Pk >= (uint32_t)kYRing) Pk -= (uint32_t)kYRing;
-                        const float2* pb = ybv + (Pk & (uint32_t)(D2 - 1)) * Q;
-                        const int qq = (int)(Pk >> lg2);
+                        const float2* pb = ybv + (Pk & (uint32_t)(D2 - 1)) * QS + (Pk >> lg2);
                         const float* tb = tp2 + kap * 8;
-                        const int nt = (T2 - kap + D2 - 1) >> lg2;
 #pragma unroll
                         for (int t = 0; t < 8; t++) {
-                            if (t < nt) {
-                                int idx = qq + t;
-                                if (idx >= Q) idx -= Q;
+                            if (t < ntm) { // warp-uniform
                                 const float h = tb[t];
-                                acc = __ffma2_rn(make_float2(h, h), pb[idx], acc);
+                                acc = __ffma2_rn(make_float2(h, h), pb[t], acc);
                             }
                         }
                     }
                     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
                     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-                    if (valid && half == 0 && v < G.nvfo) G.vfos[v].slab[G.z_off + (uint32_t)o] = acc;
+                    if (valid && half == 0 && zout) zout[o] = acc;
                 }
+#ifdef SDRPP_S1T_TRACE
+                if (tr_) { S1T_ACC(17, tz1_); }
+#endif
             }
 #ifdef SDRPP_S1T_TRACE
             if (tr_) { S1T_ACC(9, tl_); }
@@ -653,7 +677,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #ifdef SDRPP_S1T_TRACE
     if (warp == 0) { S1T_FLUSH(10); }
     if (warp == 1) { S1T_FLUSH(2); S1T_FLUSH(3); S1T_FLUSH(4); S1T_FLUSH(8); S1T_FLUSH(14); }
-    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); }
+    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); S1T_FLUSH(16); S1T_FLUSH(17); }
 #endif
     tc_fence_before();
     __syncthreads();
@@ -672,7 +696,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 
 static size_t s1t_smem_bytes(int NKH, int A, int nchunks) {
     return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) +
-           (size_t)kNV * kYRing * sizeof(float2) + 64 * sizeof(float) + 256;
+           (size_t)kNV * kYPerVfo * sizeof(float2) + 64 * sizeof(float) + 256;
 }
 
 // Fills in cta_begin / cta_per_vtile (time tiles of a VFO tile are split between CTAs so that every SM gets
@@ -793,6 +817,6 @@ cudaError_t launch_s1t_boundary(const S1TArgs& a, cudaStream_t st) {
 #ifdef SDRPP_S1T_TRACE
 extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_s1t_trace(long long* out, int rows) {
     if (rows > 256) rows = 256;
-    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 16 * (size_t)rows);
+    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 24 * (size_t)rows);
 }
 #endif
