@@ -574,9 +574,8 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         }
         // Stage 0 reads the double-buffered stage-1 region, so its history goes to the OTHER region (always, even
         // for an empty block); later stages shift in place.
-        const bool other = s == 0 || (s == 1 && g.z2); // this stage's input region alternates block by block
-        if (other || st.n_in > 0) {
-            float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : (s == 1 && g.z2) ? (slab + g.carry1_off - hist) : buf;
+        if (s == 0 || st.n_in > 0) {
+            float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : buf;
             float2 keep[8];
             int n = 0;
             for (int i = tid; i < hist && n < 8; i += kTailThreads, n++) keep[n] = buf[st.n_in + i];
@@ -640,7 +639,7 @@ tail_stage0_wide_kernel(const __grid_constant__ TailArgs a) {
     int vi = blockIdx.y, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
     const TailGroup& g = a.g[gi];
-    if (g.s_begin == 0 || g.fused0 || g.nstages == 0 || g.st[0].D != D) return; // not this instantiation's (or the tail kernel's) stage
+    if (g.s_begin == 0 || g.nstages == 0 || g.st[0].D != D) return; // not this instantiation's (or the tail kernel's) stage
     const TailStage& st = g.st[0];
     float2* slab = a.vfos[g.first_vfo + vi].slab;
     constexpr int lg = D == 2 ? 1 : D == 4 ? 2 : D == 8 ? 3 : 4;
@@ -710,7 +709,7 @@ cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStrea
         int max_out = 0;
         bool any = false;
         for (int i = 0; i < a.ngroups; i++)
-            if (a.g[i].s_begin == 1 && !a.g[i].fused0 && a.g[i].nstages > 0 && a.g[i].st[0].D == D) { any = true; max_out = std::max(max_out, a.g[i].st[0].n_out); }
+            if (a.g[i].s_begin == 1 && a.g[i].nstages > 0 && a.g[i].st[0].D == D) { any = true; max_out = std::max(max_out, a.g[i].st[0].n_out); }
         if (!any) continue;
         cudaError_t e = D == 2 ? launch_wide_t<2>(a, total_vfos, max_out, st) : D == 4 ? launch_wide_t<4>(a, total_vfos, max_out, st)
                       : D == 8 ? launch_wide_t<8>(a, total_vfos, max_out, st) : launch_wide_t<16>(a, total_vfos, max_out, st);

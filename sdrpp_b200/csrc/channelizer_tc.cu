@@ -128,10 +128,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 #ifdef SDRPP_S1T_TRACE
 // Debug build only (-DSDRPP_S1T_TRACE): per-CTA cycle counters of the three roles (tools/s1t_trace.py)
-__device__ long long g_s1t_trace[256][24];
+__device__ long long g_s1t_trace[256][16];
 #define S1T_T0(var) const long long var = clock64()
 #define S1T_ACC(slot, var) do { s1t_acc_[slot] += clock64() - (var); } while (0)
-#define S1T_DECL long long s1t_acc_[24] = { 0 }
+#define S1T_DECL long long s1t_acc_[16] = { 0 }
 #define S1T_ARG , s1t_acc_
 #define S1T_FLUSH(slot) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = s1t_acc_[slot]; } while (0)
 #define S1T_SET(slot, val) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = (val); } while (0)
@@ -152,8 +152,6 @@ constexpr int kMaxChunks = 8;
 constexpr int kEpiWarps = 16;       // 4 per TMEM lane quadrant, each with kNV/4 VFOs of the tile
 constexpr int kThreads = 64 + 32 * kEpiWarps; // warp 0 producer, warp 1 MMA issuer, warps 2.. epilogue
 constexpr int kNVW = kNV / (kEpiWarps / 4); // VFOs per epilogue warp
-constexpr int kYRing = 176;         // fused second FIR: ring of y per VFO (120 new per tile + >= 56 of history)
-constexpr int kYPerVfo = kYRing + 64; // each of the D2 planes is extended by 8 mirrored positions: windows read linearly
 constexpr int kEpiBatch = 2;         // VFOs per TMEM load batch in the epilogue
 constexpr int kXchFloats = 2 /*buffers*/ * 4 /*quadrants*/ * 7 /*lanes*/ * kNV * 2;
 
@@ -308,7 +306,7 @@ cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, cons
 // ---------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S1TPlanes& pl, uint32_t tmem_acc, int q, int hf, int lane,
-                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur, float2* yb, uint32_t kt
+                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur
 #ifdef SDRPP_S1T_TRACE
                                                   , long long* s1t_acc_
 #endif
@@ -370,16 +368,6 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
     const int64_t m = R - G.row_first;
     const bool out_row = row < kOutPerTile && m >= 0 && m < (int64_t)G.M;
     const bool take = q < 3 && lane >= 25;
-    // ring position of this row in the fused second FIR's y buffer: transposed by D2 (plane = position mod D2), the first
-    // 8 positions of a plane mirrored behind its end
-    int ypos = 0, ymirror = 0;
-    if (G.fuse) {
-        const uint32_t P = (kt * (uint32_t)kOutPerTile + (uint32_t)row) % (uint32_t)kYRing;
-        const int lg2 = 31 - __clz(G.D2), Q = kYRing >> lg2;
-        const int qq = (int)(P >> lg2);
-        ypos = (int)(P & (uint32_t)(G.D2 - 1)) * (Q + 8) + qq;
-        ymirror = qq < 8 ? Q : 0;
-    }
     const float2* xr = reinterpret_cast<const float2*>(xch) + ((hf * 4 + q + 1) * 7) * NVH; // next quadrant's hand-over
 #pragma unroll
     for (int j = 0; j < NVH; j++) {
@@ -389,14 +377,9 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
             t.x += w.x; t.y += w.y;
         }
         const int v = vt * kNV + hf * NVH + j;
-        const float2 e = cur[j];
-        const float2 yv = make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x);
-        if (out_row && v < G.nvfo) G.vfos[v].slab[G.out_off + (uint32_t)m] = yv;
-        if (G.fuse && row < kOutPerTile) {
-            // ring position of this row, stored transposed by D2 (plane = position mod D2) for the z phase
-            float2* dst = yb + (hf * NVH + j) * kYPerVfo + ypos;
-            dst[0] = yv;
-            if (ymirror) dst[ymirror] = yv;
+        if (out_row && v < G.nvfo) {
+            const float2 e = cur[j];
+            G.vfos[v].slab[G.out_off + (uint32_t)m] = make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x);
         }
     }
 }
@@ -426,9 +409,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     uint8_t* smB = smem_raw;                              // [hi|lo][kh][N][128]
     uint8_t* smA = smB + 2 * b_plane;                     // nch chunks of 16 KB (multiple of 1024: N % 8 == 0)
     float* xch = reinterpret_cast<float*>(smA + (size_t)nch * kChunkBytes);
-    float2* yb = reinterpret_cast<float2*>(xch + kXchFloats);          // [kNV][kYPerVfo] (fused second FIR)
-    float* tp2 = reinterpret_cast<float*>(yb + kNV * kYPerVfo);          // [D2][8] taps of the second FIR, by tap index mod D2
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tp2 + 64);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kXchFloats);
     uint64_t* full = bars;                 // [kMaxChunks]
     uint64_t* empty = bars + kMaxChunks;   // [kMaxChunks]
     uint64_t* bfull = bars + 2 * kMaxChunks;
@@ -441,7 +422,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #ifdef SDRPP_S1T_TRACE
     const long long tk0_ = clock64();
     if (tid == 0 && blockIdx.x < 256) {
-        for (int i = 0; i < 24; i++) g_s1t_trace[blockIdx.x][i] = 0;
+        for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0;
         g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A;
         long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
         g_s1t_trace[blockIdx.x][11] = gt_;
@@ -585,14 +566,6 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             const int v = vt * kNV + hf * NVH + j;
             stp[j] = v < G.nvfo ? phasor64((uint64_t)(kOutPerTile * a.pl.D) * G.vfos[v].dphi) : make_float2(1.0f, 0.0f);
         }
-        float2* zout = nullptr; // z[0] of this warp's VFO (warp = VFO in the second-FIR phase)
-        if (G.fuse) {
-            if (vt * kNV + (warp - 2) < G.nvfo) zout = G.vfos[vt * kNV + (warp - 2)].slab + G.z_off;
-            // slots a window may touch beyond its newest sample meet zero taps: they have to hold finite values
-            for (int i = tid - 64; i < kNV * kYPerVfo; i += 32 * kEpiWarps) yb[i] = make_float2(0.0f, 0.0f);
-            const int e = tid - 64; // tp2[kappa * 8 + t] = taps2[kappa + D2 * t]; visible after the first tile's barriers
-            if (e < 64) { const int kk = (e >> 3) + G.D2 * (e & 7); tp2[e] = ((e >> 3) < G.D2 && kk < G.T2) ? __ldg(G.taps2 + kk) : 0.0f; }
-        }
         for (int tt = tt0; tt < tt1; tt++) {
             const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
             if ((k & 7u) == 0u) exact_phase(tt);
@@ -611,64 +584,14 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             float* xb = xch + (k & 1u) * (kXchFloats / 2);
             const uint32_t acc = tmem_base + as * 256u;
             switch (A) {
-            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, yb, k S1T_ARG); break;
-            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, yb, k S1T_ARG); break;
-            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, yb, k S1T_ARG); break;
-            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, yb, k S1T_ARG); break;
-            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, yb, k S1T_ARG); break;
+            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
             }
 #pragma unroll
             for (int j = 0; j < NVH; j++) cur[j] = cmul(cur[j], stp[j]);
-            if (G.fuse) {
-                // Second decimating FIR on the y values of this CTA's tiles (decimating_fir.h:45-68): warp = VFO of the
-                // tile, lane = output. Only windows that lie inside this CTA's range of tiles; the rest (block start, range
-                // boundaries) is s1t_boundary_kernel's. The ring keeps the last 56 y of the previous tile.
-#ifdef SDRPP_S1T_TRACE
-                const long long tz0_ = clock64();
-#endif
-                asm volatile("bar.sync 2, %0;" ::"n"(32 * kEpiWarps) : "memory");
-#ifdef SDRPP_S1T_TRACE
-                if (tr_) { S1T_ACC(16, tz0_); }
-                const long long tz1_ = clock64();
-#endif
-                const int vl = warp - 2;
-                const int D2 = G.D2, T2 = G.T2, lg2 = 31 - __clz(D2), Q = kYRing >> lg2, QS = Q + 8;
-                const int ntm = (T2 + D2 - 1) >> lg2;     // taps per class k mod D2, at most (zero taps pad the classes)
-                const int mT = (int)(row_t - G.row_first);
-                const int mLo = max(0, (int)(G.row0 + (int64_t)kOutPerTile * tt0 - G.row_first));
-                const int mHi = min(G.M, mT + kOutPerTile);
-                const int mmin = max(mT, mLo + T2 - 1);
-                const int o_first = mmin <= G.off2 ? 0 : (mmin - G.off2 + D2 - 1) >> lg2;
-                const float2* ybv = yb + vl * kYPerVfo;
-                // two lanes per output (lane and lane + 16), each with half of the tap classes k mod D2
-                const int half = lane >> 4, l16 = lane & 15, kap0 = half * (D2 >> 1), kap1 = kap0 + (D2 >> 1);
-                for (int ob = o_first; ob * D2 + G.off2 < mHi; ob += 16) {
-                    const int o = ob + l16;
-                    const bool valid = o * D2 + G.off2 < mHi;
-                    const uint32_t re = valid ? (uint32_t)(o * D2 + G.off2 - mT) : (uint32_t)(T2 - 1); // row of the newest sample
-                    const uint32_t P0 = (k * (uint32_t)kOutPerTile + re - (uint32_t)(T2 - 1)) % (uint32_t)kYRing;
-                    float2 acc = make_float2(0.0f, 0.0f);
-                    for (int kap = kap0; kap < kap1; kap++) {
-                        uint32_t Pk = P0 + (uint32_t)kap;
-                        if (Pk >= (uint32_t)kYRing) Pk -= (uint32_t)kYRing;
-                        const float2* pb = ybv + (Pk & (uint32_t)(D2 - 1)) * QS + (Pk >> lg2);
-                        const float* tb = tp2 + kap * 8;
-#pragma unroll
-                        for (int t = 0; t < 8; t++) {
-                            if (t < ntm) { // warp-uniform
-                                const float h = tb[t];
-                                acc = __ffma2_rn(make_float2(h, h), pb[t], acc);
-                            }
-                        }
-                    }
-                    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16);
-                    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
-                    if (valid && half == 0 && zout) zout[o] = acc;
-                }
-#ifdef SDRPP_S1T_TRACE
-                if (tr_) { S1T_ACC(17, tz1_); }
-#endif
-            }
 #ifdef SDRPP_S1T_TRACE
             if (tr_) { S1T_ACC(9, tl_); }
 #endif
@@ -677,7 +600,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #ifdef SDRPP_S1T_TRACE
     if (warp == 0) { S1T_FLUSH(10); }
     if (warp == 1) { S1T_FLUSH(2); S1T_FLUSH(3); S1T_FLUSH(4); S1T_FLUSH(8); S1T_FLUSH(14); }
-    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); S1T_FLUSH(16); S1T_FLUSH(17); }
+    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); }
 #endif
     tc_fence_before();
     __syncthreads();
@@ -695,8 +618,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 }
 
 static size_t s1t_smem_bytes(int NKH, int A, int nchunks) {
-    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) +
-           (size_t)kNV * kYPerVfo * sizeof(float2) + 64 * sizeof(float) + 256;
+    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) + 256;
 }
 
 // Fills in cta_begin / cta_per_vtile (time tiles of a VFO tile are split between CTAs so that every SM gets
@@ -756,67 +678,11 @@ cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// The fused groups' second-FIR outputs that s1t_kernel leaves out: windows that reach before the first y of the CTA
-// range that owns their newest sample (or before the block: history pad in front of the stage-1 region). Same
-// ownership arithmetic as the kernel. Thread = (output, VFO); most threads return at once. Also carries the last
-// T2-1 y of the block to the other stage-1 region (fir.h:80), which is where the next block finds its history.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-s1t_boundary_kernel(const __grid_constant__ S1TArgs a) {
-    const S1TGroupArgs& G = a.g[blockIdx.z];
-    const int v = blockIdx.y;
-    if (!G.fuse || v >= G.nvfo) return;
-    float2* slab = G.vfos[v].slab;
-    const float2* __restrict__ y = slab + G.out_off; // y[m], m >= -(T2-1): the history pad sits in front
-    const int T2 = G.T2, D2 = G.D2;
-    if (blockIdx.x == 0) {
-        float2* dst = slab + G.carry0_off - (T2 - 1);
-        for (int i = threadIdx.x; i < T2 - 1; i += blockDim.x) dst[i] = y[G.M - (T2 - 1) + i];
-    }
-    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t m_end = o * D2 + G.off2;
-    if (m_end >= G.M) return;
-    const int64_t delta = G.row_first - G.row0;
-    const int tt = (int)((m_end + delta) / kOutPerTile);
-    const int ts = (int)(((int64_t)G.cta_per_vtile * (tt + 1) - 1) / G.n_ttiles);
-    const int tt0 = (int)((int64_t)G.n_ttiles * ts / G.cta_per_vtile);
-    const int64_t mLo = max((int64_t)0, (int64_t)kOutPerTile * tt0 - delta);
-    if (m_end - (T2 - 1) >= mLo) return; // computed in the epilogue of s1t_kernel
-    float2 acc = make_float2(0.0f, 0.0f);
-    const float2* __restrict__ w = y + (m_end - (T2 - 1));
-#pragma unroll 8
-    for (int k = 0; k < T2; k++) {
-        const float h = __ldg(G.taps2 + k);
-        acc = __ffma2_rn(make_float2(h, h), w[k], acc);
-    }
-    slab[G.z_off + (uint32_t)o] = acc;
-}
-
-bool s1t_fuse_supported(int T2, int D2) { return (D2 == 4 || D2 == 8) && T2 >= 2 && T2 <= 56 && T2 <= 8 * D2; }
-
-cudaError_t launch_s1t_boundary(const S1TArgs& a, cudaStream_t st) {
-    int max_out = 0, max_v = 0;
-    bool any = false;
-    for (int i = 0; i < a.ngroups; i++) {
-        const S1TGroupArgs& g = a.g[i];
-        if (!g.fuse) continue;
-        any = true;
-        max_out = std::max(max_out, g.M > g.off2 ? (g.M - g.off2 + g.D2 - 1) / g.D2 : 0);
-        max_v = std::max(max_v, g.nvfo);
-    }
-    if (!any) return cudaSuccess;
-    dim3 grid((unsigned)std::max(1, ceil_div(max_out, 128)), (unsigned)max_v, (unsigned)a.ngroups);
-    s1t_boundary_kernel<<<grid, 128, 0, st>>>(a);
-    return cudaGetLastError();
-}
-
 } // namespace sdrpp
 
 #ifdef SDRPP_S1T_TRACE
 extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_s1t_trace(long long* out, int rows) {
     if (rows > 256) rows = 256;
-    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 24 * (size_t)rows);
+    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 16 * (size_t)rows);
 }
 #endif

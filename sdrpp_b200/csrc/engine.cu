@@ -69,10 +69,6 @@ struct VfoPlan {
     int tc_escale = 0;
     std::vector<TailPlanStage> tail;
     uint32_t s1_off[2] = { 0, 0 }; // the two stage-1 output regions (data areas)
-    // the first tail stage runs apart from the tail kernel (wide kernel, or fused into the tensor-core stage 1 on the
-    // stage-1 stream): its output = input of the second tail stage is double-buffered too, like the stage-1 regions
-    bool z2 = false;
-    uint32_t z_off[2] = { 0, 0 };
     uint32_t final_off = 0;
     int cap_final = 0;
     size_t slab_elems = 0;
@@ -163,14 +159,6 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
         p.final_off = off + 2;
         p.slab_elems = (size_t)p.final_off + (size_t)((cap + 1) & ~1LL);
     }
-    if (p.tail.size() >= 2 && p.tail[0].type == TAIL_DECFIR && p.tail[1].type == TAIL_DECFIR &&
-        tail_stage0_wide_supported(p.tail[0].T, p.tail[0].D)) {
-        const uint32_t hc = (uint32_t)((p.tail[1].T - 1 + 1) & ~1);
-        p.z2 = true;
-        p.z_off[0] = p.tail[1].in_off;
-        p.z_off[1] = (uint32_t)((p.slab_elems + 1) & ~(size_t)1) + hc;
-        p.slab_elems = (size_t)p.z_off[1] + (size_t)((p.tail[1].cap_in + 1) & ~1);
-    }
     if (p.s1_fir && s1t_supported(p.s1_T, p.s1_D)) {
         if (dev_alloc(&p.d_s1_taps, p.s1_taps.size(), false) != cudaSuccess ||
             cudaMemcpy(p.d_s1_taps, p.s1_taps.data(), p.s1_taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -232,7 +220,6 @@ struct Group {
     uint8_t* d_B = nullptr; size_t b_cap = 0;
     int tc_shift = -1, tc_A = 0;
     bool tc_dirty = true;
-    bool fused_now = false, was_fused = false; // first tail stage fused into the tensor-core stage 1 (this / previous block)
 };
 
 struct ResultSet {
@@ -316,7 +303,6 @@ struct sdrpp_cuda_frontend {
 
     // tensor-core stage 1: fp16 hi/lo planes of the ring per first-stage decimation (index D / 64: 32 -> 0, 64 -> 1)
     int s1_mode = 0;        // 0: tensor cores where the plan allows, 1: FP32 FMA kernel only
-    bool s1_fuse = true;    // tensor-core stage 1 also runs the second decimating FIR (SDRPP_S1_FUSE=0 turns it off)
     int num_sms = 148;
     S1TPlanes tc_planes[2] = {};
     long long s1t_launches = 0;
@@ -802,9 +788,6 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         if (tc_args[pi].ngroups == 0) return SDRPP_OK;
         FE_TRY(fe, launch_s1t(tc_args[pi], fe->num_sms, st));
         fe->launches++; fe->s1t_launches++;
-        bool any_fused = false;
-        for (int i = 0; i < tc_args[pi].ngroups; i++) any_fused = any_fused || tc_args[pi].g[i].fuse;
-        if (any_fused) { FE_TRY(fe, launch_s1t_boundary(tc_args[pi], st)); fe->launches++; }
         tc_args[pi].ngroups = 0;
         return SDRPP_OK;
     };
@@ -820,7 +803,6 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         const VfoPlan& p = *g.plan;
         cudaStream_t s1s = (fork && (s1_launch & 1)) ? fe->st_s1b : st;
         Stage1Args a{};
-        g.fused_now = false;
         a.ring = ring;
         a.nvfo = (int)g.members.size();
         a.vfos = fe->d_vfos + g.first_dev;
@@ -862,14 +844,6 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 tg.n_ttiles = (int)((tg.row_first - tg.row0 + nprev + 119) / 120);
                 tg.out_off = a.out_off;
                 tg.b_scale_inv = (float)std::ldexp(1.0, -p.tc_escale);
-                if (p.z2 && fe->s1_fuse && s1t_fuse_supported(p.tail[0].T, p.tail[0].D)) {
-                    // the second decimating FIR rides in the epilogue: its decimation phase is the tail's stage-0 state
-                    tg.fuse = 1; tg.T2 = p.tail[0].T; tg.D2 = p.tail[0].D; tg.off2 = g.st.st_offset[0];
-                    tg.taps2 = p.tail[0].d_taps; tg.z_off = p.z_off[par]; tg.carry0_off = p.s1_off[par ^ 1];
-                    g.fused_now = true;
-                    // the history pad this block reads was written by the previous block's wide kernel on the tail stream
-                    if (!g.was_fused && !prof && fe->ev_tail_valid[par ^ 1]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par ^ 1], 0));
-                }
                 goto stage1_done;
             }
             // keep the window start even (16-byte aligned in the ring): if it is odd, start one sample earlier
@@ -889,7 +863,6 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         if (nprev > 0) { fe->launches++; s1_launch++; }
     stage1_done:
-        g.was_fused = g.fused_now;
 
         if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
             TailArgs t{};
@@ -907,7 +880,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             const TailPlanStage& ps = p.tail[s];
             TailStage& ts = tg.st[s];
             ts.type = ps.type; ts.T = ps.T; ts.D = ps.D; ts.interp = ps.interp; ts.taps = ps.d_taps;
-            ts.in_off = (s == 0) ? p.s1_off[par] : (s == 1 && p.z2) ? p.z_off[par] : ps.in_off;
+            ts.in_off = (s == 0) ? p.s1_off[par] : ps.in_off;
             ts.n_in = nprev; ts.offset = g.st.st_offset[s]; ts.phase = g.st.st_phase[s];
             int nout = 0;
             if (ps.type == TAIL_DECFIR) {
@@ -929,9 +902,6 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         tg.final_off = p.tail.empty() ? p.s1_off[par] : p.final_off;
         tg.carry0_off = p.s1_off[par ^ 1];
-        tg.z2 = (p.z2 && tg.s_begin == 1) ? 1 : 0;
-        tg.fused0 = g.fused_now ? 1 : 0;
-        tg.carry1_off = p.z_off[par ^ 1];
         tg.n_final = nprev; tg.demod = g.demod;
         tg.inv_dev = (float)(1.0 / (2.0 * kPi * ((p.bw / 2.0) / p.outSR))); // quadrature.h:21-28 with dev = bw/2 (fm.h:31)
         tg.abs_out = g.st.abs_out;
@@ -1286,8 +1256,6 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, fe->device) == cudaSuccess && sms > 0) fe->num_sms = sms;
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
-        const char* f = getenv("SDRPP_S1_FUSE");
-        fe->s1_fuse = !(f && !strcmp(f, "0"));
     }
     // ring: history for the longest filter + a whole spectrum frame + one block, rounded up
     {

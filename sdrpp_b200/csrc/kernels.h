@@ -121,12 +121,6 @@ struct S1TGroupArgs {
     int64_t row_first;     // absolute row in which the window of output 0 starts
     uint32_t out_off;      // slab offset (in float2) where output 0 goes
     float b_scale_inv;     // 2^-(B block exponent)
-    // second decimating FIR of the cascade fused into the epilogue (fuse != 0): z[o] = sum_k taps2[k] y[o*D2 + off2 - (T2-1) + k]
-    // for the windows that lie inside one CTA's range of time tiles; s1t_boundary_kernel computes the others from the slab
-    int fuse, T2, D2, off2;
-    const float* taps2;
-    uint32_t z_off;        // slab offset (float2) of z[0]
-    uint32_t carry0_off;   // data-area offset of the other stage-1 region (history carry of y)
     int n_vtiles, cta_per_vtile, cta_begin; // set by the launcher
 };
 struct S1TArgs {
@@ -144,9 +138,6 @@ cudaError_t launch_s1t_split(RingRef ring, const S1TPlanes& pl, int64_t abs_begi
 cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift, int A,
                                int escale, cudaStream_t st);
 cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st);
-// after launch_s1t (same args, same stream): the fused groups' outputs whose windows cross a CTA range or the block start
-cudaError_t launch_s1t_boundary(const S1TArgs& a, cudaStream_t st);
-bool s1t_fuse_supported(int T2, int D2);
 
 enum { TAIL_DECFIR = 0, TAIL_POLY = 1, TAIL_FIR = 2 };
 struct TailStage {
@@ -165,11 +156,8 @@ struct TailGroup {
     int first_vfo, nvfo;
     int nstages;
     int s_begin;         // first stage the tail kernel runs: 1 when stage 0 ran in tail_stage0_wide_kernel
-    int fused0;          // stage 0 already ran fused into the tensor-core stage 1 (the wide kernel skips the group)
     TailStage st[kTailMaxStages];
     uint32_t final_off;  // slab offset of the final output data area (one sample of history before it)
-    int z2;              // stage 1 reads a double-buffered region too: its history goes to carry1_off's region
-    uint32_t carry1_off; // data-area offset of the OTHER input region of stage 1
     uint32_t carry0_off; // data-area offset of the OTHER stage-1 region: receives the history carry of stage 0
                          // (or of the final output when there is no tail stage) for the next block
     int n_final;         // output samples this block

@@ -21,7 +21,7 @@ for i in range(6):
     fe.submit(cuda.FMT_CF32, blocks[i % 4])
     fe.wait()
 L = cuda.lib()
-buf = np.zeros((256, 24), dtype=np.int64)
+buf = np.zeros((256, 16), dtype=np.int64)
 L.sdrpp_cuda_debug_s1t_trace.argtypes = [C.c_void_p, C.c_int]
 assert L.sdrpp_cuda_debug_s1t_trace(buf.ctypes.data, 256) == 0
 t = buf[buf[:, 12] > 0]
@@ -32,7 +32,7 @@ for i in range(4):
     fe.submit(cuda.FMT_CF32, blocks[i % 4]); fe.wait()
 print("family brackets (ms): ingest, spectrum, stage1, tail =", fe.kernel_ms())
 names = {1: "kernel total", 2: "mma: wait tmem empty", 3: "mma: wait smem full", 4: "mma: issue hi chunks (16 MMA)", 8: "mma: issue lo chunks (8 MMA)", 5: "epi: wait tmem full", 6: "epi: load+sum phase",
-         7: "epi: bar.sync", 9: "epi: tile total (after wait)", 10: "producer: wait smem empty", 14: "start -> B image landed", 15: "start -> first accumulator ready", 16: "epi: bar.sync before the second FIR", 17: "epi: second FIR phase"}
+         7: "epi: bar.sync", 9: "epi: tile total (after wait)", 10: "producer: wait smem empty", 14: "start -> B image landed", 15: "start -> first accumulator ready"}
 for A in sorted(set(t[:, 13])):
     c = t[t[:, 13] == A]
     print(f"A={A}: {len(c)} CTAs, tiles per CTA {c[:, 12].min()}..{c[:, 12].max()}")
