@@ -306,7 +306,7 @@ cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, cons
 // ---------------------------------------------------------------------------------------------
 template <int A>
 __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S1TPlanes& pl, uint32_t tmem_acc, int q, int hf, int lane,
-                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur
+                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur, float2* const* outp
 #ifdef SDRPP_S1T_TRACE
                                                   , long long* s1t_acc_
 #endif
@@ -376,10 +376,10 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
             const float2 w = xr[(lane - 25) * NVH + j];
             t.x += w.x; t.y += w.y;
         }
-        const int v = vt * kNV + hf * NVH + j;
-        if (out_row && v < G.nvfo) {
+        float2* o = outp[hf * NVH + j];
+        if (out_row && o) {
             const float2 e = cur[j];
-            G.vfos[v].slab[G.out_off + (uint32_t)m] = make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x);
+            o[m] = make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x);
         }
     }
 }
@@ -409,7 +409,8 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     uint8_t* smB = smem_raw;                              // [hi|lo][kh][N][128]
     uint8_t* smA = smB + 2 * b_plane;                     // nch chunks of 16 KB (multiple of 1024: N % 8 == 0)
     float* xch = reinterpret_cast<float*>(smA + (size_t)nch * kChunkBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + kXchFloats);
+    float2** outp = reinterpret_cast<float2**>(xch + kXchFloats);      // [kNV] slab + out_off of the tile's VFOs (null: no such VFO)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(outp + kNV);
     uint64_t* full = bars;                 // [kMaxChunks]
     uint64_t* empty = bars + kMaxChunks;   // [kMaxChunks]
     uint64_t* bfull = bars + 2 * kMaxChunks;
@@ -566,6 +567,10 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             const int v = vt * kNV + hf * NVH + j;
             stp[j] = v < G.nvfo ? phasor64((uint64_t)(kOutPerTile * a.pl.D) * G.vfos[v].dphi) : make_float2(1.0f, 0.0f);
         }
+        if (tid - 64 < kNV) { // visible to the other epilogue warps after the first tile's barrier
+            const int v = vt * kNV + (tid - 64);
+            outp[tid - 64] = v < G.nvfo ? G.vfos[v].slab + G.out_off : nullptr;
+        }
         for (int tt = tt0; tt < tt1; tt++) {
             const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
             if ((k & 7u) == 0u) exact_phase(tt);
@@ -584,11 +589,11 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             float* xb = xch + (k & 1u) * (kXchFloats / 2);
             const uint32_t acc = tmem_base + as * 256u;
             switch (A) {
-            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
-            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
-            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
-            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
-            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur S1T_ARG); break;
+            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
+            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
+            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
+            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
+            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
             }
 #pragma unroll
             for (int j = 0; j < NVH; j++) cur[j] = cmul(cur[j], stp[j]);
@@ -618,7 +623,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 }
 
 static size_t s1t_smem_bytes(int NKH, int A, int nchunks) {
-    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) + 256;
+    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) + kNV * sizeof(void*) + 256;
 }
 
 // Fills in cta_begin / cta_per_vtile (time tiles of a VFO tile are split between CTAs so that every SM gets
