@@ -261,6 +261,9 @@ def run_gpu(args, rank, world, local_rank):
         os.environ.pop("NCCL_DEBUG", None)  # any level >= VERSION makes NCCL print a banner on stdout; rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
+    if world > 1:
+        # the stage-1 kernel is persistent (one CTA per SM): leave a few SMs to the NCCL broadcast of the next block
+        os.environ.setdefault("SDRPP_RESERVE_SMS", "8")
     vf_all = vfo_list()
     # shard the VFO set across ranks, balanced by per-VFO cost (sdrpp_b200/shard.py); no data-path collective
     from sdrpp_b200 import shard

@@ -459,14 +459,13 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             }
             __syncwarp();
             const uint32_t ng = a.pl.group_mask + 1;
-            uint32_t it = 0;
+            uint32_t slot = 0, ph = 0; // ring slot and its phase bit, advanced without divisions
             for (int tt = tt0; tt < tt1; tt++) {
                 const int64_t row_t = G.row0 + (int64_t)kOutPerTile * tt;
                 const uint32_t gs = (uint32_t)((uint64_t)(row_t >> 3) & a.pl.group_mask);
                 const uint32_t n1 = min(16u, ng - gs);   // groups before the ring wraps
 #pragma unroll 1
-                for (int c = 0; c < 2 * NKH; c++, it++) {
-                    const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
+                for (int c = 0; c < 2 * NKH; c++) {
                     S1T_T0(tw_);
                     mbar_wait(empty + slot, ph ^ 1u);
                     S1T_ACC(10, tw_);
@@ -478,6 +477,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                         if (n1 < 16u) bulk_g2s(dst + (size_t)n1 * 1024, plane, (16u - n1) * 1024u, full + slot);
                     }
                     __syncwarp();
+                    if (++slot == (uint32_t)nch) { slot = 0; ph ^= 1u; }
                 }
             }
         }
@@ -491,7 +491,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #endif
             tc_fence_after();
             const uint32_t sB = smem_addr(smB), sA = smem_addr(smA);
-            uint32_t it = 0;
+            uint32_t slot = 0, ph = 0;
             for (int tt = tt0; tt < tt1; tt++) {
                 const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
                 S1T_T0(tw_);
@@ -504,7 +504,6 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                     const uint64_t bh = umma_desc_sw128(sB + (uint32_t)kh * (uint32_t)N * 128u);
                     const uint64_t bl = umma_desc_sw128(sB + b_plane + (uint32_t)kh * (uint32_t)N * 128u);
                     {
-                        const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
                         S1T_T0(tf_);
                         mbar_wait(full + slot, ph);
                         S1T_ACC(3, tf_);
@@ -521,10 +520,9 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                         }
                         __syncwarp();
                         S1T_ACC(4, ti_);
-                        it++;
+                        if (++slot == (uint32_t)nch) { slot = 0; ph ^= 1u; }
                     }
                     {
-                        const uint32_t slot = it % (uint32_t)nch, ph = (it / (uint32_t)nch) & 1u;
                         S1T_T0(tf_);
                         mbar_wait(full + slot, ph);
                         S1T_ACC(3, tf_);
@@ -539,7 +537,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                         }
                         __syncwarp();
                         S1T_ACC(8, ti_);
-                        it++;
+                        if (++slot == (uint32_t)nch) { slot = 0; ph ^= 1u; }
                     }
                 }
             }

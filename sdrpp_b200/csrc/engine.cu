@@ -1254,6 +1254,10 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
     {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, fe->device) == cudaSuccess && sms > 0) fe->num_sms = sms;
+        // SMs left free for other work on the device while the persistent stage-1 kernel runs (a multi-GPU deployment
+        // sets this so that the NCCL broadcast of the next block is not queued behind it)
+        const char* rsv = getenv("SDRPP_RESERVE_SMS");
+        if (rsv) { const int r = atoi(rsv); if (r > 0 && r < fe->num_sms) fe->num_sms -= r; }
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
     }
