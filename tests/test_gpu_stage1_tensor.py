@@ -132,3 +132,81 @@ def test_retune_midstream(gpu):
     for i in range(2):
         err = po.rel_rms(gt[i], gf[i])
         assert err <= 3e-6, f"vfo {i}: {err:.3e}"
+
+
+def _compare_modes(gpu, sr, blocks, script, max_block, tol=3e-6):
+    """script(fe, block_index) -> may add / retune VFOs before the block; returns the list of live VFO ids. Runs the same
+    script in tensor and FP32 mode and compares every VFO's concatenated output."""
+    outs = []
+    for mode in (0, 1):
+        res = {}
+        with gpu.Frontend(sr, max_block=max_block) as fe:
+            fe.set_stage1_mode(mode)
+            state = {}
+            for bi, b in enumerate(blocks):
+                ids = script(fe, bi, state)
+                fe.process(po.FMT_CF32, b)
+                for name, vid in ids.items():
+                    res.setdefault(name, []).append(fe.vfo_output(vid)[0].copy())
+            tl = fe.stage1_tensor_launches
+        outs.append(({k: np.concatenate(v) for k, v in res.items()}, tl))
+    (gt, tlt), (gf, tlf) = outs
+    assert tlt > 0 and tlf == 0
+    assert gt.keys() == gf.keys()
+    x_rms = float(np.sqrt(np.mean(np.abs(np.concatenate(blocks)) ** 2)))
+    for k in gt:
+        assert len(gt[k]) == len(gf[k]), k
+        ref_rms = float(np.sqrt(np.mean(np.abs(gf[k]) ** 2)))
+        d = float(np.sqrt(np.mean(np.abs(gt[k] - gf[k]) ** 2)))
+        assert d <= tol * ref_rms + 1e-7 * x_rms, f"{k}: diff {d:.3e} ref {ref_rms:.3e}"
+
+
+def test_both_plane_sets_at_once(gpu):
+    """First-stage decimations 32 and 64 in the same front end: two sets of fp16 planes, two launches per block."""
+    sr, blk = 15.36e6, 76800
+    x = synth.baseband(blk * 5, sr, 31, carriers=[(1.0e6, "am"), (-2.0e6, "am")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(5)]
+
+    def script(fe, bi, st):
+        if bi == 0:
+            st["a"] = fe.add_vfo(24e3, 12e3, 1.0e6, po.DEMOD_NONE)     # ratio 512: first stage /32
+            st["b"] = fe.add_vfo(12e3, 6e3, -2.0e6, po.DEMOD_NONE)     # ratio 1024: first stage /64
+            assert fe.vfo_info(st["a"])["s1_decim"] == 32 and fe.vfo_info(st["b"])["s1_decim"] == 64
+        return dict(st)
+
+    _compare_modes(gpu, sr, blocks, script, blk)
+
+
+def test_more_groups_than_one_launch_holds(gpu):
+    """Eight plans of the same first stage = eight groups: the tensor kernel is launched twice per block (6 + 2)."""
+    sr, blk = 122.88e6, 614400
+    bws = [6e3, 7e3, 8e3, 9e3, 10e3, 11e3, 12e3, 12.5e3]
+    offs = [float(o) for o in synth.vfo_grid(len(bws), sr)]
+    x = synth.baseband(blk * 3, sr, 32, carriers=[(o, "fm") for o in offs], noise_dbfs=-50.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(3)]
+
+    def script(fe, bi, st):
+        if bi == 0:
+            for i, (bw, o) in enumerate(zip(bws, offs)):
+                st[f"v{i}"] = fe.add_vfo(48e3, bw, o, po.DEMOD_NONE)
+        return dict(st)
+
+    _compare_modes(gpu, sr, blocks, script, blk)
+
+
+def test_vfo_class_added_midstream_moves_the_row_origin(gpu):
+    """A second class of VFOs appears after two blocks: the row origin is chosen again for both classes and the history
+    the next windows reach back into is converted again; the first class must not notice."""
+    sr, blk = 122.88e6, 614400
+    x = synth.baseband(blk * 6, sr, 33, carriers=[(5.0e6, "fm"), (-11.0e6, "am")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(6)]
+
+    def script(fe, bi, st):
+        if bi == 0:
+            st["nfm"] = fe.add_vfo(48e3, 12.5e3, 5.0e6, po.DEMOD_NONE)
+        if bi == 2:
+            for i in range(40):                                        # enough AM VFOs to outweigh the single NFM one
+                st[f"am{i}"] = fe.add_vfo(24e3, 12e3, -11.0e6 + 25e3 * i, po.DEMOD_NONE)
+        return dict(st)
+
+    _compare_modes(gpu, sr, blocks, script, blk)
