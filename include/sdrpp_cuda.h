@@ -101,6 +101,20 @@ SDRPP_API void sdrpp_cuda_design_reshape(double sampleRate, int fftSize, double 
  * ------------------------------------------------------------------------------------------ */
 /* Source conversions (see SDRPP_FMT_*). in: nsamples interleaved I,Q pairs. Bit-exact. */
 SDRPP_API int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf32* out);
+/* SDR++ server wire packets (core/src/dsp/compression/): u16 compression type (0) | u16 PCMType |
+ * f32 scaler | payload. PCMType values: core/src/dsp/compression/pcm_type.h:4-8. */
+enum { SDRPP_PCM_I8 = 0, SDRPP_PCM_I16 = 1, SDRPP_PCM_F32 = 2 };
+/* dsp::compression::SampleStreamDecompressor::process (sample_stream_decompressor.h:13-36), the
+ * client side (source_modules/sdrpp_server_source): packet of nbytes -> cf32. Returns the number of
+ * complex samples written (0 for an unknown sample type, like the reference), < 0 on error.
+ * I8/I16 payloads are divided by 128.0f/scaler resp. 32768.0f/scaler in fp32. Bit-exact. */
+SDRPP_API int sdrpp_cuda_pcm_decompress(const void* packet, int nbytes, sdrpp_cf32* out);
+/* dsp::compression::SampleStreamCompressor::process (sample_stream_compressor.h:26-60), the server
+ * side (core/src/server.cpp): count cf32 samples -> packet (capacity 8 + count*8 bytes is always
+ * enough). scaler = the largest SIGNED scalar of the block, payload = saturated rintf(x*(128|32768)
+ * /scaler). Returns the packet size in bytes, < 0 on error. Bit-exact for finite input whose
+ * maximum is > 0 (NaN input and an all-non-positive block are undefined in the reference too). */
+SDRPP_API int sdrpp_cuda_pcm_compress(int pcm_type, const sdrpp_cf32* in, int count, void* packet);
 /* IQFrontEnd::handler (signal_path/iq_frontend.cpp:230-249): window * frame -> zero-padded forward
  * DFT of size N -> 10*log10|X|^2. frame: nz samples of format fmt; window: nz floats.
  * row: N floats (may be NULL); X: N complex FFT outputs (may be NULL; parity/debug). */
@@ -173,6 +187,11 @@ SDRPP_API int sdrpp_cuda_vfo_info(sdrpp_cuda_frontend* fe, int vfo, int* info);
 SDRPP_API int sdrpp_cuda_frontend_submit(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count);
 /* Same, with `in` already in device memory on this GPU (e.g. the target of an NCCL broadcast). */
 SDRPP_API int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt, const void* dev_in, int count);
+/* Same as _submit for one SDR++ server wire packet (SampleStreamDecompressor::run feeding the
+ * front end, source_modules/sdrpp_server_source): the 8-byte header is read on the host, the payload
+ * is converted on the device inside the ingest kernel. Returns the number of samples submitted
+ * (0 = nothing submitted: unknown sample type or empty payload), < 0 on error. */
+SDRPP_API int sdrpp_cuda_frontend_submit_pcm(sdrpp_cuda_frontend* fe, const void* packet, int nbytes);
 /* Block until the OLDEST block not yet waited for has its results on the host. Up to three blocks may be in flight
  * (submit, submit, submit, wait, submit, wait, ...): with two or more submitted ahead, the host-to-device copy of a
  * block never waits for an earlier block's results to reach the host. */

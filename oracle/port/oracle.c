@@ -99,6 +99,80 @@ API int orc_convert(int fmt, const void* in, int nscalars, float* out) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* 8f rank 3. SDR++ server wire packets: u16 compression type | u16 PCMType | f32 scaler | data */
+/* ------------------------------------------------------------------------------------------ */
+enum { ORC_PCM_I8 = 0, ORC_PCM_I16 = 1, ORC_PCM_F32 = 2 }; /* dsp/compression/pcm_type.h:4-8 */
+
+/* dsp/compression/sample_stream_decompressor.h:13-36 (generic VOLK: (float)x / scalar) */
+API int orc_pcm_decompress(int nbytes, const uint8_t* packet, cf32* out) {
+    uint16_t type;
+    float scaler, div;
+    float* o = (float*)out;
+    int n, i;
+    memcpy(&type, packet + 2, 2);
+    memcpy(&scaler, packet + 4, 4);
+    if (type == ORC_PCM_F32) {
+        memcpy(out, packet + 8, (size_t)(nbytes - 8));
+        return (nbytes - 8) / (int)sizeof(cf32);
+    }
+    if (type == ORC_PCM_I16) {
+        const int16_t* p = (const int16_t*)(packet + 8);
+        n = (nbytes - 8) / 4;
+        div = 32768.0f / scaler;
+        for (i = 0; i < 2 * n; i++) o[i] = (float)p[i] / div;
+        return n;
+    }
+    if (type == ORC_PCM_I8) {
+        const int8_t* p = (const int8_t*)(packet + 8);
+        n = (nbytes - 8) / 2;
+        div = 128.0f / scaler;
+        for (i = 0; i < 2 * n; i++) o[i] = (float)p[i] / div;
+        return n;
+    }
+    return 0;
+}
+
+/* dsp/compression/sample_stream_compressor.h:26-60: scaler = first strict maximum of the SIGNED scalars
+ * (volk_32f_index_max_32u), payload = saturated rintf(x * (128|32768)/scaler) */
+API int orc_pcm_compress(int count, int pcm_type, const cf32* in, uint8_t* packet) {
+    const float* x = (const float*)in;
+    const uint16_t comp = 0, type = (uint16_t)pcm_type;
+    float mx, k, r;
+    int i, n = 2 * count;
+    memcpy(packet, &comp, 2);
+    memcpy(packet + 2, &type, 2);
+    if (pcm_type == ORC_PCM_F32) {
+        mx = 0.0f;
+        memcpy(packet + 4, &mx, 4);
+        memcpy(packet + 8, in, (size_t)count * sizeof(cf32));
+        return 8 + count * (int)sizeof(cf32);
+    }
+    mx = x[0];
+    for (i = 1; i < n; i++) if (x[i] > mx) mx = x[i];
+    memcpy(packet + 4, &mx, 4);
+    if (pcm_type == ORC_PCM_I8) {
+        int8_t* o = (int8_t*)(packet + 8);
+        k = 128.0f / mx;
+        for (i = 0; i < n; i++) {
+            r = x[i] * k;
+            o[i] = r > 127.0f ? (int8_t)127 : r < -128.0f ? (int8_t)-128 : (int8_t)rintf(r);
+        }
+        return 8 + n;
+    }
+    if (pcm_type == ORC_PCM_I16) {
+        int16_t* o = (int16_t*)(packet + 8);
+        k = 32768.0f / mx;
+        for (i = 0; i < n; i++) {
+            r = x[i] * k;
+            if (r > 32767.0f) r = 32767.0f; else if (r < -32768.0f) r = -32768.0f;
+            o[i] = (int16_t)rintf(r);
+        }
+        return 8 + 2 * n;
+    }
+    return count; /* the reference's fall-through for an unknown type */
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* A9. Window design: dsp/window/window.h:38-64, cosine.h:7-16, coefficient headers            */
 /* ------------------------------------------------------------------------------------------ */
 static double orc_cosine(double n, double N, const double* c, int cnt) {

@@ -238,6 +238,19 @@ class _Base:
             raise ValueError("spectrum: bad size")
         return row32, X64, row64
 
+    # SDR++ server wire packets (dsp/compression/sample_stream_{de,}compressor.h)
+    def pcm_decompress(self, packet):
+        packet = np.ascontiguousarray(packet, dtype=np.uint8)
+        out = np.zeros(max(1, (len(packet) - 8) // 2), dtype=np.complex64)
+        n = self._f("pcm_decompress", _i, _i, _vp, _vp)(len(packet), _ptr(packet), _ptr(out))
+        return out[:n].copy()
+
+    def pcm_compress(self, pcm_type, x):
+        x = np.ascontiguousarray(x, dtype=np.complex64)
+        packet = np.zeros(8 + 8 * len(x), dtype=np.uint8)
+        n = self._f("pcm_compress", _i, _i, _i, _vp, _vp)(len(x), int(pcm_type), _ptr(x), _ptr(packet))
+        return packet[:n].copy()
+
 
 def _zoom(fn, view_offset, view_bw, whole_bw, row, out_size, with_idx):
     row = np.ascontiguousarray(row, dtype=np.float32)

@@ -27,6 +27,8 @@
 #include <dsp/demod/fm.h>
 #include <dsp/demod/am.h>
 #include <dsp/demod/ssb.h>
+#include <dsp/compression/sample_stream_compressor.h>
+#include <dsp/compression/sample_stream_decompressor.h>
 
 #include <vector>
 #include <thread>
@@ -384,6 +386,19 @@ API void ref_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandw
                       const float* data, float* out) {
     fft_scaler sc(viewOffset, viewBandwidth, wholeBandwidth, (size_t)fftSize, (size_t)outSize);
     sc.doZoom(data, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SDR++ server wire packets
+// ---------------------------------------------------------------------------------------------
+// dsp::compression::SampleStreamDecompressor::process (dsp/compression/sample_stream_decompressor.h:13-36)
+API int ref_pcm_decompress(int nbytes, const uint8_t* packet, complex_t* out) {
+    dsp::compression::SampleStreamDecompressor d;
+    return d.process(nbytes, packet, out);
+}
+// dsp::compression::SampleStreamCompressor::process (dsp/compression/sample_stream_compressor.h:26-60)
+API int ref_pcm_compress(int count, int pcmType, const complex_t* in, uint8_t* packet) {
+    return dsp::compression::SampleStreamCompressor::process(count, (dsp::compression::PCMType)pcmType, in, packet);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -147,3 +147,26 @@ static inline void volk_16i_s32f_convert_32f(float* out, const int16_t* in, cons
 static inline void volk_8i_s32f_convert_32f(float* out, const int8_t* in, const float scale, unsigned int n) {
     for (unsigned int i = 0; i < n; i++) out[i] = (float)in[i] / scale;
 }
+
+// --- float -> integer conversions (generic VOLK: r = x * scale; saturate; rintf) and index of the
+// --- maximum (first strict maximum), used by dsp/compression/sample_stream_compressor.h -------
+static inline void volk_32f_s32f_convert_8i(int8_t* out, const float* in, const float scale, unsigned int n) {
+    for (unsigned int i = 0; i < n; i++) {
+        const float r = in[i] * scale;
+        out[i] = r > 127.0f ? (int8_t)127 : r < -128.0f ? (int8_t)-128 : (int8_t)rintf(r);
+    }
+}
+static inline void volk_32f_s32f_convert_16i(int16_t* out, const float* in, const float scale, unsigned int n) {
+    for (unsigned int i = 0; i < n; i++) {
+        float r = in[i] * scale;
+        if (r > 32767.0f) r = 32767.0f; else if (r < -32768.0f) r = -32768.0f;
+        out[i] = (int16_t)rintf(r);
+    }
+}
+static inline void volk_32f_index_max_32u(uint32_t* target, const float* src, uint32_t n) {
+    if (n == 0) return;
+    float mx = src[0];
+    uint32_t idx = 0;
+    for (uint32_t i = 1; i < n; i++) if (src[i] > mx) { idx = i; mx = src[i]; }
+    *target = idx;
+}

@@ -39,9 +39,17 @@ __device__ __forceinline__ float cvt_i24_file(int v) { return __fdiv_rn(__fadd_r
 __device__ __forceinline__ float cvt_i32_file(int v) { return (float)__ddiv_rn(__dadd_rn((double)v, 0.5), 2147483647.5); }
 
 // Load one complex sample of input format FMT at sample index i and convert it.
+// FMT 9 / 10 (internal): SDR++ server wire packets, int8 / int16 divided by a per-packet fp32
+// divisor (sample_stream_decompressor.h:23-32; generic VOLK: (float)x / scalar).
 template <int FMT>
-__device__ __forceinline__ float2 load_sample(const void* __restrict__ base, size_t i) {
-    if constexpr (FMT == 0) {
+__device__ __forceinline__ float2 load_sample(const void* __restrict__ base, size_t i, float scale = 1.0f) {
+    if constexpr (FMT == 9) {
+        const char2 v = __ldg(reinterpret_cast<const char2*>(base) + i);
+        return make_float2(__fdiv_rn((float)v.x, scale), __fdiv_rn((float)v.y, scale));
+    } else if constexpr (FMT == 10) {
+        const short2 v = __ldg(reinterpret_cast<const short2*>(base) + i);
+        return make_float2(__fdiv_rn((float)v.x, scale), __fdiv_rn((float)v.y, scale));
+    } else if constexpr (FMT == 0) {
         return __ldg(reinterpret_cast<const float2*>(base) + i);
     } else if constexpr (FMT == 1 || FMT == 2) {
         const uchar2 v = __ldg(reinterpret_cast<const uchar2*>(base) + i);
@@ -68,8 +76,10 @@ __device__ __forceinline__ float2 load_sample(const void* __restrict__ base, siz
 }
 
 __host__ __device__ constexpr int fmt_bytes_per_sample(int fmt) {
-    return fmt == 0 ? 8 : (fmt == 1 || fmt == 2 || fmt == 3) ? 2 : (fmt == 4 || fmt == 5) ? 4 : fmt == 6 ? 6 : fmt == 7 ? 8 : 16;
+    return fmt == 0 ? 8 : (fmt == 1 || fmt == 2 || fmt == 3 || fmt == 9) ? 2 : (fmt == 4 || fmt == 5 || fmt == 10) ? 4 : fmt == 6 ? 6 : fmt == 7 ? 8 : 16;
 }
+
+constexpr int kFmtPcmI8 = 9, kFmtPcmI16 = 10; // internal formats behind sdrpp_cuda_pcm_* (run-time divisor)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);

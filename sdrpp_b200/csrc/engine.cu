@@ -643,7 +643,7 @@ static void advance_decim(int& offset, int D, int count, int* nout) {
     *nout = n;
 }
 
-static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int count, ResultSet& rs) {
+static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int count, ResultSet& rs, float scale = 1.0f) {
     cudaStream_t st = fe->st;
     const bool prof = fe->profiling;
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[0], st));
@@ -655,15 +655,15 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     const bool dc = fe->cfg.dc_blocking != 0;
     int n = count;
     if (fe->fe_stages.empty() && !dc) {
-        FE_TRY(fe, launch_ingest(fmt, d_in, count, ring, wpos, conj, st)); fe->launches++;
+        FE_TRY(fe, launch_ingest(fmt, d_in, count, ring, wpos, conj, st, scale)); fe->launches++;
     } else {
         const RingRef lin_dc{ fe->dc_in, 0xFFFFFFFFu };
         if (fe->fe_stages.empty()) {
-            FE_TRY(fe, launch_ingest(fmt, d_in, count, lin_dc, 0, false, st)); fe->launches++;
+            FE_TRY(fe, launch_ingest(fmt, d_in, count, lin_dc, 0, false, st, scale)); fe->launches++;
         } else {
             const size_t ns = fe->fe_stages.size();
             RingRef first{ fe->fe_buf[0], 0xFFFFFFFFu };
-            FE_TRY(fe, launch_ingest(fmt, d_in, count, first, (uint32_t)(fe->fe_stages[0].ntaps - 1), false, st)); fe->launches++;
+            FE_TRY(fe, launch_ingest(fmt, d_in, count, first, (uint32_t)(fe->fe_stages[0].ntaps - 1), false, st, scale)); fe->launches++;
             for (size_t s = 0; s < ns; s++) {
                 const DecimStage& ds = fe->fe_stages[s];
                 int off = fe->fe_offset[s], nout = 0;
@@ -980,10 +980,10 @@ static int wait_set(sdrpp_cuda_frontend* fe, int idx) {
     return SDRPP_OK;
 }
 
-static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count, bool device_src) {
+static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count, bool device_src, float scale = 1.0f) {
     int rc = fe_check(fe);
     if (rc != SDRPP_OK) return rc;
-    if (fmt < 0 || fmt >= SDRPP_FMT_COUNT) return fail(SDRPP_ERR_ARG, "unknown sample format");
+    if (fmt < 0 || (fmt >= SDRPP_FMT_COUNT && fmt != kFmtPcmI8 && fmt != kFmtPcmI16)) return fail(SDRPP_ERR_ARG, "unknown sample format");
     if (!in || count <= 0 || count > fe->cfg.max_block) return fail(SDRPP_ERR_ARG, "count must be in 1..max_block");
     const int slot = (int)(fe->seq % kSets);
     ResultSet& rs = fe->rs[slot];
@@ -1008,7 +1008,7 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
         FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_h2d[slot], 0));
         d_in = fe->d_raw[slot];
     }
-    rc = process_block(fe, fmt, d_in, count, rs);
+    rc = process_block(fe, fmt, d_in, count, rs, scale);
     if (rc != SDRPP_OK) return rc;
     if (!device_src) {
         // the raw buffer may be overwritten once this block's kernels are done
@@ -1140,6 +1140,74 @@ int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf32* out) {
     SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_b, outb, cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
     return SDRPP_OK;
+}
+
+// ---- SDR++ server wire packets (dsp/compression/sample_stream_{de,}compressor.h) -------------------
+// Packet: u16 compression type (0) | u16 PCMType | f32 scaler | payload (sample_stream_compressor.h:27-34).
+struct PcmHeader { int fmt; float divisor; int nsamples; };
+// Header arithmetic of SampleStreamDecompressor::process (sample_stream_decompressor.h:14-33). fmt < 0: the
+// reference returns 0 samples for an unknown sample type.
+static PcmHeader pcm_parse(const void* packet, int nbytes) {
+    uint16_t type; float scaler;
+    memcpy(&type, (const uint8_t*)packet + 2, 2);
+    memcpy(&scaler, (const uint8_t*)packet + 4, 4);
+    const int payload = nbytes - 8;
+    switch (type) {
+    case SDRPP_PCM_F32: return { SDRPP_FMT_CF32, 1.0f, payload / 8 };
+    case SDRPP_PCM_I16: return { kFmtPcmI16, 32768.0f / scaler, payload / 4 };
+    case SDRPP_PCM_I8:  return { kFmtPcmI8, 128.0f / scaler, payload / 2 };
+    }
+    return { -1, 1.0f, 0 };
+}
+
+int sdrpp_cuda_pcm_decompress(const void* packet, int nbytes, sdrpp_cf32* out) {
+    if (!packet || nbytes < 8 || !out) return fail(SDRPP_ERR_ARG, "bad argument");
+    const PcmHeader h = pcm_parse(packet, nbytes);
+    if (h.fmt < 0 || h.nsamples == 0) return 0;
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    const size_t inb = (size_t)h.nsamples * fmt_bytes_per_sample(h.fmt), outb = (size_t)h.nsamples * 8;
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, inb));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, outb));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, (const uint8_t*)packet + 8, inb, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(launch_ingest(h.fmt, g_os.d_a, h.nsamples, RingRef{ (float2*)g_os.d_b, 0xFFFFFFFFu }, 0, false, g_os.st, h.divisor));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_b, outb, cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    return h.nsamples;
+}
+
+int sdrpp_cuda_pcm_compress(int pcm_type, const sdrpp_cf32* in, int count, void* packet) {
+    if (!in || !packet || count < 0) return fail(SDRPP_ERR_ARG, "bad argument");
+    if (pcm_type != SDRPP_PCM_I8 && pcm_type != SDRPP_PCM_I16 && pcm_type != SDRPP_PCM_F32) return fail(SDRPP_ERR_ARG, "unknown PCM type");
+    uint8_t* pk = (uint8_t*)packet;
+    const uint16_t comp = 0, type = (uint16_t)pcm_type;
+    memcpy(pk, &comp, 2);
+    memcpy(pk + 2, &type, 2);
+    float scaler = 0.0f;
+    if (pcm_type == SDRPP_PCM_F32 || count == 0) {
+        // float32 needs no device work (sample_stream_compressor.h:37-41)
+        memcpy(pk + 4, &scaler, 4);
+        if (pcm_type != SDRPP_PCM_F32) return 8;
+        memcpy(pk + 8, in, (size_t)count * 8);
+        return 8 + count * 8;
+    }
+    const int bits = pcm_type == SDRPP_PCM_I8 ? 8 : 16;
+    const size_t inb = (size_t)count * 8, outb = (size_t)count * 2 * (bits / 8);
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, inb));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, outb));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, 16));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, in, inb, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(launch_pcm_compress(bits, (const float*)g_os.d_a, 2 * count, (unsigned int*)g_os.d_c, g_os.d_b,
+                                       (float*)g_os.d_c + 1, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(pk + 8, g_os.d_b, outb, cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(&scaler, (float*)g_os.d_c + 1, 4, cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    memcpy(pk + 4, &scaler, 4);
+    return 8 + (int)outb;
 }
 
 int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* window, float* row, sdrpp_cf32* X) {
@@ -1566,6 +1634,13 @@ int sdrpp_cuda_frontend_submit(sdrpp_cuda_frontend* fe, int fmt, const void* in,
 }
 int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt, const void* dev_in, int count) {
     return submit_common(fe, fmt, dev_in, count, true);
+}
+int sdrpp_cuda_frontend_submit_pcm(sdrpp_cuda_frontend* fe, const void* packet, int nbytes) {
+    if (!packet || nbytes < 8) return fail(SDRPP_ERR_ARG, "bad argument");
+    const PcmHeader h = pcm_parse(packet, nbytes);
+    if (h.fmt < 0 || h.nsamples == 0) return 0; // the decompressor emits nothing (sample_stream_decompressor.h:35,43-48)
+    const int rc = submit_common(fe, h.fmt, (const uint8_t*)packet + 8, h.nsamples, false, h.divisor);
+    return rc == SDRPP_OK ? h.nsamples : rc;
 }
 
 int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe) {

@@ -17,7 +17,12 @@ struct RingRef {
 // Ingest / pre-processing (convert.cu, preproc.cu)
 // ---------------------------------------------------------------------------------------------
 // raw samples of format fmt -> cf32 at dst[(pos+i)&mask], optional conjugate (dsp/math/conjugate.h:12-15)
-cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st);
+cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st,
+                          float scale = 1.0f);
+// SampleStreamCompressor (sample_stream_compressor.h:26-60): block maximum, then int8/int16 packing.
+// key: one device word of scratch; scaler_out: device float that receives the packet's scaler.
+cudaError_t launch_pcm_compress(int bits, const float* in, int nscalars, unsigned int* key, void* out, float* scaler_out,
+                                cudaStream_t st);
 
 // One decimating FIR stage of the front-end PowerDecimator (dsp/filter/decimating_fir.h:45-68):
 // out[m] = sum_k buf[offset + m*D + k] * taps[k], buf = [T-1 history | count new samples] (linear).

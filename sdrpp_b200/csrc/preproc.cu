@@ -18,12 +18,12 @@ __device__ __forceinline__ void ring_store(RingRef dst, uint32_t idx, float2 v, 
 // ---------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(256)
-ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos, bool conj, bool vec_ok) {
+ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos, bool conj, bool vec_ok, float scale) {
     const int stride = gridDim.x * blockDim.x;
     const int nquads = count >> 2;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
         float2 s[4];
-        if (vec_ok && FMT <= 5) {
+        if (vec_ok && (FMT <= 5 || FMT >= 9)) {
             if constexpr (FMT == 0) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(raw) + 2 * q);
                 const float4 b = __ldg(reinterpret_cast<const float4*>(raw) + 2 * q + 1);
@@ -37,26 +37,30 @@ ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos
                 for (int i = 0; i < 4; i++)
                     s[i] = FMT == 1 ? make_float2(cvt_u8_rtl(b[2 * i]), cvt_u8_rtl(b[2 * i + 1]))
                                     : make_float2(cvt_u8_tcp(b[2 * i]), cvt_u8_tcp(b[2 * i + 1]));
-            } else if constexpr (FMT == 3) {
+            } else if constexpr (FMT == 3 || FMT == 9) {
                 const uint2 w = __ldg(reinterpret_cast<const uint2*>(raw) + q);
                 const int b[8] = { (int)(signed char)(w.x & 255u), (int)(signed char)((w.x >> 8) & 255u),
                                    (int)(signed char)((w.x >> 16) & 255u), (int)(signed char)(w.x >> 24),
                                    (int)(signed char)(w.y & 255u), (int)(signed char)((w.y >> 8) & 255u),
                                    (int)(signed char)((w.y >> 16) & 255u), (int)(signed char)(w.y >> 24) };
 #pragma unroll
-                for (int i = 0; i < 4; i++) s[i] = make_float2(cvt_i8(b[2 * i]), cvt_i8(b[2 * i + 1]));
-            } else if constexpr (FMT == 4 || FMT == 5) {
+                for (int i = 0; i < 4; i++)
+                    s[i] = FMT == 3 ? make_float2(cvt_i8(b[2 * i]), cvt_i8(b[2 * i + 1]))
+                                    : make_float2(__fdiv_rn((float)b[2 * i], scale), __fdiv_rn((float)b[2 * i + 1], scale));
+            } else if constexpr (FMT == 4 || FMT == 5 || FMT == 10) {
                 const uint4 w = __ldg(reinterpret_cast<const uint4*>(raw) + q);
                 const unsigned int u[4] = { w.x, w.y, w.z, w.w };
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const int re = (int)(short)(u[i] & 0xFFFFu), im = (int)(short)(u[i] >> 16);
-                    s[i] = FMT == 4 ? make_float2(cvt_i16_file(re), cvt_i16_file(im)) : make_float2(cvt_i16_volk(re), cvt_i16_volk(im));
+                    s[i] = FMT == 4 ? make_float2(cvt_i16_file(re), cvt_i16_file(im))
+                         : FMT == 5 ? make_float2(cvt_i16_volk(re), cvt_i16_volk(im))
+                                    : make_float2(__fdiv_rn((float)re, scale), __fdiv_rn((float)im, scale));
                 }
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) s[i] = load_sample<FMT>(raw, (size_t)4 * q + i);
+            for (int i = 0; i < 4; i++) s[i] = load_sample<FMT>(raw, (size_t)4 * q + i, scale);
         }
         if (conj) {
 #pragma unroll
@@ -76,12 +80,12 @@ ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos
     const int tail0 = nquads << 2;
     const int t = tail0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (t < count) {
-        float2 v = load_sample<FMT>(raw, (size_t)t);
+        float2 v = load_sample<FMT>(raw, (size_t)t, scale);
         ring_store(dst, pos + (uint32_t)t, v, conj);
     }
 }
 
-cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st) {
+cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st, float scale) {
     if (count <= 0) return cudaSuccess;
     const int threads = 256;
     int blocks = ceil_div(ceil_div(count, 4), threads);
@@ -89,17 +93,104 @@ cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint
     if (blocks < 1) blocks = 1;
     const bool vec_ok = ((uintptr_t)raw & 15u) == 0;
     switch (fmt) {
-    case 0: ingest_kernel<0><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
-    case 1: ingest_kernel<1><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
-    case 2: ingest_kernel<2><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
-    case 3: ingest_kernel<3><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
-    case 4: ingest_kernel<4><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
-    case 5: ingest_kernel<5><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok); break;
-    case 6: ingest_kernel<6><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false); break;
-    case 7: ingest_kernel<7><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false); break;
-    case 8: ingest_kernel<8><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false); break;
+    case 0: ingest_kernel<0><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 1: ingest_kernel<1><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 2: ingest_kernel<2><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 3: ingest_kernel<3><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 4: ingest_kernel<4><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 5: ingest_kernel<5><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 6: ingest_kernel<6><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false, scale); break;
+    case 7: ingest_kernel<7><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false, scale); break;
+    case 8: ingest_kernel<8><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false, scale); break;
+    case 9: ingest_kernel<9><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 10: ingest_kernel<10><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
     default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// SDR++ server wire compression (dsp::compression::SampleStreamCompressor::process,
+// sample_stream_compressor.h:26-60): the packet's scaler is the largest SIGNED float of the block
+// (volk_32f_index_max_32u, then in[maxIdx]), and every scalar becomes rintf(x * (128|32768)/max)
+// saturated to the integer range (generic volk_32f_s32f_convert_8i / _16i). HBM-bound: 4 B in,
+// 1-2 B out per scalar, two passes over the block (the second one is served by L2 below ~100 MB).
+// ---------------------------------------------------------------------------------------------
+// Order-preserving float -> uint key: key(a) < key(b)  <=>  a < b for non-NaN a, b.
+__device__ __forceinline__ unsigned int float_key(float f) {
+    const unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(unsigned int k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void __launch_bounds__(256)
+pcm_max_kernel(const float* __restrict__ in, int nscalars, unsigned int* __restrict__ key_out) {
+    unsigned int best = 0u;
+    const int stride = gridDim.x * blockDim.x;
+    const int nquads = nscalars >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + q);
+        best = max(best, max(max(float_key(v.x), float_key(v.y)), max(float_key(v.z), float_key(v.w))));
+    }
+    const int t = (nquads << 2) + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nscalars) best = max(best, float_key(__ldg(in + t)));
+    best = __reduce_max_sync(0xFFFFFFFFu, best);
+    __shared__ unsigned int s_best[8];
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = threadIdx.x < (blockDim.x >> 5) ? s_best[threadIdx.x] : 0u;
+        best = __reduce_max_sync(0xFFFFFFFFu, best);
+        if (threadIdx.x == 0) atomicMax(key_out, best);
+    }
+}
+
+template <int BITS>
+__device__ __forceinline__ int pcm_quantise(float x, float scalar) {
+    const float r = __fmul_rn(x, scalar);
+    constexpr float lo = BITS == 8 ? -128.0f : -32768.0f, hi = BITS == 8 ? 127.0f : 32767.0f;
+    // the comparisons are false for NaN, like the reference's; the cast of a NaN is then 0 here
+    return r > hi ? (int)hi : r < lo ? (int)lo : __float2int_rn(r);
+}
+
+template <int BITS>
+__global__ void __launch_bounds__(256)
+pcm_pack_kernel(const float* __restrict__ in, int nscalars, const unsigned int* __restrict__ key, void* __restrict__ out,
+                float* __restrict__ scaler_out) {
+    const float maxv = key_float(*key);
+    const float scalar = __fdiv_rn(BITS == 8 ? 128.0f : 32768.0f, maxv);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *scaler_out = maxv;
+    const int stride = gridDim.x * blockDim.x;
+    const int nquads = nscalars >> 2;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in) + q);
+        const int a = pcm_quantise<BITS>(v.x, scalar), b = pcm_quantise<BITS>(v.y, scalar);
+        const int c = pcm_quantise<BITS>(v.z, scalar), d = pcm_quantise<BITS>(v.w, scalar);
+        if constexpr (BITS == 8)
+            reinterpret_cast<unsigned int*>(out)[q] = (a & 255) | ((b & 255) << 8) | ((c & 255) << 16) | ((unsigned)(d & 255) << 24);
+        else
+            reinterpret_cast<uint2*>(out)[q] = make_uint2((a & 0xFFFF) | ((unsigned)(b & 0xFFFF) << 16), (c & 0xFFFF) | ((unsigned)(d & 0xFFFF) << 16));
+    }
+    const int t = (nquads << 2) + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nscalars) {
+        const int a = pcm_quantise<BITS>(__ldg(in + t), scalar);
+        if constexpr (BITS == 8) reinterpret_cast<signed char*>(out)[t] = (signed char)a;
+        else reinterpret_cast<short*>(out)[t] = (short)a;
+    }
+}
+
+cudaError_t launch_pcm_compress(int bits, const float* in, int nscalars, unsigned int* key, void* out, float* scaler_out,
+                                cudaStream_t st) {
+    if (nscalars <= 0 || (bits != 8 && bits != 16)) return cudaErrorInvalidValue;
+    int blocks = ceil_div(ceil_div(nscalars, 4), 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    cudaError_t e = cudaMemsetAsync(key, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    pcm_max_kernel<<<blocks, 256, 0, st>>>(in, nscalars, key);
+    if (bits == 8) pcm_pack_kernel<8><<<blocks, 256, 0, st>>>(in, nscalars, key, out, scaler_out);
+    else pcm_pack_kernel<16><<<blocks, 256, 0, st>>>(in, nscalars, key, out, scaler_out);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,7 @@ SYMBOLS = """
 sdrpp_cuda_version sdrpp_cuda_last_error sdrpp_cuda_device_count sdrpp_cuda_init sdrpp_cuda_host_alloc
 sdrpp_cuda_host_free sdrpp_cuda_design_window sdrpp_cuda_design_lowpass sdrpp_cuda_design_resampler
 sdrpp_cuda_design_decim_plan sdrpp_cuda_design_reshape sdrpp_cuda_convert sdrpp_cuda_spectrum
+sdrpp_cuda_pcm_decompress sdrpp_cuda_pcm_compress sdrpp_cuda_frontend_submit_pcm
 sdrpp_cuda_frontend_create sdrpp_cuda_frontend_destroy sdrpp_cuda_frontend_set_sample_rate
 sdrpp_cuda_frontend_set_decimation sdrpp_cuda_frontend_set_dc_blocking sdrpp_cuda_frontend_set_invert_iq
 sdrpp_cuda_frontend_set_fft_size sdrpp_cuda_frontend_set_fft_rate sdrpp_cuda_frontend_set_fft_window
@@ -78,6 +79,9 @@ def lib():
         L.sdrpp_cuda_design_reshape.restype = None
         L.sdrpp_cuda_convert.argtypes = [_i, _vp, _i, _vp]
         L.sdrpp_cuda_spectrum.argtypes = [_i, _i, _i, _vp, _vp, _vp, _vp]
+        L.sdrpp_cuda_pcm_decompress.argtypes = [_vp, _i, _vp]
+        L.sdrpp_cuda_pcm_compress.argtypes = [_i, _vp, _i, _vp]
+        L.sdrpp_cuda_frontend_submit_pcm.argtypes = [_vp, _vp, _i]
         L.sdrpp_cuda_spectrum_device.argtypes = [_i, _i, _i, C.c_longlong, _vp, _vp, _vp, _vp]
         L.sdrpp_cuda_fft_zoom.argtypes = [_i, _vp, _d, _d, _d, _i, _vp, _vp]
         L.sdrpp_cuda_frontend_set_fft_zoom.argtypes = [_vp, _d, _d, _d, _i, _i]
@@ -189,6 +193,25 @@ def convert(fmt, raw):
     out = np.zeros(n, dtype=np.complex64)
     _check(lib().sdrpp_cuda_convert(fmt, _ptr(raw), n, _ptr(out)), "sdrpp_cuda_convert")
     return out
+
+
+PCM_I8, PCM_I16, PCM_F32 = 0, 1, 2  # dsp/compression/pcm_type.h:4-8
+
+
+def pcm_decompress(packet):
+    """SampleStreamDecompressor::process (sample_stream_decompressor.h:13-36) on one wire packet."""
+    packet = np.ascontiguousarray(packet, dtype=np.uint8)
+    out = np.zeros(max(1, (len(packet) - 8) // 2), dtype=np.complex64)
+    n = _check(lib().sdrpp_cuda_pcm_decompress(_ptr(packet), len(packet), _ptr(out)), "sdrpp_cuda_pcm_decompress")
+    return out[:n].copy()
+
+
+def pcm_compress(pcm_type, x):
+    """SampleStreamCompressor::process (sample_stream_compressor.h:26-60): cf32 block -> wire packet."""
+    x = np.ascontiguousarray(x, dtype=np.complex64)
+    packet = np.zeros(8 + 8 * len(x), dtype=np.uint8)
+    n = _check(lib().sdrpp_cuda_pcm_compress(int(pcm_type), _ptr(x), len(x), _ptr(packet)), "sdrpp_cuda_pcm_compress")
+    return packet[:n].copy()
 
 
 def spectrum(N, frame, window, fmt=FMT_CF32, want_X=False):
@@ -327,6 +350,12 @@ class Frontend:
         self._keep = raw
         _check(lib().sdrpp_cuda_frontend_submit(self.h, fmt, _ptr(raw), n), "submit")
         return n
+
+    def submit_pcm(self, packet):
+        """One SDR++ server wire packet (host memory) through the whole path; returns the sample count."""
+        packet = np.ascontiguousarray(packet, dtype=np.uint8)
+        self._keep = packet
+        return _check(lib().sdrpp_cuda_frontend_submit_pcm(self.h, _ptr(packet), len(packet)), "submit_pcm")
 
     def submit_device(self, fmt, dev_ptr, count):
         _check(lib().sdrpp_cuda_frontend_submit_device(self.h, fmt, C.c_void_p(dev_ptr), count), "submit_device")

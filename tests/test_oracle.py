@@ -102,6 +102,32 @@ def test_port_matches_reference_full_demods(port, ref):
             assert np.array_equal(_bits(da.process(blk)), _bits(db.process(blk))), name
 
 
+# ---- SDR++ server wire packets (dsp/compression): port vs the reference headers ------------------------------
+@pytest.mark.parametrize("ptype", [0, 1, 2])
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 30001])
+def test_pcm_port_vs_ref(port, ref, ptype, n):
+    from tools.make_golden import pcm_input
+    x = pcm_input(n, 1000 * ptype + n)
+    pr, pp = ref.pcm_compress(ptype, x), port.pcm_compress(ptype, x)
+    assert len(pr) == 8 + n * (2, 4, 8)[ptype]
+    assert np.array_equal(pr, pp)
+    assert np.array_equal(_bits(ref.pcm_decompress(pr)), _bits(port.pcm_decompress(pr)))
+    # header: compression type 0, sample type, scaler = largest signed scalar (0 for float32)
+    assert pr[:4].view(np.uint16).tolist() == [0, ptype]
+    assert pr[4:8].view(np.float32)[0] == (np.float32(0) if ptype == 2 else x.view(np.float32).max())
+
+
+def test_pcm_unknown_type_and_ragged_payload(port, ref):
+    pk = np.zeros(8 + 7, dtype=np.uint8)
+    pk[2] = 7  # unknown PCMType: the decompressor emits nothing
+    assert len(port.pcm_decompress(pk)) == 0 and len(ref.pcm_decompress(pk)) == 0
+    pk[2] = 1  # int16 with a payload that is not a whole number of samples: floor((count-8)/4)
+    pk[4:8] = np.array([0.5], np.float32).view(np.uint8)
+    pk[8:] = np.arange(7, dtype=np.uint8)
+    a, b = ref.pcm_decompress(pk), port.pcm_decompress(pk)
+    assert len(a) == 1 and np.array_equal(_bits(a), _bits(b))
+
+
 # ---- golden vectors generated from the compiled reference (travel to the GPU box) -----------------------------
 def _golden_cases():
     p = os.path.join(GOLD, "manifest.json")
@@ -156,6 +182,12 @@ def test_port_matches_golden(port, case):
         d = make_post(port, case["args"][0], a)
         got = np.concatenate([d.process(b) for b in post_input(a["sr"], a["seed"])])
         assert np.array_equal(_bits(got), _bits(data["out"]))
+    elif kind == "pcm":
+        from tools.make_golden import pcm_input
+        ptype, n = case["args"]
+        pk = port.pcm_compress(ptype, pcm_input(n, case["seed"]))
+        assert np.array_equal(pk, data["packet"])
+        assert np.array_equal(_bits(port.pcm_decompress(data["packet"])), _bits(data["out"]))
     else:
         pytest.fail("unknown golden kind " + kind)
 

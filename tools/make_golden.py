@@ -54,6 +54,14 @@ def make_post(lib, kind, a):
     return lib.ssb_full(a["mode"], a["bw"], a["sr"], bool(a["agc"]), a["attack"], a["decay"])
 
 
+def pcm_input(n, seed):
+    """Block whose negative excursion exceeds its (signed) maximum, so the compressor's saturation branch is taken."""
+    rng = np.random.default_rng(seed)
+    x = (0.3 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    x[n // 3] = np.complex64(-1.7 + 0.2j)
+    return x
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = po.Ref()
@@ -116,6 +124,13 @@ def main():
         rng = np.random.default_rng(seed)
         row = (rng.standard_normal(N) * 10.0 - 80.0).astype(np.float32)
         add("fft_" + name, "zoom", (N, out, vo, vb, wb), {"out": ref.fft_zoom(vo, vb, wb, row, out)}, seed=seed)
+
+    # SDR++ server wire packets: the reference's own compressor makes the packet, its own
+    # decompressor reads it back
+    for name, ptype, n, seed in [("i8", 0, 4099, 10), ("i16", 1, 4099, 11), ("f32", 2, 513, 12)]:
+        x = pcm_input(n, seed)
+        pk = ref.pcm_compress(ptype, x)
+        add("pcm_" + name, "pcm", (ptype, n), {"packet": pk, "out": ref.pcm_decompress(pk)}, seed=seed)
 
     json.dump({"generator": "tools/make_golden.py", "source": ref.lib.ref_build_info.restype and "oracle/_ref/libsdrpp_ref.so (reference dsp/ headers, IEEE flags)",
                "cases": cases}, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
