@@ -602,6 +602,57 @@ API int orc_conjugate(int count, const cf32* in, cf32* out) {
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* 8f rank 4. Radio IF chain blocks (decoder_modules/radio/src/radio_module.h:73-78)           */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { float rate, invRate, level, amp; } orc_nb;
+API orc_nb* orc_nb_create(double rate, double level) {        /* noise_reduction/noise_blanker.h:12-17,77 */
+    orc_nb* b = (orc_nb*)calloc(1, sizeof(orc_nb));
+    b->rate = (float)rate; b->invRate = 1.0f - b->rate; b->level = (float)level; b->amp = 1.0f;
+    return b;
+}
+API int orc_nb_process(orc_nb* b, int count, const cf32* in, cf32* out) {
+    int i;                                                     /* noise_reduction/noise_blanker.h:39-59 */
+    for (i = 0; i < count; i++) {
+        float inAmp = sqrtf((in[i].re * in[i].re) + (in[i].im * in[i].im)); /* complex_t::amplitude, types.h:79-81 */
+        float gain = 1.0f;
+        if (inAmp != 0.0f) {
+            float excess;
+            b->amp = (b->amp * b->invRate) + (inAmp * b->rate);
+            excess = inAmp / b->amp;
+            if (excess > b->level) gain = 1.0f / excess;
+        }
+        out[i].re = in[i].re * gain; out[i].im = in[i].im * gain;
+    }
+    return count;
+}
+API void orc_nb_destroy(orc_nb* b) { free(b); }
+
+typedef struct { float level; int mute, cnt; } orc_squelch;  /* cnt: a function-local static in the reference (squelch.h:42) */
+API orc_squelch* orc_squelch_create(double level) {
+    orc_squelch* s = (orc_squelch*)calloc(1, sizeof(orc_squelch));
+    s->level = (float)level;
+    return s;
+}
+API int orc_squelch_process(orc_squelch* s, int count, const cf32* in, cf32* out) {
+    float sum = 0.0f, level;                                   /* noise_reduction/squelch.h:34-64 */
+    int i;
+    for (i = 0; i < count; i++) sum += sqrtf(in[i].re * in[i].re + in[i].im * in[i].im);
+    sum /= (float)count;
+    level = 20.0f * log10f(sum);
+    if (s->mute) {
+        if (level < s->level || s->cnt <= 0) s->cnt = 10;
+        else if (--s->cnt == 0) s->mute = 0;
+    } else if (level < (s->level - 1.0f)) {
+        s->cnt = 0;
+        s->mute = 1;
+    }
+    if (!s->mute) memmove(out, in, (size_t)count * sizeof(cf32));
+    else memset(out, 0, (size_t)count * sizeof(cf32));
+    return count;
+}
+API void orc_squelch_destroy(orc_squelch* s) { free(s); }
+
+/* ------------------------------------------------------------------------------------------ */
 /* A16-A18. Demodulator front ends                                                             */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct { float invDev; cf32 din; } orc_quad;

@@ -173,6 +173,12 @@ class _Base:
         o.info = info
         return o
 
+    def noise_blanker(self, rate, level):
+        return _Obj(self.lib, f"{self.prefix}_nb", self._f("nb_create", _vp, _d, _d)(rate, level))
+
+    def squelch(self, level):
+        return _Obj(self.lib, f"{self.prefix}_squelch", self._f("squelch_create", _vp, _d)(level))
+
     def dcblock(self, rate):
         return _Obj(self.lib, f"{self.prefix}_dcblock", self._f("dcblock_create", _vp, _d)(rate))
 

@@ -28,6 +28,8 @@
 #include <dsp/demod/am.h>
 #include <dsp/demod/ssb.h>
 #include <dsp/compression/sample_stream_compressor.h>
+#include <dsp/noise_reduction/noise_blanker.h>
+#include <dsp/noise_reduction/squelch.h>
 #include <dsp/compression/sample_stream_decompressor.h>
 
 #include <vector>
@@ -400,6 +402,19 @@ API int ref_pcm_decompress(int nbytes, const uint8_t* packet, complex_t* out) {
 API int ref_pcm_compress(int count, int pcmType, const complex_t* in, uint8_t* packet) {
     return dsp::compression::SampleStreamCompressor::process(count, (dsp::compression::PCMType)pcmType, in, packet);
 }
+
+// ---------------------------------------------------------------------------------------------
+// radio IF chain blocks (decoder_modules/radio/src/radio_module.h:73-78)
+// ---------------------------------------------------------------------------------------------
+// dsp::noise_reduction::NoiseBlanker (dsp/noise_reduction/noise_blanker.h)
+API void* ref_nb_create(double rate, double level) { return new dsp::noise_reduction::NoiseBlanker(NULL, rate, level); }
+API int ref_nb_process(void* h, int count, complex_t* in, complex_t* out) { return ((dsp::noise_reduction::NoiseBlanker*)h)->process(count, in, out); }
+API void ref_nb_destroy(void* h) { delete (dsp::noise_reduction::NoiseBlanker*)h; }
+// dsp::noise_reduction::Squelch (dsp/noise_reduction/squelch.h). Its block counter is a function-local static: use
+// one instance at a time.
+API void* ref_squelch_create(double level) { auto* s = new dsp::noise_reduction::Squelch(); s->init(NULL, level); return s; }
+API int ref_squelch_process(void* h, int count, complex_t* in, complex_t* out) { return ((dsp::noise_reduction::Squelch*)h)->process(count, in, out); }
+API void ref_squelch_destroy(void* h) { delete (dsp::noise_reduction::Squelch*)h; }
 
 // ---------------------------------------------------------------------------------------------
 // the complete demodulators (front end + post-detector stages), float output

@@ -163,6 +163,12 @@ static inline void volk_32f_s32f_convert_16i(int16_t* out, const float* in, cons
         out[i] = (int16_t)rintf(r);
     }
 }
+// generic volk_32f_accumulator_s32f: in-order fp32 sum (noise_reduction/squelch.h:37)
+static inline void volk_32f_accumulator_s32f(float* result, const float* in, unsigned int n) {
+    float acc = 0.0f;
+    for (unsigned int i = 0; i < n; i++) acc += in[i];
+    *result = acc;
+}
 static inline void volk_32f_index_max_32u(uint32_t* target, const float* src, uint32_t n) {
     if (n == 0) return;
     float mx = src[0];

@@ -518,6 +518,55 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
     }
 }
 
+// Radio IF chain on one block of a VFO's output, in place on p[0..n) (p[-1] receives the previous block's last
+// output). Both blocks are sequential in the reference and cheap at the VFO's output rate, so one thread runs them
+// with the reference's operation order (_rn intrinsics: no contraction):
+//   dsp::noise_reduction::NoiseBlanker::process (noise_reduction/noise_blanker.h:39-59)
+//   dsp::noise_reduction::Squelch::process (noise_reduction/squelch.h:34-64); its block counter is a function-local
+//   static there (one counter for every instance in the process) and per VFO here.
+__device__ __noinline__ void if_chain_run(float* __restrict__ r, float2* p, int n) {
+    if (r[IF_NB_ON] != 0.0f) {
+        const float rate = r[IF_NB_RATE], inv_rate = r[IF_NB_INVRATE], level = r[IF_NB_LEVEL];
+        float amp = r[IF_NB_AMP];
+        for (int i = 0; i < n; i++) {
+            const float2 v = p[i];
+            const float in_amp = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+            float gain = 1.0f;
+            if (in_amp != 0.0f) {
+                amp = __fadd_rn(__fmul_rn(amp, inv_rate), __fmul_rn(in_amp, rate));
+                const float excess = __fdiv_rn(in_amp, amp);
+                if (excess > level) gain = __fdiv_rn(1.0f, excess);
+            }
+            p[i] = make_float2(__fmul_rn(v.x, gain), __fmul_rn(v.y, gain));
+        }
+        r[IF_NB_AMP] = amp;
+    }
+    if (r[IF_SQ_ON] != 0.0f) {
+        float sum = 0.0f; // volk_32fc_magnitude_32f + volk_32f_accumulator_s32f (generic: in order)
+        for (int i = 0; i < n; i++) {
+            const float2 v = p[i];
+            sum = __fadd_rn(sum, __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y))));
+        }
+        sum = __fdiv_rn(sum, (float)n);
+        const float level = __fmul_rn(20.0f, log10f(sum));
+        const float thr = r[IF_SQ_LEVEL];
+        bool mute = r[IF_SQ_MUTE] != 0.0f;
+        int cnt = (int)r[IF_SQ_CNT];
+        if (mute) {
+            if (level < thr || cnt <= 0) cnt = 10;
+            else if (--cnt == 0) mute = false;
+        } else if (level < __fadd_rn(thr, -1.0f)) {
+            cnt = 0;
+            mute = true;
+        }
+        r[IF_SQ_MUTE] = mute ? 1.0f : 0.0f;
+        r[IF_SQ_CNT] = (float)cnt;
+        r[IF_SQ_LAST_DB] = level;
+        if (mute) for (int i = 0; i < n; i++) p[i] = make_float2(0.0f, 0.0f);
+    }
+    p[-1] = make_float2(r[IF_PREV_RE], r[IF_PREV_IM]);
+}
+
 __global__ void __launch_bounds__(kTailThreads, 4)
 tail_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
@@ -586,15 +635,28 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         }
     }
 
-    // final output, demod front end, results arena
+    // final output, [radio IF chain], demod front end, results arena
     float2* fin = slab + g.final_off; // fin[-1] = last output of the previous block
     float2* o_iq = a.arena_iq + vd.out_off;
     float* o_dm = a.arena_demod + vd.out_off;
+    // The demod front end reads `src`: the VFO output itself, or -- with an IF chain record -- a copy in shared
+    // memory that the chain's blocks have worked on (the iq result stays the raw VFO output = vfo->output).
+    const float2* src = fin;
+    const bool if_on = vd.ifs != nullptr && g.n_final > 0 && g.n_final < kTailSmemSamples; // the engine refuses larger blocks
+    if (if_on) {
+        float2* p = tsm + 1; // p[-1] = last IF-chain output of the previous block
+        __syncthreads();
+        for (int i = tid; i < g.n_final; i += kTailThreads) p[i] = fin[i];
+        __syncthreads();
+        if (tid == 0) if_chain_run(vd.ifs, p, g.n_final);
+        __syncthreads();
+        src = p;
+    }
     for (int i = tid; i < g.n_final; i += kTailThreads) {
-        const float2 y = fin[i];
-        o_iq[i] = y;
+        const float2 y = src[i];
+        o_iq[i] = fin[i];
         if (g.demod == 1) {
-            const float2 p = fin[i - 1];
+            const float2 p = src[i - 1];
             // y * conj(prev) with complex_t::operator* (dsp/types.h:23-25)
             const float dre = y.x * p.x + y.y * p.y;
             const float dim = y.y * p.x - y.x * p.y;
@@ -612,6 +674,7 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         float2* nxt = (g.nstages == 0) ? (slab + g.carry0_off) : fin;
         if (g.n_final > 0) nxt[-1] = fin[g.n_final - 1];
         else if (g.nstages == 0) nxt[-1] = fin[-1];
+        if (if_on) { vd.ifs[IF_PREV_RE] = src[g.n_final - 1].x; vd.ifs[IF_PREV_IM] = src[g.n_final - 1].y; }
     }
 }
 

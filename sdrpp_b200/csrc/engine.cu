@@ -204,6 +204,8 @@ struct Vfo {
     float* post_state = nullptr;   // device: scalars | FIR history | work area
     float* post_taps = nullptr;    // device
     int post_ntaps = 0, post_hist_pad = 0;
+    // radio IF chain: device record of IF_FLOATS floats, null until first configured
+    float* if_state = nullptr;
 };
 
 struct Group {
@@ -447,7 +449,7 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
             arena += (size_t)((g.plan->cap_final + 3) & ~3);
             VfoDev& d = h[(size_t)v.dev_index];
             d.slab = v.slab; d.phi_ref = v.phi_ref; d.n_ref = v.n_ref; d.dphi = v.dphi; d.dphi2 = v.dphi2;
-            d.out_off = v.out_off; d.pad = 0;
+            d.out_off = v.out_off; d.pad = 0; d.ifs = v.if_state;
             PostDev& pd = hp[(size_t)v.dev_index];
             pd = PostDev{};
             if (v.post.enabled && v.post_state) {
@@ -1378,7 +1380,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
     if (fe->st_d2h) cudaStreamSynchronize(fe->st_d2h);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
-    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); }
+    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.if_state); }
     for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
     for (int i = 0; i < 2; i++) { cudaFree(fe->tc_planes[i].hi); cudaFree(fe->tc_planes[i].lo); cudaFree(fe->tc_planes[i].sinv); }
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
@@ -1536,7 +1538,7 @@ int sdrpp_cuda_vfo_destroy(sdrpp_cuda_frontend* fe, int id) {
     if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
     remove_from_group(fe, id);
     if (v->slab) cudaFree(v->slab);
-    cudaFree(v->post_state); cudaFree(v->post_taps);
+    cudaFree(v->post_state); cudaFree(v->post_taps); cudaFree(v->if_state); v->if_state = nullptr;
     *v = Vfo();
     return SDRPP_OK;
 }
@@ -1693,6 +1695,46 @@ int sdrpp_cuda_vfo_set_post(sdrpp_cuda_frontend* fe, int id, const sdrpp_cuda_po
     const sdrpp_cuda_post_cfg old = v->post;
     v->post = *cfg;
     if ((rc = apply_post(fe, *v)) != SDRPP_OK) { v->post = old; v->post.enabled = 0; apply_post(fe, *v); return rc; }
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_set_if_chain(sdrpp_cuda_frontend* fe, int id, const sdrpp_cuda_if_cfg* cfg) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    if (!cfg) return fail(SDRPP_ERR_ARG, "null cfg");
+    if (v->plan->cap_final + 1 > 4600) return fail(SDRPP_ERR_ARG, "IF chain: the VFO's block output exceeds the tail kernel's staging area");
+    float rec[IF_FLOATS] = { 0 };
+    if (!v->if_state) {
+        if (!cfg->nb_enabled && !cfg->squelch_enabled) return SDRPP_OK;
+        FE_TRY(fe, dev_alloc(&v->if_state, (size_t)IF_FLOATS));
+        rec[IF_NB_AMP] = 1.0f; // noise_blanker.h:77; Squelch: _isMute = false (squelch.h:79)
+        fe->layout_dirty = true;
+    } else {
+        FE_TRY(fe, cudaMemcpy(rec, v->if_state, sizeof(rec), cudaMemcpyDeviceToHost));
+    }
+    // float members assigned from doubles: _rate = rate; _invRate = 1.0f - _rate; _level = level (noise_blanker.h:13-16)
+    rec[IF_NB_ON] = cfg->nb_enabled ? 1.0f : 0.0f;
+    rec[IF_NB_RATE] = (float)cfg->nb_rate;
+    rec[IF_NB_INVRATE] = 1.0f - rec[IF_NB_RATE];
+    rec[IF_NB_LEVEL] = (float)cfg->nb_level;
+    rec[IF_SQ_ON] = cfg->squelch_enabled ? 1.0f : 0.0f;
+    rec[IF_SQ_LEVEL] = (float)cfg->squelch_level;
+    FE_TRY(fe, cudaMemcpy(v->if_state, rec, sizeof(rec), cudaMemcpyHostToDevice));
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_squelch_state(sdrpp_cuda_frontend* fe, int id, int* muted, float* level_db) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    if (!v->if_state) return fail(SDRPP_ERR_STATE, "no IF chain on this VFO");
+    float rec[IF_FLOATS];
+    FE_TRY(fe, cudaMemcpy(rec, v->if_state, sizeof(rec), cudaMemcpyDeviceToHost));
+    if (muted) *muted = rec[IF_SQ_MUTE] != 0.0f;
+    if (level_db) *level_db = rec[IF_SQ_LAST_DB];
     return SDRPP_OK;
 }
 

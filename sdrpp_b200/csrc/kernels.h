@@ -70,7 +70,13 @@ struct VfoDev {
     uint64_t dphi2;      // SSB second translation, per output sample
     uint32_t out_off;    // offset of this VFO's rows in the output arenas (samples)
     uint32_t pad;
+    float* ifs;          // radio IF chain record (IF_* below) between the VFO output and the demod front end; null = off
 };
+
+// Radio IF chain record, one per VFO that has a block of the chain enabled (decoder_modules/radio/src/radio_module.h:
+// 73-78: NoiseBlanker -> Squelch in front of the demodulator). Configuration and state, 16 floats.
+enum { IF_NB_ON = 0, IF_NB_RATE, IF_NB_INVRATE, IF_NB_LEVEL, IF_NB_AMP, IF_SQ_ON, IF_SQ_LEVEL, IF_SQ_MUTE, IF_SQ_CNT,
+       IF_PREV_RE, IF_PREV_IM, IF_SQ_LAST_DB, IF_FLOATS = 16 };
 
 constexpr int kStage1Warps = 8;     // warps per CTA, each owning R consecutive input rows
 

@@ -34,7 +34,7 @@ sdrpp_cuda_frontend_submit sdrpp_cuda_frontend_submit_device sdrpp_cuda_frontend
 sdrpp_cuda_frontend_set_readback sdrpp_cuda_vfo_output sdrpp_cuda_fft_rows sdrpp_cuda_frontend_read_iq
 sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_profiling
 sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
-sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio
+sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio sdrpp_cuda_vfo_set_if_chain sdrpp_cuda_vfo_squelch_state
 sdrpp_cuda_frontend_set_stage1_mode sdrpp_cuda_frontend_stage1_tensor_launches
 """.split()
 
@@ -50,6 +50,10 @@ class FrontendCfg(C.Structure):
 class PostCfg(C.Structure):
     _fields_ = [("enabled", _i), ("fm_lowpass", _i), ("am_agc_mode", _i), ("ssb_agc", _i),
                 ("agc_attack", _d), ("agc_decay", _d), ("dc_block_rate", _d), ("agc_gain", C.c_float)]
+
+
+class IfCfg(C.Structure):
+    _fields_ = [("nb_enabled", _i), ("nb_rate", _d), ("nb_level", _d), ("squelch_enabled", _i), ("squelch_level", _d)]
 
 
 class SdrppCudaError(RuntimeError):
@@ -109,6 +113,8 @@ def lib():
         L.sdrpp_cuda_vfo_output.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]
         L.sdrpp_cuda_fft_rows.argtypes = [_vp, C.POINTER(_vp)]
         L.sdrpp_cuda_vfo_set_post.argtypes = [_vp, _i, C.POINTER(PostCfg)]
+        L.sdrpp_cuda_vfo_set_if_chain.argtypes = [_vp, _i, C.POINTER(IfCfg)]
+        L.sdrpp_cuda_vfo_squelch_state.argtypes = [_vp, _i, _vp, _vp]
         L.sdrpp_cuda_vfo_audio.argtypes = [_vp, _i, C.POINTER(_vp)]
         L.sdrpp_cuda_frontend_read_iq.argtypes = [_vp, _vp, _i]
         L.sdrpp_cuda_frontend_launches.restype = C.c_longlong
@@ -383,6 +389,16 @@ class Frontend:
         """Post-detector stages of the demodulator behind the VFO (dsp::demod::FM / AM / SSB)."""
         cfg = PostCfg(int(enabled), int(fm_lowpass), int(am_agc_mode), int(ssb_agc), agc_attack, agc_decay, dc_block_rate, agc_gain)
         _check(lib().sdrpp_cuda_vfo_set_post(self.h, vid, C.byref(cfg)), "vfo_set_post")
+
+    def set_if_chain(self, vid, nb=False, nb_rate=500.0 / 24000.0, nb_level=10.0, squelch=False, squelch_level=-100.0):
+        """Radio IF chain in front of the demodulator: NoiseBlanker -> Squelch (radio_module.h:73-78)."""
+        cfg = IfCfg(int(nb), nb_rate, nb_level, int(squelch), squelch_level)
+        _check(lib().sdrpp_cuda_vfo_set_if_chain(self.h, vid, C.byref(cfg)), "vfo_set_if_chain")
+
+    def squelch_state(self, vid):
+        m, l = C.c_int(0), C.c_float(0)
+        _check(lib().sdrpp_cuda_vfo_squelch_state(self.h, vid, C.byref(m), C.byref(l)), "vfo_squelch_state")
+        return bool(m.value), float(l.value)
 
     def vfo_audio(self, vid):
         p = _vp()

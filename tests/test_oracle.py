@@ -128,6 +128,22 @@ def test_pcm_unknown_type_and_ragged_payload(port, ref):
     assert len(a) == 1 and np.array_equal(_bits(a), _bits(b))
 
 
+# ---- radio IF chain blocks: port vs the reference headers ----------------------------------------------------
+@pytest.mark.parametrize("n", [1, 7, 240, 1250])
+def test_if_chain_port_vs_ref(port, ref, n):
+    from tools.make_golden import if_input
+    x = if_input(40, n, 100 + n)
+    for level in (2.0, 10.0):
+        a, b = ref.noise_blanker(500.0 / 24000.0, level), port.noise_blanker(500.0 / 24000.0, level)
+        for blk in x:
+            assert np.array_equal(_bits(a.process(blk)), _bits(b.process(blk)))
+    for sq_level in (-60.0, -20.0, -8.5, 0.0):
+        a, b = ref.squelch(sq_level), port.squelch(sq_level)  # one reference Squelch at a time: its counter is a static
+        for blk in x:
+            assert np.array_equal(_bits(a.process(blk)), _bits(b.process(blk)))
+        del a
+
+
 # ---- golden vectors generated from the compiled reference (travel to the GPU box) -----------------------------
 def _golden_cases():
     p = os.path.join(GOLD, "manifest.json")
@@ -188,6 +204,16 @@ def test_port_matches_golden(port, case):
         pk = port.pcm_compress(ptype, pcm_input(n, case["seed"]))
         assert np.array_equal(pk, data["packet"])
         assert np.array_equal(_bits(port.pcm_decompress(data["packet"])), _bits(data["out"]))
+    elif kind == "if_chain":
+        from tools.make_golden import if_input
+        rate, lvl, sq_level, nblocks, n = case["args"]
+        nb, sq = port.noise_blanker(rate, lvl), port.squelch(sq_level)
+        y_nb = [nb.process(b) for b in if_input(int(nblocks), int(n), case["seed"])]
+        y_sq = [sq.process(b) for b in y_nb]
+        assert np.array_equal(_bits(np.concatenate(y_nb)), _bits(data["nb"]))
+        assert np.array_equal(_bits(np.concatenate(y_sq)), _bits(data["out"]))
+        muted = [not b.any() for b in y_sq]
+        assert any(muted) and not all(muted)  # the fixture exercises both squelch states
     else:
         pytest.fail("unknown golden kind " + kind)
 

@@ -62,6 +62,16 @@ def pcm_input(n, seed):
     return x
 
 
+def if_input(nblocks, n, seed):
+    """Blocks of a carrier that fades below and rises above a squelch level, with impulse noise for the blanker."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(nblocks * n)
+    env = np.where((t // n) % 16 < 3, 0.003, 0.4)          # three quiet blocks, thirteen loud ones, repeating
+    x = env * np.exp(2j * np.pi * 0.013 * t) + 0.001 * (rng.standard_normal(len(t)) + 1j * rng.standard_normal(len(t)))
+    x[rng.integers(0, len(t), len(t) // 97)] *= 25.0        # impulses
+    return x.astype(np.complex64).reshape(nblocks, n)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = po.Ref()
@@ -131,6 +141,13 @@ def main():
         x = pcm_input(n, seed)
         pk = ref.pcm_compress(ptype, x)
         add("pcm_" + name, "pcm", (ptype, n), {"packet": pk, "out": ref.pcm_decompress(pk)}, seed=seed)
+
+    # radio IF chain blocks: NoiseBlanker then Squelch on a bursty, fading stream, block by block
+    x = if_input(20, 240, 13)
+    nb, sq = ref.noise_blanker(500.0 / 48000.0, 3.0), ref.squelch(-20.0)
+    y_nb = [nb.process(b) for b in x]
+    y_sq = [sq.process(b) for b in y_nb]
+    add("if_chain_nb_squelch", "if_chain", (500.0 / 48000.0, 3.0, -20.0, 20, 240), {"nb": np.concatenate(y_nb), "out": np.concatenate(y_sq)}, seed=13)
 
     json.dump({"generator": "tools/make_golden.py", "source": ref.lib.ref_build_info.restype and "oracle/_ref/libsdrpp_ref.so (reference dsp/ headers, IEEE flags)",
                "cases": cases}, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
