@@ -227,23 +227,26 @@ SDRPP_API int sdrpp_cuda_vfo_set_post(sdrpp_cuda_frontend* fe, int vfo, const sd
 SDRPP_API int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int vfo, const float** audio);
 
 /* Radio IF chain between the VFO output and the demodulator front end: the order is the radio
- * module's, NoiseBlanker -> Squelch (decoder_modules/radio/src/radio_module.h:73-78). With a block enabled the VFO's
+ * module's, NoiseBlanker -> Squelch -> FMIF (decoder_modules/radio/src/radio_module.h:73-78). With a block enabled the VFO's
  * demod (and audio) results are computed from the chain's output; the iq result stays the raw VFO output (what the
  * reference exposes as vfo->output).
  *   dsp::noise_reduction::NoiseBlanker::init(in, rate, level) / process (core/src/dsp/noise_reduction/noise_blanker.h:12-17,39-59)
  *   dsp::noise_reduction::Squelch::init(in, level) / process (core/src/dsp/noise_reduction/squelch.h:19-26,34-64): mean
  *   magnitude of the block in dB against `level`, 1 dB hysteresis, 10 blocks above the level before unmuting. The
- *   reference's block counter is a function-local static shared by every Squelch in the process; here it is per VFO. */
+ *   reference's block counter is a function-local static shared by every Squelch in the process; here it is per VFO.
+ *   dsp::noise_reduction::FMIF::init(in, bins) / process (core/src/dsp/noise_reduction/fm_if.h:20-24,45-74): per sample,
+ *   Nuttall-windowed DFT of the last `bins` samples, strongest bin only, element bins/2 of the backward DFT. */
 typedef struct {
     int nb_enabled;        /* ifChain.enableBlock(&nb) */
     double nb_rate;        /* radio: 500.0 / ifSamplerate (radio_module.h:428) */
     double nb_level;       /* amplitude ratio above the running mean at which a sample is scaled down */
     int squelch_enabled;   /* ifChain.enableBlock(&squelch) */
     double squelch_level;  /* dB */
+    int fmif_bins;         /* 0: off; else FMIF::init(in, bins) / setBins, 2..64 (radio presets: 9, 15, 31, 32; radio_module.h:30-35) */
 } sdrpp_cuda_if_cfg;
 /* Creates the chain's objects on first use (NoiseBlanker amp = 1, Squelch unmuted); later calls change rate/level/enable
  * and keep the state, like setRate/setLevel/enableBlock. Needs the VFO's block output to fit the tail kernel's staging
- * area (<= 4600 samples per block), SDRPP_ERR_ARG otherwise. */
+ * area (<= 2176 samples per block), SDRPP_ERR_ARG otherwise. Changing fmif_bins clears the FMIF history (setBins). */
 SDRPP_API int sdrpp_cuda_vfo_set_if_chain(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cuda_if_cfg* cfg);
 /* Squelch state after the last submitted block: *muted, *level_db = 20*log10(mean magnitude) of that block. */
 SDRPP_API int sdrpp_cuda_vfo_squelch_state(sdrpp_cuda_frontend* fe, int vfo, int* muted, float* level_db);

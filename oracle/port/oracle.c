@@ -652,6 +652,52 @@ API int orc_squelch_process(orc_squelch* s, int count, const cf32* in, cf32* out
 }
 API void orc_squelch_destroy(orc_squelch* s) { free(s); }
 
+/* FM IF noise reduction (noise_reduction/fm_if.h:45-74): per output sample, window the last `bins` samples with a
+ * Nuttall window, forward DFT, keep the strongest bin only, backward DFT, take element bins/2. The DFTs are the
+ * mathematical definition (FFTW3f is absent here): fp64 twiddles and sums, one rounding to fp32 per output. */
+static const double C_NUTTALL_W[4] = { 0.355768, 0.487396, 0.144232, 0.012604 }; /* window/nuttall.h:6 */
+typedef struct { int bins; cf32* hist; float* win; cf32* buf; int cap; } orc_fmif;
+API orc_fmif* orc_fmif_create(int bins) {
+    orc_fmif* f = (orc_fmif*)calloc(1, sizeof(orc_fmif));
+    int i;
+    f->bins = bins;
+    f->hist = (cf32*)calloc((size_t)bins, sizeof(cf32));
+    f->win = (float*)calloc((size_t)bins, sizeof(float));
+    for (i = 0; i < bins; i++) f->win[i] = (float)orc_cosine((double)i, (double)(bins - 1), C_NUTTALL_W, 4); /* fm_if.h:111 */
+    return f;
+}
+API int orc_fmif_process(orc_fmif* f, int count, const cf32* in, cf32* out) {
+    const int n = f->bins;
+    const double fwd = -2.0 * ORC_PI / (double)n, bwd = 2.0 * ORC_PI / (double)n;
+    int i, b, k;
+    if (f->cap < count + n) { f->cap = count + n; f->buf = (cf32*)realloc(f->buf, (size_t)f->cap * sizeof(cf32)); }
+    memcpy(f->buf, f->hist, (size_t)(n - 1) * sizeof(cf32));
+    memcpy(f->buf + (n - 1), in, (size_t)count * sizeof(cf32));
+    for (i = 0; i < count; i++) {
+        float best_amp = 0.0f; cf32 best = { 0.0f, 0.0f }; int idx = 0;
+        double a, c, s;
+        for (b = 0; b < n; b++) {
+            double re = 0.0, im = 0.0;
+            cf32 X; float amp;
+            for (k = 0; k < n; k++) {
+                const double xr = (double)(f->buf[i + k].re * f->win[k]), xi = (double)(f->buf[i + k].im * f->win[k]);
+                a = fwd * (double)((b * k) % n); c = cos(a); s = sin(a);
+                re += xr * c - xi * s;
+                im += xr * s + xi * c;
+            }
+            X.re = (float)re; X.im = (float)im;
+            amp = sqrtf(X.re * X.re + X.im * X.im);
+            if (b == 0 || amp > best_amp) { best_amp = amp; best = X; idx = b; } /* volk_32f_index_max_32u: first strict maximum */
+        }
+        a = bwd * (double)((idx * (n / 2)) % n); c = cos(a); s = sin(a);
+        out[i].re = (float)((double)best.re * c - (double)best.im * s);
+        out[i].im = (float)((double)best.re * s + (double)best.im * c);
+    }
+    memcpy(f->hist, f->buf + count, (size_t)(n - 1) * sizeof(cf32));
+    return count;
+}
+API void orc_fmif_destroy(orc_fmif* f) { if (f) { free(f->hist); free(f->win); free(f->buf); free(f); } }
+
 /* ------------------------------------------------------------------------------------------ */
 /* A16-A18. Demodulator front ends                                                             */
 /* ------------------------------------------------------------------------------------------ */

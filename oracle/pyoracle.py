@@ -179,6 +179,9 @@ class _Base:
     def squelch(self, level):
         return _Obj(self.lib, f"{self.prefix}_squelch", self._f("squelch_create", _vp, _d)(level))
 
+    def fm_if(self, bins):
+        return _Obj(self.lib, f"{self.prefix}_fmif", self._f("fmif_create", _vp, _i)(bins))
+
     def dcblock(self, rate):
         return _Obj(self.lib, f"{self.prefix}_dcblock", self._f("dcblock_create", _vp, _d)(rate))
 

@@ -30,6 +30,7 @@
 #include <dsp/compression/sample_stream_compressor.h>
 #include <dsp/noise_reduction/noise_blanker.h>
 #include <dsp/noise_reduction/squelch.h>
+#include <dsp/noise_reduction/fm_if.h>
 #include <dsp/compression/sample_stream_decompressor.h>
 
 #include <vector>
@@ -415,6 +416,11 @@ API void ref_nb_destroy(void* h) { delete (dsp::noise_reduction::NoiseBlanker*)h
 API void* ref_squelch_create(double level) { auto* s = new dsp::noise_reduction::Squelch(); s->init(NULL, level); return s; }
 API int ref_squelch_process(void* h, int count, complex_t* in, complex_t* out) { return ((dsp::noise_reduction::Squelch*)h)->process(count, in, out); }
 API void ref_squelch_destroy(void* h) { delete (dsp::noise_reduction::Squelch*)h; }
+
+// dsp::noise_reduction::FMIF (dsp/noise_reduction/fm_if.h) over oracle/shim/fftw3.h
+API void* ref_fmif_create(int bins) { return new dsp::noise_reduction::FMIF(NULL, bins); }
+API int ref_fmif_process(void* h, int count, complex_t* in, complex_t* out) { return ((dsp::noise_reduction::FMIF*)h)->process(count, in, out); }
+API void ref_fmif_destroy(void* h) { delete (dsp::noise_reduction::FMIF*)h; }
 
 // ---------------------------------------------------------------------------------------------
 // the complete demodulators (front end + post-detector stages), float output

@@ -567,6 +567,57 @@ __device__ __noinline__ void if_chain_run(float* __restrict__ r, float2* p, int 
     p[-1] = make_float2(r[IF_PREV_RE], r[IF_PREV_IM]);
 }
 
+static_assert(kIfMaxBlock == kTailSmemSamples / 2 - 2 * kIfMaxBins, "IF chain staging: two half areas with room for the FMIF history");
+
+// dsp::noise_reduction::FMIF::process (noise_reduction/fm_if.h:45-74) for a whole block, one output per thread: the
+// last `bins` samples under a Nuttall window, forward DFT (bins = 9, 15, 31, 32 in the radio module: direct
+// evaluation, every thread of a warp is at the same (bin, sample) pair so window and twiddle loads are broadcasts),
+// first strongest bin, and element bins/2 of the backward DFT of that single bin = X[idx] * e^{+2 pi j idx (bins/2) / bins}.
+// p[-(bins-1) .. n) holds history | block on return of the history load; q receives the outputs, q[-1] the previous one.
+__device__ __noinline__ void if_fmif_run(float* __restrict__ r, int bins, float2* p, float2* q, int n, float* scratch) {
+    const int tid = threadIdx.x;
+    float* win = scratch;                                        // [bins]
+    float2* tw = reinterpret_cast<float2*>(scratch + kIfMaxBins); // [bins]
+    for (int i = tid; i < bins; i += kTailThreads) {
+        win[i] = r[IF_WIN + i];
+        tw[i] = make_float2(r[IF_TW + 2 * i], r[IF_TW + 2 * i + 1]);
+    }
+    for (int i = tid; i < bins - 1; i += kTailThreads) p[i - (bins - 1)] = make_float2(r[IF_HIST + 2 * i], r[IF_HIST + 2 * i + 1]);
+    if (tid == 0) q[-1] = make_float2(r[IF_PREV_RE], r[IF_PREV_IM]); // the chain's previous output
+    __syncthreads();
+    const int half = bins / 2;
+    for (int i = tid; i < n; i += kTailThreads) {
+        const float2* x = p + i - (bins - 1);
+        float best_amp = 0.0f;
+        float2 best = make_float2(0.0f, 0.0f);
+        int best_b = 0;
+        for (int b = 0; b < bins; b++) {
+            float re = 0.0f, im = 0.0f;
+            int m = 0; // (b * k) mod bins
+            for (int k = 0; k < bins; k++) {
+                const float2 v = x[k];
+                const float w = win[k];
+                const float2 t = tw[m];
+                const float xr = __fmul_rn(v.x, w), xi = __fmul_rn(v.y, w);
+                re = fmaf(xr, t.x, fmaf(-xi, t.y, re));
+                im = fmaf(xr, t.y, fmaf(xi, t.x, im));
+                m += b; if (m >= bins) m -= bins;
+            }
+            const float amp = __fsqrt_rn(__fadd_rn(__fmul_rn(re, re), __fmul_rn(im, im)));
+            if (b == 0 || amp > best_amp) { best_amp = amp; best = make_float2(re, im); best_b = b; }
+        }
+        const float2 t = tw[(best_b * half) % bins]; // backward transform: conjugate twiddle
+        q[i] = make_float2(best.x * t.x + best.y * t.y, best.y * t.x - best.x * t.y);
+    }
+    __syncthreads();
+    // the last bins-1 input samples are the next block's history (fm_if.h:72)
+    for (int i = tid; i < bins - 1; i += kTailThreads) {
+        const float2 v = p[n - (bins - 1) + i];
+        r[IF_HIST + 2 * i] = v.x; r[IF_HIST + 2 * i + 1] = v.y;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kTailThreads, 4)
 tail_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
@@ -642,14 +693,20 @@ tail_kernel(const __grid_constant__ TailArgs a) {
     // The demod front end reads `src`: the VFO output itself, or -- with an IF chain record -- a copy in shared
     // memory that the chain's blocks have worked on (the iq result stays the raw VFO output = vfo->output).
     const float2* src = fin;
-    const bool if_on = vd.ifs != nullptr && g.n_final > 0 && g.n_final < kTailSmemSamples; // the engine refuses larger blocks
+    const bool if_on = vd.ifs != nullptr && g.n_final > 0 && g.n_final <= kIfMaxBlock; // the engine refuses larger blocks
     if (if_on) {
-        float2* p = tsm + 1; // p[-1] = last IF-chain output of the previous block
+        float2* p = tsm + kIfMaxBins; // p[-1] = last IF-chain output of the previous block (or FMIF history in front)
         __syncthreads();
         for (int i = tid; i < g.n_final; i += kTailThreads) p[i] = fin[i];
         __syncthreads();
         if (tid == 0) if_chain_run(vd.ifs, p, g.n_final);
         __syncthreads();
+        const int bins = (int)vd.ifs[IF_FMIF_BINS];
+        if (bins > 0) {
+            float2* q = p + kIfMaxBlock + kIfMaxBins; // second half of the staging area
+            if_fmif_run(vd.ifs, bins, p, q, g.n_final, ttaps);
+            p = q;
+        }
         src = p;
     }
     for (int i = tid; i < g.n_final; i += kTailThreads) {

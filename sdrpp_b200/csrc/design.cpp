@@ -62,6 +62,9 @@ int design_window(int type, float* buf, int size, bool centered) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// dsp::window::nuttall(n, N) (window/nuttall.h:5-8), as called by FMIF::initBuffers (noise_reduction/fm_if.h:111)
+double window_nuttall(double n, double N) { return cosine_sum(n, N, kNuttall, 4); }
+
 // Taps: dsp/taps/windowed_sinc.h:9-29 with window::nuttall, math/sinc.h, math/hz_to_rads.h
 // ---------------------------------------------------------------------------------------------
 int lowpass_tap_count(double transWidth, double sampleRate) {

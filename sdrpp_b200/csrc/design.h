@@ -40,6 +40,9 @@ ResamplerPlan design_resampler(double inSR, double outSR);
 // dsp::multirate::PolyphaseBank (dsp/multirate/polyphase_bank.h:15-48): bank[phase][j], tpp each
 std::vector<float> build_polyphase_bank(const std::vector<float>& taps, int interp, int* tpp);
 
+// dsp::window::nuttall (window/nuttall.h:5-8)
+double window_nuttall(double n, double N);
+
 // IQFrontEnd::genReshapeParams (signal_path/iq_frontend.h:56-60)
 void reshape_params(double sampleRate, int size, double rate, int* skip, int* nz);
 

@@ -1704,10 +1704,11 @@ int sdrpp_cuda_vfo_set_if_chain(sdrpp_cuda_frontend* fe, int id, const sdrpp_cud
     Vfo* v;
     if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
     if (!cfg) return fail(SDRPP_ERR_ARG, "null cfg");
-    if (v->plan->cap_final + 1 > 4600) return fail(SDRPP_ERR_ARG, "IF chain: the VFO's block output exceeds the tail kernel's staging area");
+    if (v->plan->cap_final > kIfMaxBlock) return fail(SDRPP_ERR_ARG, "IF chain: the VFO's block output exceeds the tail kernel's staging area");
+    if (cfg->fmif_bins != 0 && (cfg->fmif_bins < 2 || cfg->fmif_bins > kIfMaxBins)) return fail(SDRPP_ERR_ARG, "fmif_bins must be 0 or 2..64");
     float rec[IF_FLOATS] = { 0 };
     if (!v->if_state) {
-        if (!cfg->nb_enabled && !cfg->squelch_enabled) return SDRPP_OK;
+        if (!cfg->nb_enabled && !cfg->squelch_enabled && !cfg->fmif_bins) return SDRPP_OK;
         FE_TRY(fe, dev_alloc(&v->if_state, (size_t)IF_FLOATS));
         rec[IF_NB_AMP] = 1.0f; // noise_blanker.h:77; Squelch: _isMute = false (squelch.h:79)
         fe->layout_dirty = true;
@@ -1721,6 +1722,17 @@ int sdrpp_cuda_vfo_set_if_chain(sdrpp_cuda_frontend* fe, int id, const sdrpp_cud
     rec[IF_NB_LEVEL] = (float)cfg->nb_level;
     rec[IF_SQ_ON] = cfg->squelch_enabled ? 1.0f : 0.0f;
     rec[IF_SQ_LEVEL] = (float)cfg->squelch_level;
+    if ((int)rec[IF_FMIF_BINS] != cfg->fmif_bins) {
+        // setBins: destroyBuffers + initBuffers (fm_if.h:26-35,91-115) -- cleared history, Nuttall window over bins - 1
+        const int n = cfg->fmif_bins;
+        for (int i = IF_HIST; i < IF_FLOATS; i++) rec[i] = 0.0f;
+        for (int i = 0; i < n; i++) {
+            rec[IF_WIN + i] = (float)window_nuttall((double)i, (double)(n - 1));
+            const double a = -2.0 * 3.14159265358979323846 * (double)i / (double)n;
+            rec[IF_TW + 2 * i] = (float)cos(a); rec[IF_TW + 2 * i + 1] = (float)sin(a);
+        }
+        rec[IF_FMIF_BINS] = (float)n;
+    }
     FE_TRY(fe, cudaMemcpy(v->if_state, rec, sizeof(rec), cudaMemcpyHostToDevice));
     return SDRPP_OK;
 }

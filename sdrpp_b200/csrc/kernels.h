@@ -74,9 +74,13 @@ struct VfoDev {
 };
 
 // Radio IF chain record, one per VFO that has a block of the chain enabled (decoder_modules/radio/src/radio_module.h:
-// 73-78: NoiseBlanker -> Squelch in front of the demodulator). Configuration and state, 16 floats.
+// 73-78: NoiseBlanker -> Squelch -> FMIF in front of the demodulator). Configuration and state: 16 scalars, then the
+// FM IF noise reduction's input history (bins - 1 samples), window (bins floats) and DFT twiddles e^{-2 pi j m / bins}.
+constexpr int kIfMaxBins = 64;
+constexpr int kIfMaxBlock = 2176; // VFO output samples per block an IF chain can take (tail kernel staging area)
 enum { IF_NB_ON = 0, IF_NB_RATE, IF_NB_INVRATE, IF_NB_LEVEL, IF_NB_AMP, IF_SQ_ON, IF_SQ_LEVEL, IF_SQ_MUTE, IF_SQ_CNT,
-       IF_PREV_RE, IF_PREV_IM, IF_SQ_LAST_DB, IF_FLOATS = 16 };
+       IF_PREV_RE, IF_PREV_IM, IF_SQ_LAST_DB, IF_FMIF_BINS /* 0 = off */,
+       IF_HIST = 16, IF_WIN = IF_HIST + 2 * kIfMaxBins, IF_TW = IF_WIN + kIfMaxBins, IF_FLOATS = IF_TW + 2 * kIfMaxBins };
 
 constexpr int kStage1Warps = 8;     // warps per CTA, each owning R consecutive input rows
 

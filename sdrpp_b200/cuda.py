@@ -53,7 +53,8 @@ class PostCfg(C.Structure):
 
 
 class IfCfg(C.Structure):
-    _fields_ = [("nb_enabled", _i), ("nb_rate", _d), ("nb_level", _d), ("squelch_enabled", _i), ("squelch_level", _d)]
+    _fields_ = [("nb_enabled", _i), ("nb_rate", _d), ("nb_level", _d), ("squelch_enabled", _i), ("squelch_level", _d),
+                ("fmif_bins", _i)]
 
 
 class SdrppCudaError(RuntimeError):
@@ -390,9 +391,9 @@ class Frontend:
         cfg = PostCfg(int(enabled), int(fm_lowpass), int(am_agc_mode), int(ssb_agc), agc_attack, agc_decay, dc_block_rate, agc_gain)
         _check(lib().sdrpp_cuda_vfo_set_post(self.h, vid, C.byref(cfg)), "vfo_set_post")
 
-    def set_if_chain(self, vid, nb=False, nb_rate=500.0 / 24000.0, nb_level=10.0, squelch=False, squelch_level=-100.0):
-        """Radio IF chain in front of the demodulator: NoiseBlanker -> Squelch (radio_module.h:73-78)."""
-        cfg = IfCfg(int(nb), nb_rate, nb_level, int(squelch), squelch_level)
+    def set_if_chain(self, vid, nb=False, nb_rate=500.0 / 24000.0, nb_level=10.0, squelch=False, squelch_level=-100.0, fmif_bins=0):
+        """Radio IF chain in front of the demodulator: NoiseBlanker -> Squelch -> FMIF (radio_module.h:73-78)."""
+        cfg = IfCfg(int(nb), nb_rate, nb_level, int(squelch), squelch_level, int(fmif_bins))
         _check(lib().sdrpp_cuda_vfo_set_if_chain(self.h, vid, C.byref(cfg)), "vfo_set_if_chain")
 
     def squelch_state(self, vid):

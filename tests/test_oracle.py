@@ -144,6 +144,29 @@ def test_if_chain_port_vs_ref(port, ref, n):
         del a
 
 
+@pytest.mark.parametrize("bins", [9, 15, 31, 32])
+def test_fm_if_port_vs_ref(port, ref, bins):
+    """FMIF (noise_reduction/fm_if.h) over the DFT stand-in for FFTW: port and reference headers agree bit for bit."""
+    from tools.make_golden import if_input
+    a, b = ref.fm_if(bins), port.fm_if(bins)
+    for blk in if_input(5, 150, 70 + bins):
+        assert np.array_equal(_bits(a.process(blk)), _bits(b.process(blk)))
+
+
+def test_fm_if_tone_passes_with_window_gain(port):
+    """Known answer: a tone on bin 3 of 32 comes out as the same tone scaled by the window's sum, delayed by bins/2 - 1
+    samples -- the backward DFT's element bins/2 re-centres the phase at the middle of the window."""
+    bins, n = 32, 256
+    t = np.arange(n + bins)
+    x = np.exp(2j * np.pi * 3 * t / bins).astype(np.complex64)
+    f = port.fm_if(bins)
+    y = f.process(x)[bins:]          # past the start-up (zero history)
+    k = np.arange(bins)
+    w = sum(c * s * np.cos(2 * np.pi * i * k / (bins - 1)) for i, (c, s) in enumerate(zip([0.355768, 0.487396, 0.144232, 0.012604], [1, -1, 1, -1])))
+    want = w.sum() * x[bins - (bins // 2 - 1):][:len(y)]
+    assert np.max(np.abs(y - want)) < 2e-5 * w.sum()
+
+
 # ---- golden vectors generated from the compiled reference (travel to the GPU box) -----------------------------
 def _golden_cases():
     p = os.path.join(GOLD, "manifest.json")
@@ -212,6 +235,8 @@ def test_port_matches_golden(port, case):
         y_sq = [sq.process(b) for b in y_nb]
         assert np.array_equal(_bits(np.concatenate(y_nb)), _bits(data["nb"]))
         assert np.array_equal(_bits(np.concatenate(y_sq)), _bits(data["out"]))
+        fm = port.fm_if(15)
+        assert np.array_equal(_bits(np.concatenate([fm.process(b) for b in y_sq])), _bits(data["fmif15"]))
         muted = [not b.any() for b in y_sq]
         assert any(muted) and not all(muted)  # the fixture exercises both squelch states
     else:

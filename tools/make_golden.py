@@ -147,7 +147,10 @@ def main():
     nb, sq = ref.noise_blanker(500.0 / 48000.0, 3.0), ref.squelch(-20.0)
     y_nb = [nb.process(b) for b in x]
     y_sq = [sq.process(b) for b in y_nb]
-    add("if_chain_nb_squelch", "if_chain", (500.0 / 48000.0, 3.0, -20.0, 20, 240), {"nb": np.concatenate(y_nb), "out": np.concatenate(y_sq)}, seed=13)
+    fm = ref.fm_if(15)
+    y_fm = [fm.process(b) for b in y_sq]
+    add("if_chain_nb_squelch", "if_chain", (500.0 / 48000.0, 3.0, -20.0, 20, 240),
+        {"nb": np.concatenate(y_nb), "out": np.concatenate(y_sq), "fmif15": np.concatenate(y_fm)}, seed=13)
 
     json.dump({"generator": "tools/make_golden.py", "source": ref.lib.ref_build_info.restype and "oracle/_ref/libsdrpp_ref.so (reference dsp/ headers, IEEE flags)",
                "cases": cases}, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
