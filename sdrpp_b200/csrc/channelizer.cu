@@ -145,6 +145,7 @@ int stage1_tap_offset(int ratio) {
             }
         }
         if (cudaMemcpyToSymbol(c_s1_taps, pool.data(), sizeof(float) * kS1PoolFloats) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) return -1; // complete before any non-blocking stream reads it
         g_s1_uploaded[dev] = true;
     }
     for (const S1PoolEntry& e : g_s1_pool) if (e.ratio == ratio) return e.off;

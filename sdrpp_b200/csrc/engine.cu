@@ -37,8 +37,25 @@ static uint64_t turns_to_u64(double turns) {
 template <class T>
 static cudaError_t dev_alloc(T** p, size_t n, bool zero = true) {
     cudaError_t e = cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+    // cudaMemset on device memory returns before the fill has run, and the legacy default stream it runs on is not
+    // ordered against this library's non-blocking streams: wait for it, or a kernel / copy enqueued right after the
+    // allocation can be overtaken by the fill (seen as a VFO table zeroed after its upload, and as fp16 planes losing
+    // their low half on the first tensor-core block). Allocation happens on configuration paths only.
     if (e == cudaSuccess && zero) e = cudaMemset(*p, 0, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess && zero) e = cudaStreamSynchronize(cudaStreamLegacy);
     return e;
+}
+
+// Configuration-path fills and uploads that are complete on return: the synchronous runtime calls may return while the
+// fill / the DMA out of the runtime's staging buffer is still queued on the legacy default stream, which this library's
+// non-blocking streams are not ordered against.
+static cudaError_t memset_sync(void* p, int v, size_t bytes) {
+    cudaError_t e = cudaMemset(p, v, bytes);
+    return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e;
+}
+static cudaError_t upload_sync(void* dst, const void* src, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -161,7 +178,7 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
     }
     if (p.s1_fir && s1t_supported(p.s1_T, p.s1_D)) {
         if (dev_alloc(&p.d_s1_taps, p.s1_taps.size(), false) != cudaSuccess ||
-            cudaMemcpy(p.d_s1_taps, p.s1_taps.data(), p.s1_taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            upload_sync(p.d_s1_taps, p.s1_taps.data(), p.s1_taps.size() * sizeof(float)) != cudaSuccess) {
             *err = std::string("tap upload: ") + cudaGetErrorString(cudaGetLastError());
             return SDRPP_ERR_CUDA;
         }
@@ -170,7 +187,7 @@ static int build_plan(VfoPlan& p, double inSR, double outSR, double bw, int max_
     }
     for (auto& s : p.tail) {
         if (dev_alloc(&s.d_taps, s.taps.size(), false) != cudaSuccess ||
-            cudaMemcpy(s.d_taps, s.taps.data(), s.taps.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            upload_sync(s.d_taps, s.taps.data(), s.taps.size() * sizeof(float)) != cudaSuccess) {
             *err = std::string("tap upload: ") + cudaGetErrorString(cudaGetLastError());
             return SDRPP_ERR_CUDA;
         }
@@ -351,7 +368,7 @@ static int configure_preproc(sdrpp_cuda_frontend* fe) {
         for (const DecimStage& s : fe->fe_stages) {
             float* t = nullptr; float2* b = nullptr;
             FE_TRY(fe, dev_alloc(&t, (size_t)s.ntaps, false));
-            FE_TRY(fe, cudaMemcpy(t, s.taps, sizeof(float) * s.ntaps, cudaMemcpyHostToDevice));
+            FE_TRY(fe, upload_sync(t, s.taps, sizeof(float) * s.ntaps));
             FE_TRY(fe, dev_alloc(&b, (size_t)(s.ntaps - 1) + (size_t)cap + 8));
             fe->fe_taps.push_back(t); fe->fe_buf.push_back(b); fe->fe_offset.push_back(0);
             cap = cap / s.decimation + 2;
@@ -374,7 +391,7 @@ static int configure_zoom(sdrpp_cuda_frontend* fe) {
     std::vector<int> idx;
     fe->zoom_ranged = zoom_indices(fe->zoom_view[0], fe->zoom_view[1], fe->zoom_view[2], fe->cfg.fft_size, fe->zoom_out, &idx);
     FE_TRY(fe, dev_alloc(&fe->d_zoom_idx, idx.size(), false));
-    FE_TRY(fe, cudaMemcpy(fe->d_zoom_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    FE_TRY(fe, upload_sync(fe->d_zoom_idx, idx.data(), idx.size() * sizeof(int)));
     FE_TRY(fe, dev_alloc(&fe->d_zoom, (size_t)fe->rows_cap * fe->zoom_out, false));
     for (int i = 0; i < kSets; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].zoom, (size_t)fe->rows_cap * fe->zoom_out * sizeof(float)));
     return SDRPP_OK;
@@ -401,7 +418,7 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     std::vector<float> w((size_t)fe->nz + 2);
     design_window(fe->cfg.fft_window, w.data(), fe->nz, true);
     FE_TRY(fe, dev_alloc(&fe->d_window, (size_t)fe->nz, false));
-    FE_TRY(fe, cudaMemcpy(fe->d_window, w.data(), sizeof(float) * fe->nz, cudaMemcpyHostToDevice));
+    FE_TRY(fe, upload_sync(fe->d_window, w.data(), sizeof(float) * fe->nz));
     int rows = fe->cfg.max_fft_rows > 0 ? fe->cfg.max_fft_rows : (int)(fe->cfg.max_block / interval + 2);
     fe->rows_cap = rows;
     FE_TRY(fe, dev_alloc(&fe->d_rows, (size_t)rows * N, false));
@@ -627,12 +644,12 @@ static int apply_post(sdrpp_cuda_frontend* fe, Vfo& v) {
     FE_TRY(fe, dev_alloc(&v.post_state, n));
     if (!taps.empty()) {
         FE_TRY(fe, dev_alloc(&v.post_taps, taps.size(), false));
-        FE_TRY(fe, cudaMemcpy(v.post_taps, taps.data(), taps.size() * sizeof(float), cudaMemcpyHostToDevice));
+        FE_TRY(fe, upload_sync(v.post_taps, taps.data(), taps.size() * sizeof(float)));
     }
     // AGC::init(.., maxGain = 10e6, .., initGain = INFINITY): amp = setPoint / initGain = 0, gain = min(initGain, maxGain)
     float init[5] = { 0.0f, (float)10e6, 0.0f, (float)10e6, 0.0f };
     if (v.post.agc_gain > 0.0f) init[1] = v.post.agc_gain; // setAGCGain (am.h:69-73, ssb.h)
-    FE_TRY(fe, cudaMemcpy(v.post_state, init, sizeof(init), cudaMemcpyHostToDevice));
+    FE_TRY(fe, upload_sync(v.post_state, init, sizeof(init)));
     return SDRPP_OK;
 }
 
@@ -1259,7 +1276,7 @@ int sdrpp_cuda_spectrum_device(int N, int nz, int frames, long long frame_stride
     if (window && (g_os.win_n != N || g_os.win_host.size() != (size_t)nz || memcmp(g_os.win_host.data(), window, (size_t)nz * 4) != 0)) {
         SDRPP_CUDA_TRY(cudaStreamSynchronize(st));
         SDRPP_CUDA_TRY(os_reserve(&g_os.d_w, &g_os.cap_w, (size_t)nz * 4));
-        SDRPP_CUDA_TRY(cudaMemcpy(g_os.d_w, window, (size_t)nz * 4, cudaMemcpyHostToDevice));
+        SDRPP_CUDA_TRY(upload_sync(g_os.d_w, window, (size_t)nz * 4));
         g_os.win_host.assign(window, window + nz);
         g_os.win_n = N;
     }
@@ -1591,7 +1608,7 @@ int sdrpp_cuda_vfo_set_bandwidth(sdrpp_cuda_frontend* fe, int id, double bw) {
     const uint32_t offs[2] = { op->tail.size() == 1 ? op->s1_off[0] : nf.in_off, op->tail.size() == 1 ? op->s1_off[1] : nf.in_off };
     if (nf.T > of.T) {
         for (int r = 0; r < (op->tail.size() == 1 ? 2 : 1); r++)
-            FE_TRY(fe, cudaMemset(v->slab + offs[r] - (nf.T - 1), 0, sizeof(float2) * (size_t)(nf.T - of.T)));
+            FE_TRY(fe, memset_sync(v->slab + offs[r] - (nf.T - 1), 0, sizeof(float2) * (size_t)(nf.T - of.T)));
     }
     const GroupState st = fe->groups[(size_t)v->group].st;
     remove_from_group(fe, id);
@@ -1612,7 +1629,7 @@ int sdrpp_cuda_vfo_reset(sdrpp_cuda_frontend* fe, int id) {
     Vfo* v;
     if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
     remove_from_group(fe, id);
-    FE_TRY(fe, cudaMemset(v->slab, 0, v->plan->slab_elems * sizeof(float2)));
+    FE_TRY(fe, memset_sync(v->slab, 0, v->plan->slab_elems * sizeof(float2)));
     // xlator.reset(): phase = 1 at the next sample (frequency_xlator.h:31-34)
     v->phi_ref = 0; v->n_ref = fe->abs_pos;
     join_group(fe, id, fe->abs_pos);
@@ -1733,7 +1750,7 @@ int sdrpp_cuda_vfo_set_if_chain(sdrpp_cuda_frontend* fe, int id, const sdrpp_cud
         }
         rec[IF_FMIF_BINS] = (float)n;
     }
-    FE_TRY(fe, cudaMemcpy(v->if_state, rec, sizeof(rec), cudaMemcpyHostToDevice));
+    FE_TRY(fe, upload_sync(v->if_state, rec, sizeof(rec)));
     return SDRPP_OK;
 }
 

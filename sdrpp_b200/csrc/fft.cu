@@ -52,7 +52,8 @@ static cudaError_t upload_table(float2** dst, int count, double denom) {
     }
     cudaError_t e = cudaMalloc((void**)dst, sizeof(float2) * (size_t)count);
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dst, h.data(), sizeof(float2) * (size_t)count, cudaMemcpyHostToDevice);
+    e = cudaMemcpy(*dst, h.data(), sizeof(float2) * (size_t)count, cudaMemcpyHostToDevice);
+    return e == cudaSuccess ? cudaStreamSynchronize(cudaStreamLegacy) : e; // complete before any non-blocking stream reads it
 }
 
 static cudaError_t get_tables(int N, int N1, int N2, SpectrumTables* out) {
