@@ -410,10 +410,10 @@ constexpr int kTailTapFloats = 3072;   // staged taps per stage
 // Stage one chunk of a stage's input [first, first+n) from the slab (L2) into shared memory.
 // Decimating FIRs store it transposed by D -- element i at [i % D][i / D] with an odd row stride -- so
 // that consecutive outputs (lanes) read consecutive addresses for every tap; others keep natural order.
-__device__ __forceinline__ void tail_stage_in(float2* sm, const float2* src, int n, int D, int qs) {
+__device__ __forceinline__ void tail_stage_in(float2* sm, const float2* src, int n, int D, int qs, bool wait = true) {
     const int lg = 31 - __clz(D); // D is a power of two (every PowerDecimator stage decimates by 2, 4, 8, ...)
     for (int i = threadIdx.x; i < n; i += kTailThreads) cp_async8(sm + (i & (D - 1)) * qs + (i >> lg), src + i);
-    cp_async_wait_all();
+    if (wait) cp_async_wait_all();
 }
 
 // FIR / decimating FIR stage, register-blocked: a thread owns OB = 4 consecutive outputs, so a staged sample is
@@ -447,7 +447,7 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
                 if (i < n) cp_async8(dst, src + i);
                 else *dst = make_float2(0.0f, 0.0f);
             }
-            cp_async_wait_all();
+            // not waited for here: the first tap table below is built while the copies are in flight
         }
         int KS = 1;
         while (KS < 8 && nthr * KS * 2 <= NT && SQ >= 8 * KS * 2) KS *= 2;
@@ -473,6 +473,7 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
                 }
                 tt[e] = h;
             }
+            if (q0 == 0) cp_async_wait_all();
             __syncthreads(); // samples (first step) and the table are staged
             if (active) {
                 const int r0 = ks * Sk + q0;
@@ -641,7 +642,7 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         } else {
             // polyphase resampler: consecutive outputs use different tap phases and input strides; one output per thread
             const bool taps_staged = (long long)st.interp * T <= kTailTapFloats;
-            if (taps_staged) for (int i = tid; i < st.interp * T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
+            bool taps_pending = taps_staged; // staged while the first chunk's copies are in flight
             int ch = (int)(((long long)(kTailSmemSamples - T - 2) * st.interp) / st.D);
             if (ch >= kTailThreads) ch -= ch % kTailThreads;
             if (ch < 1) ch = 1;
@@ -651,7 +652,12 @@ tail_kernel(const __grid_constant__ TailArgs a) {
                 const long long P1 = (long long)st.phase + (long long)(o1 - 1) * st.D;
                 const int first = st.offset + (int)(P0 / st.interp);
                 const int last = st.offset + (int)(P1 / st.interp) + T - 1;
-                tail_stage_in(tsm, buf + first, last - first + 1, 1, 0);
+                tail_stage_in(tsm, buf + first, last - first + 1, 1, 0, false);
+                if (taps_pending) {
+                    for (int i = tid; i < st.interp * T; i += kTailThreads) ttaps[i] = __ldg(st.taps + i);
+                    taps_pending = false;
+                }
+                cp_async_wait_all();
                 __syncthreads();
                 for (int o = o0 + tid; o < o1; o += kTailThreads) {
                     // closed form of polyphase_resampler.h:75-93
