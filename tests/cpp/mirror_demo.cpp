@@ -6,8 +6,12 @@
 //   mirror_demo run <in.cf32> <sr> <block> <fftN> <outprefix> <outSR> <bw> <off1> [<off2> ...]
 //      writes <outprefix>.vfo<i>.cf32 (attached VFOs), <outprefix>.solo.cf32 (standalone RxVFO of VFO 0)
 //      and <outprefix>.rows.f32 (spectrum rows, BH7 window, saturated rate sr/fftN)
+//   mirror_demo pcm <in.cf32> <pcmType> <out.packet> <out.cf32>
+//      SampleStreamCompressor::process on the whole file, then SampleStreamDecompressor::process on that packet
 #define SDRPP_SIGPATH_IMPLEMENTATION
 #include <signal_path/signal_path.h>
+#include <dsp/compression/sample_stream_compressor.h>
+#include <dsp/compression/sample_stream_decompressor.h>
 
 #include <atomic>
 #include <cstdio>
@@ -85,8 +89,27 @@ static int hostSelfTest() {
     return sum == expect ? 0 : 1;
 }
 
+static int pcmRoundTrip(const char* inPath, int type, const char* packetPath, const char* outPath) {
+    FILE* f = fopen(inPath, "rb");
+    if (!f) { return 66; }
+    std::vector<dsp::complex_t> x(1 << 20);
+    const int count = (int)fread(x.data(), sizeof(dsp::complex_t), x.size(), f);
+    fclose(f);
+    if (sdrpp_cuda_init(0) != 0) { fprintf(stderr, "%s\n", sdrpp_cuda_last_error()); return 70; }
+    std::vector<uint8_t> packet(8 + (size_t)count * sizeof(dsp::complex_t));
+    const int bytes = dsp::compression::SampleStreamCompressor::process(count, (dsp::compression::PCMType)type, x.data(), packet.data());
+    if (bytes <= 0) { fprintf(stderr, "%s\n", sdrpp_cuda_last_error()); return 70; }
+    std::vector<dsp::complex_t> y((size_t)count + 1);
+    dsp::compression::SampleStreamDecompressor dec;
+    const int n = dec.process(bytes, packet.data(), y.data());
+    f = fopen(packetPath, "wb"); fwrite(packet.data(), 1, (size_t)bytes, f); fclose(f);
+    f = fopen(outPath, "wb"); fwrite(y.data(), sizeof(dsp::complex_t), (size_t)n, f); fclose(f);
+    return n == count ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "host") { return hostSelfTest(); }
+    if (argc == 6 && std::string(argv[1]) == "pcm") { return pcmRoundTrip(argv[2], atoi(argv[3]), argv[4], argv[5]); }
     if (argc < 10 || std::string(argv[1]) != "run") { fprintf(stderr, "usage: see source\n"); return 64; }
     const std::string inPath = argv[2], prefix = argv[6];
     const double sr = atof(argv[3]);

@@ -62,3 +62,22 @@ def test_module_style_usage_matches_oracle(demo, gpu, port, tmp_path):
         _, _, row64 = port.spectrum(N, x[f * N:(f + 1) * N], w)
         mask = row64 >= row64.max() - 80.0
         assert np.abs(rows[f] - row64)[mask].max() <= 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ptype", [0, 1, 2])
+def test_compression_blocks_match_oracle(demo, gpu, port, tmp_path, ptype):
+    """dsp::compression::SampleStreamCompressor::process / SampleStreamDecompressor::process of the mirror, called the
+    way core/src/server.cpp and the sdrpp_server source call them: packet and samples bit-identical to the oracle."""
+    from tools.make_golden import pcm_input
+    x = pcm_input(30001, 50 + ptype)
+    inp = tmp_path / "in.cf32"
+    x.tofile(inp)
+    pk, out = tmp_path / "pk.bin", tmp_path / "out.cf32"
+    r = subprocess.run([demo, "pcm", str(inp), str(ptype), str(pk), str(out)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    packet = np.fromfile(pk, dtype=np.uint8)
+    want = port.pcm_compress(ptype, x)
+    assert np.array_equal(packet, want)
+    y = np.fromfile(out, dtype=np.complex64)
+    assert np.array_equal(y.view(np.uint32), port.pcm_decompress(want).view(np.uint32))
