@@ -282,33 +282,45 @@ def run_gpu(args, rank, world, local_rank):
     d_blocks = torch.empty((NB, BLOCK, 2), dtype=torch.float32, device=dev)  # > L2 (126 MB) when NB >= 32
     if rank == 0:
         d_blocks.copy_(torch.from_numpy(host.view(np.float32).reshape(NB, BLOCK, 2)))
+    # Multi-GPU: the IQ stream is broadcast in buckets of KB consecutive blocks (one NCCL call per bucket, straight out
+    # of the source buffer on the ingest rank, into one of two staging buckets elsewhere). The enqueue cost of a
+    # collective (~25-30 us of host time through torch.distributed) is what bounded the loop with one broadcast per
+    # block (tools/mgpu_probe.py); the bucket size is chosen for that latency, not for the link. Every block is
+    # still submitted on its own.
+    KB = max(1, min(args.bcast_blocks, NB)) if world > 1 else 1
+    while NB % KB:
+        KB -= 1
     if world > 1:
-        d_stage = [torch.empty((BLOCK, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        d_stage = [torch.empty((KB, BLOCK, 2), dtype=torch.float32, device=dev) for _ in range(2)]
     torch.cuda.synchronize()
 
-    consumed = [None, None]  # per staging buffer: event after which the front end no longer reads it
+    consumed = [None, None]  # per staging bucket: event after which the front end no longer reads it
+    pos = [0]                # blocks submitted in the current phase (every phase starts on a bucket boundary)
 
-    def step_device(i):
-        blk = d_blocks[i % NB]
+    def step_device(_i=None):
+        i = pos[0]
+        pos[0] += 1
         if world > 1:
-            # NVLink broadcast of the IQ block from the ingest GPU, then every rank channelizes its VFOs.
-            # Two staging buffers: the broadcast of block i+1 overlaps the kernels of block i.
-            k = i % 2
-            buf = d_stage[k]
-            cur = torch.cuda.current_stream()
-            if consumed[k] is not None:
-                cur.wait_event(consumed[k])
-            if rank == 0:
-                buf.copy_(blk, non_blocking=True)
-            dist.broadcast(buf, src=0)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            st.wait_event(ev)
-            fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
-            consumed[k] = torch.cuda.Event()
-            consumed[k].record(st)
-        else:
+            k = (i // KB) % 2
+            j = i % KB
+            base = (i - j) % NB
+            if j == 0:
+                # NVLink broadcast of the next KB blocks from the ingest GPU; the broadcast of bucket b+1 overlaps the
+                # kernels of bucket b
+                cur = torch.cuda.current_stream()
+                if consumed[k] is not None:
+                    cur.wait_event(consumed[k])
+                dist.broadcast(d_blocks[base:base + KB] if rank == 0 else d_stage[k], src=0)
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                st.wait_event(ev)
+            blk = d_blocks[base + j] if rank == 0 else d_stage[k][j]
             fe.submit_device(cuda.FMT_CF32, blk.data_ptr(), BLOCK)
+            if j == KB - 1:
+                consumed[k] = torch.cuda.Event()
+                consumed[k].record(st)
+        else:
+            fe.submit_device(cuda.FMT_CF32, d_blocks[i % NB].data_ptr(), BLOCK)
 
     def barrier():
         if world > 1:
@@ -320,6 +332,7 @@ def run_gpu(args, rank, world, local_rank):
     for i in range(args.warmup):
         step_device(i)
     barrier()
+    pos[0] = 0
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -347,6 +360,9 @@ def run_gpu(args, rank, world, local_rank):
     fe.set_profiling(True)
     fam = np.zeros(4)
     nprof = max(4, min(args.steps, 16))
+    barrier()
+    pos[0] = 0
+    consumed[0] = consumed[1] = None
     for i in range(nprof):
         step_device(i)
         fe.wait()
@@ -418,9 +434,12 @@ def run_gpu(args, rank, world, local_rank):
             pin.array[:] = host[0]
             pin_t = torch.from_numpy(pin.array.view(np.float32).reshape(BLOCK, 2))
 
+        barrier()
+        consumed[0] = consumed[1] = None
+
         def step_e2e(i):
             k = i % 2
-            buf = d_stage[k]
+            buf = d_stage[k][0]   # end to end keeps one broadcast per block: each block comes from the host as it is submitted
             cur = torch.cuda.current_stream()
             if consumed[k] is not None:
                 cur.wait_event(consumed[k])
@@ -574,7 +593,7 @@ def run_gpu(args, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "block": BLOCK, "vfos": NVFO, "fft": FFT_N, "vfos_per_gpu": len(mine),
                        "l2": f"inputs cycle through {NB} distinct blocks = {NB * BLOCK * 8 / 1e6:.0f} MB (> 126 MB L2)",
-                       "parallelism": f"vfo-shard x{world} + NCCL broadcast" if world > 1 else "1 GPU"},
+                       "parallelism": f"vfo-shard x{world} + NCCL broadcast of {KB}-block buckets" if world > 1 else "1 GPU"},
             "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roof, "roofline_spectrum": roof_fft, "spectrum_batched": spec_batched,
             "kernel_ms_per_step": {"ingest": float(ingest_ms), "spectrum": float(fft_ms), "channelizer_stage1": float(s1_ms), "channelizer_tail": float(tail_ms)},
@@ -595,6 +614,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--input-blocks", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bcast-blocks", type=int, default=4, help="N > 1: IQ blocks per NCCL broadcast (bucket size)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
