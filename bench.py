@@ -287,9 +287,7 @@ def run_gpu(args, rank, world, local_rank):
     # collective (~25-30 us of host time through torch.distributed) is what bounded the loop with one broadcast per
     # block (tools/mgpu_probe.py); the bucket size is chosen for that latency, not for the link. Every block is
     # still submitted on its own.
-    KB = max(1, min(args.bcast_blocks, NB)) if world > 1 else 1
-    while NB % KB:
-        KB -= 1
+    KB = shard.fit_bucket(args.bcast_blocks, NB) if world > 1 else 1
     if world > 1:
         d_stage = [torch.empty((KB, BLOCK, 2), dtype=torch.float32, device=dev) for _ in range(2)]
     torch.cuda.synchronize()
@@ -301,9 +299,7 @@ def run_gpu(args, rank, world, local_rank):
         i = pos[0]
         pos[0] += 1
         if world > 1:
-            k = (i // KB) % 2
-            j = i % KB
-            base = (i - j) % NB
+            k, j, base = shard.bucket_slot(i, KB, NB)
             if j == 0:
                 # NVLink broadcast of the next KB blocks from the ingest GPU; the broadcast of bucket b+1 overlaps the
                 # kernels of bucket b

@@ -40,3 +40,20 @@ def broadcast_block(tensor, src=0):
     import torch.distributed as dist
     dist.broadcast(tensor, src=src)
     return tensor
+
+
+def bucket_slot(i, bucket_blocks, source_blocks):
+    """Where block i of a phase lives when the stream is broadcast in buckets of `bucket_blocks` consecutive blocks out
+    of a circular source of `source_blocks` blocks (a multiple of the bucket size): (staging bucket 0/1, index inside the
+    bucket, index of the bucket's first block in the source)."""
+    assert bucket_blocks >= 1 and source_blocks % bucket_blocks == 0
+    j = i % bucket_blocks
+    return (i // bucket_blocks) % 2, j, (i - j) % source_blocks
+
+
+def fit_bucket(bucket_blocks, source_blocks):
+    """Largest bucket size <= the requested one that divides the source length."""
+    kb = max(1, min(int(bucket_blocks), int(source_blocks)))
+    while source_blocks % kb:
+        kb -= 1
+    return kb

@@ -64,3 +64,49 @@ def test_gloo_world2_shard_and_broadcast():
         assert same, f"rank {rank}: broadcast block differs"
         assert owned == [1] * 40
         assert n == 20
+
+
+def test_bucket_indexing():
+    assert shard.fit_bucket(4, 32) == 4 and shard.fit_bucket(8, 20) == 5 and shard.fit_bucket(99, 6) == 6 and shard.fit_bucket(0, 6) == 1
+    seen = []
+    for i in range(40):
+        k, j, base = shard.bucket_slot(i, 4, 8)
+        assert k == (i // 4) % 2 and 0 <= j < 4 and base % 4 == 0 and base < 8
+        seen.append(base + j)
+    assert seen == [i % 8 for i in range(40)]  # blocks are consumed in stream order
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        NB, KB, n = 8, 4, 64
+        src = torch.arange(NB * n * 2, dtype=torch.float32).reshape(NB, n, 2) if rank == 0 else None
+        stage = [torch.zeros(KB, n, 2) for _ in range(2)]
+        got = []
+        for i in range(20):  # the loop of bench.py's step_device for N > 1, without the streams
+            k, j, base = shard.bucket_slot(i, KB, NB)
+            if j == 0:
+                shard.broadcast_block(src[base:base + KB] if rank == 0 else stage[k], src=0)
+            blk = src[base + j] if rank == 0 else stage[k][j]
+            got.append(float(blk[0, 0]))
+        q.put((rank, got))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_bucketed_broadcast():
+    """Every rank submits the same block sequence when the stream is broadcast in 4-block buckets."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = [float((i % 8) * 64 * 2) for i in range(20)]
+    assert res[0] == want and res[1] == want
