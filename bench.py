@@ -354,7 +354,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- per-kernel-family device time (CUDA events on the front end's stream, inside the library) ----
     fe.set_profiling(True)
-    fam = np.zeros(4)
+    fam_steps = []
     nprof = max(4, min(args.steps, 16))
     barrier()
     pos[0] = 0
@@ -362,8 +362,10 @@ def run_gpu(args, rank, world, local_rank):
     for i in range(nprof):
         step_device(i)
         fe.wait()
-        fam += np.array(fe.kernel_ms())
-    fam /= nprof
+        fam_steps.append(fe.kernel_ms())
+    # median over the profiled steps: a bracket that happens to span a host hiccup (the launches of a family are enqueued
+    # one by one between its two events) would otherwise leak into the roofline figures
+    fam = np.median(np.array(fam_steps), axis=0)
     fe.set_profiling(False)
 
     # ---- end to end through the host API (e2e): pinned host block -> H2D -> path -> D2H results --------
@@ -390,13 +392,14 @@ def run_gpu(args, rank, world, local_rank):
             step_host(i); consume()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        step_host(0)
-        step_host(1)
-        for i in range(2, args.steps):
-            step_host(i)      # block i is copied in while blocks i-2 and i-1 are still in flight (three result sets)
-            consume()         # results of block i-2
-        consume()
-        consume()
+        ahead = max(1, min(args.e2e_ahead, 4, args.steps))
+        for i in range(ahead):
+            step_host(i)
+        for i in range(ahead, args.steps):
+            step_host(i)      # block i is copied in while blocks i-ahead .. i-1 are still in flight (five result sets)
+            consume()         # results of block i-ahead
+        for i in range(ahead):
+            consume()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         d2h = 0
@@ -610,6 +613,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--input-blocks", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-ahead", type=int, default=4, help="blocks submitted ahead of the one being consumed in the end-to-end leg (1..4)")
     ap.add_argument("--bcast-blocks", type=int, default=4, help="N > 1: IQ blocks per NCCL broadcast (bucket size)")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -192,9 +192,10 @@ SDRPP_API int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt
  * is converted on the device inside the ingest kernel. Returns the number of samples submitted
  * (0 = nothing submitted: unknown sample type or empty payload), < 0 on error. */
 SDRPP_API int sdrpp_cuda_frontend_submit_pcm(sdrpp_cuda_frontend* fe, const void* packet, int nbytes);
-/* Block until the OLDEST block not yet waited for has its results on the host. Up to three blocks may be in flight
- * (submit, submit, submit, wait, submit, wait, ...): with two or more submitted ahead, the host-to-device copy of a
- * block never waits for an earlier block's results to reach the host. */
+/* Block until the OLDEST block not yet waited for has its results on the host. Up to five blocks may be in flight
+ * (submit x5, wait, submit, wait, ...): with blocks submitted ahead, the host-to-device copy of a block never waits for an
+ * earlier block's results to reach the host, and the end-to-end rate is no longer bound by one block's latency
+ * (copy in + kernels + copy out) divided by the blocks in flight. A sixth submit blocks until the oldest is done. */
 SDRPP_API int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe);
 /* Skip the device->host copies of results (kernel-only timing); default 1 = copy. */
 SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled);

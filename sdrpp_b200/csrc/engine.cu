@@ -257,7 +257,7 @@ struct ResultSet {
 
 using namespace sdrpp;
 
-constexpr int kSets = 3; // result sets / raw staging buffers / result arenas
+constexpr int kSets = 5; // result sets / raw staging buffers / result arenas: blocks the caller may have in flight
 
 struct sdrpp_cuda_frontend {
     int device = 0;
