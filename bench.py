@@ -363,9 +363,16 @@ def run_gpu(args, rank, world, local_rank):
         step_device(i)
         fe.wait()
         fam_steps.append(fe.kernel_ms())
-    # median over the profiled steps: a bracket that happens to span a host hiccup (the launches of a family are enqueued
-    # one by one between its two events) would otherwise leak into the roofline figures
-    fam = np.median(np.array(fam_steps), axis=0)
+    # mean over the profiled steps without outliers: a bracket that happens to span a host hiccup (the launches of a
+    # family are enqueued one by one between its two events) would otherwise leak into the roofline figures. The plain
+    # mean is kept otherwise because the spectrum family is empty in the steps that complete no frame.
+    fs = np.array(fam_steps)
+    fam = np.zeros(fs.shape[1])
+    for c in range(fs.shape[1]):
+        col = fs[:, c]
+        pos = col[col > 0]
+        keep = col[col <= 4.0 * np.median(pos)] if len(pos) else col
+        fam[c] = float(np.mean(keep)) if len(keep) else 0.0
     fe.set_profiling(False)
 
     # ---- end to end through the host API (e2e): pinned host block -> H2D -> path -> D2H results --------
