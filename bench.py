@@ -443,18 +443,21 @@ def run_gpu(args, rank, world, local_rank):
         barrier()
         consumed[0] = consumed[1] = None
 
+        nslots = 2 * KB           # the staging buckets of the device-resident leg, used block by block here
+        cons_e = [None] * nslots
+
         def step_e2e(i):
-            k = i % 2
-            buf = d_stage[k][0]   # end to end keeps one broadcast per block: each block comes from the host as it is submitted
+            sl = i % nslots
+            buf = d_stage[sl // KB][sl % KB]   # end to end keeps one broadcast per block: each block comes from the host as it is submitted
             cur = torch.cuda.current_stream()
-            if consumed[k] is not None:
-                cur.wait_event(consumed[k])
+            if cons_e[sl] is not None:
+                cur.wait_event(cons_e[sl])
             if rank == 0:
                 buf.copy_(pin_t, non_blocking=True)   # H2D from pinned host memory, every step
             dist.broadcast(buf, src=0)
             ev = torch.cuda.Event(); ev.record(cur); st.wait_event(ev)
             fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
-            consumed[k] = torch.cuda.Event(); consumed[k].record(st)
+            cons_e[sl] = torch.cuda.Event(); cons_e[sl].record(st)
 
         sink = 0.0
 
@@ -467,12 +470,15 @@ def run_gpu(args, rank, world, local_rank):
         for i in range(args.warmup):
             step_e2e(i); consume()
         barrier()
+        ahead = max(1, min(args.e2e_ahead, 4, nslots - 1, args.steps))
         t0 = time.perf_counter()
-        step_e2e(0)
-        for i in range(1, args.steps):
+        for i in range(ahead):
             step_e2e(i)
+        for i in range(ahead, args.steps):
+            step_e2e(i)       # blocks i-ahead .. i-1 are still in flight (five result sets)
             consume()
-        consume()
+        for i in range(ahead):
+            consume()
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
