@@ -507,13 +507,18 @@ API void orc_resampler_destroy(orc_resamp* r) { if (!r) return; orc_powerdecim_d
 /* ------------------------------------------------------------------------------------------ */
 /* A11. FrequencyXlator: channel/frequency_xlator.h:15-23,43-50 on VOLK's generic rotator2     */
 /* ------------------------------------------------------------------------------------------ */
-typedef struct { cf32 phase, delta; } orc_xlat;
+/* ideal = 1: the "ideal NCO" flavour: same fp32-quantised increment, but the phase is the closed form
+ * n * arg(delta) kept in extended precision instead of the fp32 recurrence; the sample multiply stays fp32. It
+ * separates an implementation's own error from the reference rotator's random walk: |ref_f32 - ideal| is the
+ * reference's walk, |gpu - ideal| the GPU's error. */
+typedef struct { cf32 phase, delta; int ideal; long double turns, phi; } orc_xlat;
 
 static cf32 cmul(cf32 a, cf32 b) { cf32 r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
 
 API void orc_xlator_set_offset(orc_xlat* x, double offsetHz, double sampleRate) {
     double w = 2.0 * ORC_PI * (offsetHz / sampleRate);     /* math/hz_to_rads.h:6-8 */
     x->delta.re = (float)cos(w); x->delta.im = (float)sin(w);
+    x->turns = (long double)atan2((double)x->delta.im, (double)x->delta.re) / (2.0L * 3.14159265358979323846264338327950288L);
 }
 API orc_xlat* orc_xlator_create(double offsetHz, double sampleRate) {
     orc_xlat* x = (orc_xlat*)calloc(1, sizeof(orc_xlat));
@@ -521,12 +526,27 @@ API orc_xlat* orc_xlator_create(double offsetHz, double sampleRate) {
     orc_xlator_set_offset(x, offsetHz, sampleRate);
     return x;
 }
-API void orc_xlator_reset(orc_xlat* x) { x->phase.re = 1.0f; x->phase.im = 0.0f; }
+API orc_xlat* orc_xlator_create_ideal(double offsetHz, double sampleRate) {
+    orc_xlat* x = orc_xlator_create(offsetHz, sampleRate);
+    x->ideal = 1;
+    return x;
+}
+API void orc_xlator_reset(orc_xlat* x) { x->phase.re = 1.0f; x->phase.im = 0.0f; x->phi = 0.0L; }
 API void orc_xlator_state(const orc_xlat* x, float* phase, float* delta) {
     phase[0] = x->phase.re; phase[1] = x->phase.im; delta[0] = x->delta.re; delta[1] = x->delta.im;
 }
 API int orc_xlator_process(orc_xlat* x, int count, const cf32* in, cf32* out) {
     int i = 0, j, nfull = count / 512, tail = count % 512;
+    if (x->ideal) {
+        for (i = 0; i < count; i++) {
+            const double a = 2.0 * ORC_PI * (double)x->phi;
+            cf32 p; p.re = (float)cos(a); p.im = (float)sin(a);
+            out[i] = cmul(in[i], p);
+            x->phi += x->turns;
+            x->phi -= floorl(x->phi + 0.5L);     /* keep |phi| <= 0.5 turns: no precision loss over long runs */
+        }
+        return count;
+    }
     for (j = 0; j < nfull; j++) {
         int k;
         for (k = 0; k < 512; k++, i++) { out[i] = cmul(in[i], x->phase); x->phase = cmul(x->phase, x->delta); }
@@ -563,6 +583,11 @@ API orc_vfo* orc_rxvfo_create(double inSR, double outSR, double bw, double offse
     v->x = orc_xlator_create(-offset, inSR);
     v->r = orc_resampler_create(inSR, outSR);
     vfo_make_filter(v);
+    return v;
+}
+API orc_vfo* orc_rxvfo_create_ideal(double inSR, double outSR, double bw, double offset) {
+    orc_vfo* v = orc_rxvfo_create(inSR, outSR, bw, offset);
+    v->x->ideal = 1;
     return v;
 }
 API int orc_rxvfo_process(orc_vfo* v, int count, const cf32* in, cf32* out) {
@@ -731,6 +756,11 @@ API orc_ssb* orc_ssb_create(int mode, double bandwidth, double sampleRate) {
     orc_ssb* s = (orc_ssb*)calloc(1, sizeof(orc_ssb));        /* demod/ssb.h:119-126: USB +bw/2, LSB -bw/2, DSB 0 */
     double tr = (mode == 0) ? bandwidth / 2.0 : (mode == 1) ? -bandwidth / 2.0 : 0.0;
     s->x = orc_xlator_create(tr, sampleRate);
+    return s;
+}
+API orc_ssb* orc_ssb_create_ideal(int mode, double bandwidth, double sampleRate) {
+    orc_ssb* s = orc_ssb_create(mode, bandwidth, sampleRate);
+    s->x->ideal = 1;
     return s;
 }
 API int orc_ssb_process(orc_ssb* s, int count, const cf32* in, float* out) {

@@ -148,8 +148,11 @@ class _Base:
     def resampler(self, in_sr, out_sr):
         return _Obj(self.lib, f"{self.prefix}_resampler", self._f("resampler_create", _vp, _d, _d)(in_sr, out_sr))
 
-    def xlator(self, offset_hz, sr):
-        o = _Obj(self.lib, f"{self.prefix}_xlator", self._f("xlator_create", _vp, _d, _d)(offset_hz, sr))
+    def xlator(self, offset_hz, sr, ideal=False):
+        """FrequencyXlator; ideal=True: the ideal-NCO flavour (closed-form phase from the fp32-quantised increment)."""
+        if ideal and self.prefix == "ref":
+            return _Obj(self.lib, "ref_xlatorideal", self._f("xlator_create_ideal", _vp, _d, _d)(offset_hz, sr))
+        o = _Obj(self.lib, f"{self.prefix}_xlator", self._f("xlator_create_ideal" if ideal else "xlator_create", _vp, _d, _d)(offset_hz, sr))
 
         def state():
             ph, dl = (C.c_float * 2)(), (C.c_float * 2)()
@@ -159,8 +162,10 @@ class _Base:
         o.set_offset = lambda off, sr_: self._f("xlator_set_offset", None, _vp, _d, _d)(o.h, off, sr_)
         return o
 
-    def rxvfo(self, in_sr, out_sr, bw, offset):
-        o = _Obj(self.lib, f"{self.prefix}_rxvfo", self._f("rxvfo_create", _vp, _d, _d, _d, _d)(in_sr, out_sr, bw, offset))
+    def rxvfo(self, in_sr, out_sr, bw, offset, ideal_nco=False):
+        """RxVFO; ideal_nco=True: same object with the xlator's fp32 phase recurrence replaced by the closed form."""
+        o = _Obj(self.lib, f"{self.prefix}_rxvfo",
+                 self._f("rxvfo_create_ideal" if ideal_nco else "rxvfo_create", _vp, _d, _d, _d, _d)(in_sr, out_sr, bw, offset))
         o.set_offset = lambda off: self._f("rxvfo_set_offset", None, _vp, _d)(o.h, off)
 
         def info():
@@ -188,8 +193,8 @@ class _Base:
     def quadrature(self, deviation, sr):
         return _Obj(self.lib, f"{self.prefix}_quadrature", self._f("quadrature_create", _vp, _d, _d)(deviation, sr), out_dtype=np.float32)
 
-    def ssb(self, mode, bw, sr):
-        return _Obj(self.lib, f"{self.prefix}_ssb", self._f("ssb_create", _vp, _i, _d, _d)(mode, bw, sr), out_dtype=np.float32)
+    def ssb(self, mode, bw, sr, ideal_nco=False):
+        return _Obj(self.lib, f"{self.prefix}_ssb", self._f("ssb_create_ideal" if ideal_nco else "ssb_create", _vp, _i, _d, _d)(mode, bw, sr), out_dtype=np.float32)
 
     def am_magnitude(self, x):
         x = _c64(x)
@@ -219,12 +224,12 @@ class _Base:
     def ssb_full(self, mode, bw, sr, agc_enabled, attack, decay):
         return self._post_obj(self._f("ssbfull_create", _vp, _i, _d, _d, _i, _d, _d)(mode, bw, sr, int(agc_enabled), attack, decay), "ssbfull")
 
-    def demod(self, kind, bw, sr):
+    def demod(self, kind, bw, sr, ideal_nco=False):
         """Demod front end object for a VFO output stream (kind = DEMOD_*), or None."""
         if kind == DEMOD_QUAD:
             return self.quadrature(bw / 2.0, sr)
         if kind in (DEMOD_USB, DEMOD_LSB, DEMOD_DSB):
-            return self.ssb({DEMOD_USB: 0, DEMOD_LSB: 1, DEMOD_DSB: 2}[kind], bw, sr)
+            return self.ssb({DEMOD_USB: 0, DEMOD_LSB: 1, DEMOD_DSB: 2}[kind], bw, sr, ideal_nco=ideal_nco)
         if kind == DEMOD_AM:
             class _AM:
                 def process(s, x, out_cap=None):

@@ -199,22 +199,80 @@ API void ref_xlator_state(void* h, float* phase, float* delta) {
 }
 API void ref_xlator_destroy(void* h) { delete (dsp::channel::FrequencyXlator*)h; }
 
-// dsp::channel::RxVFO (dsp/channel/rx_vfo.h)
-API void* ref_rxvfo_create(double inSR, double outSR, double bw, double offset) { return new dsp::channel::RxVFO(NULL, inSR, outSR, bw, offset); }
-API int ref_rxvfo_process(void* h, int count, const complex_t* in, complex_t* out) { return ((dsp::channel::RxVFO*)h)->process(count, in, out); }
-API void ref_rxvfo_set_offset(void* h, double offset) { ((dsp::channel::RxVFO*)h)->setOffset(offset); }
-API void ref_rxvfo_set_bandwidth(void* h, double bw) { ((dsp::channel::RxVFO*)h)->setBandwidth(bw); }
-API void ref_rxvfo_set_out_samplerate(void* h, double outSR, double bw) { ((dsp::channel::RxVFO*)h)->setOutSamplerate(outSR, bw); }
-API void ref_rxvfo_set_in_samplerate(void* h, double inSR) { ((dsp::channel::RxVFO*)h)->setInSamplerate(inSR); }
-API void ref_rxvfo_reset(void* h) { ((dsp::channel::RxVFO*)h)->reset(); }
+// "Ideal NCO" flavour: the reference's FrequencyXlator with its fp32 phase recurrence replaced by the closed
+// form n * arg(phaseDelta) in extended precision -- the SAME fp32-quantised increment the reference computes in
+// FrequencyXlator::init (frequency_xlator.h:15-23), the same fp32 complex multiply per sample, everything downstream the
+// reference's own blocks. |ref_f32 - ideal| is the reference rotator's own random walk, |gpu - ideal| the GPU's error.
+struct IdealNco {
+    long double turns = 0, phi = 0;
+    void setOffset(double offsetHz, double sampleRate) {
+        dsp::channel::FrequencyXlator x(NULL, offsetHz, sampleRate);        // the reference rounds the increment
+        XlatPeek* p = static_cast<XlatPeek*>(&x);
+        turns = (long double)atan2((double)p->phaseDelta.imag(), (double)p->phaseDelta.real()) / (2.0L * 3.14159265358979323846264338327950288L);
+    }
+    void reset() { phi = 0; }
+    void process(int count, const complex_t* in, complex_t* out) {
+        for (int i = 0; i < count; i++) {
+            const double a = 2.0 * M_PI * (double)phi;
+            const lv_32fc_t ph((float)cos(a), (float)sin(a));
+            const lv_32fc_t y = oracle_cmul(lv_32fc_t(in[i].re, in[i].im), ph); // the rotator's per-sample product (volk shim)
+            out[i].re = y.real(); out[i].im = y.imag();
+            phi += turns;
+            phi -= floorl(phi + 0.5L);
+        }
+    }
+};
+
+// dsp::channel::RxVFO (dsp/channel/rx_vfo.h). ideal: RxVFO at offset 0 (its xlator multiplies by exactly 1) behind an IdealNco.
+struct VfoObj {
+    dsp::channel::RxVFO* vfo = nullptr;
+    bool ideal = false;
+    IdealNco nco;
+    double inSR = 0;
+    std::vector<complex_t> tmp;
+    ~VfoObj() { delete vfo; }
+};
+API void* ref_rxvfo_create(double inSR, double outSR, double bw, double offset) {
+    VfoObj* o = new VfoObj;
+    o->vfo = new dsp::channel::RxVFO(NULL, inSR, outSR, bw, offset);
+    o->inSR = inSR;
+    return o;
+}
+API void* ref_rxvfo_create_ideal(double inSR, double outSR, double bw, double offset) {
+    VfoObj* o = new VfoObj;
+    o->vfo = new dsp::channel::RxVFO(NULL, inSR, outSR, bw, 0.0);
+    o->ideal = true; o->inSR = inSR;
+    o->nco.setOffset(-offset, inSR);                                        // xlator.init(NULL, -_offset, _inSamplerate), rx_vfo.h:27
+    return o;
+}
+API int ref_rxvfo_process(void* h, int count, const complex_t* in, complex_t* out) {
+    VfoObj* o = (VfoObj*)h;
+    if (!o->ideal) return o->vfo->process(count, in, out);
+    o->tmp.resize(count + 16);
+    o->nco.process(count, in, o->tmp.data());
+    return o->vfo->process(count, o->tmp.data(), out);
+}
+API void ref_rxvfo_set_offset(void* h, double offset) {
+    VfoObj* o = (VfoObj*)h;
+    if (o->ideal) o->nco.setOffset(-offset, o->inSR); else o->vfo->setOffset(offset);
+}
+API void ref_rxvfo_set_bandwidth(void* h, double bw) { ((VfoObj*)h)->vfo->setBandwidth(bw); }
+API void ref_rxvfo_set_out_samplerate(void* h, double outSR, double bw) { ((VfoObj*)h)->vfo->setOutSamplerate(outSR, bw); }
+API void ref_rxvfo_set_in_samplerate(void* h, double inSR) { ((VfoObj*)h)->vfo->setInSamplerate(inSR); ((VfoObj*)h)->inSR = inSR; }
+API void ref_rxvfo_reset(void* h) { VfoObj* o = (VfoObj*)h; o->vfo->reset(); o->nco.reset(); }
 // info[0..5] as ref_resampler_info, info[6]=channel filter tap count (0 when bypassed).
 API void ref_rxvfo_info(void* h, int* info, float* rtaps, int rcap, float* ftaps, int fcap) {
-    VfoPeek* v = static_cast<VfoPeek*>((dsp::channel::RxVFO*)h);
+    VfoPeek* v = static_cast<VfoPeek*>(((VfoObj*)h)->vfo);
     resampler_info(static_cast<ResampPeek*>(&v->resamp), info, rtaps, rcap);
     info[6] = v->filterNeeded ? (int)v->ftaps.size : 0;
     if (ftaps && v->filterNeeded) memcpy(ftaps, v->ftaps.taps, sizeof(float) * std::min<int>(v->ftaps.size, fcap));
 }
-API void ref_rxvfo_destroy(void* h) { delete (dsp::channel::RxVFO*)h; }
+API void ref_rxvfo_destroy(void* h) { delete (VfoObj*)h; }
+
+// FrequencyXlator alone, ideal flavour
+API void* ref_xlator_create_ideal(double offsetHz, double sampleRate) { IdealNco* n = new IdealNco; n->setOffset(offsetHz, sampleRate); return n; }
+API int ref_xlatorideal_process(void* h, int count, const complex_t* in, complex_t* out) { ((IdealNco*)h)->process(count, in, out); return count; }
+API void ref_xlatorideal_destroy(void* h) { delete (IdealNco*)h; }
 
 // dsp::correction::DCBlocker<complex_t> (dsp/correction/dc_blocker.h); rate = 50/effectiveSr in
 // IQFrontEnd::genDCBlockRate (signal_path/iq_frontend.h:52-54)
@@ -243,17 +301,25 @@ API int ref_am_magnitude(int count, const complex_t* in, float* out) {
 
 // SSB front end: FrequencyXlator at getTranslation() then ComplexToReal, as in
 // dsp::demod::SSB::process (dsp/demod/ssb.h:90-101, translation :119-126). mode 0 USB, 1 LSB, 2 DSB.
-struct SsbObj { dsp::channel::FrequencyXlator x; std::vector<complex_t> tmp; };
+struct SsbObj { dsp::channel::FrequencyXlator x; std::vector<complex_t> tmp; bool ideal = false; IdealNco nco; };
 API void* ref_ssb_create(int mode, double bandwidth, double sampleRate) {
     SsbObj* o = new SsbObj;
     double tr = (mode == 0) ? bandwidth / 2.0 : (mode == 1) ? -bandwidth / 2.0 : 0.0;
     o->x.init(NULL, tr, sampleRate);
     return o;
 }
+API void* ref_ssb_create_ideal(int mode, double bandwidth, double sampleRate) {
+    SsbObj* o = new SsbObj;
+    double tr = (mode == 0) ? bandwidth / 2.0 : (mode == 1) ? -bandwidth / 2.0 : 0.0;
+    o->x.init(NULL, tr, sampleRate);
+    o->ideal = true; o->nco.setOffset(tr, sampleRate);
+    return o;
+}
 API int ref_ssb_process(void* h, int count, const complex_t* in, float* out) {
     SsbObj* o = (SsbObj*)h;
     o->tmp.resize(count);
-    o->x.process(count, in, o->tmp.data());
+    if (o->ideal) o->nco.process(count, in, o->tmp.data());
+    else o->x.process(count, in, o->tmp.data());
     return dsp::convert::ComplexToReal::process(count, o->tmp.data(), out);
 }
 API void ref_ssb_destroy(void* h) { delete (SsbObj*)h; }

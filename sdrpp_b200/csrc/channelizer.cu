@@ -722,14 +722,16 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         if (g.demod == 1) {
             const float2 p = src[i - 1];
             // y * conj(prev) with complex_t::operator* (dsp/types.h:23-25)
-            const float dre = y.x * p.x + y.y * p.y;
-            const float dim = y.y * p.x - y.x * p.y;
-            o_dm[i] = atan2f(dim, dre) * g.inv_dev;
+            // in the reference's operation order, no contraction: (re*b.re) - (im*b.im), (im*b.re) + (re*b.im) with b = conj(prev)
+            const float dre = __fadd_rn(__fmul_rn(y.x, p.x), __fmul_rn(y.y, p.y));
+            const float dim = __fsub_rn(__fmul_rn(y.y, p.x), __fmul_rn(y.x, p.y));
+            o_dm[i] = __fmul_rn(atan2f(dim, dre), g.inv_dev);
         } else if (g.demod == 2) {
-            o_dm[i] = sqrtf(y.x * y.x + y.y * y.y);
+            // volk_32fc_magnitude_32f (generic): sqrtf(re*re + im*im), bit-exact with IEEE sqrt
+            o_dm[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
         } else if (g.demod >= 3) {
             const float2 w = phasor_u64((uint64_t)(g.abs_out + i) * vd.dphi2);
-            o_dm[i] = y.x * w.x - y.y * w.y;
+            o_dm[i] = __fsub_rn(__fmul_rn(y.x, w.x), __fmul_rn(y.y, w.y));
         }
     }
     __syncthreads();

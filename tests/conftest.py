@@ -13,6 +13,33 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+# Achieved parity residuals, printed after the run (also under -q) and written to gpurun_out/parity_residuals.txt:
+# tests call parity_report("name", gpu_vs_ideal=..., ref_walk=...) so the numbers behind every gate are on record.
+_RESIDUALS = []
+
+
+def parity_report(name, **vals):
+    _RESIDUALS.append((name, vals))
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    if not _RESIDUALS:
+        return
+    lines = []
+    for name, vals in _RESIDUALS:
+        lines.append(name + ": " + ", ".join(f"{k}={v:.3e}" if isinstance(v, float) else f"{k}={v}" for k, v in vals.items()))
+    terminalreporter.section("parity residuals (achieved, beside each gate)")
+    for ln in lines:
+        terminalreporter.write_line(ln)
+    try:
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_residuals.txt"), "w") as f:
+            f.write("\n".join(lines) + "\n")
+    except OSError:
+        pass
+
+
 def _ensure_port():
     path = os.path.join(ROOT, "oracle", "liboracle_port.so")
     if not os.path.exists(path):
@@ -43,6 +70,11 @@ def ref():
         else:
             pytest.skip("oracle/_ref not built and /root/reference absent")
     return pyoracle.Ref()
+
+
+@pytest.fixture(scope="session")
+def report():
+    return parity_report
 
 
 @pytest.fixture(scope="session")

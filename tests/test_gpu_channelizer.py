@@ -2,9 +2,14 @@
 
 Protocol (SURVEY 8d and App. C.2): integer index arithmetic (per-block output counts) is exact;
 everything after the NCO is checked stage-isolated with offset 0 (NCO = identity) to <= 1e-5
-relative RMS; NCO-containing outputs are checked (a) directly over a short window after reset and
-(b) per block after fitting one complex scalar (the slow fp32 phase walk of the reference
-rotator factors out of the linear stages)."""
+relative RMS; NCO-containing outputs are gated at <= 1e-5 relative RMS, directly (no alignment, whole
+run), against the oracle's IDEAL-NCO flavour: the reference's own blocks with the xlator's fp32 phase
+recurrence replaced by the closed form n * arg(inc) of the SAME fp32-quantised increment. The
+distance of the reference's fp32 rotator from that ideal (its own random walk, 1e-5 ... 2e-4 per
+block of 1e5 ... 6e5 samples) is measured on the same input and reported beside every gate
+(conftest.parity_report -> terminal summary, gpurun_out/parity_residuals.txt).
+The demod front ends are gated stage-isolated: the oracle's Quadrature / AM / SSB applied to the
+GPU's own VFO output against the GPU's demod output (<= 1e-5; AM bit-exact)."""
 import numpy as np
 import pytest
 
@@ -41,9 +46,9 @@ def run_gpu(gpu, sr, vfos, blocks, fmt=po.FMT_CF32, max_block=None, **kw):
     return out
 
 
-def run_oracle(orc, sr, vfo, blocks):
-    o = orc.rxvfo(sr, vfo[0], vfo[1], vfo[2])
-    d = orc.demod(vfo[3], vfo[1], vfo[0])
+def run_oracle(orc, sr, vfo, blocks, ideal_nco=False):
+    o = orc.rxvfo(sr, vfo[0], vfo[1], vfo[2], ideal_nco=ideal_nco)
+    d = orc.demod(vfo[3], vfo[1], vfo[0], ideal_nco=ideal_nco)
     res = []
     for b in blocks:
         y = o.process(b)
@@ -75,27 +80,52 @@ def test_plan_info_matches_oracle(gpu, port, inSR, outSR, bw, blk):
         assert gi[k] == oi[k], (k, gi, oi)
 
 
-@pytest.mark.parametrize("inSR,outSR,bw,blk", PLANS[:4] + PLANS[6:7])
-def test_with_nco_short_window_and_aligned(gpu, port, inSR, outSR, bw, blk):
+def cat(res):
+    return np.concatenate([a for a, _ in res])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("inSR,outSR,bw,blk", PLANS)
+def test_with_nco_vs_ideal(gpu, port, report, inSR, outSR, bw, blk, mode):
+    """A11 + A15: NCO-containing VFO output against the ideal-NCO oracle, direct, <= 1e-5 over the whole run; the
+    reference rotator's own walk beside it. mode 0: tensor-core stage 1 where the plan allows, 1: FP32 kernel."""
     off = 0.2137 * inSR / 2.4
     nblocks = 4
     x = synth.baseband(blk * nblocks, inSR, 8, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
     blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
-    g = run_gpu(gpu, inSR, [(outSR, bw, off, po.DEMOD_NONE)], blocks)[0]
-    r = run_oracle(port, inSR, (outSR, bw, off, po.DEMOD_NONE), blocks)
-    # (a) direct comparison over the first <= 4096 input samples after reset
-    n_short = max(8, int(4096 * outSR / inSR))
-    ga = np.concatenate([a for a, _ in g]); ra = np.concatenate([a for a, _ in r])
-    assert len(ga) == len(ra)
-    e0 = po.rel_rms(ga[:n_short], ra[:n_short]) if np.any(ra[:n_short]) else 0.0
-    assert e0 <= 3e-5, f"short-window rel-RMS {e0:.3e}"
-    # (b) per block, after fitting one complex scalar
-    for b in range(nblocks):
-        if len(r[b][0]) < 8:
-            continue
-        res, c = po.aligned_rel_rms(g[b][0], r[b][0])
-        assert res <= 5e-5, f"block {b}: aligned residual {res:.3e} (c={c})"
-        assert abs(abs(c) - 1.0) < 1e-3 and abs(np.angle(c)) < 2e-2
+    out = [[]]
+    with gpu.Frontend(inSR, max_block=blk) as fe:
+        fe.set_stage1_mode(mode)
+        vid = fe.add_vfo(outSR, bw, off)
+        for b in blocks:
+            fe.process(po.FMT_CF32, b)
+            out[0].append(fe.vfo_output(vid))
+    g = out[0]
+    ideal = run_oracle(port, inSR, (outSR, bw, off, po.DEMOD_NONE), blocks, ideal_nco=True)
+    r32 = run_oracle(port, inSR, (outSR, bw, off, po.DEMOD_NONE), blocks)
+    assert [len(a) for a, _ in g] == [len(a) for a, _ in ideal]
+    err = po.rel_rms(cat(g), cat(ideal))
+    walk = po.rel_rms(cat(r32), cat(ideal))
+    last = po.rel_rms(g[-1][0], ideal[-1][0])
+    walk_last = po.rel_rms(r32[-1][0], ideal[-1][0])
+    report(f"A11/A15 nco {inSR/1e6:g}M->{outSR/1e3:g}k mode{mode}", gpu_vs_ideal=err, gpu_vs_ideal_last_block=last,
+           ref_f32_vs_ideal=walk, ref_f32_vs_ideal_last_block=walk_last, gate=TOL)
+    assert err <= TOL, f"GPU vs ideal-NCO oracle: {err:.3e} (reference's own walk: {walk:.3e})"
+    assert last <= TOL, f"last block: {last:.3e}"
+
+
+def test_xlator_alone_vs_ideal(gpu, port, report):
+    """A11 alone: a VFO whose plan is translation only (48k -> 48k, bw == outSR: no resampler, no filter)."""
+    sr, blk, off = 48e3, 4800, 5123.0
+    x = synth.baseband(blk * 20, sr, 31, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(20)]
+    g = run_gpu(gpu, sr, [(sr, sr, off, po.DEMOD_NONE)], blocks)[0]
+    xi, xr = port.xlator(-off, sr, ideal=True), port.xlator(-off, sr)
+    ideal = np.concatenate([xi.process(b) for b in blocks])
+    r32 = np.concatenate([xr.process(b) for b in blocks])
+    err, walk = po.rel_rms(cat(g), ideal), po.rel_rms(r32, ideal)
+    report("A11 xlator alone 48k x 96000 samples", gpu_vs_ideal=err, ref_f32_vs_ideal=walk, gate=TOL)
+    assert err <= TOL, f"{err:.3e}"
 
 
 def test_counts_ragged_blocks(gpu, port):
@@ -113,50 +143,58 @@ def test_counts_ragged_blocks(gpu, port):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("demod,outSR,bw", [(po.DEMOD_QUAD, 250e3, 200e3), (po.DEMOD_QUAD, 48e3, 12.5e3),
-                                            (po.DEMOD_AM, 24e3, 12e3), (po.DEMOD_USB, 48e3, 2.7e3),
-                                            (po.DEMOD_LSB, 48e3, 2.7e3), (po.DEMOD_DSB, 48e3, 4.6e3)])
-def test_demod_front_ends(gpu, port, demod, outSR, bw):
+DEMODS = [(po.DEMOD_QUAD, 250e3, 200e3), (po.DEMOD_QUAD, 48e3, 12.5e3), (po.DEMOD_AM, 24e3, 12e3), (po.DEMOD_USB, 48e3, 2.7e3),
+          (po.DEMOD_LSB, 48e3, 2.7e3), (po.DEMOD_DSB, 48e3, 4.6e3)]
+
+
+@pytest.mark.parametrize("demod,outSR,bw", DEMODS)
+def test_demod_front_ends(gpu, port, report, demod, outSR, bw):
+    """A16-A18, stage-isolated: the oracle's demod front end applied to the GPU's OWN VFO output (state carried from
+    block to block) against the GPU's demod output, <= 1e-5 (AM: bit-exact; SSB: the oracle's second NCO in the ideal
+    flavour). The end-to-end figure against the oracle chain is reported beside it."""
     inSR, blk, nblocks = 2.4e6, 12000, 6
     kind = {po.DEMOD_QUAD: "fm", po.DEMOD_AM: "am"}.get(demod, "cw")
     x = synth.baseband(blk * nblocks, inSR, 10, carriers=[(0.0 if kind != "cw" else 700.0, kind)], tones=0, noise_dbfs=-60.0).astype(np.complex64)
     blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
     g = run_gpu(gpu, inSR, [(outSR, bw, 0.0, demod)], blocks)[0]
-    r = run_oracle(port, inSR, (outSR, bw, 0.0, demod), blocks)
-    gd = np.concatenate([d for _, d in g]); rd = np.concatenate([d for _, d in r])
-    assert len(gd) == len(rd) and len(gd) > 100
-    # skip the filter transient (and the first Quadrature sample)
-    s = len(gd) // 3
-    if demod == po.DEMOD_QUAD:
-        # compare as phase increments: atan2 is ill-conditioned only where |y| ~ 0 (not here)
-        err = np.sqrt(np.mean((gd[s:] - rd[s:]) ** 2)) / max(np.sqrt(np.mean(rd[s:] ** 2)), 1e-3)
-        assert err <= 2e-4, f"quadrature rel err {err:.3e}"
-    else:
-        err = po.rel_rms(gd[s:], rd[s:])
-        assert err <= 3e-5, f"demod {demod} rel-RMS {err:.3e}"
+    d = port.demod(demod, bw, outSR, ideal_nco=True)
+    iso = np.concatenate([d.process(iq) for iq, _ in g])      # oracle demod on the GPU's own iq
+    gd = np.concatenate([dm for _, dm in g])
+    assert len(gd) == len(iso) and len(gd) > 100
+    s = 1 if demod == po.DEMOD_QUAD else 0                    # Quadrature's first sample after reset (SURVEY A.11)
+    err = float(np.sqrt(np.mean((gd[s:].astype(np.float64) - iso[s:]) ** 2)) / max(np.sqrt(np.mean(iso[s:].astype(np.float64) ** 2)), 1e-30))
+    r = run_oracle(port, inSR, (outSR, bw, 0.0, demod), blocks, ideal_nco=True)
+    rd = np.concatenate([dm for _, dm in r])
+    t = len(gd) // 3                                          # end to end: past the filter transient
+    e2e = float(np.sqrt(np.mean((gd[t:].astype(np.float64) - rd[t:]) ** 2)) / max(np.sqrt(np.mean(rd[t:].astype(np.float64) ** 2)), 1e-30))
+    report(f"A16-18 demod {demod} {outSR/1e3:g}k/{bw/1e3:g}k", stage_isolated=err, bit_exact=bool(np.array_equal(gd[s:], iso[s:])),
+           end_to_end_vs_oracle_chain=e2e, gate=TOL)
+    assert err <= TOL, f"demod {demod}: stage-isolated {err:.3e}"
+    if demod == po.DEMOD_AM:
+        assert np.array_equal(gd, iso), "AM magnitude must be bit-exact on the same input"
 
 
-def test_many_vfos_two_classes(gpu, port):
-    """70 VFOs (NFM/AM alternating) share one IQ block; spot-check members against the oracle."""
+def test_many_vfos_two_classes(gpu, port, report):
+    """70 VFOs (NFM/AM alternating) share one IQ block; spot-check members against the ideal-NCO oracle at 1e-5.
+    Every spot-checked channel holds a carrier of its own class, so the gate is relative to the channel's content."""
     inSR, blk, nblocks = 20e6, 100000, 2
     offs = synth.vfo_grid(70, inSR)
     vfos = []
     for i, o in enumerate(offs):
         vfos.append((48e3, 12.5e3, float(o), po.DEMOD_QUAD) if i % 2 == 0 else (24e3, 12e3, float(o), po.DEMOD_AM))
-    x = synth.baseband(blk * nblocks, inSR, 11, carriers=[(float(offs[i]), "fm" if i % 2 == 0 else "am") for i in (0, 1, 33, 34, 68, 69)],
+    check = (0, 1, 31, 32, 33, 34, 63, 64, 68, 69)
+    x = synth.baseband(blk * nblocks, inSR, 11, carriers=[(float(offs[i]), "fm" if i % 2 == 0 else "am") for i in check],
                        noise_dbfs=-50.0).astype(np.complex64)
     blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
-    x_rms = float(np.sqrt(np.mean(np.abs(x) ** 2)))
     g = run_gpu(gpu, inSR, vfos, blocks)
-    for i in (0, 1, 31, 32, 33, 34, 63, 64, 68, 69):
-        r = run_oracle(port, inSR, vfos[i], blocks)
-        for b in range(nblocks):
-            assert len(g[i][b][0]) == len(r[b][0])
-            res, c = po.aligned_rel_rms(g[i][b][0], r[b][0])
-            # Channels without a carrier hold only noise ~-80 dBFS while the reference rotator's own fp32
-            # rounding is relative to the full-band signal (~-6 dBFS): gate those on absolute error.
-            ref_rms = float(np.sqrt(np.mean(np.abs(r[b][0]) ** 2)))
-            assert res * ref_rms <= 5e-5 * ref_rms + 3e-7 * x_rms, f"vfo {i} block {b}: {res:.3e}"
+    worst = 0.0
+    for i in check:
+        r = run_oracle(port, inSR, vfos[i], blocks, ideal_nco=True)
+        assert [len(a) for a, _ in g[i]] == [len(a) for a, _ in r]
+        err = po.rel_rms(cat(g[i]), cat(r))
+        worst = max(worst, err)
+        assert err <= TOL, f"vfo {i}: {err:.3e}"
+    report("A15 70 VFOs at 20 MS/s, 10 spot-checked", worst_gpu_vs_ideal=worst, gate=TOL)
 
 
 def test_retune_reset_add_remove(gpu, port):
@@ -165,12 +203,12 @@ def test_retune_reset_add_remove(gpu, port):
     blocks = [x[i * blk:(i + 1) * blk] for i in range(6)]
     with gpu.Frontend(inSR, max_block=blk) as fe:
         a = fe.add_vfo(outSR, bw, 100e3)
-        oa = port.rxvfo(inSR, outSR, bw, 100e3)
+        oa = port.rxvfo(inSR, outSR, bw, 100e3, ideal_nco=True)
         ob = None
         for b in range(6):
             if b == 2:
                 fe.vfo_set_offset(a, -300e3); oa.set_offset(-300e3)
-                vb = fe.add_vfo(outSR, bw, 100e3); ob = port.rxvfo(inSR, outSR, bw, 100e3)
+                vb = fe.add_vfo(outSR, bw, 100e3); ob = port.rxvfo(inSR, outSR, bw, 100e3, ideal_nco=True)
             if b == 4:
                 fe.vfo_reset(a); oa.reset()
                 fe.remove_vfo(vb); ob = None
@@ -182,14 +220,14 @@ def test_retune_reset_add_remove(gpu, port):
             # history samples of stage 1 (26 input samples), a transient that rings through the later
             # filters; compare after it has died out.
             s = 500 if b == 2 else 0
-            res, _ = po.aligned_rel_rms(ya[s:], ra[s:])
-            assert res <= 3e-5, f"vfo a block {b}: {res:.3e}"
+            res = po.rel_rms(ya[s:], ra[s:])
+            assert res <= TOL, f"vfo a block {b}: {res:.3e}"
             if ob is not None:
                 yb, _ = fe.vfo_output(vb)
                 rb = ob.process(blocks[b])
                 assert len(yb) == len(rb)
-                res, _ = po.aligned_rel_rms(yb, rb)
-                assert res <= 3e-5, f"vfo b block {b}: {res:.3e}"
+                res = po.rel_rms(yb, rb)
+                assert res <= TOL, f"vfo b block {b}: {res:.3e}"
 
 
 def test_frontend_decimation_int16_dc_conj(gpu, port):
@@ -215,7 +253,7 @@ def test_frontend_decimation_int16_dc_conj(gpu, port):
                 r = vf.process(y)
                 assert len(g) == len(r)
                 if b > 1 and len(r):
-                    assert po.rel_rms(g, r) <= 3e-5
+                    assert po.rel_rms(g, r) <= TOL, f"vfo block {b}: {po.rel_rms(g, r):.3e}"
 
 
 # every PowerDecimator ratio as a first stage, the no-predecimation modes and an interpolating resampler
@@ -241,18 +279,12 @@ def test_all_plan_shapes(gpu, port, inSR, outSR, bw, blk):
     nblocks = 3
     x = synth.baseband(blk * nblocks, inSR, 17, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
     blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
-    for offset, aligned in ((0.0, False), (off, True)):
+    for offset in (0.0, off):
         g = run_gpu(gpu, inSR, [(outSR, bw, offset, po.DEMOD_NONE)], blocks)[0]
-        r = run_oracle(port, inSR, (outSR, bw, offset, po.DEMOD_NONE), blocks)
+        r = run_oracle(port, inSR, (outSR, bw, offset, po.DEMOD_NONE), blocks, ideal_nco=True)
         assert [len(a) for a, _ in g] == [len(a) for a, _ in r]
-        ga = np.concatenate([a for a, _ in g]); ra = np.concatenate([a for a, _ in r])
-        if not aligned:
-            assert po.rel_rms(ga, ra) <= TOL, f"offset 0: {po.rel_rms(ga, ra):.3e}"
-        else:
-            for b in range(nblocks):
-                if len(r[b][0]) >= 8:
-                    res, _ = po.aligned_rel_rms(g[b][0], r[b][0])
-                    assert res <= 5e-5, f"block {b}: {res:.3e}"
+        err = po.rel_rms(cat(g), cat(r))
+        assert err <= TOL, f"offset {offset}: {err:.3e}"
 
 
 def test_max_block_and_cfg3_spectrum(gpu, port):
@@ -262,7 +294,7 @@ def test_max_block_and_cfg3_spectrum(gpu, port):
     x = synth.baseband(blk * 2, sr, 23, carriers=[(3.1e6, "fm")], noise_dbfs=-40.0).astype(np.complex64)
     with gpu.Frontend(sr, fft_size=N, fft_rate=20.0, fft_window=po.WIN_BH7, max_block=blk) as fe:
         vid = fe.add_vfo(250e3, 200e3, 3.1e6, po.DEMOD_QUAD)
-        orc = port.rxvfo(sr, 250e3, 200e3, 3.1e6)
+        orc = port.rxvfo(sr, 250e3, 200e3, 3.1e6, ideal_nco=True)
         rows = []
         for b in range(2):
             fe.process(po.FMT_CF32, x[b * blk:(b + 1) * blk])
@@ -270,8 +302,8 @@ def test_max_block_and_cfg3_spectrum(gpu, port):
             y, _ = fe.vfo_output(vid)
             ref = orc.process(x[b * blk:(b + 1) * blk])
             assert len(y) == len(ref) == 12500
-            res, _ = po.aligned_rel_rms(y, ref)
-            assert res <= 1e-4, res   # 1e6 input samples per block: the reference rotator's own walk
+            res = po.rel_rms(y, ref)
+            assert res <= TOL, res
         rows = np.concatenate(rows)
     assert rows.shape == (2, N)
     skip, nz = port.reshape_params(sr, N, 20.0)

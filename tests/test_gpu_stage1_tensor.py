@@ -4,7 +4,7 @@ tcgen05 matrix product with fp16 hi/lo split operands.
 Checked three ways, all through the C ABI: (1) against the oracle with offset 0 (NCO = identity) at the
 1e-5 gate of SURVEY 8d; (2) against the library's own FP32 FMA stage 1 (mode 1) on identical inputs -- both
 evaluate the same ideal NCO, so they must agree far inside the gate, whatever the VFO offsets; (3) with the
-NCO against the oracle after fitting one complex scalar per block. Every test asserts that the
+NCO against the oracle's ideal-NCO flavour, directly, at 1e-5. Every test asserts that the
 tensor-core kernel actually ran."""
 import numpy as np
 import pytest
@@ -80,23 +80,27 @@ def test_matches_fp32_kernel_many_vfos(gpu, inSR, outSR, bw, blk):
     print(f"worst tensor-vs-fp32 relative difference {worst:.3e}")
 
 
-def test_nco_against_oracle_aligned(gpu, port):
-    inSR, outSR, bw, blk = 122.88e6, 48e3, 12.5e3, 614400
+@pytest.mark.parametrize("inSR,outSR,bw,blk", TC_PLANS)
+def test_nco_against_ideal_oracle(gpu, port, report, inSR, outSR, bw, blk):
+    """With the NCO, against the oracle's ideal-NCO flavour: direct, per block, <= 1e-5 (the reference rotator's own walk
+    away from the same ideal is reported beside it)."""
     off = 0.2137 * inSR / 2.4
     nblocks = 3
     x = synth.baseband(blk * nblocks, inSR, 23, carriers=[(off, "fm")], noise_dbfs=-40.0).astype(np.complex64)
     blocks = [x[i * blk:(i + 1) * blk] for i in range(nblocks)]
     g, counts, tl = run(gpu, inSR, [(outSR, bw, off, po.DEMOD_NONE)], blocks, 0)
     assert tl >= nblocks - 1
-    o = port.rxvfo(inSR, outSR, bw, off)
+    o, o32 = port.rxvfo(inSR, outSR, bw, off, ideal_nco=True), port.rxvfo(inSR, outSR, bw, off)
     p = 0
+    worst, walk = 0.0, 0.0
     for b in range(nblocks):
-        r = o.process(blocks[b])
+        r, r32 = o.process(blocks[b]), o32.process(blocks[b])
         assert counts[0][b] == len(r)
-        res, c = po.aligned_rel_rms(g[0][p:p + len(r)], r)
+        err = po.rel_rms(g[0][p:p + len(r)], r)
+        worst, walk = max(worst, err), max(walk, po.rel_rms(r32, r))
         p += len(r)
-        assert res <= 5e-5, f"block {b}: aligned residual {res:.3e}"
-        assert abs(abs(c) - 1.0) < 1e-3 and abs(np.angle(c)) < 2e-2
+        assert err <= 1e-5, f"block {b}: {err:.3e}"
+    report(f"A11 tensor stage 1 {inSR/1e6:g}M->{outSR/1e3:g}k", gpu_vs_ideal_worst_block=worst, ref_f32_vs_ideal_worst_block=walk, gate=1e-5)
 
 
 @pytest.mark.parametrize("scale", [1e-6, 1.0, 3000.0])
