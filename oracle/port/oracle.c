@@ -304,6 +304,9 @@ API int orc_decim_plan(int ratio, int* decimation, int* tapcount, const float** 
 /* A4/A14. FIR and decimating FIR: filter/fir.h:62-83, filter/decimating_fir.h:45-68           */
 /* State: T-1 past inputs (zero at reset) and the integer `offset` (0 at reset).               */
 /* ------------------------------------------------------------------------------------------ */
+#ifndef ORC_ACC_T
+#define ORC_ACC_T float
+#endif
 typedef struct {
     int ntaps, decim, offset;
     float* taps;
@@ -312,14 +315,16 @@ typedef struct {
 } orc_fir;
 
 static void dot_cf(cf32* res, const cf32* x, const float* t, int n) {
-    /* volk_32fc_32f_dot_prod_32fc generic: sequential fp32, separate re/im sums */
-    float re = 0.0f, im = 0.0f;
+    /* volk_32fc_32f_dot_prod_32fc generic: sequential fp32, separate re/im sums. ORC_ACC_T = double builds the
+     * "f64" flavour (liboracle_port_f64.so): the same chain with exact-product, fp64-accumulated dot products, used to
+     * measure the fp32 scatter of an implementation (the reference's own included) against a common truth. */
+    ORC_ACC_T re = 0, im = 0;
     int k;
     for (k = 0; k < n; k++) {
-        re += x[k].re * t[k];
-        im += x[k].im * t[k];
+        re += (ORC_ACC_T)x[k].re * (ORC_ACC_T)t[k];
+        im += (ORC_ACC_T)x[k].im * (ORC_ACC_T)t[k];
     }
-    res->re = re; res->im = im;
+    res->re = (float)re; res->im = (float)im;
 }
 
 API orc_fir* orc_fir_create(const float* taps, int ntaps, int decim) {

@@ -283,8 +283,9 @@ class Port(_Base):
     """Plain-C restatement (oracle/port/oracle.c)."""
     prefix = "orc"
 
-    def __init__(self):
-        path = os.path.join(HERE, "liboracle_port.so")
+    def __init__(self, flavour=""):
+        """flavour '' = fp32 (the parity oracle); 'f64' = fp64-accumulated dot products (scatter adjudication only)."""
+        path = os.path.join(HERE, "liboracle_port.so" if not flavour else f"liboracle_port_{flavour}.so")
         if not os.path.exists(path):
             raise FileNotFoundError(f"{path} missing: run `make -C oracle port` (or __graft_entry__.build())")
         self.lib = C.CDLL(path)
