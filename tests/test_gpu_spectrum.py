@@ -12,14 +12,14 @@ pytestmark = pytest.mark.gpu
 
 TOL_X = 1e-5
 TOL_DB = 0.01
-SCATTER_X = 4.0  # allowed ratio to the reference's own fp32 round-off on noise-floor bins
+SCATTER_X = 2.0  # N >= 128K only (App. C.10): allowed ratio to the oracle's own fp32-FFT error on the gated bins
 
 
 def _frame(n, seed, noise=-40.0):
     return synth.baseband(n, 2.4e6, seed, carriers=[(300e3, "fm"), (-500e3, "am")], noise_dbfs=noise).astype(np.complex64)
 
 
-def _check(gpu, port, N, nz, wtype, seed):
+def _check(gpu, port, N, nz, wtype, seed, report=None):
     x = _frame(nz, seed)
     w = port.window(wtype, nz)
     row32, X64, row64 = port.spectrum(N, x, w)
@@ -29,23 +29,25 @@ def _check(gpu, port, N, nz, wtype, seed):
     assert err <= TOL_X, f"N={N} nz={nz}: X rel-RMS {err:.3e}"
     mask = row64 >= row64.max() - 100.0
     d = np.abs(row.astype(np.float64) - row64)[mask]
-    # 0.01 dB on the gated bins, or -- where even the reference's own fp32 FFT misses that (large N puts
-    # the per-bin noise floor ~95 dB under the tones, App. C.10) -- no worse than SCATTER_X times its error
+    # 0.01 dB on the gated bins, strictly, below 128K points. From 128K up the per-bin noise floor sits ~95 dB under the
+    # tones and even the oracle's own fp32 FFT misses 0.01 dB on a few gated bins (App. C.10): there, no worse than
+    # SCATTER_X times its error
     d_ref = np.abs(row32.astype(np.float64) - row64)[mask]
-    gate = max(TOL_DB, SCATTER_X * d_ref.max())
-    print(f"N={N}: gated max |dB| gpu {d.max():.4f} ref32 {d_ref.max():.4f}")
+    gate = max(TOL_DB, SCATTER_X * d_ref.max()) if N >= (1 << 17) else TOL_DB
+    if report is not None:
+        report(f"A10 spectrum N={N} nz={nz} win{wtype}", X_rel_rms=err, row_db_within_100dB=float(d.max()), oracle_fp32_fft_db=float(d_ref.max()), gate_db=float(gate))
     assert d.max() <= gate, f"N={N}: max |dB| {d.max():.4f} (ref fp32 {d_ref.max():.4f}) on {mask.sum()} gated bins"
     strong = row64 >= row64.max() - 60.0
     assert np.abs(row.astype(np.float64) - row64)[strong].max() <= TOL_DB
     # the GPU must not be worse than the reference's own fp32 scatter below the gate
     ref_scatter = np.percentile(np.abs(row32.astype(np.float64) - row64), 99.9)
     gpu_scatter = np.percentile(np.abs(row.astype(np.float64) - row64), 99.9)
-    assert gpu_scatter <= max(SCATTER_X * ref_scatter, TOL_DB), (gpu_scatter, ref_scatter)
+    assert gpu_scatter <= max(4.0 * ref_scatter, TOL_DB), (gpu_scatter, ref_scatter)
 
 
 @pytest.mark.parametrize("N", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288, 1048576])
-def test_sizes_bh7(gpu, port, N):
-    _check(gpu, port, N, N, po.WIN_BH7, seed=N % 97)
+def test_sizes_bh7(gpu, port, report, N):
+    _check(gpu, port, N, N, po.WIN_BH7, seed=N % 97, report=report)
 
 
 @pytest.mark.parametrize("wtype", range(7))
