@@ -6,12 +6,17 @@
 //     channelizer, IQFrontEnd's worker fills `out` every block, run()/process() are not used;
 //   * standalone: constructed directly, like any dsp::Processor; process(count, in, out) pushes the
 //     block through a private one-VFO front end (H2D, kernels, D2H inside the call).
-// Same public names, argument meaning and error behaviour as the reference class.
+// Same public names, argument meaning and error behaviour as the reference class. Replaces core/src/dsp/channel/rx_vfo.h
+// in the source overlay (tools/make_overlay.py); dsp::Processor / dsp::block / dsp::complex_t are the reference's own.
 #pragma once
 #include <cstring>
 #include <mutex>
 #include "../processor.h"
-#include "../../../sdrpp_cuda.h"
+// the reference's rx_vfo.h brings these two in and code downstream relies on that (e.g. dsp/demod/broadcast_fm.h uses
+// dsp::channel::FrequencyXlator without including it)
+#include "frequency_xlator.h"
+#include "../multirate/rational_resampler.h"
+#include <sdrpp_cuda.h>
 
 class IQFrontEnd;
 
@@ -111,6 +116,8 @@ namespace dsp::channel {
         // an attached VFO has no worker of its own: IQFrontEnd's worker feeds `out`
         void doStart() override { if (ownsFe) { base_type::doStart(); } }
         void doStop() override { if (ownsFe) { base_type::doStop(); } }
+        // attached mode: the front end re-planned this VFO for a new input rate (IQFrontEnd::setSampleRate / setDecimation)
+        void noteInSamplerate(double inSr) { _inSamplerate = inSr; }
         template <class F> void withEngine(F f) {
             if (!fe || vfoId < 0) { return; }
             if (engineMtx) { std::lock_guard<std::recursive_mutex> l(*engineMtx); f(); } else { f(); }

@@ -4,7 +4,7 @@
 // sdrpp_cuda_pcm_compress, bit-identical to the reference's generic-VOLK result.
 #pragma once
 #include "../processor.h"
-#include "../../../sdrpp_cuda.h"
+#include <sdrpp_cuda.h>
 #include "pcm_type.h"
 
 namespace dsp::compression {

@@ -5,7 +5,7 @@
 // packet to sdrpp_cuda_frontend_submit_pcm instead.
 #pragma once
 #include "../processor.h"
-#include "../../../sdrpp_cuda.h"
+#include <sdrpp_cuda.h>
 #include "pcm_type.h"
 
 namespace dsp::compression {

@@ -1,15 +1,19 @@
 // dsp::stream<T>: the blocking double-buffer hand-off between one writer and one reader
-// (contract of the reference's core/src/dsp/stream.h:24-140, re-implemented).
+// (contract of the reference's core/src/dsp/stream.h:24-140, re-implemented). Replaces that file in the source overlay
+// (tools/make_overlay.py).
 //
 // Differences that matter for the GPU path: both buffers are PINNED host memory
 // (sdrpp_cuda_host_alloc) so an IQ block can be DMA'd to the device straight out of readBuf; if no
 // CUDA device is present the allocation falls back to ordinary aligned memory so that host-only code
 // (and CPU tests) still work -- compute calls still fail loudly without a GPU.
 #pragma once
+#include <string.h>
 #include <condition_variable>
 #include <cstdlib>
 #include <mutex>
-#include "../../sdrpp_cuda.h"
+#include <volk/volk.h>      // like the reference's stream.h: the rest of dsp/ relies on these two arriving through it
+#include "buffer/buffer.h"
+#include <sdrpp_cuda.h>
 
 #define STREAM_BUFFER_SIZE 1000000 // elements per buffer, as in the reference (stream.h:9)
 

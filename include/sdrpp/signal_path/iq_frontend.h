@@ -1,195 +1,106 @@
-// IQFrontEnd -- host-side mirror of sigpath::iqFrontEnd (reference: core/src/signal_path/iq_frontend.h:14-104,
-// iq_frontend.cpp:15-296). Same public methods; the pre-processing chain, the splitter fan-out, the spectrum
-// branch and every bound RxVFO run as one stream-ordered launch sequence per IQ block on the GPU
-// (sdrpp_cuda_frontend_*), driven by a single worker thread instead of a thread per block.
+// IQFrontEnd -- drop-in replacement of core/src/signal_path/iq_frontend.h (reference: iq_frontend.h:14-104). Same
+// public interface, member for member; the implementation (sdrpp_b200/host/iq_frontend.cpp, which replaces
+// core/src/signal_path/iq_frontend.cpp) drives the CUDA library through its C ABI (sdrpp_cuda.h) instead of the
+// reference's thread-per-block chain: the pre-processing chain, the splitter fan-out, the spectrum branch and every
+// bound RxVFO run as one stream-ordered launch sequence per IQ block on the GPU.
+//
+// Two host threads per front end: `ingest` reads the input stream and submits blocks (up to four ahead), `deliver`
+// waits for finished blocks in order and hands spectrum rows to the acquire/release pair and VFO blocks to their
+// RxVFO::out streams -- the H2D copy and the kernels of block i+1 run while block i is being delivered.
 #pragma once
-#include <algorithm>
-#include <atomic>
-#include <cstdio>
-#include <cstring>
+#include <condition_variable>
 #include <map>
-#include <stdexcept>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+// the same dsp/ headers the reference's iq_frontend.h includes: modules rely on them arriving through signal_path.h
+// (e.g. decoder_modules/radio/src/demodulators/wfm.h uses dsp::sink::Handler and dsp::buffer::Reshaper that way)
+#include "../dsp/buffer/frame_buffer.h"
+#include "../dsp/buffer/reshaper.h"
+#include "../dsp/multirate/power_decimator.h"
+#include "../dsp/correction/dc_blocker.h"
+#include "../dsp/chain.h"
+#include "../dsp/routing/splitter.h"
 #include "../dsp/channel/rx_vfo.h"
+#include "../dsp/sink/handler_sink.h"
+#include "../dsp/math/conjugate.h"
 #include "../dsp/window/window.h"
-#include "../../sdrpp_cuda.h"
+#include <sdrpp_cuda.h>
 
 class IQFrontEnd {
 public:
-    ~IQFrontEnd() {
-        if (!_init) { return; }
-        stop();
-        for (auto& [name, vfo] : vfos) { delete vfo; }
-        if (fe) { sdrpp_cuda_frontend_destroy(fe); }
-    }
+    ~IQFrontEnd();
 
-    void init(dsp::stream<dsp::complex_t>* in, double sampleRate, bool buffering, int decimRatio, bool dcBlocking, int fftSize,
-              double fftRate, dsp::window::windowType fftWindow, float* (*acquireFFTBuffer)(void* ctx),
-              void (*releaseFFTBuffer)(void* ctx), void* fftCtx) {
-        _in = in; _sampleRate = sampleRate; _decimRatio = decimRatio; _fftSize = fftSize; _fftRate = fftRate; _fftWindow = fftWindow;
-        _acquireFFTBuffer = acquireFFTBuffer; _releaseFFTBuffer = releaseFFTBuffer; _fftCtx = fftCtx;
-        (void)buffering; // the 32-deep SampleFrameBuffer is replaced by the library's pinned/device double buffering
-        sdrpp_cuda_frontend_cfg cfg{};
-        cfg.sample_rate = sampleRate; cfg.decim_ratio = decimRatio; cfg.dc_blocking = dcBlocking; cfg.invert_iq = 0;
-        cfg.fft_size = fftSize; cfg.fft_rate = fftRate; cfg.fft_window = (int)fftWindow; cfg.max_block = STREAM_BUFFER_SIZE;
-        fe = sdrpp_cuda_frontend_create(&cfg);
-        if (!fe) { fprintf(stderr, "[IQFrontEnd] %s\n", sdrpp_cuda_last_error()); }
-        effectiveSr = _sampleRate / _decimRatio;
-        _init = true;
-    }
+    void init(dsp::stream<dsp::complex_t>* in, double sampleRate, bool buffering, int decimRatio, bool dcBlocking, int fftSize, double fftRate, dsp::window::windowType fftWindow, float* (*acquireFFTBuffer)(void* ctx), void (*releaseFFTBuffer)(void* ctx), void* fftCtx);
 
-    void setInput(dsp::stream<dsp::complex_t>* in) {
-        const bool was = running;
-        stop();
-        _in = in;
-        if (was) { start(); }
-    }
+    void updateFFTSize();
 
-    void setSampleRate(double sampleRate) {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        _sampleRate = sampleRate;
-        effectiveSr = _sampleRate / _decimRatio;
-        if (fe) { sdrpp_cuda_frontend_set_sample_rate(fe, sampleRate); }
-    }
+    void setInput(dsp::stream<dsp::complex_t>* in);
+    void setSampleRate(double sampleRate);
     inline double getSampleRate() { return _sampleRate / _decimRatio; }
-    void setBuffering(bool enabled) { (void)enabled; }
-    void setDecimation(int ratio) {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        _decimRatio = ratio;
-        effectiveSr = _sampleRate / _decimRatio;
-        if (fe) { sdrpp_cuda_frontend_set_decimation(fe, ratio); }
-    }
-    void setInvertIQ(bool enabled) { std::lock_guard<std::recursive_mutex> lck(mtx); if (fe) { sdrpp_cuda_frontend_set_invert_iq(fe, enabled); } }
-    void setDCBlocking(bool enabled) { std::lock_guard<std::recursive_mutex> lck(mtx); if (fe) { sdrpp_cuda_frontend_set_dc_blocking(fe, enabled); } }
 
-    // Raw (post-preprocessing) IQ taps, as the Splitter hands them out (recorder, iq_frontend.cpp:114-120)
-    void bindIQStream(dsp::stream<dsp::complex_t>* stream) {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        if (std::find(bound.begin(), bound.end(), stream) != bound.end()) { throw std::runtime_error("[IQFrontEnd] stream already bound"); }
-        bound.push_back(stream);
-    }
-    void unbindIQStream(dsp::stream<dsp::complex_t>* stream) {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        auto it = std::find(bound.begin(), bound.end(), stream);
-        if (it == bound.end()) { throw std::runtime_error("[IQFrontEnd] stream not bound"); }
-        bound.erase(it);
-    }
+    void setBuffering(bool enabled);
+    void setDecimation(int ratio);
+    void setInvertIQ(bool enabled);
+    void setDCBlocking(bool enabled);
 
-    dsp::channel::RxVFO* addVFO(std::string name, double sampleRate, double bandwidth, double offset) {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        if (vfos.find(name) != vfos.end()) {
-            fprintf(stderr, "[IQFrontEnd] Tried to add VFO with existing name.\n");
-            return NULL;
-        }
-        if (!fe) { return NULL; }
-        const int id = sdrpp_cuda_vfo_create(fe, sampleRate, bandwidth, offset, SDRPP_DEMOD_NONE);
-        if (id < 0) { fprintf(stderr, "[IQFrontEnd] %s\n", sdrpp_cuda_last_error()); return NULL; }
-        auto* vfo = new dsp::channel::RxVFO();
-        vfo->attach(fe, id, &mtx, effectiveSr, sampleRate, bandwidth, offset);
-        vfos[name] = vfo;
-        return vfo;
-    }
-    void removeVFO(std::string name) {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        auto it = vfos.find(name);
-        if (it == vfos.end()) {
-            fprintf(stderr, "[IQFrontEnd] Tried to remove a VFO that doesn't exist.\n");
-            return;
-        }
-        it->second->out.stopWriter();
-        sdrpp_cuda_vfo_destroy(fe, it->second->vfoId);
-        delete it->second;
-        vfos.erase(it);
-    }
+    void bindIQStream(dsp::stream<dsp::complex_t>* stream);
+    void unbindIQStream(dsp::stream<dsp::complex_t>* stream);
 
-    void setFFTSize(int size) { std::lock_guard<std::recursive_mutex> lck(mtx); _fftSize = size; if (fe) { sdrpp_cuda_frontend_set_fft_size(fe, size); } }
-    void setFFTRate(double rate) { std::lock_guard<std::recursive_mutex> lck(mtx); _fftRate = rate; if (fe) { sdrpp_cuda_frontend_set_fft_rate(fe, rate); } }
-    void setFFTWindow(dsp::window::windowType w) { std::lock_guard<std::recursive_mutex> lck(mtx); _fftWindow = w; if (fe) { sdrpp_cuda_frontend_set_fft_window(fe, (int)w); } }
-    void flushInputBuffer() {}
+    dsp::channel::RxVFO* addVFO(std::string name, double sampleRate, double bandwidth, double offset);
+    void removeVFO(std::string name);
 
-    void start() {
-        std::lock_guard<std::recursive_mutex> lck(mtx);
-        if (running || !_init || !_in) { return; }
-        running = true;
-        worker = std::thread(&IQFrontEnd::workerLoop, this);
-    }
-    void stop() {
-        {
-            std::lock_guard<std::recursive_mutex> lck(mtx);
-            if (!running) { return; }
-            running = false;
-        }
-        if (_in) { _in->stopReader(); }
-        for (auto& [name, vfo] : vfos) { vfo->out.stopWriter(); }
-        for (auto* s : bound) { s->stopWriter(); }
-        if (worker.joinable()) { worker.join(); }
-        if (_in) { _in->clearReadStop(); }
-        for (auto& [name, vfo] : vfos) { vfo->out.clearWriteStop(); }
-        for (auto* s : bound) { s->clearWriteStop(); }
-    }
+    void setFFTSize(int size);
+    void setFFTRate(double rate);
+    void setFFTWindow(dsp::window::windowType fftWindow);
 
-    double getEffectiveSamplerate() { return effectiveSr; }
+    void flushInputBuffer();
+
+    void start();
+    void stop();
+
+    double getEffectiveSamplerate();
+
+    // Extension (not in the reference): the engine handle, for sources that hand raw device samples over instead of
+    // converting on the CPU (sdrpp_cuda_frontend_submit with SDRPP_FMT_U8_RTL ...), and the
+    // blocks delivered so far.
     sdrpp_cuda_frontend* engine() { return fe; }
+    long long blocksDelivered();
 
 protected:
-    void workerLoop() {
-        while (true) {
-            const int count = _in->read();
-            if (count < 0) { return; }
-            std::unique_lock<std::recursive_mutex> lck(mtx);
-            if (!fe || sdrpp_cuda_frontend_submit(fe, SDRPP_FMT_CF32, _in->readBuf, count) < 0 || sdrpp_cuda_frontend_wait(fe) < 0) {
-                fprintf(stderr, "[IQFrontEnd] %s\n", sdrpp_cuda_last_error());
-                _in->flush();
-                continue;
-            }
-            _in->flush();
-            // spectrum rows: acquire/release are always called as a pair, once per line (iq_frontend.cpp:239-248)
-            const float* rows = nullptr;
-            const int nrows = sdrpp_cuda_fft_rows(fe, &rows);
-            for (int r = 0; r < nrows; r++) {
-                float* dst = _acquireFFTBuffer ? _acquireFFTBuffer(_fftCtx) : nullptr;
-                if (dst) { memcpy(dst, rows + (size_t)r * _fftSize, sizeof(float) * (size_t)_fftSize); }
-                if (_releaseFFTBuffer) { _releaseFFTBuffer(_fftCtx); }
-            }
-            // VFO outputs into each RxVFO::out (swap blocks until the consumer flushed the previous block)
-            std::vector<dsp::channel::RxVFO*> live;
-            for (auto& [name, vfo] : vfos) { live.push_back(vfo); }
-            std::vector<dsp::stream<dsp::complex_t>*> taps = bound;
-            const sdrpp_cf32* iq = nullptr;
-            for (auto* vfo : live) {
-                const int n = sdrpp_cuda_vfo_output(fe, vfo->vfoId, &iq, nullptr);
-                if (n > 0) { memcpy(vfo->out.writeBuf, iq, sizeof(dsp::complex_t) * (size_t)n); }
-                vfo->pendingOut = n;
-            }
-            int nraw = 0;
-            if (!taps.empty()) {
-                nraw = sdrpp_cuda_frontend_read_iq(fe, (sdrpp_cf32*)taps[0]->writeBuf, STREAM_BUFFER_SIZE);
-                for (size_t i = 1; i < taps.size(); i++) { memcpy(taps[i]->writeBuf, taps[0]->writeBuf, sizeof(dsp::complex_t) * (size_t)std::max(nraw, 0)); }
-            }
-            lck.unlock(); // never hold the control mutex while blocked on a consumer
-            for (auto* vfo : live) { if (vfo->pendingOut > 0) { vfo->out.swap(vfo->pendingOut); } }
-            for (auto* s : taps) { if (nraw > 0) { s->swap(nraw); } }
-        }
-    }
+    void ingestLoop();
+    void deliverLoop();
+    void deliverBlock();
+    void updateFFTPath(bool updateWaterfall = false);
+
+    static constexpr int kMaxAhead = 4; // blocks submitted and not yet delivered (the engine keeps five result sets)
 
     dsp::stream<dsp::complex_t>* _in = nullptr;
     sdrpp_cuda_frontend* fe = nullptr;
-    std::recursive_mutex mtx;
-    std::thread worker;
-    bool running = false;
+    std::recursive_mutex mtx;   // control surface + every engine call except the blocking waits
+    std::mutex swapMtx;         // held by the deliver thread while it swaps blocks into the output streams
+    std::thread ingestThread, deliverThread;
+    std::mutex flowMtx;
+    std::condition_variable flowCv;
+    long long submitted = 0, delivered = 0;
+    bool running = false, stopping = false;
+
+    // VFOs and raw IQ taps
     std::map<std::string, dsp::channel::RxVFO*> vfos;
     std::vector<dsp::stream<dsp::complex_t>*> bound;
 
+    // Parameters
     double _sampleRate = 0;
     double _decimRatio = 1;
     int _fftSize = 0;
     double _fftRate = 0;
-    dsp::window::windowType _fftWindow = dsp::window::NUTTALL;
+    dsp::window::windowType _fftWindow = dsp::window::windowType::NUTTALL;
     float* (*_acquireFFTBuffer)(void* ctx) = nullptr;
     void (*_releaseFFTBuffer)(void* ctx) = nullptr;
     void* _fftCtx = nullptr;
+
     double effectiveSr = 0;
+
     bool _init = false;
 };

@@ -197,6 +197,18 @@ SDRPP_API int sdrpp_cuda_frontend_submit_pcm(sdrpp_cuda_frontend* fe, const void
  * earlier block's results to reach the host, and the end-to-end rate is no longer bound by one block's latency
  * (copy in + kernels + copy out) divided by the blocks in flight. A sixth submit blocks until the oldest is done. */
 SDRPP_API int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe);
+/* Block until the host-to-device copy of the LAST submitted block has left the caller's buffer, i.e. until that buffer
+ * may be reused (dsp::stream::flush() of the input stream, dsp/stream.h:88-96) -- long before the block's results exist.
+ * Immediate for pageable memory (staged inside submit) and for device sources. */
+SDRPP_API int sdrpp_cuda_frontend_wait_input(sdrpp_cuda_frontend* fe);
+/* Blocks submitted and not yet waited for (0..5). */
+SDRPP_API int sdrpp_cuda_frontend_pending(sdrpp_cuda_frontend* fe);
+/* Wait for everything in flight and DISCARD the results not yet waited for: the next wait() returns the next submit.
+ * (Control calls -- setters, VFO create/destroy -- never discard: blocks submitted before them are still handed back by
+ * wait() in order, with the row layout they were computed with.)
+ * Threading: one thread may submit (submit*, wait_input) while another waits and reads results (wait, vfo_output,
+ * fft_rows, ...); all other calls must be serialised by the caller against both. */
+SDRPP_API int sdrpp_cuda_frontend_drain(sdrpp_cuda_frontend* fe);
 /* Skip the device->host copies of results (kernel-only timing); default 1 = copy. */
 SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled);
 

@@ -1,8 +1,9 @@
+// GUI-LESS TEST HARNESS (include/sdrpp_headless).
 // Stub of ImGui::WaterfallVFO: only the state and offset arithmetic that VFOManager::VFO and the
 // modules touch (reference: core/src/gui/widgets/waterfall.h, waterfall.cpp:1236-1296). No drawing.
 #pragma once
 #include <cstdint>
-#include "../../utils/event.h"
+#include <utils/event.h>
 
 typedef uint32_t ImU32;
 

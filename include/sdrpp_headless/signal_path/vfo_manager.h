@@ -1,13 +1,16 @@
+// GUI-LESS TEST HARNESS (include/sdrpp_headless): not part of the drop-in. In the application the reference's own
+// signal_path/vfo_manager.{h,cpp} is used unchanged on top of the replaced IQFrontEnd / RxVFO; this header restates its
+// surface without ImGui so that tests/cpp/mirror_demo.cpp can drive the path like a module does.
 // VFOManager -- host-side mirror of sigpath::vfoManager (reference: core/src/signal_path/vfo_manager.h:6-67,
 // vfo_manager.cpp). Named VFO registry pairing a dsp::channel::RxVFO with a (stub) waterfall widget.
 #pragma once
 #include <cmath>
 #include <map>
 #include <string>
-#include "../dsp/channel/rx_vfo.h"
+#include <dsp/channel/rx_vfo.h>
 #include "../gui/widgets/waterfall_vfo.h"
-#include "../utils/event.h"
-#include "iq_frontend.h"
+#include <utils/event.h>
+#include <signal_path/iq_frontend.h>
 
 namespace sigpath { extern IQFrontEnd iqFrontEnd; }
 

@@ -248,7 +248,10 @@ struct ResultSet {
     float* rows = nullptr;
     float* zoom = nullptr;
     int nrows = 0;
-    std::vector<int> counts; // per VFO id
+    std::vector<int> counts;      // per VFO id
+    std::vector<uint32_t> offs;   // per VFO id: arena offset of its rows WHEN THE BLOCK WAS SUBMITTED (the layout may change later)
+    std::vector<int> demods;      // per VFO id: demod kind at submit (0: no demod row)
+    std::vector<char> has_audio;
     cudaEvent_t done = nullptr;
     bool pending = false;
 };
@@ -264,7 +267,13 @@ struct sdrpp_cuda_frontend {
     sdrpp_cuda_frontend_cfg cfg{};
     double eff_sr = 0;
     cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr, st_s1b = nullptr, st_d2h = nullptr;
-    cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft = nullptr, ev_tail[2] = { nullptr, nullptr };
+    cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft[2] = { nullptr, nullptr }, ev_tail[2] = { nullptr, nullptr };
+    bool ev_fft_valid[2] = { false, false };
+    // One submitting thread and one waiting thread may use a front end concurrently (submit / wait_input on one,
+    // wait + result getters on the other); everything else is serialised by the caller. wait() drops the lock while
+    // it blocks on the block's completion event.
+    std::mutex api_mtx;
+    int last_in_slot = -1;
     cudaEvent_t ev_s1_fork = nullptr, ev_s1_join = nullptr;
     bool ev_tail_valid[2] = { false, false };
     long long blk = 0; // blocks processed (parity selects the stage-1 output region)
@@ -413,8 +422,8 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     reshape_params(fe->eff_sr, N, fe->cfg.fft_rate, &fe->skip, &fe->nz);
     if (fe->nz < 1) return fail(SDRPP_ERR_ARG, "fft_rate too high for this sample rate");
     const long long interval = (long long)fe->nz + fe->skip;
-    if ((long long)fe->nz + fe->cfg.max_block + 4096 > (1LL << fe->ring_log2))
-        return fail(SDRPP_ERR_ARG, "ring too small for this fft size / block size");
+    if ((long long)fe->nz + 3LL * fe->cfg.max_block + 4096 > (1LL << fe->ring_log2))
+        return fail(SDRPP_ERR_ARG, "ring too small for this fft size / block size (needs nz + 3 * max_block + 4096 samples)");
     std::vector<float> w((size_t)fe->nz + 2);
     design_window(fe->cfg.fft_window, w.data(), fe->nz, true);
     FE_TRY(fe, dev_alloc(&fe->d_window, (size_t)fe->nz, false));
@@ -519,6 +528,7 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
     if (arena > fe->rs_arena_cap) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
         for (int i = 0; i < kSets; i++) {
+            fe->rs[i].counts.clear(); // results of earlier blocks do not survive a growth of the result arena
             if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
             if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
             if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
@@ -666,6 +676,11 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     cudaStream_t st = fe->st;
     const bool prof = fe->profiling;
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[0], st));
+    // The spectrum is the one reader of the ring that is not ordered on `st`: before block i overwrites ring samples,
+    // the spectrum work of block i-2 must be done. Frames of block i-1 may still be in flight; they reach back at most
+    // nz + max_block samples from the end of block i-1, so a ring of nz + 3*max_block samples (what create() sizes and
+    // configure_fft checks) can never be overwritten under a frame that is still being read.
+    if (!prof && fe->cfg.fft_size > 0 && fe->ev_fft_valid[fe->blk & 1]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_fft[fe->blk & 1], 0));
 
     // ---- pre-processing chain: [decim] -> [dc block] -> [conjugate] -> ring (iq_frontend.cpp:30-37)
     const RingRef ring{ fe->ring, fe->ring_mask };
@@ -751,8 +766,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     }
     if (fe->readback && rs.nrows > 0 && (fe->zoom_keep_raw || fe->zoom_out <= 0))
         FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, sf));
-    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[2], st));
-    else FE_TRY(fe, cudaEventRecord(fe->ev_fft, sf));
+    if (prof) { FE_TRY(fe, cudaEventRecord(fe->pev[2], st)); fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false; }
+    else { FE_TRY(fe, cudaEventRecord(fe->ev_fft[par], sf)); fe->ev_fft_valid[par] = true; }
 
     // ---- channelizer ----------------------------------------------------------------------------
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
@@ -965,8 +980,15 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
 
     // ---- results to pinned host memory --------------------------------------------------------------
     rs.counts.assign(fe->vfos.size(), 0);
+    rs.offs.assign(fe->vfos.size(), 0);
+    rs.demods.assign(fe->vfos.size(), 0);
+    rs.has_audio.assign(fe->vfos.size(), 0);
     for (const Group& g : fe->groups)
-        for (int id : g.members) rs.counts[(size_t)id] = g.last_n_final;
+        for (int id : g.members) {
+            const Vfo& v = fe->vfos[(size_t)id];
+            rs.counts[(size_t)id] = g.last_n_final; rs.offs[(size_t)id] = v.out_off; rs.demods[(size_t)id] = v.demod;
+            rs.has_audio[(size_t)id] = (v.post.enabled && v.post_state) ? 1 : 0;
+        }
     // The copies run on their own stream behind the tail, so the tail of the next block does not queue up behind
     // them; the pinned result set and the arena of this parity are free again once the caller has waited for
     // block i (it must, before submitting block i+2).
@@ -985,7 +1007,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         if (fe->post_active > 0)
             FE_TRY(fe, cudaMemcpyAsync(rs.audio, fe->d_arena_audio + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
     }
-    if (!prof) FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_fft, 0)); // the block is done when its rows are on the host too
+    if (!prof) FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_fft[par], 0)); // the block is done when its rows are on the host too
     FE_TRY(fe, cudaEventRecord(rs.done, sd));
     rs.pending = true;
     fe->blk++;
@@ -1004,6 +1026,7 @@ static int wait_set(sdrpp_cuda_frontend* fe, int idx) {
 static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int count, bool device_src, float scale = 1.0f) {
     int rc = fe_check(fe);
     if (rc != SDRPP_OK) return rc;
+    std::lock_guard<std::mutex> api(fe->api_mtx);
     if (fmt < 0 || (fmt >= SDRPP_FMT_COUNT && fmt != kFmtPcmI8 && fmt != kFmtPcmI16)) return fail(SDRPP_ERR_ARG, "unknown sample format");
     if (!in || count <= 0 || count > fe->cfg.max_block) return fail(SDRPP_ERR_ARG, "count must be in 1..max_block");
     const int slot = (int)(fe->seq % kSets);
@@ -1028,6 +1051,9 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
         FE_TRY(fe, cudaEventRecord(fe->ev_h2d[slot], fe->st_copy));
         FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_h2d[slot], 0));
         d_in = fe->d_raw[slot];
+        fe->last_in_slot = slot;
+    } else {
+        fe->last_in_slot = -1;
     }
     rc = process_block(fe, fmt, d_in, count, rs, scale);
     if (rc != SDRPP_OK) return rc;
@@ -1350,7 +1376,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
     }
-    // ring: history for the longest filter + a whole spectrum frame + one block, rounded up
+    // ring: history for the longest filter + a whole spectrum frame + three blocks (the spectrum of block i-1 may still
+    // read while block i is written, see process_block), rounded up to a power of two
     {
         long long need = (long long)fe->cfg.max_block * 3 + std::max(fe->cfg.fft_size, 0) * 2LL + 8192;
         int lg = 16;
@@ -1368,7 +1395,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaStreamCreateWithFlags(&fe->st_s1b, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
     if (cudaEventCreateWithFlags(&fe->ev_ingest, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&fe->ev_fft, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_fft[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_fft[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1428,7 +1456,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_tail) cudaStreamDestroy(fe->st_tail);
     if (fe->st_d2h) cudaStreamDestroy(fe->st_d2h);
     if (fe->st_s1b) cudaStreamDestroy(fe->st_s1b);
-    for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft, fe->ev_tail[0], fe->ev_tail[1], fe->ev_s1_fork, fe->ev_s1_join }) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft[0], fe->ev_fft[1], fe->ev_tail[0], fe->ev_tail[1], fe->ev_s1_fork, fe->ev_s1_join }) if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete fe;
     return SDRPP_OK;
@@ -1437,6 +1465,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
 static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     int rc = fe_check(fe);
     if (rc != SDRPP_OK) return rc;
+    std::lock_guard<std::mutex> api(fe->api_mtx);
     FE_TRY(fe, cudaStreamSynchronize(fe->st_copy));
     FE_TRY(fe, cudaStreamSynchronize(fe->st));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_fft));
@@ -1444,9 +1473,11 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, cudaStreamSynchronize(fe->st_d2h));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_s1b));
     fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;
-    // everything submitted so far is complete: nothing is left to wait for
+    fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false;
+    // Everything submitted so far is complete. Blocks the caller has not waited for yet stay queued: wait() still hands
+    // them back one by one, in order (their result sets remember the row offsets of their own VFO layout), so a control
+    // call between submit and wait loses no output -- like the reference, which never drops samples on a retune.
     for (int i = 0; i < kSets; i++) fe->rs[i].pending = false;
-    if (fe->seq > 0) { fe->waited = fe->seq; fe->cur = (int)((fe->seq - 1) % kSets); }
     return SDRPP_OK;
 }
 
@@ -1667,12 +1698,26 @@ int sdrpp_cuda_frontend_submit_pcm(sdrpp_cuda_frontend* fe, const void* packet, 
 int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe) {
     int rc = fe_check(fe);
     if (rc != SDRPP_OK) return rc;
+    std::unique_lock<std::mutex> api(fe->api_mtx);
     if (fe->seq == 0) return fail(SDRPP_ERR_STATE, "nothing submitted");
     // oldest block not yet waited for
     if (fe->waited < fe->seq - kSets) fe->waited = fe->seq - kSets;
     if (fe->waited >= fe->seq) fe->waited = fe->seq - 1;
     const int slot = (int)(fe->waited % kSets);
-    if ((rc = wait_set(fe, slot)) != SDRPP_OK) return rc;
+    ResultSet& rs = fe->rs[slot];
+    if (rs.pending) {
+        // block on the completion event without the lock: the submitting thread may enqueue the next blocks meanwhile
+        cudaEvent_t done = rs.done;
+        api.unlock();
+        cudaError_t e = cudaEventSynchronize(done);
+        api.lock();
+        if (e != cudaSuccess) {
+            fe->sticky = std::string("cudaEventSynchronize(done): ") + cudaGetErrorString(e);
+            set_last_error(fe->sticky);
+            return SDRPP_ERR_CUDA;
+        }
+        rs.pending = false;
+    }
     fe->cur = slot;
     fe->waited++;
     if (fe->profiling && fe->pev_valid && fe->waited == fe->seq) {
@@ -1685,8 +1730,36 @@ int sdrpp_cuda_frontend_wait(sdrpp_cuda_frontend* fe) {
     return SDRPP_OK;
 }
 
-int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled) {
+int sdrpp_cuda_frontend_wait_input(sdrpp_cuda_frontend* fe) {
+    int rc = fe_check(fe);
+    if (rc != SDRPP_OK) return rc;
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> api(fe->api_mtx);
+        if (fe->last_in_slot >= 0) ev = fe->ev_h2d[fe->last_in_slot];
+    }
+    if (ev) FE_TRY(fe, cudaEventSynchronize(ev));
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_drain(sdrpp_cuda_frontend* fe) {
     int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    std::lock_guard<std::mutex> api(fe->api_mtx);
+    if (fe->seq > 0) { fe->waited = fe->seq; fe->cur = (int)((fe->seq - 1) % kSets); }
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_pending(sdrpp_cuda_frontend* fe) {
+    if (!fe) return fail(SDRPP_ERR_ARG, "null front end");
+    std::lock_guard<std::mutex> api(fe->api_mtx);
+    long long w = fe->waited;
+    if (w < fe->seq - kSets) w = fe->seq - kSets;
+    return (int)(fe->seq - w);
+}
+
+int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled) {
+    int rc = sdrpp_cuda_frontend_drain(fe); // a measurement control, not a reference setter: starts from a clean slate
     if (rc != SDRPP_OK) return rc;
     fe->readback = enabled != 0;
     return SDRPP_OK;
@@ -1698,9 +1771,11 @@ int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int id, const sdrpp_cf32** iq
     if (rc != SDRPP_OK) return rc;
     if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
     const ResultSet& rs = fe->rs[fe->cur];
-    const int n = (size_t)id < rs.counts.size() ? rs.counts[(size_t)id] : 0;
-    if (iq) *iq = rs.iq ? rs.iq + v->out_off : nullptr;
-    if (demod) *demod = (v->demod != SDRPP_DEMOD_NONE && rs.demod) ? rs.demod + v->out_off : nullptr;
+    const bool have = (size_t)id < rs.counts.size();   // false: the VFO did not exist when that block was submitted
+    const int n = have ? rs.counts[(size_t)id] : 0;
+    const uint32_t off = have ? rs.offs[(size_t)id] : 0;
+    if (iq) *iq = (rs.iq && have) ? rs.iq + off : nullptr;
+    if (demod) *demod = (have && rs.demods[(size_t)id] != SDRPP_DEMOD_NONE && rs.demod) ? rs.demod + off : nullptr;
     return n;
 }
 
@@ -1776,8 +1851,9 @@ int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int id, const float** audio) {
     if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
     if (!v->post.enabled) return fail(SDRPP_ERR_STATE, "post-detector stages are not enabled for this VFO");
     const ResultSet& rs = fe->rs[fe->cur];
-    if (audio) *audio = rs.audio ? rs.audio + v->out_off : nullptr;
-    return (size_t)id < rs.counts.size() ? rs.counts[(size_t)id] : 0;
+    const bool have = (size_t)id < rs.counts.size() && rs.has_audio[(size_t)id];
+    if (audio) *audio = (rs.audio && have) ? rs.audio + rs.offs[(size_t)id] : nullptr;
+    return have ? rs.counts[(size_t)id] : 0;
 }
 
 int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows) {
@@ -1830,7 +1906,7 @@ int sdrpp_cuda_frontend_set_stage1_mode(sdrpp_cuda_frontend* fe, int mode) {
 }
 void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe) { return fe ? (void*)fe->st : nullptr; }
 int sdrpp_cuda_frontend_set_profiling(sdrpp_cuda_frontend* fe, int enabled) {
-    int rc = fe_quiesce(fe);
+    int rc = sdrpp_cuda_frontend_drain(fe);
     if (rc != SDRPP_OK) return rc;
     fe->profiling = enabled != 0;
     fe->pev_valid = false;

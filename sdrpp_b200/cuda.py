@@ -36,6 +36,7 @@ sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_
 sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
 sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio sdrpp_cuda_vfo_set_if_chain sdrpp_cuda_vfo_squelch_state
 sdrpp_cuda_frontend_set_stage1_mode sdrpp_cuda_frontend_stage1_tensor_launches
+sdrpp_cuda_frontend_wait_input sdrpp_cuda_frontend_pending sdrpp_cuda_frontend_drain
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -111,6 +112,9 @@ def lib():
         L.sdrpp_cuda_frontend_submit.argtypes = [_vp, _i, _vp, _i]
         L.sdrpp_cuda_frontend_submit_device.argtypes = [_vp, _i, _vp, _i]
         L.sdrpp_cuda_frontend_wait.argtypes = [_vp]
+        L.sdrpp_cuda_frontend_wait_input.argtypes = [_vp]
+        L.sdrpp_cuda_frontend_pending.argtypes = [_vp]
+        L.sdrpp_cuda_frontend_drain.argtypes = [_vp]
         L.sdrpp_cuda_vfo_output.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]
         L.sdrpp_cuda_fft_rows.argtypes = [_vp, C.POINTER(_vp)]
         L.sdrpp_cuda_vfo_set_post.argtypes = [_vp, _i, C.POINTER(PostCfg)]
@@ -369,6 +373,17 @@ class Frontend:
 
     def wait(self):
         _check(lib().sdrpp_cuda_frontend_wait(self.h), "wait")
+
+    def wait_input(self):
+        _check(lib().sdrpp_cuda_frontend_wait_input(self.h), "wait_input")
+
+    def drain(self):
+        """Wait for everything in flight and discard results not yet waited for."""
+        _check(lib().sdrpp_cuda_frontend_drain(self.h), "drain")
+
+    @property
+    def pending(self):
+        return lib().sdrpp_cuda_frontend_pending(self.h)
 
     def process(self, fmt, raw):
         self.submit(fmt, raw)

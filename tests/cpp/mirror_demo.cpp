@@ -8,12 +8,19 @@
 //      and <outprefix>.rows.f32 (spectrum rows, BH7 window, saturated rate sr/fftN)
 //   mirror_demo pcm <in.cf32> <pcmType> <out.packet> <out.cf32>
 //      SampleStreamCompressor::process on the whole file, then SampleStreamDecompressor::process on that packet
+//   mirror_demo bench <sr> <block> <fftN> <nvfo> <nblocks> <readers>
+//      end-to-end throughput THROUGH THE C++ INTERFACE modules use: a source thread swaps pinned cf32 blocks into the
+//      input dsp::stream, sigpath::iqFrontEnd (saturated fftN-point Blackman-Harris-4 spectrum with acquire/release
+//      callbacks) feeds nvfo VFOs (alternating NFM 12.5k->48k / AM 12k->24k on the bench grid) created through
+//      sigpath::vfoManager, and `readers` consumer threads read()/flush() every VFO::output stream. Prints one JSON line.
 #define SDRPP_SIGPATH_IMPLEMENTATION
 #include <signal_path/signal_path.h>
 #include <dsp/compression/sample_stream_compressor.h>
 #include <dsp/compression/sample_stream_decompressor.h>
 
 #include <atomic>
+#include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <string>
@@ -107,8 +114,70 @@ static int pcmRoundTrip(const char* inPath, int type, const char* packetPath, co
     return n == count ? 0 : 1;
 }
 
+static int benchRun(double sr, int block, int fftN, int nvfo, int nblocks, int nreaders) {
+    if (sdrpp_cuda_init(0) < 0) { fprintf(stderr, "%s\n", sdrpp_cuda_last_error()); return 70; }
+    g_rowbuf.resize((size_t)fftN);
+    static std::atomic<long long> rowsSeen{0};
+    dsp::stream<dsp::complex_t> src;
+    sigpath::iqFrontEnd.init(&src, sr, true, 1, false, fftN, sr / fftN, dsp::window::BLACKMAN_HARRIS4,
+                             [](void*) -> float* { return g_rowbuf.data(); }, [](void*) { rowsSeen++; }, NULL);
+    std::vector<VFOManager::VFO*> vfos;
+    for (int i = 0; i < nvfo; i++) {
+        const double off = ((double)i - (nvfo - 1) / 2.0) * (0.9 * sr / nvfo);
+        const bool nfm = (i % 2) == 0;
+        auto* v = sigpath::vfoManager.createVFO("vfo" + std::to_string(i), ImGui::WaterfallVFO::REF_CENTER, off, nfm ? 12500.0 : 12000.0,
+                                                nfm ? 48000.0 : 24000.0, 1000.0, 200000.0, true);
+        if (!v) { fprintf(stderr, "createVFO failed: %s\n", sdrpp_cuda_last_error()); return 71; }
+        vfos.push_back(v);
+    }
+    // both halves of the input stream's double buffer hold a synthetic block (tone + pseudo-random noise); the source
+    // thread then only swaps, like a driver whose DMA target is the stream buffer
+    auto fill = [&](dsp::complex_t* b, uint32_t seed) {
+        uint32_t s = seed;
+        for (int i = 0; i < block; i++) {
+            s = s * 1664525u + 1013904223u; const float a = (float)(int32_t)s * (0.01f / 2147483648.0f);
+            s = s * 1664525u + 1013904223u; const float c = (float)(int32_t)s * (0.01f / 2147483648.0f);
+            const float ph = 0.001f * (float)(i % 6283);
+            b[i] = dsp::complex_t{ 0.3f * cosf(ph) + a, 0.3f * sinf(ph) + c };
+        }
+    };
+    fill(src.writeBuf, 1u); fill(src.readBuf, 2u);
+    std::atomic<long long> samplesOut{0};
+    std::vector<std::thread> readers;
+    for (int r = 0; r < nreaders; r++) {
+        readers.emplace_back([&, r] {
+            long long local = 0;
+            while (true) {
+                for (size_t i = (size_t)r; i < vfos.size(); i += (size_t)nreaders) {
+                    int n = vfos[i]->output->read();
+                    if (n < 0) { samplesOut += local; return; }
+                    local += n;
+                    vfos[i]->output->flush();
+                }
+            }
+        });
+    }
+    sigpath::iqFrontEnd.start();
+    const int warm = 8;
+    for (int b = 0; b < warm; b++) { if (!src.swap(block)) { return 74; } }
+    while (sigpath::iqFrontEnd.blocksDelivered() < warm) { std::this_thread::yield(); }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int b = 0; b < nblocks; b++) { if (!src.swap(block)) { return 74; } }
+    while (sigpath::iqFrontEnd.blocksDelivered() < warm + nblocks) { std::this_thread::yield(); }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    sigpath::iqFrontEnd.stop();
+    for (auto* v : vfos) { v->output->stopReader(); }
+    for (auto& t : readers) { t.join(); }
+    printf("{\"e2e_cpp_msps\": %.1f, \"blocks\": %d, \"block\": %d, \"vfos\": %d, \"fft\": %d, \"reader_threads\": %d, \"seconds\": %.4f, "
+           "\"spectrum_rows\": %lld, \"vfo_samples_read\": %lld}\n",
+           (double)nblocks * block / dt / 1e6, nblocks, block, nvfo, fftN, nreaders, dt, rowsSeen.load(), samplesOut.load());
+    for (auto* v : vfos) { sigpath::vfoManager.deleteVFO(v); }
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "host") { return hostSelfTest(); }
+    if (argc == 8 && std::string(argv[1]) == "bench") { return benchRun(atof(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoi(argv[6]), atoi(argv[7])); }
     if (argc == 6 && std::string(argv[1]) == "pcm") { return pcmRoundTrip(argv[2], atoi(argv[3]), argv[4], argv[5]); }
     if (argc < 10 || std::string(argv[1]) != "run") { fprintf(stderr, "usage: see source\n"); return 64; }
     const std::string inPath = argv[2], prefix = argv[6];

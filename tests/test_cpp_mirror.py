@@ -1,8 +1,10 @@
-"""The C++ host-side mirror of the reference interface (include/sdrpp/): dsp::stream / dsp::block /
-dsp::Processor, dsp::channel::RxVFO, IQFrontEnd, VFOManager, sigpath:: singletons. A small C++ program
-(tests/cpp/mirror_demo.cpp) uses them exactly as an SDR++ module would and is checked against the oracle."""
+"""The C++ drop-in (include/sdrpp/ + sdrpp_b200/host/): dsp::stream, dsp::channel::RxVFO and IQFrontEnd replaced over
+the C ABI, everything else -- dsp::block, dsp::Processor, dsp::complex_t, threading, logging -- the reference's own
+files through the source overlay. A small GUI-less C++ program (tests/cpp/mirror_demo.cpp) uses them exactly as an
+SDR++ module would and is checked against the oracle."""
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -16,13 +18,16 @@ DEMO = os.path.join(ROOT, "tests", "cpp", "mirror_demo")
 
 @pytest.fixture(scope="module")
 def demo(cuda_lib):
-    src = os.path.join(ROOT, "tests", "cpp", "mirror_demo.cpp")
-    deps = [src] + [os.path.join(dp, f) for dp, _, fs in os.walk(os.path.join(ROOT, "include")) for f in fs]
-    if not os.path.exists(DEMO) or any(os.path.getmtime(d) > os.path.getmtime(DEMO) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include", "sdrpp"), "-I" + os.path.join(ROOT, "include"),
-                               src, "-o", DEMO, "-L" + os.path.join(ROOT, "sdrpp_b200"), "-lsdrpp_cuda",
-                               "-Wl,-rpath," + os.path.join(ROOT, "sdrpp_b200"), "-lpthread"])
-    return DEMO
+    """The demo is compiled against the source overlay of the reference tree (tools/make_overlay.py), so it can only be
+    (re)built where /root/reference exists; on the GPU box the binary built here is used if its content stamp is current."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_overlay
+    if os.path.isdir("/root/reference/core/src"):
+        return make_overlay.build_demo()
+    if not make_overlay.demo_is_current():
+        pytest.fail("tests/cpp/mirror_demo is missing or stale and the reference tree is not here to rebuild it: "
+                    "run __graft_entry__.build() in the build container")
+    return make_overlay.DEMO
 
 
 def test_host_side_stream_block_semantics(demo):
