@@ -1,16 +1,18 @@
 #!/usr/bin/env python3
 """bench.py -- sustained input MS/s of the SDR++ signal-path hot loop on B200.
 
-Workload (BASELINE.json configs[4] + the 1M-point spectrum the metric is quoted on): 122.88 MS/s
-complex64 IQ in blocks of 614,400 samples (sr/200), a saturated 1,048,576-point Blackman-Harris-4
-spectrum (every sample enters one frame) and 512 VFOs alternating NFM (12.5 kHz -> 48 kS/s,
-quadrature demod) and AM (12 kHz -> 24 kS/s, magnitude). A "step" is one IQ block through
-conversion/ingest -> spectrum frames -> 512-VFO channelizer -> demod front ends.
+Default workload = BASELINE.json configs[4] + the 1M-point spectrum the metric is quoted on (--config 5): 122.88 MS/s
+complex64 IQ in blocks of 614,400 samples (sr/200), a saturated 1,048,576-point Blackman-Harris-4 spectrum (every sample
+enters one frame) and 512 VFOs alternating NFM (12.5 kHz -> 48 kS/s, quadrature demod) and AM (12 kHz -> 24 kS/s,
+magnitude). --config 2 / 3 / 4 time the other BASELINE configurations (sdrpp_b200/workloads.py) with their packed sample
+formats going over the host link packed. A "step" is one IQ block through conversion/ingest -> [front-end decimation] ->
+spectrum frames -> channelizer -> demod front ends.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C] [--impl reference]
 
-N > 1 (torchrun, one rank per GPU): the VFO set is sharded across ranks, every step the block is
-broadcast from rank 0 over NCCL (NVLink) and the spectrum stays on rank 0.
+N > 1 (torchrun, one rank per GPU): the VFO set is sharded across ranks; the library itself (sdrpp_cuda_comm_*, NCCL
+over NVLink) broadcasts every raw block from rank 0 inside sdrpp_cuda_frontend_submit*, the spectrum stays on rank 0
+(SURVEY 8e). torch.distributed is used for the barrier and the max-over-ranks reductions only.
 """
 import argparse
 import collections
@@ -27,71 +29,48 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SR = 122.88e6
-BLOCK = 614400
-FFT_N = 1 << 20
-NVFO = 512
-NFM = (48e3, 12.5e3, 1)   # outSR, bw, demod (quadrature)
-AM = (24e3, 12e3, 2)      # outSR, bw, demod (magnitude)
-WORKLOAD = ("122.88 MS/s cf32 IQ, blocks of 614400; saturated 1048576-pt Blackman-Harris-4 spectrum; "
-            "512 VFOs alternating NFM 12.5k->48k (quadrature) / AM 12k->24k (magnitude)")
+from sdrpp_b200 import workloads  # noqa: E402
+
 METRIC = "sustained input MS/s (1M-pt FFT + N-VFO channelizer); % of B200 HBM roofline"
-
-
-def vfo_list():
-    from sdrpp_b200 import synth
-    offs = synth.vfo_grid(NVFO, SR)
-    return [((NFM if i % 2 == 0 else AM)[0], (NFM if i % 2 == 0 else AM)[1], float(offs[i]), (NFM if i % 2 == 0 else AM)[2])
-            for i in range(NVFO)]
-
-
-def make_blocks(nblocks, seed=5):
-    """Synthetic IQ: a few tones/carriers + white noise at -40 dBFS, complex64, nblocks x BLOCK."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    n = nblocks * BLOCK
-    out = np.empty(n, dtype=np.complex64)
-    offs = [v[2] for v in vfo_list()[::64]]
-    chunk = 1 << 20
-    sigma = np.float32(10.0 ** (-40.0 / 20.0) / np.sqrt(2.0))
-    for s in range(0, n, chunk):
-        m = min(chunk, n - s)
-        t = (np.arange(s, s + m, dtype=np.float64)) / SR
-        x = np.zeros(m, dtype=np.complex64)
-        for i, f in enumerate(offs):
-            ph = (2.0 * np.pi) * ((f * t) % 1.0)
-            x += np.float32(0.05) * (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64)
-        x += sigma * (rng.standard_normal(m, dtype=np.float32) + 1j * rng.standard_normal(m, dtype=np.float32))
-        out[s:s + m] = x
-    return out.reshape(nblocks, BLOCK)
 
 
 # ---------------------------------------------------------------------------------------------
 # algorithmic work per input sample (SURVEY 8d)
 # ---------------------------------------------------------------------------------------------
-def algorithmic_model(vfos):
+def algorithmic_model(w, vfos):
+    """Per RAW input sample of workload w, for the VFO list `vfos` (a rank's shard): the reference's own flop count
+    (NCO 8 + 4 per tap and output for every FIR) and the minimal bytes of SURVEY 8d."""
     from sdrpp_b200 import cuda
-    flops = 0.0
-    out_bytes = 0.0
-    s1_flops = 0.0
+    flops = s1_flops = out_bytes = 0.0
     for (osr, bw, _off, demod) in vfos:
-        info, _ = cuda.design_resampler(SR, osr)
-        f = 8.0  # NCO complex multiply + phase advance per input sample
-        rate = 1.0
+        info, _ = cuda.design_resampler(w.eff_sr, osr)
+        f, rate = 8.0, 1.0
         stages = cuda.design_decim_plan(info["predec"]) if info["mode"] in (0, 1) else []
         for i, (d, taps) in enumerate(stages):
-            c = 4.0 * len(taps) * rate / d   # 2 mul + 2 add per tap per output
+            c = 4.0 * len(taps) * rate / d
             f += c
             if i == 0:
                 s1_flops += 8.0 + c
             rate /= d
+        if not stages:
+            s1_flops += 8.0
         if info["mode"] in (0, 2):
-            f += 4.0 * info["tpp"] * (osr / SR)
+            f += 4.0 * info["tpp"] * (osr / w.eff_sr)
         if bw != osr:
-            f += 4.0 * int(3.8 * osr / (bw / 20.0)) * (osr / SR)
+            f += 4.0 * int(3.8 * osr / (bw / 20.0)) * (osr / w.eff_sr)
         flops += f
-        out_bytes += (osr / SR) * (8 + (4 if demod else 0))
-    return dict(flops_per_sample=flops, stage1_flops_per_sample=s1_flops, chan_bytes_per_sample=8.0 + out_bytes,
-                fft_bytes_per_sample=12.0, fft_flops_per_sample=5.0 * 20 + 12)
+        out_bytes += (osr / w.eff_sr) * (8 + (4 if demod else 0))
+    k = 1.0 / w.decim   # per raw sample
+    fe_flops = 0.0
+    if w.decim > 1:
+        rate = 1.0
+        for d, taps in cuda.design_decim_plan(w.decim):
+            fe_flops += 4.0 * len(taps) * rate / d
+            rate /= d
+    return dict(flops_per_sample=flops * k, stage1_flops_per_sample=s1_flops * k, chan_bytes_per_sample=(8.0 + out_bytes) * k,
+                convert_bytes_per_sample=w.bytes_per_sample + 8.0, decim_bytes_per_sample=(8.0 + 8.0 / w.decim) if w.decim > 1 else 0.0,
+                decim_flops_per_sample=fe_flops, fft_bytes_per_sample=(w.bytes_per_sample + 4.0) * k if w.decim == 1 else 12.0 * k,
+                fft_flops_per_sample=(5.0 * np.log2(w.fft_size) + 12) * k)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -165,78 +144,98 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
-def cpu_reference(nblocks=2, sample_vfos=None, fft_frames=1):
-    """Times the reference's CPU implementation of the path on a bounded sample of the workload:
-    `sample_vfos` of the 512 VFOs (thread-per-VFO multiplexed on all host cores, as
-    ref_bench_channelizer does) on nblocks blocks plus fft_frames 1M-point spectrum lines, scaled to
-    the full VFO count. Returns (MS/s, info dict)."""
+def cpu_reference(w, nblocks=2, sample_vfos=None, fft_frames=1):
+    """Times the reference's CPU implementation of workload w on a bounded sample: `sample_vfos` of its VFOs
+    (thread-per-VFO multiplexed on all host cores, like the reference's thread-per-block model) on nblocks blocks, one
+    spectrum line on one thread, and -- where the workload has them -- the source conversion loop and the front-end
+    PowerDecimator on one thread each (the reference runs every block on a thread of its own: the stream advances at
+    the pace of the slowest stage). Returns (MS/s of raw input, info dict)."""
     from oracle import pyoracle as po
     cores = os.cpu_count() or 1
-    kind = "reference"
-    if po.have_ref("fast"):
-        lib = po.Ref("fast")
-    elif po.have_ref(""):
-        lib = po.Ref("")
-    else:
-        lib = None
-    vf = vfo_list()
+    lib = po.Ref("fast") if po.have_ref("fast") else (po.Ref("") if po.have_ref("") else None)
+    port = po.Port()
+    kind = "reference" if lib is not None else "port"
+    vf = w.vfos
     if sample_vfos is None:
-        sample_vfos = min(NVFO, 2 * cores)
-    pick = [vf[(i * NVFO) // sample_vfos] for i in range(sample_vfos)]
-    if "blocks" not in _CPU_CACHE:
-        _CPU_CACHE["blocks"] = make_blocks(2, seed=5).reshape(-1)  # 1,228,800 samples >= one spectrum frame
-    blocks = _CPU_CACHE["blocks"]
-    if lib is not None:
-        win = lib.window(po.WIN_BH4, FFT_N)
-        # the block handed to every VFO thread is the first BLOCK samples; the spectrum thread reads FFT_N
-        buf = np.ascontiguousarray(blocks[:max(BLOCK, FFT_N)])
-        # ref_bench_channelizer(count=len(block)): pass exactly BLOCK for the VFOs by timing the two legs apart
-        t_ch = lib.bench_channelizer(SR, pick, buf[:BLOCK], nblocks, cores)
-        t_fft = lib.bench_channelizer(SR, pick[:1], buf, 0, 1, fft=(FFT_N, win, fft_frames))
+        sample_vfos = min(w.nvfo, 2 * cores)
+    pick = [vf[(i * w.nvfo) // sample_vfos] for i in range(sample_vfos)]
+    need = max(w.block, w.fft_size * w.decim)
+    nb = -(-need // w.block)
+    key = ("raw", w.idx)
+    if key not in _CPU_CACHE:
+        _CPU_CACHE[key] = w.make_blocks(nb)
+    raw = _CPU_CACHE[key]
+    stages = {}
+    # source conversion (A1) on one thread
+    if w.fmt != po.FMT_CF32:
+        t0 = time.perf_counter()
+        x_blocks = [port.convert(w.fmt, raw[b]) for b in range(nb)]
+        stages["convert"] = (time.perf_counter() - t0) / (nb * w.block)
     else:
-        kind = "port"
-        port = po.Port()
+        x_blocks = [raw[b] for b in range(nb)]
+    # front-end PowerDecimator (A3) on one thread
+    if w.decim > 1:
+        pd = (lib or port).powerdecim(w.decim)
+        t0 = time.perf_counter()
+        x_blocks = [pd.process(x) for x in x_blocks]
+        stages["front_end_decimation"] = (time.perf_counter() - t0) / (nb * w.block)
+    stream = np.ascontiguousarray(np.concatenate(x_blocks))
+    blk_eff = w.block // w.decim
+    if lib is not None:
+        win = lib.window(w.fft_window, w.fft_size)
+        t_ch = lib.bench_channelizer(w.eff_sr, pick, stream[:blk_eff], nblocks, min(cores, sample_vfos))
+        t_fft = lib.bench_channelizer(w.eff_sr, pick[:1], stream[:w.fft_size], 0, 1, fft=(w.fft_size, win, fft_frames))
+        threads = min(cores, sample_vfos)
+    else:
         t0 = time.perf_counter()
         for v in pick:
-            o = port.rxvfo(SR, v[0], v[1], v[2])
+            o = port.rxvfo(w.eff_sr, v[0], v[1], v[2])
             for _ in range(nblocks):
-                o.process(blocks[:BLOCK])
+                o.process(stream[:blk_eff])
         t_ch = time.perf_counter() - t0
-        cores_used = 1
         t0 = time.perf_counter()
-        win = port.window(po.WIN_BH4, FFT_N)
+        win = port.window(w.fft_window, w.fft_size)
         for _ in range(fft_frames):
-            port.spectrum(FFT_N, blocks[:FFT_N], win, want64=False)
+            port.spectrum(w.fft_size, stream[:w.fft_size], win, want64=False)
         t_fft = time.perf_counter() - t0
-        cores = cores_used
-    # the channelizer workers and the spectrum thread run concurrently in the reference; the stream
-    # advances at the pace of the slower consumer
-    sec_per_sample_ch = (t_ch * (NVFO / float(sample_vfos))) / (nblocks * BLOCK)
-    sec_per_sample_fft = t_fft / (fft_frames * FFT_N)
-    msps = 1e-6 / max(sec_per_sample_ch, sec_per_sample_fft)
-    info = dict(kind=kind, cores=cores,
-                sample=f"{sample_vfos} of {NVFO} VFOs x {nblocks} blocks of {BLOCK} (scaled x{NVFO / sample_vfos:g}) on {cores} threads "
-                       f"+ {fft_frames} x 1M-pt spectrum line on 1 thread; generic-VOLK shim, -O3 -ffast-math",
-                channelizer_msps=1e-6 / sec_per_sample_ch, spectrum_msps=1e-6 / sec_per_sample_fft,
-                seconds=t_ch + t_fft)
+        threads = 1
+    stages["channelizer"] = (t_ch * (w.nvfo / float(sample_vfos))) / (nblocks * w.block)
+    stages["spectrum"] = t_fft / (fft_frames * w.fft_size * w.decim)
+    slowest = max(stages, key=stages.get)
+    msps = 1e-6 / stages[slowest]
+    info = dict(kind=kind, cores=threads,
+                sample=f"{sample_vfos} of {w.nvfo} VFOs x {nblocks} blocks of {w.block} (scaled x{w.nvfo / sample_vfos:g}) on {threads} threads "
+                       f"+ {fft_frames} x {w.fft_size}-pt spectrum line on 1 thread"
+                       + (" + source conversion loop on 1 thread" if "convert" in stages else "")
+                       + (f" + PowerDecimator x{w.decim} on 1 thread" if w.decim > 1 else "")
+                       + "; reference dsp/ headers, generic-VOLK shim, -O3 -ffast-math; stream rate = the slowest stage",
+                stage_msps={k: 1e-6 / v for k, v in stages.items()}, slowest_stage=slowest, seconds=t_ch + t_fft)
     return msps, info
+
+
+def config_dict(w, **extra):
+    d = {"workload": w.describe(), "baseline_config": w.idx, "block": w.block, "vfos": w.nvfo, "fft": w.fft_size}
+    d.update(extra)
+    return d
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    w = workloads.config(args.config)
     vals, info = [], None
     for i in range(args.warmup + args.steps):
-        v, info = cpu_reference(nblocks=1)
+        v, info = cpu_reference(w, nblocks=1)
         if i >= args.warmup:
             vals.append(v)
     value = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * BLOCK / (value * 1e6), "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * w.block / (value * 1e6), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "block": BLOCK, "vfos": NVFO, "fft": FFT_N},
-        "cpu_baseline": {"value": value, "unit": "MS/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
+        "config": config_dict(w),
+        "cpu_baseline": {"value": value, "unit": "MS/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+                         "stage_msps": info["stage_msps"], "slowest_stage": info["slowest_stage"]},
         "e2e": {"value": value, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -249,86 +248,88 @@ def run_reference(args, rank, world):
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from sdrpp_b200 import cuda
-    from oracle import pyoracle as po  # only for the cpu_baseline leg below (rank 0, N = 1)
+    from sdrpp_b200 import cuda, shard
 
     if cuda.device_count() <= 0:
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+    w = workloads.config(args.config)
     torch.cuda.set_device(local_rank)
     cuda.init(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
     if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # any level >= VERSION makes NCCL print a banner on stdout; rank 0 prints ONE JSON line
+        # rank 0 prints ONE JSON line on stdout: NCCL's own log (NCCL_DEBUG, if the caller set it) goes to stderr
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
+        # the library owns the communicator of the data path; torch.distributed only carries its 128-byte id
+        box = [cuda.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = cuda.Comm(box[0], rank, world, local_rank)
 
-    if world > 1:
-        # the stage-1 kernel is persistent (one CTA per SM): leave a few SMs to the NCCL broadcast of the next block
-        os.environ.setdefault("SDRPP_RESERVE_SMS", "8")
-    vf_all = vfo_list()
-    # shard the VFO set across ranks, balanced by per-VFO cost (sdrpp_b200/shard.py); no data-path collective
-    from sdrpp_b200 import shard
-    costs = [shard.vfo_cost(SR, v[0], v[1], cuda.design_resampler, cuda.design_decim_plan) for v in vf_all]
-    # rank 0 also ingests, broadcasts and runs the 1M-point spectrum (~25 us per step); at the measured
-    # ~32 ns per cost unit of stage 1 (0.256 ms for 512 VFOs x 15.4) that is ~770 units of VFO work it cannot take
-    base = [770.0] + [0.0] * (world - 1) if world > 1 else None
-    mine = [vf_all[i] for i in shard.shard_vfos(costs, world, base)[rank]]
+    # shard the VFO set across ranks, balanced by per-VFO cost (sdrpp_b200/shard.py); rank 0 also ingests, broadcasts and
+    # runs the spectrum, so it gets a base load
+    costs = [shard.vfo_cost(w.eff_sr, v[0], v[1], cuda.design_resampler, cuda.design_decim_plan) for v in w.vfos]
+    base = [args.rank0_base_load] + [0.0] * (world - 1) if world > 1 else None
+    mine_idx = shard.shard_vfos(costs, world, base)[rank]
+    mine = [w.vfos[i] for i in mine_idx]
     with_fft = (rank == 0)
-    fe = cuda.Frontend(SR, fft_size=FFT_N if with_fft else 0, fft_rate=SR / FFT_N, fft_window=cuda.WIN_BH4, max_block=BLOCK)
+
+    def new_frontend():
+        f = cuda.Frontend(w.sr, decim_ratio=w.decim, fft_size=w.fft_size if with_fft else 0, fft_rate=w.fft_rate,
+                          fft_window=w.fft_window, max_block=w.block)
+        if comm is not None:
+            f.set_comm(comm, 0)
+        return f
+
+    fe = new_frontend()
     ids = [fe.add_vfo(*v) for v in mine]
     st = torch.cuda.ExternalStream(fe.stream, device=dev)
 
-    NB = args.input_blocks
-    host = make_blocks(NB) if rank == 0 else None
-    d_blocks = torch.empty((NB, BLOCK, 2), dtype=torch.float32, device=dev)  # > L2 (126 MB) when NB >= 32
+    # ---- source blocks resident in HBM on the ingest rank, laid out over more than the L2 (126 MB) --------------------
+    blk_bytes = w.block * w.bytes_per_sample
+    nbase = max(4, min(args.input_blocks, -(-(160 << 20) // blk_bytes)))
+    NB = max(nbase, -(-(160 << 20) // blk_bytes)) if rank == 0 else 0
+    host = w.make_blocks(nbase) if rank == 0 else None
+    d_src = None
     if rank == 0:
-        d_blocks.copy_(torch.from_numpy(host.view(np.float32).reshape(NB, BLOCK, 2)))
-    # Multi-GPU: the IQ stream is broadcast in buckets of KB consecutive blocks (one NCCL call per bucket, straight out
-    # of the source buffer on the ingest rank, into one of two staging buckets elsewhere). The enqueue cost of a
-    # collective (~25-30 us of host time through torch.distributed) is what bounded the loop with one broadcast per
-    # block (tools/mgpu_probe.py); the bucket size is chosen for that latency, not for the link. Every block is
-    # still submitted on its own.
-    KB = shard.fit_bucket(args.bcast_blocks, NB) if world > 1 else 1
-    if world > 1:
-        d_stage = [torch.empty((KB, BLOCK, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+        hb = torch.from_numpy(host.view(np.uint8).reshape(nbase, blk_bytes))
+        d_src = torch.empty((NB, blk_bytes), dtype=torch.uint8, device=dev)
+        for s in range(0, NB, nbase):
+            n = min(nbase, NB - s)
+            d_src[s:s + n].copy_(hb[:n])
     torch.cuda.synchronize()
 
-    consumed = [None, None]  # per staging bucket: event after which the front end no longer reads it
-    pos = [0]                # blocks submitted in the current phase (every phase starts on a bucket boundary)
-
-    def step_device(_i=None):
-        i = pos[0]
-        pos[0] += 1
-        if world > 1:
-            k, j, base = shard.bucket_slot(i, KB, NB)
-            if j == 0:
-                # NVLink broadcast of the next KB blocks from the ingest GPU; the broadcast of bucket b+1 overlaps the
-                # kernels of bucket b
-                cur = torch.cuda.current_stream()
-                if consumed[k] is not None:
-                    cur.wait_event(consumed[k])
-                dist.broadcast(d_blocks[base:base + KB] if rank == 0 else d_stage[k], src=0)
-                ev = torch.cuda.Event()
-                ev.record(cur)
-                st.wait_event(ev)
-            blk = d_blocks[base + j] if rank == 0 else d_stage[k][j]
-            fe.submit_device(cuda.FMT_CF32, blk.data_ptr(), BLOCK)
-            if j == KB - 1:
-                consumed[k] = torch.cuda.Event()
-                consumed[k].record(st)
+    def step_device(i):
+        if rank == 0:
+            fe.submit_device(w.fmt, d_src[i % NB].data_ptr(), w.block)   # N > 1: the library broadcasts it from here
         else:
-            fe.submit_device(cuda.FMT_CF32, d_blocks[i % NB].data_ptr(), BLOCK)
+            fe.submit_shared(w.fmt, w.block)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max(x):
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum_int(x):
+        if world == 1:
+            return int(x)
+        t = torch.tensor([x], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return int(t.item())
+
     # ---- device-resident timing (value) ------------------------------------------------------------
     fe.set_readback(False)
     for i in range(args.warmup):
         step_device(i)
     barrier()
-    pos[0] = 0
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -338,184 +339,174 @@ def run_gpu(args, rank, world, local_rank):
     e0.record(st)
     for i in range(args.steps):
         step_device(args.warmup + i)
+    fe.join_streams()      # the event below covers the spectrum, tail and broadcast streams of the last blocks too
     e1.record(st)
     barrier()
-    ms = e0.elapsed_time(e1)
-    launches = fe.launches - l0
+    ms = reduce_max(e0.elapsed_time(e1))
+    launches = reduce_sum_int(fe.launches - l0)
     clk = clocks.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        lt = torch.tensor([launches], dtype=torch.int64, device=dev)
-        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-        launches = int(lt.item())
-    value = args.steps * BLOCK / (ms * 1e-3) / 1e6
+    value = args.steps * w.block / (ms * 1e-3) / 1e6
+    tensor_launches = reduce_sum_int(fe.stage1_tensor_launches)
 
     # ---- per-kernel-family device time (CUDA events on the front end's stream, inside the library) ----
     fe.set_profiling(True)
     fam_steps = []
     nprof = max(4, min(args.steps, 16))
     barrier()
-    pos[0] = 0
-    consumed[0] = consumed[1] = None
     for i in range(nprof):
         step_device(i)
         fe.wait()
         fam_steps.append(fe.kernel_ms())
-    # mean over the profiled steps without outliers: a bracket that happens to span a host hiccup (the launches of a
-    # family are enqueued one by one between its two events) would otherwise leak into the roofline figures. The plain
-    # mean is kept otherwise because the spectrum family is empty in the steps that complete no frame.
+    # mean over the profiled steps without outliers (a bracket that spans a host hiccup); plain mean otherwise because
+    # the spectrum family is empty in the steps that complete no frame
     fs = np.array(fam_steps)
     fam = np.zeros(fs.shape[1])
     for c in range(fs.shape[1]):
         col = fs[:, c]
-        pos = col[col > 0]
-        keep = col[col <= 4.0 * np.median(pos)] if len(pos) else col
+        nz = col[col > 0]
+        keep = col[col <= 4.0 * np.median(nz)] if len(nz) else col
         fam[c] = float(np.mean(keep)) if len(keep) else 0.0
     fe.set_profiling(False)
+    barrier()
 
-    # ---- end to end through the host API (e2e): pinned host block -> H2D -> path -> D2H results --------
+    # ---- end to end through the host API (e2e): pinned host block -> H2D -> [broadcast] -> path -> D2H results --------
     fe.set_readback(True)
-    e2e = None
-    if world == 1:
-        pin = [cuda.PinnedArray((BLOCK,), np.complex64) for _ in range(4)]
+    raw_dtype = w.np_dtype
+    pin = None
+    if rank == 0:
+        pin = [cuda.PinnedArray((w.block * w.scalars_per_sample,), raw_dtype) for _ in range(4)]
         for j, p in enumerate(pin):
-            p.array[:] = host[j % NB]
-        touched = 0.0
+            p.array[:] = host[j % nbase]
+    sink = [0.0]
 
-        def step_host(i):
-            fe.submit(cuda.FMT_CF32, pin[i % len(pin)], BLOCK)
+    def step_host(i):
+        if rank == 0:
+            fe.submit(w.fmt, pin[i % len(pin)], w.block)
+        else:
+            fe.submit_shared(w.fmt, w.block)
 
-        def consume():
-            nonlocal touched
-            fe.wait()
-            iq, dm = fe.vfo_output(ids[0], copy=False)
+    def consume():
+        fe.wait()
+        if ids:
+            iq, _dm = fe.vfo_output(ids[0], copy=False)
+            sink[0] += float(iq[0].real) if len(iq) else 0.0
+        if with_fft:
             rows = fe.fft_rows(copy=False)
-            touched += float(iq[0].real) if len(iq) else 0.0
-            touched += float(rows[0, 0]) if len(rows) else 0.0
+            sink[0] += float(rows[0, 0]) if len(rows) else 0.0
 
-        for i in range(args.warmup):
-            step_host(i); consume()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ahead = max(1, min(args.e2e_ahead, 4, args.steps))
-        for i in range(ahead):
-            step_host(i)
-        for i in range(ahead, args.steps):
-            step_host(i)      # block i is copied in while blocks i-ahead .. i-1 are still in flight (five result sets)
-            consume()         # results of block i-ahead
-        for i in range(ahead):
-            consume()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        d2h = 0
-        for vid, v in zip(ids, mine):
-            n = len(fe.vfo_output(vid, copy=False)[0])
-            d2h += n * (8 + 4)
-        d2h += int(FFT_N * 4 * BLOCK / FFT_N)
-        # the host link on its own: the same pinned block copied host -> device back to back (what bounds e2e for cf32 input)
-        hsrc = torch.from_numpy(pin[0].array.view(np.float32))
-        hdst = torch.empty_like(d_blocks[0].view(-1))
+    for i in range(args.warmup):
+        step_host(i); consume()
+    barrier()
+    t0 = time.perf_counter()
+    ahead = max(1, min(args.e2e_ahead, 4, args.steps))
+    for i in range(ahead):
+        step_host(i)
+    for i in range(ahead, args.steps):
+        step_host(i)      # block i is copied in while blocks i-ahead .. i-1 are still in flight (five result sets)
+        consume()         # results of block i-ahead
+    for i in range(ahead):
+        consume()
+    barrier()
+    dt = reduce_max(time.perf_counter() - t0)
+    d2h = sum(len(fe.vfo_output(vid, copy=False)[0]) * (8 + (4 if v[3] else 0)) for vid, v in zip(ids, mine))
+    d2h = reduce_sum_int(d2h) + int(w.fft_size * 4 * (w.block / w.decim) / w.fft_size)
+    e2e = {"value": args.steps * w.block / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": blk_bytes, "d2h_bytes_per_step": int(d2h),
+           "blocks_in_flight": ahead + 1,
+           "note": "pinned host block (packed sample format) -> cudaMemcpyAsync H2D -> " + ("ncclBroadcast inside the library -> " if world > 1 else "")
+                   + "full path -> D2H of every VFO's iq + demod rows and every spectrum row; wall clock, max over ranks"}
+    if rank == 0:
+        # the host link on its own: the same pinned block copied host -> device back to back (the ceiling of any e2e number)
+        hsrc = torch.from_numpy(pin[0].array.view(np.uint8))
+        hdst = torch.empty(blk_bytes, dtype=torch.uint8, device=dev)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(20, min(2000, int((64 << 20) / blk_bytes)))
         for _ in range(3):
             hdst.copy_(hsrc, non_blocking=True)
         torch.cuda.synchronize()
         c0.record()
-        for _ in range(20):
+        for _ in range(reps):
             hdst.copy_(hsrc, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
-        h2d_gbs = 20 * BLOCK * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        e2e = {"value": args.steps * BLOCK / dt / 1e6, "unit": "MS/s", "h2d_bytes_per_step": BLOCK * 8, "d2h_bytes_per_step": int(d2h),
-               "h2d_link_gbs": h2d_gbs, "h2d_link_bound_msps": h2d_gbs * 1e9 / 8 / 1e6,
-               "note": "pinned host block -> cudaMemcpyAsync H2D -> full path -> D2H of all VFO outputs + spectrum rows; wall clock. "
-                       "h2d_link_gbs: the same 4.9 MB pinned block copied back to back with nothing else running = the ceiling of any cf32 e2e number on this host link"}
+        h2d_gbs = reps * blk_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        e2e["h2d_link_gbs"] = h2d_gbs
+        e2e["h2d_link_bound_msps"] = h2d_gbs * 1e9 / w.bytes_per_sample / 1e6
         for p in pin:
             p.free()
-    else:
-        # multi-GPU: the host edge is rank 0's; report the same sharded run fed from pinned host memory on rank 0
-        pin = cuda.PinnedArray((BLOCK,), np.complex64) if rank == 0 else None
-        if rank == 0:
-            pin.array[:] = host[0]
-            pin_t = torch.from_numpy(pin.array.view(np.float32).reshape(BLOCK, 2))
-
-        barrier()
-        consumed[0] = consumed[1] = None
-
-        nslots = 2 * KB           # the staging buckets of the device-resident leg, used block by block here
-        cons_e = [None] * nslots
-
-        def step_e2e(i):
-            sl = i % nslots
-            buf = d_stage[sl // KB][sl % KB]   # end to end keeps one broadcast per block: each block comes from the host as it is submitted
-            cur = torch.cuda.current_stream()
-            if cons_e[sl] is not None:
-                cur.wait_event(cons_e[sl])
-            if rank == 0:
-                buf.copy_(pin_t, non_blocking=True)   # H2D from pinned host memory, every step
-            dist.broadcast(buf, src=0)
-            ev = torch.cuda.Event(); ev.record(cur); st.wait_event(ev)
-            fe.submit_device(cuda.FMT_CF32, buf.data_ptr(), BLOCK)
-            cons_e[sl] = torch.cuda.Event(); cons_e[sl].record(st)
-
-        sink = 0.0
-
-        def consume():
-            nonlocal sink
-            fe.wait()                                  # results of the oldest outstanding block are on the host
-            iq, _ = fe.vfo_output(ids[0], copy=False)
-            sink += float(iq[0].real) if len(iq) else 0.0
-
-        for i in range(args.warmup):
-            step_e2e(i); consume()
-        barrier()
-        ahead = max(1, min(args.e2e_ahead, 4, nslots - 1, args.steps))
-        t0 = time.perf_counter()
-        for i in range(ahead):
-            step_e2e(i)
-        for i in range(ahead, args.steps):
-            step_e2e(i)       # blocks i-ahead .. i-1 are still in flight (five result sets)
-            consume()
-        for i in range(ahead):
-            consume()
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        d2h = sum(len(fe.vfo_output(vid, copy=False)[0]) * 12 for vid in ids)
-        dd = torch.tensor([d2h], dtype=torch.int64, device=dev)
-        dist.all_reduce(dd, op=dist.ReduceOp.SUM)
-        e2e = {"value": args.steps * BLOCK / float(t.item()) / 1e6, "unit": "MS/s", "h2d_bytes_per_step": BLOCK * 8,
-               "d2h_bytes_per_step": int(dd.item()) + int(FFT_N * 4 * BLOCK / FFT_N),
-               "note": "rank 0 pinned host block -> H2D -> NCCL broadcast -> sharded path -> per-rank D2H; wall clock, max over ranks"}
+    barrier()
 
     # ---- the spectrum kernels with a full machine's worth of frames (rank 0, N = 1) --------------------------
-    # One streaming step completes at most one 1M-point frame = 128 CTAs; this leg shows what the same kernels
-    # sustain when every SM has work: FB frames back to back from HBM (FB x 8 MB in, FB x 4 MB out, > L2).
     spec_batched = None
-    if rank == 0 and world == 1:
-        FB = min(24, d_blocks.numel() // (2 * FFT_N))
-        src = d_blocks.view(-1)[: 2 * FB * FFT_N].view(FB * FFT_N, 2) if d_blocks.numel() >= 2 * FB * FFT_N else None
-        if src is not None and FB >= 4:
-            rows_dev = torch.empty((FB, FFT_N), dtype=torch.float32, device=dev)
-            win = cuda.design_window(cuda.WIN_BH4, FFT_N)
+    if rank == 0 and world == 1 and w.fmt == workloads.FMT_CF32 and w.decim == 1:
+        N = w.fft_size
+        FB = min(24, (NB * w.block) // N)
+        if FB >= 4:
+            src = d_src.view(-1)[: FB * N * 8]
+            rows_dev = torch.empty((FB, N), dtype=torch.float32, device=dev)
+            win = cuda.design_window(w.fft_window, N)
             sptr = st.cuda_stream
             for _ in range(3):
-                cuda.spectrum_device(FFT_N, FFT_N, FB, FFT_N, src.data_ptr(), win, rows_dev.data_ptr(), sptr)
+                cuda.spectrum_device(N, N, FB, N, src.data_ptr(), win, rows_dev.data_ptr(), sptr)
             torch.cuda.synchronize()
             b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             reps = 10
             b0.record(st)
             for _ in range(reps):
-                cuda.spectrum_device(FFT_N, FFT_N, FB, FFT_N, src.data_ptr(), None, rows_dev.data_ptr(), sptr)  # cached window
+                cuda.spectrum_device(N, N, FB, N, src.data_ptr(), None, rows_dev.data_ptr(), sptr)  # cached window
             b1.record(st)
             torch.cuda.synchronize()
             bms = b0.elapsed_time(b1) / reps
-            spec_batched = {"frames_per_call": FB, "ms_per_call": bms, "msps": FB * FFT_N / (bms * 1e-3) / 1e6,
-                            "achieved": 12.0 * FB * FFT_N / (bms * 1e-3) / 1e9, "unit": "GB/s",
-                            "note": "sdrpp_cuda_spectrum_device: FB x 1M-pt frames per call from HBM-resident input (> L2), 12 B/sample algorithmic, CUDA events"}
+            spec_batched = {"frames_per_call": FB, "ms_per_call": bms, "msps": FB * N / (bms * 1e-3) / 1e6,
+                            "achieved": 12.0 * FB * N / (bms * 1e-3) / 1e9, "unit": "GB/s",
+                            "note": "sdrpp_cuda_spectrum_device: FB frames per call from HBM-resident input (> L2), 12 B/sample algorithmic, CUDA events"}
             del rows_dev
+    comm_info = comm.info() if comm is not None else None
+    fe.close()
+
+    # ---- parity check OUTSIDE the timed region: the same workload, the same feed, against the oracle ------------------
+    parity = None
+    if not args.no_parity:
+        from tests import parity_workload   # test infrastructure (oracle = checker only)
+
+        def feed(f, fmt, raw):
+            if rank == 0:
+                f.submit(fmt, raw)
+            else:
+                f.submit_shared(fmt, w.block)
+
+        nb_par = {2: 40, 3: 11, 4: 14, 5: 4}[w.idx]
+        res = parity_workload.check_workload(cuda, w, nblocks=nb_par, vfo_ids=mine_idx, with_fft=with_fft, submit=feed if world > 1 else None,
+                                             frontend_setup=(lambda f: f.set_comm(comm, 0)) if comm is not None else None,
+                                             spot_count=32 if world == 1 else 12)
+        ok_all = reduce_sum_int(0 if res["ok"] else 1) == 0
+        worst_iq = reduce_max(res["worst_iq_rel_rms"])
+        worst_dm = reduce_max(res["worst_demod_stage_isolated"])
+        checked = reduce_sum_int(res["vfos_checked"])
+        parity = {"ok": ok_all, "ranks": world, "vfos_checked": checked, "gate": res["gate"], "worst_iq_rel_rms_vs_ideal_nco_oracle": worst_iq,
+                  "worst_demod_stage_isolated": worst_dm, "counts_exact": res["counts_exact"], "blocks": res["blocks"],
+                  "ref_f32_rotator_vs_ideal": res["ref_f32_rotator_vs_ideal"], "adjudicated_rank0": res["adjudicated"],
+                  "rows_checked_rank0": res.get("rows"), "worst_row_db_within_100dB_rank0": res.get("worst_row_db_within_100dB"),
+                  "failures_rank0": res["failures"],
+                  "note": "fresh front end(s) with the benchmarked VFO shards, blocks through the same submit path (N > 1: the library's "
+                          "broadcast), spot VFOs of every rank's shard against the ideal-NCO oracle chain; tests/parity_workload.py"}
+
+    # ---- the C++ interface modules link against (IQFrontEnd + VFOManager + dsp::stream), N = 1 -------------------------
+    e2e_cpp = None
+    demo = os.path.join(ROOT, "tests", "cpp", "mirror_demo")
+    if rank == 0 and world == 1 and w.fmt == workloads.FMT_CF32 and os.path.exists(demo) and not args.no_cpp:
+        try:
+            r = subprocess.run([demo, "bench", repr(w.sr), str(w.block), str(w.fft_size), str(w.nvfo), str(max(50, min(400, args.steps))), "8"],
+                               capture_output=True, text=True, timeout=300)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and last:
+                e2e_cpp = json.loads(last[-1])
+                e2e_cpp["note"] = ("tests/cpp/mirror_demo bench: a source thread swaps pinned blocks into the input dsp::stream, sigpath::iqFrontEnd "
+                                   "(ingest / deliver / spectrum threads over the C ABI) feeds VFOs created through sigpath::vfoManager, 8 consumer "
+                                   "threads read()/flush() every VFO::output stream, acquire/release receive every spectrum row")
+            else:
+                e2e_cpp = {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            e2e_cpp = {"error": str(ex)}
 
     # ---- roofline + baseline objects (rank 0) -------------------------------------------------------------
     if rank == 0:
@@ -525,95 +516,107 @@ def run_gpu(args, rank, world, local_rank):
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        model = algorithmic_model(mine)
-        s1_ms, fft_ms, tail_ms, ingest_ms = fam[2], fam[1], fam[3], fam[0]
-        # per launch: the block read once (8 B/sample) + that group's outputs; a step has one launch per VFO class
-        n_s1_launches = len({(v[0], v[1], v[3]) for v in mine})
-        chan_bytes = (8.0 * n_s1_launches + (model["chan_bytes_per_sample"] - 8.0)) * BLOCK
-        traffic = None
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        model = algorithmic_model(w, mine)
+        ingest_ms, fft_ms, s1_ms, tail_ms = fam[0], fam[1], fam[2], fam[3]
+        traffic = {}
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["kernels"]
-            want = "s1t_" if fe.stage1_tensor_launches > 0 else "stage1_kernel"
-            traffic = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for name, k in tj.items() if want in name) or None
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["kernels"]
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": "stage1_kernel (NCO folded into the first decimating FIR; both VFO-class launches of a step)",
-                "achieved": chan_bytes / (s1_ms * 1e-3) / 1e9 if s1_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                "frac": (chan_bytes / (s1_ms * 1e-3) / 1e9 / hbm_peak) if s1_ms > 0 else None, "traffic": traffic,
-                "traffic_note": "dram__bytes_read+write summed over the step's stage-1 launches, ncu --set full at N=1 (profiles/r1_traffic.json)",
-                "peak_source": peak_src, "ms_per_step": float(s1_ms), "launches_per_step": n_s1_launches,
-                "algorithmic_bytes_per_step": chan_bytes,
-                "note": "minimal-bytes accounting (8 B/sample in + outputs, SURVEY 8d); this kernel is FP32-FMA-bound, see fp32"}
+
+        def traffic_of(pat):
+            v = sum(k["dram_read_bytes"] + k["dram_write_bytes"] for name, k in traffic.items() if pat in name)
+            return v or None
+
+        def hbm_row(kernel, bytes_per_sample, ms_, note, pat=None):
+            by = bytes_per_sample * w.block
+            return {"bound": "hbm", "kernel": kernel, "achieved": by / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": by / (ms_ * 1e-3) / 1e9 / hbm_peak if ms_ > 0 else None, "traffic": traffic_of(pat) if pat and w.idx == 5 else None,
+                    "peak_source": peak_src, "ms_per_step": float(ms_), "algorithmic_bytes_per_step": by, "note": note}
+
+        rows = {}
+        # ingest family: conversion (+ front-end decimation where the workload has it)
+        pre_bytes = model["convert_bytes_per_sample"] + model["decim_bytes_per_sample"] - (8.0 if w.decim > 1 else 0.0)
+        rows["ingest"] = hbm_row("ingest_kernel" + (" + decim_stage_kernel x2 (PowerDecimator x%d)" % w.decim if w.decim > 1 else ""), pre_bytes, ingest_ms,
+                                 "conversion %g B/sample in + 8 B out" % w.bytes_per_sample + (" fused with the first decimator stage's input; + 8/%d B out" % w.decim if w.decim > 1 else "")
+                                 + " (SURVEY 8d rows 1-2)", "ingest")
+        rows["spectrum"] = hbm_row("fft_cols_kernel + fft_rows_kernel (window + %d-pt FFT + dB row)" % w.fft_size, model["fft_bytes_per_sample"], fft_ms,
+                                   "SURVEY 8d: sample in (packed size for packed formats) + 4 B out per spectrum sample", "fft_")
+        if rows["spectrum"]["ms_per_step"] > 0:
+            rows["spectrum"]["msps"] = w.block / (fft_ms * 1e-3) / 1e6
         sm_clk = (clk or {}).get("sm_mhz") or 1965.0
         fma_peak = 148 * 128 * 2 * sm_clk * 1e6 / 1e12
-        s1_flops = model["stage1_flops_per_sample"] * BLOCK
+        s1_flops = model["stage1_flops_per_sample"] * w.block
         fp32 = {"achieved": s1_flops / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None, "peak": fma_peak, "unit": "TFLOP/s",
                 "frac": (s1_flops / (s1_ms * 1e-3) / 1e12 / fma_peak) if s1_ms > 0 else None,
                 "peak_source": f"148 SM x 128 FMA lanes x 2 x {sm_clk:.0f} MHz (median SM clock sampled under load)",
                 "algorithmic_flops_per_sample": model["stage1_flops_per_sample"]}
-        if fe.stage1_tensor_launches > 0:
-            # Stage 1 ran on the tensor cores (channelizer_tc.cu). Algorithmic flops stay the reference's own count for
-            # NCO + first decimating FIR; the kernel executes more: complex x complex products, three fp16
-            # products per fp32 product, tap matrix padded to whole rows, 128-row tiles for 120 outputs.
+        chan_min = hbm_row("channelizer stage 1 (NCO + first decimating FIR of every VFO)", model["chan_bytes_per_sample"], s1_ms,
+                           "minimal-bytes accounting of SURVEY 8d: the stream read ONCE (8 B per decimated sample) + every VFO's outputs", "s1t_")
+        if tensor_launches > 0:
             tens_peak = float(peaks.get("bf16_tflops", 2250.0))
             tens_src = ("MEASURED_PEAKS.json bf16_tflops (cuBLAS dense, burst; fp16 runs at the same rate)" if "bf16_tflops" in peaks
                         else "fallback 2250 TFLOP/s nominal dense fp16 (B200_PROFILING.md)")
             executed = 0.0
             for (osr, bw, dm), cnt in collections.Counter((v[0], v[1], v[3]) for v in mine).items():
-                plan = cuda.design_resampler(SR, osr)[0]
+                plan = cuda.design_resampler(w.eff_sr, osr)[0]
                 st1 = cuda.design_decim_plan(plan["predec"])[0] if plan["predec"] > 1 else None
                 if st1 is None or st1[0] not in (32, 64):
                     continue
                 D, T = int(st1[0]), len(st1[1])
                 A = -(-T // D)
-                executed += (-(-cnt // 16)) * (-(-(BLOCK // D) // 120)) * 3 * (2 * D // 16) * 2.0 * 128 * (32 * A) * 16
-            hbm_view = {k: roof[k] for k in ("achieved", "peak", "unit", "frac", "algorithmic_bytes_per_step", "note")}
-            hbm_view["note"] = "minimal-bytes accounting (8 B/sample in + outputs, SURVEY 8d)"
-            roof = {"bound": "tensor",
-                    "kernel": "s1t_split_kernel + s1t_kernel (tcgen05: NCO + first decimating FIR of every VFO as one split-fp16 matrix product per step)",
-                    "achieved": fp32["achieved"], "peak": tens_peak, "unit": "TFLOP/s",
-                    "frac": fp32["achieved"] / tens_peak if fp32["achieved"] else None,
-                    "traffic": traffic, "traffic_note": roof["traffic_note"], "peak_source": tens_src,
-                    "ms_per_step": float(s1_ms), "launches_per_step": 2,
-                    "algorithmic_flops_per_step": s1_flops, "algorithmic_flops_per_sample": model["stage1_flops_per_sample"],
-                    "executed": {"tflops": executed / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None,
-                                 "frac_of_peak": executed / (s1_ms * 1e-3) / 1e12 / tens_peak if s1_ms > 0 else None,
-                                 "flops_per_step": executed,
-                                 "note": "tensor-core flops issued: 3 fp16 products x complex x (tap matrix padded to ceil(T/D) rows) x 128-row tiles per 120 outputs"},
-                    "hbm": hbm_view, "fp32_equivalent": fp32,
-                    "note": "algorithmic flops = the reference's count for NCO + first FIR (what the FP32 kernel of mode 1 executes); ms_per_step covers the fp16 split of the block and the matrix-product kernel"}
+                executed += (-(-cnt // 16)) * (-(-((w.block // w.decim) // D) // 120)) * 3 * (2 * D // 16) * 2.0 * 128 * (32 * A) * 16
+            rows["channelizer_stage1"] = {
+                "bound": "tensor",
+                "kernel": "s1t_split_kernel + s1t_kernel (tcgen05: NCO + first decimating FIR of every VFO as one split-fp16 matrix product per step)",
+                "achieved": fp32["achieved"], "peak": tens_peak, "unit": "TFLOP/s", "frac": fp32["achieved"] / tens_peak if fp32["achieved"] else None,
+                "traffic": traffic_of("s1t_") if w.idx == 5 else None,
+                "traffic_note": "dram__bytes_read+write of the step's s1t_split + s1t launches, ncu --set full at N=1 (profiles/r2_traffic.json)",
+                "peak_source": tens_src, "ms_per_step": float(s1_ms), "launches_per_step": 2,
+                "algorithmic_flops_per_step": s1_flops, "algorithmic_flops_per_sample": model["stage1_flops_per_sample"],
+                "executed": {"tflops": executed / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None,
+                             "frac_of_peak": executed / (s1_ms * 1e-3) / 1e12 / tens_peak if s1_ms > 0 else None, "flops_per_step": executed,
+                             "note": "tensor-core flops issued: 3 fp16 products x complex x (tap matrix padded to ceil(T/D) rows) x 128-row tiles per 120 outputs"},
+                "hbm": {k: chan_min[k] for k in ("achieved", "peak", "unit", "frac", "algorithmic_bytes_per_step", "note")},
+                "fp32_equivalent": fp32,
+                "note": "algorithmic flops = the reference's count for NCO + first FIR (SURVEY 8d); ms_per_step covers the fp16 split of the block and the matrix-product kernel"}
         else:
-            roof["fp32"] = fp32
-        fft_bytes = 12.0 * BLOCK
-        roof_fft = {"bound": "hbm", "kernel": "fft_cols_kernel + fft_rows_kernel (window + 1M-pt FFT + dB row)",
-                    "achieved": fft_bytes / (fft_ms * 1e-3) / 1e9 if fft_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": (fft_bytes / (fft_ms * 1e-3) / 1e9 / hbm_peak) if fft_ms > 0 else None, "traffic": None,
-                    "ms_per_step": float(fft_ms), "algorithmic_bytes_per_step": fft_bytes,
-                    "msps": BLOCK / (fft_ms * 1e-3) / 1e6 if fft_ms > 0 else None}
+            chan_min["kernel"] = "stage1_kernel / mix_only_kernel (FP32: NCO folded into the first decimating FIR, one launch per VFO class)"
+            chan_min["fp32"] = fp32
+            chan_min["note"] += "; the kernel is FP32-FMA-bound (SURVEY 8d), see fp32"
+            rows["channelizer_stage1"] = chan_min
+        rows["channelizer_tail"] = {"kernel": "tail_stage0_wide_kernel + tail_kernel (remaining FIR stages, polyphase resampler, channel filter, demod front ends)",
+                                    "ms_per_step": float(tail_ms), "note": "latency/barrier-bound (<= 1 FMA per input sample and VFO); runs beside stage 1 of the next block"}
+        dominant = max(("ingest", "spectrum", "channelizer_stage1"), key=lambda k: rows[k]["ms_per_step"])
+        roof = dict(rows[dominant])
+        roof["family"] = dominant
         if spec_batched:
             spec_batched["peak"] = hbm_peak
             spec_batched["frac"] = spec_batched["achieved"] / hbm_peak
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, info = cpu_reference(nblocks=2)
+            v, info = cpu_reference(w, nblocks=2)
             cpu = {"value": v, "unit": "MS/s", "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
-                   "channelizer_msps": info["channelizer_msps"], "spectrum_msps": info["spectrum_msps"]}
+                   "stage_msps": info["stage_msps"], "slowest_stage": info["slowest_stage"]}
+        dtype = "f32 (stage 1: 3 x fp16-split products, fp32 accumulate)" if tensor_launches > 0 else "f32"
         line = {
             "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "block": BLOCK, "vfos": NVFO, "fft": FFT_N, "vfos_per_gpu": len(mine),
-                       "l2": f"inputs cycle through {NB} distinct blocks = {NB * BLOCK * 8 / 1e6:.0f} MB (> 126 MB L2)",
-                       "parallelism": f"vfo-shard x{world} + NCCL broadcast of {KB}-block buckets" if world > 1 else "1 GPU"},
-            "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roof, "roofline_spectrum": roof_fft, "spectrum_batched": spec_batched,
+            "dtype": dtype, "data": "synthetic",
+            "config": config_dict(w, vfos_per_gpu=len(mine),
+                                  l2=f"inputs cycle through {NB} block buffers = {NB * blk_bytes / 1e6:.0f} MB of HBM (> 126 MB L2)",
+                                  parallelism=(f"vfo-shard x{world}; one ncclBroadcast of the raw block per step issued by the library (sdrpp_cuda_comm_*), spectrum on rank 0"
+                                               if world > 1 else "1 GPU")),
+            "clocks": clk, "e2e": e2e, "e2e_cpp": e2e_cpp, "gpu_launches": int(launches), "parity_check": parity,
+            "roofline": roof, "rooflines": rows, "roofline_spectrum": rows["spectrum"], "spectrum_batched": spec_batched,
             "kernel_ms_per_step": {"ingest": float(ingest_ms), "spectrum": float(fft_ms), "channelizer_stage1": float(s1_ms), "channelizer_tail": float(tail_ms)},
-            "cpu_baseline": cpu,
+            "comm": comm_info, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
-    fe.close()
-    if world > 1:
+    if comm is not None:
+        barrier()
+        comm.close()
         dist.barrier()
         dist.destroy_process_group()
 
@@ -624,10 +627,13 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--input-blocks", type=int, default=32)
+    ap.add_argument("--config", type=int, default=5, choices=[2, 3, 4, 5], help="BASELINE.json configuration (default 5: the metric's)")
+    ap.add_argument("--input-blocks", type=int, default=32, help="distinct synthetic blocks (tiled over > 126 MB of HBM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-cpp", action="store_true")
     ap.add_argument("--e2e-ahead", type=int, default=4, help="blocks submitted ahead of the one being consumed in the end-to-end leg (1..4)")
-    ap.add_argument("--bcast-blocks", type=int, default=4, help="N > 1: IQ blocks per NCCL broadcast (bucket size)")
+    ap.add_argument("--rank0-base-load", type=float, default=770.0, help="N > 1: VFO-cost units rank 0 is charged for ingest + spectrum")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

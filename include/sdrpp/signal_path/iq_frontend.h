@@ -4,11 +4,13 @@
 // reference's thread-per-block chain: the pre-processing chain, the splitter fan-out, the spectrum branch and every
 // bound RxVFO run as one stream-ordered launch sequence per IQ block on the GPU.
 //
-// Two host threads per front end: `ingest` reads the input stream and submits blocks (up to four ahead), `deliver`
-// waits for finished blocks in order and hands spectrum rows to the acquire/release pair and VFO blocks to their
-// RxVFO::out streams -- the H2D copy and the kernels of block i+1 run while block i is being delivered.
+// Host threads per front end: `ingest` reads the input stream and submits blocks (up to four ahead); `deliver` waits for
+// finished blocks in order and, with a few helpers, copies + swaps VFO blocks into their RxVFO::out streams; `spectrum`
+// hands finished rows to the acquire/release pair (the reference's FFT sink thread). The H2D copy and the kernels of
+// block i+1 run while block i is being delivered.
 #pragma once
 #include <condition_variable>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
@@ -72,6 +74,9 @@ protected:
     void ingestLoop();
     void deliverLoop();
     void deliverBlock();
+    void spectrumLoop();
+    void helperLoop(int k);
+    void deliverShard(int k);
     void updateFFTPath(bool updateWaterfall = false);
 
     static constexpr int kMaxAhead = 4; // blocks submitted and not yet delivered (the engine keeps five result sets)
@@ -80,11 +85,23 @@ protected:
     sdrpp_cuda_frontend* fe = nullptr;
     std::recursive_mutex mtx;   // control surface + every engine call except the blocking waits
     std::mutex swapMtx;         // held by the deliver thread while it swaps blocks into the output streams
-    std::thread ingestThread, deliverThread;
+    std::thread ingestThread, deliverThread, spectrumThread;
+    std::vector<std::thread> helpers;
     std::mutex flowMtx;
     std::condition_variable flowCv;
     long long submitted = 0, delivered = 0;
     bool running = false, stopping = false;
+    // rows of the block being delivered, handed to the spectrum thread (at most one block behind the deliver thread, so
+    // the engine's result set is still intact when it copies)
+    std::deque<std::pair<const float*, int>> rowsQueue;
+    long long rowsPosted = 0, rowsDone = 0;
+    // VFO blocks of the block being delivered, sharded over the deliver thread + helpers
+    struct OutItem { dsp::channel::RxVFO* vfo; const sdrpp_cf32* iq; int n; };
+    std::vector<OutItem> outItems;
+    std::vector<dsp::stream<dsp::complex_t>*> outTaps;
+    int outRaw = 0;
+    long long shardGen = 0;
+    int shardsLeft = 0;
 
     // VFOs and raw IQ taps
     std::map<std::string, dsp::channel::RxVFO*> vfos;

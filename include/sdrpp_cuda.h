@@ -209,6 +209,31 @@ SDRPP_API int sdrpp_cuda_frontend_pending(sdrpp_cuda_frontend* fe);
  * Threading: one thread may submit (submit*, wait_input) while another waits and reads results (wait, vfo_output,
  * fft_rows, ...); all other calls must be serialised by the caller against both. */
 SDRPP_API int sdrpp_cuda_frontend_drain(sdrpp_cuda_frontend* fe);
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: one process per GPU, the VFO set sharded across them (no VFO needs another's data), every IQ block
+ * broadcast from the ingest rank over NVLink. Replaces the fan-out of dsp::routing::Splitter::run
+ * (dsp/routing/splitter.h:46-60: memcpy + swap per consumer). The library owns the NCCL communicator and issues ONE
+ * ncclBroadcast of the raw, still packed samples per block on a stream of its own; conversion and pre-processing then
+ * run redundantly on every GPU, so every rank sees bit-identical samples. NCCL is loaded at run time (libnccl.so.2).
+ *
+ *   rank 0:      sdrpp_cuda_comm_unique_id(id)  -> hand the 128 bytes to the other processes (file, socket, MPI ...)
+ *   every rank:  c = sdrpp_cuda_comm_create(id, rank, nranks, device);  sdrpp_cuda_frontend_set_comm(fe, c, root)
+ *   per block:   root:   sdrpp_cuda_frontend_submit(fe, fmt, host_block, count)   (or _submit_device)
+ *                others: sdrpp_cuda_frontend_submit_shared(fe, fmt, count)        (same fmt/count, same order)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdrpp_cuda_comm sdrpp_cuda_comm;
+SDRPP_API int sdrpp_cuda_comm_unique_id(void* id128);
+SDRPP_API sdrpp_cuda_comm* sdrpp_cuda_comm_create(const void* id128, int rank, int nranks, int device);
+SDRPP_API int sdrpp_cuda_comm_destroy(sdrpp_cuda_comm* c);
+/* rank / size / NCCL version code / broadcasts issued and bytes broadcast since creation (any pointer may be NULL) */
+SDRPP_API int sdrpp_cuda_comm_info(sdrpp_cuda_comm* c, int* rank, int* nranks, int* nccl_version, long long* broadcasts, long long* bytes);
+/* Attach a front end to a communicator (NULL detaches). From then on every submit on `root` broadcasts the block and
+ * every other rank must mirror it with _submit_shared. */
+SDRPP_API int sdrpp_cuda_frontend_set_comm(sdrpp_cuda_frontend* fe, sdrpp_cuda_comm* c, int root);
+/* Non-root ranks: take part in the broadcast of the block the root is submitting (count samples of format fmt) and run
+ * this rank's share of the path on it. */
+SDRPP_API int sdrpp_cuda_frontend_submit_shared(sdrpp_cuda_frontend* fe, int fmt, int count);
+
 /* Skip the device->host copies of results (kernel-only timing); default 1 = copy. */
 SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled);
 
@@ -283,6 +308,9 @@ SDRPP_API int sdrpp_cuda_frontend_read_iq(sdrpp_cuda_frontend* fe, sdrpp_cf32* o
  * (cudaStream_t) the front end enqueues on, for device-side timing with events. */
 SDRPP_API long long sdrpp_cuda_frontend_launches(sdrpp_cuda_frontend* fe);
 SDRPP_API void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe);
+/* Make that stream wait for everything enqueued so far on the front end's other streams (spectrum, tail, result copies,
+ * broadcast): an event recorded on it afterwards covers the whole of the blocks submitted up to here. No host sync. */
+SDRPP_API int sdrpp_cuda_frontend_join_streams(sdrpp_cuda_frontend* fe);
 /* Device-time of the kernels of the last waited block, by kernel family, measured with CUDA
  * events on the front end's stream when profiling is enabled (ms). idx: 0 ingest/preproc,
  * 1 spectrum, 2 channelizer stage 1, 3 channelizer tail. */

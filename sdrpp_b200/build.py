@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libsdrpp_cuda.so")
 BLOB = os.path.join(HERE, "data", "decim_plans.bin")
 
-SOURCES = ["design.cpp", "preproc.cu", "fft.cu", "channelizer.cu", "channelizer_tc.cu", "engine.cu"]
+SOURCES = ["design.cpp", "preproc.cu", "fft.cu", "channelizer.cu", "channelizer_tc.cu", "comm.cu", "engine.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -76,7 +76,7 @@ def build(force=False, verbose=False):
     if verbose:
         for obj, log in results:
             sys.stderr.write(log)
-    cmd = [NVCC, "-shared", "-o", LIB, *[o for o, _ in results], "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [NVCC, "-shared", "-o", LIB, *[o for o, _ in results], "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "design.h"
 #include "kernels.h"
+#include "comm.h"
 #include "../../include/sdrpp_cuda.h"
 
 #include <algorithm>
@@ -274,6 +275,13 @@ struct sdrpp_cuda_frontend {
     // it blocks on the block's completion event.
     std::mutex api_mtx;
     int last_in_slot = -1;
+
+    // multi-GPU feed (comm.cu): every submit is one ncclBroadcast of the raw block from comm_root on st_bcast
+    sdrpp_cuda_comm* comm = nullptr;
+    int comm_root = 0;
+    cudaStream_t st_bcast = nullptr;
+    cudaEvent_t ev_bcast[kSets] = { nullptr };
+    cudaEvent_t ev_join = nullptr;
     cudaEvent_t ev_s1_fork = nullptr, ev_s1_join = nullptr;
     bool ev_tail_valid[2] = { false, false };
     long long blk = 0; // blocks processed (parity selects the stage-1 output region)
@@ -1028,14 +1036,21 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
     if (rc != SDRPP_OK) return rc;
     std::lock_guard<std::mutex> api(fe->api_mtx);
     if (fmt < 0 || (fmt >= SDRPP_FMT_COUNT && fmt != kFmtPcmI8 && fmt != kFmtPcmI16)) return fail(SDRPP_ERR_ARG, "unknown sample format");
-    if (!in || count <= 0 || count > fe->cfg.max_block) return fail(SDRPP_ERR_ARG, "count must be in 1..max_block");
+    if (count <= 0 || count > fe->cfg.max_block) return fail(SDRPP_ERR_ARG, "count must be in 1..max_block");
+    {
+        const bool needs_data = !(fe->comm && fe->comm->nranks > 1 && fe->comm->rank != fe->comm_root);
+        if (needs_data && !in) return fail(SDRPP_ERR_ARG, "null sample buffer");
+        if (!needs_data && in) return fail(SDRPP_ERR_STATE, "this rank receives its blocks from the communicator's root: use sdrpp_cuda_frontend_submit_shared");
+    }
     const int slot = (int)(fe->seq % kSets);
     ResultSet& rs = fe->rs[slot];
     rc = wait_set(fe, slot); // the block that used this result set kSets submits ago must be done
     if (rc != SDRPP_OK) return rc;
     const void* d_in = in;
-    if (!device_src) {
-        const size_t bytes = (size_t)count * fmt_bytes_per_sample(fmt);
+    const bool shared = fe->comm != nullptr && fe->comm->nranks > 1;
+    const bool is_root = !shared || fe->comm->rank == fe->comm_root;
+    const size_t bytes = (size_t)count * fmt_bytes_per_sample(fmt);
+    if (is_root && !device_src) {
         const void* src = in;
         cudaPointerAttributes attr{};
         bool pinned = (cudaPointerGetAttributes(&attr, in) == cudaSuccess) && (attr.type == cudaMemoryTypeHost);
@@ -1049,15 +1064,32 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
         }
         FE_TRY(fe, cudaMemcpyAsync(fe->d_raw[slot], src, bytes, cudaMemcpyHostToDevice, fe->st_copy));
         FE_TRY(fe, cudaEventRecord(fe->ev_h2d[slot], fe->st_copy));
-        FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_h2d[slot], 0));
+        if (!shared) FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_h2d[slot], 0));
         d_in = fe->d_raw[slot];
         fe->last_in_slot = slot;
     } else {
         fe->last_in_slot = -1;
     }
+    if (shared) {
+        // One broadcast of the raw (packed) block per submit, on its own stream so that the broadcast of block i+1 runs
+        // beside the kernels of block i. Root: in place out of the staged / caller's device buffer; others: into d_raw.
+        cudaStream_t sb = fe->st_bcast;
+        void* recv;
+        if (is_root) {
+            if (!device_src) FE_TRY(fe, cudaStreamWaitEvent(sb, fe->ev_h2d[slot], 0));
+            recv = const_cast<void*>(d_in);
+        } else {
+            if (fe->consumed_valid[slot]) FE_TRY(fe, cudaStreamWaitEvent(sb, fe->ev_consumed[slot], 0));
+            recv = fe->d_raw[slot];
+            d_in = recv;
+        }
+        FE_TRY(fe, comm_broadcast(fe->comm, d_in, recv, bytes, fe->comm_root, sb));
+        FE_TRY(fe, cudaEventRecord(fe->ev_bcast[slot], sb));
+        FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_bcast[slot], 0));
+    }
     rc = process_block(fe, fmt, d_in, count, rs, scale);
     if (rc != SDRPP_OK) return rc;
-    if (!device_src) {
+    if (!device_src || !is_root) {
         // the raw buffer may be overwritten once this block's kernels are done
         FE_TRY(fe, cudaEventRecord(fe->ev_consumed[slot], fe->st));
         fe->consumed_valid[slot] = true;
@@ -1392,7 +1424,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaStreamCreateWithFlags(&fe->st_fft, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_tail, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_d2h, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&fe->st_s1b, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
+        cudaStreamCreateWithFlags(&fe->st_s1b, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_bcast, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
     if (cudaEventCreateWithFlags(&fe->ev_ingest, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_fft[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -1409,6 +1442,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         if (cudaEventCreateWithFlags(&fe->ev_h2d[i], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
         if (cudaEventCreateWithFlags(&fe->ev_consumed[i], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
         if (cudaEventCreateWithFlags(&fe->rs[i].done, cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+        if (cudaEventCreateWithFlags(&fe->ev_bcast[i], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
         cudaEventRecord(fe->ev_h2d[i], fe->st_copy);
     }
     for (int i = 0; i < 5; i++) if (cudaEventCreate(&fe->pev[i]) != cudaSuccess) return bail("event creation failed");
@@ -1427,6 +1461,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_tail) cudaStreamSynchronize(fe->st_tail);
     if (fe->st_d2h) cudaStreamSynchronize(fe->st_d2h);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
+    if (fe->st_bcast) cudaStreamSynchronize(fe->st_bcast);
     for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.if_state); }
     for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
     for (int i = 0; i < 2; i++) { cudaFree(fe->tc_planes[i].hi); cudaFree(fe->tc_planes[i].lo); cudaFree(fe->tc_planes[i].sinv); }
@@ -1443,6 +1478,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->ev_h2d[i]) cudaEventDestroy(fe->ev_h2d[i]);
         if (fe->ev_consumed[i]) cudaEventDestroy(fe->ev_consumed[i]);
         if (fe->rs[i].done) cudaEventDestroy(fe->rs[i].done);
+        if (fe->ev_bcast[i]) cudaEventDestroy(fe->ev_bcast[i]);
         if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
         if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
         if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
@@ -1456,6 +1492,8 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_tail) cudaStreamDestroy(fe->st_tail);
     if (fe->st_d2h) cudaStreamDestroy(fe->st_d2h);
     if (fe->st_s1b) cudaStreamDestroy(fe->st_s1b);
+    if (fe->st_bcast) cudaStreamDestroy(fe->st_bcast);
+    if (fe->ev_join) cudaEventDestroy(fe->ev_join);
     for (cudaEvent_t e : { fe->ev_ingest, fe->ev_s1, fe->ev_fft[0], fe->ev_fft[1], fe->ev_tail[0], fe->ev_tail[1], fe->ev_s1_fork, fe->ev_s1_join }) if (e) cudaEventDestroy(e);
     cudaGetLastError();
     delete fe;
@@ -1472,6 +1510,7 @@ static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, cudaStreamSynchronize(fe->st_tail));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_d2h));
     FE_TRY(fe, cudaStreamSynchronize(fe->st_s1b));
+    FE_TRY(fe, cudaStreamSynchronize(fe->st_bcast));
     fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;
     fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false;
     // Everything submitted so far is complete. Blocks the caller has not waited for yet stay queued: wait() still hands
@@ -1686,6 +1725,36 @@ int sdrpp_cuda_frontend_submit(sdrpp_cuda_frontend* fe, int fmt, const void* in,
 }
 int sdrpp_cuda_frontend_submit_device(sdrpp_cuda_frontend* fe, int fmt, const void* dev_in, int count) {
     return submit_common(fe, fmt, dev_in, count, true);
+}
+int sdrpp_cuda_frontend_join_streams(sdrpp_cuda_frontend* fe) {
+    int rc = fe_check(fe);
+    if (rc != SDRPP_OK) return rc;
+    std::lock_guard<std::mutex> api(fe->api_mtx);
+    if (!fe->ev_join) FE_TRY(fe, cudaEventCreateWithFlags(&fe->ev_join, cudaEventDisableTiming));
+    for (cudaStream_t s : { fe->st_fft, fe->st_tail, fe->st_d2h, fe->st_s1b, fe->st_bcast, fe->st_copy }) {
+        FE_TRY(fe, cudaEventRecord(fe->ev_join, s));
+        FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_join, 0));
+    }
+    return SDRPP_OK;
+}
+int sdrpp_cuda_frontend_submit_shared(sdrpp_cuda_frontend* fe, int fmt, int count) {
+    if (!fe || !fe->comm || fe->comm->nranks < 2 || fe->comm->rank == fe->comm_root)
+        return fail(SDRPP_ERR_STATE, "submit_shared is for the non-root ranks of an attached communicator");
+    return submit_common(fe, fmt, nullptr, count, true);
+}
+int sdrpp_cuda_frontend_set_comm(sdrpp_cuda_frontend* fe, sdrpp_cuda_comm* c, int root) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (c && (root < 0 || root >= c->nranks)) return fail(SDRPP_ERR_ARG, "root out of range");
+    if (c && c->device != fe->device) return fail(SDRPP_ERR_ARG, "communicator and front end live on different devices");
+    fe->comm = c; fe->comm_root = root;
+    // the persistent stage-1 kernel takes one CTA per SM with all of its shared memory: leave a few SMs to the NCCL
+    // kernel, or the broadcast of block i+1 queues behind stage 1 of block i
+    if (c && c->nranks > 1 && !getenv("SDRPP_RESERVE_SMS")) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, fe->device) == cudaSuccess && sms > 16) fe->num_sms = sms - 8;
+    }
+    return SDRPP_OK;
 }
 int sdrpp_cuda_frontend_submit_pcm(sdrpp_cuda_frontend* fe, const void* packet, int nbytes) {
     if (!packet || nbytes < 8) return fail(SDRPP_ERR_ARG, "bad argument");

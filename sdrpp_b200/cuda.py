@@ -36,7 +36,9 @@ sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_
 sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
 sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio sdrpp_cuda_vfo_set_if_chain sdrpp_cuda_vfo_squelch_state
 sdrpp_cuda_frontend_set_stage1_mode sdrpp_cuda_frontend_stage1_tensor_launches
-sdrpp_cuda_frontend_wait_input sdrpp_cuda_frontend_pending sdrpp_cuda_frontend_drain
+sdrpp_cuda_frontend_wait_input sdrpp_cuda_frontend_pending sdrpp_cuda_frontend_drain sdrpp_cuda_frontend_join_streams
+sdrpp_cuda_comm_unique_id sdrpp_cuda_comm_create sdrpp_cuda_comm_destroy sdrpp_cuda_comm_info sdrpp_cuda_frontend_set_comm
+sdrpp_cuda_frontend_submit_shared
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -115,6 +117,14 @@ def lib():
         L.sdrpp_cuda_frontend_wait_input.argtypes = [_vp]
         L.sdrpp_cuda_frontend_pending.argtypes = [_vp]
         L.sdrpp_cuda_frontend_drain.argtypes = [_vp]
+        L.sdrpp_cuda_frontend_join_streams.argtypes = [_vp]
+        L.sdrpp_cuda_comm_unique_id.argtypes = [_vp]
+        L.sdrpp_cuda_comm_create.restype = _vp
+        L.sdrpp_cuda_comm_create.argtypes = [_vp, _i, _i, _i]
+        L.sdrpp_cuda_comm_destroy.argtypes = [_vp]
+        L.sdrpp_cuda_comm_info.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
+        L.sdrpp_cuda_frontend_set_comm.argtypes = [_vp, _vp, _i]
+        L.sdrpp_cuda_frontend_submit_shared.argtypes = [_vp, _i, _i]
         L.sdrpp_cuda_vfo_output.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]
         L.sdrpp_cuda_fft_rows.argtypes = [_vp, C.POINTER(_vp)]
         L.sdrpp_cuda_vfo_set_post.argtypes = [_vp, _i, C.POINTER(PostCfg)]
@@ -279,6 +289,34 @@ class PinnedArray:
             pass
 
 
+# ---- multi-GPU communicator (one process per GPU; the library owns the NCCL communicator) -----------------------
+def comm_unique_id():
+    """128 bytes created on one rank (normally 0) and handed to every other rank out of band."""
+    buf = (C.c_char * 128)()
+    _check(lib().sdrpp_cuda_comm_unique_id(buf), "comm_unique_id")
+    return bytes(buf)
+
+
+class Comm:
+    def __init__(self, unique_id, rank, nranks, device):
+        assert len(unique_id) == 128
+        self.rank, self.nranks = rank, nranks
+        self.h = lib().sdrpp_cuda_comm_create(C.c_char_p(unique_id), rank, nranks, device)
+        if not self.h:
+            raise SdrppCudaError("sdrpp_cuda_comm_create failed: " + last_error())
+
+    def info(self):
+        r, n, v = _i(), _i(), _i()
+        b, by = C.c_longlong(), C.c_longlong()
+        _check(lib().sdrpp_cuda_comm_info(self.h, C.byref(r), C.byref(n), C.byref(v), C.byref(b), C.byref(by)), "comm_info")
+        return dict(rank=r.value, nranks=n.value, nccl_version=v.value, broadcasts=b.value, bytes=by.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sdrpp_cuda_comm_destroy(self.h)
+            self.h = None
+
+
 # ---- front end ---------------------------------------------------------------------------------
 class Frontend:
     """sigpath::iqFrontEnd + the VFO set of sigpath::vfoManager on one GPU."""
@@ -373,6 +411,16 @@ class Frontend:
 
     def wait(self):
         _check(lib().sdrpp_cuda_frontend_wait(self.h), "wait")
+
+    def set_comm(self, comm, root=0):
+        """Attach to a communicator: submits on `root` broadcast the raw block, the other ranks call submit_shared."""
+        _check(lib().sdrpp_cuda_frontend_set_comm(self.h, comm.h if comm is not None else None, root), "set_comm")
+
+    def submit_shared(self, fmt, count):
+        _check(lib().sdrpp_cuda_frontend_submit_shared(self.h, fmt, count), "submit_shared")
+
+    def join_streams(self):
+        _check(lib().sdrpp_cuda_frontend_join_streams(self.h), "join_streams")
 
     def wait_input(self):
         _check(lib().sdrpp_cuda_frontend_wait_input(self.h), "wait_input")

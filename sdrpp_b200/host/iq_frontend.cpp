@@ -188,7 +188,12 @@ void IQFrontEnd::start() {
     stopping = false;
     if (fe) { sdrpp_cuda_frontend_drain(fe); }
     submitted = delivered = 0;
+    rowsPosted = rowsDone = 0; shardGen = 0; shardsLeft = 0; rowsQueue.clear();
     ingestThread = std::thread(&IQFrontEnd::ingestLoop, this);
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int nhelp = hw >= 16 ? 3 : hw >= 8 ? 1 : 0;
+    for (int k = 0; k < nhelp; k++) { helpers.emplace_back(&IQFrontEnd::helperLoop, this, k + 1); }
+    spectrumThread = std::thread(&IQFrontEnd::spectrumLoop, this);
     deliverThread = std::thread(&IQFrontEnd::deliverLoop, this);
 }
 
@@ -209,6 +214,9 @@ void IQFrontEnd::stop() {
     }
     if (ingestThread.joinable()) { ingestThread.join(); }
     if (deliverThread.joinable()) { deliverThread.join(); }
+    if (spectrumThread.joinable()) { spectrumThread.join(); }
+    for (auto& h : helpers) { if (h.joinable()) { h.join(); } }
+    helpers.clear();
     if (_in) { _in->clearReadStop(); }
     std::lock_guard<std::recursive_mutex> lck(mtx);
     for (auto& [name, vfo] : vfos) { vfo->out.clearWriteStop(); }
@@ -266,43 +274,93 @@ void IQFrontEnd::deliverLoop() {
         } else {
             deliverBlock();
         }
-        { std::lock_guard<std::mutex> f(flowMtx); delivered++; }
+        {
+            // the spectrum thread may lag one block: rows of block d are still intact while block d+1 is delivered
+            std::unique_lock<std::mutex> f(flowMtx);
+            flowCv.wait(f, [&] { return stopping || rowsDone >= rowsPosted - 1; });
+            delivered++;
+        }
         flowCv.notify_all();
     }
 }
 
 void IQFrontEnd::deliverBlock() {
     std::unique_lock<std::recursive_mutex> lck(mtx);
-    // spectrum rows: acquire/release are always called as a pair, once per line (iq_frontend.cpp:239-248); acquire may
-    // return NULL (the row is skipped)
+    // spectrum rows go to the spectrum thread
     const float* rows = nullptr;
     const int nrows = sdrpp_cuda_fft_rows(fe, &rows);
-    for (int r = 0; r < nrows; r++) {
-        float* dst = _acquireFFTBuffer ? _acquireFFTBuffer(_fftCtx) : nullptr;
-        if (dst) { memcpy(dst, rows + (size_t)r * _fftSize, sizeof(float) * (size_t)_fftSize); }
-        if (_releaseFFTBuffer) { _releaseFFTBuffer(_fftCtx); }
-    }
     // VFO blocks into each RxVFO::out (Splitter::run + RxVFO::run of the reference, splitter.h:46-60, rx_vfo.h:102-114)
-    std::vector<dsp::channel::RxVFO*> live;
-    live.reserve(vfos.size());
+    outItems.clear();
     for (auto& [name, vfo] : vfos) {
         const sdrpp_cf32* iq = nullptr;
         const int n = sdrpp_cuda_vfo_output(fe, vfo->vfoId, &iq, nullptr);
-        vfo->pendingOut = n > 0 && iq ? n : 0;
-        if (vfo->pendingOut > 0) {
-            memcpy(vfo->out.writeBuf, iq, sizeof(dsp::complex_t) * (size_t)n);
-            live.push_back(vfo);
-        }
+        if (n > 0 && iq) { outItems.push_back(OutItem{ vfo, iq, n }); }
     }
-    std::vector<dsp::stream<dsp::complex_t>*> taps = bound;
-    int nraw = 0;
-    if (!taps.empty()) {
-        nraw = sdrpp_cuda_frontend_read_iq(fe, (sdrpp_cf32*)taps[0]->writeBuf, STREAM_BUFFER_SIZE);
-        for (size_t i = 1; i < taps.size(); i++) { memcpy(taps[i]->writeBuf, taps[0]->writeBuf, sizeof(dsp::complex_t) * (size_t)std::max(nraw, 0)); }
+    outTaps = bound;
+    outRaw = 0;
+    if (!outTaps.empty()) {
+        outRaw = sdrpp_cuda_frontend_read_iq(fe, (sdrpp_cf32*)outTaps[0]->writeBuf, STREAM_BUFFER_SIZE);
+        for (size_t i = 1; i < outTaps.size(); i++) { memcpy(outTaps[i]->writeBuf, outTaps[0]->writeBuf, sizeof(dsp::complex_t) * (size_t)std::max(outRaw, 0)); }
     }
     // never hold the control mutex while blocked on a consumer; swapMtx keeps removeVFO / unbindIQStream out meanwhile
     std::lock_guard<std::mutex> sw(swapMtx);
     lck.unlock();
-    for (auto* vfo : live) { vfo->out.swap(vfo->pendingOut); }
-    for (auto* s : taps) { if (nraw > 0) { s->swap(nraw); } }
+    {
+        std::lock_guard<std::mutex> f(flowMtx);
+        if (nrows > 0) { rowsQueue.emplace_back(rows, nrows); rowsPosted++; }
+        shardGen++;
+        shardsLeft = (int)helpers.size();
+    }
+    flowCv.notify_all();
+    deliverShard(0);
+    for (auto* s : outTaps) { if (outRaw > 0) { s->swap(outRaw); } }
+    std::unique_lock<std::mutex> f(flowMtx);
+    flowCv.wait(f, [&] { return shardsLeft == 0 || stopping; });
+}
+
+// copy + swap of every (1 + helpers)-th VFO block: 512 VFOs are 512 condition-variable hand-overs per IQ block
+void IQFrontEnd::deliverShard(int k) {
+    const size_t stride = helpers.size() + 1;
+    for (size_t i = (size_t)k; i < outItems.size(); i += stride) {
+        const OutItem& it = outItems[i];
+        memcpy(it.vfo->out.writeBuf, it.iq, sizeof(dsp::complex_t) * (size_t)it.n);
+        it.vfo->out.swap(it.n);
+    }
+}
+
+void IQFrontEnd::helperLoop(int k) {
+    long long seen = 0;
+    while (true) {
+        {
+            std::unique_lock<std::mutex> f(flowMtx);
+            flowCv.wait(f, [&] { return stopping || shardGen > seen; });
+            if (shardGen == seen) { return; }   // stopping, nothing posted
+            seen = shardGen;
+        }
+        deliverShard(k);
+        { std::lock_guard<std::mutex> f(flowMtx); shardsLeft--; }
+        flowCv.notify_all();
+    }
+}
+
+// acquire/release are always called as a pair, once per line (iq_frontend.cpp:239-248); acquire may return NULL (the
+// row is skipped). The reference runs this on the FFT sink's own thread too.
+void IQFrontEnd::spectrumLoop() {
+    while (true) {
+        const float* rows; int nrows;
+        {
+            std::unique_lock<std::mutex> f(flowMtx);
+            flowCv.wait(f, [&] { return stopping || rowsPosted > rowsDone; });
+            if (rowsQueue.empty()) { return; }
+            rows = rowsQueue.front().first; nrows = rowsQueue.front().second;
+            rowsQueue.pop_front();
+        }
+        for (int r = 0; r < nrows; r++) {
+            float* dst = _acquireFFTBuffer ? _acquireFFTBuffer(_fftCtx) : nullptr;
+            if (dst) { memcpy(dst, rows + (size_t)r * _fftSize, sizeof(float) * (size_t)_fftSize); }
+            if (_releaseFFTBuffer) { _releaseFFTBuffer(_fftCtx); }
+        }
+        { std::lock_guard<std::mutex> f(flowMtx); rowsDone++; }
+        flowCv.notify_all();
+    }
 }

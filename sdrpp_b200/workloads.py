@@ -39,10 +39,10 @@ class Workload:
         return len(self.vfos)
 
     def tone_vfos(self):
-        """Indices of the VFOs that get a carrier in the synthetic stream: every 8th tile-first VFO of each class
-        plus the very last VFOs, so spot checks find channels with content in both classes."""
+        """Indices of the VFOs that get a carrier in the synthetic stream: four VFOs of each class spread over the set
+        plus the very last ones, so spot checks find channels with content in both classes."""
         n = self.nvfo
-        step = max(1, n // 8)
+        step = max(1, n // 4)
         idx = sorted(set(list(range(0, n, step)) + list(range(1, n, step)) + [n - 2, n - 1]) & set(range(n)))
         return idx
 

@@ -50,7 +50,7 @@ def _rel(a, b):
 
 
 def check_workload(cuda, w, nblocks=4, spots=None, vfo_ids=None, with_fft=True, stage1_mode=0, submit=None, raw_blocks=None,
-                   rows_to_check=2):
+                   rows_to_check=2, frontend_setup=None, spot_count=32):
     """Runs `nblocks` blocks of workload `w` through a fresh front end and checks spot VFOs and spectrum rows.
 
     vfo_ids: the subset of w.vfos this front end owns (a rank's shard; default all). spots: indices INTO w.vfos to
@@ -60,14 +60,17 @@ def check_workload(cuda, w, nblocks=4, spots=None, vfo_ids=None, with_fft=True, 
     port64 = None
     owned = list(range(w.nvfo)) if vfo_ids is None else list(vfo_ids)
     if spots is None:
-        spots = [i for i in default_spots(w) if i in set(owned)]
-        if vfo_ids is not None and len(spots) < 8:
-            spots = sorted(set(spots + owned[:: max(1, len(owned) // 8)]))[:16]
+        spots = [i for i in default_spots(w, spot_count) if i in set(owned)]
+        if vfo_ids is not None and len(spots) < min(spot_count, len(owned)):
+            extra = owned[:: max(1, len(owned) // max(1, spot_count - len(spots)))]
+            spots = sorted(set(spots + extra))[:max(spot_count, len(spots))]
     raw = w.make_blocks(nblocks) if raw_blocks is None else raw_blocks
     fe = cuda.Frontend(w.sr, decim_ratio=w.decim, fft_size=w.fft_size if with_fft else 0, fft_rate=w.fft_rate,
                        fft_window=w.fft_window, max_block=w.block)
     res = {"workload": w.describe(), "blocks": int(nblocks), "vfos_owned": len(owned), "vfos_checked": len(spots), "gate": TOL}
     try:
+        if frontend_setup is not None:
+            frontend_setup(fe)
         fe.set_stage1_mode(stage1_mode)
         ids = {i: fe.add_vfo(*w.vfos[i]) for i in owned}
         got = {i: [] for i in spots}

@@ -112,7 +112,7 @@ def _demo_digest():
         for dp, _, fs in os.walk(os.path.join(ROOT, base)):
             paths += [os.path.join(dp, f) for f in fs]
     for p in sorted(paths):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, ROOT).encode())   # relative: the repository lives elsewhere on the GPU box
         h.update(open(p, "rb").read())
     return h.hexdigest()
 
