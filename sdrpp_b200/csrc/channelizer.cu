@@ -620,6 +620,21 @@ __device__ __noinline__ void if_fmif_run(float* __restrict__ r, int bins, float2
     __syncthreads();
 }
 
+// Demod front end of one output sample y (prev = the sample before it), in the reference's operation order with no
+// contraction: Quadrature (demod/quadrature.h:41-56: (y * conj(prev)).phase() * invDeviation with complex_t::operator*,
+// dsp/types.h:23-25), AM magnitude (volk_32fc_magnitude_32f, am.h:122: bit-exact with IEEE sqrt), SSB second
+// translation + real part (ssb.h:90-101).
+__device__ __forceinline__ float demod_front_end(const TailGroup& g, const VfoDev& vd, float2 y, float2 p, int i) {
+    if (g.demod == 1) {
+        const float dre = __fadd_rn(__fmul_rn(y.x, p.x), __fmul_rn(y.y, p.y));
+        const float dim = __fsub_rn(__fmul_rn(y.y, p.x), __fmul_rn(y.x, p.y));
+        return __fmul_rn(atan2f(dim, dre), g.inv_dev);
+    }
+    if (g.demod == 2) return __fsqrt_rn(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
+    const float2 w = phasor_u64((uint64_t)(g.abs_out + i) * vd.dphi2);
+    return __fsub_rn(__fmul_rn(y.x, w.x), __fmul_rn(y.y, w.y));
+}
+
 __global__ void __launch_bounds__(kTailThreads, 4)
 tail_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
@@ -717,22 +732,8 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         src = p;
     }
     for (int i = tid; i < g.n_final; i += kTailThreads) {
-        const float2 y = src[i];
         o_iq[i] = fin[i];
-        if (g.demod == 1) {
-            const float2 p = src[i - 1];
-            // y * conj(prev) with complex_t::operator* (dsp/types.h:23-25)
-            // in the reference's operation order, no contraction: (re*b.re) - (im*b.im), (im*b.re) + (re*b.im) with b = conj(prev)
-            const float dre = __fadd_rn(__fmul_rn(y.x, p.x), __fmul_rn(y.y, p.y));
-            const float dim = __fsub_rn(__fmul_rn(y.y, p.x), __fmul_rn(y.x, p.y));
-            o_dm[i] = __fmul_rn(atan2f(dim, dre), g.inv_dev);
-        } else if (g.demod == 2) {
-            // volk_32fc_magnitude_32f (generic): sqrtf(re*re + im*im), bit-exact with IEEE sqrt
-            o_dm[i] = __fsqrt_rn(__fadd_rn(__fmul_rn(y.x, y.x), __fmul_rn(y.y, y.y)));
-        } else if (g.demod >= 3) {
-            const float2 w = phasor_u64((uint64_t)(g.abs_out + i) * vd.dphi2);
-            o_dm[i] = __fsub_rn(__fmul_rn(y.x, w.x), __fmul_rn(y.y, w.y));
-        }
+        if (g.demod != 0) o_dm[i] = demod_front_end(g, vd, src[i], src[i - 1], i);
     }
     __syncthreads();
     if (tid == 0) {
@@ -742,6 +743,157 @@ tail_kernel(const __grid_constant__ TailArgs a) {
         else if (g.nstages == 0) nxt[-1] = fin[-1];
         if (if_on) { vd.ifs[IF_PREV_RE] = src[g.n_final - 1].x; vd.ifs[IF_PREV_IM] = src[g.n_final - 1].y; }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tail, low-latency form. tail_kernel walks a VFO's stages through the slab: every stage stages its input from L2,
+// builds a tap table, computes, stores, carries its history -- four to six dependent L2 round trips and as many
+// barriers per stage, ~36 us per CTA whatever the VFO count. When a VFO's stage inputs of this block all fit in shared
+// memory at once (every high-decimation plan: a few thousand samples), ONE round trip fetches everything -- the first
+// stage's input, every stage's T-1 history samples, every tap table, the previous final sample -- the stages then run
+// back to back out of shared memory with one barrier each, and only the results and the new histories go back.
+// Same arithmetic (fir.h:62-83, decimating_fir.h:45-68, polyphase_resampler.h:69-99), same slab layout, so the two
+// kernels can alternate block by block. The engine picks this one per group and block (tail_fast_fits).
+// ---------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 256;
+constexpr int kFastMaxSamples = 12288;  // float2 of stage regions a CTA may hold (96 KB)
+constexpr int kFastTapFloats = 3072;
+
+__host__ __device__ inline int fast_region(int T, int n_in) { return ((T - 1) + n_in + 1) & ~1; }
+
+bool tail_fast_fits(const TailGroup& g, int* samples) {
+    if (g.nstages > kTailMaxStages || g.nstages < 1) return false;
+    int pos = 0, tp = 0;
+    for (int s = g.s_begin; s < g.nstages; s++) {
+        const TailStage& st = g.st[s];
+        pos += fast_region(st.T, st.n_in);
+        tp += ((st.type == TAIL_POLY ? st.interp * st.T : st.T) + 3) & ~3;
+    }
+    pos += (g.n_final + 2 + 1) & ~1;
+    if (samples) *samples = pos;
+    return pos <= kFastMaxSamples && tp <= kFastTapFloats;
+}
+
+__global__ void __launch_bounds__(kFastThreads)
+tail_fast_kernel(const __grid_constant__ TailArgs a) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    float* taps = reinterpret_cast<float*>(tail_smem);                          // [kFastTapFloats]
+    float2* x = reinterpret_cast<float2*>(tail_smem + kFastTapFloats * 4);      // stage regions [hist | data] ..., then [prev | final]
+    int vi = blockIdx.x, gi = 0;
+    while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
+    const TailGroup& g = a.g[gi];
+    const VfoDev vd = a.vfos[g.first_vfo + vi];
+    float2* slab = vd.slab;
+    const int tid = threadIdx.x;
+
+    int roff[kTailMaxStages + 1], toff[kTailMaxStages];
+    {
+        int pos = 0, tp = 0;
+        for (int s = g.s_begin; s < g.nstages; s++) {
+            roff[s] = pos; toff[s] = tp;
+            pos += fast_region(g.st[s].T, g.st[s].n_in);
+            tp += ((g.st[s].type == TAIL_POLY ? g.st[s].interp * g.st[s].T : g.st[s].T) + 3) & ~3;
+        }
+        roff[g.nstages] = pos;
+    }
+    float2* fin = x + roff[g.nstages] + 1;   // fin[-1] = last output of the previous block
+
+    // ---- one round trip: everything this block needs ------------------------------------------------------------------
+    if (g.s_begin < g.nstages) {
+        const TailStage& st = g.st[g.s_begin];
+        const float2* __restrict__ src = slab + st.in_off;
+        float2* dst = x + roff[g.s_begin] + (st.T - 1);
+        for (int i = tid; i < st.n_in; i += kFastThreads) cp_async8(dst + i, src + i);
+    } else {
+        const float2* __restrict__ src = slab + g.final_off;   // every stage already ran (wide first stage only)
+        for (int i = tid; i < g.n_final; i += kFastThreads) cp_async8(fin + i, src + i);
+    }
+    for (int s = g.s_begin; s < g.nstages; s++) {
+        const TailStage& st = g.st[s];
+        const int hist = st.T - 1;
+        const float2* __restrict__ hsrc = slab + st.in_off - hist;
+        for (int i = tid; i < hist; i += kFastThreads) cp_async8(x + roff[s] + i, hsrc + i);
+        const int nt = st.type == TAIL_POLY ? st.interp * st.T : st.T;
+        for (int i = tid; i < nt; i += kFastThreads) taps[toff[s] + i] = __ldg(st.taps + i);
+    }
+    if (tid == 0) fin[-1] = slab[g.final_off - 1];
+    cp_async_wait_all();
+    __syncthreads();
+
+    // ---- the stages, back to back out of shared memory ------------------------------------------------------------------
+    for (int s = g.s_begin; s < g.nstages; s++) {
+        const TailStage& st = g.st[s];
+        const int T = st.T;
+        const float2* __restrict__ in = x + roff[s];
+        float2* __restrict__ out = (s + 1 < g.nstages) ? x + roff[s + 1] + (g.st[s + 1].T - 1) : fin;
+        const float* __restrict__ h0 = taps + toff[s];
+        for (int o = tid; o < st.n_out; o += kFastThreads) {
+            const float2* __restrict__ xp;
+            const float* __restrict__ h;
+            if (st.type == TAIL_POLY) {
+                // closed form of polyphase_resampler.h:75-93
+                const long long P = (long long)st.phase + (long long)o * st.D;
+                xp = in + st.offset + (int)(P / st.interp);
+                h = h0 + (int)(P % st.interp) * T;
+            } else {
+                xp = in + st.offset + o * (st.type == TAIL_DECFIR ? st.D : 1);
+                h = h0;
+            }
+            float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+            int k = 0;
+            for (; k + 4 <= T; k += 4) {
+                const float t0 = h[k], t1 = h[k + 1], t2 = h[k + 2], t3 = h[k + 3];
+                a0 = __ffma2_rn(make_float2(t0, t0), xp[k], a0);
+                a1 = __ffma2_rn(make_float2(t1, t1), xp[k + 1], a1);
+                a2 = __ffma2_rn(make_float2(t2, t2), xp[k + 2], a2);
+                a3 = __ffma2_rn(make_float2(t3, t3), xp[k + 3], a3);
+            }
+            for (; k < T; k++) { const float t = h[k]; a0 = __ffma2_rn(make_float2(t, t), xp[k], a0); }
+            out[o] = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+        }
+        __syncthreads();
+    }
+
+    // ---- results, new histories -----------------------------------------------------------------------------------------
+    float2* o_iq = a.arena_iq + vd.out_off;
+    float* o_dm = a.arena_demod + vd.out_off;
+    for (int i = tid; i < g.n_final; i += kFastThreads) {
+        const float2 y = fin[i];
+        o_iq[i] = y;
+        if (g.demod != 0) o_dm[i] = demod_front_end(g, vd, y, fin[i - 1], i);
+    }
+    for (int s = g.s_begin; s < g.nstages; s++) {
+        const TailStage& st = g.st[s];
+        const int hist = st.T - 1;
+        // stage 0 reads the double-buffered stage-1 region: its history goes to the OTHER region (always, even for an
+        // empty block); later stages keep theirs in front of their own input area (fir.h:80)
+        if (s == 0 || st.n_in > 0) {
+            float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : (slab + st.in_off - hist);
+            const float2* src = x + roff[s] + st.n_in;
+            for (int i = tid; i < hist; i += kFastThreads) dst[i] = src[i];
+        }
+    }
+    if (tid == 0 && g.n_final > 0) slab[g.final_off - 1] = fin[g.n_final - 1];
+}
+
+cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st) {
+    if (total_vfos <= 0) return cudaSuccess;
+    int need = 0;
+    for (int i = 0; i < a.ngroups; i++) {
+        int n = 0;
+        if (!tail_fast_fits(a.g[i], &n)) return cudaErrorInvalidValue;
+        need = std::max(need, n);
+    }
+    const size_t smem = (size_t)kFastTapFloats * sizeof(float) + (size_t)(need + 8) * sizeof(float2);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tail_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(kFastTapFloats * sizeof(float) + (kFastMaxSamples + 8) * sizeof(float2)));
+        if (e != cudaSuccess) return e;
+        attr_done = true;
+    }
+    tail_fast_kernel<<<total_vfos, kFastThreads, smem, st>>>(a);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

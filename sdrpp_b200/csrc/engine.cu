@@ -339,6 +339,7 @@ struct sdrpp_cuda_frontend {
 
     // tensor-core stage 1: fp16 hi/lo planes of the ring per first-stage decimation (index D / 64: 32 -> 0, 64 -> 1)
     int s1_mode = 0;        // 0: tensor cores where the plan allows, 1: FP32 FMA kernel only
+    int tail_mode = 0;      // 0: low-latency tail kernel where a block fits (default), 1: general tail kernel only (SDRPP_TAIL_MODE=general)
     int num_sms = 148;
     S1TPlanes tc_planes[2] = {};
     long long s1t_launches = 0;
@@ -780,8 +781,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     // ---- channelizer ----------------------------------------------------------------------------
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
     if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
-    std::vector<TailArgs> tails;
-    std::vector<int> tail_totals;
+    std::vector<TailArgs> tails, tails_fast;
+    std::vector<int> tail_totals, tail_fast_totals;
     // Tensor-core stage 1: refresh the fp16 hi/lo planes of the ring for every first-stage decimation in use
     // (one conversion serves all VFOs and plans of that decimation), then collect the eligible groups per plane set.
     S1TArgs tc_args[2] = {};
@@ -908,14 +909,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         if (nprev > 0) { fe->launches++; s1_launch++; }
     stage1_done:
 
-        if (tails.empty() || tails.back().ngroups == kTailMaxGroups) {
-            TailArgs t{};
-            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq + (size_t)aset * fe->arena_cap; t.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
-            tails.push_back(t); tail_totals.push_back(0);
-        }
-        TailArgs& t = tails.back();
-        TailGroup& tg = t.g[t.ngroups++];
-        tail_totals.back() += (int)g.members.size();
+        TailGroup tg{};
         tg.first_vfo = g.first_dev; tg.nvfo = (int)g.members.size();
         tg.nstages = (int)p.tail.size();
         // a leading decimating FIR still sees 1/D of the input rate per VFO: it gets its own wide launch
@@ -951,6 +945,19 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         tg.abs_out = g.st.abs_out;
         g.st.abs_out += nprev;
         g.last_n_final = nprev;
+        // Low-latency tail when this block's stage inputs fit in shared memory at once and no member carries a radio IF
+        // chain (that lives in the general kernel); both kernels keep the same slab state, so the choice is per block.
+        bool fast = fe->tail_mode == 0 && tail_fast_fits(tg, nullptr);
+        if (fast) for (int id : g.members) if (fe->vfos[(size_t)id].if_state) { fast = false; break; }
+        std::vector<TailArgs>& lst = fast ? tails_fast : tails;
+        std::vector<int>& tot = fast ? tail_fast_totals : tail_totals;
+        if (lst.empty() || lst.back().ngroups == kTailMaxGroups) {
+            TailArgs t{};
+            t.vfos = fe->d_vfos; t.arena_iq = fe->d_arena_iq + (size_t)aset * fe->arena_cap; t.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
+            lst.push_back(t); tot.push_back(0);
+        }
+        lst.back().g[lst.back().ngroups++] = tg;
+        tot.back() += (int)g.members.size();
     }
     for (int pi = 0; pi < 2; pi++) { int rc = flush_tc(pi); if (rc != SDRPP_OK) return rc; }
     if (forked) {
@@ -962,13 +969,20 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         FE_TRY(fe, cudaEventRecord(fe->ev_s1, st));
         FE_TRY(fe, cudaStreamWaitEvent(stl, fe->ev_s1, 0));
     }
-    for (size_t i = 0; i < tails.size(); i++) {
-        bool wide = false;
-        for (int k = 0; k < tails[i].ngroups; k++) wide = wide || tails[i].g[k].s_begin == 1;
-        if (wide && tail_totals[i] > 0) { FE_TRY(fe, launch_tail_stage0_wide(tails[i], tail_totals[i], stl)); fe->launches++; }
-        FE_TRY(fe, launch_tail(tails[i], tail_totals[i], stl));
-        if (tail_totals[i] > 0) fe->launches++;
+    for (int pass = 0; pass < 2; pass++) {
+        std::vector<TailArgs>& lst = pass ? tails : tails_fast;
+        std::vector<int>& tot = pass ? tail_totals : tail_fast_totals;
+        for (size_t i = 0; i < lst.size(); i++) {
+            bool wide = false;
+            for (int k = 0; k < lst[i].ngroups; k++) wide = wide || lst[i].g[k].s_begin == 1;
+            if (wide && tot[i] > 0) { FE_TRY(fe, launch_tail_stage0_wide(lst[i], tot[i], stl)); fe->launches++; }
+            FE_TRY(fe, pass ? launch_tail(lst[i], tot[i], stl) : launch_tail_fast(lst[i], tot[i], stl));
+            if (tot[i] > 0) fe->launches++;
+        }
     }
+    // the post-detector pass below walks every group, whichever tail kernel it took
+    tails.insert(tails.end(), tails_fast.begin(), tails_fast.end());
+    tail_totals.insert(tail_totals.end(), tail_fast_totals.begin(), tail_fast_totals.end());
     if (fe->post_active > 0) {
         // post-detector stages of the VFOs that have them, on the outputs the tail just wrote
         for (size_t i = 0; i < tails.size(); i++) {
@@ -1405,6 +1419,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         // sets this so that the NCCL broadcast of the next block is not queued behind it)
         const char* rsv = getenv("SDRPP_RESERVE_SMS");
         if (rsv) { const int r = atoi(rsv); if (r > 0 && r < fe->num_sms) fe->num_sms -= r; }
+        const char* tm = getenv("SDRPP_TAIL_MODE");
+        fe->tail_mode = (tm && (!strcmp(tm, "general") || !strcmp(tm, "1"))) ? 1 : 0;
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
     }

@@ -188,6 +188,9 @@ struct TailArgs {
     float* arena_demod;
 };
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st);
+// the low-latency form for groups whose stage inputs of this block fit in shared memory at once (tail_fast_fits)
+bool tail_fast_fits(const TailGroup& g, int* samples);
+cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st);
 // stage 0 of the groups with s_begin == 1 on a wide grid (a decimating FIR); launch before launch_tail
 cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStream_t st);
 bool tail_stage0_wide_supported(int T, int D);
