@@ -757,28 +757,65 @@ tail_kernel(const __grid_constant__ TailArgs a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kFastThreads = 256;
 constexpr int kFastMaxSamples = 12288;  // float2 of stage regions a CTA may hold (96 KB)
-constexpr int kFastTapFloats = 3072;
+constexpr int kFastTapFloats = 4096;
+constexpr int kFastOB = 4;              // outputs per thread of a FIR stage (register blocking)
+constexpr int kFastScratch = kFastThreads * kFastOB; // float2: split-K partial sums
 
-__host__ __device__ inline int fast_region(int T, int n_in) { return ((T - 1) + n_in + 1) & ~1; }
+// A stage's input region [T-1 history | n_in data] in shared memory. FIR stages read it register-blocked (a thread owns
+// four consecutive outputs, so a sample and a float4 of taps serve up to four MACs -- at one load per MAC the kernel was
+// bound by shared-memory bandwidth, profiles/r2d), which needs the region transposed by M = 4*D: element i at plane
+// i % M, position i / M, so that the threads of a warp (consecutive output groups) read consecutive positions of one
+// plane. The polyphase stage and the final output keep natural order (M = 1).
+struct FastRegion {
+    int base;   // float2 offset of the region in the sample area
+    int M, lgM; // transposition modulus (power of two) and its log2; M = 1: natural order
+    int qs;     // positions per plane (odd), M > 1
+    int len;    // elements (history + data)
+};
+__host__ __device__ inline int fast_stage_M(const TailStage& st) { return st.type == TAIL_POLY ? 1 : kFastOB * (st.type == TAIL_DECFIR ? st.D : 1); }
+__host__ __device__ inline int fast_ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+__host__ __device__ inline int fast_region_floats2(const TailStage& st, FastRegion* r, int base) {
+    const int len = (st.T - 1) + st.n_in;
+    const int M = fast_stage_M(st);
+    const int lgM = fast_ilog2(M);
+    // the last output group of a blocked reader runs up to 6*D elements past the data (outputs beyond n_out, zero taps):
+    // those elements exist and are zero (0 * garbage could be NaN)
+    const int D = st.type == TAIL_DECFIR ? st.D : 1;
+    const int padded = len + 6 * D + 8;
+    const int qs = M > 1 ? (((padded + M - 1) >> lgM) + 1) | 1 : 0;
+    if (r) { r->base = base; r->M = M; r->lgM = lgM; r->qs = qs; r->len = len; }
+    return M > 1 ? ((M * qs + 1) & ~1) : ((padded + 1) & ~1);
+}
+__host__ __device__ inline int fast_tap_floats(const TailStage& st) {
+    if (st.type == TAIL_POLY) return (st.interp * st.T + 3) & ~3;
+    const int D = st.type == TAIL_DECFIR ? st.D : 1;
+    return 4 * (st.T + (kFastOB - 1) * D);   // float4 table (h[s], h[s-D], h[s-2D], h[s-3D]) for s < T + 3D
+}
 
 bool tail_fast_fits(const TailGroup& g, int* samples) {
     if (g.nstages > kTailMaxStages || g.nstages < 1) return false;
     int pos = 0, tp = 0;
     for (int s = g.s_begin; s < g.nstages; s++) {
         const TailStage& st = g.st[s];
-        pos += fast_region(st.T, st.n_in);
-        tp += ((st.type == TAIL_POLY ? st.interp * st.T : st.T) + 3) & ~3;
+        if (st.type == TAIL_DECFIR && (st.D & (st.D - 1)) != 0) return false;
+        pos += fast_region_floats2(st, nullptr, 0);
+        tp += fast_tap_floats(st);
     }
     pos += (g.n_final + 2 + 1) & ~1;
+    pos += kFastScratch;
     if (samples) *samples = pos;
     return pos <= kFastMaxSamples && tp <= kFastTapFloats;
+}
+
+__device__ __forceinline__ float2& fast_at(float2* x, const FastRegion& r, int i) {
+    return r.M > 1 ? x[r.base + (i & (r.M - 1)) * r.qs + (i >> r.lgM)] : x[r.base + i];
 }
 
 __global__ void __launch_bounds__(kFastThreads)
 tail_fast_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* taps = reinterpret_cast<float*>(tail_smem);                          // [kFastTapFloats]
-    float2* x = reinterpret_cast<float2*>(tail_smem + kFastTapFloats * 4);      // stage regions [hist | data] ..., then [prev | final]
+    float2* x = reinterpret_cast<float2*>(tail_smem + kFastTapFloats * 4);      // stage regions ..., [prev | final], split-K scratch
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
     const TailGroup& g = a.g[gi];
@@ -786,24 +823,28 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
     float2* slab = vd.slab;
     const int tid = threadIdx.x;
 
-    int roff[kTailMaxStages + 1], toff[kTailMaxStages];
+    FastRegion reg[kTailMaxStages + 1];
+    int toff[kTailMaxStages];
+    int pos = 0;
     {
-        int pos = 0, tp = 0;
+        int tp = 0;
         for (int s = g.s_begin; s < g.nstages; s++) {
-            roff[s] = pos; toff[s] = tp;
-            pos += fast_region(g.st[s].T, g.st[s].n_in);
-            tp += ((g.st[s].type == TAIL_POLY ? g.st[s].interp * g.st[s].T : g.st[s].T) + 3) & ~3;
+            toff[s] = tp;
+            pos += fast_region_floats2(g.st[s], &reg[s], pos);
+            tp += fast_tap_floats(g.st[s]);
         }
-        roff[g.nstages] = pos;
     }
-    float2* fin = x + roff[g.nstages] + 1;   // fin[-1] = last output of the previous block
+    FastRegion& rf = reg[g.nstages];     // final: natural order, element 0 = last output of the previous block
+    rf.base = pos; rf.M = 1; rf.lgM = 0; rf.qs = 0; rf.len = g.n_final + 1;
+    float2* fin = x + rf.base + 1;
+    float2* scratch = x + rf.base + ((g.n_final + 2 + 1) & ~1);
 
     // ---- one round trip: everything this block needs ------------------------------------------------------------------
     if (g.s_begin < g.nstages) {
         const TailStage& st = g.st[g.s_begin];
-        const float2* __restrict__ src = slab + st.in_off;
-        float2* dst = x + roff[g.s_begin] + (st.T - 1);
-        for (int i = tid; i < st.n_in; i += kFastThreads) cp_async8(dst + i, src + i);
+        const FastRegion& r = reg[g.s_begin];
+        const float2* __restrict__ src = slab + st.in_off - (st.T - 1);     // [history | data], contiguous in the slab
+        for (int i = tid; i < r.len; i += kFastThreads) cp_async8(&fast_at(x, r, i), src + i);
     } else {
         const float2* __restrict__ src = slab + g.final_off;   // every stage already ran (wide first stage only)
         for (int i = tid; i < g.n_final; i += kFastThreads) cp_async8(fin + i, src + i);
@@ -811,10 +852,29 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
     for (int s = g.s_begin; s < g.nstages; s++) {
         const TailStage& st = g.st[s];
         const int hist = st.T - 1;
-        const float2* __restrict__ hsrc = slab + st.in_off - hist;
-        for (int i = tid; i < hist; i += kFastThreads) cp_async8(x + roff[s] + i, hsrc + i);
-        const int nt = st.type == TAIL_POLY ? st.interp * st.T : st.T;
-        for (int i = tid; i < nt; i += kFastThreads) taps[toff[s] + i] = __ldg(st.taps + i);
+        if (s > g.s_begin) {
+            const float2* __restrict__ hsrc = slab + st.in_off - hist;
+            for (int i = tid; i < hist; i += kFastThreads) cp_async8(&fast_at(x, reg[s], i), hsrc + i);
+        }
+        if (st.type == TAIL_POLY) {
+            for (int i = tid; i < st.interp * st.T; i += kFastThreads) taps[toff[s] + i] = __ldg(st.taps + i);
+        } else {
+            const int D = st.type == TAIL_DECFIR ? st.D : 1, T = st.T;
+            float4* t4 = reinterpret_cast<float4*>(taps + toff[s]);
+            for (int sv = tid; sv < T + (kFastOB - 1) * D; sv += kFastThreads) {
+                float4 h;
+                h.x = sv < T ? __ldg(st.taps + sv) : 0.0f;
+                h.y = (sv - D >= 0 && sv - D < T) ? __ldg(st.taps + sv - D) : 0.0f;
+                h.z = (sv - 2 * D >= 0 && sv - 2 * D < T) ? __ldg(st.taps + sv - 2 * D) : 0.0f;
+                h.w = (sv - 3 * D >= 0 && sv - 3 * D < T) ? __ldg(st.taps + sv - 3 * D) : 0.0f;
+                t4[sv] = h;
+            }
+        }
+    }
+    for (int s = g.s_begin; s < g.nstages; s++) {
+        if (reg[s].M == 1) continue;
+        const int D = g.st[s].type == TAIL_DECFIR ? g.st[s].D : 1;
+        for (int i = reg[s].len + tid; i < reg[s].len + 6 * D + 8; i += kFastThreads) fast_at(x, reg[s], i) = make_float2(0.0f, 0.0f);
     }
     if (tid == 0) fin[-1] = slab[g.final_off - 1];
     cp_async_wait_all();
@@ -824,32 +884,88 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
     for (int s = g.s_begin; s < g.nstages; s++) {
         const TailStage& st = g.st[s];
         const int T = st.T;
-        const float2* __restrict__ in = x + roff[s];
-        float2* __restrict__ out = (s + 1 < g.nstages) ? x + roff[s + 1] + (g.st[s + 1].T - 1) : fin;
-        const float* __restrict__ h0 = taps + toff[s];
-        for (int o = tid; o < st.n_out; o += kFastThreads) {
-            const float2* __restrict__ xp;
-            const float* __restrict__ h;
-            if (st.type == TAIL_POLY) {
+        const FastRegion& ri = reg[s];
+        const FastRegion& ro = reg[s + 1];
+        const int obase = (s + 1 < g.nstages) ? (g.st[s + 1].T - 1) : 1;   // outputs land behind the consumer's history
+        if (st.type == TAIL_POLY) {
+            const float2* __restrict__ in = x + ri.base;
+            const float* __restrict__ h0 = taps + toff[s];
+            for (int o = tid; o < st.n_out; o += kFastThreads) {
                 // closed form of polyphase_resampler.h:75-93
                 const long long P = (long long)st.phase + (long long)o * st.D;
-                xp = in + st.offset + (int)(P / st.interp);
-                h = h0 + (int)(P % st.interp) * T;
-            } else {
-                xp = in + st.offset + o * (st.type == TAIL_DECFIR ? st.D : 1);
-                h = h0;
+                const float2* __restrict__ xp = in + st.offset + (int)(P / st.interp);
+                const float* __restrict__ h = h0 + (int)(P % st.interp) * T;
+                float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+                int k = 0;
+                for (; k + 4 <= T; k += 4) {
+                    const float t0 = h[k], t1 = h[k + 1], t2 = h[k + 2], t3 = h[k + 3];
+                    a0 = __ffma2_rn(make_float2(t0, t0), xp[k], a0);
+                    a1 = __ffma2_rn(make_float2(t1, t1), xp[k + 1], a1);
+                    a2 = __ffma2_rn(make_float2(t2, t2), xp[k + 2], a2);
+                    a3 = __ffma2_rn(make_float2(t3, t3), xp[k + 3], a3);
+                }
+                for (; k < T; k++) { const float t = h[k]; a0 = __ffma2_rn(make_float2(t, t), xp[k], a0); }
+                fast_at(x, ro, obase + o) = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
             }
-            float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
-            int k = 0;
-            for (; k + 4 <= T; k += 4) {
-                const float t0 = h[k], t1 = h[k + 1], t2 = h[k + 2], t3 = h[k + 3];
-                a0 = __ffma2_rn(make_float2(t0, t0), xp[k], a0);
-                a1 = __ffma2_rn(make_float2(t1, t1), xp[k + 1], a1);
-                a2 = __ffma2_rn(make_float2(t2, t2), xp[k + 2], a2);
-                a3 = __ffma2_rn(make_float2(t3, t3), xp[k + 3], a3);
+            __syncthreads();
+            continue;
+        }
+        // FIR / decimating FIR, register-blocked: thread (og, ks) owns outputs 4*og .. 4*og+3 over a slice of the S = 3D + T
+        // window steps; step j meets element offset + 4*og*D + j and the taps (h[j], h[j-D], h[j-2D], h[j-3D]).
+        const int D = st.type == TAIL_DECFIR ? st.D : 1;
+        const int G = (st.n_out + kFastOB - 1) / kFastOB;
+        const int S = (kFastOB - 1) * D + T;
+        int KS = 1;
+        while (KS < 8 && G * KS * 2 <= kFastThreads && S >= 32 * KS) KS *= 2;
+        const int Sk = (S + KS - 1) / KS;
+        const float4* __restrict__ t4 = reinterpret_cast<const float4*>(taps + toff[s]);
+        for (int g0 = 0; g0 < G; g0 += kFastThreads / KS) {
+            const int gcount = min(kFastThreads / KS, G - g0);
+            const int og = g0 + tid % (kFastThreads / KS), ks = tid / (kFastThreads / KS);
+            const bool active = (tid % (kFastThreads / KS)) < gcount && ks < KS;
+            float2 acc[kFastOB];
+#pragma unroll
+            for (int r = 0; r < kFastOB; r++) acc[r] = make_float2(0.0f, 0.0f);
+            if (active) {
+                const int e0 = st.offset + kFastOB * og * D;     // first element of the group's window
+                const int j1 = min(S, (ks + 1) * Sk);
+                // element e0 + j sits at plane (e0 + j) % M, position (e0 + j) / M; e0 = offset (mod M) for every group
+                const float2* __restrict__ xb = x + ri.base;
+#pragma unroll 4
+                for (int j = ks * Sk; j < j1; j++) {
+                    const int e = e0 + j;
+                    const float2 v = xb[(e & (ri.M - 1)) * ri.qs + (e >> ri.lgM)];
+                    const float4 h = t4[j];
+                    acc[0] = __ffma2_rn(make_float2(h.x, h.x), v, acc[0]);
+                    acc[1] = __ffma2_rn(make_float2(h.y, h.y), v, acc[1]);
+                    acc[2] = __ffma2_rn(make_float2(h.z, h.z), v, acc[2]);
+                    acc[3] = __ffma2_rn(make_float2(h.w, h.w), v, acc[3]);
+                }
             }
-            for (; k < T; k++) { const float t = h[k]; a0 = __ffma2_rn(make_float2(t, t), xp[k], a0); }
-            out[o] = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
+            if (KS > 1) {
+                if (active && ks > 0) {
+#pragma unroll
+                    for (int r = 0; r < kFastOB; r++) scratch[((ks - 1) * (kFastThreads / KS) + (og - g0)) * kFastOB + r] = acc[r];
+                }
+                __syncthreads();
+                if (active && ks == 0) {
+                    for (int q = 1; q < KS; q++) {
+#pragma unroll
+                        for (int r = 0; r < kFastOB; r++) {
+                            const float2 v = scratch[((q - 1) * (kFastThreads / KS) + (og - g0)) * kFastOB + r];
+                            acc[r].x += v.x; acc[r].y += v.y;
+                        }
+                    }
+                }
+            }
+            if (active && ks == 0) {
+#pragma unroll
+                for (int r = 0; r < kFastOB; r++) {
+                    const int o = kFastOB * og + r;
+                    if (o < st.n_out) fast_at(x, ro, obase + o) = acc[r];
+                }
+            }
+            if (KS > 1) __syncthreads();   // scratch is reused by the next round of groups
         }
         __syncthreads();
     }
@@ -869,8 +985,7 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
         // empty block); later stages keep theirs in front of their own input area (fir.h:80)
         if (s == 0 || st.n_in > 0) {
             float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : (slab + st.in_off - hist);
-            const float2* src = x + roff[s] + st.n_in;
-            for (int i = tid; i < hist; i += kFastThreads) dst[i] = src[i];
+            for (int i = tid; i < hist; i += kFastThreads) dst[i] = fast_at(x, reg[s], st.n_in + i);
         }
     }
     if (tid == 0 && g.n_final > 0) slab[g.final_off - 1] = fin[g.n_final - 1];
