@@ -339,7 +339,8 @@ struct sdrpp_cuda_frontend {
 
     // tensor-core stage 1: fp16 hi/lo planes of the ring per first-stage decimation (index D / 64: 32 -> 0, 64 -> 1)
     int s1_mode = 0;        // 0: tensor cores where the plan allows, 1: FP32 FMA kernel only
-    int tail_mode = 0;      // 0: low-latency tail kernel where a block fits (default), 1: general tail kernel only (SDRPP_TAIL_MODE=general)
+    int tail_mode = 0;      // 0: low-latency tail kernel when the VFO set is smaller than the machine (default), 1: general
+                            // tail kernel only (SDRPP_TAIL_MODE=general), 2: low-latency kernel wherever a block fits (=fast)
     int num_sms = 148;
     S1TPlanes tc_planes[2] = {};
     long long s1t_launches = 0;
@@ -781,6 +782,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     // ---- channelizer ----------------------------------------------------------------------------
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
     if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
+    int total_vfos_all = 0;
+    for (const Group& g : fe->groups) total_vfos_all += (int)g.members.size();
     std::vector<TailArgs> tails, tails_fast;
     std::vector<int> tail_totals, tail_fast_totals;
     // Tensor-core stage 1: refresh the fp16 hi/lo planes of the ring for every first-stage decimation in use
@@ -947,7 +950,10 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         g.last_n_final = nprev;
         // Low-latency tail when this block's stage inputs fit in shared memory at once and no member carries a radio IF
         // chain (that lives in the general kernel); both kernels keep the same slab state, so the choice is per block.
-        bool fast = fe->tail_mode == 0 && tail_fast_fits(tg, nullptr);
+        // Measured (profiles/r2e): with fewer VFOs than SMs the tail is bound by one CTA's chain of dependent round trips
+        // and the low-latency kernel wins (100 WFM VFOs: 73 -> 58 us per step); with several CTAs per SM both kernels are
+        // bound by instruction issue and the general one (tap tables built per segment, fewer instructions) is ahead.
+        bool fast = (fe->tail_mode == 0 ? total_vfos_all <= fe->num_sms : fe->tail_mode == 2) && tail_fast_fits(tg, nullptr);
         if (fast) for (int id : g.members) if (fe->vfos[(size_t)id].if_state) { fast = false; break; }
         std::vector<TailArgs>& lst = fast ? tails_fast : tails;
         std::vector<int>& tot = fast ? tail_fast_totals : tail_totals;
@@ -1420,7 +1426,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         const char* rsv = getenv("SDRPP_RESERVE_SMS");
         if (rsv) { const int r = atoi(rsv); if (r > 0 && r < fe->num_sms) fe->num_sms -= r; }
         const char* tm = getenv("SDRPP_TAIL_MODE");
-        fe->tail_mode = (tm && (!strcmp(tm, "general") || !strcmp(tm, "1"))) ? 1 : 0;
+        fe->tail_mode = (tm && (!strcmp(tm, "general") || !strcmp(tm, "1"))) ? 1 : (tm && (!strcmp(tm, "fast") || !strcmp(tm, "2"))) ? 2 : 0;
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
     }

@@ -76,7 +76,9 @@ def test_if_chain(gpu, port, name, vfo, chain, tol):
             fe_raw.process(po.FMT_CF32, b)
             y, d = fe.vfo_output(vid)
             y0, d0 = fe_raw.vfo_output(vraw)
-            assert np.array_equal(y.view(np.uint32), y0.view(np.uint32))  # the iq result stays the raw VFO output
+            # the iq result stays the raw VFO output (the plain VFO takes the low-latency tail kernel, the one with a chain the
+            # general one: same arithmetic, different summation order)
+            assert len(y) == len(y0) and (len(y) == 0 or rel_rms(y, y0) <= 1e-6)
             p = y
             if nb is not None:
                 p = nb.process(p)
