@@ -299,6 +299,26 @@ SDRPP_API int sdrpp_cuda_frontend_set_fft_zoom(sdrpp_cuda_frontend* fe, double v
                                                double wholeBandwidth, int outSize, int keep_raw);
 /* Zoomed rows completed in the last waited block (each outSize floats): returns the row count. */
 SDRPP_API int sdrpp_cuda_fft_zoomed_rows(sdrpp_cuda_frontend* fe, const float** rows);
+/* The waterfall's per-line display state on the ZOOMED row (WaterFall::pushFFT, gui/widgets/waterfall.cpp:918-956), kept on
+ * the device: FFT smoothing latest = speed*latest + (1-speed)*smoothingBuf (setFFTSmoothing / setFFTSmoothingSpeed,
+ * waterfall.cpp:1183-1211; the zoomed rows handed back are then the smoothed ones) and peak hold hold[i] = max(latest[i],
+ * hold[i] - holdSpeed) for i >= 1 (setFFTHold / setFFTHoldSpeed, waterfall.cpp:1169-1181). Needs set_fft_zoom. */
+SDRPP_API int sdrpp_cuda_frontend_set_fft_display(sdrpp_cuda_frontend* fe, int smoothing, float smoothingSpeed, int hold, float holdSpeed);
+/* The peak-hold row after the last waited block: returns its width (0 when hold is off or the block completed no row). */
+SDRPP_API int sdrpp_cuda_fft_hold_row(sdrpp_cuda_frontend* fe, const float** row);
+/* WaterFall::calculateVFOSignalInfo (gui/widgets/waterfall.cpp:563-603) for this VFO on every RAW spectrum row, on the
+ * device: strength = largest bin inside the VFO's bandwidth, snr = strength - mean of the half-bandwidth shoulders on
+ * both sides (what the scanner module reads, misc_modules/scanner/src/main.cpp:164). centerOffset and bandwidth are the
+ * VFO's own, wholeBandwidth the effective sample rate. */
+SDRPP_API int sdrpp_cuda_vfo_set_signal_info(sdrpp_cuda_frontend* fe, int vfo, int enabled);
+/* setSNRSmoothing / setSNRSmoothingSpeed (waterfall.cpp:1213-1220): snr = (1-speed)*snr + speed*new, row by row. */
+SDRPP_API int sdrpp_cuda_frontend_set_snr_smoothing(sdrpp_cuda_frontend* fe, int enabled, float speed);
+/* Per-row results of the last waited block (up to cap rows): returns the row count. level_max (optional) = the maximum of
+ * the last ten levels (selectedVFO_LevelMax, waterfall.cpp:937-948). */
+SDRPP_API int sdrpp_cuda_vfo_signal_info(sdrpp_cuda_frontend* fe, int vfo, float* strength, float* snr, float* level_max, int cap);
+/* One-shot form on a host row of N floats, for nvfo (centerOffset, bandwidth) pairs. */
+SDRPP_API int sdrpp_cuda_signal_info(int N, const float* row, int nvfo, const double* centerOffset, const double* bandwidth,
+                                     double wholeBandwidth, float* strength, float* snr);
 /* The post-preprocessing IQ block as the Splitter would hand it to bound streams
  * (IQFrontEnd::bindIQStream, signal_path/iq_frontend.cpp:114-116; recorder tap). Copies up to cap
  * samples of the last block to `out` (device->host); returns the count. */

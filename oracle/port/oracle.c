@@ -1031,4 +1031,54 @@ API void orc_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandw
     }
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* level / SNR read-out and the waterfall's per-line display state              */
+/* ------------------------------------------------------------------------------------------ */
+/* WaterFall::calculateVFOSignalInfo, gui/widgets/waterfall.cpp:563-603 (restated: the widget cannot be compiled here) */
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+API int orc_vfo_signal_info(const float* fftLine, int rawFFTSize, double centerOffset, double bandwidth, double wholeBandwidth,
+                            float* strength, float* snr) {
+    double vfoMinSizeFreq = centerOffset - bandwidth;
+    double vfoMinFreq = centerOffset - (bandwidth / 2.0);
+    double vfoMaxFreq = centerOffset + (bandwidth / 2.0);
+    double vfoMaxSizeFreq = centerOffset + bandwidth;
+    int vfoMinSideOffset = clampi((int)(((vfoMinSizeFreq / (wholeBandwidth / 2.0)) * (double)(rawFFTSize / 2)) + (rawFFTSize / 2)), 0, rawFFTSize);
+    int vfoMinOffset = clampi((int)(((vfoMinFreq / (wholeBandwidth / 2.0)) * (double)(rawFFTSize / 2)) + (rawFFTSize / 2)), 0, rawFFTSize);
+    int vfoMaxOffset = clampi((int)(((vfoMaxFreq / (wholeBandwidth / 2.0)) * (double)(rawFFTSize / 2)) + (rawFFTSize / 2)), 0, rawFFTSize);
+    int vfoMaxSideOffset = clampi((int)(((vfoMaxSizeFreq / (wholeBandwidth / 2.0)) * (double)(rawFFTSize / 2)) + (rawFFTSize / 2)), 0, rawFFTSize);
+    double avg = 0;
+    float max = -INFINITY;
+    int avgCount = 0, i;
+    if (!fftLine) return 0;
+    for (i = vfoMinSideOffset; i < vfoMinOffset; i++) { avg += fftLine[i]; avgCount++; }
+    for (i = vfoMaxOffset + 1; i < vfoMaxSideOffset; i++) { avg += fftLine[i]; avgCount++; }
+    avg /= (double)(avgCount);
+    for (i = vfoMinOffset; i <= vfoMaxOffset && i < rawFFTSize; i++) { if (fftLine[i] > max) max = fftLine[i]; }   /* the reference reads fftLine[rawFFTSize] when the VFO touches the upper edge */
+    *strength = max;
+    *snr = (float)(max - avg);
+    return 1;
+}
+/* WaterFall::pushFFT, waterfall.cpp:918-925 (smoothing: three generic-VOLK calls) and :951-956 (peak hold), on nrows zoomed
+ * rows of dataWidth pixels in place; smoothingBuf / latestFFTHold carry from call to call. */
+API void orc_fft_display(int dataWidth, int nrows, float* rows, int smoothing, float alpha, float* smoothingBuf, int hold, float holdSpeed,
+                         float* latestFFTHold) {
+    const float beta = 1.0f - alpha;
+    int r, i;
+    for (r = 0; r < nrows; r++) {
+        float* latestFFT = rows + (size_t)r * (size_t)dataWidth;
+        if (smoothing) {
+            for (i = 0; i < dataWidth; i++) latestFFT[i] = latestFFT[i] * alpha;            /* volk_32f_s32f_multiply_32f */
+            for (i = 0; i < dataWidth; i++) smoothingBuf[i] = smoothingBuf[i] * beta;       /* volk_32f_s32f_multiply_32f */
+            for (i = 0; i < dataWidth; i++) smoothingBuf[i] = smoothingBuf[i] + latestFFT[i]; /* volk_32f_x2_add_32f */
+            memcpy(latestFFT, smoothingBuf, sizeof(float) * (size_t)dataWidth);
+        }
+        if (hold) {
+            for (i = 1; i < dataWidth; i++) {
+                const float d = latestFFTHold[i] - holdSpeed;
+                latestFFTHold[i] = (latestFFT[i] < d) ? d : latestFFT[i];                   /* std::max<float>(latestFFT[i], hold - speed) */
+            }
+        }
+    }
+}
+
 API const char* orc_build_info(void) { return "oracle port: plain-C restatement, IEEE fp32, generic-VOLK semantics"; }

@@ -306,6 +306,22 @@ class Port(_Base):
         """fft_scaler::doZoom; returns (pixels, bin boundaries)."""
         return _zoom(self._f("fft_zoom", None, _d, _d, _d, _i, _i, _vp, _vp, _vp), view_offset, view_bw, whole_bw, row, out_size, True)
 
+    def vfo_signal_info(self, row, center_offset, bandwidth, whole_bw):
+        """WaterFall::calculateVFOSignalInfo (waterfall.cpp:563-603): (strength, snr) of one raw row."""
+        row = np.ascontiguousarray(row, dtype=np.float32)
+        st, sn = C.c_float(0), C.c_float(0)
+        self._f("vfo_signal_info", _i, _vp, _i, _d, _d, _d, _vp, _vp)(_ptr(row), len(row), center_offset, bandwidth, whole_bw, C.byref(st), C.byref(sn))
+        return st.value, sn.value
+
+    def fft_display(self, rows, smoothing, alpha, smooth_buf, hold, hold_speed, hold_buf):
+        """WaterFall::pushFFT smoothing + peak hold on zoomed rows (in place on copies); returns (rows, smooth_buf, hold_buf)."""
+        rows = np.array(rows, dtype=np.float32, copy=True)
+        sb = np.array(smooth_buf, dtype=np.float32, copy=True)
+        hb = np.array(hold_buf, dtype=np.float32, copy=True)
+        self._f("fft_display", None, _i, _i, _vp, _i, C.c_float, _vp, _i, C.c_float, _vp)(rows.shape[1], rows.shape[0], _ptr(rows), int(smoothing), alpha, _ptr(sb),
+                                                                                           int(hold), hold_speed, _ptr(hb))
+        return rows, sb, hb
+
     def reshape_params(self, sr, size, rate):
         skip, nz = _i(), _i()
         self._f("reshape_params", None, _d, _i, _d, _vp, _vp)(sr, size, rate, C.byref(skip), C.byref(nz))

@@ -210,6 +210,15 @@ bool zoom_indices(double viewOffset, double viewBandwidth, double wholeBandwidth
     return true;
 }
 
+void signal_info_bins(double centerOffset, double bandwidth, double wholeBandwidth, int rawFFTSize, int out[4]) {
+    // gui/widgets/waterfall.cpp:567-574, operation for operation (double arithmetic, truncation to int, clamp to [0, size])
+    const double f[4] = { centerOffset - bandwidth, centerOffset - (bandwidth / 2.0), centerOffset + (bandwidth / 2.0), centerOffset + bandwidth };
+    for (int i = 0; i < 4; i++) {
+        const int v = (int)(((f[i] / (wholeBandwidth / 2.0)) * (double)(rawFFTSize / 2)) + (rawFFTSize / 2));
+        out[i] = v < 0 ? 0 : (v > rawFFTSize ? rawFFTSize : v);
+    }
+}
+
 void xlator_increment(double offsetHz, double sampleRate, float* inc_re, float* inc_im, double* turns_eff) {
     const double w = 2.0 * kPi * (offsetHz / sampleRate); // math/hz_to_rads.h:6-8
     const float re = (float)cos(w), im = (float)sin(w);   // frequency_xlator.h:17-19

@@ -50,6 +50,9 @@ void reshape_params(double sampleRate, int size, double rate, int* skip, int* nz
 // idx has outSize+1 entries; pixel i covers bins [idx[i], max(idx[i]+1, idx[i+1])) when ranged, bin idx[i] otherwise.
 bool zoom_indices(double viewOffset, double viewBandwidth, double wholeBandwidth, int fftSize, int outSize, std::vector<int>* idx);
 
+// Bin ranges of WaterFall::calculateVFOSignalInfo (gui/widgets/waterfall.cpp:567-574): out = (minSide, min, max, maxSide).
+void signal_info_bins(double centerOffset, double bandwidth, double wholeBandwidth, int rawFFTSize, int out[4]);
+
 // FrequencyXlator increment (dsp/channel/frequency_xlator.h:15-23): the fp32-quantised phasor
 // (cos w, sin w) and the frequency it actually realises, in turns per sample.
 void xlator_increment(double offsetHz, double sampleRate, float* inc_re, float* inc_im, double* turns_eff);

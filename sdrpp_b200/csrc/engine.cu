@@ -17,6 +17,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -224,6 +225,11 @@ struct Vfo {
     int post_ntaps = 0, post_hist_pad = 0;
     // radio IF chain: device record of IF_FLOATS floats, null until first configured
     float* if_state = nullptr;
+    // level / SNR read-out on every spectrum row: slot in the signal-info table, -1 = off
+    bool sig_on = false;
+    int sig_slot = -1;
+    float sig_snr = 0.0f;              // smoothed SNR carried from row to row (waterfall.cpp:928-932)
+    std::vector<float> sig_levels;     // last 10 levels (selectedVFO_LevelHistory)
 };
 
 struct Group {
@@ -248,6 +254,11 @@ struct ResultSet {
     float* audio = nullptr;
     float* rows = nullptr;
     float* zoom = nullptr;
+    float* hold = nullptr;        // peak-hold row after this block (zoom_out floats)
+    float2* sig = nullptr;        // (strength, snr) per row and signal-info slot
+    int nsig = 0;
+    std::vector<int> sig_slot;    // per VFO id: slot at submit, -1 = off
+    std::set<int> sig_done;       // VFO ids whose row-to-row recurrences (SNR smoothing, level history) were applied
     int nrows = 0;
     std::vector<int> counts;      // per VFO id
     std::vector<uint32_t> offs;   // per VFO id: arena offset of its rows WHEN THE BLOCK WAS SUBMITTED (the layout may change later)
@@ -320,6 +331,13 @@ struct sdrpp_cuda_frontend {
     int zoom_out = 0; bool zoom_ranged = false, zoom_keep_raw = true;
     double zoom_view[3] = { 0, 0, 0 };
     int* d_zoom_idx = nullptr; float* d_zoom = nullptr;
+    // display state on the zoomed row (WaterFall::pushFFT): smoothing buffer, peak hold, latest row
+    bool disp_smoothing = false, disp_hold = false;
+    float disp_alpha = 0.5f, disp_hold_speed = 0.3f;
+    float* d_disp = nullptr;      // [smooth | hold | latest] x zoom_out
+    // level / SNR of selected VFOs on every raw row (WaterFall::calculateVFOSignalInfo)
+    int4* d_sig_bins = nullptr; float2* d_sig = nullptr; int sig_cap = 0, nsig = 0; bool sig_dirty = true;
+    bool snr_smoothing = false; float snr_alpha = 0.5f;
 
     // VFOs
     std::vector<Vfo> vfos;
@@ -405,7 +423,9 @@ static int configure_preproc(sdrpp_cuda_frontend* fe) {
 static int configure_zoom(sdrpp_cuda_frontend* fe) {
     if (fe->d_zoom_idx) { cudaFree(fe->d_zoom_idx); fe->d_zoom_idx = nullptr; }
     if (fe->d_zoom) { cudaFree(fe->d_zoom); fe->d_zoom = nullptr; }
+    if (fe->d_disp) { cudaFree(fe->d_disp); fe->d_disp = nullptr; }
     for (int i = 0; i < kSets; i++) if (fe->rs[i].zoom) { cudaFreeHost(fe->rs[i].zoom); fe->rs[i].zoom = nullptr; }
+    for (int i = 0; i < kSets; i++) if (fe->rs[i].hold) { cudaFreeHost(fe->rs[i].hold); fe->rs[i].hold = nullptr; }
     if (fe->zoom_out <= 0 || fe->cfg.fft_size <= 0 || fe->rows_cap <= 0) return SDRPP_OK;
     std::vector<int> idx;
     fe->zoom_ranged = zoom_indices(fe->zoom_view[0], fe->zoom_view[1], fe->zoom_view[2], fe->cfg.fft_size, fe->zoom_out, &idx);
@@ -413,6 +433,13 @@ static int configure_zoom(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, upload_sync(fe->d_zoom_idx, idx.data(), idx.size() * sizeof(int)));
     FE_TRY(fe, dev_alloc(&fe->d_zoom, (size_t)fe->rows_cap * fe->zoom_out, false));
     for (int i = 0; i < kSets; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].zoom, (size_t)fe->rows_cap * fe->zoom_out * sizeof(float)));
+    // smoothing buffer, peak hold and latest row start at -1000 dB ("hide everything", waterfall.cpp:774-788)
+    {
+        std::vector<float> init((size_t)3 * fe->zoom_out, -1000.0f);
+        FE_TRY(fe, dev_alloc(&fe->d_disp, init.size(), false));
+        FE_TRY(fe, upload_sync(fe->d_disp, init.data(), init.size() * sizeof(float)));
+        for (int i = 0; i < kSets; i++) FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].hold, (size_t)fe->zoom_out * sizeof(float)));
+    }
     return SDRPP_OK;
 }
 
@@ -618,6 +645,7 @@ static void set_nco(sdrpp_cuda_frontend* fe, Vfo& v, double offset, bool keep_ph
     v.dphi = turns_to_u64(turns);
     v.phi_ref = phi_now; v.n_ref = now;
     v.offset = offset;
+    fe->sig_dirty = true;
     // SSB second translation (demod/ssb.h:119-126) at the output rate
     double tr = 0.0;
     if (v.demod == SDRPP_DEMOD_USB) tr = v.bw / 2.0;
@@ -670,6 +698,43 @@ static int apply_post(sdrpp_cuda_frontend* fe, Vfo& v) {
     float init[5] = { 0.0f, (float)10e6, 0.0f, (float)10e6, 0.0f };
     if (v.post.agc_gain > 0.0f) init[1] = v.post.agc_gain; // setAGCGain (am.h:69-73, ssb.h)
     FE_TRY(fe, upload_sync(v.post_state, init, sizeof(init)));
+    return SDRPP_OK;
+}
+
+// Signal-info table: one (minSide, min, max, maxSide) bin record per VFO with the read-out enabled, rebuilt when a VFO is
+// retuned, resized, enabled or removed. centerOffset / bandwidth are the VFO's own (what its WaterfallVFO carries),
+// wholeBandwidth the effective sample rate (gui::waterfall.setBandwidth, core.cpp:52-55).
+static int refresh_signal_info(sdrpp_cuda_frontend* fe) {
+    if (!fe->sig_dirty) return SDRPP_OK;
+    std::vector<int4> bins;
+    for (Vfo& v : fe->vfos) {
+        v.sig_slot = -1;
+        if (!v.alive || !v.sig_on) continue;
+        int b[4];
+        signal_info_bins(v.offset, v.bw, fe->eff_sr, fe->cfg.fft_size, b);
+        v.sig_slot = (int)bins.size();
+        bins.push_back(make_int4(b[0], b[1], b[2], b[3]));
+    }
+    fe->nsig = (int)bins.size();
+    const int need = fe->nsig * std::max(fe->rows_cap, 1);
+    if (fe->nsig > 0 && (need > fe->sig_cap || !fe->d_sig_bins)) {
+        FE_TRY(fe, cudaStreamSynchronize(fe->st_fft));
+        cudaFree(fe->d_sig_bins); cudaFree(fe->d_sig);
+        fe->d_sig_bins = nullptr; fe->d_sig = nullptr;
+        FE_TRY(fe, dev_alloc(&fe->d_sig_bins, (size_t)std::max(fe->nsig, 16), false));
+        FE_TRY(fe, dev_alloc(&fe->d_sig, (size_t)std::max(need, 16), false));
+        for (int i = 0; i < kSets; i++) {
+            if (fe->rs[i].sig) cudaFreeHost(fe->rs[i].sig);
+            fe->rs[i].sig = nullptr;
+            FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].sig, (size_t)std::max(need, 16) * sizeof(float2)));
+        }
+        fe->sig_cap = std::max(need, 16);
+    }
+    if (fe->nsig > 0) {
+        FE_TRY(fe, cudaStreamSynchronize(fe->st_fft));
+        FE_TRY(fe, upload_sync(fe->d_sig_bins, bins.data(), bins.size() * sizeof(int4)));
+    }
+    fe->sig_dirty = false;
     return SDRPP_OK;
 }
 
@@ -771,8 +836,30 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     if (rs.nrows > 0 && fe->zoom_out > 0) {
         FE_TRY(fe, launch_fft_zoom(fe->d_rows, fe->cfg.fft_size, rs.nrows, fe->d_zoom_idx, fe->zoom_out, fe->zoom_ranged, fe->d_zoom, sf));
         fe->launches++;
+        if (fe->disp_smoothing || fe->disp_hold) {
+            const int W = fe->zoom_out;
+            FE_TRY(fe, launch_fft_display(fe->d_zoom, W, rs.nrows, fe->disp_smoothing, fe->disp_alpha, fe->d_disp, fe->disp_hold, fe->disp_hold_speed,
+                                          fe->d_disp + W, fe->d_disp + 2 * W, sf));
+            fe->launches++;
+            if (fe->readback && fe->disp_hold) FE_TRY(fe, cudaMemcpyAsync(rs.hold, fe->d_disp + W, (size_t)W * sizeof(float), cudaMemcpyDeviceToHost, sf));
+        }
         if (fe->readback)
             FE_TRY(fe, cudaMemcpyAsync(rs.zoom, fe->d_zoom, (size_t)rs.nrows * fe->zoom_out * sizeof(float), cudaMemcpyDeviceToHost, sf));
+    }
+    rs.nsig = 0;
+    rs.sig_done.clear();
+    if (rs.nrows > 0 && fe->cfg.fft_size > 0) {
+        int rc = refresh_signal_info(fe);
+        if (rc != SDRPP_OK) return rc;
+        if (fe->nsig > 0) {
+            FE_TRY(fe, launch_signal_info(fe->d_rows, fe->cfg.fft_size, rs.nrows, fe->d_sig_bins, fe->nsig, fe->d_sig, sf));
+            fe->launches++;
+            if (fe->readback)
+                FE_TRY(fe, cudaMemcpyAsync(rs.sig, fe->d_sig, (size_t)rs.nrows * fe->nsig * sizeof(float2), cudaMemcpyDeviceToHost, sf));
+            rs.nsig = fe->nsig;
+            rs.sig_slot.assign(fe->vfos.size(), -1);
+            for (size_t id = 0; id < fe->vfos.size(); id++) if (fe->vfos[id].alive && fe->vfos[id].sig_on) rs.sig_slot[id] = fe->vfos[id].sig_slot;
+        }
     }
     if (fe->readback && rs.nrows > 0 && (fe->zoom_keep_raw || fe->zoom_out <= 0))
         FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, sf));
@@ -1399,6 +1486,31 @@ int sdrpp_cuda_fft_zoom(int N, const float* row, double viewOffset, double viewB
     return SDRPP_OK;
 }
 
+int sdrpp_cuda_signal_info(int N, const float* row, int nvfo, const double* centerOffset, const double* bandwidth, double wholeBandwidth,
+                           float* strength, float* snr) {
+    if (N < 2 || !row || nvfo < 1 || !centerOffset || !bandwidth || !(wholeBandwidth > 0)) return fail(SDRPP_ERR_ARG, "bad argument");
+    std::vector<int4> bins((size_t)nvfo);
+    for (int v = 0; v < nvfo; v++) {
+        int b[4];
+        signal_info_bins(centerOffset[v], bandwidth[v], wholeBandwidth, N, b);
+        bins[(size_t)v] = make_int4(b[0], b[1], b[2], b[3]);
+    }
+    std::lock_guard<std::mutex> lck(g_os.mtx);
+    int rc = os_prepare();
+    if (rc != SDRPP_OK) return rc;
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, (size_t)N * 4));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, (size_t)nvfo * sizeof(int4)));
+    SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, (size_t)nvfo * sizeof(float2)));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, row, (size_t)N * 4, cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_b, bins.data(), (size_t)nvfo * sizeof(int4), cudaMemcpyHostToDevice, g_os.st));
+    SDRPP_CUDA_TRY(launch_signal_info((const float*)g_os.d_a, N, 1, (const int4*)g_os.d_b, nvfo, (float2*)g_os.d_c, g_os.st));
+    std::vector<float2> out((size_t)nvfo);
+    SDRPP_CUDA_TRY(cudaMemcpyAsync(out.data(), g_os.d_c, (size_t)nvfo * sizeof(float2), cudaMemcpyDeviceToHost, g_os.st));
+    SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
+    for (int v = 0; v < nvfo; v++) { if (strength) strength[v] = out[(size_t)v].x; if (snr) snr[v] = out[(size_t)v].y; }
+    return SDRPP_OK;
+}
+
 // ---- front end ---------------------------------------------------------------------------------
 sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* cfg) {
     if (!cfg) { set_last_error("null cfg"); return nullptr; }
@@ -1492,7 +1604,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     for (float2* b : fe->fe_buf) cudaFree(b);
     cudaFree(fe->dc_in); cudaFree(fe->dc_state); cudaFree(fe->dc_scratch);
     cudaFree(fe->ring); cudaFree(fe->d_window); cudaFree(fe->d_inter); cudaFree(fe->d_rows);
-    cudaFree(fe->d_zoom_idx); cudaFree(fe->d_zoom);
+    cudaFree(fe->d_zoom_idx); cudaFree(fe->d_zoom); cudaFree(fe->d_disp); cudaFree(fe->d_sig_bins); cudaFree(fe->d_sig);
     cudaFree(fe->d_vfos); cudaFree(fe->d_post); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod); cudaFree(fe->d_arena_audio);
     for (int i = 0; i < kSets; i++) {
         if (fe->h_stage[i]) cudaFreeHost(fe->h_stage[i]);
@@ -1506,6 +1618,8 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
         if (fe->rs[i].rows) cudaFreeHost(fe->rs[i].rows);
         if (fe->rs[i].zoom) cudaFreeHost(fe->rs[i].zoom);
+        if (fe->rs[i].hold) cudaFreeHost(fe->rs[i].hold);
+        if (fe->rs[i].sig) cudaFreeHost(fe->rs[i].sig);
     }
     for (int i = 0; i < 5; i++) if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
     if (fe->st) cudaStreamDestroy(fe->st);
@@ -1963,6 +2077,87 @@ int sdrpp_cuda_frontend_set_fft_zoom(sdrpp_cuda_frontend* fe, double viewOffset,
     fe->zoom_out = outSize; fe->zoom_keep_raw = keep_raw != 0;
     fe->zoom_view[0] = viewOffset; fe->zoom_view[1] = viewBandwidth; fe->zoom_view[2] = wholeBandwidth;
     return configure_zoom(fe);
+}
+
+int sdrpp_cuda_frontend_set_fft_display(sdrpp_cuda_frontend* fe, int smoothing, float smoothingSpeed, int hold, float holdSpeed) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    if (fe->zoom_out <= 0 || !fe->d_disp) return fail(SDRPP_ERR_STATE, "smoothing / peak hold work on the zoomed row: call sdrpp_cuda_frontend_set_fft_zoom first");
+    const int W = fe->zoom_out;
+    if (smoothing && !fe->disp_smoothing) {
+        // setFFTSmoothing(true): the smoothing buffer starts as a copy of the latest row (waterfall.cpp:1197-1201)
+        FE_TRY(fe, cudaMemcpy(fe->d_disp, fe->d_disp + 2 * W, (size_t)W * sizeof(float), cudaMemcpyDeviceToDevice));
+        FE_TRY(fe, cudaStreamSynchronize(cudaStreamLegacy));
+    }
+    if (hold && !fe->disp_hold) {
+        // setFFTHold(true): the hold row restarts at -1000 dB (waterfall.cpp:1169-1177)
+        std::vector<float> init((size_t)W, -1000.0f);
+        FE_TRY(fe, upload_sync(fe->d_disp + W, init.data(), init.size() * sizeof(float)));
+    }
+    fe->disp_smoothing = smoothing != 0; fe->disp_alpha = smoothingSpeed;
+    fe->disp_hold = hold != 0; fe->disp_hold_speed = holdSpeed;
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_fft_hold_row(sdrpp_cuda_frontend* fe, const float** row) {
+    if (!fe) return fail(SDRPP_ERR_ARG, "null front end");
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    const ResultSet& rs = fe->rs[fe->cur];
+    if (row) *row = rs.hold;
+    return (fe->disp_hold && rs.hold && rs.nrows > 0) ? fe->zoom_out : 0;
+}
+
+int sdrpp_cuda_vfo_set_signal_info(sdrpp_cuda_frontend* fe, int id, int enabled) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    Vfo* v;
+    if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
+    if (enabled && fe->cfg.fft_size <= 0) return fail(SDRPP_ERR_STATE, "the level / SNR read-out needs the spectrum branch (fft_size > 0)");
+    v->sig_on = enabled != 0;
+    if (!enabled) { v->sig_snr = 0.0f; v->sig_levels.clear(); }
+    fe->sig_dirty = true;
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_set_snr_smoothing(sdrpp_cuda_frontend* fe, int enabled, float speed) {
+    int rc = fe_quiesce(fe);
+    if (rc != SDRPP_OK) return rc;
+    fe->snr_smoothing = enabled != 0; fe->snr_alpha = speed;
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_vfo_signal_info(sdrpp_cuda_frontend* fe, int id, float* strength, float* snr, float* level_max, int cap) {
+    Vfo* v;
+    int rc = vfo_get(fe, id, &v);
+    if (rc != SDRPP_OK) return rc;
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    ResultSet& rs = fe->rs[fe->cur];
+    if ((size_t)id >= rs.sig_slot.size() || rs.sig_slot[(size_t)id] < 0 || rs.nsig <= 0 || !rs.sig) return 0;
+    const int slot = rs.sig_slot[(size_t)id];
+    const int n = std::min(rs.nrows, std::max(cap, 0));
+    // the scalar recurrences of WaterFall::pushFFT (waterfall.cpp:927-949) on the per-row device results: optional SNR
+    // smoothing and the maximum of the last ten levels. Applied once per block, when its results are first read.
+    if (!rs.sig_done.count(id)) {
+        for (int r = 0; r < rs.nrows; r++) {
+            float2& e = rs.sig[(size_t)r * rs.nsig + slot];
+            if (fe->snr_smoothing) { v->sig_snr = ((1.0f - fe->snr_alpha) * v->sig_snr) + (fe->snr_alpha * e.y); e.y = v->sig_snr; }
+            else v->sig_snr = e.y;
+            v->sig_levels.push_back(e.x);
+            if (v->sig_levels.size() > 10) v->sig_levels.erase(v->sig_levels.begin());
+        }
+        rs.sig_done.insert(id);
+    }
+    for (int r = 0; r < n; r++) {
+        const float2 e = rs.sig[(size_t)r * rs.nsig + slot];
+        if (strength) strength[r] = e.x;
+        if (snr) snr[r] = e.y;
+    }
+    if (level_max) {
+        float m = -INFINITY;
+        for (float l : v->sig_levels) m = std::max(m, l);
+        *level_max = m;
+    }
+    return rs.nrows;
 }
 
 int sdrpp_cuda_fft_zoomed_rows(sdrpp_cuda_frontend* fe, const float** rows) {

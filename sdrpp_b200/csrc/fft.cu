@@ -271,6 +271,79 @@ cudaError_t launch_fft_zoom(const float* rows, int N, int nrows, const int* idx,
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// WaterFall::calculateVFOSignalInfo (gui/widgets/waterfall.cpp:563-603) on the device, for every (VFO, row) pair of a
+// block: strength = the largest bin inside the VFO's bandwidth, snr = strength - mean of the bins in the two half-
+// bandwidth shoulders beside it (summed in double like the reference; the order of the additions differs). One CTA per
+// pair; bins = (minSide, min, max, maxSide) are computed on the host with the reference's clamp arithmetic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+signal_info_kernel(const float* __restrict__ rows, int N, const int4* __restrict__ bins, float2* __restrict__ out, int nsig) {
+    __shared__ double ssum[8];
+    __shared__ float smax[8];
+    __shared__ int scnt[8];
+    const int v = blockIdx.x, r = blockIdx.y, tid = threadIdx.x;
+    const int4 b = bins[v];
+    const float* __restrict__ row = rows + (size_t)r * N;
+    double sum = 0.0;
+    int cnt = 0;
+    for (int i = b.x + tid; i < b.y; i += 256) { sum += (double)row[i]; cnt++; }          // left shoulder  [minSide, min)
+    for (int i = b.z + 1 + tid; i < b.w; i += 256) { sum += (double)row[i]; cnt++; }      // right shoulder (max, maxSide)
+    float m = -INFINITY;
+    for (int i = b.y + tid; i <= b.z && i < N; i += 256) { const float x = row[i]; m = (x > m) ? x : m; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const float x = __shfl_xor_sync(0xffffffffu, m, o); m = (x > m) ? x : m;
+    }
+    if ((tid & 31) == 0) { ssum[tid >> 5] = sum; smax[tid >> 5] = m; scnt[tid >> 5] = cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; w++) { sum += ssum[w]; cnt += scnt[w]; m = (smax[w] > m) ? smax[w] : m; }
+        const double avg = sum / (double)cnt;                    // 0/0 = NaN when there is no shoulder, as in the reference
+        out[(size_t)r * nsig + v] = make_float2(m, (float)((double)m - avg));   // strength = max; snr = max - avg (float - double)
+    }
+}
+
+cudaError_t launch_signal_info(const float* rows, int N, int nrows, const int4* bins, int nsig, float2* out, cudaStream_t st) {
+    if (nrows <= 0 || nsig <= 0) return cudaSuccess;
+    signal_info_kernel<<<dim3((unsigned)nsig, (unsigned)nrows), 256, 0, st>>>(rows, N, bins, out, nsig);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// The waterfall's per-line display state on the zoomed row (WaterFall::pushFFT, gui/widgets/waterfall.cpp:918-956):
+// FFT smoothing latest = alpha*latest + beta*smoothingBuf (three VOLK calls: two multiplies and an add, each rounded)
+// and peak hold hold[i] = max(latest[i], hold[i] - speed) for i >= 1. Sequential from line to line, parallel over the
+// pixels: one thread per pixel walks the block's rows in order. `latest` keeps the last (smoothed) row, which is what
+// setFFTSmoothing(true) seeds the smoothing buffer with (waterfall.cpp:1197-1201).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+fft_display_kernel(float* __restrict__ zoom, int W, int nrows, bool smoothing, float alpha, float beta, float* __restrict__ smooth,
+                   bool hold_on, float hold_speed, float* __restrict__ hold, float* __restrict__ latest) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= W) return;
+    float sb = smooth[i], hb = hold[i], v = latest[i];
+    for (int r = 0; r < nrows; r++) {
+        v = zoom[(size_t)r * W + i];
+        if (smoothing) {
+            sb = __fadd_rn(__fmul_rn(sb, beta), __fmul_rn(v, alpha));
+            v = sb;
+            zoom[(size_t)r * W + i] = v;
+        }
+        if (hold_on && i >= 1) { const float d = __fsub_rn(hb, hold_speed); hb = (v < d) ? d : v; }   // std::max(latest, hold - speed)
+    }
+    smooth[i] = sb; hold[i] = hb; latest[i] = v;
+}
+
+cudaError_t launch_fft_display(float* zoom, int W, int nrows, bool smoothing, float alpha, float* smooth, bool hold_on, float hold_speed,
+                               float* hold, float* latest, cudaStream_t st) {
+    if (nrows <= 0 || W <= 0) return cudaSuccess;
+    fft_display_kernel<<<ceil_div(W, 256), 256, 0, st>>>(zoom, W, nrows, smoothing, alpha, 1.0f - alpha, smooth, hold_on, hold_speed, hold, latest);
+    return cudaGetLastError();
+}
+
 int spectrum_split(int N, int* N1, int* N2) {
     int lg = 0;
     while ((1 << lg) < N) lg++;

@@ -58,6 +58,13 @@ cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long 
 // [idx[i], idx[i+1]) (ranged) or rows[r][idx[i]] (point sampling). Reads are clamped to the row.
 cudaError_t launch_fft_zoom(const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out, cudaStream_t st);
 
+// WaterFall::calculateVFOSignalInfo (gui/widgets/waterfall.cpp:563-603) for nsig VFOs x nrows rows: out[r*nsig + v] =
+// (strength, snr); bins[v] = (minSide, min, max, maxSide) bin indices (design.h: signal_info_bins).
+cudaError_t launch_signal_info(const float* rows, int N, int nrows, const int4* bins, int nsig, float2* out, cudaStream_t st);
+// FFT smoothing and peak hold of the zoomed rows, in place (WaterFall::pushFFT, waterfall.cpp:918-956); state buffers of W floats.
+cudaError_t launch_fft_display(float* zoom, int W, int nrows, bool smoothing, float alpha, float* smooth, bool hold_on, float hold_speed,
+                               float* hold, float* latest, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------
 // Channelizer (channelizer.cu)
 // ---------------------------------------------------------------------------------------------

@@ -38,7 +38,8 @@ sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio sdrpp_cuda_vfo_set_if_chain sdrpp_c
 sdrpp_cuda_frontend_set_stage1_mode sdrpp_cuda_frontend_stage1_tensor_launches
 sdrpp_cuda_frontend_wait_input sdrpp_cuda_frontend_pending sdrpp_cuda_frontend_drain sdrpp_cuda_frontend_join_streams
 sdrpp_cuda_comm_unique_id sdrpp_cuda_comm_create sdrpp_cuda_comm_destroy sdrpp_cuda_comm_info sdrpp_cuda_frontend_set_comm
-sdrpp_cuda_frontend_submit_shared
+sdrpp_cuda_frontend_submit_shared sdrpp_cuda_frontend_set_fft_display sdrpp_cuda_fft_hold_row sdrpp_cuda_vfo_set_signal_info
+sdrpp_cuda_frontend_set_snr_smoothing sdrpp_cuda_vfo_signal_info sdrpp_cuda_signal_info
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -125,6 +126,12 @@ def lib():
         L.sdrpp_cuda_comm_info.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]
         L.sdrpp_cuda_frontend_set_comm.argtypes = [_vp, _vp, _i]
         L.sdrpp_cuda_frontend_submit_shared.argtypes = [_vp, _i, _i]
+        L.sdrpp_cuda_frontend_set_fft_display.argtypes = [_vp, _i, C.c_float, _i, C.c_float]
+        L.sdrpp_cuda_fft_hold_row.argtypes = [_vp, C.POINTER(_vp)]
+        L.sdrpp_cuda_vfo_set_signal_info.argtypes = [_vp, _i, _i]
+        L.sdrpp_cuda_frontend_set_snr_smoothing.argtypes = [_vp, _i, C.c_float]
+        L.sdrpp_cuda_vfo_signal_info.argtypes = [_vp, _i, _vp, _vp, _vp, _i]
+        L.sdrpp_cuda_signal_info.argtypes = [_i, _vp, _i, _vp, _vp, _d, _vp, _vp]
         L.sdrpp_cuda_vfo_output.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]
         L.sdrpp_cuda_fft_rows.argtypes = [_vp, C.POINTER(_vp)]
         L.sdrpp_cuda_vfo_set_post.argtypes = [_vp, _i, C.POINTER(PostCfg)]
@@ -262,6 +269,16 @@ def fft_zoom(row, view_offset, view_bw, whole_bw, out_size):
     idx = np.zeros(out_size + 1, dtype=np.int32)
     _check(lib().sdrpp_cuda_fft_zoom(len(row), _ptr(row), view_offset, view_bw, whole_bw, out_size, _ptr(out), _ptr(idx)), "sdrpp_cuda_fft_zoom")
     return out, idx
+
+
+def signal_info(row, center_offsets, bandwidths, whole_bw):
+    """WaterFall::calculateVFOSignalInfo on the GPU for several (centerOffset, bandwidth) pairs; returns (strength, snr)."""
+    row = np.ascontiguousarray(row, dtype=np.float32)
+    co = np.ascontiguousarray(center_offsets, dtype=np.float64)
+    bw = np.ascontiguousarray(bandwidths, dtype=np.float64)
+    st, sn = np.zeros(len(co), np.float32), np.zeros(len(co), np.float32)
+    _check(lib().sdrpp_cuda_signal_info(len(row), _ptr(row), len(co), _ptr(co), _ptr(bw), whole_bw, _ptr(st), _ptr(sn)), "sdrpp_cuda_signal_info")
+    return st, sn
 
 
 # ---- pinned host buffers -----------------------------------------------------------------------
@@ -490,6 +507,30 @@ class Frontend:
             return np.zeros((0, getattr(self, "zoom_out", 0)), np.float32)
         a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n, self.zoom_out))
         return a.copy() if copy else a
+
+    def set_fft_display(self, smoothing=False, smoothing_speed=0.5, hold=False, hold_speed=0.3):
+        """FFT smoothing and peak hold on the zoomed row (WaterFall::pushFFT)."""
+        _check(lib().sdrpp_cuda_frontend_set_fft_display(self.h, int(smoothing), smoothing_speed, int(hold), hold_speed), "set_fft_display")
+
+    def fft_hold_row(self):
+        p = _vp()
+        n = _check(lib().sdrpp_cuda_fft_hold_row(self.h, C.byref(p)), "fft_hold_row")
+        if n == 0:
+            return np.zeros(0, np.float32)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).copy()
+
+    def vfo_set_signal_info(self, vid, enabled=True):
+        _check(lib().sdrpp_cuda_vfo_set_signal_info(self.h, vid, int(enabled)), "vfo_set_signal_info")
+
+    def set_snr_smoothing(self, enabled, speed=0.5):
+        _check(lib().sdrpp_cuda_frontend_set_snr_smoothing(self.h, int(enabled), speed), "set_snr_smoothing")
+
+    def vfo_signal_info(self, vid, cap=64):
+        st, sn = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+        mx = C.c_float(0)
+        n = _check(lib().sdrpp_cuda_vfo_signal_info(self.h, vid, _ptr(st), _ptr(sn), C.byref(mx), cap), "vfo_signal_info")
+        n = min(n, cap)
+        return st[:n], sn[:n], float(mx.value)
 
     def read_iq(self, cap):
         out = np.zeros(cap, dtype=np.complex64)
