@@ -87,6 +87,10 @@ SDRPP_API void sdrpp_cuda_host_free(void* p);
 SDRPP_API int sdrpp_cuda_design_window(int type, float* buf, int size, int centered);
 /* dsp::taps::lowPass (dsp/taps/low_pass.h:7-11). Returns the tap count; writes min(count,cap). */
 SDRPP_API int sdrpp_cuda_design_lowpass(double cutoff, double transWidth, double sampleRate, float* out, int cap);
+/* dsp::taps::bandPass<dsp::complex_t> (dsp/taps/band_pass.h:10-25): complex band-pass taps, interleaved (re, im); the pilot
+ * filter of the WFM stereo decoder is bandPass(18750, 19250, 3000, sampleRate, true). Returns the tap count. */
+SDRPP_API int sdrpp_cuda_design_bandpass_complex(double bandStart, double bandStop, double transWidth, double sampleRate,
+                                                 int oddTapCount, float* out, int cap);
 /* dsp::multirate::RationalResampler::reconfigure (dsp/multirate/rational_resampler.h:121-167).
  * info[0]=mode (0 BOTH,1 DECIM_ONLY,2 RESAMP_ONLY,3 NONE) [1]=predec ratio [2]=interp [3]=decim
  * [4]=tap count [5]=taps per phase; taps (optional) are already scaled by interp. */
@@ -246,6 +250,10 @@ SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrp
  *   QUADRATURE: dsp::demod::FM<float>  -- optional low-pass FIR lowPass(bw/2, bw/20, outSR) (dsp/demod/fm.h:86-103,117-145)
  *   AM:         dsp::demod::AM<float>  -- [carrier AGC] -> magnitude -> DC block -> [audio AGC] -> low-pass (dsp/demod/am.h:27-44,114-146)
  *   USB/LSB/DSB: dsp::demod::SSB<float> -- AGC on the real output (dsp/demod/ssb.h:21-36,90-101)
+ *   QUADRATURE with wfm = 1: dsp::demod::BroadcastFM (dsp/demod/broadcast_fm.h:35-65,147-214), the WFM stereo decoder of the
+ *               radio module (decoder_modules/radio/src/demodulators/wfm.h): 19 kHz pilot band-pass -> PLL -> L-R down-conversion
+ *               -> L/R matrix -> 15 kHz low-pass; deviation = bandwidth / 2. Stereo output: sdrpp_cuda_vfo_audio_stereo. The RDS
+ *               side output (rdsOut) is not built.
  * with dsp::loop::AGC (dsp/loop/agc.h:87-147: setPoint 1, maxGain 10e6, maxOutputAmp 10, initGain INFINITY) and
  * dsp::correction::DCBlocker<float> (dsp/correction/dc_blocker.h:54-60). The radio module passes attack/decay/rate
  * already divided by the IF sample rate (decoder_modules/radio/src/demodulators/am.h:38, usb.h:40). */
@@ -258,11 +266,16 @@ typedef struct {
     double agc_decay;      /* per-sample decay coefficient */
     double dc_block_rate;  /* AM: dcBlockRate */
     float agc_gain;        /* > 0: setAGCGain(agc_gain) after init (the fixed gain when the audio AGC is off) */
+    int wfm;               /* QUADRATURE only: 1 = dsp::demod::BroadcastFM (stereo decoder) instead of dsp::demod::FM */
+    int wfm_stereo;        /* BroadcastFM _stereo (setStereo); the low-pass switch is fm_lowpass (setLowPass) */
 } sdrpp_cuda_post_cfg;
 /* (Re)initialises the VFO's post-detector objects; also redone when the VFO's bandwidth or rate changes. */
 SDRPP_API int sdrpp_cuda_vfo_set_post(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cuda_post_cfg* cfg);
 /* Demodulated audio of the last waited block: returns the sample count; *audio -> float[count]. */
 SDRPP_API int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int vfo, const float** audio);
+/* Stereo demodulators (wfm = 1): left and right channel rows of the last waited block (dsp::stereo_t de-interleaved);
+ * for mono demodulators *right = *left. Returns the sample count. */
+SDRPP_API int sdrpp_cuda_vfo_audio_stereo(sdrpp_cuda_frontend* fe, int vfo, const float** left, const float** right);
 
 /* Radio IF chain between the VFO output and the demodulator front end: the order is the radio
  * module's, NoiseBlanker -> Squelch -> FMIF (decoder_modules/radio/src/radio_module.h:73-78). With a block enabled the VFO's

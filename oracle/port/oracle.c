@@ -1032,6 +1032,152 @@ API void orc_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandw
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* dsp::demod::BroadcastFM (demod/broadcast_fm.h), the WFM stereo decoder; RDS output off */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double deviation, samplerate; int stereo, lowPass;
+    orc_quad* demod;
+    int np, na, delay;
+    cf32* ptaps; float* ataps;
+    float pll_alpha, pll_beta, pll_phase, pll_freq, pll_init_freq, pll_min, pll_max;
+    float* pbuf; float* dbuf; float* lbuf; float* rbuf;   /* [hist | block] buffers, grown on demand */
+    int cap;
+} orc_wfm;
+static double nuttall_d(double n, double N) {
+    static const double c[4] = { 0.355768, 0.487396, 0.144232, 0.012604 };
+    return orc_cosine(n, N, c, 4);
+}
+/* taps::bandPass<complex_t>(bandStart, bandStop, transWidth, sampleRate, oddTapCount): taps/band_pass.h:10-25, windowed_sinc.h:9-29 */
+static cf32* bandpass_complex(double bandStart, double bandStop, double transWidth, double sampleRate, int odd, int* count_out) {
+    float offsetOmega = (float)(2.0 * ORC_PI * (((bandStart + bandStop) / 2.0) / sampleRate));
+    int count = (int)(3.8 * sampleRate / transWidth), i;
+    double omega = 2.0 * ORC_PI * (((bandStop - bandStart) / 2.0) / sampleRate), half, corr;
+    cf32* taps;
+    if (odd && !(count % 2)) count++;
+    half = (double)count / 2.0; corr = 1.0 * omega / ORC_PI;
+    taps = (cf32*)malloc(sizeof(cf32) * (size_t)count);
+    for (i = 0; i < count; i++) {
+        double t = (double)i - half + 0.5, x = t * omega, n = t - half;
+        cf32 cplx, w, r;
+        float wn = (float)nuttall_d(n, (double)count), ph = -offsetOmega * (float)n;
+        cplx.re = (float)((x == 0.0) ? 1.0 : (sin(x) / x)); cplx.im = 0.0f;
+        w.re = cosf(ph) * wn; w.im = sinf(ph) * wn;
+        r.re = (cplx.re * w.re) - (cplx.im * w.im); r.im = (cplx.im * w.re) + (cplx.re * w.im);
+        taps[i].re = r.re * (float)corr; taps[i].im = r.im * (float)corr;
+    }
+    *count_out = count;
+    return taps;
+}
+API orc_wfm* orc_wfm_create(double deviation, double samplerate, int stereo, int lowPass) {
+    orc_wfm* w = (orc_wfm*)calloc(1, sizeof(orc_wfm));
+    float bw = (float)(25000.0 / samplerate), damp = (float)(sqrt(2.0) / 2.0), den;
+    w->deviation = deviation; w->samplerate = samplerate; w->stereo = stereo; w->lowPass = lowPass;
+    w->demod = orc_quadrature_create(deviation, samplerate);
+    w->ptaps = bandpass_complex(18750.0, 19250.0, 3000.0, samplerate, 1, &w->np);
+    w->na = orc_lowpass_taps(15000.0, 4000.0, samplerate, NULL, 0);
+    w->ataps = (float*)malloc(sizeof(float) * (size_t)w->na);
+    orc_lowpass_taps(15000.0, 4000.0, samplerate, w->ataps, w->na);
+    w->delay = ((w->np - 1) / 2) + 1;
+    den = (float)(1.0 + 2.0 * damp * bw + bw * bw);          /* PhaseControlLoop<float>::criticallyDamped */
+    w->pll_alpha = (4 * damp * bw) / den; w->pll_beta = (4 * bw * bw) / den;
+    w->pll_init_freq = (float)(2.0 * ORC_PI * (19000.0 / samplerate));
+    w->pll_min = (float)(2.0 * ORC_PI * (18750.0 / samplerate)); w->pll_max = (float)(2.0 * ORC_PI * (19250.0 / samplerate));
+    w->pll_phase = 0.0f; w->pll_freq = w->pll_init_freq;
+    return w;
+}
+API void orc_wfm_taps(const orc_wfm* w, int* n, float* pilot, int pcap, float* audio, int acap) {
+    n[0] = w->np; n[1] = w->na;
+    if (pilot) memcpy(pilot, w->ptaps, sizeof(cf32) * (size_t)(w->np < pcap ? w->np : pcap));
+    if (audio) memcpy(audio, w->ataps, sizeof(float) * (size_t)(w->na < acap ? w->na : acap));
+}
+static void wfm_reserve(orc_wfm* w, int n) {
+    if (n <= w->cap) return;
+    {
+        float* nb[4]; int hist[4], i;
+        float** old[4];
+        old[0] = &w->pbuf; old[1] = &w->dbuf; old[2] = &w->lbuf; old[3] = &w->rbuf;
+        hist[0] = w->np - 1; hist[1] = w->delay; hist[2] = w->na - 1; hist[3] = w->na - 1;
+        for (i = 0; i < 4; i++) {
+            nb[i] = (float*)calloc((size_t)(hist[i] + n + 16), sizeof(float));
+            if (*old[i]) { memcpy(nb[i], *old[i], sizeof(float) * (size_t)hist[i]); free(*old[i]); }
+            *old[i] = nb[i];
+        }
+        w->cap = n;
+    }
+}
+static void ffir_inplace(float* buf, int hist, int n, const float* taps, int nt, float* out) {
+    int i, k;                                  /* FIR<float,float>::process, fir.h:62-83; volk_32f_x2_dot_prod_32f generic */
+    for (i = 0; i < n; i++) { ORC_ACC_T acc = 0; for (k = 0; k < nt; k++) acc += (ORC_ACC_T)buf[i + k] * (ORC_ACC_T)taps[k]; out[i] = (float)acc; }
+    memmove(buf, buf + n, sizeof(float) * (size_t)hist);
+}
+/* BroadcastFM::process, broadcast_fm.h:147-214; out = interleaved stereo_t (l, r) */
+API int orc_wfm_process(orc_wfm* w, int count, const cf32* in, float* out) {
+    const float PI = 3.1415926535f;            /* FL_M_PI */
+    float* mpx = (float*)malloc(sizeof(float) * (size_t)(count + 1));
+    int i, k;
+    orc_quadrature_process(w->demod, count, in, mpx);
+    wfm_reserve(w, count);
+    if (w->stereo) {
+        cf32* pil = (cf32*)malloc(sizeof(cf32) * (size_t)(count + 1));
+        float* l = w->lbuf + (w->na - 1); float* r = w->rbuf + (w->na - 1);
+        memcpy(w->pbuf + (w->np - 1), mpx, sizeof(float) * (size_t)count);
+        for (i = 0; i < count; i++) {          /* pilotFir on rtoc's (mpx, 0): volk_32fc_x2_dot_prod_32fc generic */
+            ORC_ACC_T re = 0, im = 0;
+            for (k = 0; k < w->np; k++) {
+                const ORC_ACC_T ar = w->pbuf[i + k], ai = 0.0f, br = w->ptaps[k].re, bi = w->ptaps[k].im;
+                re += ar * br - ai * bi; im += ar * bi + ai * br;
+            }
+            pil[i].re = (float)re; pil[i].im = (float)im;
+        }
+        memmove(w->pbuf, w->pbuf + count, sizeof(float) * (size_t)(w->np - 1));
+        memcpy(w->dbuf + w->delay, mpx, sizeof(float) * (size_t)count);   /* lprDelay / lmrDelay: the same delayed mpx */
+        for (i = 0; i < count; i++) {
+            cf32 vco, c, m1, m2; float err, d = w->dbuf[i], lmr;
+            vco.re = cosf(w->pll_phase); vco.im = sinf(w->pll_phase);                     /* loop/pll.h:66-72 */
+            err = atan2f(pil[i].im, pil[i].re) - w->pll_phase;
+            if (err > PI) err -= 2.0f * PI; else if (err <= -PI) err += 2.0f * PI;      /* math/normalize_phase.h */
+            w->pll_freq += w->pll_beta * err;                                             /* phase_control_loop.h:58-66 */
+            if (w->pll_freq > w->pll_max) w->pll_freq = w->pll_max; else if (w->pll_freq < w->pll_min) w->pll_freq = w->pll_min;
+            w->pll_phase += w->pll_freq + (w->pll_alpha * err);
+            while (w->pll_phase > PI) w->pll_phase -= (PI - (-PI));
+            while (w->pll_phase < -PI) w->pll_phase += (PI - (-PI));
+            c.re = vco.re; c.im = -vco.im;                                                /* math/conjugate.h */
+            m1.re = d * c.re - 0.0f * c.im; m1.im = d * c.im + 0.0f * c.re;               /* volk_32fc_x2_multiply_32fc, twice */
+            m2.re = m1.re * c.re - m1.im * c.im;
+            lmr = m2.re * 2.0f;
+            l[i] = d + lmr; r[i] = d - lmr;
+        }
+        memmove(w->dbuf, w->dbuf + count, sizeof(float) * (size_t)w->delay);
+        if (w->lowPass) {
+            float* tl = (float*)malloc(sizeof(float) * (size_t)(count + 1)); float* tr = (float*)malloc(sizeof(float) * (size_t)(count + 1));
+            ffir_inplace(w->lbuf, w->na - 1, count, w->ataps, w->na, tl);
+            ffir_inplace(w->rbuf, w->na - 1, count, w->ataps, w->na, tr);
+            for (i = 0; i < count; i++) { out[2 * i] = tl[i]; out[2 * i + 1] = tr[i]; }
+            free(tl); free(tr);
+        } else {
+            for (i = 0; i < count; i++) { out[2 * i] = l[i]; out[2 * i + 1] = r[i]; }
+        }
+        free(pil);
+    } else {
+        if (w->lowPass) {
+            float* t = (float*)malloc(sizeof(float) * (size_t)(count + 1));
+            memcpy(w->lbuf + (w->na - 1), mpx, sizeof(float) * (size_t)count);
+            ffir_inplace(w->lbuf, w->na - 1, count, w->ataps, w->na, t);
+            for (i = 0; i < count; i++) { out[2 * i] = t[i]; out[2 * i + 1] = t[i]; }
+            free(t);
+        } else {
+            for (i = 0; i < count; i++) { out[2 * i] = mpx[i]; out[2 * i + 1] = mpx[i]; }
+        }
+    }
+    free(mpx);
+    return count;
+}
+API void orc_wfm_destroy(orc_wfm* w) {
+    if (!w) return;
+    orc_quadrature_destroy(w->demod); free(w->ptaps); free(w->ataps); free(w->pbuf); free(w->dbuf); free(w->lbuf); free(w->rbuf); free(w);
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* level / SNR read-out and the waterfall's per-line display state              */
 /* ------------------------------------------------------------------------------------------ */
 /* WaterFall::calculateVFOSignalInfo, gui/widgets/waterfall.cpp:563-603 (restated: the widget cannot be compiled here) */

@@ -224,6 +224,30 @@ class _Base:
     def ssb_full(self, mode, bw, sr, agc_enabled, attack, decay):
         return self._post_obj(self._f("ssbfull_create", _vp, _i, _d, _d, _i, _d, _d)(mode, bw, sr, int(agc_enabled), attack, decay), "ssbfull")
 
+    def wfm(self, deviation, sr, stereo=True, low_pass=True):
+        """dsp::demod::BroadcastFM (RDS output off): process(iq) -> interleaved (l, r) floats, 2 per input sample."""
+        lib, pre = self.lib, self.prefix
+        h = self._f("wfm_create", _vp, _d, _d, _i, _i)(deviation, sr, int(stereo), int(low_pass))
+        o = _Obj(lib, f"{pre}_wfm", h, out_dtype=np.float32)
+        base = self
+
+        def process(x, out_cap=None):
+            x = _c64(x)
+            out = np.zeros(2 * len(x) + 16, dtype=np.float32)
+            fn = getattr(lib, f"{pre}_wfm_process"); fn.restype = _i; fn.argtypes = [_vp, _i, _vp, _vp]
+            n = fn(o.h, len(x), _ptr(x), _ptr(out))
+            return out[:2 * n].reshape(n, 2).copy()
+        o.process = process
+
+        def taps():
+            n = (_i * 2)()
+            base._f("wfm_taps", None, _vp, _vp, _vp, _i, _vp, _i)(o.h, n, None, 0, None, 0)
+            p, a = np.zeros(2 * n[0], np.float32), np.zeros(n[1], np.float32)
+            base._f("wfm_taps", None, _vp, _vp, _vp, _i, _vp, _i)(o.h, n, _ptr(p), n[0], _ptr(a), n[1])
+            return p.view(np.complex64), a
+        o.taps = taps
+        return o
+
     def demod(self, kind, bw, sr, ideal_nco=False):
         """Demod front end object for a VFO output stream (kind = DEMOD_*), or None."""
         if kind == DEMOD_QUAD:

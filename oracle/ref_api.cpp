@@ -27,6 +27,7 @@
 #include <dsp/demod/fm.h>
 #include <dsp/demod/am.h>
 #include <dsp/demod/ssb.h>
+#include <dsp/demod/broadcast_fm.h>
 #include <dsp/compression/sample_stream_compressor.h>
 #include <dsp/noise_reduction/noise_blanker.h>
 #include <dsp/noise_reduction/squelch.h>
@@ -519,6 +520,31 @@ API void* ref_ssbfull_create(int mode, double bandwidth, double samplerate, int 
 }
 API int ref_ssbfull_process(void* h, int count, const complex_t* in, float* out) { return ((dsp::demod::SSB<float>*)h)->process(count, in, out); }
 API void ref_ssbfull_destroy(void* h) { delete (dsp::demod::SSB<float>*)h; }
+
+// dsp::demod::BroadcastFM (dsp/demod/broadcast_fm.h): quadrature demod -> [19 kHz pilot band-pass -> PLL -> L-R down-conversion
+// -> L/R matrix] -> [15 kHz low-pass] -> interleaved stereo. out: 2*count floats (l, r, l, r ...). RDS output off.
+struct WfmPeek : dsp::demod::BroadcastFM {
+    using Base = dsp::demod::BroadcastFM;
+    using Base::pilotFirTaps; using Base::audioFirTaps;
+};
+API void* ref_wfm_create(double deviation, double samplerate, int stereo, int lowPass) {
+    auto* d = new dsp::demod::BroadcastFM();
+    d->init(NULL, deviation, samplerate, stereo != 0, lowPass != 0, false);
+    d->reset();
+    return d;
+}
+API int ref_wfm_process(void* h, int count, complex_t* in, float* out) {
+    int rdsCount = 0;
+    return ((dsp::demod::BroadcastFM*)h)->process(count, in, (dsp::stereo_t*)out, rdsCount, NULL);
+}
+// pilot band-pass taps (complex, interleaved) and audio low-pass taps; returns the two tap counts through n[0], n[1]
+API void ref_wfm_taps(void* h, int* n, float* pilot, int pcap, float* audio, int acap) {
+    WfmPeek* w = static_cast<WfmPeek*>((dsp::demod::BroadcastFM*)h);
+    n[0] = (int)w->pilotFirTaps.size; n[1] = (int)w->audioFirTaps.size;
+    if (pilot) memcpy(pilot, w->pilotFirTaps.taps, sizeof(complex_t) * std::min<int>(n[0], pcap));
+    if (audio) memcpy(audio, w->audioFirTaps.taps, sizeof(float) * std::min<int>(n[1], acap));
+}
+API void ref_wfm_destroy(void* h) { delete (dsp::demod::BroadcastFM*)h; }
 
 API const char* ref_build_info() {
 #ifdef __FAST_MATH__

@@ -1179,6 +1179,103 @@ __device__ __forceinline__ void post_fir(float* work, int n, const float* __rest
     for (int j = threadIdx.x; j < hist; j += kPostThreads, c++) work[j - hist] = keep[c];
 }
 
+// dsp::demod::BroadcastFM::process (demod/broadcast_fm.h:147-214) behind the quadrature front end, RDS output off.
+// mpx = the discriminator output. Stereo: the 19 kHz pilot is isolated by a complex band-pass FIR (taps::bandPass<complex_t>,
+// applied to (mpx, 0)), a PLL (loop/pll.h:66-72 over loop/phase_control_loop.h:58-66: sequential, one thread, the
+// reference's operation order) locks a VCO to it, the mpx delayed by the filter's group delay is multiplied twice by
+// conj(vco) -- down-converting the 38 kHz L-R subcarrier -- doubled, and L = (L+R) + (L-R), R = (L+R) - (L-R); both then
+// go through the 15 kHz low-pass when enabled. Mono: the low-pass on mpx, copied to both channels.
+// State (global, per VFO): [0] PLL phase [1] PLL freq .. [16] pilot (2 cap) | vco (2 cap) | pilot-FIR input [Tp-1 hist | cap] |
+// delay line [delay | cap] | L [Ta-1 hist | cap] | R [Ta-1 hist | cap].
+__device__ __noinline__ void post_wfm(const PostDev& pd, int n, const float* __restrict__ dm, float* __restrict__ out_l, float* __restrict__ out_r,
+                                      float* staps) {
+    const int tid = threadIdx.x;
+    const bool stereo = (pd.mode & 1) != 0, lowpass = (pd.mode & 2) != 0;
+    const int Tp = pd.ntaps, Ta = pd.ntaps2, delay = pd.delay, cap = pd.cap;
+    float* st = pd.state;
+    float2* pil = reinterpret_cast<float2*>(st + 16);   // [cap] pilot filter output
+    float2* vco = pil + cap;                            // [cap] PLL output
+    float* pbuf = st + 16 + 4 * cap;             // [Tp-1 | cap]
+    float* dbuf = pbuf + (Tp - 1) + cap;         // [delay | cap]
+    float* lbuf = dbuf + delay + cap;            // [Ta-1 | cap]
+    float* rbuf = lbuf + (Ta - 1) + cap;         // [Ta-1 | cap]
+    for (int i = tid; i < Ta; i += kPostThreads) staps[i] = pd.taps2[i];
+    if (!stereo) {
+        // raw MPX to both channels, through alFir when the low-pass is on (broadcast_fm.h:203-209)
+        if (lowpass) {
+            for (int i = tid; i < n; i += kPostThreads) lbuf[(Ta - 1) + i] = dm[i];
+            __syncthreads();
+            post_fir(lbuf + (Ta - 1), n, staps, Ta, out_l);
+            __syncthreads();
+            for (int i = tid; i < n; i += kPostThreads) out_r[i] = out_l[i];
+        } else {
+            for (int i = tid; i < n; i += kPostThreads) { out_l[i] = dm[i]; out_r[i] = dm[i]; }
+        }
+        return;
+    }
+    for (int i = tid; i < n; i += kPostThreads) { const float v = dm[i]; pbuf[(Tp - 1) + i] = v; dbuf[delay + i] = v; }
+    __syncthreads();
+    // pilot band-pass: FIR<complex_t, complex_t> on (mpx, 0) -- volk_32fc_x2_dot_prod_32fc with a zero imaginary input
+    const float2* __restrict__ ptaps = reinterpret_cast<const float2*>(pd.taps);
+    for (int i = tid; i < n; i += kPostThreads) {
+        float re = 0.0f, im = 0.0f;
+        for (int k = 0; k < Tp; k++) { const float v = pbuf[i + k]; const float2 t = __ldg(ptaps + k); re = fmaf(v, t.x, re); im = fmaf(v, t.y, im); }
+        pil[i] = make_float2(re, im);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // loop::PLL::process: out = phasor(phase); advance(normalizePhase(in.phase() - phase))
+        constexpr float PI = 3.1415926535f;      // FL_M_PI (math/constants.h)
+        const float pdelta = __fsub_rn(PI, -PI);
+        float phase = st[0], freq = st[1];
+        for (int i = 0; i < n; i++) {
+            vco[i] = make_float2(cosf(phase), sinf(phase));
+            const float2 p = pil[i];
+            float err = __fsub_rn(atan2f(p.y, p.x), phase);
+            if (err > PI) err = __fsub_rn(err, __fmul_rn(2.0f, PI));
+            else if (err <= -PI) err = __fadd_rn(err, __fmul_rn(2.0f, PI));
+            freq = __fadd_rn(freq, __fmul_rn(pd.pll_beta, err));
+            if (freq > pd.pll_max_freq) freq = pd.pll_max_freq; else if (freq < pd.pll_min_freq) freq = pd.pll_min_freq;
+            phase = __fadd_rn(phase, __fadd_rn(freq, __fmul_rn(pd.pll_alpha, err)));
+            while (phase > PI) phase = __fsub_rn(phase, pdelta);
+            while (phase < -PI) phase = __fadd_rn(phase, pdelta);
+        }
+        st[0] = phase; st[1] = freq;
+    }
+    __syncthreads();
+    // lmr = Re((d, 0) * conj(vco) * conj(vco)) * 2 (two volk_32fc_x2_multiply_32fc, ComplexToReal, x2); L = d + lmr, R = d - lmr
+    for (int i = tid; i < n; i += kPostThreads) {
+        const float d = dbuf[i];
+        const float2 c = make_float2(vco[i].x, -vco[i].y);
+        const float m1r = __fsub_rn(__fmul_rn(d, c.x), __fmul_rn(0.0f, c.y)), m1i = __fadd_rn(__fmul_rn(d, c.y), __fmul_rn(0.0f, c.x));
+        const float m2r = __fsub_rn(__fmul_rn(m1r, c.x), __fmul_rn(m1i, c.y));
+        const float lmr = __fmul_rn(m2r, 2.0f);
+        const float l = __fadd_rn(d, lmr), r = __fsub_rn(d, lmr);
+        if (lowpass) { lbuf[(Ta - 1) + i] = l; rbuf[(Ta - 1) + i] = r; } else { out_l[i] = l; out_r[i] = r; }
+    }
+    __syncthreads();
+    if (lowpass) {
+        post_fir(lbuf + (Ta - 1), n, staps, Ta, out_l);
+        __syncthreads();
+        post_fir(rbuf + (Ta - 1), n, staps, Ta, out_r);
+        __syncthreads();
+    }
+    // carry the pilot filter's input history and the delay line (fir.h:80, math/delay.h:52-61)
+    {
+        float keep[(2048 + kPostThreads - 1) / kPostThreads];
+        int c = 0;
+        for (int j = tid; j < Tp - 1; j += kPostThreads, c++) keep[c] = pbuf[n + j];
+        __syncthreads();
+        c = 0;
+        for (int j = tid; j < Tp - 1; j += kPostThreads, c++) pbuf[j] = keep[c];
+        c = 0;
+        for (int j = tid; j < delay; j += kPostThreads, c++) keep[c] = dbuf[n + j];
+        __syncthreads();
+        c = 0;
+        for (int j = tid; j < delay; j += kPostThreads, c++) dbuf[j] = keep[c];
+    }
+}
+
 __global__ void __launch_bounds__(kPostThreads)
 post_kernel(const __grid_constant__ PostArgs a) {
     __shared__ float staps[kPostTapFloats];
@@ -1196,7 +1293,9 @@ post_kernel(const __grid_constant__ PostArgs a) {
     const AgcCoef c{ pd.attack, pd.inv_attack, pd.decay, pd.inv_decay, pd.set_point, pd.max_gain, pd.max_out };
     for (int i = tid; i < pd.ntaps; i += kPostThreads) staps[i] = pd.taps[i];
 
-    if (pd.kind == POST_FM) {
+    if (pd.kind == POST_WFM) {
+        post_wfm(pd, n, dm, out, a.arena_audio_r + pd.out_off, staps);
+    } else if (pd.kind == POST_FM) {
         if (pd.ntaps > 0) {
             for (int i = tid; i < n; i += kPostThreads) work[i] = dm[i];
             __syncthreads();

@@ -210,6 +210,41 @@ bool zoom_indices(double viewOffset, double viewBandwidth, double wholeBandwidth
     return true;
 }
 
+// dsp::taps::bandPass<complex_t>(bandStart, bandStop, transWidth, sampleRate, oddTapCount) (taps/band_pass.h:10-25 over
+// taps/windowed_sinc.h:9-29), operation for operation: the sinc in double, the window = phasor(-offsetOmega * (float)n)
+// (cosf / sinf of a float) times the Nuttall window cast to float, the correction factor cast to float.
+std::vector<float> design_bandpass_complex(double bandStart, double bandStop, double transWidth, double sampleRate, bool oddTapCount) {
+    const float offsetOmega = (float)(2.0 * kPi * (((bandStart + bandStop) / 2.0) / sampleRate));
+    int count = (int)(3.8 * sampleRate / transWidth);
+    if (oddTapCount && !(count % 2)) count++;
+    const double omega = 2.0 * kPi * (((bandStop - bandStart) / 2.0) / sampleRate);
+    const double half = (double)count / 2.0;
+    const double corr = 1.0 * omega / kPi;
+    std::vector<float> taps((size_t)2 * (size_t)std::max(count, 0));
+    for (int i = 0; i < count; i++) {
+        const double t = (double)i - half + 0.5;
+        const double x = t * omega;
+        const float sc = (float)((x == 0.0) ? 1.0 : (sin(x) / x));
+        const double n = t - half;
+        const float ph = -offsetOmega * (float)n;
+        const float wn = (float)window_nuttall(n, (double)count);
+        const float wre = cosf(ph) * wn, wim = sinf(ph) * wn;          // complex_t * double: each part times (float)b
+        const float re = (sc * wre) - (0.0f * wim), im = (0.0f * wre) + (sc * wim); // complex_t * complex_t, types.h:23-25
+        taps[2 * (size_t)i] = re * (float)corr;
+        taps[2 * (size_t)i + 1] = im * (float)corr;
+    }
+    return taps;
+}
+
+// PhaseControlLoop<float>::criticallyDamped (loop/phase_control_loop.h:31-36): the float T makes every intermediate a float
+// only where the reference's expression does (sqrt(2.0)/2.0 is a double rounded into the float dampningFactor).
+void pll_critically_damped(float bandwidth, float* alpha, float* beta) {
+    const float dampningFactor = (float)(sqrt(2.0) / 2.0);
+    const float denominator = (float)(1.0 + 2.0 * dampningFactor * bandwidth + bandwidth * bandwidth);
+    *alpha = (4 * dampningFactor * bandwidth) / denominator;
+    *beta = (4 * bandwidth * bandwidth) / denominator;
+}
+
 void signal_info_bins(double centerOffset, double bandwidth, double wholeBandwidth, int rawFFTSize, int out[4]) {
     // gui/widgets/waterfall.cpp:567-574, operation for operation (double arithmetic, truncation to int, clamp to [0, size])
     const double f[4] = { centerOffset - bandwidth, centerOffset - (bandwidth / 2.0), centerOffset + (bandwidth / 2.0), centerOffset + bandwidth };

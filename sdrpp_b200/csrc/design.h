@@ -50,6 +50,10 @@ void reshape_params(double sampleRate, int size, double rate, int* skip, int* nz
 // idx has outSize+1 entries; pixel i covers bins [idx[i], max(idx[i]+1, idx[i+1])) when ranged, bin idx[i] otherwise.
 bool zoom_indices(double viewOffset, double viewBandwidth, double wholeBandwidth, int fftSize, int outSize, std::vector<int>* idx);
 
+// dsp::taps::bandPass<complex_t> (taps/band_pass.h): interleaved (re, im) taps. PhaseControlLoop<float>::criticallyDamped.
+std::vector<float> design_bandpass_complex(double bandStart, double bandStop, double transWidth, double sampleRate, bool oddTapCount);
+void pll_critically_damped(float bandwidth, float* alpha, float* beta);
+
 // Bin ranges of WaterFall::calculateVFOSignalInfo (gui/widgets/waterfall.cpp:567-574): out = (minSide, min, max, maxSide).
 void signal_info_bins(double centerOffset, double bandwidth, double wholeBandwidth, int rawFFTSize, int out[4]);
 

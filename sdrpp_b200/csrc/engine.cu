@@ -223,6 +223,10 @@ struct Vfo {
     float* post_state = nullptr;   // device: scalars | FIR history | work area
     float* post_taps = nullptr;    // device
     int post_ntaps = 0, post_hist_pad = 0;
+    // BroadcastFM (POST_WFM): pilot band-pass (complex) in post_taps, audio low-pass in post_taps2
+    float* post_taps2 = nullptr;
+    int post_ntaps2 = 0, post_delay = 0, post_cap = 0;
+    float pll_alpha = 0, pll_beta = 0, pll_min = 0, pll_max = 0;
     // radio IF chain: device record of IF_FLOATS floats, null until first configured
     float* if_state = nullptr;
     // level / SNR read-out on every spectrum row: slot in the signal-info table, -1 = off
@@ -252,6 +256,8 @@ struct ResultSet {
     sdrpp_cf32* iq = nullptr;
     float* demod = nullptr;
     float* audio = nullptr;
+    float* audio_r = nullptr;     // right channel of stereo demodulators
+    std::vector<char> stereo;     // per VFO id: stereo demodulator at submit
     float* rows = nullptr;
     float* zoom = nullptr;
     float* hold = nullptr;        // peak-hold row after this block (zoom_out floats)
@@ -346,7 +352,9 @@ struct sdrpp_cuda_frontend {
     bool layout_dirty = true;
     VfoDev* d_vfos = nullptr; int d_vfos_cap = 0;
     PostDev* d_post = nullptr; int post_active = 0; // per-VFO post-detector records (same indexing as d_vfos)
-    float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; float* d_arena_audio = nullptr; size_t arena_cap = 0, arena_used = 0;
+    float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; float* d_arena_audio = nullptr; float* d_arena_audio_r = nullptr;
+    size_t arena_cap = 0, arena_used = 0;
+    int post_stereo = 0;   // VFOs with a stereo demodulator (POST_WFM): the right-channel arena is copied back too
 
     // results
     ResultSet rs[kSets];
@@ -504,6 +512,7 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
     std::vector<VfoDev> h((size_t)std::max(total, 1));
     std::vector<PostDev> hp((size_t)std::max(total, 1));
     fe->post_active = 0;
+    fe->post_stereo = 0;
     for (Group& g : fe->groups) {
         for (size_t i = 0; i < g.members.size(); i++) {
             Vfo& v = fe->vfos[(size_t)g.members[i]];
@@ -516,8 +525,13 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
             PostDev& pd = hp[(size_t)v.dev_index];
             pd = PostDev{};
             if (v.post.enabled && v.post_state) {
-                pd.kind = v.demod == SDRPP_DEMOD_QUADRATURE ? POST_FM : v.demod == SDRPP_DEMOD_AM ? POST_AM : POST_SSB;
+                pd.kind = v.demod == SDRPP_DEMOD_QUADRATURE ? (v.post.wfm ? POST_WFM : POST_FM) : v.demod == SDRPP_DEMOD_AM ? POST_AM : POST_SSB;
                 pd.mode = pd.kind == POST_FM ? (v.post.fm_lowpass != 0) : pd.kind == POST_AM ? v.post.am_agc_mode : (v.post.ssb_agc != 0);
+                if (pd.kind == POST_WFM) {
+                    pd.mode = (v.post.wfm_stereo ? 1 : 0) | (v.post.fm_lowpass ? 2 : 0);
+                    pd.taps2 = v.post_taps2; pd.ntaps2 = v.post_ntaps2; pd.delay = v.post_delay; pd.cap = v.post_cap;
+                    pd.pll_alpha = v.pll_alpha; pd.pll_beta = v.pll_beta; pd.pll_min_freq = v.pll_min; pd.pll_max_freq = v.pll_max;
+                }
                 pd.ntaps = v.post_ntaps; pd.hist_pad = v.post_hist_pad; pd.taps = v.post_taps; pd.state = v.post_state;
                 pd.out_off = v.out_off;
                 // AGC::init(NULL, 1.0, attack, decay, 10e6, 10.0, INFINITY) (am.h:32-33, ssb.h:27); coefficients as floats (agc.h:22-33)
@@ -525,6 +539,7 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
                 pd.decay = (float)v.post.agc_decay; pd.inv_decay = 1.0f - pd.decay;
                 pd.dc_rate = (float)v.post.dc_block_rate; pd.set_point = 1.0f; pd.max_gain = (float)10e6; pd.max_out = 10.0f;
                 fe->post_active++;
+                if (pd.kind == POST_WFM) fe->post_stereo++;
             }
         }
         if (g.g_dirty) g.tc_dirty = true;
@@ -555,12 +570,14 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
         if (fe->d_arena_iq) cudaFree(fe->d_arena_iq);
         if (fe->d_arena_demod) cudaFree(fe->d_arena_demod);
-        if (fe->d_arena_audio) cudaFree(fe->d_arena_audio);
+        if (fe->d_arena_audio) cudaFree(fe->d_arena_audio); cudaFree(fe->d_arena_audio_r);
+        if (fe->d_arena_audio_r) cudaFree(fe->d_arena_audio_r);
         fe->arena_cap = arena + arena / 2 + 1024;
         // one result arena per result set: the device-to-host copy of block i runs beside the tail of block i+1
         FE_TRY(fe, dev_alloc(&fe->d_arena_iq, kSets * fe->arena_cap));
         FE_TRY(fe, dev_alloc(&fe->d_arena_demod, kSets * fe->arena_cap));
         FE_TRY(fe, dev_alloc(&fe->d_arena_audio, kSets * fe->arena_cap));
+        FE_TRY(fe, dev_alloc(&fe->d_arena_audio_r, kSets * fe->arena_cap));
     }
     if (arena > fe->rs_arena_cap) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
@@ -569,6 +586,8 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
             if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
             if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
             if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
+            if (fe->rs[i].audio_r) cudaFreeHost(fe->rs[i].audio_r);
+            FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].audio_r, fe->arena_cap * sizeof(float)));
             FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].iq, fe->arena_cap * sizeof(sdrpp_cf32)));
             FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].demod, fe->arena_cap * sizeof(float)));
             FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].audio, fe->arena_cap * sizeof(float)));
@@ -673,11 +692,33 @@ static int get_plan(sdrpp_cuda_frontend* fe, double outSR, double bw, std::share
 // (Re)build the post-detector objects of a VFO for its current (demod, outSR, bw): the demodulators' init()
 // (fm.h:25-44, am.h:27-44, ssb.h:21-36). Filter and AGC state start from reset.
 static int apply_post(sdrpp_cuda_frontend* fe, Vfo& v) {
-    cudaFree(v.post_state); cudaFree(v.post_taps);
-    v.post_state = nullptr; v.post_taps = nullptr; v.post_ntaps = 0; v.post_hist_pad = 0;
+    cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.post_taps2);
+    v.post_state = nullptr; v.post_taps = nullptr; v.post_taps2 = nullptr; v.post_ntaps = 0; v.post_hist_pad = 0; v.post_ntaps2 = 0;
     fe->layout_dirty = true;
     if (!v.post.enabled) return SDRPP_OK;
     if (v.demod == SDRPP_DEMOD_NONE) return fail(SDRPP_ERR_STATE, "post-detector stages need a demodulator front end");
+    if (v.demod == SDRPP_DEMOD_QUADRATURE && v.post.wfm) {
+        // BroadcastFM::init (broadcast_fm.h:35-65)
+        const std::vector<float> pilot = design_bandpass_complex(18750.0, 19250.0, 3000.0, v.outSR, true);
+        const std::vector<float> audio = design_lowpass(15000.0, 4000.0, v.outSR);
+        const int Tp = (int)pilot.size() / 2, Ta = (int)audio.size();
+        if (Tp < 3 || Tp > 2048 || Ta < 1 || Ta > 2048) return fail(SDRPP_ERR_ARG, "BroadcastFM: the IF sample rate gives an unusable pilot / audio filter (needs roughly 100 kS/s .. 1.6 MS/s)");
+        v.post_ntaps = Tp; v.post_ntaps2 = Ta; v.post_hist_pad = 0;
+        v.post_delay = ((Tp - 1) / 2) + 1;
+        v.post_cap = v.plan->cap_final + 8;
+        pll_critically_damped((float)(25000.0 / v.outSR), &v.pll_alpha, &v.pll_beta);
+        v.pll_min = (float)(2.0 * kPi * (18750.0 / v.outSR)); v.pll_max = (float)(2.0 * kPi * (19250.0 / v.outSR));
+        const size_t n = 16 + 4 * (size_t)v.post_cap + (size_t)(Tp - 1) + (size_t)v.post_delay + 2 * (size_t)(Ta - 1) + 4 * (size_t)v.post_cap + 16;
+        FE_TRY(fe, dev_alloc(&v.post_state, n));
+        FE_TRY(fe, dev_alloc(&v.post_taps, pilot.size(), false));
+        FE_TRY(fe, upload_sync(v.post_taps, pilot.data(), pilot.size() * sizeof(float)));
+        FE_TRY(fe, dev_alloc(&v.post_taps2, audio.size(), false));
+        FE_TRY(fe, upload_sync(v.post_taps2, audio.data(), audio.size() * sizeof(float)));
+        // PLL::reset: phase = initPhase (0), freq = initFreq = hzToRads(19000, samplerate) as a float
+        float init[2] = { 0.0f, (float)(2.0 * kPi * (19000.0 / v.outSR)) };
+        FE_TRY(fe, upload_sync(v.post_state, init, sizeof(init)));
+        return SDRPP_OK;
+    }
     std::vector<float> taps;
     const bool fm = v.demod == SDRPP_DEMOD_QUADRATURE, am = v.demod == SDRPP_DEMOD_AM;
     if ((fm && v.post.fm_lowpass) || am) {
@@ -1088,6 +1129,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             }
             pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq + (size_t)aset * fe->arena_cap; pa.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
             pa.arena_audio = fe->d_arena_audio + (size_t)aset * fe->arena_cap;
+            pa.arena_audio_r = fe->d_arena_audio_r + (size_t)aset * fe->arena_cap;
             if (any && tail_totals[i] > 0) { FE_TRY(fe, launch_post(pa, tail_totals[i], stl)); fe->launches++; }
         }
     }
@@ -1098,11 +1140,13 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     rs.offs.assign(fe->vfos.size(), 0);
     rs.demods.assign(fe->vfos.size(), 0);
     rs.has_audio.assign(fe->vfos.size(), 0);
+    rs.stereo.assign(fe->vfos.size(), 0);
     for (const Group& g : fe->groups)
         for (int id : g.members) {
             const Vfo& v = fe->vfos[(size_t)id];
             rs.counts[(size_t)id] = g.last_n_final; rs.offs[(size_t)id] = v.out_off; rs.demods[(size_t)id] = v.demod;
             rs.has_audio[(size_t)id] = (v.post.enabled && v.post_state) ? 1 : 0;
+            rs.stereo[(size_t)id] = (v.post.enabled && v.post_state && v.post.wfm && v.demod == SDRPP_DEMOD_QUADRATURE) ? 1 : 0;
         }
     // The copies run on their own stream behind the tail, so the tail of the next block does not queue up behind
     // them; the pinned result set and the arena of this parity are free again once the caller has waited for
@@ -1121,6 +1165,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
         if (fe->post_active > 0)
             FE_TRY(fe, cudaMemcpyAsync(rs.audio, fe->d_arena_audio + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
+        if (fe->post_stereo > 0)
+            FE_TRY(fe, cudaMemcpyAsync(rs.audio_r, fe->d_arena_audio_r + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
     }
     if (!prof) FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_fft[par], 0)); // the block is done when its rows are on the host too
     FE_TRY(fe, cudaEventRecord(rs.done, sd));
@@ -1288,6 +1334,13 @@ int sdrpp_cuda_design_lowpass(double cutoff, double transWidth, double sampleRat
         std::vector<float> t = design_lowpass(cutoff, transWidth, sampleRate);
         memcpy(out, t.data(), sizeof(float) * (size_t)std::min(n, cap));
     }
+    return n;
+}
+int sdrpp_cuda_design_bandpass_complex(double bandStart, double bandStop, double transWidth, double sampleRate, int oddTapCount, float* out, int cap) {
+    if (!(transWidth > 0) || !(sampleRate > 0) || !(bandStop > bandStart)) return fail(SDRPP_ERR_ARG, "bad filter spec");
+    const std::vector<float> t = design_bandpass_complex(bandStart, bandStop, transWidth, sampleRate, oddTapCount != 0);
+    const int n = (int)t.size() / 2;
+    if (out && cap > 0) memcpy(out, t.data(), sizeof(float) * 2 * (size_t)std::min(n, cap));
     return n;
 }
 int sdrpp_cuda_design_resampler(double inSR, double outSR, int* info, float* taps, int cap) {
@@ -1596,7 +1649,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_d2h) cudaStreamSynchronize(fe->st_d2h);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
     if (fe->st_bcast) cudaStreamSynchronize(fe->st_bcast);
-    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.if_state); }
+    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.post_taps2); cudaFree(v.if_state); }
     for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
     for (int i = 0; i < 2; i++) { cudaFree(fe->tc_planes[i].hi); cudaFree(fe->tc_planes[i].lo); cudaFree(fe->tc_planes[i].sinv); }
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
@@ -1605,7 +1658,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     cudaFree(fe->dc_in); cudaFree(fe->dc_state); cudaFree(fe->dc_scratch);
     cudaFree(fe->ring); cudaFree(fe->d_window); cudaFree(fe->d_inter); cudaFree(fe->d_rows);
     cudaFree(fe->d_zoom_idx); cudaFree(fe->d_zoom); cudaFree(fe->d_disp); cudaFree(fe->d_sig_bins); cudaFree(fe->d_sig);
-    cudaFree(fe->d_vfos); cudaFree(fe->d_post); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod); cudaFree(fe->d_arena_audio);
+    cudaFree(fe->d_vfos); cudaFree(fe->d_post); cudaFree(fe->d_arena_iq); cudaFree(fe->d_arena_demod); cudaFree(fe->d_arena_audio); cudaFree(fe->d_arena_audio_r);
     for (int i = 0; i < kSets; i++) {
         if (fe->h_stage[i]) cudaFreeHost(fe->h_stage[i]);
         if (fe->d_raw[i]) cudaFree(fe->d_raw[i]);
@@ -1616,6 +1669,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->rs[i].iq) cudaFreeHost(fe->rs[i].iq);
         if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
         if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
+        if (fe->rs[i].audio_r) cudaFreeHost(fe->rs[i].audio_r);
         if (fe->rs[i].rows) cudaFreeHost(fe->rs[i].rows);
         if (fe->rs[i].zoom) cudaFreeHost(fe->rs[i].zoom);
         if (fe->rs[i].hold) cudaFreeHost(fe->rs[i].hold);
@@ -1763,7 +1817,7 @@ int sdrpp_cuda_vfo_destroy(sdrpp_cuda_frontend* fe, int id) {
     if ((rc = vfo_get(fe, id, &v)) != SDRPP_OK) return rc;
     remove_from_group(fe, id);
     if (v->slab) cudaFree(v->slab);
-    cudaFree(v->post_state); cudaFree(v->post_taps); cudaFree(v->if_state); v->if_state = nullptr;
+    cudaFree(v->post_state); cudaFree(v->post_taps); cudaFree(v->post_taps2); cudaFree(v->if_state); v->if_state = nullptr;
     *v = Vfo();
     return SDRPP_OK;
 }
@@ -2059,6 +2113,17 @@ int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int id, const float** audio) {
     const bool have = (size_t)id < rs.counts.size() && rs.has_audio[(size_t)id];
     if (audio) *audio = (rs.audio && have) ? rs.audio + rs.offs[(size_t)id] : nullptr;
     return have ? rs.counts[(size_t)id] : 0;
+}
+
+int sdrpp_cuda_vfo_audio_stereo(sdrpp_cuda_frontend* fe, int id, const float** left, const float** right) {
+    const float* l = nullptr;
+    const int n = sdrpp_cuda_vfo_audio(fe, id, &l);
+    if (n < 0) return n;
+    const ResultSet& rs = fe->rs[fe->cur];
+    const bool st = (size_t)id < rs.stereo.size() && rs.stereo[(size_t)id] && rs.audio_r && l;
+    if (left) *left = l;
+    if (right) *right = st ? rs.audio_r + rs.offs[(size_t)id] : l;
+    return n;
 }
 
 int sdrpp_cuda_fft_rows(sdrpp_cuda_frontend* fe, const float** rows) {

@@ -205,7 +205,7 @@ bool tail_stage0_wide_supported(int T, int D);
 // Post-detector stages of the three demodulators: FM low-pass (dsp/demod/fm.h:86-103), AM
 // [carrier AGC] -> magnitude -> DC block -> [audio AGC] -> low-pass (dsp/demod/am.h:114-146), SSB AGC
 // (dsp/demod/ssb.h:90-101); dsp::loop::AGC (dsp/loop/agc.h:87-147). One CTA per VFO, after the tail.
-enum { POST_NONE = 0, POST_FM = 1, POST_AM = 2, POST_SSB = 3 };
+enum { POST_NONE = 0, POST_FM = 1, POST_AM = 2, POST_SSB = 3, POST_WFM = 4 };
 struct PostDev {
     int kind;            // POST_*
     int mode;            // FM: 1 = low-pass; AM: AGCMode (0 OFF, 1 CARRIER, 2 AUDIO); SSB: 1 = AGC enabled
@@ -216,6 +216,12 @@ struct PostDev {
     uint32_t out_off;    // offset of this VFO's rows in the output arenas (samples)
     float attack, inv_attack, decay, inv_decay;
     float dc_rate, set_point, max_gain, max_out;
+    // POST_WFM (dsp::demod::BroadcastFM, demod/broadcast_fm.h): mode bit 0 = stereo, bit 1 = low-pass; taps = the 19 kHz pilot
+    // band-pass (complex, interleaved, ntaps of them), taps2 = the 15 kHz audio low-pass (ntaps2); PLL coefficients and limits
+    const float* taps2;
+    int ntaps2, delay, cap;
+    float pll_alpha, pll_beta, pll_min_freq, pll_max_freq;
+    float* out_r;        // right channel rows (arena), indexed like out_off
 };
 struct PostArgs {
     int ngroups;
@@ -224,6 +230,7 @@ struct PostArgs {
     const float2* arena_iq;
     const float* arena_demod;
     float* arena_audio;
+    float* arena_audio_r;        // right channel of stereo demodulators (POST_WFM); mono kinds leave it alone
 };
 cudaError_t launch_post(const PostArgs& a, int total_vfos, cudaStream_t st);
 

@@ -57,3 +57,13 @@ def test_decim_plan_invalid(cuda_lib):
 @pytest.mark.parametrize("sr,n,rate", [(2.4e6, 65536, 15.0), (3.2e6, 131072, 20.0), (20e6, 1048576, 20.0), (122.88e6, 1048576, 122.88e6 / 1048576), (8e6, 1024, 20.0)])
 def test_reshape(cuda_lib, port, sr, n, rate):
     assert cuda_lib.design_reshape(sr, n, rate) == port.reshape_params(sr, n, rate)
+
+
+@pytest.mark.parametrize("sr", [250e3, 240e3, 192e3])
+def test_wfm_pilot_bandpass_bit_exact(cuda_lib, ref, sr):
+    """dsp::taps::bandPass<complex_t>(18750, 19250, 3000, sr, true), the pilot filter of dsp::demod::BroadcastFM."""
+    got = cuda_lib.design_bandpass_complex(18750.0, 19250.0, 3000.0, sr, odd=True)
+    pilot, audio = ref.wfm(75e3, sr).taps()
+    assert len(got) == len(pilot) and len(got) % 2 == 1
+    assert np.array_equal(got.view(np.uint32), pilot.view(np.uint32))
+    assert np.array_equal(cuda_lib.design_lowpass(15000.0, 4000.0, sr), audio)

@@ -3,8 +3,9 @@ dsp::demod::AM<float> carrier/audio AGC + DC blocker + low-pass, dsp::demod::SSB
 
 The stages are checked in isolation: the oracle's complete demodulator is fed the GPU's own VFO output (cf32), so
 the only differences left are those of the stages under test (the VFO itself is gated in test_gpu_channelizer.py).
-The AGC and DC blocker recurrences use the reference's operation order, so their gate is 1e-5 relative RMS; the FM
-branch inherits the discriminator's 2e-4 gate (atan2f implementations differ by ~1 ulp)."""
+Every branch is gated at 1e-5 relative RMS: the AGC and DC blocker recurrences and the discriminator's complex product use
+the reference's operation order (atan2f implementations differ by ~1 ulp, 5e-8 here). The WFM stereo decoder
+(dsp::demod::BroadcastFM, SURVEY 8f rank 4) is checked the same way in all four stereo / low-pass modes."""
 import numpy as np
 import pytest
 
@@ -43,9 +44,9 @@ def run(gpu, vfo, post, blocks, sizes=None):
 
 
 CASES = [
-    ("fm_nfm_lp", (48e3, 12.5e3, 100e3, po.DEMOD_QUAD), dict(fm_lowpass=True), lambda o: o.fm_full(48e3, 12.5e3, True), 2e-4),
-    ("fm_wfm_lp", (250e3, 200e3, -300e3, po.DEMOD_QUAD), dict(fm_lowpass=True), lambda o: o.fm_full(250e3, 200e3, True), 2e-4),
-    ("fm_nolp", (48e3, 12.5e3, 100e3, po.DEMOD_QUAD), dict(fm_lowpass=False), lambda o: o.fm_full(48e3, 12.5e3, False), 2e-4),
+    ("fm_nfm_lp", (48e3, 12.5e3, 100e3, po.DEMOD_QUAD), dict(fm_lowpass=True), lambda o: o.fm_full(48e3, 12.5e3, True), 1e-5),
+    ("fm_wfm_lp", (250e3, 200e3, -300e3, po.DEMOD_QUAD), dict(fm_lowpass=True), lambda o: o.fm_full(250e3, 200e3, True), 1e-5),
+    ("fm_nolp", (48e3, 12.5e3, 100e3, po.DEMOD_QUAD), dict(fm_lowpass=False), lambda o: o.fm_full(48e3, 12.5e3, False), 1e-5),
     ("am_off", (24e3, 12e3, 100e3, po.DEMOD_AM), dict(am_agc_mode=0, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3, agc_gain=3.0),
      lambda o: o.am_full(0, 12e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3, 3.0), 1e-5),
     ("am_carrier", (24e3, 12e3, 100e3, po.DEMOD_AM), dict(am_agc_mode=1, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3),
@@ -53,9 +54,9 @@ CASES = [
     ("am_audio", (24e3, 12e3, 100e3, po.DEMOD_AM), dict(am_agc_mode=2, agc_attack=50 / 24e3, agc_decay=5 / 24e3, dc_block_rate=100 / 24e3),
      lambda o: o.am_full(2, 12e3, 50 / 24e3, 5 / 24e3, 100 / 24e3, 24e3), 1e-5),
     ("usb_agc", (48e3, 2.7e3, 100e3, po.DEMOD_USB), dict(ssb_agc=True, agc_attack=50 / 48e3, agc_decay=5 / 48e3),
-     lambda o: o.ssb_full(0, 2.7e3, 48e3, True, 50 / 48e3, 5 / 48e3), 3e-5),
+     lambda o: o.ssb_full(0, 2.7e3, 48e3, True, 50 / 48e3, 5 / 48e3), 1e-5),
     ("lsb_fixed", (48e3, 2.7e3, 100e3, po.DEMOD_LSB), dict(ssb_agc=False, agc_attack=50 / 48e3, agc_decay=5 / 48e3, agc_gain=2.0),
-     None, 3e-5),
+     None, 1e-5),
 ]
 
 
@@ -130,7 +131,58 @@ def test_post_many_vfos_mixed(gpu, port):
                 got[k].append(fe.vfo_audio(ids[k])); want[k].append(os_[k].process(y))
             with pytest.raises(gpu.SdrppCudaError):
                 fe.vfo_audio(ids[3])
-        for k, tol in ((0, 2e-4), (1, 1e-5), (2, 3e-5)):
+        for k, tol in ((0, 1e-5), (1, 1e-5), (2, 1e-5)):
             g, w = np.concatenate(got[k]), np.concatenate(want[k])
             err = np.sqrt(np.mean((g - w) ** 2)) / max(np.sqrt(np.mean(w ** 2)), 1e-3)
             assert err <= tol, (k, err)
+
+
+def wfm_stream(nblocks, offset, seed):
+    """A stereo FM broadcast signal: L = 1 kHz, R = 2.5 kHz, 19 kHz pilot, L-R on the 38 kHz subcarrier, 75 kHz deviation."""
+    rng = np.random.default_rng(seed)
+    n = nblocks * BLK
+    t = np.arange(n) / IN_SR
+    L, R = 0.5 * np.sin(2 * np.pi * 1000.0 * t), 0.3 * np.sin(2 * np.pi * 2500.0 * t)
+    mpx = 0.45 * (L + R) + 0.45 * (L - R) * np.sin(2 * np.pi * 38000.0 * t) + 0.1 * np.sin(2 * np.pi * 19000.0 * t)
+    ph = 2 * np.pi * ((offset * t) % 1.0) + 2 * np.pi * 75e3 * np.cumsum(mpx) / IN_SR
+    x = 0.5 * np.exp(1j * ph) + 1e-4 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    x = x.astype(np.complex64)
+    return [x[i * BLK:(i + 1) * BLK] for i in range(nblocks)]
+
+
+@pytest.mark.parametrize("out_sr", [250e3, 240e3])
+@pytest.mark.parametrize("stereo,low_pass", [(True, True), (True, False), (False, True), (False, False)])
+def test_wfm_stereo_decoder(gpu, port, report, out_sr, stereo, low_pass):
+    """dsp::demod::BroadcastFM behind a WFM VFO (radio module: bandwidth 150 kHz, deviation = bandwidth / 2): the oracle's
+    decoder applied to the GPU's own VFO output against the GPU's (l, r), <= 1e-5 -- the pilot PLL is a feedback loop over
+    cosf / sinf / atan2f, whose implementations differ by an ulp, and stays inside the gate -- and the two channels separate."""
+    bw = 150e3
+    blocks = wfm_stream(40, -300e3, 27)
+    o = port.wfm(bw / 2.0, out_sr, stereo, low_pass)
+    got, want = [], []
+    with gpu.Frontend(IN_SR, max_block=BLK) as fe:
+        vid = fe.add_vfo(out_sr, bw, -300e3, po.DEMOD_QUAD)
+        fe.set_post(vid, fm_lowpass=low_pass, wfm=True, wfm_stereo=stereo)
+        for b in blocks:
+            fe.process(po.FMT_CF32, b)
+            y, _ = fe.vfo_output(vid)
+            l, r = fe.vfo_audio_stereo(vid)
+            assert len(l) == len(r) == len(y)
+            got.append(np.stack([l, r], axis=1)); want.append(o.process(y))
+    g, w = np.concatenate(got), np.concatenate(want)
+    assert g.shape == w.shape and np.all(np.isfinite(g))
+    s = len(g) // 4                               # past the PLL's lock-in and the filters' start-up
+    err = float(np.sqrt(np.mean((g[s:].astype(np.float64) - w[s:]) ** 2)) / np.sqrt(np.mean(w[s:].astype(np.float64) ** 2)))
+    err0 = float(np.sqrt(np.mean((g[:s].astype(np.float64) - w[:s]) ** 2)) / np.sqrt(np.mean(w[:s].astype(np.float64) ** 2)))
+    report(f"8f-4 BroadcastFM {out_sr/1e3:g}k stereo={int(stereo)} lp={int(low_pass)}", locked=err, lock_in_quarter=err0, gate=1e-5)
+    assert err <= 1e-5, f"rel-RMS {err:.3e}"
+    assert err0 <= 1e-4, f"lock-in: {err0:.3e}"
+    if stereo and low_pass:
+        # channel separation: 1 kHz on the left only, 2.5 kHz on the right only
+        n = len(g) - s
+        sp = np.abs(np.fft.rfft(g[s:] * np.hanning(n)[:, None], axis=0))
+        f = np.fft.rfftfreq(n, 1.0 / out_sr)
+        k1, k2 = int(np.argmin(np.abs(f - 1000.0))), int(np.argmin(np.abs(f - 2500.0)))
+        assert sp[k1, 0] > 30.0 * sp[k1, 1] and sp[k2, 1] > 30.0 * sp[k2, 0]
+    if not stereo:
+        assert np.array_equal(g[:, 0], g[:, 1])

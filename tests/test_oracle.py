@@ -245,3 +245,17 @@ def test_port_matches_golden(port, case):
 
 def test_golden_present():
     assert len(_golden_cases()) >= 8, "tests/golden is empty: run tools/make_golden.py where /root/reference exists"
+
+
+@pytest.mark.parametrize("stereo,low_pass", [(1, 1), (1, 0), (0, 1), (0, 0)])
+def test_port_broadcast_fm_bit_exact_vs_reference(port, ref, stereo, low_pass):
+    """dsp::demod::BroadcastFM (demod/broadcast_fm.h): the C restatement against the reference's own header, block by block."""
+    sr, n, blk = 250e3, 25000, 1250
+    t = np.arange(n) / sr
+    L, R = 0.5 * np.sin(2 * np.pi * 1000 * t), 0.3 * np.sin(2 * np.pi * 2500 * t)
+    mpx = 0.45 * (L + R) + 0.45 * (L - R) * np.sin(2 * np.pi * 38000 * t) + 0.1 * np.sin(2 * np.pi * 19000 * t)
+    x = (0.5 * np.exp(1j * 2 * np.pi * 75e3 * np.cumsum(mpx) / sr)).astype(np.complex64)
+    a, b = port.wfm(75e3, sr, stereo, low_pass), ref.wfm(75e3, sr, stereo, low_pass)
+    for i in range(0, n, blk):
+        ya, yb = a.process(x[i:i + blk]), b.process(x[i:i + blk])
+        assert ya.shape == (blk, 2) and np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
