@@ -36,7 +36,7 @@ def stream(nblocks, offset, seed):
 def rel_rms(a, b):
     a, b = np.asarray(a), np.asarray(b)
     a, b = (a.astype(np.complex128), b.astype(np.complex128)) if np.iscomplexobj(a) or np.iscomplexobj(b) else (a.astype(np.float64), b.astype(np.float64))
-    return np.sqrt(np.sum((a - b) ** 2) / max(np.sum(b ** 2), 1e-300))
+    return float(np.sqrt(np.sum(np.abs(a - b) ** 2) / max(np.sum(np.abs(b) ** 2), 1e-300)))
 
 
 def front_end(port, demod, bw, sr):
