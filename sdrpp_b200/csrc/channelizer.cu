@@ -755,8 +755,8 @@ tail_kernel(const __grid_constant__ TailArgs a) {
 // Same arithmetic (fir.h:62-83, decimating_fir.h:45-68, polyphase_resampler.h:69-99), same slab layout, so the two
 // kernels can alternate block by block. The engine picks this one per group and block (tail_fast_fits).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 256;
-constexpr int kFastMaxSamples = 12288;  // float2 of stage regions a CTA may hold (96 KB)
+constexpr int kFastThreads = 1024;      // the kernel runs when there are fewer VFOs than SMs: one CTA per SM, all of its threads on one VFO
+constexpr int kFastMaxSamples = 20480;  // float2 of stage regions + split-K scratch a CTA may hold (160 KB)
 constexpr int kFastTapFloats = 4096;
 constexpr int kFastOB = 4;              // outputs per thread of a FIR stage (register blocking)
 constexpr int kFastScratch = kFastThreads * kFastOB; // float2: split-K partial sums
@@ -811,7 +811,7 @@ __device__ __forceinline__ float2& fast_at(float2* x, const FastRegion& r, int i
     return r.M > 1 ? x[r.base + (i & (r.M - 1)) * r.qs + (i >> r.lgM)] : x[r.base + i];
 }
 
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, 1)
 tail_fast_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* taps = reinterpret_cast<float*>(tail_smem);                          // [kFastTapFloats]

@@ -390,6 +390,15 @@ namespace sdrpp {
         }                                                                                        \
     } while (0)
 
+// SDRPP_DEBUG_ERR=1: report a CUDA error left behind by an earlier, unchecked runtime call (it would otherwise surface at the
+// next kernel launch's cudaGetLastError and be blamed on that launch)
+static void debug_stale(const char* where) {
+    static const bool on = getenv("SDRPP_DEBUG_ERR") != nullptr;
+    if (!on) return;
+    const cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) fprintf(stderr, "[sdrpp_cuda] stale CUDA error at %s: %s\n", where, cudaGetErrorString(e));
+}
+
 static int fe_check(sdrpp_cuda_frontend* fe) {
     if (!fe) return fail(SDRPP_ERR_ARG, "null front end");
     if (!fe->sticky.empty()) { set_last_error(fe->sticky); return SDRPP_ERR_CUDA; }
@@ -570,7 +579,7 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
         if (fe->d_arena_iq) cudaFree(fe->d_arena_iq);
         if (fe->d_arena_demod) cudaFree(fe->d_arena_demod);
-        if (fe->d_arena_audio) cudaFree(fe->d_arena_audio); cudaFree(fe->d_arena_audio_r);
+        if (fe->d_arena_audio) cudaFree(fe->d_arena_audio);
         if (fe->d_arena_audio_r) cudaFree(fe->d_arena_audio_r);
         fe->arena_cap = arena + arena / 2 + 1024;
         // one result arena per result set: the device-to-host copy of block i runs beside the tail of block i+1
@@ -791,6 +800,7 @@ static void advance_decim(int& offset, int D, int count, int* nout) {
 static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int count, ResultSet& rs, float scale = 1.0f) {
     cudaStream_t st = fe->st;
     const bool prof = fe->profiling;
+    debug_stale("process_block entry");
     if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[0], st));
     // The spectrum is the one reader of the ring that is not ordered on `st`: before block i overwrites ring samples,
     // the spectrum work of block i-2 must be done. Frames of block i-1 may still be in flight; they reach back at most
@@ -908,7 +918,9 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     else { FE_TRY(fe, cudaEventRecord(fe->ev_fft[par], sf)); fe->ev_fft_valid[par] = true; }
 
     // ---- channelizer ----------------------------------------------------------------------------
+    debug_stale("before rebuild_layout");
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
+    debug_stale("after rebuild_layout");
     if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
     int total_vfos_all = 0;
     for (const Group& g : fe->groups) total_vfos_all += (int)g.members.size();
@@ -1693,6 +1705,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
 static int fe_quiesce(sdrpp_cuda_frontend* fe) {
     int rc = fe_check(fe);
     if (rc != SDRPP_OK) return rc;
+    debug_stale("quiesce entry");
     std::lock_guard<std::mutex> api(fe->api_mtx);
     FE_TRY(fe, cudaStreamSynchronize(fe->st_copy));
     FE_TRY(fe, cudaStreamSynchronize(fe->st));
