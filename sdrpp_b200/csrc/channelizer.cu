@@ -345,12 +345,7 @@ static cudaError_t launch_stage1_t(const Stage1Args& a, cudaStream_t st) {
     const size_t tile = (size_t)ROWS * a.D * sizeof(float2);
     const size_t parts = (size_t)W * NP * 32 * sizeof(float2);
     const size_t smem = 128 + parts + (size_t)(a.D / 2) * 32 * 16 + tile;
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stage1_kernel<A, R, W, DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = smem;
-    }
+    if (cudaError_t e = ensure_dynamic_smem((const void*)stage1_kernel<A, R, W, DT>, smem); e != cudaSuccess) return e;
     dim3 grid(ceil_div(a.M, OUT), ceil_div(a.nvfo, 32));
     stage1_kernel<A, R, W, DT><<<grid, W * 32, smem, st>>>(a);
     return cudaGetLastError();
@@ -1000,13 +995,7 @@ cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st)
         need = std::max(need, n);
     }
     const size_t smem = (size_t)kFastTapFloats * sizeof(float) + (size_t)(need + 8) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tail_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(kFastTapFloats * sizeof(float) + (kFastMaxSamples + 8) * sizeof(float2)));
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem((const void*)tail_fast_kernel, kFastTapFloats * sizeof(float) + (kFastMaxSamples + 8) * sizeof(float2)); e != cudaSuccess) return e;
     tail_fast_kernel<<<total_vfos, kFastThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
@@ -1086,12 +1075,7 @@ static cudaError_t launch_wide_t(const TailArgs& a, int total_vfos, int max_out,
     constexpr int lg = D == 2 ? 1 : D == 4 ? 2 : D == 8 ? 3 : 4;
     constexpr int qs = (kWideOut + (kWideMaxTaps >> lg) + 2) | 1;
     const size_t smem = (size_t)(kWideMaxTaps + 16) * sizeof(float) + (size_t)D * qs * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tail_stage0_wide_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem((const void*)tail_stage0_wide_kernel<D>, smem); e != cudaSuccess) return e;
     dim3 grid((unsigned)std::max(1, ceil_div(max_out, kWideOut)), (unsigned)total_vfos);
     tail_stage0_wide_kernel<D><<<grid, kWideThreads, smem, st>>>(a);
     return cudaGetLastError();
@@ -1117,12 +1101,7 @@ cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStrea
 cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {
     if (total_vfos <= 0) return cudaSuccess;
     const size_t smem = (size_t)kTailTapFloats * sizeof(float) + (size_t)(kTailSmemSamples + 512) * sizeof(float2);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem((const void*)tail_kernel, smem); e != cudaSuccess) return e;
     tail_kernel<<<total_vfos, kTailThreads, smem, st>>>(a);
     return cudaGetLastError();
 }

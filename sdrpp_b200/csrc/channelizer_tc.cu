@@ -669,13 +669,7 @@ cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
     if (s1t_smem_bytes(NKH, maxA, nch) > cap) return cudaErrorInvalidValue;
     a.nchunks = nch;
     const size_t smem = s1t_smem_bytes(NKH, maxA, nch);
-    static size_t attr_set[3] = { 0, 0, 0 };
-    if (smem > attr_set[NKH]) {
-        cudaError_t e = NKH == 1 ? cudaFuncSetAttribute(s1t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                                 : cudaFuncSetAttribute(s1t_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set[NKH] = smem;
-    }
+    if (cudaError_t e = ensure_dynamic_smem(NKH == 1 ? (const void*)s1t_kernel<1> : (const void*)s1t_kernel<2>, smem); e != cudaSuccess) return e;
     if (NKH == 1) s1t_kernel<1><<<ctas, kThreads, smem, st>>>(a);
     else s1t_kernel<2><<<ctas, kThreads, smem, st>>>(a);
     return cudaGetLastError();

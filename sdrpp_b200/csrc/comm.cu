@@ -12,10 +12,25 @@
 
 #include <dlfcn.h>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 
 namespace sdrpp {
+
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+    static std::mutex mtx;
+    static std::map<std::pair<const void*, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lck(mtx);
+    size_t& cur = done[std::make_pair(func, dev)];
+    if (bytes <= cur) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 namespace {
 

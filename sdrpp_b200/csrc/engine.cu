@@ -369,6 +369,7 @@ struct sdrpp_cuda_frontend {
                             // tail kernel only (SDRPP_TAIL_MODE=general), 2: low-latency kernel wherever a block fits (=fast)
     int num_sms = 148;
     S1TPlanes tc_planes[2] = {};
+    bool planes_skipped[2] = { false, false }; // a block went by without refreshing the planes (FP32-only mode)
     long long s1t_launches = 0;
 
     // profiling
@@ -929,6 +930,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     // Tensor-core stage 1: refresh the fp16 hi/lo planes of the ring for every first-stage decimation in use
     // (one conversion serves all VFOs and plans of that decimation), then collect the eligible groups per plane set.
     S1TArgs tc_args[2] = {};
+    if (fe->s1_mode != 0 && n > 0) fe->planes_skipped[0] = fe->planes_skipped[1] = true;
     if (fe->s1_mode == 0 && n > 0) {
         for (int pi = 0; pi < 2; pi++) {
             const int D = pi ? 64 : 32;
@@ -960,10 +962,19 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 FE_TRY(fe, dev_alloc(&pl.lo, bytes));
                 FE_TRY(fe, dev_alloc(&pl.sinv, (size_t)ngroups));
                 pl.D = D; pl.group_mask = ngroups - 1; pl.origin = best;
+                pl.valid_from = abs_block;       // nothing before this block has been converted
             } else if (best_cost < cur_cost) {
                 // new origin: the history the next windows reach back into has to be converted again
                 pl.origin = best;
                 split_from = std::max<int64_t>(0, abs_block - 4096);
+                pl.valid_from = std::max(pl.valid_from, split_from);
+            } else if (pl.valid_from > abs_block) {
+                pl.valid_from = abs_block;
+            }
+            if (fe->planes_skipped[pi]) {
+                // blocks went by without a conversion (FP32-only mode): the rows before this block are stale
+                pl.valid_from = std::max(pl.valid_from, abs_block);
+                fe->planes_skipped[pi] = false;
             }
             tc_args[pi].pl = pl;
             FE_TRY(fe, launch_s1t_split(ring, pl, split_from, abs_block + n, st));
@@ -1006,7 +1017,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             // tensor cores when the whole window lies after the group's epoch (history before it reads as zero,
             // which only the FP32 kernel does)
             const int pi = p.s1_D >> 6;
-            if (p.tc_ok && tc_args[pi].pl.hi && nprev > 0 && a.abs_first >= g.st.abs_valid && a.abs_first >= tc_args[pi].pl.origin) {
+            if (p.tc_ok && tc_args[pi].pl.hi && nprev > 0 && a.abs_first >= g.st.abs_valid && a.abs_first >= tc_args[pi].pl.origin &&
+                a.abs_first >= tc_args[pi].pl.valid_from) {
                 const int64_t rel_first = a.abs_first - tc_args[pi].pl.origin;
                 const int shift = (int)(rel_first % p.s1_D);
                 const int A = s1t_A(p.s1_T, p.s1_D, shift);
@@ -1732,6 +1744,12 @@ static int replan_all(sdrpp_cuda_frontend* fe) {
         std::shared_ptr<VfoPlan> plan;
         int rc = get_plan(fe, v.outSR, v.bw, &plan);
         if (rc != SDRPP_OK) return rc;
+        if (v.if_state && plan->cap_final > kIfMaxBlock) {
+            // the chain cannot follow the new input rate (its staging area holds kIfMaxBlock output samples per block): it is
+            // switched off rather than silently bypassed
+            cudaFree(v.if_state); v.if_state = nullptr;
+            set_last_error("IF chain of a VFO disabled: its block output no longer fits the chain's staging area at the new rate");
+        }
         v.plan = plan;
         if (v.slab) cudaFree(v.slab);
         v.slab = nullptr;
@@ -1852,6 +1870,8 @@ static int vfo_replan(sdrpp_cuda_frontend* fe, int id, double outSR, double bw, 
     if (rc != SDRPP_OK) return rc;
     std::shared_ptr<VfoPlan> plan;
     if ((rc = get_plan(fe, outSR, bw, &plan)) != SDRPP_OK) return rc;
+    if (v->if_state && plan->cap_final > kIfMaxBlock)
+        return fail(SDRPP_ERR_ARG, "the new output rate makes the VFO's block output exceed the IF chain's staging area: disable the chain first");
     remove_from_group(fe, id);
     v->outSR = outSR; v->bw = bw; v->plan = plan;
     if (v->slab) cudaFree(v->slab);

@@ -215,12 +215,7 @@ static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 template <class P, int B>
 static cudaError_t launch_cols(const SpectrumArgs& a, const SpectrumTables& tabs, int N2, int log2N, cudaStream_t st) {
     const size_t smem = (P::L + (size_t)N2 + fft_exchange_elems<P, true, B>()) * sizeof(float2);
-    static size_t attr_set = 0;
-    if (smem > attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(fft_cols_kernel<P, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_set = smem;
-    }
+    if (cudaError_t e = ensure_dynamic_smem((const void*)fft_cols_kernel<P, B>, smem); e != cudaSuccess) return e;
     dim3 grid(N2 / B, a.frames);
     fft_cols_kernel<P, B><<<grid, P::T * B, smem, st>>>(a, tabs, N2, log2N, ilog2(N2));
     return cudaGetLastError();
@@ -231,12 +226,7 @@ static cudaError_t launch_rows(const SpectrumArgs& a, const SpectrumTables& tabs
     constexpr size_t ex = fft_exchange_elems<P, false, B>() * sizeof(float2);
     constexpr size_t tr = FROM_SAMPLES ? 0 : (size_t)P::L * (B + 1) * sizeof(float);
     constexpr size_t smem = P::L * sizeof(float2) + (ex > tr ? ex : tr);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(fft_rows_kernel<P, B, FROM_SAMPLES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr_done = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem((const void*)fft_rows_kernel<P, B, FROM_SAMPLES>, smem); e != cudaSuccess) return e;
     dim3 grid(FROM_SAMPLES ? ceil_div(a.frames, B) : N1 / B, FROM_SAMPLES ? 1 : a.frames);
     fft_rows_kernel<P, B, FROM_SAMPLES><<<grid, P::T * B, smem, st>>>(a, tabs, N1, log2N);
     return cudaGetLastError();

@@ -131,6 +131,7 @@ struct S1TPlanes {
     uint8_t* hi;
     uint8_t* lo;
     float* sinv;
+    int64_t valid_from;    // absolute sample index from which the planes hold converted samples (host bookkeeping)
 };
 struct S1TGroupArgs {
     const uint8_t* bblob;  // B images of the group's VFO tiles (s1t_b_bytes)

@@ -214,3 +214,32 @@ def test_vfo_class_added_midstream_moves_the_row_origin(gpu):
         return dict(st)
 
     _compare_modes(gpu, sr, blocks, script, blk)
+
+
+def test_mode_switch_on_a_live_front_end(gpu):
+    """Tensor -> FP32 -> tensor on a live front end: while the FP32 kernel runs, the fp16 planes are not refreshed, so the
+    first tensor-core block after switching back must not read them for history (it falls back to the FP32 kernel for the
+    blocks whose windows reach before the planes' valid range)."""
+    sr, blk = 61.44e6, 307200
+    x = synth.baseband(blk * 8, sr, 35, carriers=[(2.0e6, "fm")], noise_dbfs=-40.0).astype(np.complex64)
+    blocks = [x[i * blk:(i + 1) * blk] for i in range(8)]
+    outs = []
+    for toggled in (True, False):
+        res = []
+        with gpu.Frontend(sr, max_block=blk) as fe:
+            fe.set_stage1_mode(0 if toggled else 1)
+            vid = fe.add_vfo(48e3, 12.5e3, 2.0e6, po.DEMOD_NONE)
+            for bi, b in enumerate(blocks):
+                if toggled and bi == 3:
+                    fe.set_stage1_mode(1)
+                if toggled and bi == 5:
+                    fe.set_stage1_mode(0)
+                fe.process(po.FMT_CF32, b)
+                res.append(fe.vfo_output(vid)[0].copy())
+            tl = fe.stage1_tensor_launches
+        outs.append((np.concatenate(res), tl))
+    (gt, tlt), (gf, tlf) = outs
+    assert tlt >= 3 and tlf == 0
+    assert len(gt) == len(gf)
+    err = po.rel_rms(gt, gf)
+    assert err <= 3e-6, f"{err:.3e}"
