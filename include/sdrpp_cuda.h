@@ -242,7 +242,7 @@ SDRPP_API int sdrpp_cuda_frontend_submit_shared(sdrpp_cuda_frontend* fe, int fmt
 SDRPP_API int sdrpp_cuda_frontend_set_readback(sdrpp_cuda_frontend* fe, int enabled);
 
 /* Results of the last waited block. Pointers are into pinned host memory owned by the front end
- * and stay valid until the next submit (with blocks submitted ahead: until the third submit after the block's own). */
+ * and stay valid until the fifth submit after the block's own (five result sets rotate). */
 /* RxVFO::out for this block: returns the output sample count; *iq -> cf32[count];
  * *demod -> float[count] (NULL when demod == NONE). */
 SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cf32** iq, const float** demod);
