@@ -806,17 +806,35 @@ __device__ __forceinline__ float2& fast_at(float2* x, const FastRegion& r, int i
     return r.M > 1 ? x[r.base + (i & (r.M - 1)) * r.qs + (i >> r.lgM)] : x[r.base + i];
 }
 
+#ifdef SDRPP_TAILFAST_TRACE
+__device__ long long g_tailfast_trace[16];
+#define TF_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_tailfast_trace[i] = clock64(); } while (0)
+#else
+#define TF_MARK(i) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kFastThreads, 1)
 tail_fast_kernel(const __grid_constant__ TailArgs a) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* taps = reinterpret_cast<float*>(tail_smem);                          // [kFastTapFloats]
     float2* x = reinterpret_cast<float2*>(tail_smem + kFastTapFloats * 4);      // stage regions ..., [prev | final], split-K scratch
+    const int tid = threadIdx.x;
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
-    const TailGroup& g = a.g[gi];
-    const VfoDev vd = a.vfos[g.first_vfo + vi];
+    TF_MARK(0);
+    // The group record (480 bytes of a 2.9 KB kernel parameter) is read word by word by different threads, so its
+    // constant-cache misses overlap, and lives in shared memory from here on: walked by one thread after the other it
+    // cost 3.9 k cycles of cold misses before the first load was issued (tools/tailfast_trace.py).
+    __shared__ TailGroup sg;
+    {
+        const int* src = reinterpret_cast<const int*>(&a.g[gi]);
+        int* dst = reinterpret_cast<int*>(&sg);
+        for (int i = tid; i < (int)(sizeof(TailGroup) / sizeof(int)); i += kFastThreads) dst[i] = src[i];
+    }
+    const VfoDev vd = a.vfos[a.g[gi].first_vfo + vi];
+    __syncthreads();
+    const TailGroup& g = sg;
     float2* slab = vd.slab;
-    const int tid = threadIdx.x;
 
     FastRegion reg[kTailMaxStages + 1];
     int toff[kTailMaxStages];
@@ -834,6 +852,7 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
     float2* fin = x + rf.base + 1;
     float2* scratch = x + rf.base + ((g.n_final + 2 + 1) & ~1);
 
+    TF_MARK(1);
     // ---- one round trip: everything this block needs ------------------------------------------------------------------
     if (g.s_begin < g.nstages) {
         const TailStage& st = g.st[g.s_begin];
@@ -872,8 +891,10 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
         for (int i = reg[s].len + tid; i < reg[s].len + 6 * D + 8; i += kFastThreads) fast_at(x, reg[s], i) = make_float2(0.0f, 0.0f);
     }
     if (tid == 0) fin[-1] = slab[g.final_off - 1];
+    TF_MARK(2);
     cp_async_wait_all();
     __syncthreads();
+    TF_MARK(3);
 
     // ---- the stages, back to back out of shared memory ------------------------------------------------------------------
     for (int s = g.s_begin; s < g.nstages; s++) {
@@ -885,11 +906,13 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
         if (st.type == TAIL_POLY) {
             const float2* __restrict__ in = x + ri.base;
             const float* __restrict__ h0 = taps + toff[s];
-            for (int o = tid; o < st.n_out; o += kFastThreads) {
-                // closed form of polyphase_resampler.h:75-93
-                const long long P = (long long)st.phase + (long long)o * st.D;
-                const float2* __restrict__ xp = in + st.offset + (int)(P / st.interp);
-                const float* __restrict__ h = h0 + (int)(P % st.interp) * T;
+            const int p_phase = st.phase, p_D = st.D, p_interp = st.interp, p_off = st.offset, p_nout = st.n_out;
+            for (int o = tid; o < p_nout; o += kFastThreads) {
+                // closed form of polyphase_resampler.h:75-93 (phase + o*D fits 32 bits: o < 2^20, D < 2^11)
+                const int P = p_phase + o * p_D;
+                const int q = P / p_interp;
+                const float2* __restrict__ xp = in + p_off + q;
+                const float* __restrict__ h = h0 + (P - q * p_interp) * T;
                 float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
                 int k = 0;
                 for (; k + 4 <= T; k += 4) {
@@ -903,12 +926,15 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
                 fast_at(x, ro, obase + o) = make_float2((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y));
             }
             __syncthreads();
+            TF_MARK(4 + s);
             continue;
         }
         // FIR / decimating FIR, register-blocked: thread (og, ks) owns outputs 4*og .. 4*og+3 over a slice of the S = 3D + T
         // window steps; step j meets element offset + 4*og*D + j and the taps (h[j], h[j-D], h[j-2D], h[j-3D]).
         const int D = st.type == TAIL_DECFIR ? st.D : 1;
-        const int G = (st.n_out + kFastOB - 1) / kFastOB;
+        const int n_out = st.n_out, st_offset = st.offset;
+        const int r_base = ri.base, r_mask = ri.M - 1, r_qs = ri.qs, r_lg = ri.lgM;   // plain registers for the inner loop
+        const int G = (n_out + kFastOB - 1) / kFastOB;
         const int S = (kFastOB - 1) * D + T;
         int KS = 1;
         while (KS < 8 && G * KS * 2 <= kFastThreads && S >= 32 * KS) KS *= 2;
@@ -921,15 +947,16 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
             float2 acc[kFastOB];
 #pragma unroll
             for (int r = 0; r < kFastOB; r++) acc[r] = make_float2(0.0f, 0.0f);
+            if (s == g.nstages - 1) TF_MARK(13);
             if (active) {
-                const int e0 = st.offset + kFastOB * og * D;     // first element of the group's window
+                const int e0 = st_offset + kFastOB * og * D;     // first element of the group's window
                 const int j1 = min(S, (ks + 1) * Sk);
                 // element e0 + j sits at plane (e0 + j) % M, position (e0 + j) / M; e0 = offset (mod M) for every group
-                const float2* __restrict__ xb = x + ri.base;
+                const float2* __restrict__ xb = x + r_base;
 #pragma unroll 4
                 for (int j = ks * Sk; j < j1; j++) {
                     const int e = e0 + j;
-                    const float2 v = xb[(e & (ri.M - 1)) * ri.qs + (e >> ri.lgM)];
+                    const float2 v = xb[(e & r_mask) * r_qs + (e >> r_lg)];
                     const float4 h = t4[j];
                     acc[0] = __ffma2_rn(make_float2(h.x, h.x), v, acc[0]);
                     acc[1] = __ffma2_rn(make_float2(h.y, h.y), v, acc[1]);
@@ -937,6 +964,7 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
                     acc[3] = __ffma2_rn(make_float2(h.w, h.w), v, acc[3]);
                 }
             }
+            if (s == g.nstages - 1) TF_MARK(14);
             if (KS > 1) {
                 if (active && ks > 0) {
 #pragma unroll
@@ -957,12 +985,14 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
 #pragma unroll
                 for (int r = 0; r < kFastOB; r++) {
                     const int o = kFastOB * og + r;
-                    if (o < st.n_out) fast_at(x, ro, obase + o) = acc[r];
+                    if (o < n_out) fast_at(x, ro, obase + o) = acc[r];
                 }
             }
+            if (s == g.nstages - 1) TF_MARK(15);
             if (KS > 1) __syncthreads();   // scratch is reused by the next round of groups
         }
         __syncthreads();
+        TF_MARK(4 + s);
     }
 
     // ---- results, new histories -----------------------------------------------------------------------------------------
@@ -984,6 +1014,7 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
         }
     }
     if (tid == 0 && g.n_final > 0) slab[g.final_off - 1] = fin[g.n_final - 1];
+    TF_MARK(12);
 }
 
 cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st) {
@@ -1349,6 +1380,11 @@ cudaError_t launch_post(const PostArgs& a, int total_vfos, cudaStream_t st) {
 
 } // namespace sdrpp
 
+#ifdef SDRPP_TAILFAST_TRACE
+extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_tailfast_trace(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_tailfast_trace, sizeof(long long) * 16);
+}
+#endif
 #ifdef SDRPP_S1_TRACE
 extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_s1_trace(long long* out, int rows) {
     if (rows > sdrpp::kS1TraceCap) rows = sdrpp::kS1TraceCap;

@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace sdrpp {
@@ -638,6 +639,18 @@ cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
         g.n_vtiles = ceil_div(g.nvfo, kNV);
         maxA = std::max(maxA, g.A);
         total += (double)g.n_vtiles * g.n_ttiles * g.A;
+    }
+    // Experiment knob (SDRPP_S1T_TILES_PER_CTA, default 1 = off): cap the grid so that a CTA gets at least that many time
+    // tiles, leaving SMs to the tail / spectrum / ingest kernels of the neighbouring blocks. Measured on 16 .. 128 VFOs
+    // (profiles/README.md): the step does not move for 1 .. 8 tiles per CTA -- a small VFO set is bound by the latency of
+    // the tail chain, not by SMs -- and gets slower beyond.
+    {
+        double tiles = 0.0;
+        int vtiles = 0;
+        for (int i = 0; i < a.ngroups; i++) { tiles += (double)a.g[i].n_vtiles * a.g[i].n_ttiles; vtiles += a.g[i].n_vtiles; }
+        static const int per_cta = getenv("SDRPP_S1T_TILES_PER_CTA") ? std::max(1, atoi(getenv("SDRPP_S1T_TILES_PER_CTA"))) : 1;
+        const int want = std::max(vtiles, (int)std::ceil(tiles / per_cta));
+        if (want < num_sms) num_sms = want;
     }
     // CTAs per VFO tile: proportional share of the SMs, at least 1, at most one per time tile
     int used = 0;
