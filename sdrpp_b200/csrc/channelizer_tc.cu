@@ -129,10 +129,10 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 #ifdef SDRPP_S1T_TRACE
 // Debug build only (-DSDRPP_S1T_TRACE): per-CTA cycle counters of the three roles (tools/s1t_trace.py)
-__device__ long long g_s1t_trace[256][16];
+__device__ long long g_s1t_trace[256][24];
 #define S1T_T0(var) const long long var = clock64()
 #define S1T_ACC(slot, var) do { s1t_acc_[slot] += clock64() - (var); } while (0)
-#define S1T_DECL long long s1t_acc_[16] = { 0 }
+#define S1T_DECL long long s1t_acc_[24] = { 0 }
 #define S1T_ARG , s1t_acc_
 #define S1T_FLUSH(slot) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = s1t_acc_[slot]; } while (0)
 #define S1T_SET(slot, val) do { if (blockIdx.x < 256) g_s1t_trace[blockIdx.x][slot] = (val); } while (0)
@@ -303,11 +303,15 @@ cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, cons
 // (VFOs kNVW*hf .. of the tile). Thread = one row R. Per VFO: load the 2A accumulator columns and sum
 // V[R+a][a] over a with warp shuffles, each term weighted by the block scale of the row it comes from; the part
 // that reaches into the next warp's rows is handed over through shared memory (written by the lanes it wraps
-// onto). cur[j] = e^{j phi(R)} of the thread's row for VFO j, advanced by the caller from tile to tile.
+// onto). cur[j] = e^{j phi(R)} of the thread's row for VFO j, advanced by the caller from tile to tile; sc = block scale
+// of the thread's row (loaded one tile ahead by the caller), m = output index of the row, obase[j] = where output 0 of
+// VFO j goes (null: no such VFO). Everything the tile needs besides the accumulator sits in registers: a shared-memory
+// or constant-bank round trip here queues behind the MMA operand stream (tools/s1t_trace.py: the store phase took 785
+// cycles per tile while it fetched its pointers from shared memory, the scale load 290).
 // ---------------------------------------------------------------------------------------------
 template <int A>
-__device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S1TPlanes& pl, uint32_t tmem_acc, int q, int hf, int lane,
-                                                  int vt, int64_t row_t, float* xch, uint64_t* tempty_bar, const float2* cur, float2* const* outp
+__device__ __forceinline__ void s1t_epilogue_tile(uint32_t tmem_acc, int q, int hf, int lane, float sc, int m, int M, float* xch,
+                                                  uint64_t* tempty_bar, const float2* cur, float2* const* obase
 #ifdef SDRPP_S1T_TRACE
                                                   , long long* s1t_acc_
 #endif
@@ -317,8 +321,6 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
     const long long tl0_ = clock64();
 #endif
     const int row = q * 32 + lane;
-    const int64_t R = row_t + row;
-    const float sc = pl.sinv[(uint32_t)((uint64_t)(R >> 3) & pl.group_mask)] * G.b_scale_inv;
     // weight of the term taken from lane (lane + a) & 31: its row's scale, routed to the in-warp sum (scA) or to
     // the sum that belongs to the previous quadrant's row (scW)
     float scA[A], scW[A];
@@ -329,6 +331,9 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
         scA[a] = wrapped ? 0.0f : s;
         scW[a] = wrapped ? s : 0.0f;
     }
+#ifdef SDRPP_S1T_TRACE
+    if (q == 2 && hf == 0 && lane == 0) { s1t_acc_[16] += (long long)(scA[0] != 12345.0f) * (clock64() - tl0_); }
+#endif
     const uint32_t t0 = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * NVH * 2 * A);
     float2 y[NVH];
     float2* xw = reinterpret_cast<float2*>(xch) + ((hf * 4 + q) * 7) * NVH;
@@ -365,9 +370,9 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory"); // the epilogue warps: wrapped sums visible
 #ifdef SDRPP_S1T_TRACE
     if (q == 2 && hf == 0 && lane == 0) { S1T_ACC(7, tb_); }
+    const long long ts_ = clock64();
 #endif
-    const int64_t m = R - G.row_first;
-    const bool out_row = row < kOutPerTile && m >= 0 && m < (int64_t)G.M;
+    const bool out_row = row < kOutPerTile && m >= 0 && m < M;
     const bool take = q < 3 && lane >= 25;
     const float2* xr = reinterpret_cast<const float2*>(xch) + ((hf * 4 + q + 1) * 7) * NVH; // next quadrant's hand-over
 #pragma unroll
@@ -377,12 +382,15 @@ __device__ __forceinline__ void s1t_epilogue_tile(const S1TGroupArgs& G, const S
             const float2 w = xr[(lane - 25) * NVH + j];
             t.x += w.x; t.y += w.y;
         }
-        float2* o = outp[hf * NVH + j];
+        float2* o = obase[j];
         if (out_row && o) {
             const float2 e = cur[j];
-            o[m] = make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x);
+            __stcg(o + m, make_float2(t.x * e.x - t.y * e.y, t.x * e.y + t.y * e.x));
         }
     }
+#ifdef SDRPP_S1T_TRACE
+    if (q == 2 && hf == 0 && lane == 0) { S1T_ACC(17, ts_); }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -410,8 +418,8 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
     uint8_t* smB = smem_raw;                              // [hi|lo][kh][N][128]
     uint8_t* smA = smB + 2 * b_plane;                     // nch chunks of 16 KB (multiple of 1024: N % 8 == 0)
     float* xch = reinterpret_cast<float*>(smA + (size_t)nch * kChunkBytes);
-    float2** outp = reinterpret_cast<float2**>(xch + kXchFloats);      // [kNV] slab + out_off of the tile's VFOs (null: no such VFO)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(outp + kNV);
+    ulonglong2* nco = reinterpret_cast<ulonglong2*>(xch + kXchFloats);   // [kNV] (P0, W) of the tile's VFOs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(nco + kNV);
     uint64_t* full = bars;                 // [kMaxChunks]
     uint64_t* empty = bars + kMaxChunks;   // [kMaxChunks]
     uint64_t* bfull = bars + 2 * kMaxChunks;
@@ -424,7 +432,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #ifdef SDRPP_S1T_TRACE
     const long long tk0_ = clock64();
     if (tid == 0 && blockIdx.x < 256) {
-        for (int i = 0; i < 16; i++) g_s1t_trace[blockIdx.x][i] = 0;
+        for (int i = 0; i < 24; i++) g_s1t_trace[blockIdx.x][i] = 0;
         g_s1t_trace[blockIdx.x][12] = tt1 - tt0; g_s1t_trace[blockIdx.x][13] = A;
         long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));
         g_s1t_trace[blockIdx.x][11] = gt_;
@@ -547,32 +555,61 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
         // ===== epilogue warps =====
         const int q = warp & 3, hf = (warp - 2) >> 2;
         constexpr int NVH = kNVW;
-        // NCO phase of this thread's row per VFO: exact (64-bit accumulator) every 8 tiles, advanced by the
-        // constant tile step in between
+        const int row = q * 32 + lane;
+        const int64_t g_row0 = G.row0;
+        const int g_M = G.M, g_nvfo = G.nvfo, D = a.pl.D;
+        const float b_scale_inv = G.b_scale_inv;
+        const VfoDev* g_vfos = G.vfos;
+        const float* __restrict__ sinv = a.pl.sinv;
+        const uint32_t gmask = a.pl.group_mask;
+        // output index of this thread's row in time tile 0 (advances by kOutPerTile per tile); fits 32 bits: |row0 - row_first| < 8
+        int m = (int)(g_row0 - G.row_first) + row + kOutPerTile * tt0;
+        // NCO phase of this thread's row per VFO: exact (64-bit accumulator) every 8 tiles, advanced by the constant tile
+        // step in between. phase(R) = P0 + R * W with P0 = phi_ref + (origin - n_ref) * dphi, W = D * dphi (mod 2^64): the
+        // two words per VFO are computed once per CTA and kept in shared memory, so the refresh has no global round trip.
         float2 cur[NVH], stp[NVH];
+        float2* obase[NVH];
+        if (tid - 64 < kNV) {
+            const int v = vt * kNV + (tid - 64);
+            uint64_t p0 = 0, w = 0;
+            if (v < g_nvfo) {
+                const VfoDev* vd = g_vfos + v;
+                w = (uint64_t)D * vd->dphi;
+                p0 = vd->phi_ref + (uint64_t)((int64_t)a.pl.origin - vd->n_ref) * vd->dphi;
+            }
+            nco[tid - 64] = make_ulonglong2(p0, w);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
         auto exact_phase = [&](int tt) {
-            const int64_t R = G.row0 + (int64_t)kOutPerTile * tt + q * 32 + lane;
+            const uint64_t R = (uint64_t)(g_row0 + (int64_t)kOutPerTile * tt + row);
 #pragma unroll
             for (int j = 0; j < NVH; j++) {
-                const int v = vt * kNV + hf * NVH + j;
-                if (v < G.nvfo) {
-                    const VfoDev* vd = G.vfos + v;
-                    cur[j] = phasor64(vd->phi_ref + (uint64_t)(R * (int64_t)a.pl.D + a.pl.origin - vd->n_ref) * vd->dphi);
-                } else cur[j] = make_float2(1.0f, 0.0f);
+                const ulonglong2 c = nco[hf * NVH + j];
+                cur[j] = phasor64(c.x + R * c.y);
             }
         };
 #pragma unroll
         for (int j = 0; j < NVH; j++) {
             const int v = vt * kNV + hf * NVH + j;
-            stp[j] = v < G.nvfo ? phasor64((uint64_t)(kOutPerTile * a.pl.D) * G.vfos[v].dphi) : make_float2(1.0f, 0.0f);
+            stp[j] = phasor64((uint64_t)kOutPerTile * nco[hf * NVH + j].y);
+            obase[j] = v < g_nvfo ? g_vfos[v].slab + G.out_off : nullptr;
         }
-        if (tid - 64 < kNV) { // visible to the other epilogue warps after the first tile's barrier
-            const int v = vt * kNV + (tid - 64);
-            outp[tid - 64] = v < G.nvfo ? G.vfos[v].slab + G.out_off : nullptr;
-        }
+        auto row_scale = [&](int tt) {
+            const int64_t R = g_row0 + (int64_t)kOutPerTile * tt + row;
+            return __ldg(sinv + (uint32_t)((uint64_t)(R >> 3) & gmask)) * b_scale_inv;
+        };
+        float sc_next = tt1 > tt0 ? row_scale(tt0) : 0.0f;
         for (int tt = tt0; tt < tt1; tt++) {
             const uint32_t k = (uint32_t)(tt - tt0), as = k & 1u, aph = (k >> 1) & 1u;
+#ifdef SDRPP_S1T_TRACE
+            const long long tx_ = clock64();
+#endif
             if ((k & 7u) == 0u) exact_phase(tt);
+#ifdef SDRPP_S1T_TRACE
+            if (warp == 2 && lane == 0) { s1t_acc_[18] += (long long)(cur[0].x != 12345.0f) * (clock64() - tx_); }
+#endif
+            const float sc = sc_next;
+            if (tt + 1 < tt1) sc_next = row_scale(tt + 1);   // in flight while this tile is summed
 #ifdef SDRPP_S1T_TRACE
             const bool tr_ = warp == 2 && lane == 0;
             const long long te_ = clock64();
@@ -584,16 +621,16 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
             const long long tl_ = clock64();
 #endif
             tc_fence_after();
-            const int64_t row_t = G.row0 + (int64_t)kOutPerTile * tt;
             float* xb = xch + (k & 1u) * (kXchFloats / 2);
             const uint32_t acc = tmem_base + as * 256u;
             switch (A) {
-            case 4: s1t_epilogue_tile<4>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
-            case 5: s1t_epilogue_tile<5>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
-            case 6: s1t_epilogue_tile<6>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
-            case 7: s1t_epilogue_tile<7>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
-            default: s1t_epilogue_tile<8>(G, a.pl, acc, q, hf, lane, vt, row_t, xb, tempty + as, cur, outp S1T_ARG); break;
+            case 4: s1t_epilogue_tile<4>(acc, q, hf, lane, sc, m, g_M, xb, tempty + as, cur, obase S1T_ARG); break;
+            case 5: s1t_epilogue_tile<5>(acc, q, hf, lane, sc, m, g_M, xb, tempty + as, cur, obase S1T_ARG); break;
+            case 6: s1t_epilogue_tile<6>(acc, q, hf, lane, sc, m, g_M, xb, tempty + as, cur, obase S1T_ARG); break;
+            case 7: s1t_epilogue_tile<7>(acc, q, hf, lane, sc, m, g_M, xb, tempty + as, cur, obase S1T_ARG); break;
+            default: s1t_epilogue_tile<8>(acc, q, hf, lane, sc, m, g_M, xb, tempty + as, cur, obase S1T_ARG); break;
             }
+            m += kOutPerTile;
 #pragma unroll
             for (int j = 0; j < NVH; j++) cur[j] = cmul(cur[j], stp[j]);
 #ifdef SDRPP_S1T_TRACE
@@ -604,7 +641,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 #ifdef SDRPP_S1T_TRACE
     if (warp == 0) { S1T_FLUSH(10); }
     if (warp == 1) { S1T_FLUSH(2); S1T_FLUSH(3); S1T_FLUSH(4); S1T_FLUSH(8); S1T_FLUSH(14); }
-    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); }
+    if (warp == 2) { S1T_FLUSH(5); S1T_FLUSH(6); S1T_FLUSH(7); S1T_FLUSH(9); S1T_FLUSH(15); S1T_FLUSH(16); S1T_FLUSH(17); S1T_FLUSH(18); }
 #endif
     tc_fence_before();
     __syncthreads();
@@ -622,7 +659,7 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
 }
 
 static size_t s1t_smem_bytes(int NKH, int A, int nchunks) {
-    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) + kNV * sizeof(void*) + 256;
+    return 1024 + (size_t)2 * NKH * (2 * A * kNV) * 128 + (size_t)nchunks * kChunkBytes + kXchFloats * sizeof(float) + kNV * sizeof(ulonglong2) + 256;
 }
 
 // Fills in cta_begin / cta_per_vtile (time tiles of a VFO tile are split between CTAs so that every SM gets
@@ -693,6 +730,6 @@ cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
 #ifdef SDRPP_S1T_TRACE
 extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_s1t_trace(long long* out, int rows) {
     if (rows > 256) rows = 256;
-    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 16 * (size_t)rows);
+    return (int)cudaMemcpyFromSymbol(out, sdrpp::g_s1t_trace, sizeof(long long) * 24 * (size_t)rows);
 }
 #endif

@@ -8,20 +8,20 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench  # noqa: E402
-from sdrpp_b200 import cuda  # noqa: E402
+from sdrpp_b200 import cuda, workloads  # noqa: E402
 
 cuda.init(0)
-fe = cuda.Frontend(bench.SR, fft_size=0, fft_rate=bench.SR / bench.FFT_N, fft_window=cuda.WIN_BH4, max_block=bench.BLOCK)
-for v in bench.vfo_list():
+w = workloads.config(int(os.environ.get("S1T_TRACE_CONFIG", "5")))
+fe = cuda.Frontend(w.sr, fft_size=0, fft_rate=w.fft_rate, fft_window=w.fft_window, max_block=w.block)
+for v in w.vfos:
     fe.add_vfo(*v)
-blocks = bench.make_blocks(4)
+blocks = w.make_blocks(4)
 fe.set_readback(False)
 for i in range(6):
     fe.submit(cuda.FMT_CF32, blocks[i % 4])
     fe.wait()
 L = cuda.lib()
-buf = np.zeros((256, 16), dtype=np.int64)
+buf = np.zeros((256, 24), dtype=np.int64)
 L.sdrpp_cuda_debug_s1t_trace.argtypes = [C.c_void_p, C.c_int]
 assert L.sdrpp_cuda_debug_s1t_trace(buf.ctypes.data, 256) == 0
 t = buf[buf[:, 12] > 0]
@@ -32,7 +32,7 @@ for i in range(4):
     fe.submit(cuda.FMT_CF32, blocks[i % 4]); fe.wait()
 print("family brackets (ms): ingest, spectrum, stage1, tail =", fe.kernel_ms())
 names = {1: "kernel total", 2: "mma: wait tmem empty", 3: "mma: wait smem full", 4: "mma: issue hi chunks (16 MMA)", 8: "mma: issue lo chunks (8 MMA)", 5: "epi: wait tmem full", 6: "epi: load+sum phase",
-         7: "epi: bar.sync", 9: "epi: tile total (after wait)", 10: "producer: wait smem empty", 14: "start -> B image landed", 15: "start -> first accumulator ready"}
+         7: "epi: bar.sync", 9: "epi: tile total (after wait)", 16: "epi: scale load + shuffles", 17: "epi: store phase", 18: "epi: exact phase (every 8 tiles)", 10: "producer: wait smem empty", 14: "start -> B image landed", 15: "start -> first accumulator ready"}
 for A in sorted(set(t[:, 13])):
     c = t[t[:, 13] == A]
     print(f"A={A}: {len(c)} CTAs, tiles per CTA {c[:, 12].min()}..{c[:, 12].max()}")
