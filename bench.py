@@ -327,6 +327,13 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- device-resident timing (value) ------------------------------------------------------------
     fe.set_readback(False)
+    # Untimed: the front end instantiates a CUDA graph for a block's command sequence the second time it sees it (~30
+    # distinct sequences in a steady stream: result slot x region parity x frame-completing or not). A continuous stream is
+    # past this after a fraction of a second; the benchmark runs it before its warm-up steps so that the timed steps are
+    # steady-state ones.
+    for i in range(max(0, args.graph_warmup)):
+        step_device(i)
+    barrier()
     for i in range(args.warmup):
         step_device(i)
     barrier()
@@ -461,6 +468,7 @@ def run_gpu(args, rank, world, local_rank):
                             "note": "sdrpp_cuda_spectrum_device: FB frames per call from HBM-resident input (> L2), 12 B/sample algorithmic, CUDA events"}
             del rows_dev
     comm_info = comm.info() if comm is not None else None
+    graph_stats = fe.graph_stats()
     fe.close()
 
     # ---- parity check OUTSIDE the timed region: the same workload, the same feed, against the oracle ------------------
@@ -611,7 +619,9 @@ def run_gpu(args, rank, world, local_rank):
             "clocks": clk, "e2e": e2e, "e2e_cpp": e2e_cpp, "gpu_launches": int(launches), "parity_check": parity,
             "roofline": roof, "rooflines": rows, "roofline_spectrum": rows["spectrum"], "spectrum_batched": spec_batched,
             "kernel_ms_per_step": {"ingest": float(ingest_ms), "spectrum": float(fft_ms), "channelizer_stage1": float(s1_ms), "channelizer_tail": float(tail_ms)},
-            "comm": comm_info, "cpu_baseline": cpu,
+            "comm": comm_info, "graphs": dict(graph_stats, warmup_blocks=args.graph_warmup,
+                                              note="rank 0; stage-1 and tail command runs replayed as instantiated CUDA graphs / executed command by command, whole run"),
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if comm is not None:
@@ -632,6 +642,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-cpp", action="store_true")
+    ap.add_argument("--graph-warmup", type=int, default=192, help="untimed blocks in front of the warm-up steps (CUDA-graph instantiation)")
     ap.add_argument("--e2e-ahead", type=int, default=4, help="blocks submitted ahead of the one being consumed in the end-to-end leg (1..4)")
     ap.add_argument("--rank0-base-load", type=float, default=770.0, help="N > 1: VFO-cost units rank 0 is charged for ingest + spectrum")
     args = ap.parse_args()

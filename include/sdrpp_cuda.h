@@ -355,6 +355,15 @@ SDRPP_API float sdrpp_cuda_frontend_kernel_ms(sdrpp_cuda_frontend* fe, int idx);
  * FMA kernel otherwise; mode 1 uses the FP32 FMA kernel only. The environment variable SDRPP_S1_MODE=fp32 sets
  * mode 1 at creation. _stage1_tensor_launches counts the tensor-core stage-1 launches since creation. */
 SDRPP_API int sdrpp_cuda_frontend_set_stage1_mode(sdrpp_cuda_frontend* fe, int mode);
+/* CUDA graphs. A block is planned into a command list; the kernels of its stage-1 part (descriptor upload, ingest, spectrum,
+ * fp16 split, stage 1) and of its tail part are replayed as one instantiated graph each whenever exactly the same command
+ * sequence has run before (everything that changes per block travels in a device-resident descriptor, so graphs are
+ * never updated). A sequence is instantiated the second time it is seen; a steady stream settles on about 30 graphs
+ * within ~150 blocks. _set_graphs(0) runs every block command by command (also: environment SDRPP_GRAPHS=0); results are
+ * bit-identical either way. _graph_stats: out[0] tagged runs replayed as a graph, out[1] graphs instantiated, out[2] tagged
+ * runs executed command by command, out[3] microseconds spent instantiating. */
+SDRPP_API int sdrpp_cuda_frontend_set_graphs(sdrpp_cuda_frontend* fe, int enabled);
+SDRPP_API int sdrpp_cuda_frontend_graph_stats(sdrpp_cuda_frontend* fe, long long* out4);
 SDRPP_API long long sdrpp_cuda_frontend_stage1_tensor_launches(sdrpp_cuda_frontend* fe);
 
 #ifdef __cplusplus

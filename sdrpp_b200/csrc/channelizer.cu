@@ -193,7 +193,8 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 // DT: decimation as a compile-time constant (row strides become immediates), or 0 to take it from the arguments.
 template <int A, int R, int W, int DT>
 __global__ void __launch_bounds__(W * 32, 2)
-stage1_kernel(const __grid_constant__ Stage1Args a) {
+stage1_kernel(const Stage1Args* __restrict__ ap) {
+    const Stage1Args a = *ap;   // per-block arguments (launcher descriptor)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ROWS = W * R;
     constexpr int OUT = ROWS - (A - 1);
@@ -340,22 +341,23 @@ stage1_kernel(const __grid_constant__ Stage1Args a) {
 }
 
 template <int A, int R, int W, int DT>
-static cudaError_t launch_stage1_t(const Stage1Args& a, cudaStream_t st) {
+static cudaError_t launch_stage1_t(Launcher& L, int sid, const Stage1Args& a) {
     constexpr int ROWS = W * R, OUT = ROWS - (A - 1), NP = R + A - 1;
     const size_t tile = (size_t)ROWS * a.D * sizeof(float2);
     const size_t parts = (size_t)W * NP * 32 * sizeof(float2);
     const size_t smem = 128 + parts + (size_t)(a.D / 2) * 32 * 16 + tile;
     if (cudaError_t e = ensure_dynamic_smem((const void*)stage1_kernel<A, R, W, DT>, smem); e != cudaSuccess) return e;
     dim3 grid(ceil_div(a.M, OUT), ceil_div(a.nvfo, 32));
-    stage1_kernel<A, R, W, DT><<<grid, W * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    const Stage1Args* d = L.push(a);
+    if (!d) return cudaErrorMemoryAllocation;
+    return L.kernel(sid, (const void*)stage1_kernel<A, R, W, DT>, grid, dim3(W * 32), smem, d);
 }
 
-cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st) {
+cudaError_t launch_stage1(Launcher& L, int sid, const Stage1Args& a) {
     if (a.M <= 0 || a.nvfo <= 0) return cudaSuccess;
     if (a.tap_off < 0) return cudaErrorInvalidValue;
     // the shapes the PowerDecimator plans produce at high ratios get the decimation as a compile-time constant
-#define SDRPP_S1P_CASE(AA, DD) if (a.A == AA && a.D == DD) return launch_stage1_t<AA, SDRPP_S1_R, SDRPP_S1_W, DD>(a, st);
+#define SDRPP_S1P_CASE(AA, DD) if (a.A == AA && a.D == DD) return launch_stage1_t<AA, SDRPP_S1_R, SDRPP_S1_W, DD>(L, sid, a);
     SDRPP_S1P_CASE(5, 32)
     SDRPP_S1P_CASE(5, 64)
     SDRPP_S1P_CASE(6, 64)
@@ -363,19 +365,20 @@ cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st) {
     SDRPP_S1P_CASE(6, 128)
 #undef SDRPP_S1P_CASE
     switch (a.A) {
-    case 2: return launch_stage1_t<2, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
-    case 3: return launch_stage1_t<3, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
-    case 4: return launch_stage1_t<4, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
-    case 5: return launch_stage1_t<5, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
-    case 6: return launch_stage1_t<6, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
-    case 7: return launch_stage1_t<7, SDRPP_S1_R, SDRPP_S1_W, 0>(a, st);
+    case 2: return launch_stage1_t<2, SDRPP_S1_R, SDRPP_S1_W, 0>(L, sid, a);
+    case 3: return launch_stage1_t<3, SDRPP_S1_R, SDRPP_S1_W, 0>(L, sid, a);
+    case 4: return launch_stage1_t<4, SDRPP_S1_R, SDRPP_S1_W, 0>(L, sid, a);
+    case 5: return launch_stage1_t<5, SDRPP_S1_R, SDRPP_S1_W, 0>(L, sid, a);
+    case 6: return launch_stage1_t<6, SDRPP_S1_R, SDRPP_S1_W, 0>(L, sid, a);
+    case 7: return launch_stage1_t<7, SDRPP_S1_R, SDRPP_S1_W, 0>(L, sid, a);
     }
     return cudaErrorInvalidValue;
 }
 
 // D = 1: translation only (RationalResampler modes RESAMP_ONLY / NONE, rational_resampler.h:83-97)
 __global__ void __launch_bounds__(256)
-mix_only_kernel(const __grid_constant__ Stage1Args a) {
+mix_only_kernel(const Stage1Args* __restrict__ ap) {
+    const Stage1Args a = *ap;   // per-block arguments (launcher descriptor)
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y;
     if (m >= a.M) return;
@@ -386,11 +389,12 @@ mix_only_kernel(const __grid_constant__ Stage1Args a) {
     vd.slab[a.out_off + m] = cmul(x, phasor_u64(ph));
 }
 
-cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st) {
+cudaError_t launch_mix_only(Launcher& L, int sid, const Stage1Args& a) {
     if (a.M <= 0 || a.nvfo <= 0) return cudaSuccess;
     dim3 grid(ceil_div(a.M, 256), a.nvfo);
-    mix_only_kernel<<<grid, 256, 0, st>>>(a);
-    return cudaGetLastError();
+    const Stage1Args* d = L.push(a);
+    if (!d) return cudaErrorMemoryAllocation;
+    return L.kernel(sid, (const void*)mix_only_kernel, grid, dim3(256), 0, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -631,7 +635,8 @@ __device__ __forceinline__ float demod_front_end(const TailGroup& g, const VfoDe
 }
 
 __global__ void __launch_bounds__(kTailThreads, 4)
-tail_kernel(const __grid_constant__ TailArgs a) {
+tail_kernel(const TailArgs* __restrict__ ap) {
+    const TailArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory)
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* ttaps = reinterpret_cast<float*>(tail_smem);                           // [kTailTapFloats]
     float2* tsm = reinterpret_cast<float2*>(tail_smem + kTailTapFloats * 4);      // staged samples
@@ -814,7 +819,8 @@ __device__ long long g_tailfast_trace[16];
 #endif
 
 __global__ void __launch_bounds__(kFastThreads, 1)
-tail_fast_kernel(const __grid_constant__ TailArgs a) {
+tail_fast_kernel(const TailArgs* __restrict__ ap) {
+    const TailArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory)
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* taps = reinterpret_cast<float*>(tail_smem);                          // [kFastTapFloats]
     float2* x = reinterpret_cast<float2*>(tail_smem + kFastTapFloats * 4);      // stage regions ..., [prev | final], split-K scratch
@@ -1017,7 +1023,7 @@ tail_fast_kernel(const __grid_constant__ TailArgs a) {
     TF_MARK(12);
 }
 
-cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st) {
+cudaError_t launch_tail_fast(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos) {
     if (total_vfos <= 0) return cudaSuccess;
     int need = 0;
     for (int i = 0; i < a.ngroups; i++) {
@@ -1027,8 +1033,7 @@ cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st)
     }
     const size_t smem = (size_t)kFastTapFloats * sizeof(float) + (size_t)(need + 8) * sizeof(float2);
     if (cudaError_t e = ensure_dynamic_smem((const void*)tail_fast_kernel, kFastTapFloats * sizeof(float) + (kFastMaxSamples + 8) * sizeof(float2)); e != cudaSuccess) return e;
-    tail_fast_kernel<<<total_vfos, kFastThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)tail_fast_kernel, dim3((unsigned)total_vfos), dim3(kFastThreads), smem, d_a);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1048,7 +1053,8 @@ constexpr int kWideMaxTaps = 128;
 // A tap load serves the thread's four outputs; accumulation is packed FMA on (re, im).
 template <int D>
 __global__ void __launch_bounds__(kWideThreads, 10)
-tail_stage0_wide_kernel(const __grid_constant__ TailArgs a) {
+tail_stage0_wide_kernel(const TailArgs* __restrict__ ap) {
+    const TailArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory)
     extern __shared__ __align__(16) unsigned char tail_smem[];
     float* taps = reinterpret_cast<float*>(tail_smem);                            // [kWideMaxTaps + 16], zero padded
     float2* xs = reinterpret_cast<float2*>(tail_smem + (kWideMaxTaps + 16) * 4);  // transposed window
@@ -1102,19 +1108,18 @@ tail_stage0_wide_kernel(const __grid_constant__ TailArgs a) {
 }
 
 template <int D>
-static cudaError_t launch_wide_t(const TailArgs& a, int total_vfos, int max_out, cudaStream_t st) {
+static cudaError_t launch_wide_t(Launcher& L, int sid, const TailArgs* d_a, int total_vfos, int max_out) {
     constexpr int lg = D == 2 ? 1 : D == 4 ? 2 : D == 8 ? 3 : 4;
     constexpr int qs = (kWideOut + (kWideMaxTaps >> lg) + 2) | 1;
     const size_t smem = (size_t)(kWideMaxTaps + 16) * sizeof(float) + (size_t)D * qs * sizeof(float2);
     if (cudaError_t e = ensure_dynamic_smem((const void*)tail_stage0_wide_kernel<D>, smem); e != cudaSuccess) return e;
     dim3 grid((unsigned)std::max(1, ceil_div(max_out, kWideOut)), (unsigned)total_vfos);
-    tail_stage0_wide_kernel<D><<<grid, kWideThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)tail_stage0_wide_kernel<D>, grid, dim3(kWideThreads), smem, d_a);
 }
 
 bool tail_stage0_wide_supported(int T, int D) { return T <= kWideMaxTaps && (D == 2 || D == 4 || D == 8 || D == 16); }
 
-cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStream_t st) {
+cudaError_t launch_tail_stage0_wide(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos) {
     if (total_vfos <= 0) return cudaSuccess;
     for (int D : { 2, 4, 8, 16 }) {
         int max_out = 0;
@@ -1122,19 +1127,19 @@ cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStrea
         for (int i = 0; i < a.ngroups; i++)
             if (a.g[i].s_begin == 1 && a.g[i].nstages > 0 && a.g[i].st[0].D == D) { any = true; max_out = std::max(max_out, a.g[i].st[0].n_out); }
         if (!any) continue;
-        cudaError_t e = D == 2 ? launch_wide_t<2>(a, total_vfos, max_out, st) : D == 4 ? launch_wide_t<4>(a, total_vfos, max_out, st)
-                      : D == 8 ? launch_wide_t<8>(a, total_vfos, max_out, st) : launch_wide_t<16>(a, total_vfos, max_out, st);
+        cudaError_t e = D == 2 ? launch_wide_t<2>(L, sid, d_a, total_vfos, max_out) : D == 4 ? launch_wide_t<4>(L, sid, d_a, total_vfos, max_out)
+                      : D == 8 ? launch_wide_t<8>(L, sid, d_a, total_vfos, max_out) : launch_wide_t<16>(L, sid, d_a, total_vfos, max_out);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }
 
-cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st) {
+cudaError_t launch_tail(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos) {
     if (total_vfos <= 0) return cudaSuccess;
     const size_t smem = (size_t)kTailTapFloats * sizeof(float) + (size_t)(kTailSmemSamples + 512) * sizeof(float2);
     if (cudaError_t e = ensure_dynamic_smem((const void*)tail_kernel, smem); e != cudaSuccess) return e;
-    tail_kernel<<<total_vfos, kTailThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    (void)a;
+    return L.kernel(sid, (const void*)tail_kernel, dim3((unsigned)total_vfos), dim3(kTailThreads), smem, d_a);
 }
 
 
@@ -1287,7 +1292,8 @@ __device__ __noinline__ void post_wfm(const PostDev& pd, int n, const float* __r
 }
 
 __global__ void __launch_bounds__(kPostThreads)
-post_kernel(const __grid_constant__ PostArgs a) {
+post_kernel(const PostArgs* __restrict__ ap) {
+    const PostArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory)
     __shared__ float staps[kPostTapFloats];
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
@@ -1372,10 +1378,11 @@ post_kernel(const __grid_constant__ PostArgs a) {
     }
 }
 
-cudaError_t launch_post(const PostArgs& a, int total_vfos, cudaStream_t st) {
+cudaError_t launch_post(Launcher& L, int sid, const PostArgs& a, int total_vfos) {
     if (total_vfos <= 0) return cudaSuccess;
-    post_kernel<<<total_vfos, kPostThreads, 0, st>>>(a);
-    return cudaGetLastError();
+    const PostArgs* d = L.push(a);
+    if (!d) return cudaErrorMemoryAllocation;
+    return L.kernel(sid, (const void*)post_kernel, dim3((unsigned)total_vfos), dim3(kPostThreads), 0, d);
 }
 
 } // namespace sdrpp

@@ -165,9 +165,18 @@ constexpr int kXchFloats = 2 /*buffers*/ * 4 /*quadrants*/ * 7 /*lanes*/ * kNV *
 // (8 fp16: re0 im0 .. re3 im3) of the row and stores it at the swizzled chunk position (chunk ^ row).
 // Samples at or beyond abs_end (not written yet) are stored as zeros.
 // ---------------------------------------------------------------------------------------------
+struct S1TSplitArgs {    // per-block arguments, read through the launcher's descriptor
+    RingRef ring;
+    S1TPlanes pl;
+    int64_t g_first, abs_end;
+};
+
 __global__ void __launch_bounds__(256)
-s1t_split_kernel(RingRef ring, S1TPlanes pl, int64_t g_first, int64_t abs_end) {
+s1t_split_kernel(const S1TSplitArgs* __restrict__ ap) {
     __shared__ float red[8];
+    const RingRef ring = ap->ring;
+    const S1TPlanes pl = ap->pl;
+    const int64_t g_first = ap->g_first, abs_end = ap->abs_end;
     const int D = pl.D;
     const int t = threadIdx.x;
     const int64_t g = g_first + blockIdx.x;
@@ -219,13 +228,14 @@ s1t_split_kernel(RingRef ring, S1TPlanes pl, int64_t g_first, int64_t abs_end) {
     if (t == 0) pl.sinv[slot] = __uint_as_float((uint32_t)(127 - e) << 23);
 }
 
-cudaError_t launch_s1t_split(RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end, cudaStream_t st) {
+cudaError_t launch_s1t_split(Launcher& L, int sid, RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end) {
     if (abs_end <= abs_begin) return cudaSuccess;
     const int gs = 8 * pl.D;
     if (abs_end <= pl.origin) return cudaSuccess;
     const int64_t g0 = std::max<int64_t>(abs_begin - pl.origin, 0) / gs, g1 = (abs_end - 1 - pl.origin) / gs;
-    s1t_split_kernel<<<(unsigned)(g1 - g0 + 1), 2 * pl.D, 0, st>>>(ring, pl, g0, abs_end);
-    return cudaGetLastError();
+    const S1TSplitArgs* d = L.push(S1TSplitArgs{ ring, pl, g0, abs_end });
+    if (!d) return cudaErrorMemoryAllocation;
+    return L.kernel(sid, (const void*)s1t_split_kernel, dim3((unsigned)(g1 - g0 + 1)), dim3((unsigned)(2 * pl.D)), 0, d);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -290,12 +300,11 @@ int s1t_b_exponent(const float* taps, int T) {
     return std::max(-40, std::min(60, 14 - ex));
 }
 
-cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift, int A,
-                               int escale, cudaStream_t st) {
+cudaError_t launch_s1t_build_b(Launcher& L, int sid, uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift,
+                               int A, int escale) {
     const int N = 2 * A * kNV, NKH = D >> 5;
     dim3 grid(ceil_div(NKH * N * 8, 256), ceil_div(nvfo, kNV));
-    s1t_build_b_kernel<<<grid, 256, 0, st>>>(blob, vfos, nvfo, d_taps, T, D, shift, A, escale);
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)s1t_build_b_kernel, grid, dim3(256), 0, blob, vfos, nvfo, d_taps, T, D, shift, A, escale);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -399,8 +408,9 @@ __device__ __forceinline__ void s1t_epilogue_tile(uint32_t tmem_acc, int q, int 
 // ---------------------------------------------------------------------------------------------
 template <int NKH>
 __global__ void __launch_bounds__(kThreads, 1)
-s1t_kernel(const __grid_constant__ S1TArgs a) {
+s1t_kernel(const S1TArgs* __restrict__ ap) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const S1TArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory): read once per role
     int gi = 0;
     while (gi + 1 < a.ngroups && (int)blockIdx.x >= a.g[gi + 1].cta_begin) gi++;
     const S1TGroupArgs& G = a.g[gi];
@@ -467,18 +477,23 @@ s1t_kernel(const __grid_constant__ S1TArgs a) {
                 for (int i = 0; i < 2 * NKH; i++) bulk_g2s(smB + (size_t)i * piece, bsrc + (size_t)i * piece, piece, bfull);
             }
             __syncwarp();
-            const uint32_t ng = a.pl.group_mask + 1;
+            // the arguments live in device memory now: keep what the loop needs in registers (every barrier wait below is a
+            // compiler memory fence, so a field read inside the loop would be loaded again on every pass)
+            const uint32_t gmask = a.pl.group_mask, ng = gmask + 1;
+            const uint8_t* const pl_hi = a.pl.hi;
+            const uint8_t* const pl_lo = a.pl.lo;
+            const int64_t g_row0 = G.row0;
             uint32_t slot = 0, ph = 0; // ring slot and its phase bit, advanced without divisions
             for (int tt = tt0; tt < tt1; tt++) {
-                const int64_t row_t = G.row0 + (int64_t)kOutPerTile * tt;
-                const uint32_t gs = (uint32_t)((uint64_t)(row_t >> 3) & a.pl.group_mask);
+                const int64_t row_t = g_row0 + (int64_t)kOutPerTile * tt;
+                const uint32_t gs = (uint32_t)((uint64_t)(row_t >> 3) & gmask);
                 const uint32_t n1 = min(16u, ng - gs);   // groups before the ring wraps
 #pragma unroll 1
                 for (int c = 0; c < 2 * NKH; c++) {
                     S1T_T0(tw_);
                     mbar_wait(empty + slot, ph ^ 1u);
                     S1T_ACC(10, tw_);
-                    const uint8_t* plane = ((c & 1) ? a.pl.lo : a.pl.hi) + (size_t)(c >> 1) * ng * 1024;
+                    const uint8_t* plane = ((c & 1) ? pl_lo : pl_hi) + (size_t)(c >> 1) * ng * 1024;
                     uint8_t* dst = smA + (size_t)slot * kChunkBytes;
                     if (elect_one()) {
                         mbar_expect_tx(full + slot, (uint32_t)kChunkBytes);
@@ -664,7 +679,7 @@ static size_t s1t_smem_bytes(int NKH, int A, int nchunks) {
 
 // Fills in cta_begin / cta_per_vtile (time tiles of a VFO tile are split between CTAs so that every SM gets
 // about the same number of MMA cycles) and launches one persistent grid for all groups.
-cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
+cudaError_t launch_s1t(Launcher& L, int sid, S1TArgs& a, int num_sms) {
     if (a.ngroups <= 0) return cudaSuccess;
     const int NKH = a.pl.D >> 5;
     if (NKH != 1 && NKH != 2) return cudaErrorInvalidValue;
@@ -720,9 +735,9 @@ cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st) {
     a.nchunks = nch;
     const size_t smem = s1t_smem_bytes(NKH, maxA, nch);
     if (cudaError_t e = ensure_dynamic_smem(NKH == 1 ? (const void*)s1t_kernel<1> : (const void*)s1t_kernel<2>, smem); e != cudaSuccess) return e;
-    if (NKH == 1) s1t_kernel<1><<<ctas, kThreads, smem, st>>>(a);
-    else s1t_kernel<2><<<ctas, kThreads, smem, st>>>(a);
-    return cudaGetLastError();
+    const S1TArgs* d = L.push(a);
+    if (!d) return cudaErrorMemoryAllocation;
+    return L.kernel(sid, NKH == 1 ? (const void*)s1t_kernel<1> : (const void*)s1t_kernel<2>, dim3((unsigned)ctas), dim3(kThreads), smem, d);
 }
 
 } // namespace sdrpp

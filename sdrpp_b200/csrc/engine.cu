@@ -14,7 +14,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <mutex>
 #include <set>
@@ -279,6 +281,8 @@ struct ResultSet {
 using namespace sdrpp;
 
 constexpr int kSets = 5; // result sets / raw staging buffers / result arenas: blocks the caller may have in flight
+constexpr size_t kDescBytes = 256 * 1024; // per-slot descriptor arena (per-block kernel arguments)
+constexpr size_t kMaxGraphs = 96;         // instantiated graphs kept per kind
 
 struct sdrpp_cuda_frontend {
     int device = 0;
@@ -371,6 +375,24 @@ struct sdrpp_cuda_frontend {
     S1TPlanes tc_planes[2] = {};
     bool planes_skipped[2] = { false, false }; // a block went by without refreshing the planes (FP32-only mode)
     long long s1t_launches = 0;
+
+    // command list of the block being planned, per-slot descriptors, instantiated graphs (launcher.h)
+    Launcher L;
+    unsigned char* h_desc[kSets] = { nullptr };   // pinned
+    unsigned char* d_desc[kSets] = { nullptr };
+    cudaStream_t st_desc = nullptr;               // descriptor uploads
+    cudaEvent_t ev_desc = nullptr;
+    bool run_replayable[GRAPH_KINDS] = { true, true, true };
+    bool graphs_on = true;                        // SDRPP_GRAPHS=0: every block command by command
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; std::vector<unsigned char> sig; };
+    std::unordered_map<uint64_t, GraphEntry> gcache[GRAPH_KINDS];
+    std::unordered_map<uint64_t, int> gseen[GRAPH_KINDS];
+    long long graph_replays = 0, graph_captures = 0, direct_runs = 0, capture_us = 0;
+    cudaEvent_t ev_fftk = nullptr;                // join of the spectrum branch inside the stage-1 graph (fft_order 0)
+    // Where the spectrum kernels of a block run (SDRPP_FFT_ORDER): 0 = a branch of the stage-1 graph, joined at its end;
+    // 1 = a graph of their own on the spectrum stream behind stage 1 (beside the tail); 2 = a graph of their own right
+    // behind ingest (ingest launched directly, beside the fp16 split and stage 1: the stream topology of round 1).
+    int fft_order = 0;
 
     // profiling
     bool profiling = false;
@@ -485,7 +507,7 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, upload_sync(fe->d_window, w.data(), sizeof(float) * fe->nz));
     int rows = fe->cfg.max_fft_rows > 0 ? fe->cfg.max_fft_rows : (int)(fe->cfg.max_block / interval + 2);
     fe->rows_cap = rows;
-    FE_TRY(fe, dev_alloc(&fe->d_rows, (size_t)rows * N, false));
+    FE_TRY(fe, dev_alloc(&fe->d_rows, (size_t)2 * rows * N, false));   // one set of rows per block parity: the copy of block i runs beside the spectrum of block i+1
     if (N1 > 1) {
         // frames per launch group: keep the four-step intermediate within ~32 MB so it stays in L2
         fe->inter_frames = std::max(1, std::min(rows, (int)((32u << 20) / ((size_t)N * 8))));
@@ -798,16 +820,115 @@ static void advance_decim(int& offset, int D, int count, int* nout) {
     *nout = n;
 }
 
+
+// ---- execution of a planned block (launcher.h) ---------------------------------------------------------------------
+static uint64_t fnv1a(const unsigned char* p, size_t n) {
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Commands [i, j) carry the same graph tag. Replay the instantiated graph of exactly this sequence if there is one;
+// instantiate one (stream capture of the very commands) when the sequence shows up for the second time; run the commands
+// one by one otherwise. The launch stream is the one the run's commands are ordered on: main for stage 1, tail for the tail.
+static int run_tagged(sdrpp_cuda_frontend* fe, int kind, size_t i, size_t j) {
+    Launcher& L = fe->L;
+    bool replayable = fe->graphs_on && fe->run_replayable[kind];
+    for (size_t k = i; k < j && replayable; k++) if (L.cmds[k].type == Cmd::CALL) replayable = false;
+    if (replayable) {
+        const unsigned char* sig = reinterpret_cast<const unsigned char*>(&L.cmds[i]);
+        const size_t nbytes = (j - i) * sizeof(Cmd);
+        const uint64_t h = fnv1a(sig, nbytes);
+        cudaStream_t origin = L.streams[kind == GRAPH_S1 ? SID_MAIN : kind == GRAPH_FFT ? SID_FFT : SID_TAIL];
+        auto it = fe->gcache[kind].find(h);
+        if (it != fe->gcache[kind].end() && it->second.sig.size() == nbytes && memcmp(it->second.sig.data(), sig, nbytes) == 0) {
+            FE_TRY(fe, cudaGraphLaunch(it->second.exec, origin));
+            fe->graph_replays++;
+            return SDRPP_OK;
+        }
+        if (it == fe->gcache[kind].end() && ++fe->gseen[kind][h] >= 2 && fe->gcache[kind].size() < kMaxGraphs) {
+            cudaGraph_t graph = nullptr;
+            const auto t0 = std::chrono::steady_clock::now();
+            FE_TRY(fe, cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e = cudaSuccess;
+            for (size_t k = i; k < j && e == cudaSuccess; k++) e = L.exec(L.cmds[k]);
+            const cudaError_t e2 = cudaStreamEndCapture(origin, &graph);
+            if (e == cudaSuccess) e = e2;
+            sdrpp_cuda_frontend::GraphEntry ge;
+            if (e == cudaSuccess) e = cudaGraphInstantiate(&ge.exec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (e != cudaSuccess) {
+                // not capturable after all: remember not to try again and run the commands directly
+                cudaGetLastError();
+                fe->gseen[kind][h] = -(1 << 30);
+            } else {
+                ge.sig.assign(sig, sig + nbytes);
+                fe->capture_us += (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+                FE_TRY(fe, cudaGraphLaunch(ge.exec, origin));
+                fe->gcache[kind].emplace(h, std::move(ge));
+                fe->gseen[kind].erase(h);
+                fe->graph_captures++;
+                return SDRPP_OK;
+            }
+        }
+        if (fe->gseen[kind].size() > 4096) fe->gseen[kind].clear();
+    }
+    for (size_t k = i; k < j; k++) FE_TRY(fe, L.exec(L.cmds[k]));
+    fe->direct_runs++;
+    return SDRPP_OK;
+}
+
+static int execute_block(sdrpp_cuda_frontend* fe) {
+    Launcher& L = fe->L;
+    if (L.desc_used > L.desc_cap) return fail(SDRPP_ERR_STATE, "block descriptor overflow");
+    // The per-block descriptor travels on a stream of its own, off the block's critical path: the slot's previous block is
+    // done (submit waited for it), so the copy needs no ordering against kernels and is over long before the main stream gets
+    // to this block. As the first node of the stage-1 graph it cost ~6 us per step (copy latency in front of ingest).
+    if (L.desc_used > 0) {
+        FE_TRY(fe, cudaMemcpyAsync(L.d_desc, L.h_desc, (L.desc_used + 255) & ~(size_t)255, cudaMemcpyHostToDevice, fe->st_desc));
+        FE_TRY(fe, cudaEventRecord(fe->ev_desc, fe->st_desc));
+        FE_TRY(fe, cudaStreamWaitEvent(L.streams[SID_MAIN], fe->ev_desc, 0));
+    }
+    const size_t n = L.cmds.size();
+    size_t i = 0;
+    while (i < n) {
+        const int kind = L.cmds[i].graph;
+        if (kind == GRAPH_NONE) { FE_TRY(fe, L.exec(L.cmds[i])); i++; continue; }
+        size_t j = i;
+        while (j < n && L.cmds[j].graph == kind) j++;
+        const int rc = run_tagged(fe, kind, i, j);
+        if (rc != SDRPP_OK) return rc;
+        i = j;
+    }
+    L.deferred = false;
+    return SDRPP_OK;
+}
+
 static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int count, ResultSet& rs, float scale = 1.0f) {
-    cudaStream_t st = fe->st;
     const bool prof = fe->profiling;
     debug_stale("process_block entry");
-    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[0], st));
+    // PLAN: every command of the block goes into the launcher's list (launcher.h); execute_block() at the end runs it,
+    // as instantiated graphs where the same sequence has been seen before. Profiling serialises everything on the main stream.
+    Launcher& L = fe->L;
+    const int slot_d = (int)(&rs - fe->rs);
+    L.begin_block(fe->h_desc[slot_d], fe->d_desc[slot_d], kDescBytes);
+    L.deferred = true;
+    fe->run_replayable[GRAPH_S1] = fe->run_replayable[GRAPH_TAIL] = fe->run_replayable[GRAPH_FFT] = true;
+    const int fft_order = prof ? 0 : fe->fft_order;
+    const long long kernels0 = L.kernels;
+    const int st = SID_MAIN;
+    if (prof) FE_TRY(fe, L.record(st, fe->pev[0]));
     // The spectrum is the one reader of the ring that is not ordered on `st`: before block i overwrites ring samples,
     // the spectrum work of block i-2 must be done. Frames of block i-1 may still be in flight; they reach back at most
     // nz + max_block samples from the end of block i-1, so a ring of nz + 3*max_block samples (what create() sizes and
     // configure_fft checks) can never be overwritten under a frame that is still being read.
-    if (!prof && fe->cfg.fft_size > 0 && fe->ev_fft_valid[fe->blk & 1]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_fft[fe->blk & 1], 0));
+    if (!prof && fe->cfg.fft_size > 0 && fe->ev_fft_valid[fe->blk & 1]) FE_TRY(fe, L.wait(st, fe->ev_fft[fe->blk & 1]));
+
+    const int par = (int)(fe->blk & 1);
+    if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, L.wait(st, fe->ev_tail[par])); // stage-1 region `par` was last read by the tail of block i-2
+
+    // ---- GRAPH_S1: ingest, [spectrum kernels (forked),] fp16 split, stage 1 (the descriptor is uploaded by execute_block) --
+    L.cur_graph = (prof || fft_order == 2) ? GRAPH_NONE : GRAPH_S1;
 
     // ---- pre-processing chain: [decim] -> [dc block] -> [conjugate] -> ring (iq_frontend.cpp:30-37)
     const RingRef ring{ fe->ring, fe->ring_mask };
@@ -816,15 +937,15 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     const bool dc = fe->cfg.dc_blocking != 0;
     int n = count;
     if (fe->fe_stages.empty() && !dc) {
-        FE_TRY(fe, launch_ingest(fmt, d_in, count, ring, wpos, conj, st, scale)); fe->launches++;
+        FE_TRY(fe, launch_ingest(L, st, fmt, d_in, count, ring, wpos, conj, scale));
     } else {
         const RingRef lin_dc{ fe->dc_in, 0xFFFFFFFFu };
         if (fe->fe_stages.empty()) {
-            FE_TRY(fe, launch_ingest(fmt, d_in, count, lin_dc, 0, false, st, scale)); fe->launches++;
+            FE_TRY(fe, launch_ingest(L, st, fmt, d_in, count, lin_dc, 0, false, scale));
         } else {
             const size_t ns = fe->fe_stages.size();
             RingRef first{ fe->fe_buf[0], 0xFFFFFFFFu };
-            FE_TRY(fe, launch_ingest(fmt, d_in, count, first, (uint32_t)(fe->fe_stages[0].ntaps - 1), false, st, scale)); fe->launches++;
+            FE_TRY(fe, launch_ingest(L, st, fmt, d_in, count, first, (uint32_t)(fe->fe_stages[0].ntaps - 1), false, scale));
             for (size_t s = 0; s < ns; s++) {
                 const DecimStage& ds = fe->fe_stages[s];
                 int off = fe->fe_offset[s], nout = 0;
@@ -835,8 +956,16 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 if (!last) { dst = RingRef{ fe->fe_buf[s + 1], 0xFFFFFFFFu }; pos = (uint32_t)(fe->fe_stages[s + 1].ntaps - 1); }
                 else if (dc) { dst = lin_dc; pos = 0; }
                 else { dst = ring; pos = wpos; cj = conj; }
-                FE_TRY(fe, launch_decim_stage(fe->fe_buf[s], fe->fe_taps[s], ds.ntaps, ds.decimation, off0, nout, dst, pos, cj, st));
-                FE_TRY(fe, launch_shift_history(fe->fe_buf[s], ds.ntaps - 1, n, st));
+                // the front-end decimator and the DC blocker keep their by-value launches: a block that runs them is executed
+                // command by command (Launcher::call), never replayed as a graph
+                {
+                    const float2* buf = fe->fe_buf[s]; const float* tp = fe->fe_taps[s];
+                    const int T = ds.ntaps, D = ds.decimation, nin = n;
+                    FE_TRY(fe, L.call(st, [=](cudaStream_t cs) {
+                        cudaError_t e = launch_decim_stage(buf, tp, T, D, off0, nout, dst, pos, cj, cs);
+                        return e != cudaSuccess ? e : launch_shift_history(const_cast<float2*>(buf), T - 1, nin, cs);
+                    }));
+                }
                 fe->launches += (nout > 0 ? 1 : 0) + ((ds.ntaps > 1 && n > 0) ? 1 : 0);
                 fe->fe_offset[s] = off;
                 n = nout;
@@ -844,27 +973,46 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         if (dc) {
             const float rate = (float)(50.0 / fe->eff_sr); // IQFrontEnd::genDCBlockRate, iq_frontend.h:52-54
-            FE_TRY(fe, launch_dc_block(fe->dc_in, n, rate, fe->dc_state, fe->dc_scratch, ring, wpos, conj, st, &fe->launches));
+            {
+                float2* din = fe->dc_in; float2* dst8 = fe->dc_state; float2* dsc = fe->dc_scratch; const int nn = n;
+                FE_TRY(fe, L.call(st, [=](cudaStream_t cs) { long long dummy = 0; return launch_dc_block(din, nn, rate, dst8, dsc, ring, wpos, conj, cs, &dummy); }));
+                fe->launches += 3;
+            }
         }
     }
     const int64_t abs_block = fe->abs_pos;
     fe->abs_pos += n;
     fe->last_count = n;
-    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[1], st));
+    if (prof) FE_TRY(fe, L.record(st, fe->pev[1]));
     // Three consumers of the ring run concurrently (the reference's Splitter fan-out): the spectrum on st_fft,
     // stage 1 on st, and the tail of the PREVIOUS block on st_tail. Profiling serialises everything on st so
     // that per-family CUDA-event times are those of the kernels alone.
-    cudaStream_t sf = prof ? st : fe->st_fft;
-    cudaStream_t stl = prof ? st : fe->st_tail;
-    const int par = (int)(fe->blk & 1);
+    const int sf = prof ? st : SID_FFT;
+    const int stl = prof ? st : SID_TAIL;
     const int aset = (int)(&rs - fe->rs); // result set (and result arena) of this block
-    if (!prof) {
-        FE_TRY(fe, cudaEventRecord(fe->ev_ingest, st));
-        FE_TRY(fe, cudaStreamWaitEvent(sf, fe->ev_ingest, 0));
+    if (!prof && fft_order != 1) {
+        FE_TRY(fe, L.record(st, fe->ev_ingest));
+        FE_TRY(fe, L.wait(sf, fe->ev_ingest));
     }
+    // fft_order 1 / 2: the spectrum commands go to a list of their own (a GRAPH_FFT run on the spectrum stream), spliced in
+    // behind stage 1 (1) or right here (2)
+    std::vector<Cmd> main_cmds;
+    const int graph_before_fft = L.cur_graph;
+    if (fft_order != 0) { main_cmds.swap(L.cmds); L.cur_graph = GRAPH_FFT; }
 
     // ---- spectrum frames completed by this block (reshaper.h:102-129 keep/skip + handler) --------
+    // Their kernels are a branch of the stage-1 graph; the device-to-host copies of the rows follow the graph (a copy
+    // inside it would hold the next block's stage 1 back until 4 MB per row have crossed the link).
+    struct PendingCopy { void* dst; const void* src; size_t bytes; };
+    std::vector<PendingCopy> fft_copies;
+    auto fft_copy = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (prof) return L.memcpy_async(st, dst, src, bytes, cudaMemcpyDeviceToHost);
+        if (fft_order != 0) { const int g = L.cur_graph; L.cur_graph = GRAPH_NONE; const cudaError_t e = L.memcpy_async(sf, dst, src, bytes, cudaMemcpyDeviceToHost); L.cur_graph = g; return e; }
+        fft_copies.push_back(PendingCopy{ dst, src, bytes });
+        return cudaSuccess;
+    };
     rs.nrows = 0;
+    float* const rows_dev = fe->d_rows ? fe->d_rows + (size_t)par * fe->rows_cap * fe->cfg.fft_size : nullptr;
     if (fe->cfg.fft_size > 0) {
         const int N = fe->cfg.fft_size;
         const int64_t interval = (int64_t)fe->nz + fe->skip;
@@ -879,24 +1027,25 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             a.start = (uint32_t)((uint64_t)(first + (int64_t)f0 * interval) & fe->ring_mask);
             a.frame_stride = (uint32_t)interval;
             a.nz = fe->nz; a.window = fe->d_window; a.inter = fe->d_inter;
-            a.rows = fe->d_rows + (size_t)f0 * N; a.X = nullptr;
+            a.rows = rows_dev + (size_t)f0 * N; a.X = nullptr;
             a.frames = std::min(fe->inter_frames, frames - f0);
-            FE_TRY(fe, launch_spectrum(N, a, sf, &fe->launches));
+            FE_TRY(fe, launch_spectrum(L, sf, N, a, nullptr));
         }
         rs.nrows = frames;
     }
+    // zoom / display state / level read-out write buffers that the copies behind the graph read (not double-buffered): such a
+    // block runs command by command, where the spectrum stream orders kernels and copies
+    if (fft_order == 0 && rs.nrows > 0 && (fe->zoom_out > 0 || fe->nsig > 0 || fe->sig_dirty)) fe->run_replayable[GRAPH_S1] = false;
     if (rs.nrows > 0 && fe->zoom_out > 0) {
-        FE_TRY(fe, launch_fft_zoom(fe->d_rows, fe->cfg.fft_size, rs.nrows, fe->d_zoom_idx, fe->zoom_out, fe->zoom_ranged, fe->d_zoom, sf));
-        fe->launches++;
+        FE_TRY(fe, launch_fft_zoom(L, sf, rows_dev, fe->cfg.fft_size, rs.nrows, fe->d_zoom_idx, fe->zoom_out, fe->zoom_ranged, fe->d_zoom));
         if (fe->disp_smoothing || fe->disp_hold) {
             const int W = fe->zoom_out;
-            FE_TRY(fe, launch_fft_display(fe->d_zoom, W, rs.nrows, fe->disp_smoothing, fe->disp_alpha, fe->d_disp, fe->disp_hold, fe->disp_hold_speed,
-                                          fe->d_disp + W, fe->d_disp + 2 * W, sf));
-            fe->launches++;
-            if (fe->readback && fe->disp_hold) FE_TRY(fe, cudaMemcpyAsync(rs.hold, fe->d_disp + W, (size_t)W * sizeof(float), cudaMemcpyDeviceToHost, sf));
+            FE_TRY(fe, launch_fft_display(L, sf, fe->d_zoom, W, rs.nrows, fe->disp_smoothing, fe->disp_alpha, fe->d_disp, fe->disp_hold, fe->disp_hold_speed,
+                                          fe->d_disp + W, fe->d_disp + 2 * W));
+            if (fe->readback && fe->disp_hold) FE_TRY(fe, fft_copy(rs.hold, fe->d_disp + W, (size_t)W * sizeof(float)));
         }
         if (fe->readback)
-            FE_TRY(fe, cudaMemcpyAsync(rs.zoom, fe->d_zoom, (size_t)rs.nrows * fe->zoom_out * sizeof(float), cudaMemcpyDeviceToHost, sf));
+            FE_TRY(fe, fft_copy(rs.zoom, fe->d_zoom, (size_t)rs.nrows * fe->zoom_out * sizeof(float)));
     }
     rs.nsig = 0;
     rs.sig_done.clear();
@@ -904,25 +1053,33 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         int rc = refresh_signal_info(fe);
         if (rc != SDRPP_OK) return rc;
         if (fe->nsig > 0) {
-            FE_TRY(fe, launch_signal_info(fe->d_rows, fe->cfg.fft_size, rs.nrows, fe->d_sig_bins, fe->nsig, fe->d_sig, sf));
-            fe->launches++;
+            FE_TRY(fe, launch_signal_info(L, sf, rows_dev, fe->cfg.fft_size, rs.nrows, fe->d_sig_bins, fe->nsig, fe->d_sig));
             if (fe->readback)
-                FE_TRY(fe, cudaMemcpyAsync(rs.sig, fe->d_sig, (size_t)rs.nrows * fe->nsig * sizeof(float2), cudaMemcpyDeviceToHost, sf));
+                FE_TRY(fe, fft_copy(rs.sig, fe->d_sig, (size_t)rs.nrows * fe->nsig * sizeof(float2)));
             rs.nsig = fe->nsig;
             rs.sig_slot.assign(fe->vfos.size(), -1);
             for (size_t id = 0; id < fe->vfos.size(); id++) if (fe->vfos[id].alive && fe->vfos[id].sig_on) rs.sig_slot[id] = fe->vfos[id].sig_slot;
         }
     }
     if (fe->readback && rs.nrows > 0 && (fe->zoom_keep_raw || fe->zoom_out <= 0))
-        FE_TRY(fe, cudaMemcpyAsync(rs.rows, fe->d_rows, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float), cudaMemcpyDeviceToHost, sf));
-    if (prof) { FE_TRY(fe, cudaEventRecord(fe->pev[2], st)); fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false; }
-    else { FE_TRY(fe, cudaEventRecord(fe->ev_fft[par], sf)); fe->ev_fft_valid[par] = true; }
+        FE_TRY(fe, fft_copy(rs.rows, rows_dev, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float)));
+    if (prof) { FE_TRY(fe, L.record(st, fe->pev[2])); fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false; }
+    else if (fft_order == 0) FE_TRY(fe, L.record(sf, fe->ev_fftk));   // the spectrum branch joins the main stream again at the end of the stage-1 graph
+    std::vector<Cmd> fft_cmds;
+    if (fft_order != 0) {
+        L.cur_graph = GRAPH_NONE;
+        FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
+        fe->ev_fft_valid[par] = true;
+        fft_cmds.swap(L.cmds);
+        L.cmds.swap(main_cmds);
+        if (fft_order == 2) { L.cmds.insert(L.cmds.end(), fft_cmds.begin(), fft_cmds.end()); fft_cmds.clear(); L.cur_graph = GRAPH_S1; }
+        else L.cur_graph = graph_before_fft;
+    }
 
     // ---- channelizer ----------------------------------------------------------------------------
     debug_stale("before rebuild_layout");
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
     debug_stale("after rebuild_layout");
-    if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_tail[par], 0)); // region `par` was last read by the tail of block i-2
     int total_vfos_all = 0;
     for (const Group& g : fe->groups) total_vfos_all += (int)g.members.size();
     std::vector<TailArgs> tails, tails_fast;
@@ -977,14 +1134,13 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 fe->planes_skipped[pi] = false;
             }
             tc_args[pi].pl = pl;
-            FE_TRY(fe, launch_s1t_split(ring, pl, split_from, abs_block + n, st));
-            fe->launches++;
+            FE_TRY(fe, launch_s1t_split(L, st, ring, pl, split_from, abs_block + n));
         }
     }
     auto flush_tc = [&](int pi) -> int {
         if (tc_args[pi].ngroups == 0) return SDRPP_OK;
-        FE_TRY(fe, launch_s1t(tc_args[pi], fe->num_sms, st));
-        fe->launches++; fe->s1t_launches++;
+        FE_TRY(fe, launch_s1t(L, st, tc_args[pi], fe->num_sms));
+        fe->s1t_launches++;
         tc_args[pi].ngroups = 0;
         return SDRPP_OK;
     };
@@ -994,11 +1150,11 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     // tensor-core launch on `st`): saves three runtime calls per block.
     const bool fork = fe->groups.size() > 1;
     bool forked = false;
-    if (fork) FE_TRY(fe, cudaEventRecord(fe->ev_s1_fork, st));
+    if (fork) FE_TRY(fe, L.record(st, fe->ev_s1_fork));
     int s1_launch = 0;
     for (Group& g : fe->groups) {
         const VfoPlan& p = *g.plan;
-        cudaStream_t s1s = (fork && (s1_launch & 1)) ? fe->st_s1b : st;
+        const int s1s = (fork && (s1_launch & 1) && !prof) ? SID_S1B : st;
         Stage1Args a{};
         a.ring = ring;
         a.nvfo = (int)g.members.size();
@@ -1024,13 +1180,12 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 const int A = s1t_A(p.s1_T, p.s1_D, shift);
                 const size_t need = s1t_b_bytes(A, p.s1_D, a.nvfo);
                 if (need > g.b_cap) {
-                    if (g.d_B) { FE_TRY(fe, cudaStreamSynchronize(st)); cudaFree(g.d_B); g.d_B = nullptr; }
+                    if (g.d_B) { FE_TRY(fe, cudaStreamSynchronize(fe->st)); cudaFree(g.d_B); g.d_B = nullptr; }
                     FE_TRY(fe, dev_alloc(&g.d_B, need, false));
                     g.b_cap = need; g.tc_dirty = true;
                 }
                 if (g.tc_dirty || shift != g.tc_shift || A != g.tc_A) {
-                    FE_TRY(fe, launch_s1t_build_b(g.d_B, a.vfos, a.nvfo, p.d_s1_taps, p.s1_T, p.s1_D, shift, A, p.tc_escale, st));
-                    fe->launches++;
+                    FE_TRY(fe, launch_s1t_build_b(L, st, g.d_B, a.vfos, a.nvfo, p.d_s1_taps, p.s1_T, p.s1_D, shift, A, p.tc_escale));
                     g.tc_shift = shift; g.tc_A = A; g.tc_dirty = false;
                 }
                 if (tc_args[pi].ngroups == kS1TMaxGroups) { int rc = flush_tc(pi); if (rc != SDRPP_OK) return rc; }
@@ -1051,17 +1206,17 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             a.T = p.s1_T + pad;
             a.tap_off = p.s1_tap_off + pad * p.s1_A * p.s1_D;
             a.ring_first = (uint32_t)((uint64_t)a.abs_first & fe->ring_mask);
-            if (s1s != st && !forked) { FE_TRY(fe, cudaStreamWaitEvent(fe->st_s1b, fe->ev_s1_fork, 0)); forked = true; }
-            FE_TRY(fe, launch_stage1(a, s1s));
+            if (s1s != st && !forked) { FE_TRY(fe, L.wait(SID_S1B, fe->ev_s1_fork)); forked = true; }
+            FE_TRY(fe, launch_stage1(L, s1s, a));
         } else {
             nprev = n;
             a.D = 1; a.T = 1; a.A = 1; a.tap_off = 0; a.M = n; a.G = nullptr;
             a.abs_first = abs_block;
             a.ring_first = wpos;
-            if (s1s != st && !forked) { FE_TRY(fe, cudaStreamWaitEvent(fe->st_s1b, fe->ev_s1_fork, 0)); forked = true; }
-            FE_TRY(fe, launch_mix_only(a, s1s));
+            if (s1s != st && !forked) { FE_TRY(fe, L.wait(SID_S1B, fe->ev_s1_fork)); forked = true; }
+            FE_TRY(fe, launch_mix_only(L, s1s, a));
         }
-        if (nprev > 0) { fe->launches++; s1_launch++; }
+        if (nprev > 0) s1_launch++;
     stage1_done:
 
         TailGroup tg{};
@@ -1119,13 +1274,28 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     }
     for (int pi = 0; pi < 2; pi++) { int rc = flush_tc(pi); if (rc != SDRPP_OK) return rc; }
     if (forked) {
-        FE_TRY(fe, cudaEventRecord(fe->ev_s1_join, fe->st_s1b));
-        FE_TRY(fe, cudaStreamWaitEvent(st, fe->ev_s1_join, 0));
+        FE_TRY(fe, L.record(SID_S1B, fe->ev_s1_join));
+        FE_TRY(fe, L.wait(st, fe->ev_s1_join));
     }
-    if (prof) FE_TRY(fe, cudaEventRecord(fe->pev[3], st));
+    if (prof) FE_TRY(fe, L.record(st, fe->pev[3]));
     else {
-        FE_TRY(fe, cudaEventRecord(fe->ev_s1, st));
-        FE_TRY(fe, cudaStreamWaitEvent(stl, fe->ev_s1, 0));
+        if (fft_order == 0) FE_TRY(fe, L.wait(st, fe->ev_fftk));        // join of the spectrum branch: last node of the stage-1 graph
+        L.cur_graph = GRAPH_NONE;
+        FE_TRY(fe, L.record(st, fe->ev_s1));
+        if (fft_order == 0) {
+            // rows to the host behind the graph
+            FE_TRY(fe, L.wait(sf, fe->ev_s1));
+            for (const PendingCopy& c : fft_copies) FE_TRY(fe, L.memcpy_async(sf, c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost));
+            FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
+            fe->ev_fft_valid[par] = true;
+        }
+        FE_TRY(fe, L.wait(stl, fe->ev_s1));
+        if (fft_order == 1) {
+            // the spectrum of this block runs behind its stage 1, beside its tail
+            FE_TRY(fe, L.wait(sf, fe->ev_s1));
+            L.cmds.insert(L.cmds.end(), fft_cmds.begin(), fft_cmds.end());
+        }
+        L.cur_graph = GRAPH_TAIL;
     }
     for (int pass = 0; pass < 2; pass++) {
         std::vector<TailArgs>& lst = pass ? tails : tails_fast;
@@ -1133,9 +1303,11 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         for (size_t i = 0; i < lst.size(); i++) {
             bool wide = false;
             for (int k = 0; k < lst[i].ngroups; k++) wide = wide || lst[i].g[k].s_begin == 1;
-            if (wide && tot[i] > 0) { FE_TRY(fe, launch_tail_stage0_wide(lst[i], tot[i], stl)); fe->launches++; }
-            FE_TRY(fe, pass ? launch_tail(lst[i], tot[i], stl) : launch_tail_fast(lst[i], tot[i], stl));
-            if (tot[i] > 0) fe->launches++;
+            if (tot[i] <= 0) continue;
+            const TailArgs* d_args = L.push(lst[i]);
+            if (!d_args) return fail(SDRPP_ERR_STATE, "block descriptor overflow");
+            if (wide) FE_TRY(fe, launch_tail_stage0_wide(L, stl, lst[i], d_args, tot[i]));
+            FE_TRY(fe, pass ? launch_tail(L, stl, lst[i], d_args, tot[i]) : launch_tail_fast(L, stl, lst[i], d_args, tot[i]));
         }
     }
     // the post-detector pass below walks every group, whichever tail kernel it took
@@ -1154,10 +1326,11 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             pa.post = fe->d_post; pa.arena_iq = fe->d_arena_iq + (size_t)aset * fe->arena_cap; pa.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
             pa.arena_audio = fe->d_arena_audio + (size_t)aset * fe->arena_cap;
             pa.arena_audio_r = fe->d_arena_audio_r + (size_t)aset * fe->arena_cap;
-            if (any && tail_totals[i] > 0) { FE_TRY(fe, launch_post(pa, tail_totals[i], stl)); fe->launches++; }
+            if (any && tail_totals[i] > 0) FE_TRY(fe, launch_post(L, stl, pa, tail_totals[i]));
         }
     }
-    if (prof) { FE_TRY(fe, cudaEventRecord(fe->pev[4], st)); fe->pev_valid = true; }
+    L.cur_graph = GRAPH_NONE;
+    if (prof) { FE_TRY(fe, L.record(st, fe->pev[4])); fe->pev_valid = true; }
 
     // ---- results to pinned host memory --------------------------------------------------------------
     rs.counts.assign(fe->vfos.size(), 0);
@@ -1175,25 +1348,30 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     // The copies run on their own stream behind the tail, so the tail of the next block does not queue up behind
     // them; the pinned result set and the arena of this parity are free again once the caller has waited for
     // block i (it must, before submitting block i+2).
-    cudaStream_t sd = prof ? st : fe->st_d2h;
+    const int sd = prof ? st : SID_D2H;
     if (!prof) {
-        FE_TRY(fe, cudaEventRecord(fe->ev_tail[par], stl));
+        FE_TRY(fe, L.record(stl, fe->ev_tail[par]));
         fe->ev_tail_valid[par] = true;
-        FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_tail[par], 0));
+        FE_TRY(fe, L.wait(sd, fe->ev_tail[par]));
     } else {
         fe->ev_tail_valid[0] = fe->ev_tail_valid[1] = false;  // everything ran in order on st
     }
     if (fe->readback && fe->arena_used > 0) {
         const size_t ao = (size_t)aset * fe->arena_cap;
-        FE_TRY(fe, cudaMemcpyAsync(rs.iq, fe->d_arena_iq + ao, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost, sd));
-        FE_TRY(fe, cudaMemcpyAsync(rs.demod, fe->d_arena_demod + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
+        FE_TRY(fe, L.memcpy_async(sd, rs.iq, fe->d_arena_iq + ao, fe->arena_used * sizeof(float2), cudaMemcpyDeviceToHost));
+        FE_TRY(fe, L.memcpy_async(sd, rs.demod, fe->d_arena_demod + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost));
         if (fe->post_active > 0)
-            FE_TRY(fe, cudaMemcpyAsync(rs.audio, fe->d_arena_audio + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
+            FE_TRY(fe, L.memcpy_async(sd, rs.audio, fe->d_arena_audio + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost));
         if (fe->post_stereo > 0)
-            FE_TRY(fe, cudaMemcpyAsync(rs.audio_r, fe->d_arena_audio_r + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost, sd));
+            FE_TRY(fe, L.memcpy_async(sd, rs.audio_r, fe->d_arena_audio_r + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost));
     }
-    if (!prof) FE_TRY(fe, cudaStreamWaitEvent(sd, fe->ev_fft[par], 0)); // the block is done when its rows are on the host too
-    FE_TRY(fe, cudaEventRecord(rs.done, sd));
+    if (!prof) FE_TRY(fe, L.wait(sd, fe->ev_fft[par])); // the block is done when its rows are on the host too
+    FE_TRY(fe, L.record(sd, rs.done));
+    fe->launches += L.kernels - kernels0;
+    {
+        const int rc = execute_block(fe);
+        if (rc != SDRPP_OK) return rc;
+    }
     rs.pending = true;
     fe->blk++;
     return SDRPP_OK;
@@ -1286,8 +1464,13 @@ struct OneShot {
     void* d_w = nullptr; size_t cap_w = 0;   // spectrum_device: cached window (natural order)
     std::vector<float> win_host; int win_n = 0;
     int device = -1;
+    // immediate-mode launcher of the one-shot operations: pageable host copy of the argument records, device twin used as a ring
+    Launcher L;
+    std::vector<unsigned char> h_desc;
+    unsigned char* d_desc = nullptr;
 };
 static OneShot g_os;
+constexpr size_t kOsDescBytes = 64 * 1024;
 static thread_local int g_device = 0;
 
 static cudaError_t os_reserve(void** p, size_t* cap, size_t bytes) {
@@ -1305,10 +1488,24 @@ static int os_prepare() {
         g_os.d_a = g_os.d_b = g_os.d_c = g_os.d_d = g_os.d_w = nullptr;
         g_os.cap_a = g_os.cap_b = g_os.cap_c = g_os.cap_d = g_os.cap_w = 0;
         g_os.win_host.clear(); g_os.win_n = 0;
+        g_os.d_desc = nullptr;
         g_os.device = g_device;
     }
     if (!g_os.st) SDRPP_CUDA_TRY(cudaStreamCreateWithFlags(&g_os.st, cudaStreamNonBlocking));
+    if (!g_os.d_desc) {
+        SDRPP_CUDA_TRY(cudaMalloc((void**)&g_os.d_desc, kOsDescBytes));
+        g_os.h_desc.assign(kOsDescBytes, 0);
+        g_os.L.begin_block(g_os.h_desc.data(), g_os.d_desc, kOsDescBytes);
+    }
     return SDRPP_OK;
+}
+// launcher that runs every command at once on `st`; argument records go round the device ring (a record is overwritten
+// thousands of calls later, long after the kernel that read it)
+static Launcher& os_launcher(cudaStream_t st) {
+    Launcher& L = g_os.L;
+    L.immediate(st);
+    if (L.desc_used + 8192 > L.desc_cap) L.desc_used = L.desc_flushed = 0;
+    return L;
 }
 
 } // namespace sdrpp
@@ -1399,7 +1596,7 @@ int sdrpp_cuda_convert(int fmt, const void* in, int nsamples, sdrpp_cf32* out) {
     SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, inb));
     SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, outb));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, in, inb, cudaMemcpyHostToDevice, g_os.st));
-    SDRPP_CUDA_TRY(launch_ingest(fmt, g_os.d_a, nsamples, RingRef{ (float2*)g_os.d_b, 0xFFFFFFFFu }, 0, false, g_os.st));
+    SDRPP_CUDA_TRY(launch_ingest(os_launcher(g_os.st), SID_MAIN, fmt, g_os.d_a, nsamples, RingRef{ (float2*)g_os.d_b, 0xFFFFFFFFu }, 0, false));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_b, outb, cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
     return SDRPP_OK;
@@ -1434,7 +1631,7 @@ int sdrpp_cuda_pcm_decompress(const void* packet, int nbytes, sdrpp_cf32* out) {
     SDRPP_CUDA_TRY(os_reserve(&g_os.d_a, &g_os.cap_a, inb));
     SDRPP_CUDA_TRY(os_reserve(&g_os.d_b, &g_os.cap_b, outb));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, (const uint8_t*)packet + 8, inb, cudaMemcpyHostToDevice, g_os.st));
-    SDRPP_CUDA_TRY(launch_ingest(h.fmt, g_os.d_a, h.nsamples, RingRef{ (float2*)g_os.d_b, 0xFFFFFFFFu }, 0, false, g_os.st, h.divisor));
+    SDRPP_CUDA_TRY(launch_ingest(os_launcher(g_os.st), SID_MAIN, h.fmt, g_os.d_a, h.nsamples, RingRef{ (float2*)g_os.d_b, 0xFFFFFFFFu }, 0, false, h.divisor));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_b, outb, cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
     return h.nsamples;
@@ -1491,14 +1688,14 @@ int sdrpp_cuda_spectrum(int N, int nz, int fmt, const void* frame, const float* 
     float* d_win = (float*)((char*)g_os.d_b + woff);
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, frame, inb, cudaMemcpyHostToDevice, g_os.st));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(d_win, window, (size_t)nz * 4, cudaMemcpyHostToDevice, g_os.st));
-    SDRPP_CUDA_TRY(launch_ingest(fmt, g_os.d_a, nz, RingRef{ d_frame, 0xFFFFFFFFu }, 0, false, g_os.st));
+    SDRPP_CUDA_TRY(launch_ingest(os_launcher(g_os.st), SID_MAIN, fmt, g_os.d_a, nz, RingRef{ d_frame, 0xFFFFFFFFu }, 0, false));
     SpectrumArgs a{};
     a.in = d_frame; a.ring_mask = 0xFFFFFFFFu; a.start = 0; a.frame_stride = 0; a.nz = nz; a.window = d_win;
     a.inter = (float2*)g_os.d_c;
     a.rows = row ? (float*)g_os.d_d : nullptr;
     a.X = X ? (float2*)((char*)g_os.d_d + (size_t)N * 4) : nullptr;
     a.frames = 1;
-    SDRPP_CUDA_TRY(launch_spectrum(N, a, g_os.st, nullptr));
+    SDRPP_CUDA_TRY(launch_spectrum(os_launcher(g_os.st), SID_MAIN, N, a, nullptr));
     if (row) SDRPP_CUDA_TRY(cudaMemcpyAsync(row, a.rows, (size_t)N * 4, cudaMemcpyDeviceToHost, g_os.st));
     if (X) SDRPP_CUDA_TRY(cudaMemcpyAsync(X, a.X, (size_t)N * 8, cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
@@ -1537,7 +1734,7 @@ int sdrpp_cuda_spectrum_device(int N, int nz, int frames, long long frame_stride
         a.in = dev_in + (size_t)f0 * (size_t)frame_stride; a.ring_mask = 0xFFFFFFFFu; a.start = 0; a.frame_stride = (uint32_t)frame_stride;
         a.nz = nz; a.window = (const float*)g_os.d_w; a.inter = (float2*)g_os.d_c;
         a.rows = dev_rows + (size_t)f0 * N; a.X = nullptr; a.frames = std::min(group, frames - f0);
-        SDRPP_CUDA_TRY(launch_spectrum(N, a, st, nullptr));
+        SDRPP_CUDA_TRY(launch_spectrum(os_launcher(st), SID_MAIN, N, a, nullptr));
     }
     if (!stream) SDRPP_CUDA_TRY(cudaStreamSynchronize(st));
     return SDRPP_OK;
@@ -1557,7 +1754,7 @@ int sdrpp_cuda_fft_zoom(int N, const float* row, double viewOffset, double viewB
     SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, (size_t)outSize * 4));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, row, (size_t)N * 4, cudaMemcpyHostToDevice, g_os.st));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_b, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, g_os.st));
-    SDRPP_CUDA_TRY(launch_fft_zoom((const float*)g_os.d_a, N, 1, (const int*)g_os.d_b, outSize, ranged, (float*)g_os.d_c, g_os.st));
+    SDRPP_CUDA_TRY(launch_fft_zoom(os_launcher(g_os.st), SID_MAIN, (const float*)g_os.d_a, N, 1, (const int*)g_os.d_b, outSize, ranged, (float*)g_os.d_c));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(out, g_os.d_c, (size_t)outSize * 4, cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
     return SDRPP_OK;
@@ -1580,7 +1777,7 @@ int sdrpp_cuda_signal_info(int N, const float* row, int nvfo, const double* cent
     SDRPP_CUDA_TRY(os_reserve(&g_os.d_c, &g_os.cap_c, (size_t)nvfo * sizeof(float2)));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_a, row, (size_t)N * 4, cudaMemcpyHostToDevice, g_os.st));
     SDRPP_CUDA_TRY(cudaMemcpyAsync(g_os.d_b, bins.data(), (size_t)nvfo * sizeof(int4), cudaMemcpyHostToDevice, g_os.st));
-    SDRPP_CUDA_TRY(launch_signal_info((const float*)g_os.d_a, N, 1, (const int4*)g_os.d_b, nvfo, (float2*)g_os.d_c, g_os.st));
+    SDRPP_CUDA_TRY(launch_signal_info(os_launcher(g_os.st), SID_MAIN, (const float*)g_os.d_a, N, 1, (const int4*)g_os.d_b, nvfo, (float2*)g_os.d_c));
     std::vector<float2> out((size_t)nvfo);
     SDRPP_CUDA_TRY(cudaMemcpyAsync(out.data(), g_os.d_c, (size_t)nvfo * sizeof(float2), cudaMemcpyDeviceToHost, g_os.st));
     SDRPP_CUDA_TRY(cudaStreamSynchronize(g_os.st));
@@ -1636,6 +1833,7 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaStreamCreateWithFlags(&fe->st_tail, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_d2h, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_s1b, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&fe->st_desc, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&fe->st_bcast, cudaStreamNonBlocking) != cudaSuccess) return bail("stream creation failed");
     if (cudaEventCreateWithFlags(&fe->ev_ingest, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1, cudaEventDisableTiming) != cudaSuccess ||
@@ -1644,7 +1842,18 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaEventCreateWithFlags(&fe->ev_s1_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_s1_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+        cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_desc, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_fftk, cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+    fe->L.streams[SID_MAIN] = fe->st; fe->L.streams[SID_FFT] = fe->st_fft; fe->L.streams[SID_TAIL] = fe->st_tail;
+    fe->L.streams[SID_S1B] = fe->st_s1b; fe->L.streams[SID_D2H] = fe->st_d2h;
+    { const char* g = getenv("SDRPP_GRAPHS"); fe->graphs_on = !(g && g[0] == '0'); }
+    { const char* g = getenv("SDRPP_FFT_ORDER"); if (g && g[0] >= '0' && g[0] <= '2') fe->fft_order = g[0] - '0'; }
+    for (int i = 0; i < kSets; i++) {
+        if (cudaMallocHost((void**)&fe->h_desc[i], kDescBytes) != cudaSuccess) return bail("descriptor allocation failed");
+        if (cudaMalloc((void**)&fe->d_desc[i], kDescBytes) != cudaSuccess) return bail("descriptor allocation failed");
+        memset(fe->h_desc[i], 0, kDescBytes);
+    }
     if (dev_alloc(&fe->ring, (size_t)1 << fe->ring_log2) != cudaSuccess) return bail("ring allocation failed");
     fe->raw_cap = (size_t)fe->cfg.max_block * 16; // widest input format: complex f64
     for (int i = 0; i < kSets; i++) {
@@ -1673,6 +1882,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_d2h) cudaStreamSynchronize(fe->st_d2h);
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
     if (fe->st_bcast) cudaStreamSynchronize(fe->st_bcast);
+    if (fe->st_desc) cudaStreamSynchronize(fe->st_desc);
     for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.post_taps2); cudaFree(v.if_state); }
     for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
     for (int i = 0; i < 2; i++) { cudaFree(fe->tc_planes[i].hi); cudaFree(fe->tc_planes[i].lo); cudaFree(fe->tc_planes[i].sinv); }
@@ -1700,6 +1910,11 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->rs[i].sig) cudaFreeHost(fe->rs[i].sig);
     }
     for (int i = 0; i < 5; i++) if (fe->pev[i]) cudaEventDestroy(fe->pev[i]);
+    for (int k = 0; k < GRAPH_KINDS; k++) { for (auto& e : fe->gcache[k]) if (e.second.exec) cudaGraphExecDestroy(e.second.exec); fe->gcache[k].clear(); }
+    for (int i = 0; i < kSets; i++) { if (fe->h_desc[i]) cudaFreeHost(fe->h_desc[i]); if (fe->d_desc[i]) cudaFree(fe->d_desc[i]); }
+    if (fe->ev_fftk) cudaEventDestroy(fe->ev_fftk);
+    if (fe->ev_desc) cudaEventDestroy(fe->ev_desc);
+    if (fe->st_desc) cudaStreamDestroy(fe->st_desc);
     if (fe->st) cudaStreamDestroy(fe->st);
     if (fe->st_copy) cudaStreamDestroy(fe->st_copy);
     if (fe->st_fft) cudaStreamDestroy(fe->st_fft);
@@ -2289,6 +2504,21 @@ int sdrpp_cuda_frontend_set_stage1_mode(sdrpp_cuda_frontend* fe, int mode) {
     return SDRPP_OK;
 }
 void* sdrpp_cuda_frontend_stream(sdrpp_cuda_frontend* fe) { return fe ? (void*)fe->st : nullptr; }
+int sdrpp_cuda_frontend_set_graphs(sdrpp_cuda_frontend* fe, int enabled) {
+    int rc = fe_check(fe);
+    if (rc != SDRPP_OK) return rc;
+    std::lock_guard<std::mutex> api(fe->api_mtx);
+    fe->graphs_on = enabled != 0;
+    return SDRPP_OK;
+}
+
+int sdrpp_cuda_frontend_graph_stats(sdrpp_cuda_frontend* fe, long long* out4) {
+    if (!fe || !out4) return fail(SDRPP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> api(fe->api_mtx);
+    out4[0] = fe->graph_replays; out4[1] = fe->graph_captures; out4[2] = fe->direct_runs; out4[3] = fe->capture_us;
+    return SDRPP_OK;
+}
+
 int sdrpp_cuda_frontend_set_profiling(sdrpp_cuda_frontend* fe, int enabled) {
     int rc = sdrpp_cuda_frontend_drain(fe);
     if (rc != SDRPP_OK) return rc;

@@ -85,7 +85,9 @@ __device__ __forceinline__ void load_table(float2* dst, const float2* __restrict
 // ---------------------------------------------------------------------------------------------
 template <class P, int B>
 __global__ void __launch_bounds__(P::T* B)
-fft_cols_kernel(SpectrumArgs a, SpectrumTables tabs, int N2, int log2N, int log2N2) {
+fft_cols_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N2, int log2N, int log2N2) {
+    const SpectrumArgs a = *ap;   // per-block arguments (launcher descriptor)
+    if ((int)blockIdx.y >= a.frames) return;
     extern __shared__ __align__(16) float2 sm[];
     constexpr int E = P::E, T = P::T, L = P::L;
     float2* tw = sm;              // [L]   exp(-2 pi i j / N1)
@@ -133,7 +135,9 @@ fft_cols_kernel(SpectrumArgs a, SpectrumTables tabs, int N2, int log2N, int log2
 // ---------------------------------------------------------------------------------------------
 template <class P, int B, bool FROM_SAMPLES>
 __global__ void __launch_bounds__(P::T* B)
-fft_rows_kernel(SpectrumArgs a, SpectrumTables tabs, int N1, int log2N) {
+fft_rows_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N1, int log2N) {
+    const SpectrumArgs a = *ap;   // per-block arguments (launcher descriptor)
+    if (!FROM_SAMPLES && (int)blockIdx.y >= a.frames) return;
     extern __shared__ __align__(16) float2 sm[];
     constexpr int E = P::E, T = P::T, L = P::L;
     float2* tw = sm;        // [L] exp(-2 pi i j / N2)
@@ -213,23 +217,21 @@ using P4096 = FftPlan<4096, 16, 16, 16, 16>;
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 template <class P, int B>
-static cudaError_t launch_cols(const SpectrumArgs& a, const SpectrumTables& tabs, int N2, int log2N, cudaStream_t st) {
+static cudaError_t launch_cols(Launcher& L, int sid, const SpectrumArgs& a, const SpectrumArgs* d_a, const SpectrumTables& tabs, int N2, int log2N) {
     const size_t smem = (P::L + (size_t)N2 + fft_exchange_elems<P, true, B>()) * sizeof(float2);
     if (cudaError_t e = ensure_dynamic_smem((const void*)fft_cols_kernel<P, B>, smem); e != cudaSuccess) return e;
     dim3 grid(N2 / B, a.frames);
-    fft_cols_kernel<P, B><<<grid, P::T * B, smem, st>>>(a, tabs, N2, log2N, ilog2(N2));
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)fft_cols_kernel<P, B>, grid, dim3(P::T * B), smem, d_a, tabs, N2, log2N, ilog2(N2));
 }
 
 template <class P, int B, bool FROM_SAMPLES>
-static cudaError_t launch_rows(const SpectrumArgs& a, const SpectrumTables& tabs, int N1, int log2N, cudaStream_t st) {
+static cudaError_t launch_rows(Launcher& L, int sid, const SpectrumArgs& a, const SpectrumArgs* d_a, const SpectrumTables& tabs, int N1, int log2N) {
     constexpr size_t ex = fft_exchange_elems<P, false, B>() * sizeof(float2);
     constexpr size_t tr = FROM_SAMPLES ? 0 : (size_t)P::L * (B + 1) * sizeof(float);
     constexpr size_t smem = P::L * sizeof(float2) + (ex > tr ? ex : tr);
     if (cudaError_t e = ensure_dynamic_smem((const void*)fft_rows_kernel<P, B, FROM_SAMPLES>, smem); e != cudaSuccess) return e;
     dim3 grid(FROM_SAMPLES ? ceil_div(a.frames, B) : N1 / B, FROM_SAMPLES ? 1 : a.frames);
-    fft_rows_kernel<P, B, FROM_SAMPLES><<<grid, P::T * B, smem, st>>>(a, tabs, N1, log2N);
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)fft_rows_kernel<P, B, FROM_SAMPLES>, grid, dim3(P::T * B), smem, d_a, tabs, N1, log2N);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -254,11 +256,10 @@ fft_zoom_kernel(const float* __restrict__ rows, int N, const int* __restrict__ i
     if (lane == 0) out[(size_t)blockIdx.y * outSize + px] = m;
 }
 
-cudaError_t launch_fft_zoom(const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out, cudaStream_t st) {
+cudaError_t launch_fft_zoom(Launcher& L, int sid, const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out) {
     if (nrows <= 0 || outSize <= 0) return cudaSuccess;
     dim3 grid(ceil_div(outSize, 8), nrows);
-    fft_zoom_kernel<<<grid, 256, 0, st>>>(rows, N, idx, outSize, ranged, out);
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)fft_zoom_kernel, grid, dim3(256), 0, rows, N, idx, outSize, ranged, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -296,10 +297,9 @@ signal_info_kernel(const float* __restrict__ rows, int N, const int4* __restrict
     }
 }
 
-cudaError_t launch_signal_info(const float* rows, int N, int nrows, const int4* bins, int nsig, float2* out, cudaStream_t st) {
+cudaError_t launch_signal_info(Launcher& L, int sid, const float* rows, int N, int nrows, const int4* bins, int nsig, float2* out) {
     if (nrows <= 0 || nsig <= 0) return cudaSuccess;
-    signal_info_kernel<<<dim3((unsigned)nsig, (unsigned)nrows), 256, 0, st>>>(rows, N, bins, out, nsig);
-    return cudaGetLastError();
+    return L.kernel(sid, (const void*)signal_info_kernel, dim3((unsigned)nsig, (unsigned)nrows), dim3(256), 0, rows, N, bins, out, nsig);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -327,11 +327,12 @@ fft_display_kernel(float* __restrict__ zoom, int W, int nrows, bool smoothing, f
     smooth[i] = sb; hold[i] = hb; latest[i] = v;
 }
 
-cudaError_t launch_fft_display(float* zoom, int W, int nrows, bool smoothing, float alpha, float* smooth, bool hold_on, float hold_speed,
-                               float* hold, float* latest, cudaStream_t st) {
+cudaError_t launch_fft_display(Launcher& L, int sid, float* zoom, int W, int nrows, bool smoothing, float alpha, float* smooth, bool hold_on,
+                               float hold_speed, float* hold, float* latest) {
     if (nrows <= 0 || W <= 0) return cudaSuccess;
-    fft_display_kernel<<<ceil_div(W, 256), 256, 0, st>>>(zoom, W, nrows, smoothing, alpha, 1.0f - alpha, smooth, hold_on, hold_speed, hold, latest);
-    return cudaGetLastError();
+    const float beta = 1.0f - alpha;
+    return L.kernel(sid, (const void*)fft_display_kernel, dim3((unsigned)ceil_div(W, 256)), dim3(256), 0, zoom, W, nrows, smoothing, alpha, beta, smooth,
+                    hold_on, hold_speed, hold, latest);
 }
 
 int spectrum_split(int N, int* N1, int* N2) {
@@ -344,42 +345,44 @@ int spectrum_split(int N, int* N1, int* N2) {
     return lg;
 }
 
-cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long long* launches) {
+cudaError_t launch_spectrum(Launcher& L, int sid, int N, const SpectrumArgs& a, long long* launches) {
     int N1, N2;
     const int lg = spectrum_split(N, &N1, &N2);
     if (lg < 0 || a.frames <= 0) return cudaErrorInvalidValue;
     SpectrumTables tabs;
     cudaError_t e = get_tables(N, N1, N2, &tabs);
     if (e != cudaSuccess) return e;
+    const SpectrumArgs* d_a = L.push(a);
+    if (!d_a) return cudaErrorMemoryAllocation;
     if (N1 == 1) {
         switch (N) {
-        case 64: e = launch_rows<P64, 16, true>(a, tabs, 1, lg, st); break;
-        case 128: e = launch_rows<P128, 16, true>(a, tabs, 1, lg, st); break;
-        case 256: e = launch_rows<P256, 8, true>(a, tabs, 1, lg, st); break;
-        case 512: e = launch_rows<P512, 8, true>(a, tabs, 1, lg, st); break;
-        case 1024: e = launch_rows<P1024, 4, true>(a, tabs, 1, lg, st); break;
-        case 2048: e = launch_rows<P2048, 2, true>(a, tabs, 1, lg, st); break;
-        case 4096: e = launch_rows<P4096, 1, true>(a, tabs, 1, lg, st); break;
+        case 64: e = launch_rows<P64, 16, true>(L, sid, a, d_a, tabs, 1, lg); break;
+        case 128: e = launch_rows<P128, 16, true>(L, sid, a, d_a, tabs, 1, lg); break;
+        case 256: e = launch_rows<P256, 8, true>(L, sid, a, d_a, tabs, 1, lg); break;
+        case 512: e = launch_rows<P512, 8, true>(L, sid, a, d_a, tabs, 1, lg); break;
+        case 1024: e = launch_rows<P1024, 4, true>(L, sid, a, d_a, tabs, 1, lg); break;
+        case 2048: e = launch_rows<P2048, 2, true>(L, sid, a, d_a, tabs, 1, lg); break;
+        case 4096: e = launch_rows<P4096, 1, true>(L, sid, a, d_a, tabs, 1, lg); break;
         }
         if (launches) *launches += 1;
         return e;
     }
     switch (N1) {
-    case 64: e = launch_cols<P64, 16>(a, tabs, N2, lg, st); break;
-    case 128: e = launch_cols<P128, 16>(a, tabs, N2, lg, st); break;
-    case 256: e = launch_cols<P256, 16>(a, tabs, N2, lg, st); break;
-    case 512: e = launch_cols<P512, 16>(a, tabs, N2, lg, st); break;
-    case 1024: e = launch_cols<P1024, SDRPP_FFT_CB>(a, tabs, N2, lg, st); break;
-    case 2048: e = launch_cols<P2048, 8>(a, tabs, N2, lg, st); break;
+    case 64: e = launch_cols<P64, 16>(L, sid, a, d_a, tabs, N2, lg); break;
+    case 128: e = launch_cols<P128, 16>(L, sid, a, d_a, tabs, N2, lg); break;
+    case 256: e = launch_cols<P256, 16>(L, sid, a, d_a, tabs, N2, lg); break;
+    case 512: e = launch_cols<P512, 16>(L, sid, a, d_a, tabs, N2, lg); break;
+    case 1024: e = launch_cols<P1024, SDRPP_FFT_CB>(L, sid, a, d_a, tabs, N2, lg); break;
+    case 2048: e = launch_cols<P2048, 8>(L, sid, a, d_a, tabs, N2, lg); break;
     default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;
     switch (N2) {
-    case 128: e = launch_rows<P128, 16, false>(a, tabs, N1, lg, st); break;
-    case 256: e = launch_rows<P256, 16, false>(a, tabs, N1, lg, st); break;
-    case 512: e = launch_rows<P512, 16, false>(a, tabs, N1, lg, st); break;
-    case 1024: e = launch_rows<P1024, SDRPP_FFT_RB, false>(a, tabs, N1, lg, st); break;
-    case 2048: e = launch_rows<P2048, 8, false>(a, tabs, N1, lg, st); break;
+    case 128: e = launch_rows<P128, 16, false>(L, sid, a, d_a, tabs, N1, lg); break;
+    case 256: e = launch_rows<P256, 16, false>(L, sid, a, d_a, tabs, N1, lg); break;
+    case 512: e = launch_rows<P512, 16, false>(L, sid, a, d_a, tabs, N1, lg); break;
+    case 1024: e = launch_rows<P1024, SDRPP_FFT_RB, false>(L, sid, a, d_a, tabs, N1, lg); break;
+    case 2048: e = launch_rows<P2048, 8, false>(L, sid, a, d_a, tabs, N1, lg); break;
     default: return cudaErrorInvalidValue;
     }
     if (launches) *launches += 2;

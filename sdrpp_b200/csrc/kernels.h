@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "launcher.h"
 
 namespace sdrpp {
 
@@ -17,8 +18,8 @@ struct RingRef {
 // Ingest / pre-processing (convert.cu, preproc.cu)
 // ---------------------------------------------------------------------------------------------
 // raw samples of format fmt -> cf32 at dst[(pos+i)&mask], optional conjugate (dsp/math/conjugate.h:12-15)
-cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st,
-                          float scale = 1.0f);
+// (L, sid): the command goes to stream `sid` of the launcher; per-block arguments travel in the launcher's descriptor.
+cudaError_t launch_ingest(Launcher& L, int sid, int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, float scale = 1.0f);
 // SampleStreamCompressor (sample_stream_compressor.h:26-60): block maximum, then int8/int16 packing.
 // key: one device word of scratch; scaler_out: device float that receives the packet's scaler.
 cudaError_t launch_pcm_compress(int bits, const float* in, int nscalars, unsigned int* key, void* out, float* scaler_out,
@@ -52,18 +53,18 @@ struct SpectrumArgs {
     int frames;
 };
 int spectrum_split(int N, int* N1, int* N2);
-cudaError_t launch_spectrum(int N, const SpectrumArgs& a, cudaStream_t st, long long* launches);
+cudaError_t launch_spectrum(Launcher& L, int sid, int N, const SpectrumArgs& a, long long* launches);
 
 // Waterfall zoom / max-decimation of dB rows (gui/widgets/fft_scaler.h:41-64): out[r][i] = max over bins
 // [idx[i], idx[i+1]) (ranged) or rows[r][idx[i]] (point sampling). Reads are clamped to the row.
-cudaError_t launch_fft_zoom(const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out, cudaStream_t st);
+cudaError_t launch_fft_zoom(Launcher& L, int sid, const float* rows, int N, int nrows, const int* idx, int outSize, bool ranged, float* out);
 
 // WaterFall::calculateVFOSignalInfo (gui/widgets/waterfall.cpp:563-603) for nsig VFOs x nrows rows: out[r*nsig + v] =
 // (strength, snr); bins[v] = (minSide, min, max, maxSide) bin indices (design.h: signal_info_bins).
-cudaError_t launch_signal_info(const float* rows, int N, int nrows, const int4* bins, int nsig, float2* out, cudaStream_t st);
+cudaError_t launch_signal_info(Launcher& L, int sid, const float* rows, int N, int nrows, const int4* bins, int nsig, float2* out);
 // FFT smoothing and peak hold of the zoomed rows, in place (WaterFall::pushFFT, waterfall.cpp:918-956); state buffers of W floats.
-cudaError_t launch_fft_display(float* zoom, int W, int nrows, bool smoothing, float alpha, float* smooth, bool hold_on, float hold_speed,
-                               float* hold, float* latest, cudaStream_t st);
+cudaError_t launch_fft_display(Launcher& L, int sid, float* zoom, int W, int nrows, bool smoothing, float alpha, float* smooth, bool hold_on,
+                               float hold_speed, float* hold, float* latest);
 
 // ---------------------------------------------------------------------------------------------
 // Channelizer (channelizer.cu)
@@ -112,9 +113,9 @@ int stage1_A(int T, int D);                                // rows of the tap ma
 int stage1_tap_offset(int ratio);                          // also uploads the pool to the current device
 size_t stage1_g_elems(int A, int D, int nvfo);          // float4 elements of G
 void stage1_g_index(int A, int D, int v, int p, size_t* idx4, int* half); // where F[p] of VFO v lives
-cudaError_t launch_stage1(const Stage1Args& a, cudaStream_t st);
+cudaError_t launch_stage1(Launcher& L, int sid, const Stage1Args& a);
 // D = 1, T = 1 (no pre-decimation): pure translation.
-cudaError_t launch_mix_only(const Stage1Args& a, cudaStream_t st);
+cudaError_t launch_mix_only(Launcher& L, int sid, const Stage1Args& a);
 
 // ---------------------------------------------------------------------------------------------
 // Stage 1 on the tensor cores (channelizer_tc.cu): same result as launch_stage1 for first-stage decimations of
@@ -157,10 +158,10 @@ int s1t_A(int T, int D, int shift);
 int s1t_b_exponent(const float* taps, int T);
 size_t s1t_b_bytes(int A, int D, int nvfo);
 // samples [abs_begin, abs_end) were just written to the ring: (re)build the 8-row groups they touch
-cudaError_t launch_s1t_split(RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end, cudaStream_t st);
-cudaError_t launch_s1t_build_b(uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift, int A,
-                               int escale, cudaStream_t st);
-cudaError_t launch_s1t(S1TArgs& a, int num_sms, cudaStream_t st);
+cudaError_t launch_s1t_split(Launcher& L, int sid, RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end);
+cudaError_t launch_s1t_build_b(Launcher& L, int sid, uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift,
+                               int A, int escale);
+cudaError_t launch_s1t(Launcher& L, int sid, S1TArgs& a, int num_sms);
 
 enum { TAIL_DECFIR = 0, TAIL_POLY = 1, TAIL_FIR = 2 };
 struct TailStage {
@@ -195,12 +196,13 @@ struct TailArgs {
     float2* arena_iq;
     float* arena_demod;
 };
-cudaError_t launch_tail(const TailArgs& a, int total_vfos, cudaStream_t st);
+// the three tail launchers take the DEVICE copy of the arguments (Launcher::push) beside the host copy they size the grid from
+cudaError_t launch_tail(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos);
 // the low-latency form for groups whose stage inputs of this block fit in shared memory at once (tail_fast_fits)
 bool tail_fast_fits(const TailGroup& g, int* samples);
-cudaError_t launch_tail_fast(const TailArgs& a, int total_vfos, cudaStream_t st);
+cudaError_t launch_tail_fast(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos);
 // stage 0 of the groups with s_begin == 1 on a wide grid (a decimating FIR); launch before launch_tail
-cudaError_t launch_tail_stage0_wide(const TailArgs& a, int total_vfos, cudaStream_t st);
+cudaError_t launch_tail_stage0_wide(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos);
 bool tail_stage0_wide_supported(int T, int D);
 
 // Post-detector stages of the three demodulators: FM low-pass (dsp/demod/fm.h:86-103), AM
@@ -233,6 +235,6 @@ struct PostArgs {
     float* arena_audio;
     float* arena_audio_r;        // right channel of stereo demodulators (POST_WFM); mono kinds leave it alone
 };
-cudaError_t launch_post(const PostArgs& a, int total_vfos, cudaStream_t st);
+cudaError_t launch_post(Launcher& L, int sid, const PostArgs& a, int total_vfos);
 
 } // namespace sdrpp

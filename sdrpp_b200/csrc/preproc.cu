@@ -16,9 +16,24 @@ __device__ __forceinline__ void ring_store(RingRef dst, uint32_t idx, float2 v, 
 // Conversion. HBM-bound: 2/4/8 B in, 8 B out per sample. Each thread converts 4 consecutive
 // samples from one 8/16/32-byte load and, when the destination is aligned, two 16-byte stores.
 // ---------------------------------------------------------------------------------------------
+struct IngestArgs {      // per-block arguments, read through the launcher's descriptor
+    const void* raw;
+    int count;
+    RingRef dst;
+    uint32_t pos;
+    int conj, vec_ok;
+    float scale;
+};
+
 template <int FMT>
 __global__ void __launch_bounds__(256)
-ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos, bool conj, bool vec_ok, float scale) {
+ingest_kernel(const IngestArgs* __restrict__ ap) {
+    const void* __restrict__ raw = ap->raw;
+    const int count = ap->count;
+    const RingRef dst = ap->dst;
+    const uint32_t pos = ap->pos;
+    const bool conj = ap->conj != 0, vec_ok = ap->vec_ok != 0;
+    const float scale = ap->scale;
     const int stride = gridDim.x * blockDim.x;
     const int nquads = count >> 2;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += stride) {
@@ -85,28 +100,31 @@ ingest_kernel(const void* __restrict__ raw, int count, RingRef dst, uint32_t pos
     }
 }
 
-cudaError_t launch_ingest(int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, cudaStream_t st, float scale) {
+cudaError_t launch_ingest(Launcher& L, int sid, int fmt, const void* raw, int count, RingRef dst, uint32_t pos, bool conj, float scale) {
     if (count <= 0) return cudaSuccess;
     const int threads = 256;
     int blocks = ceil_div(ceil_div(count, 4), threads);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    const bool vec_ok = ((uintptr_t)raw & 15u) == 0;
+    IngestArgs a{ raw, count, dst, pos, conj ? 1 : 0, (((uintptr_t)raw & 15u) == 0 && !(fmt >= 6 && fmt <= 8)) ? 1 : 0, scale };
+    const IngestArgs* d = L.push(a);
+    if (!d) return cudaErrorMemoryAllocation;
+    const void* fn = nullptr;
     switch (fmt) {
-    case 0: ingest_kernel<0><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 1: ingest_kernel<1><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 2: ingest_kernel<2><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 3: ingest_kernel<3><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 4: ingest_kernel<4><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 5: ingest_kernel<5><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 6: ingest_kernel<6><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false, scale); break;
-    case 7: ingest_kernel<7><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false, scale); break;
-    case 8: ingest_kernel<8><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, false, scale); break;
-    case 9: ingest_kernel<9><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
-    case 10: ingest_kernel<10><<<blocks, threads, 0, st>>>(raw, count, dst, pos, conj, vec_ok, scale); break;
+    case 0: fn = (const void*)ingest_kernel<0>; break;
+    case 1: fn = (const void*)ingest_kernel<1>; break;
+    case 2: fn = (const void*)ingest_kernel<2>; break;
+    case 3: fn = (const void*)ingest_kernel<3>; break;
+    case 4: fn = (const void*)ingest_kernel<4>; break;
+    case 5: fn = (const void*)ingest_kernel<5>; break;
+    case 6: fn = (const void*)ingest_kernel<6>; break;
+    case 7: fn = (const void*)ingest_kernel<7>; break;
+    case 8: fn = (const void*)ingest_kernel<8>; break;
+    case 9: fn = (const void*)ingest_kernel<9>; break;
+    case 10: fn = (const void*)ingest_kernel<10>; break;
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
+    return L.kernel(sid, fn, dim3((unsigned)blocks), dim3((unsigned)threads), 0, d);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ sdrpp_cuda_frontend_launches sdrpp_cuda_frontend_stream sdrpp_cuda_frontend_set_
 sdrpp_cuda_frontend_kernel_ms sdrpp_cuda_fft_zoom sdrpp_cuda_frontend_set_fft_zoom sdrpp_cuda_fft_zoomed_rows sdrpp_cuda_spectrum_device
 sdrpp_cuda_vfo_set_post sdrpp_cuda_vfo_audio sdrpp_cuda_vfo_set_if_chain sdrpp_cuda_vfo_squelch_state
 sdrpp_cuda_frontend_set_stage1_mode sdrpp_cuda_frontend_stage1_tensor_launches
+sdrpp_cuda_frontend_set_graphs sdrpp_cuda_frontend_graph_stats
 sdrpp_cuda_frontend_wait_input sdrpp_cuda_frontend_pending sdrpp_cuda_frontend_drain sdrpp_cuda_frontend_join_streams
 sdrpp_cuda_comm_unique_id sdrpp_cuda_comm_create sdrpp_cuda_comm_destroy sdrpp_cuda_comm_info sdrpp_cuda_frontend_set_comm
 sdrpp_cuda_frontend_submit_shared sdrpp_cuda_frontend_set_fft_display sdrpp_cuda_fft_hold_row sdrpp_cuda_vfo_set_signal_info
@@ -146,6 +147,8 @@ def lib():
         L.sdrpp_cuda_frontend_stage1_tensor_launches.restype = C.c_longlong
         L.sdrpp_cuda_frontend_stage1_tensor_launches.argtypes = [_vp]
         L.sdrpp_cuda_frontend_set_stage1_mode.argtypes = [_vp, _i]
+        L.sdrpp_cuda_frontend_set_graphs.argtypes = [_vp, _i]
+        L.sdrpp_cuda_frontend_graph_stats.argtypes = [_vp, _vp]
         L.sdrpp_cuda_frontend_stream.restype = _vp
         L.sdrpp_cuda_frontend_stream.argtypes = [_vp]
         L.sdrpp_cuda_frontend_kernel_ms.restype = C.c_float
@@ -561,6 +564,15 @@ class Frontend:
     @property
     def stage1_tensor_launches(self):
         return lib().sdrpp_cuda_frontend_stage1_tensor_launches(self.h)
+
+    def set_graphs(self, enabled):
+        """CUDA-graph replay of repeated blocks (default on); off: every block command by command. Same results."""
+        _check(lib().sdrpp_cuda_frontend_set_graphs(self.h, int(enabled)), "set_graphs")
+
+    def graph_stats(self):
+        out = (C.c_longlong * 4)()
+        _check(lib().sdrpp_cuda_frontend_graph_stats(self.h, out), "graph_stats")
+        return {"replayed_runs": int(out[0]), "graphs_instantiated": int(out[1]), "direct_runs": int(out[2]), "instantiate_us": int(out[3])}
 
     def set_stage1_mode(self, mode):
         """0: tensor cores where the plan allows (default), 1: FP32 FMA kernel only."""
