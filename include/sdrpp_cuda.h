@@ -252,8 +252,9 @@ SDRPP_API int sdrpp_cuda_vfo_output(sdrpp_cuda_frontend* fe, int vfo, const sdrp
  *   USB/LSB/DSB: dsp::demod::SSB<float> -- AGC on the real output (dsp/demod/ssb.h:21-36,90-101)
  *   QUADRATURE with wfm = 1: dsp::demod::BroadcastFM (dsp/demod/broadcast_fm.h:35-65,147-214), the WFM stereo decoder of the
  *               radio module (decoder_modules/radio/src/demodulators/wfm.h): 19 kHz pilot band-pass -> PLL -> L-R down-conversion
- *               -> L/R matrix -> 15 kHz low-pass; deviation = bandwidth / 2. Stereo output: sdrpp_cuda_vfo_audio_stereo. The RDS
- *               side output (rdsOut) is not built.
+ *               -> L/R matrix -> 15 kHz low-pass; deviation = bandwidth / 2. Stereo output: sdrpp_cuda_vfo_audio_stereo. With
+ *               wfm_rds = 1 the decoder's RDS side output (rdsOut, broadcast_fm.h:50-51,168-175,188-198) is produced as well:
+ *               (mpx, 0) translated by -57 kHz and resampled to 5 kS/s; read it with sdrpp_cuda_vfo_rds.
  * with dsp::loop::AGC (dsp/loop/agc.h:87-147: setPoint 1, maxGain 10e6, maxOutputAmp 10, initGain INFINITY) and
  * dsp::correction::DCBlocker<float> (dsp/correction/dc_blocker.h:54-60). The radio module passes attack/decay/rate
  * already divided by the IF sample rate (decoder_modules/radio/src/demodulators/am.h:38, usb.h:40). */
@@ -268,6 +269,7 @@ typedef struct {
     float agc_gain;        /* > 0: setAGCGain(agc_gain) after init (the fixed gain when the audio AGC is off) */
     int wfm;               /* QUADRATURE only: 1 = dsp::demod::BroadcastFM (stereo decoder) instead of dsp::demod::FM */
     int wfm_stereo;        /* BroadcastFM _stereo (setStereo); the low-pass switch is fm_lowpass (setLowPass) */
+    int wfm_rds;           /* BroadcastFM _rdsOut (setRDSOut): the 5 kS/s complex RDS baseband beside the audio */
 } sdrpp_cuda_post_cfg;
 /* (Re)initialises the VFO's post-detector objects; also redone when the VFO's bandwidth or rate changes. */
 SDRPP_API int sdrpp_cuda_vfo_set_post(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cuda_post_cfg* cfg);
@@ -276,6 +278,9 @@ SDRPP_API int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int vfo, const float
 /* Stereo demodulators (wfm = 1): left and right channel rows of the last waited block (dsp::stereo_t de-interleaved);
  * for mono demodulators *right = *left. Returns the sample count. */
 SDRPP_API int sdrpp_cuda_vfo_audio_stereo(sdrpp_cuda_frontend* fe, int vfo, const float** left, const float** right);
+/* BroadcastFM::rdsOut (dsp/demod/broadcast_fm.h:229) of the last waited block: returns the sample count (the reference swaps
+ * the stream only when it is non-zero); *rds -> cf32[count] at 5 kS/s. SDRPP_ERR_STATE unless wfm = wfm_rds = 1. */
+SDRPP_API int sdrpp_cuda_vfo_rds(sdrpp_cuda_frontend* fe, int vfo, const sdrpp_cf32** rds);
 
 /* Radio IF chain between the VFO output and the demodulator front end: the order is the radio
  * module's, NoiseBlanker -> Squelch -> FMIF (decoder_modules/radio/src/radio_module.h:73-78). With a block enabled the VFO's

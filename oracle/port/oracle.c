@@ -1032,7 +1032,7 @@ API void orc_fft_zoom(double viewOffset, double viewBandwidth, double wholeBandw
 }
 
 /* ------------------------------------------------------------------------------------------ */
-/* dsp::demod::BroadcastFM (demod/broadcast_fm.h), the WFM stereo decoder; RDS output off */
+/* dsp::demod::BroadcastFM (demod/broadcast_fm.h), the WFM stereo decoder and its RDS side output */
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     double deviation, samplerate; int stereo, lowPass;
@@ -1042,6 +1042,8 @@ typedef struct {
     float pll_alpha, pll_beta, pll_phase, pll_freq, pll_init_freq, pll_min, pll_max;
     float* pbuf; float* dbuf; float* lbuf; float* rbuf;   /* [hist | block] buffers, grown on demand */
     int cap;
+    int rds;                 /* _rdsOut: xlator.init(NULL, -57000.0, samplerate), rdsResamp.init(NULL, samplerate, 5000.0) (broadcast_fm.h:50-51) */
+    orc_xlat* rx; orc_resamp* rr;
 } orc_wfm;
 static double nuttall_d(double n, double N) {
     static const double c[4] = { 0.355768, 0.487396, 0.144232, 0.012604 };
@@ -1085,6 +1087,16 @@ API orc_wfm* orc_wfm_create(double deviation, double samplerate, int stereo, int
     w->pll_phase = 0.0f; w->pll_freq = w->pll_init_freq;
     return w;
 }
+/* rds = 1: the reference's own rotator; rds = 2: the ideal-NCO flavour of the translation, everything else the same */
+API orc_wfm* orc_wfm_create_rds(double deviation, double samplerate, int stereo, int lowPass, int rds) {
+    orc_wfm* w = orc_wfm_create(deviation, samplerate, stereo, lowPass);
+    w->rds = rds;
+    if (rds) {
+        w->rx = (rds == 2) ? orc_xlator_create_ideal(-57000.0, samplerate) : orc_xlator_create(-57000.0, samplerate);
+        w->rr = orc_resampler_create(samplerate, 5000.0);
+    }
+    return w;
+}
 API void orc_wfm_taps(const orc_wfm* w, int* n, float* pilot, int pcap, float* audio, int acap) {
     n[0] = w->np; n[1] = w->na;
     if (pilot) memcpy(pilot, w->ptaps, sizeof(cf32) * (size_t)(w->np < pcap ? w->np : pcap));
@@ -1111,12 +1123,24 @@ static void ffir_inplace(float* buf, int hist, int n, const float* taps, int nt,
     memmove(buf, buf + n, sizeof(float) * (size_t)hist);
 }
 /* BroadcastFM::process, broadcast_fm.h:147-214; out = interleaved stereo_t (l, r) */
-API int orc_wfm_process(orc_wfm* w, int count, const cf32* in, float* out) {
+static int wfm_process(orc_wfm* w, int count, const cf32* in, float* out, cf32* rds, int* rdsCount) {
     const float PI = 3.1415926535f;            /* FL_M_PI */
     float* mpx = (float*)malloc(sizeof(float) * (size_t)(count + 1));
     int i, k;
     orc_quadrature_process(w->demod, count, in, mpx);
     wfm_reserve(w, count);
+    if (rdsCount) *rdsCount = 0;
+    if (w->rds && rds) {
+        /* rtoc (convert/real_to_complex.h: (x, 0)) -> xlator -> rdsResamp, broadcast_fm.h:168-175 (stereo) / 188-198 (mono): the
+         * same values either way -- the stereo branch translates rtoc's buffer in place AFTER the delay line has copied it */
+        cf32* c = (cf32*)malloc(sizeof(cf32) * (size_t)(count + 1));
+        int n;
+        for (i = 0; i < count; i++) { c[i].re = mpx[i]; c[i].im = 0.0f; }
+        orc_xlator_process(w->rx, count, c, c);
+        n = orc_resampler_process(w->rr, count, c, rds);
+        if (rdsCount) *rdsCount = n;
+        free(c);
+    }
     if (w->stereo) {
         cf32* pil = (cf32*)malloc(sizeof(cf32) * (size_t)(count + 1));
         float* l = w->lbuf + (w->na - 1); float* r = w->rbuf + (w->na - 1);
@@ -1172,8 +1196,11 @@ API int orc_wfm_process(orc_wfm* w, int count, const cf32* in, float* out) {
     free(mpx);
     return count;
 }
+API int orc_wfm_process(orc_wfm* w, int count, const cf32* in, float* out) { return wfm_process(w, count, in, out, NULL, NULL); }
+API int orc_wfm_process_rds(orc_wfm* w, int count, const cf32* in, float* out, cf32* rds, int* rdsCount) { return wfm_process(w, count, in, out, rds, rdsCount); }
 API void orc_wfm_destroy(orc_wfm* w) {
     if (!w) return;
+    orc_xlator_destroy(w->rx); orc_resampler_destroy(w->rr);
     orc_quadrature_destroy(w->demod); free(w->ptaps); free(w->ataps); free(w->pbuf); free(w->dbuf); free(w->lbuf); free(w->rbuf); free(w);
 }
 

@@ -224,16 +224,31 @@ class _Base:
     def ssb_full(self, mode, bw, sr, agc_enabled, attack, decay):
         return self._post_obj(self._f("ssbfull_create", _vp, _i, _d, _d, _i, _d, _d)(mode, bw, sr, int(agc_enabled), attack, decay), "ssbfull")
 
-    def wfm(self, deviation, sr, stereo=True, low_pass=True):
-        """dsp::demod::BroadcastFM (RDS output off): process(iq) -> interleaved (l, r) floats, 2 per input sample."""
+    def wfm(self, deviation, sr, stereo=True, low_pass=True, rds=False, ideal_nco=False):
+        """dsp::demod::BroadcastFM: process(iq) -> interleaved (l, r) floats, 2 per input sample. rds=True: the decoder's RDS side
+        output is on and process returns (lr, rds) -- rds = complex samples at 5 kS/s produced by this call. ideal_nco (port only):
+        the -57 kHz translation with the closed-form phase instead of the fp32 rotator."""
         lib, pre = self.lib, self.prefix
-        h = self._f("wfm_create", _vp, _d, _d, _i, _i)(deviation, sr, int(stereo), int(low_pass))
+        if rds and pre == "orc":
+            h = self._f("wfm_create_rds", _vp, _d, _d, _i, _i, _i)(deviation, sr, int(stereo), int(low_pass), 2 if ideal_nco else 1)
+        elif rds:
+            if ideal_nco:
+                raise ValueError("the reference build has no ideal-NCO BroadcastFM (its xlator is a private member)")
+            h = self._f("wfm_create_rds", _vp, _d, _d, _i, _i)(deviation, sr, int(stereo), int(low_pass))
+        else:
+            h = self._f("wfm_create", _vp, _d, _d, _i, _i)(deviation, sr, int(stereo), int(low_pass))
         o = _Obj(lib, f"{pre}_wfm", h, out_dtype=np.float32)
         base = self
 
         def process(x, out_cap=None):
             x = _c64(x)
             out = np.zeros(2 * len(x) + 16, dtype=np.float32)
+            if rds:
+                r = np.zeros(len(x) + 16, dtype=cf32)
+                nr = _i(0)
+                fn = getattr(lib, f"{pre}_wfm_process_rds"); fn.restype = _i; fn.argtypes = [_vp, _i, _vp, _vp, _vp, _vp]
+                n = fn(o.h, len(x), _ptr(x), _ptr(out), _ptr(r), C.byref(nr))
+                return out[:2 * n].reshape(n, 2).copy(), r[:nr.value].copy()
             fn = getattr(lib, f"{pre}_wfm_process"); fn.restype = _i; fn.argtypes = [_vp, _i, _vp, _vp]
             n = fn(o.h, len(x), _ptr(x), _ptr(out))
             return out[:2 * n].reshape(n, 2).copy()

@@ -545,6 +545,21 @@ API void ref_wfm_taps(void* h, int* n, float* pilot, int pcap, float* audio, int
     if (audio) memcpy(audio, w->audioFirTaps.taps, sizeof(float) * std::min<int>(n[1], acap));
 }
 API void ref_wfm_destroy(void* h) { delete (dsp::demod::BroadcastFM*)h; }
+// The same decoder with its RDS side output on (_rdsOut, broadcast_fm.h:168-175,188-198): (mpx, 0) translated by -57 kHz
+// (the decoder's own FrequencyXlator) and resampled to 5 kS/s (its own RationalResampler). rds receives the samples of this
+// call (at most count of them), *rdsCount their number.
+API void* ref_wfm_create_rds(double deviation, double samplerate, int stereo, int lowPass) {
+    auto* d = new dsp::demod::BroadcastFM();
+    d->init(NULL, deviation, samplerate, stereo != 0, lowPass != 0, true);
+    d->reset();
+    return d;
+}
+API int ref_wfm_process_rds(void* h, int count, complex_t* in, float* out, complex_t* rds, int* rdsCount) {
+    int n = 0;
+    const int rc = ((dsp::demod::BroadcastFM*)h)->process(count, in, (dsp::stereo_t*)out, n, rds);
+    if (rdsCount) *rdsCount = n;
+    return rc;
+}
 
 API const char* ref_build_info() {
 #ifdef __FAST_MATH__

@@ -1378,6 +1378,80 @@ post_kernel(const PostArgs* __restrict__ ap) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// RDS side output of BroadcastFM (kernels.h: RdsDev / RdsBlk). Stages run back to back on the VFO's own history buffers;
+// a block of a 250 kS/s WFM channel is 1250 samples in and 25 out, so one CTA per VFO and plain loops.
+// ---------------------------------------------------------------------------------------------
+constexpr int kRdsThreads = 256;
+
+// the last `hist` samples of [hist | n] become the history of the next block (fir.h:80); ascending chunks never read a
+// position an earlier chunk has already written
+__device__ __forceinline__ void rds_carry(float2* buf, int hist, int n) {
+    for (int base = 0; base < hist; base += kRdsThreads) {
+        const int j = base + (int)threadIdx.x;
+        float2 v = make_float2(0.0f, 0.0f);
+        if (j < hist) v = buf[n + j];
+        __syncthreads();
+        if (j < hist) buf[j] = v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kRdsThreads)
+rds_kernel(const RdsArgs* __restrict__ ap) {
+    const RdsArgs& a = *ap;
+    const RdsDev d = a.tab[a.first + blockIdx.x];
+    const RdsBlk& b = a.blk[blockIdx.x];
+    const int n = b.n, tid = threadIdx.x;
+    if (n <= 0) return;
+    const float* __restrict__ dm = a.arena_demod + d.in_off;
+    float2* __restrict__ out = a.arena_rds + d.out_off;
+    // RealToComplex (x, 0) and FrequencyXlator: out = in * phasor, volk_32fc_s32fc_x2_rotator's complex multiply
+    float2* first = d.nstages > 0 ? d.state + d.buf_off[0] + (d.T[0] - 1) : (d.tpp > 0 ? d.state + d.pbuf_off + (d.tpp - 1) : out);
+    for (int i = tid; i < n; i += kRdsThreads) {
+        const float2 p = phasor_u64(b.phase0 + (uint64_t)i * d.dphi);
+        first[i] = cmul(make_float2(dm[i], 0.0f), p);
+    }
+    __syncthreads();
+    int cur = n;
+    for (int s = 0; s < d.nstages; s++) {
+        const int T = d.T[s], D = d.D[s], nout = b.nout[s];
+        float2* buf = d.state + d.buf_off[s];
+        float2* dst = (s + 1 < d.nstages) ? d.state + d.buf_off[s + 1] + (d.T[s + 1] - 1) : (d.tpp > 0 ? d.state + d.pbuf_off + (d.tpp - 1) : out);
+        const float* __restrict__ h = d.taps[s];
+        for (int j = tid; j < nout; j += kRdsThreads) {
+            const float2* x = buf + b.off[s] + j * D;       // decimating_fir.h:51-62: dot(&buffer[offset], taps), offset += D
+            float2 acc = make_float2(0.0f, 0.0f);
+            for (int k = 0; k < T; k++) { const float t = __ldg(h + k); acc = __ffma2_rn(make_float2(t, t), x[k], acc); }
+            dst[j] = acc;
+        }
+        __syncthreads();
+        rds_carry(buf, T - 1, cur);
+        cur = nout;
+    }
+    if (d.tpp > 0) {
+        float2* buf = d.state + d.pbuf_off;
+        for (int m = tid; m < b.npoly; m += kRdsThreads) {
+            // closed form of polyphase_resampler.h:75-93
+            const long long P = (long long)b.pphase + (long long)m * d.decim;
+            const float2* x = buf + b.poff + (int)(P / d.interp);
+            const float* __restrict__ h = d.bank + (size_t)(P % d.interp) * d.tpp;
+            float2 acc = make_float2(0.0f, 0.0f);
+            for (int k = 0; k < d.tpp; k++) { const float t = __ldg(h + k); acc = __ffma2_rn(make_float2(t, t), x[k], acc); }
+            out[m] = acc;
+        }
+        __syncthreads();
+        rds_carry(buf, d.tpp - 1, cur);
+    }
+}
+
+cudaError_t launch_rds(Launcher& L, int sid, const RdsArgs& a) {
+    if (a.count <= 0) return cudaSuccess;
+    const RdsArgs* d = L.push(a);
+    if (!d) return cudaErrorMemoryAllocation;
+    return L.kernel(sid, (const void*)rds_kernel, dim3((unsigned)a.count), dim3(kRdsThreads), 0, d);
+}
+
 cudaError_t launch_post(Launcher& L, int sid, const PostArgs& a, int total_vfos) {
     if (total_vfos <= 0) return cudaSuccess;
     const PostArgs* d = L.push(a);

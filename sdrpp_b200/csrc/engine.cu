@@ -208,6 +208,19 @@ struct GroupState {
     int64_t abs_out = 0;   // output samples produced since the epoch
 };
 
+// RDS side output of BroadcastFM (broadcast_fm.h:50-51): xlator.init(NULL, -57000.0, samplerate) and
+// rdsResamp.init(NULL, samplerate, 5000.0). Taps are shared by every VFO of the same IF sample rate (at 250 kS/s the
+// reference's plan rounds 7812.5 to 7813 and ends up with a 5000-phase bank of 593,750 taps: 2.4 MB).
+struct RdsPlan {
+    ResamplerPlan rp;
+    std::vector<DecimStage> stages;
+    float* d_taps[kRdsMaxStages] = { nullptr };
+    float* d_bank = nullptr;
+    int tpp = 0;
+    uint64_t dphi = 0;
+    ~RdsPlan() { for (float* t : d_taps) if (t) cudaFree(t); if (d_bank) cudaFree(d_bank); }
+};
+
 struct Vfo {
     bool alive = false;
     double outSR = 0, bw = 0, offset = 0;
@@ -229,6 +242,12 @@ struct Vfo {
     float* post_taps2 = nullptr;
     int post_ntaps2 = 0, post_delay = 0, post_cap = 0;
     float pll_alpha = 0, pll_beta = 0, pll_min = 0, pll_max = 0;
+    // RDS side output (post.wfm_rds): shared plan, own history buffers, the integer state of the reference's blocks
+    std::shared_ptr<RdsPlan> rds;
+    float2* rds_state = nullptr;
+    uint32_t rds_buf_off[kRdsMaxStages] = { 0 }, rds_pbuf_off = 0, rds_out_off = 0;
+    int rds_off[kRdsMaxStages] = { 0 }, rds_pphase = 0, rds_poff = 0, rds_out_cap = 0, rds_slot = -1;
+    uint64_t rds_n = 0;            // discriminator samples translated so far (NCO phase = rds_n * dphi)
     // radio IF chain: device record of IF_FLOATS floats, null until first configured
     float* if_state = nullptr;
     // level / SNR read-out on every spectrum row: slot in the signal-info table, -1 = off
@@ -259,6 +278,9 @@ struct ResultSet {
     float* demod = nullptr;
     float* audio = nullptr;
     float* audio_r = nullptr;     // right channel of stereo demodulators
+    float2* rds = nullptr;        // RDS side outputs (pinned), rows at rds_offs
+    std::vector<int> rds_counts;  // per VFO id: RDS samples of this block (-1: output off)
+    std::vector<uint32_t> rds_offs;
     std::vector<char> stereo;     // per VFO id: stereo demodulator at submit
     float* rows = nullptr;
     float* zoom = nullptr;
@@ -359,6 +381,11 @@ struct sdrpp_cuda_frontend {
     float2* d_arena_iq = nullptr; float* d_arena_demod = nullptr; float* d_arena_audio = nullptr; float* d_arena_audio_r = nullptr;
     size_t arena_cap = 0, arena_used = 0;
     int post_stereo = 0;   // VFOs with a stereo demodulator (POST_WFM): the right-channel arena is copied back too
+    // RDS side outputs: table of the VFOs that have one (device order), arena of their rows per result set
+    std::map<long long, std::shared_ptr<RdsPlan>> rds_plans;   // by IF sample rate in milli-hertz
+    std::vector<int> rds_ids;                  // VFO ids in table order
+    RdsDev* d_rds_tab = nullptr; int rds_tab_cap = 0;
+    float2* d_arena_rds = nullptr; size_t rds_arena_cap = 0, rds_arena_used = 0, rs_rds_cap = 0;
 
     // results
     ResultSet rs[kSets];
@@ -597,6 +624,58 @@ static int rebuild_layout(sdrpp_cuda_frontend* fe) {
         FE_TRY(fe, cudaMemcpyAsync(fe->d_post, hp.data(), sizeof(PostDev) * (size_t)total, cudaMemcpyHostToDevice, fe->st));
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
     }
+    // RDS side outputs: table in device order, rows packed in an arena of their own
+    {
+        std::vector<RdsDev> tab;
+        fe->rds_ids.clear();
+        size_t rarena = 0;
+        for (Group& g : fe->groups)
+            for (int id : g.members) {
+                Vfo& v = fe->vfos[(size_t)id];
+                v.rds_slot = -1;
+                if (!(v.post.enabled && v.post_state && v.post.wfm && v.post.wfm_rds && v.rds && v.rds_state && v.demod == SDRPP_DEMOD_QUADRATURE)) continue;
+                RdsDev d{};
+                d.in_off = v.out_off; d.out_off = (uint32_t)rarena; v.rds_out_off = d.out_off;
+                rarena += (size_t)v.rds_out_cap;
+                d.nstages = (int)v.rds->stages.size();
+                for (int s = 0; s < d.nstages; s++) {
+                    d.T[s] = v.rds->stages[(size_t)s].ntaps; d.D[s] = v.rds->stages[(size_t)s].decimation;
+                    d.taps[s] = v.rds->d_taps[s]; d.buf_off[s] = v.rds_buf_off[s];
+                }
+                d.interp = v.rds->rp.interp; d.decim = v.rds->rp.decim; d.tpp = v.rds->tpp; d.bank = v.rds->d_bank; d.pbuf_off = v.rds_pbuf_off;
+                d.state = v.rds_state; d.dphi = v.rds->dphi;
+                v.rds_slot = (int)tab.size();
+                tab.push_back(d);
+                fe->rds_ids.push_back(id);
+            }
+        fe->rds_arena_used = rarena;
+        if ((int)tab.size() > fe->rds_tab_cap) {
+            FE_TRY(fe, cudaStreamSynchronize(fe->st));
+            cudaFree(fe->d_rds_tab); fe->d_rds_tab = nullptr;
+            fe->rds_tab_cap = std::max((int)tab.size(), 16);
+            FE_TRY(fe, dev_alloc(&fe->d_rds_tab, (size_t)fe->rds_tab_cap));
+        }
+        if (!tab.empty()) {
+            FE_TRY(fe, cudaMemcpyAsync(fe->d_rds_tab, tab.data(), sizeof(RdsDev) * tab.size(), cudaMemcpyHostToDevice, fe->st));
+            FE_TRY(fe, cudaStreamSynchronize(fe->st));
+        }
+        if (rarena > fe->rds_arena_cap) {
+            FE_TRY(fe, cudaStreamSynchronize(fe->st));
+            cudaFree(fe->d_arena_rds); fe->d_arena_rds = nullptr;
+            fe->rds_arena_cap = rarena + rarena / 2 + 256;
+            FE_TRY(fe, dev_alloc(&fe->d_arena_rds, kSets * fe->rds_arena_cap));
+        }
+        if (rarena > fe->rs_rds_cap) {
+            FE_TRY(fe, cudaStreamSynchronize(fe->st));
+            for (int i = 0; i < kSets; i++) {
+                fe->rs[i].rds_counts.clear();
+                if (fe->rs[i].rds) cudaFreeHost(fe->rs[i].rds);
+                fe->rs[i].rds = nullptr;
+                FE_TRY(fe, cudaMallocHost((void**)&fe->rs[i].rds, fe->rds_arena_cap * sizeof(float2)));
+            }
+            fe->rs_rds_cap = fe->rds_arena_cap;
+        }
+    }
     fe->arena_used = arena;
     if (arena > fe->arena_cap) {
         FE_TRY(fe, cudaStreamSynchronize(fe->st));
@@ -721,11 +800,58 @@ static int get_plan(sdrpp_cuda_frontend* fe, double outSR, double bw, std::share
     return SDRPP_OK;
 }
 
+// BroadcastFM::init with rdsOut (broadcast_fm.h:50-51): the plan (shared per IF sample rate) and this VFO's fresh state.
+static int apply_rds(sdrpp_cuda_frontend* fe, Vfo& v) {
+    const long long key = (long long)llround(v.outSR * 1000.0);
+    std::shared_ptr<RdsPlan> pl;
+    auto it = fe->rds_plans.find(key);
+    if (it != fe->rds_plans.end()) pl = it->second;
+    else {
+        pl = std::make_shared<RdsPlan>();
+        pl->rp = design_resampler(v.outSR, 5000.0);
+        if (pl->rp.mode == 0 || pl->rp.mode == 1) pl->stages = decim_plan(pl->rp.predec);
+        if ((int)pl->stages.size() > kRdsMaxStages) return fail(SDRPP_ERR_ARG, "BroadcastFM RDS output: the IF sample rate needs more PowerDecimator stages than supported");
+        for (size_t s = 0; s < pl->stages.size(); s++) {
+            FE_TRY(fe, dev_alloc(&pl->d_taps[s], (size_t)pl->stages[s].ntaps, false));
+            FE_TRY(fe, upload_sync(pl->d_taps[s], pl->stages[s].taps, sizeof(float) * (size_t)pl->stages[s].ntaps));
+        }
+        if (pl->rp.mode == 0 || pl->rp.mode == 2) {
+            const std::vector<float> bank = build_polyphase_bank(pl->rp.taps, pl->rp.interp, &pl->tpp);
+            FE_TRY(fe, dev_alloc(&pl->d_bank, bank.size(), false));
+            FE_TRY(fe, upload_sync(pl->d_bank, bank.data(), bank.size() * sizeof(float)));
+        }
+        double turns = 0;
+        xlator_increment(-57000.0, v.outSR, nullptr, nullptr, &turns);
+        pl->dphi = turns_to_u64(turns);
+        fe->rds_plans[key] = pl;
+    }
+    v.rds = pl;
+    // history buffers [T-1 | block] per stage, sized for the VFO's largest block
+    size_t elems = 0;
+    long long cap = v.plan->cap_final + 8;
+    for (size_t s = 0; s < pl->stages.size(); s++) {
+        v.rds_buf_off[s] = (uint32_t)elems;
+        elems += (size_t)(pl->stages[s].ntaps - 1) + (size_t)cap + 8;
+        cap = cap / pl->stages[s].decimation + 2;
+    }
+    if (pl->tpp > 0) {
+        v.rds_pbuf_off = (uint32_t)elems;
+        elems += (size_t)(pl->tpp - 1) + (size_t)cap + 8;
+        cap = (cap * pl->rp.interp) / pl->rp.decim + 4;
+    }
+    v.rds_out_cap = (int)((cap + 3) & ~3LL);
+    FE_TRY(fe, dev_alloc(&v.rds_state, elems + 8));   // zeroed: the blocks' cleared buffers
+    for (int& o : v.rds_off) o = 0;
+    v.rds_pphase = 0; v.rds_poff = 0; v.rds_n = 0;
+    return SDRPP_OK;
+}
+
 // (Re)build the post-detector objects of a VFO for its current (demod, outSR, bw): the demodulators' init()
 // (fm.h:25-44, am.h:27-44, ssb.h:21-36). Filter and AGC state start from reset.
 static int apply_post(sdrpp_cuda_frontend* fe, Vfo& v) {
     cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.post_taps2);
     v.post_state = nullptr; v.post_taps = nullptr; v.post_taps2 = nullptr; v.post_ntaps = 0; v.post_hist_pad = 0; v.post_ntaps2 = 0;
+    cudaFree(v.rds_state); v.rds_state = nullptr; v.rds.reset(); v.rds_slot = -1;
     fe->layout_dirty = true;
     if (!v.post.enabled) return SDRPP_OK;
     if (v.demod == SDRPP_DEMOD_NONE) return fail(SDRPP_ERR_STATE, "post-detector stages need a demodulator front end");
@@ -749,6 +875,10 @@ static int apply_post(sdrpp_cuda_frontend* fe, Vfo& v) {
         // PLL::reset: phase = initPhase (0), freq = initFreq = hzToRads(19000, samplerate) as a float
         float init[2] = { 0.0f, (float)(2.0 * kPi * (19000.0 / v.outSR)) };
         FE_TRY(fe, upload_sync(v.post_state, init, sizeof(init)));
+        if (v.post.wfm_rds) {
+            const int rc = apply_rds(fe, v);
+            if (rc != SDRPP_OK) return rc;
+        }
         return SDRPP_OK;
     }
     std::vector<float> taps;
@@ -1329,6 +1459,51 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             if (any && tail_totals[i] > 0) FE_TRY(fe, launch_post(L, stl, pa, tail_totals[i]));
         }
     }
+    // RDS side outputs of the WFM decoders (behind the tail, which wrote the discriminator rows they start from)
+    rs.rds_counts.clear();
+    if (!fe->rds_ids.empty()) {
+        rs.rds_counts.assign(fe->vfos.size(), -1);
+        rs.rds_offs.assign(fe->vfos.size(), 0);
+        for (size_t k0 = 0; k0 < fe->rds_ids.size(); k0 += kRdsPerLaunch) {
+            RdsArgs ra{};
+            ra.tab = fe->d_rds_tab; ra.arena_demod = fe->d_arena_demod + (size_t)aset * fe->arena_cap;
+            ra.arena_rds = fe->d_arena_rds + (size_t)aset * fe->rds_arena_cap;
+            ra.first = (int)k0; ra.count = (int)std::min<size_t>(kRdsPerLaunch, fe->rds_ids.size() - k0);
+            bool any = false;
+            for (int k = 0; k < ra.count; k++) {
+                const int id = fe->rds_ids[k0 + (size_t)k];
+                Vfo& v = fe->vfos[(size_t)id];
+                RdsBlk& b = ra.blk[k];
+                b.n = fe->groups[(size_t)v.group].last_n_final;
+                b.phase0 = v.rds_n * v.rds->dphi;
+                v.rds_n += (uint64_t)b.n;
+                int cur = b.n;
+                for (size_t s2 = 0; s2 < v.rds->stages.size(); s2++) {
+                    b.off[s2] = v.rds_off[s2];
+                    advance_decim(v.rds_off[s2], v.rds->stages[s2].decimation, cur, &b.nout[s2]);
+                    cur = b.nout[s2];
+                }
+                b.pphase = v.rds_pphase; b.poff = v.rds_poff; b.npoly = 0;
+                if (v.rds->tpp > 0) {
+                    // polyphase_resampler.h:75-93 in closed form
+                    const long long interp = v.rds->rp.interp, decim = v.rds->rp.decim;
+                    const long long c = (long long)cur - b.poff;
+                    long long cnt = 0;
+                    if (c > 0) cnt = (c * interp - b.pphase + decim - 1) / decim;
+                    const long long P = (long long)b.pphase + cnt * decim;
+                    v.rds_poff = (int)((long long)b.poff + P / interp - cur);
+                    v.rds_pphase = (int)(P % interp);
+                    b.npoly = (int)cnt;
+                    cur = (int)cnt;
+                }
+                b.nfinal = std::min(cur, v.rds_out_cap);
+                rs.rds_counts[(size_t)id] = b.nfinal;
+                rs.rds_offs[(size_t)id] = v.rds_out_off;
+                any = any || b.n > 0;
+            }
+            if (any) FE_TRY(fe, launch_rds(L, stl, ra));
+        }
+    }
     L.cur_graph = GRAPH_NONE;
     if (prof) { FE_TRY(fe, L.record(st, fe->pev[4])); fe->pev_valid = true; }
 
@@ -1365,6 +1540,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         if (fe->post_stereo > 0)
             FE_TRY(fe, L.memcpy_async(sd, rs.audio_r, fe->d_arena_audio_r + ao, fe->arena_used * sizeof(float), cudaMemcpyDeviceToHost));
     }
+    if (fe->readback && !fe->rds_ids.empty() && fe->rds_arena_used > 0)
+        FE_TRY(fe, L.memcpy_async(sd, rs.rds, fe->d_arena_rds + (size_t)aset * fe->rds_arena_cap, fe->rds_arena_used * sizeof(float2), cudaMemcpyDeviceToHost));
     if (!prof) FE_TRY(fe, L.wait(sd, fe->ev_fft[par])); // the block is done when its rows are on the host too
     FE_TRY(fe, L.record(sd, rs.done));
     fe->launches += L.kernels - kernels0;
@@ -1883,7 +2060,8 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     if (fe->st_s1b) cudaStreamSynchronize(fe->st_s1b);
     if (fe->st_bcast) cudaStreamSynchronize(fe->st_bcast);
     if (fe->st_desc) cudaStreamSynchronize(fe->st_desc);
-    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.post_taps2); cudaFree(v.if_state); }
+    for (Vfo& v : fe->vfos) { if (v.slab) cudaFree(v.slab); cudaFree(v.post_state); cudaFree(v.post_taps); cudaFree(v.post_taps2); cudaFree(v.if_state); cudaFree(v.rds_state); v.rds.reset(); }
+    fe->rds_plans.clear(); cudaFree(fe->d_rds_tab); cudaFree(fe->d_arena_rds);
     for (Group& g : fe->groups) { if (g.d_G) cudaFree(g.d_G); if (g.d_B) cudaFree(g.d_B); }
     for (int i = 0; i < 2; i++) { cudaFree(fe->tc_planes[i].hi); cudaFree(fe->tc_planes[i].lo); cudaFree(fe->tc_planes[i].sinv); }
     fe->vfos.clear(); fe->groups.clear(); fe->plan_cache.clear();
@@ -1904,6 +2082,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
         if (fe->rs[i].demod) cudaFreeHost(fe->rs[i].demod);
         if (fe->rs[i].audio) cudaFreeHost(fe->rs[i].audio);
         if (fe->rs[i].audio_r) cudaFreeHost(fe->rs[i].audio_r);
+        if (fe->rs[i].rds) cudaFreeHost(fe->rs[i].rds);
         if (fe->rs[i].rows) cudaFreeHost(fe->rs[i].rows);
         if (fe->rs[i].zoom) cudaFreeHost(fe->rs[i].zoom);
         if (fe->rs[i].hold) cudaFreeHost(fe->rs[i].hold);
@@ -2064,6 +2243,7 @@ int sdrpp_cuda_vfo_destroy(sdrpp_cuda_frontend* fe, int id) {
     remove_from_group(fe, id);
     if (v->slab) cudaFree(v->slab);
     cudaFree(v->post_state); cudaFree(v->post_taps); cudaFree(v->post_taps2); cudaFree(v->if_state); v->if_state = nullptr;
+    cudaFree(v->rds_state); v->rds_state = nullptr; v->rds.reset(); v->rds_slot = -1;
     *v = Vfo();
     return SDRPP_OK;
 }
@@ -2361,6 +2541,18 @@ int sdrpp_cuda_vfo_audio(sdrpp_cuda_frontend* fe, int id, const float** audio) {
     const bool have = (size_t)id < rs.counts.size() && rs.has_audio[(size_t)id];
     if (audio) *audio = (rs.audio && have) ? rs.audio + rs.offs[(size_t)id] : nullptr;
     return have ? rs.counts[(size_t)id] : 0;
+}
+
+int sdrpp_cuda_vfo_rds(sdrpp_cuda_frontend* fe, int id, const sdrpp_cf32** rds) {
+    Vfo* v;
+    int rc = vfo_get(fe, id, &v);
+    if (rc != SDRPP_OK) return rc;
+    if (fe->cur < 0) return fail(SDRPP_ERR_STATE, "no completed block");
+    if (!(v->post.enabled && v->post.wfm && v->post.wfm_rds)) return fail(SDRPP_ERR_STATE, "the RDS output is not enabled for this VFO");
+    const ResultSet& rs = fe->rs[fe->cur];
+    const bool have = (size_t)id < rs.rds_counts.size() && rs.rds_counts[(size_t)id] >= 0 && rs.rds;
+    if (rds) *rds = have ? reinterpret_cast<const sdrpp_cf32*>(rs.rds + rs.rds_offs[(size_t)id]) : nullptr;
+    return have ? rs.rds_counts[(size_t)id] : 0;
 }
 
 int sdrpp_cuda_vfo_audio_stereo(sdrpp_cuda_frontend* fe, int id, const float** left, const float** right) {

@@ -237,4 +237,40 @@ struct PostArgs {
 };
 cudaError_t launch_post(Launcher& L, int sid, const PostArgs& a, int total_vfos);
 
+// RDS side output of dsp::demod::BroadcastFM (demod/broadcast_fm.h:168-175,188-198): the discriminator output as (mpx, 0),
+// translated by -57 kHz (FrequencyXlator, 64-bit phase accumulator on the fp32-quantised increment) and resampled to 5 kS/s by
+// the decoder's RationalResampler (PowerDecimator stages, then the polyphase resampler). One CTA per VFO with the output on.
+constexpr int kRdsMaxStages = 4;
+constexpr int kRdsPerLaunch = 64;
+struct RdsDev {
+    uint32_t in_off;                 // the VFO's row in the demod arena
+    uint32_t out_off;                // its row in the RDS arena (float2)
+    int nstages;                     // PowerDecimator stages (0: RESAMP_ONLY / NONE)
+    int T[kRdsMaxStages], D[kRdsMaxStages];
+    const float* taps[kRdsMaxStages];
+    uint32_t buf_off[kRdsMaxStages]; // float2 offset of [T-1 history | block] in state
+    int interp, decim, tpp;          // polyphase resampler (tpp = 0: none)
+    const float* bank;               // [interp][tpp]
+    uint32_t pbuf_off;               // [tpp-1 history | block]
+    float2* state;
+    uint64_t dphi;
+};
+// per block and VFO: every integer of the reference's state machines, computed on the host (decimating_fir.h:51-62,
+// polyphase_resampler.h:75-93) -- the device keeps sample history only
+struct RdsBlk {
+    int n;                           // discriminator samples of this block
+    int off[kRdsMaxStages], nout[kRdsMaxStages];
+    int pphase, poff, npoly;         // polyphase state at the start of the block, outputs of the block
+    int nfinal;
+    uint64_t phase0;                 // NCO phase of the block's first sample
+};
+struct RdsArgs {
+    const RdsDev* tab;               // table of the VFOs with the output on
+    const float* arena_demod;
+    float2* arena_rds;
+    int first, count;                // table range of this launch
+    RdsBlk blk[kRdsPerLaunch];
+};
+cudaError_t launch_rds(Launcher& L, int sid, const RdsArgs& a);
+
 } // namespace sdrpp

@@ -40,7 +40,7 @@ sdrpp_cuda_frontend_set_graphs sdrpp_cuda_frontend_graph_stats
 sdrpp_cuda_frontend_wait_input sdrpp_cuda_frontend_pending sdrpp_cuda_frontend_drain sdrpp_cuda_frontend_join_streams
 sdrpp_cuda_comm_unique_id sdrpp_cuda_comm_create sdrpp_cuda_comm_destroy sdrpp_cuda_comm_info sdrpp_cuda_frontend_set_comm
 sdrpp_cuda_frontend_submit_shared sdrpp_cuda_frontend_set_fft_display sdrpp_cuda_fft_hold_row sdrpp_cuda_vfo_set_signal_info
-sdrpp_cuda_frontend_set_snr_smoothing sdrpp_cuda_vfo_signal_info sdrpp_cuda_signal_info sdrpp_cuda_vfo_audio_stereo sdrpp_cuda_design_bandpass_complex
+sdrpp_cuda_frontend_set_snr_smoothing sdrpp_cuda_vfo_signal_info sdrpp_cuda_signal_info sdrpp_cuda_vfo_audio_stereo sdrpp_cuda_vfo_rds sdrpp_cuda_design_bandpass_complex
 """.split()
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double
@@ -54,7 +54,7 @@ class FrontendCfg(C.Structure):
 
 class PostCfg(C.Structure):
     _fields_ = [("enabled", _i), ("fm_lowpass", _i), ("am_agc_mode", _i), ("ssb_agc", _i),
-                ("agc_attack", _d), ("agc_decay", _d), ("dc_block_rate", _d), ("agc_gain", C.c_float), ("wfm", _i), ("wfm_stereo", _i)]
+                ("agc_attack", _d), ("agc_decay", _d), ("dc_block_rate", _d), ("agc_gain", C.c_float), ("wfm", _i), ("wfm_stereo", _i), ("wfm_rds", _i)]
 
 
 class IfCfg(C.Structure):
@@ -141,6 +141,7 @@ def lib():
         L.sdrpp_cuda_vfo_squelch_state.argtypes = [_vp, _i, _vp, _vp]
         L.sdrpp_cuda_vfo_audio.argtypes = [_vp, _i, C.POINTER(_vp)]
         L.sdrpp_cuda_vfo_audio_stereo.argtypes = [_vp, _i, C.POINTER(_vp), C.POINTER(_vp)]
+        L.sdrpp_cuda_vfo_rds.argtypes = [_vp, _i, C.POINTER(_vp)]
         L.sdrpp_cuda_frontend_read_iq.argtypes = [_vp, _vp, _i]
         L.sdrpp_cuda_frontend_launches.restype = C.c_longlong
         L.sdrpp_cuda_frontend_launches.argtypes = [_vp]
@@ -478,9 +479,9 @@ class Frontend:
         return (a.copy(), d.copy() if d is not None else None) if copy else (a, d)
 
     def set_post(self, vid, enabled=True, fm_lowpass=True, am_agc_mode=0, ssb_agc=True, agc_attack=0.0, agc_decay=0.0,
-                 dc_block_rate=0.0, agc_gain=0.0, wfm=False, wfm_stereo=True):
+                 dc_block_rate=0.0, agc_gain=0.0, wfm=False, wfm_stereo=True, wfm_rds=False):
         """Post-detector stages of the demodulator behind the VFO (dsp::demod::FM / AM / SSB; wfm: dsp::demod::BroadcastFM)."""
-        cfg = PostCfg(int(enabled), int(fm_lowpass), int(am_agc_mode), int(ssb_agc), agc_attack, agc_decay, dc_block_rate, agc_gain, int(wfm), int(wfm_stereo))
+        cfg = PostCfg(int(enabled), int(fm_lowpass), int(am_agc_mode), int(ssb_agc), agc_attack, agc_decay, dc_block_rate, agc_gain, int(wfm), int(wfm_stereo), int(wfm_rds))
         _check(lib().sdrpp_cuda_vfo_set_post(self.h, vid, C.byref(cfg)), "vfo_set_post")
 
     def set_if_chain(self, vid, nb=False, nb_rate=500.0 / 24000.0, nb_level=10.0, squelch=False, squelch_level=-100.0, fmif_bins=0):
@@ -507,6 +508,14 @@ class Frontend:
             return np.zeros(0, np.float32), np.zeros(0, np.float32)
         return (np.ctypeslib.as_array(C.cast(l, C.POINTER(C.c_float)), shape=(n,)).copy(),
                 np.ctypeslib.as_array(C.cast(r, C.POINTER(C.c_float)), shape=(n,)).copy())
+
+    def vfo_rds(self, vid):
+        """BroadcastFM::rdsOut of the last waited block: complex samples at 5 kS/s (needs set_post(wfm=True, wfm_rds=True))."""
+        p = _vp()
+        n = _check(lib().sdrpp_cuda_vfo_rds(self.h, vid, C.byref(p)), "vfo_rds")
+        if n == 0:
+            return np.zeros(0, np.complex64)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(2 * n,)).copy().view(np.complex64)
 
     def fft_rows(self, copy=True):
         p = _vp()

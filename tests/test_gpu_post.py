@@ -186,3 +186,75 @@ def test_wfm_stereo_decoder(gpu, port, report, out_sr, stereo, low_pass):
         assert sp[k1, 0] > 10.0 * sp[k1, 1] and sp[k2, 1] > 10.0 * sp[k2, 0]   # >= 20 dB (the reference decoder itself gives 26 dB at 240 kS/s)
     if not stereo:
         assert np.array_equal(g[:, 0], g[:, 1])
+
+
+def wfm_rds_stream(nblocks, offset, seed):
+    """wfm_stream plus an RDS-like BPSK subcarrier at 57 kHz (1187.5 symbols/s)."""
+    rng = np.random.default_rng(seed)
+    n = nblocks * BLK
+    t = np.arange(n) / IN_SR
+    L, R = 0.5 * np.sin(2 * np.pi * 1000.0 * t), 0.3 * np.sin(2 * np.pi * 2500.0 * t)
+    bits = rng.integers(0, 2, int(t[-1] * 1187.5) + 2) * 2.0 - 1.0
+    sym = bits[(t * 1187.5).astype(int)]
+    mpx = (0.4 * (L + R) + 0.4 * (L - R) * np.sin(2 * np.pi * 38000.0 * t) + 0.1 * np.sin(2 * np.pi * 19000.0 * t)
+           + 0.05 * sym * np.cos(2 * np.pi * 57000.0 * t))
+    ph = 2 * np.pi * ((offset * t) % 1.0) + 2 * np.pi * 75e3 * np.cumsum(mpx) / IN_SR
+    x = 0.5 * np.exp(1j * ph) + 1e-4 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))
+    x = x.astype(np.complex64)
+    return [x[i * BLK:(i + 1) * BLK] for i in range(nblocks)]
+
+
+@pytest.mark.parametrize("out_sr", [250e3, 240e3])
+@pytest.mark.parametrize("stereo", [True, False])
+def test_wfm_rds_side_output(gpu, port, report, out_sr, stereo):
+    """BroadcastFM::rdsOut (broadcast_fm.h:168-175,188-198): (mpx, 0) -> FrequencyXlator(-57 kHz) -> RationalResampler(-> 5 kS/s).
+    Stage-isolated: the oracle's translation (ideal-NCO flavour) and resampler applied to the GPU's own
+    discriminator row; per-block sample counts exact, samples <= 1e-5. The reference decoder's own RDS output (fp32 rotator)
+    on the GPU's VFO output is reported beside it. Ragged blocks; two VFOs share the plan (250 k: a 5000-phase bank)."""
+    bw = 150e3
+    blocks = wfm_rds_stream(60, -300e3, 31)
+    sizes = [BLK, 7, BLK - 1, 5000, BLK, 1, 11999]
+    xl = [port.xlator(-57000.0, out_sr, ideal=True) for _ in range(2)]
+    rr = [port.resampler(out_sr, 5000.0) for _ in range(2)]
+    full = port.wfm(bw / 2.0, out_sr, stereo, True, rds=True)
+    got, want, ref_own = [[], []], [[], []], []
+    audio_g, audio_w = [], []
+    with gpu.Frontend(IN_SR, max_block=BLK) as fe:
+        ids = [fe.add_vfo(out_sr, bw, -300e3, po.DEMOD_QUAD), fe.add_vfo(out_sr, bw, -300e3 + 20e3, po.DEMOD_QUAD)]
+        for vid in ids:
+            fe.set_post(vid, fm_lowpass=True, wfm=True, wfm_stereo=stereo, wfm_rds=True)
+        other = fe.add_vfo(out_sr, bw, 100e3, po.DEMOD_QUAD)
+        fe.set_post(other, fm_lowpass=True, wfm=True, wfm_stereo=stereo)
+        for i, b in enumerate(blocks):
+            b = b[:sizes[i % len(sizes)]]
+            fe.process(po.FMT_CF32, b)
+            for k, vid in enumerate(ids):
+                y, dm = fe.vfo_output(vid)
+                r = fe.vfo_rds(vid)
+                w = rr[k].process(xl[k].process(dm.astype(np.complex64)))
+                assert len(r) == len(w), (i, k, len(r), len(w))
+                got[k].append(r); want[k].append(w)
+                if k == 0:
+                    lr, r_own = full.process(y)
+                    assert len(r_own) == len(r)
+                    ref_own.append(r_own)
+                    l, rt = fe.vfo_audio_stereo(vid)
+                    audio_g.append(np.stack([l, rt], axis=1)); audio_w.append(lr)
+            with pytest.raises(gpu.SdrppCudaError):
+                fe.vfo_rds(other)
+    for k in range(2):
+        g, w = np.concatenate(got[k]), np.concatenate(want[k])
+        assert len(g) > 500 and np.all(np.isfinite(g.view(np.float32)))
+        err = float(np.sqrt(np.sum(np.abs(g.astype(np.complex128) - w) ** 2) / np.sum(np.abs(w.astype(np.complex128)) ** 2)))
+        if k == 0:
+            o = np.concatenate(ref_own)
+            walk = float(np.sqrt(np.sum(np.abs(o.astype(np.complex128) - g) ** 2) / np.sum(np.abs(g.astype(np.complex128)) ** 2)))
+            report(f"8f-4 BroadcastFM RDS output {out_sr/1e3:g}k stereo={int(stereo)}", stage_isolated_vs_ideal_nco=err,
+                   reference_decoder_fp32_rotator_vs_gpu=walk, samples=len(g), gate=1e-5)
+            assert walk <= 2e-4, walk
+        assert err <= 1e-5, f"vfo {k}: rel-RMS {err:.3e}"
+    # the audio outputs are unchanged by the side output
+    ag, aw = np.concatenate(audio_g), np.concatenate(audio_w)
+    s = len(ag) // 4
+    aerr = float(np.sqrt(np.mean((ag[s:].astype(np.float64) - aw[s:]) ** 2)) / np.sqrt(np.mean(aw[s:].astype(np.float64) ** 2)))
+    assert aerr <= 1e-5, aerr

@@ -239,6 +239,18 @@ def test_port_matches_golden(port, case):
         assert np.array_equal(_bits(np.concatenate([fm.process(b) for b in y_sq])), _bits(data["fmif15"]))
         muted = [not b.any() for b in y_sq]
         assert any(muted) and not all(muted)  # the fixture exercises both squelch states
+    elif kind == "wfm_rds":
+        from tools.make_golden import wfm_input
+        sr, stereo = case["args"]
+        x = wfm_input(sum(case["blocks"]), sr, case["seed"])
+        d = port.wfm(75e3, sr, int(stereo), 1, rds=True)
+        lrs, rs, p = [], [], 0
+        for b in case["blocks"]:
+            lr, r = d.process(x[p:p + b]); p += b
+            lrs.append(lr); rs.append(r)
+        assert [len(r) for r in rs] == case["counts"]
+        assert np.array_equal(_bits(np.concatenate(lrs)), _bits(data["lr"]))
+        assert np.array_equal(_bits(np.concatenate(rs)), _bits(data["rds"]))
     else:
         pytest.fail("unknown golden kind " + kind)
 
@@ -259,3 +271,40 @@ def test_port_broadcast_fm_bit_exact_vs_reference(port, ref, stereo, low_pass):
     for i in range(0, n, blk):
         ya, yb = a.process(x[i:i + blk]), b.process(x[i:i + blk])
         assert ya.shape == (blk, 2) and np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+
+
+def _wfm_rds_signal(sr, n, seed=5):
+    from tools.make_golden import wfm_input
+    return wfm_input(n, sr, seed)
+
+
+@pytest.mark.parametrize("sr", [250e3, 240e3])
+@pytest.mark.parametrize("stereo", [1, 0])
+def test_port_broadcast_fm_rds_bit_exact_vs_reference(port, ref, sr, stereo):
+    """BroadcastFM with _rdsOut (broadcast_fm.h:168-175,188-198): the decoder's own xlator(-57 kHz) + RationalResampler(-> 5 kS/s)
+    on (mpx, 0); ragged blocks, audio and RDS outputs and the per-call RDS counts bit for bit."""
+    n = 30000
+    x = _wfm_rds_signal(sr, n)
+    a, b = port.wfm(75e3, sr, stereo, 1, rds=True), ref.wfm(75e3, sr, stereo, 1, rds=True)
+    sizes = [1250, 1, 777, 1250, 3000, 2, 1250]
+    i, k, total = 0, 0, 0
+    while i < n:
+        m = min(sizes[k % len(sizes)], n - i); k += 1
+        (ya, ra), (yb, rb) = a.process(x[i:i + m]), b.process(x[i:i + m])
+        assert np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+        assert len(ra) == len(rb) and np.array_equal(ra.view(np.uint32), rb.view(np.uint32))
+        total += len(ra)
+        i += m
+    assert abs(total - n * 5000.0 / sr) <= 2 + n * 1e-4     # 250 k: IntSR rounds to 7813, interp/decim = 5000/7813
+
+
+def test_port_rds_ideal_flavour_close_to_rotator(port):
+    """The ideal-NCO flavour of the RDS translation against the reference rotator on a short run: the rotator has barely
+    walked yet, so the two agree to ~1e-6; everything behind the translation is the same code."""
+    sr, n = 250e3, 25000
+    x = _wfm_rds_signal(sr, n)
+    a, b = port.wfm(75e3, sr, 1, 1, rds=True), port.wfm(75e3, sr, 1, 1, rds=True, ideal_nco=True)
+    (_, ra), (_, rb) = a.process(x), b.process(x)
+    assert len(ra) == len(rb) > 400
+    err = np.sqrt(np.sum(np.abs(ra - rb) ** 2) / np.sum(np.abs(rb) ** 2))
+    assert err < 2e-5, err

@@ -54,6 +54,19 @@ def make_post(lib, kind, a):
     return lib.ssb_full(a["mode"], a["bw"], a["sr"], bool(a["agc"]), a["attack"], a["decay"])
 
 
+def wfm_input(n, sr, seed):
+    """FM-modulated broadcast multiplex at the VFO rate: L / R tones, 19 kHz pilot, L-R on 38 kHz, a BPSK-like 57 kHz RDS
+    subcarrier (1187.5 symbols/s), 75 kHz deviation."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n) / sr
+    L, R = 0.5 * np.sin(2 * np.pi * 1000 * t), 0.3 * np.sin(2 * np.pi * 2500 * t)
+    bits = rng.integers(0, 2, int(n / sr * 1187.5) + 2) * 2.0 - 1.0
+    sym = bits[(t * 1187.5).astype(int)]
+    mpx = (0.4 * (L + R) + 0.4 * (L - R) * np.sin(2 * np.pi * 38000 * t) + 0.1 * np.sin(2 * np.pi * 19000 * t)
+           + 0.05 * sym * np.cos(2 * np.pi * 57000 * t))
+    return (0.5 * np.exp(1j * 2 * np.pi * 75e3 * np.cumsum(mpx) / sr)).astype(np.complex64)
+
+
 def pcm_input(n, seed):
     """Block whose negative excursion exceeds its (signed) maximum, so the compressor's saturation branch is taken."""
     rng = np.random.default_rng(seed)
@@ -151,6 +164,18 @@ def main():
     y_fm = [fm.process(b) for b in y_sq]
     add("if_chain_nb_squelch", "if_chain", (500.0 / 48000.0, 3.0, -20.0, 20, 240),
         {"nb": np.concatenate(y_nb), "out": np.concatenate(y_sq), "fmif15": np.concatenate(y_fm)}, seed=13)
+
+    # dsp::demod::BroadcastFM with its RDS side output: stereo audio and the 5 kS/s RDS baseband, ragged blocks
+    for name, sr, stereo, seed in [("250k_stereo", 250e3, 1, 14), ("240k_mono", 240e3, 0, 15)]:
+        blocks = [1250, 1, 777, 1250, 3000, 2, 1250, 1250, 1250, 1250]
+        x = wfm_input(sum(blocks), sr, seed)
+        d = ref.wfm(75e3, sr, stereo, 1, rds=True)
+        lrs, rs, p = [], [], 0
+        for b in blocks:
+            lr, r = d.process(x[p:p + b]); p += b
+            lrs.append(lr); rs.append(r)
+        add("wfm_rds_" + name, "wfm_rds", (sr, stereo), {"lr": np.concatenate(lrs), "rds": np.concatenate(rs)}, seed=seed, blocks=blocks,
+            counts=[len(r) for r in rs])
 
     json.dump({"generator": "tools/make_golden.py", "source": ref.lib.ref_build_info.restype and "oracle/_ref/libsdrpp_ref.so (reference dsp/ headers, IEEE flags)",
                "cases": cases}, open(os.path.join(GOLD, "manifest.json"), "w"), indent=1)
