@@ -438,6 +438,26 @@ def run_gpu(args, rank, world, local_rank):
         h2d_gbs = reps * blk_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
         e2e["h2d_link_gbs"] = h2d_gbs
         e2e["h2d_link_bound_msps"] = h2d_gbs * 1e9 / w.bytes_per_sample / 1e6
+        # ... and with this rank's result bytes going the other way at the same time, in the proportion of a step: PCIe is
+        # full duplex, but the read requests of the block copy share the upstream direction with the result data
+        # (tools/e2e_probe.py: 53 -> 41 GB/s with the reverse direction saturated). This is the ceiling of an end-to-end
+        # number that reads every result back on this host.
+        d2h_rank0 = max(1, int(d2h if world == 1 else sum(len(fe.vfo_output(vid, copy=False)[0]) * (8 + (4 if v[3] else 0)) for vid, v in zip(ids, mine))
+                               + int(w.fft_size * 4 * (w.block / w.decim) / w.fft_size)))
+        dsrc2 = torch.empty(d2h_rank0, dtype=torch.uint8, device=dev)
+        hdst2 = torch.empty(d2h_rank0, dtype=torch.uint8).pin_memory()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        c0.record()
+        for _ in range(reps):
+            hdst.copy_(hsrc, non_blocking=True)
+            with torch.cuda.stream(side):
+                hdst2.copy_(dsrc2, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        bidir_gbs = reps * blk_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        e2e["h2d_link_gbs_with_results_going_back"] = bidir_gbs
+        e2e["link_bound_bidirectional_msps"] = bidir_gbs * 1e9 / w.bytes_per_sample / 1e6
         for p in pin:
             p.free()
     barrier()

@@ -403,7 +403,10 @@ cudaError_t launch_mix_only(Launcher& L, int sid, const Stage1Args& a) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kTailThreads = 256;
 // 36 KB samples + 4 KB slack + 12 KB taps = 52 KB: four CTAs per SM, so 512 VFOs are a single wave on 148 SMs
-constexpr int kTailSmemSamples = 4608; // staged input samples per chunk
+#ifndef SDRPP_TAIL_SMEM_SAMPLES
+#define SDRPP_TAIL_SMEM_SAMPLES 4608
+#endif
+constexpr int kTailSmemSamples = SDRPP_TAIL_SMEM_SAMPLES; // staged input samples per chunk
 constexpr int kTailTapFloats = 3072;   // staged taps per stage
 
 // Stage one chunk of a stage's input [first, first+n) from the slab (L2) into shared memory.
@@ -568,7 +571,7 @@ __device__ __noinline__ void if_chain_run(float* __restrict__ r, float2* p, int 
     p[-1] = make_float2(r[IF_PREV_RE], r[IF_PREV_IM]);
 }
 
-static_assert(kIfMaxBlock == kTailSmemSamples / 2 - 2 * kIfMaxBins, "IF chain staging: two half areas with room for the FMIF history");
+static_assert(SDRPP_TAIL_SMEM_SAMPLES != 4608 || kIfMaxBlock == kTailSmemSamples / 2 - 2 * kIfMaxBins, "IF chain staging: two half areas with room for the FMIF history");
 
 // dsp::noise_reduction::FMIF::process (noise_reduction/fm_if.h:45-74) for a whole block, one output per thread: the
 // last `bins` samples under a Nuttall window, forward DFT (bins = 9, 15, 31, 32 in the radio module: direct
@@ -755,11 +758,14 @@ tail_kernel(const TailArgs* __restrict__ ap) {
 // Same arithmetic (fir.h:62-83, decimating_fir.h:45-68, polyphase_resampler.h:69-99), same slab layout, so the two
 // kernels can alternate block by block. The engine picks this one per group and block (tail_fast_fits).
 // ---------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 1024;      // the kernel runs when there are fewer VFOs than SMs: one CTA per SM, all of its threads on one VFO
-constexpr int kFastMaxSamples = 20480;  // float2 of stage regions + split-K scratch a CTA may hold (160 KB)
+// Two shapes of the same kernel: 1024 threads and up to 160 KB of stage regions when there are fewer VFOs than SMs (one CTA
+// per SM, all of its threads on one VFO), and 256 threads with <= 39.7 KB of regions -- four CTAs per SM, so that 512 VFOs
+// are one wave and one CTA's round trip to L2 hides behind its neighbours' arithmetic -- when the VFO set is larger.
+constexpr int kFastThreadsWide = 1024, kFastThreadsNarrow = 256;
+__host__ __device__ constexpr int fast_max_samples(int nt) { return nt >= 1024 ? 20480 : 5080; }  // float2 of stage regions + split-K scratch
 constexpr int kFastTapFloats = 4096;
 constexpr int kFastOB = 4;              // outputs per thread of a FIR stage (register blocking)
-constexpr int kFastScratch = kFastThreads * kFastOB; // float2: split-K partial sums
+// split-K partial sums: threads * kFastOB float2 of scratch
 
 // A stage's input region [T-1 history | n_in data] in shared memory. FIR stages read it register-blocked (a thread owns
 // four consecutive outputs, so a sample and a float4 of taps serve up to four MACs -- at one load per MAC the kernel was
@@ -792,7 +798,13 @@ __host__ __device__ inline int fast_tap_floats(const TailStage& st) {
     return 4 * (st.T + (kFastOB - 1) * D);   // float4 table (h[s], h[s-D], h[s-2D], h[s-3D]) for s < T + 3D
 }
 
-bool tail_fast_fits(const TailGroup& g, int* samples) {
+__host__ __device__ inline int fast_tap_bytes(int tap_floats) { return (tap_floats * 4 + 15) & ~15; }
+// The narrow shape has to fit beside the persistent stage-1 CTA of the NEXT block (189 KB of the SM's 228 KB with its
+// four-chunk operand ring): tap tables + stage regions <= 41 KB, sized per group instead of a fixed tap area.
+constexpr int kFastNarrowBytes = 41984;
+
+bool tail_fast_fits(const TailGroup& g, int* samples, int threads, int* tap_floats) {
+    const int kFastScratch = threads * kFastOB, kFastMaxSamples = fast_max_samples(threads);
     if (g.nstages > kTailMaxStages || g.nstages < 1) return false;
     int pos = 0, tp = 0;
     for (int s = g.s_begin; s < g.nstages; s++) {
@@ -804,6 +816,8 @@ bool tail_fast_fits(const TailGroup& g, int* samples) {
     pos += (g.n_final + 2 + 1) & ~1;
     pos += kFastScratch;
     if (samples) *samples = pos;
+    if (tap_floats) *tap_floats = tp;
+    if (threads < 1024 && fast_tap_bytes(tp) + (pos + 8) * (int)sizeof(float2) > kFastNarrowBytes) return false;
     return pos <= kFastMaxSamples && tp <= kFastTapFloats;
 }
 
@@ -818,12 +832,13 @@ __device__ long long g_tailfast_trace[16];
 #define TF_MARK(i) do {} while (0)
 #endif
 
-__global__ void __launch_bounds__(kFastThreads, 1)
+template <int kFastThreads>
+__global__ void __launch_bounds__(kFastThreads, kFastThreads >= 1024 ? 1 : 4)
 tail_fast_kernel(const TailArgs* __restrict__ ap) {
     const TailArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory)
     extern __shared__ __align__(16) unsigned char tail_smem[];
-    float* taps = reinterpret_cast<float*>(tail_smem);                          // [kFastTapFloats]
-    float2* x = reinterpret_cast<float2*>(tail_smem + kFastTapFloats * 4);      // stage regions ..., [prev | final], split-K scratch
+    float* taps = reinterpret_cast<float*>(tail_smem);                          // the group's tap tables, then (16-byte aligned):
+    float2* x;                                                                  // stage regions ..., [prev | final], split-K scratch
     const int tid = threadIdx.x;
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
@@ -852,6 +867,7 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
             pos += fast_region_floats2(g.st[s], &reg[s], pos);
             tp += fast_tap_floats(g.st[s]);
         }
+        x = reinterpret_cast<float2*>(tail_smem + fast_tap_bytes(tp));
     }
     FastRegion& rf = reg[g.nstages];     // final: natural order, element 0 = last output of the previous block
     rf.base = pos; rf.M = 1; rf.lgM = 0; rf.qs = 0; rf.len = g.n_final + 1;
@@ -1023,17 +1039,18 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
     TF_MARK(12);
 }
 
-cudaError_t launch_tail_fast(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos) {
+cudaError_t launch_tail_fast(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos, int threads) {
     if (total_vfos <= 0) return cudaSuccess;
-    int need = 0;
+    if (threads != kFastThreadsWide && threads != kFastThreadsNarrow) return cudaErrorInvalidValue;
+    size_t smem = 0;
     for (int i = 0; i < a.ngroups; i++) {
-        int n = 0;
-        if (!tail_fast_fits(a.g[i], &n)) return cudaErrorInvalidValue;
-        need = std::max(need, n);
+        int n = 0, tp = 0;
+        if (!tail_fast_fits(a.g[i], &n, threads, &tp)) return cudaErrorInvalidValue;
+        smem = std::max(smem, (size_t)fast_tap_bytes(tp) + (size_t)(n + 8) * sizeof(float2));
     }
-    const size_t smem = (size_t)kFastTapFloats * sizeof(float) + (size_t)(need + 8) * sizeof(float2);
-    if (cudaError_t e = ensure_dynamic_smem((const void*)tail_fast_kernel, kFastTapFloats * sizeof(float) + (kFastMaxSamples + 8) * sizeof(float2)); e != cudaSuccess) return e;
-    return L.kernel(sid, (const void*)tail_fast_kernel, dim3((unsigned)total_vfos), dim3(kFastThreads), smem, d_a);
+    const void* fn = threads == kFastThreadsWide ? (const void*)tail_fast_kernel<kFastThreadsWide> : (const void*)tail_fast_kernel<kFastThreadsNarrow>;
+    if (cudaError_t e = ensure_dynamic_smem(fn, kFastTapFloats * sizeof(float) + (fast_max_samples(threads) + 8) * sizeof(float2)); e != cudaSuccess) return e;
+    return L.kernel(sid, fn, dim3((unsigned)total_vfos), dim3((unsigned)threads), smem, d_a);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -169,8 +169,14 @@ struct S1TSplitArgs {    // per-block arguments, read through the launcher's des
     RingRef ring;
     S1TPlanes pl;
     int64_t g_first, abs_end;
+    // fused ingest (cf32 blocks that need no conversion): samples at or after abs_block come from the block itself and are
+    // written to the ring on the way -- the separate 4.9 MB ring copy and its launch are gone
+    const float2* raw;
+    int64_t abs_block;
+    int conj;
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
 s1t_split_kernel(const S1TSplitArgs* __restrict__ ap) {
     __shared__ float red[8];
@@ -184,8 +190,49 @@ s1t_split_kernel(const S1TSplitArgs* __restrict__ ap) {
     const int r = t / cpr, c16 = t - r * cpr;
     const int64_t n0 = g * (int64_t)(8 * D) + (int64_t)r * D + (int64_t)c16 * 4 + pl.origin;
     float v[8];
-    {
-        const uint32_t i0 = (uint32_t)((uint64_t)n0 & ring.mask);
+    const uint32_t i0 = (uint32_t)((uint64_t)n0 & ring.mask);
+    bool from_ring = true;
+    if constexpr (FUSED) {
+        const int64_t abs_block = ap->abs_block;
+        if (n0 + 3 >= abs_block && n0 < abs_end) {
+            from_ring = false;
+            const float2* __restrict__ raw = ap->raw;
+            const float sgn = ap->conj ? -1.0f : 1.0f;
+            if (n0 >= abs_block && n0 + 3 < abs_end) {
+                const int64_t k = n0 - abs_block;
+                if ((k & 1) == 0) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(raw + k));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(raw + k + 2));
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const float2 x = __ldg(raw + k + i); v[2 * i] = x.x; v[2 * i + 1] = x.y; }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) v[2 * i + 1] *= sgn;
+                // n0 is a multiple of 4 and so is the ring length: 16-byte aligned, never wraps inside the quad
+                float4* o = reinterpret_cast<float4*>(ring.base + i0);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+                // the quad straddles the start or the end of the block
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int64_t n = n0 + i;
+                    float2 x = make_float2(0.0f, 0.0f);
+                    if (n >= abs_block && n < abs_end) {
+                        x = __ldg(raw + (n - abs_block));
+                        x.y *= sgn;
+                        ring.base[(i0 + (uint32_t)i) & ring.mask] = x;
+                    } else if (n >= 0 && n < abs_block) {
+                        x = ring.base[(i0 + (uint32_t)i) & ring.mask];
+                    }
+                    v[2 * i] = x.x; v[2 * i + 1] = x.y;
+                }
+            }
+        }
+    }
+    if (from_ring) {
         const float4 a = *reinterpret_cast<const float4*>(ring.base + i0);
         const float4 b = *reinterpret_cast<const float4*>(ring.base + i0 + 2);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
@@ -228,14 +275,27 @@ s1t_split_kernel(const S1TSplitArgs* __restrict__ ap) {
     if (t == 0) pl.sinv[slot] = __uint_as_float((uint32_t)(127 - e) << 23);
 }
 
-cudaError_t launch_s1t_split(Launcher& L, int sid, RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end) {
+// raw != nullptr: the block [abs_block, abs_end) is still in the caller's cf32 buffer `raw` and this launch also writes it
+// to the ring (the caller has checked with s1t_split_covers that every new sample lies in a converted group)
+cudaError_t launch_s1t_split(Launcher& L, int sid, RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end,
+                             const void* raw, int64_t abs_block, bool conj) {
     if (abs_end <= abs_begin) return cudaSuccess;
     const int gs = 8 * pl.D;
     if (abs_end <= pl.origin) return cudaSuccess;
     const int64_t g0 = std::max<int64_t>(abs_begin - pl.origin, 0) / gs, g1 = (abs_end - 1 - pl.origin) / gs;
-    const S1TSplitArgs* d = L.push(S1TSplitArgs{ ring, pl, g0, abs_end });
+    const S1TSplitArgs* d = L.push(S1TSplitArgs{ ring, pl, g0, abs_end, reinterpret_cast<const float2*>(raw), abs_block, conj ? 1 : 0 });
     if (!d) return cudaErrorMemoryAllocation;
-    return L.kernel(sid, (const void*)s1t_split_kernel, dim3((unsigned)(g1 - g0 + 1)), dim3((unsigned)(2 * pl.D)), 0, d);
+    const void* fn = raw ? (const void*)s1t_split_kernel<true> : (const void*)s1t_split_kernel<false>;
+    return L.kernel(sid, fn, dim3((unsigned)(g1 - g0 + 1)), dim3((unsigned)(2 * pl.D)), 0, d);
+}
+
+// Does a split launch over [abs_begin, abs_end) convert every sample from abs_block on? (Not at the very start of a stream,
+// where the first group begins at the row origin.)
+bool s1t_split_covers(const S1TPlanes& pl, int64_t abs_begin, int64_t abs_block, int64_t abs_end) {
+    if (abs_end <= abs_begin || abs_end <= pl.origin || abs_begin > abs_block) return false;
+    const int gs = 8 * pl.D;
+    const int64_t g0 = std::max<int64_t>(abs_begin - pl.origin, 0) / gs;
+    return g0 * gs + pl.origin <= abs_block;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -407,7 +467,14 @@ __device__ __forceinline__ void s1t_epilogue_tile(uint32_t tmem_acc, int q, int 
 // group over a contiguous range of time tiles.
 // ---------------------------------------------------------------------------------------------
 template <int NKH>
+// Experiment knob (profiles/r2m_coresidency.txt): -DSDRPP_S1T_MAXNREG=80 (the compiler's own choice is 96; 16-20 bytes of
+// spills, same kernel time) together with SDRPP_S1T_SMEM_CAP=190000 leaves 19 K registers and 42 KB of shared memory per SM
+// for a narrow tail CTA of the previous block.
+#ifdef SDRPP_S1T_MAXNREG
+__global__ void __maxnreg__(SDRPP_S1T_MAXNREG)
+#else
 __global__ void __launch_bounds__(kThreads, 1)
+#endif
 s1t_kernel(const S1TArgs* __restrict__ ap) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const S1TArgs& a = *ap;   // per-block arguments in the launcher's descriptor (device memory): read once per role
@@ -728,10 +795,12 @@ cudaError_t launch_s1t(Launcher& L, int sid, S1TArgs& a, int num_sms) {
     int ctas = 0;
     for (int i = 0; i < a.ngroups; i++) { a.g[i].cta_begin = ctas; ctas += a.g[i].cta_per_vtile * a.g[i].n_vtiles; }
     // A-operand ring: as many 16 KB chunks as fit beside the largest B image
-    const size_t cap = 232448;
+    // SDRPP_S1T_SMEM_CAP (experiment knob): a smaller budget shortens the operand ring; four chunks (190000) measured as fast
+    // as the six to eight that fit in 227 KB
+    static const size_t cap = getenv("SDRPP_S1T_SMEM_CAP") ? (size_t)atol(getenv("SDRPP_S1T_SMEM_CAP")) : 232448;
     int nch = kMaxChunks;
     while (nch > 2 * NKH && s1t_smem_bytes(NKH, maxA, nch) > cap) nch--;
-    if (s1t_smem_bytes(NKH, maxA, nch) > cap) return cudaErrorInvalidValue;
+    if (s1t_smem_bytes(NKH, maxA, nch) > 232448) return cudaErrorInvalidValue;   // `cap` is a preference, 227 KB the limit (A = 8)
     a.nchunks = nch;
     const size_t smem = s1t_smem_bytes(NKH, maxA, nch);
     if (cudaError_t e = ensure_dynamic_smem(NKH == 1 ? (const void*)s1t_kernel<1> : (const void*)s1t_kernel<2>, smem); e != cudaSuccess) return e;

@@ -28,6 +28,11 @@ cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
     size_t& cur = done[std::make_pair(func, dev)];
     if (bytes <= cur) return cudaSuccess;
     e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    // The SM's shared-memory carve-out is chosen per kernel from what ITS CTAs need (stage 1: 189 KB -> the 196 KB setting),
+    // and it cannot change while CTAs are resident: without this preference a tail CTA of the previous block never fits
+    // beside the persistent stage-1 CTA although 228 KB would hold both (seen as a tail kernel that takes 75 us instead of 37
+    // whenever it overlaps stage 1, tools/timeline_probe.py). Every kernel with opt-in shared memory asks for the largest.
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) cur = bytes;
     return e;
 }

@@ -419,8 +419,16 @@ struct sdrpp_cuda_frontend {
     // Where the spectrum kernels of a block run (SDRPP_FFT_ORDER): 0 = a branch of the stage-1 graph, joined at its end;
     // 1 = a graph of their own on the spectrum stream behind stage 1 (beside the tail); 2 = a graph of their own right
     // behind ingest (ingest launched directly, beside the fp16 split and stage 1: the stream topology of round 1).
-    int fft_order = 0;
+    int fft_order = -1;                           // -1: by where the block comes from (2 device-resident, 0 host), see process_block
+    bool blk_device_src = false;                  // the block being planned was submitted from device memory
+    bool fuse_ingest = true;                      // SDRPP_FUSE_INGEST=0: always the separate ingest kernel
 
+    // timeline probe (SDRPP_TIMELINE=1, tools/timeline_probe.py): timing events on the streams the kernels really run on,
+    // for the last kTlBlocks blocks; blocks run command by command while it is on
+    static constexpr int kTlBlocks = 16, kTlMarks = 8;
+    bool timeline = false;
+    cudaEvent_t tl_ev[kTlBlocks][kTlMarks] = {};
+    long long tl_blk[kTlBlocks] = {};
     // profiling
     bool profiling = false;
     cudaEvent_t pev[5] = { nullptr };
@@ -1044,7 +1052,10 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     L.begin_block(fe->h_desc[slot_d], fe->d_desc[slot_d], kDescBytes);
     L.deferred = true;
     fe->run_replayable[GRAPH_S1] = fe->run_replayable[GRAPH_TAIL] = fe->run_replayable[GRAPH_FFT] = true;
-    const int fft_order = prof ? 0 : fe->fft_order;
+    // Default: a block that arrives over the host link hides the join of order 0 behind its copy and gains from the smaller
+    // number of submissions (end to end 5.0 -> 5.3 GS/s); a device-resident block runs the spectrum beside the split and the
+    // start of stage 1 (order 2: 6.2 -> 6.5 GS/s). profiles/r2l_graph_ab.txt.
+    const int fft_order = prof ? 0 : fe->fft_order >= 0 ? fe->fft_order : (fe->blk_device_src ? 2 : 0);
     const long long kernels0 = L.kernels;
     const int st = SID_MAIN;
     if (prof) FE_TRY(fe, L.record(st, fe->pev[0]));
@@ -1057,6 +1068,14 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     const int par = (int)(fe->blk & 1);
     if (!prof && fe->ev_tail_valid[par]) FE_TRY(fe, L.wait(st, fe->ev_tail[par])); // stage-1 region `par` was last read by the tail of block i-2
 
+    auto tl_mark = [&](int sid, int k) -> int {
+        if (!fe->timeline || prof) return SDRPP_OK;
+        const int slot = (int)(fe->blk % sdrpp_cuda_frontend::kTlBlocks);
+        fe->tl_blk[slot] = fe->blk;
+        FE_TRY(fe, L.record(sid, fe->tl_ev[slot][k]));
+        return SDRPP_OK;
+    };
+    if (int rc = tl_mark(st, 0); rc != SDRPP_OK) return rc;
     // ---- GRAPH_S1: ingest, [spectrum kernels (forked),] fp16 split, stage 1 (the descriptor is uploaded by execute_block) --
     L.cur_graph = (prof || fft_order == 2) ? GRAPH_NONE : GRAPH_S1;
 
@@ -1066,8 +1085,12 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     const bool conj = fe->cfg.invert_iq != 0;
     const bool dc = fe->cfg.dc_blocking != 0;
     int n = count;
+    // A cf32 block that needs no conversion is not copied to the ring by a kernel of its own: the fp16 split of the
+    // tensor-core stage 1 reads it in place and writes the ring on the way (launch_s1t_split with `raw`). Decided below, when
+    // the split is planned; until then the plain ingest is pending.
+    bool plain_pending = false;
     if (fe->fe_stages.empty() && !dc) {
-        FE_TRY(fe, launch_ingest(L, st, fmt, d_in, count, ring, wpos, conj, scale));
+        plain_pending = true;
     } else {
         const RingRef lin_dc{ fe->dc_in, 0xFFFFFFFFu };
         if (fe->fe_stages.empty()) {
@@ -1113,99 +1136,6 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     const int64_t abs_block = fe->abs_pos;
     fe->abs_pos += n;
     fe->last_count = n;
-    if (prof) FE_TRY(fe, L.record(st, fe->pev[1]));
-    // Three consumers of the ring run concurrently (the reference's Splitter fan-out): the spectrum on st_fft,
-    // stage 1 on st, and the tail of the PREVIOUS block on st_tail. Profiling serialises everything on st so
-    // that per-family CUDA-event times are those of the kernels alone.
-    const int sf = prof ? st : SID_FFT;
-    const int stl = prof ? st : SID_TAIL;
-    const int aset = (int)(&rs - fe->rs); // result set (and result arena) of this block
-    if (!prof && fft_order != 1) {
-        FE_TRY(fe, L.record(st, fe->ev_ingest));
-        FE_TRY(fe, L.wait(sf, fe->ev_ingest));
-    }
-    // fft_order 1 / 2: the spectrum commands go to a list of their own (a GRAPH_FFT run on the spectrum stream), spliced in
-    // behind stage 1 (1) or right here (2)
-    std::vector<Cmd> main_cmds;
-    const int graph_before_fft = L.cur_graph;
-    if (fft_order != 0) { main_cmds.swap(L.cmds); L.cur_graph = GRAPH_FFT; }
-
-    // ---- spectrum frames completed by this block (reshaper.h:102-129 keep/skip + handler) --------
-    // Their kernels are a branch of the stage-1 graph; the device-to-host copies of the rows follow the graph (a copy
-    // inside it would hold the next block's stage 1 back until 4 MB per row have crossed the link).
-    struct PendingCopy { void* dst; const void* src; size_t bytes; };
-    std::vector<PendingCopy> fft_copies;
-    auto fft_copy = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
-        if (prof) return L.memcpy_async(st, dst, src, bytes, cudaMemcpyDeviceToHost);
-        if (fft_order != 0) { const int g = L.cur_graph; L.cur_graph = GRAPH_NONE; const cudaError_t e = L.memcpy_async(sf, dst, src, bytes, cudaMemcpyDeviceToHost); L.cur_graph = g; return e; }
-        fft_copies.push_back(PendingCopy{ dst, src, bytes });
-        return cudaSuccess;
-    };
-    rs.nrows = 0;
-    float* const rows_dev = fe->d_rows ? fe->d_rows + (size_t)par * fe->rows_cap * fe->cfg.fft_size : nullptr;
-    if (fe->cfg.fft_size > 0) {
-        const int N = fe->cfg.fft_size;
-        const int64_t interval = (int64_t)fe->nz + fe->skip;
-        int frames = 0;
-        const int64_t first = fe->fft_next;
-        while (fe->fft_next + fe->nz <= fe->abs_pos && frames < fe->rows_cap) { frames++; fe->fft_next += interval; }
-        // frames beyond the row buffer are dropped (like a waterfall that cannot keep up)
-        while (fe->fft_next + fe->nz <= fe->abs_pos) fe->fft_next += interval;
-        for (int f0 = 0; f0 < frames; f0 += fe->inter_frames) {
-            SpectrumArgs a{};
-            a.in = fe->ring; a.ring_mask = fe->ring_mask;
-            a.start = (uint32_t)((uint64_t)(first + (int64_t)f0 * interval) & fe->ring_mask);
-            a.frame_stride = (uint32_t)interval;
-            a.nz = fe->nz; a.window = fe->d_window; a.inter = fe->d_inter;
-            a.rows = rows_dev + (size_t)f0 * N; a.X = nullptr;
-            a.frames = std::min(fe->inter_frames, frames - f0);
-            FE_TRY(fe, launch_spectrum(L, sf, N, a, nullptr));
-        }
-        rs.nrows = frames;
-    }
-    // zoom / display state / level read-out write buffers that the copies behind the graph read (not double-buffered): such a
-    // block runs command by command, where the spectrum stream orders kernels and copies
-    if (fft_order == 0 && rs.nrows > 0 && (fe->zoom_out > 0 || fe->nsig > 0 || fe->sig_dirty)) fe->run_replayable[GRAPH_S1] = false;
-    if (rs.nrows > 0 && fe->zoom_out > 0) {
-        FE_TRY(fe, launch_fft_zoom(L, sf, rows_dev, fe->cfg.fft_size, rs.nrows, fe->d_zoom_idx, fe->zoom_out, fe->zoom_ranged, fe->d_zoom));
-        if (fe->disp_smoothing || fe->disp_hold) {
-            const int W = fe->zoom_out;
-            FE_TRY(fe, launch_fft_display(L, sf, fe->d_zoom, W, rs.nrows, fe->disp_smoothing, fe->disp_alpha, fe->d_disp, fe->disp_hold, fe->disp_hold_speed,
-                                          fe->d_disp + W, fe->d_disp + 2 * W));
-            if (fe->readback && fe->disp_hold) FE_TRY(fe, fft_copy(rs.hold, fe->d_disp + W, (size_t)W * sizeof(float)));
-        }
-        if (fe->readback)
-            FE_TRY(fe, fft_copy(rs.zoom, fe->d_zoom, (size_t)rs.nrows * fe->zoom_out * sizeof(float)));
-    }
-    rs.nsig = 0;
-    rs.sig_done.clear();
-    if (rs.nrows > 0 && fe->cfg.fft_size > 0) {
-        int rc = refresh_signal_info(fe);
-        if (rc != SDRPP_OK) return rc;
-        if (fe->nsig > 0) {
-            FE_TRY(fe, launch_signal_info(L, sf, rows_dev, fe->cfg.fft_size, rs.nrows, fe->d_sig_bins, fe->nsig, fe->d_sig));
-            if (fe->readback)
-                FE_TRY(fe, fft_copy(rs.sig, fe->d_sig, (size_t)rs.nrows * fe->nsig * sizeof(float2)));
-            rs.nsig = fe->nsig;
-            rs.sig_slot.assign(fe->vfos.size(), -1);
-            for (size_t id = 0; id < fe->vfos.size(); id++) if (fe->vfos[id].alive && fe->vfos[id].sig_on) rs.sig_slot[id] = fe->vfos[id].sig_slot;
-        }
-    }
-    if (fe->readback && rs.nrows > 0 && (fe->zoom_keep_raw || fe->zoom_out <= 0))
-        FE_TRY(fe, fft_copy(rs.rows, rows_dev, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float)));
-    if (prof) { FE_TRY(fe, L.record(st, fe->pev[2])); fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false; }
-    else if (fft_order == 0) FE_TRY(fe, L.record(sf, fe->ev_fftk));   // the spectrum branch joins the main stream again at the end of the stage-1 graph
-    std::vector<Cmd> fft_cmds;
-    if (fft_order != 0) {
-        L.cur_graph = GRAPH_NONE;
-        FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
-        fe->ev_fft_valid[par] = true;
-        fft_cmds.swap(L.cmds);
-        L.cmds.swap(main_cmds);
-        if (fft_order == 2) { L.cmds.insert(L.cmds.end(), fft_cmds.begin(), fft_cmds.end()); fft_cmds.clear(); L.cur_graph = GRAPH_S1; }
-        else L.cur_graph = graph_before_fft;
-    }
-
     // ---- channelizer ----------------------------------------------------------------------------
     debug_stale("before rebuild_layout");
     if (fe->layout_dirty) { int rc = rebuild_layout(fe); if (rc != SDRPP_OK) return rc; }
@@ -1213,6 +1143,13 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     int total_vfos_all = 0;
     for (const Group& g : fe->groups) total_vfos_all += (int)g.members.size();
     std::vector<TailArgs> tails, tails_fast;
+    // The low-latency tail kernel (all 1024 threads of an SM on one VFO) is chosen when the VFO set is smaller than the machine:
+    // there one CTA's chain of round trips is what a step waits for. With several CTAs per SM the tail is bound by its
+    // instruction count and the general kernel is ahead. SDRPP_TAIL_MODE pins one: general / fast / narrow -- narrow is the
+    // low-latency kernel with 256 threads and <= 41 KB, built to run BESIDE the persistent stage-1 CTA of the next block
+    // (with SDRPP_S1T_SMEM_CAP=190000 and -DSDRPP_S1T_MAXNREG=80); measured: both kernels then run at half speed, they
+    // compete for shared-memory bandwidth (profiles/r2m_coresidency.txt), so it is not a default.
+    const int fast_threads = fe->tail_mode == 3 ? 256 : 1024;
     std::vector<int> tail_totals, tail_fast_totals;
     // Tensor-core stage 1: refresh the fp16 hi/lo planes of the ring for every first-stage decimation in use
     // (one conversion serves all VFOs and plans of that decimation), then collect the eligible groups per plane set.
@@ -1264,9 +1201,114 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
                 fe->planes_skipped[pi] = false;
             }
             tc_args[pi].pl = pl;
+            if (plain_pending && fe->fuse_ingest && fmt == SDRPP_FMT_CF32 && scale == 1.0f && (((uintptr_t)d_in) & 15u) == 0 &&
+                s1t_split_covers(pl, split_from, abs_block, abs_block + n)) {
+                FE_TRY(fe, launch_s1t_split(L, st, ring, pl, split_from, abs_block + n, d_in, abs_block, conj));
+                plain_pending = false;
+                continue;
+            }
+            if (plain_pending) { FE_TRY(fe, launch_ingest(L, st, fmt, d_in, count, ring, wpos, conj, scale)); plain_pending = false; }
             FE_TRY(fe, launch_s1t_split(L, st, ring, pl, split_from, abs_block + n));
         }
     }
+    if (plain_pending) { FE_TRY(fe, launch_ingest(L, st, fmt, d_in, count, ring, wpos, conj, scale)); plain_pending = false; }
+    if (int rc = tl_mark(st, 1); rc != SDRPP_OK) return rc;
+    if (prof) FE_TRY(fe, L.record(st, fe->pev[1]));
+    // Three consumers of the ring run concurrently (the reference's Splitter fan-out): the spectrum on st_fft,
+    // stage 1 on st, and the tail of the PREVIOUS block on st_tail. Profiling serialises everything on st so
+    // that per-family CUDA-event times are those of the kernels alone.
+    const int sf = prof ? st : SID_FFT;
+    const int stl = prof ? st : SID_TAIL;
+    const int aset = (int)(&rs - fe->rs); // result set (and result arena) of this block
+    if (!prof && fft_order != 1) {
+        FE_TRY(fe, L.record(st, fe->ev_ingest));
+        FE_TRY(fe, L.wait(sf, fe->ev_ingest));
+    }
+    // fft_order 1 / 2: the spectrum commands go to a list of their own (a GRAPH_FFT run on the spectrum stream), spliced in
+    // behind stage 1 (1) or right here (2)
+    std::vector<Cmd> main_cmds;
+    const int graph_before_fft = L.cur_graph;
+    if (fft_order != 0) { main_cmds.swap(L.cmds); L.cur_graph = GRAPH_FFT; }
+
+    if (int rc = tl_mark(sf, 3); rc != SDRPP_OK) return rc;
+    // ---- spectrum frames completed by this block (reshaper.h:102-129 keep/skip + handler) --------
+    // Their kernels are a branch of the stage-1 graph; the device-to-host copies of the rows follow the graph (a copy
+    // inside it would hold the next block's stage 1 back until 4 MB per row have crossed the link).
+    struct PendingCopy { void* dst; const void* src; size_t bytes; };
+    std::vector<PendingCopy> fft_copies;
+    auto fft_copy = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        if (prof) return L.memcpy_async(st, dst, src, bytes, cudaMemcpyDeviceToHost);
+        if (fft_order != 0) { const int g = L.cur_graph; L.cur_graph = GRAPH_NONE; const cudaError_t e = L.memcpy_async(sf, dst, src, bytes, cudaMemcpyDeviceToHost); L.cur_graph = g; return e; }
+        fft_copies.push_back(PendingCopy{ dst, src, bytes });
+        return cudaSuccess;
+    };
+    rs.nrows = 0;
+    float* const rows_dev = fe->d_rows ? fe->d_rows + (size_t)par * fe->rows_cap * fe->cfg.fft_size : nullptr;
+    if (fe->cfg.fft_size > 0) {
+        const int N = fe->cfg.fft_size;
+        const int64_t interval = (int64_t)fe->nz + fe->skip;
+        int frames = 0;
+        const int64_t first = fe->fft_next;
+        while (fe->fft_next + fe->nz <= fe->abs_pos && frames < fe->rows_cap) { frames++; fe->fft_next += interval; }
+        // frames beyond the row buffer are dropped (like a waterfall that cannot keep up)
+        while (fe->fft_next + fe->nz <= fe->abs_pos) fe->fft_next += interval;
+        for (int f0 = 0; f0 < frames; f0 += fe->inter_frames) {
+            SpectrumArgs a{};
+            a.in = fe->ring; a.ring_mask = fe->ring_mask;
+            a.start = (uint32_t)((uint64_t)(first + (int64_t)f0 * interval) & fe->ring_mask);
+            a.frame_stride = (uint32_t)interval;
+            a.nz = fe->nz; a.window = fe->d_window; a.inter = fe->d_inter;
+            a.rows = rows_dev + (size_t)f0 * N; a.X = nullptr;
+            a.frames = std::min(fe->inter_frames, frames - f0);
+            FE_TRY(fe, launch_spectrum(L, sf, N, a, nullptr));
+        }
+        rs.nrows = frames;
+    }
+    // zoom / display state / level read-out write buffers that the copies behind the graph read (not double-buffered): such a
+    // block runs command by command, where the spectrum stream orders kernels and copies
+    if (fft_order == 0 && rs.nrows > 0 && (fe->zoom_out > 0 || fe->nsig > 0 || fe->sig_dirty)) fe->run_replayable[GRAPH_S1] = false;
+    if (rs.nrows > 0 && fe->zoom_out > 0) {
+        FE_TRY(fe, launch_fft_zoom(L, sf, rows_dev, fe->cfg.fft_size, rs.nrows, fe->d_zoom_idx, fe->zoom_out, fe->zoom_ranged, fe->d_zoom));
+        if (fe->disp_smoothing || fe->disp_hold) {
+            const int W = fe->zoom_out;
+            FE_TRY(fe, launch_fft_display(L, sf, fe->d_zoom, W, rs.nrows, fe->disp_smoothing, fe->disp_alpha, fe->d_disp, fe->disp_hold, fe->disp_hold_speed,
+                                          fe->d_disp + W, fe->d_disp + 2 * W));
+            if (fe->readback && fe->disp_hold) FE_TRY(fe, fft_copy(rs.hold, fe->d_disp + W, (size_t)W * sizeof(float)));
+        }
+        if (fe->readback)
+            FE_TRY(fe, fft_copy(rs.zoom, fe->d_zoom, (size_t)rs.nrows * fe->zoom_out * sizeof(float)));
+    }
+    if (int rc = tl_mark(sf, 4); rc != SDRPP_OK) return rc;
+    rs.nsig = 0;
+    rs.sig_done.clear();
+    if (rs.nrows > 0 && fe->cfg.fft_size > 0) {
+        int rc = refresh_signal_info(fe);
+        if (rc != SDRPP_OK) return rc;
+        if (fe->nsig > 0) {
+            FE_TRY(fe, launch_signal_info(L, sf, rows_dev, fe->cfg.fft_size, rs.nrows, fe->d_sig_bins, fe->nsig, fe->d_sig));
+            if (fe->readback)
+                FE_TRY(fe, fft_copy(rs.sig, fe->d_sig, (size_t)rs.nrows * fe->nsig * sizeof(float2)));
+            rs.nsig = fe->nsig;
+            rs.sig_slot.assign(fe->vfos.size(), -1);
+            for (size_t id = 0; id < fe->vfos.size(); id++) if (fe->vfos[id].alive && fe->vfos[id].sig_on) rs.sig_slot[id] = fe->vfos[id].sig_slot;
+        }
+    }
+    if (fe->readback && rs.nrows > 0 && (fe->zoom_keep_raw || fe->zoom_out <= 0))
+        FE_TRY(fe, fft_copy(rs.rows, rows_dev, (size_t)rs.nrows * fe->cfg.fft_size * sizeof(float)));
+    if (prof) { FE_TRY(fe, L.record(st, fe->pev[2])); fe->ev_fft_valid[0] = fe->ev_fft_valid[1] = false; }
+    else if (fft_order == 0) FE_TRY(fe, L.record(sf, fe->ev_fftk));   // the spectrum branch joins the main stream again at the end of the stage-1 graph
+    std::vector<Cmd> fft_cmds;
+    if (fft_order != 0) {
+        L.cur_graph = GRAPH_NONE;
+        FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
+        fe->ev_fft_valid[par] = true;
+        fft_cmds.swap(L.cmds);
+        L.cmds.swap(main_cmds);
+        if (fft_order == 2) { L.cmds.insert(L.cmds.end(), fft_cmds.begin(), fft_cmds.end()); fft_cmds.clear(); L.cur_graph = GRAPH_S1; }
+        else L.cur_graph = graph_before_fft;
+    }
+
+    // ---- channelizer: stage 1 of every group (the layout, the fp16 planes and their conversion were planned above) ----
     auto flush_tc = [&](int pi) -> int {
         if (tc_args[pi].ngroups == 0) return SDRPP_OK;
         FE_TRY(fe, launch_s1t(L, st, tc_args[pi], fe->num_sms));
@@ -1390,7 +1432,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         // Measured (profiles/r2e): with fewer VFOs than SMs the tail is bound by one CTA's chain of dependent round trips
         // and the low-latency kernel wins (100 WFM VFOs: 73 -> 58 us per step); with several CTAs per SM both kernels are
         // bound by instruction issue and the general one (tap tables built per segment, fewer instructions) is ahead.
-        bool fast = (fe->tail_mode == 0 ? total_vfos_all <= fe->num_sms : fe->tail_mode == 2) && tail_fast_fits(tg, nullptr);
+        bool fast = (fe->tail_mode == 0 ? total_vfos_all <= fe->num_sms : fe->tail_mode != 1) && tail_fast_fits(tg, nullptr, fast_threads);
         if (fast) for (int id : g.members) if (fe->vfos[(size_t)id].if_state) { fast = false; break; }
         std::vector<TailArgs>& lst = fast ? tails_fast : tails;
         std::vector<int>& tot = fast ? tail_fast_totals : tail_totals;
@@ -1407,6 +1449,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         FE_TRY(fe, L.record(SID_S1B, fe->ev_s1_join));
         FE_TRY(fe, L.wait(st, fe->ev_s1_join));
     }
+    if (int rc = tl_mark(st, 2); rc != SDRPP_OK) return rc;
     if (prof) FE_TRY(fe, L.record(st, fe->pev[3]));
     else {
         if (fft_order == 0) FE_TRY(fe, L.wait(st, fe->ev_fftk));        // join of the spectrum branch: last node of the stage-1 graph
@@ -1427,6 +1470,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         }
         L.cur_graph = GRAPH_TAIL;
     }
+    if (int rc = tl_mark(stl, 5); rc != SDRPP_OK) return rc;
     for (int pass = 0; pass < 2; pass++) {
         std::vector<TailArgs>& lst = pass ? tails : tails_fast;
         std::vector<int>& tot = pass ? tail_totals : tail_fast_totals;
@@ -1437,9 +1481,11 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             const TailArgs* d_args = L.push(lst[i]);
             if (!d_args) return fail(SDRPP_ERR_STATE, "block descriptor overflow");
             if (wide) FE_TRY(fe, launch_tail_stage0_wide(L, stl, lst[i], d_args, tot[i]));
-            FE_TRY(fe, pass ? launch_tail(L, stl, lst[i], d_args, tot[i]) : launch_tail_fast(L, stl, lst[i], d_args, tot[i]));
+            if (i == 0) { if (int rc = tl_mark(stl, 6); rc != SDRPP_OK) return rc; }
+            FE_TRY(fe, pass ? launch_tail(L, stl, lst[i], d_args, tot[i]) : launch_tail_fast(L, stl, lst[i], d_args, tot[i], fast_threads));
         }
     }
+    if (int rc = tl_mark(stl, 7); rc != SDRPP_OK) return rc;
     // the post-detector pass below walks every group, whichever tail kernel it took
     tails.insert(tails.end(), tails_fast.begin(), tails_fast.end());
     tail_totals.insert(tail_totals.end(), tail_fast_totals.begin(), tail_fast_totals.end());
@@ -1619,6 +1665,7 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
         FE_TRY(fe, cudaEventRecord(fe->ev_bcast[slot], sb));
         FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_bcast[slot], 0));
     }
+    fe->blk_device_src = device_src || !is_root;
     rc = process_block(fe, fmt, d_in, count, rs, scale);
     if (rc != SDRPP_OK) return rc;
     if (!device_src || !is_root) {
@@ -1989,7 +2036,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         const char* rsv = getenv("SDRPP_RESERVE_SMS");
         if (rsv) { const int r = atoi(rsv); if (r > 0 && r < fe->num_sms) fe->num_sms -= r; }
         const char* tm = getenv("SDRPP_TAIL_MODE");
-        fe->tail_mode = (tm && (!strcmp(tm, "general") || !strcmp(tm, "1"))) ? 1 : (tm && (!strcmp(tm, "fast") || !strcmp(tm, "2"))) ? 2 : 0;
+        fe->tail_mode = (tm && (!strcmp(tm, "general") || !strcmp(tm, "1"))) ? 1 : (tm && (!strcmp(tm, "fast") || !strcmp(tm, "2"))) ? 2
+                      : (tm && (!strcmp(tm, "narrow") || !strcmp(tm, "3"))) ? 3 : 0;
         const char* m = getenv("SDRPP_S1_MODE");
         fe->s1_mode = (m && (!strcmp(m, "fp32") || !strcmp(m, "1"))) ? 1 : 0;
     }
@@ -2025,6 +2073,11 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
     fe->L.streams[SID_MAIN] = fe->st; fe->L.streams[SID_FFT] = fe->st_fft; fe->L.streams[SID_TAIL] = fe->st_tail;
     fe->L.streams[SID_S1B] = fe->st_s1b; fe->L.streams[SID_D2H] = fe->st_d2h;
     { const char* g = getenv("SDRPP_GRAPHS"); fe->graphs_on = !(g && g[0] == '0'); }
+    if (const char* g = getenv("SDRPP_TIMELINE"); g && g[0] == '1') {
+        fe->timeline = true; fe->graphs_on = false;
+        for (auto& row : fe->tl_ev) for (cudaEvent_t& e : row) { if (cudaEventCreate(&e) != cudaSuccess) return bail("event creation failed"); cudaEventRecord(e, fe->st); }
+    }
+    { const char* g = getenv("SDRPP_FUSE_INGEST"); fe->fuse_ingest = !(g && g[0] == '0'); }
     { const char* g = getenv("SDRPP_FFT_ORDER"); if (g && g[0] >= '0' && g[0] <= '2') fe->fft_order = g[0] - '0'; }
     for (int i = 0; i < kSets; i++) {
         if (cudaMallocHost((void**)&fe->h_desc[i], kDescBytes) != cudaSuccess) return bail("descriptor allocation failed");
@@ -2702,6 +2755,29 @@ int sdrpp_cuda_frontend_set_graphs(sdrpp_cuda_frontend* fe, int enabled) {
     std::lock_guard<std::mutex> api(fe->api_mtx);
     fe->graphs_on = enabled != 0;
     return SDRPP_OK;
+}
+
+// Timeline probe: for each of the last blocks, milliseconds of the eight marks relative to mark 0 of the OLDEST block kept.
+// out[b * 9 + 0] = block number, out[b * 9 + 1 + k] = time of mark k (0 main start, 1 ingest/split done, 2 stage 1 done, 3 spectrum
+// start, 4 spectrum done, 5 tail start, 6 wide stage done, 7 tail done). Returns the number of blocks written.
+extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_timeline(sdrpp_cuda_frontend* fe, float* out, int cap_blocks) {
+    if (!fe || !fe->timeline || !out) return 0;
+    cudaDeviceSynchronize();
+    constexpr int NB = sdrpp_cuda_frontend::kTlBlocks, NM = sdrpp_cuda_frontend::kTlMarks;
+    int oldest = 0;
+    for (int i = 1; i < NB; i++) if (fe->tl_blk[i] < fe->tl_blk[oldest]) oldest = i;
+    int n = 0;
+    for (int k = 0; k < NB && n < cap_blocks; k++) {
+        const int slot = (oldest + k) % NB;
+        out[n * 9] = (float)fe->tl_blk[slot];
+        for (int m = 0; m < NM; m++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, fe->tl_ev[oldest][0], fe->tl_ev[slot][m]) != cudaSuccess) { cudaGetLastError(); ms = -1.0f; }
+            out[n * 9 + 1 + m] = ms;
+        }
+        n++;
+    }
+    return n;
 }
 
 int sdrpp_cuda_frontend_graph_stats(sdrpp_cuda_frontend* fe, long long* out4) {

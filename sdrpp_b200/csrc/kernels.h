@@ -158,7 +158,9 @@ int s1t_A(int T, int D, int shift);
 int s1t_b_exponent(const float* taps, int T);
 size_t s1t_b_bytes(int A, int D, int nvfo);
 // samples [abs_begin, abs_end) were just written to the ring: (re)build the 8-row groups they touch
-cudaError_t launch_s1t_split(Launcher& L, int sid, RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end);
+cudaError_t launch_s1t_split(Launcher& L, int sid, RingRef ring, const S1TPlanes& pl, int64_t abs_begin, int64_t abs_end,
+                             const void* raw = nullptr, int64_t abs_block = 0, bool conj = false);
+bool s1t_split_covers(const S1TPlanes& pl, int64_t abs_begin, int64_t abs_block, int64_t abs_end);
 cudaError_t launch_s1t_build_b(Launcher& L, int sid, uint8_t* blob, const VfoDev* vfos, int nvfo, const float* d_taps, int T, int D, int shift,
                                int A, int escale);
 cudaError_t launch_s1t(Launcher& L, int sid, S1TArgs& a, int num_sms);
@@ -199,8 +201,8 @@ struct TailArgs {
 // the three tail launchers take the DEVICE copy of the arguments (Launcher::push) beside the host copy they size the grid from
 cudaError_t launch_tail(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos);
 // the low-latency form for groups whose stage inputs of this block fit in shared memory at once (tail_fast_fits)
-bool tail_fast_fits(const TailGroup& g, int* samples);
-cudaError_t launch_tail_fast(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos);
+bool tail_fast_fits(const TailGroup& g, int* samples, int threads = 1024, int* tap_floats = nullptr);
+cudaError_t launch_tail_fast(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos, int threads = 1024);
 // stage 0 of the groups with s_begin == 1 on a wide grid (a decimating FIR); launch before launch_tail
 cudaError_t launch_tail_stage0_wide(Launcher& L, int sid, const TailArgs& a, const TailArgs* d_a, int total_vfos);
 bool tail_stage0_wide_supported(int T, int D);
