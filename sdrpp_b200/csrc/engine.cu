@@ -313,6 +313,7 @@ struct sdrpp_cuda_frontend {
     cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr, st_s1b = nullptr, st_d2h = nullptr;
     cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft[2] = { nullptr, nullptr }, ev_tail[2] = { nullptr, nullptr };
     bool ev_fft_valid[2] = { false, false };
+    cudaEvent_t ev_rows[5] = { nullptr };   // per result set: the block's spectrum rows (zoomed rows, level read-outs) are on the host
     // One submitting thread and one waiting thread may use a front end concurrently (submit / wait_input on one,
     // wait + result getters on the other); everything else is serialised by the caller. wait() drops the lock while
     // it blocks on the block's completion event.
@@ -425,7 +426,7 @@ struct sdrpp_cuda_frontend {
 
     // timeline probe (SDRPP_TIMELINE=1, tools/timeline_probe.py): timing events on the streams the kernels really run on,
     // for the last kTlBlocks blocks; blocks run command by command while it is on
-    static constexpr int kTlBlocks = 16, kTlMarks = 8;
+    static constexpr int kTlBlocks = 32, kTlMarks = 10;
     bool timeline = false;
     cudaEvent_t tl_ev[kTlBlocks][kTlMarks] = {};
     long long tl_blk[kTlBlocks] = {};
@@ -542,7 +543,9 @@ static int configure_fft(sdrpp_cuda_frontend* fe) {
     FE_TRY(fe, upload_sync(fe->d_window, w.data(), sizeof(float) * fe->nz));
     int rows = fe->cfg.max_fft_rows > 0 ? fe->cfg.max_fft_rows : (int)(fe->cfg.max_block / interval + 2);
     fe->rows_cap = rows;
-    FE_TRY(fe, dev_alloc(&fe->d_rows, (size_t)2 * rows * N, false));   // one set of rows per block parity: the copy of block i runs beside the spectrum of block i+1
+    // one set of rows per result set: the copy of block i's rows to the host may still be crossing the link while the spectrum
+    // kernels of the following blocks run (the main stream waits for spectrum KERNELS only, never for a row copy)
+    FE_TRY(fe, dev_alloc(&fe->d_rows, (size_t)kSets * rows * N, false));
     if (N1 > 1) {
         // frames per launch group: keep the four-step intermediate within ~32 MB so it stays in L2
         fe->inter_frames = std::max(1, std::min(rows, (int)((32u << 20) / ((size_t)N * 8))));
@@ -1243,7 +1246,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         return cudaSuccess;
     };
     rs.nrows = 0;
-    float* const rows_dev = fe->d_rows ? fe->d_rows + (size_t)par * fe->rows_cap * fe->cfg.fft_size : nullptr;
+    float* const rows_dev = fe->d_rows ? fe->d_rows + (size_t)aset * fe->rows_cap * fe->cfg.fft_size : nullptr;
     if (fe->cfg.fft_size > 0) {
         const int N = fe->cfg.fft_size;
         const int64_t interval = (int64_t)fe->nz + fe->skip;
@@ -1263,6 +1266,13 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
             FE_TRY(fe, launch_spectrum(L, sf, N, a, nullptr));
         }
         rs.nrows = frames;
+    }
+    // the ring is free again (for the main stream, two blocks on) once the spectrum KERNELS have read it
+    if (!prof && fft_order != 0) {
+        const int g = L.cur_graph; L.cur_graph = GRAPH_NONE;
+        FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
+        L.cur_graph = g;
+        fe->ev_fft_valid[par] = true;
     }
     // zoom / display state / level read-out write buffers that the copies behind the graph read (not double-buffered): such a
     // block runs command by command, where the spectrum stream orders kernels and copies
@@ -1300,8 +1310,7 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     std::vector<Cmd> fft_cmds;
     if (fft_order != 0) {
         L.cur_graph = GRAPH_NONE;
-        FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
-        fe->ev_fft_valid[par] = true;
+        FE_TRY(fe, L.record(sf, fe->ev_rows[aset]));
         fft_cmds.swap(L.cmds);
         L.cmds.swap(main_cmds);
         if (fft_order == 2) { L.cmds.insert(L.cmds.end(), fft_cmds.begin(), fft_cmds.end()); fft_cmds.clear(); L.cur_graph = GRAPH_S1; }
@@ -1456,11 +1465,14 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         L.cur_graph = GRAPH_NONE;
         FE_TRY(fe, L.record(st, fe->ev_s1));
         if (fft_order == 0) {
+            // the spectrum kernels were a branch of the main stream's own graph: the ring is ordered by the stream itself; the
+            // event only serves a later block that runs in another order
+            FE_TRY(fe, L.record(st, fe->ev_fft[par]));
+            fe->ev_fft_valid[par] = true;
             // rows to the host behind the graph
             FE_TRY(fe, L.wait(sf, fe->ev_s1));
             for (const PendingCopy& c : fft_copies) FE_TRY(fe, L.memcpy_async(sf, c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost));
-            FE_TRY(fe, L.record(sf, fe->ev_fft[par]));
-            fe->ev_fft_valid[par] = true;
+            FE_TRY(fe, L.record(sf, fe->ev_rows[aset]));
         }
         FE_TRY(fe, L.wait(stl, fe->ev_s1));
         if (fft_order == 1) {
@@ -1588,7 +1600,8 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
     }
     if (fe->readback && !fe->rds_ids.empty() && fe->rds_arena_used > 0)
         FE_TRY(fe, L.memcpy_async(sd, rs.rds, fe->d_arena_rds + (size_t)aset * fe->rds_arena_cap, fe->rds_arena_used * sizeof(float2), cudaMemcpyDeviceToHost));
-    if (!prof) FE_TRY(fe, L.wait(sd, fe->ev_fft[par])); // the block is done when its rows are on the host too
+    if (!prof) FE_TRY(fe, L.wait(sd, fe->ev_rows[aset])); // the block is done when its rows are on the host too
+    if (int rc = tl_mark(sd, 9); rc != SDRPP_OK) return rc;
     FE_TRY(fe, L.record(sd, rs.done));
     fe->launches += L.kernels - kernels0;
     {
@@ -1642,6 +1655,7 @@ static int submit_common(sdrpp_cuda_frontend* fe, int fmt, const void* in, int c
         }
         FE_TRY(fe, cudaMemcpyAsync(fe->d_raw[slot], src, bytes, cudaMemcpyHostToDevice, fe->st_copy));
         FE_TRY(fe, cudaEventRecord(fe->ev_h2d[slot], fe->st_copy));
+        if (fe->timeline) FE_TRY(fe, cudaEventRecord(fe->tl_ev[fe->blk % sdrpp_cuda_frontend::kTlBlocks][8], fe->st_copy));
         if (!shared) FE_TRY(fe, cudaStreamWaitEvent(fe->st, fe->ev_h2d[slot], 0));
         d_in = fe->d_raw[slot];
         fe->last_in_slot = slot;
@@ -2069,6 +2083,9 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_desc, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_rows[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&fe->ev_rows[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_rows[2], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&fe->ev_rows[3], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fe->ev_rows[4], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_fftk, cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
     fe->L.streams[SID_MAIN] = fe->st; fe->L.streams[SID_FFT] = fe->st_fft; fe->L.streams[SID_TAIL] = fe->st_tail;
     fe->L.streams[SID_S1B] = fe->st_s1b; fe->L.streams[SID_D2H] = fe->st_d2h;
@@ -2146,6 +2163,7 @@ int sdrpp_cuda_frontend_destroy(sdrpp_cuda_frontend* fe) {
     for (int i = 0; i < kSets; i++) { if (fe->h_desc[i]) cudaFreeHost(fe->h_desc[i]); if (fe->d_desc[i]) cudaFree(fe->d_desc[i]); }
     if (fe->ev_fftk) cudaEventDestroy(fe->ev_fftk);
     if (fe->ev_desc) cudaEventDestroy(fe->ev_desc);
+    for (cudaEvent_t e : fe->ev_rows) if (e) cudaEventDestroy(e);
     if (fe->st_desc) cudaStreamDestroy(fe->st_desc);
     if (fe->st) cudaStreamDestroy(fe->st);
     if (fe->st_copy) cudaStreamDestroy(fe->st_copy);
@@ -2758,8 +2776,9 @@ int sdrpp_cuda_frontend_set_graphs(sdrpp_cuda_frontend* fe, int enabled) {
 }
 
 // Timeline probe: for each of the last blocks, milliseconds of the eight marks relative to mark 0 of the OLDEST block kept.
-// out[b * 9 + 0] = block number, out[b * 9 + 1 + k] = time of mark k (0 main start, 1 ingest/split done, 2 stage 1 done, 3 spectrum
-// start, 4 spectrum done, 5 tail start, 6 wide stage done, 7 tail done). Returns the number of blocks written.
+// out[b * 11 + 0] = block number, out[b * 11 + 1 + k] = time of mark k (0 main start, 1 ingest/split done, 2 stage 1 done, 3 spectrum
+// start, 4 spectrum done, 5 tail start, 6 wide stage done, 7 tail done, 8 host-to-device copy done, 9 results on the host).
+// Returns the number of blocks written.
 extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_timeline(sdrpp_cuda_frontend* fe, float* out, int cap_blocks) {
     if (!fe || !fe->timeline || !out) return 0;
     cudaDeviceSynchronize();
@@ -2769,11 +2788,11 @@ extern "C" __attribute__((visibility("default"))) int sdrpp_cuda_debug_timeline(
     int n = 0;
     for (int k = 0; k < NB && n < cap_blocks; k++) {
         const int slot = (oldest + k) % NB;
-        out[n * 9] = (float)fe->tl_blk[slot];
+        out[n * 11] = (float)fe->tl_blk[slot];
         for (int m = 0; m < NM; m++) {
             float ms = 0.0f;
             if (cudaEventElapsedTime(&ms, fe->tl_ev[oldest][0], fe->tl_ev[slot][m]) != cudaSuccess) { cudaGetLastError(); ms = -1.0f; }
-            out[n * 9 + 1 + m] = ms;
+            out[n * 11 + 1 + m] = ms;
         }
         n++;
     }
