@@ -571,9 +571,16 @@ def run_gpu(args, rank, world, local_rank):
         rows = {}
         # ingest family: conversion (+ front-end decimation where the workload has it)
         pre_bytes = model["convert_bytes_per_sample"] + model["decim_bytes_per_sample"] - (8.0 if w.decim > 1 else 0.0)
-        rows["ingest"] = hbm_row("ingest_kernel" + (" + decim_stage_kernel x2 (PowerDecimator x%d)" % w.decim if w.decim > 1 else ""), pre_bytes, ingest_ms,
-                                 "conversion %g B/sample in + 8 B out" % w.bytes_per_sample + (" fused with the first decimator stage's input; + 8/%d B out" % w.decim if w.decim > 1 else "")
-                                 + " (SURVEY 8d rows 1-2)", "ingest")
+        fused_ingest = (w.fmt == workloads.FMT_CF32 and w.decim == 1 and tensor_launches > 0 and os.environ.get("SDRPP_FUSE_INGEST", "1") != "0")
+        if fused_ingest:
+            # cf32 blocks are not copied to the ring by a kernel of their own: the fp16 split of the tensor-core stage 1 reads the
+            # block in place and writes ring + hi/lo planes (8 B in, 8 B ring, 4 + 4 B planes per sample)
+            rows["ingest"] = hbm_row("s1t_split_kernel<fused cf32 ingest> (ring write + fp16 hi/lo planes of the tensor-core stage 1)", 24.0, ingest_ms,
+                                     "8 B/sample in + 8 B ring + 8 B fp16 hi/lo planes; the separate conversion pass of SURVEY 8d rows 1-2 (16 B/sample) is gone", "s1t_split")
+        else:
+            rows["ingest"] = hbm_row("ingest_kernel" + (" + decim_stage_kernel x2 (PowerDecimator x%d)" % w.decim if w.decim > 1 else "") + (" + s1t_split_kernel" if tensor_launches > 0 else ""), pre_bytes, ingest_ms,
+                                     "conversion %g B/sample in + 8 B out" % w.bytes_per_sample + (" fused with the first decimator stage's input; + 8/%d B out" % w.decim if w.decim > 1 else "")
+                                     + " (SURVEY 8d rows 1-2)", "ingest")
         rows["spectrum"] = hbm_row("fft_cols_kernel + fft_rows_kernel (window + %d-pt FFT + dB row)" % w.fft_size, model["fft_bytes_per_sample"], fft_ms,
                                    "SURVEY 8d: sample in (packed size for packed formats) + 4 B out per spectrum sample", "fft_")
         if rows["spectrum"]["ms_per_step"] > 0:
@@ -602,18 +609,18 @@ def run_gpu(args, rank, world, local_rank):
                 executed += (-(-cnt // 16)) * (-(-((w.block // w.decim) // D) // 120)) * 3 * (2 * D // 16) * 2.0 * 128 * (32 * A) * 16
             rows["channelizer_stage1"] = {
                 "bound": "tensor",
-                "kernel": "s1t_split_kernel + s1t_kernel (tcgen05: NCO + first decimating FIR of every VFO as one split-fp16 matrix product per step)",
+                "kernel": "s1t_kernel (tcgen05: NCO + first decimating FIR of every VFO as one split-fp16 matrix product per step; the fp16 split of the block is timed with the ingest family)",
                 "achieved": fp32["achieved"], "peak": tens_peak, "unit": "TFLOP/s", "frac": fp32["achieved"] / tens_peak if fp32["achieved"] else None,
-                "traffic": traffic_of("s1t_") if w.idx == 5 else None,
-                "traffic_note": "dram__bytes_read+write of the step's s1t_split + s1t launches, ncu --set full at N=1 (profiles/r2_traffic.json)",
-                "peak_source": tens_src, "ms_per_step": float(s1_ms), "launches_per_step": 2,
+                "traffic": traffic_of("s1t_kernel") if w.idx == 5 else None,
+                "traffic_note": "dram__bytes_read+write of the step's s1t_kernel launch, ncu --set full at N=1 (profiles/r2_traffic.json): 9.5 MB against 9.8 MB of fp16 planes -- the 32 VFO tiles re-read them out of L2",
+                "peak_source": tens_src, "ms_per_step": float(s1_ms), "launches_per_step": 1,
                 "algorithmic_flops_per_step": s1_flops, "algorithmic_flops_per_sample": model["stage1_flops_per_sample"],
                 "executed": {"tflops": executed / (s1_ms * 1e-3) / 1e12 if s1_ms > 0 else None,
                              "frac_of_peak": executed / (s1_ms * 1e-3) / 1e12 / tens_peak if s1_ms > 0 else None, "flops_per_step": executed,
                              "note": "tensor-core flops issued: 3 fp16 products x complex x (tap matrix padded to ceil(T/D) rows) x 128-row tiles per 120 outputs"},
                 "hbm": {k: chan_min[k] for k in ("achieved", "peak", "unit", "frac", "algorithmic_bytes_per_step", "note")},
                 "fp32_equivalent": fp32,
-                "note": "algorithmic flops = the reference's count for NCO + first FIR (SURVEY 8d); ms_per_step covers the fp16 split of the block and the matrix-product kernel"}
+                "note": "algorithmic flops = the reference's count for NCO + first FIR (SURVEY 8d); ms_per_step is the matrix-product kernel (CUDA events around it inside the library)"}
         else:
             chan_min["kernel"] = "stage1_kernel / mix_only_kernel (FP32: NCO folded into the first decimating FIR, one launch per VFO class)"
             chan_min["fp32"] = fp32
