@@ -72,6 +72,9 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ float2 phasor_u64(uint64_t phase) {
@@ -779,7 +782,13 @@ struct FastRegion {
     int len;    // elements (history + data)
 };
 __host__ __device__ inline int fast_stage_M(const TailStage& st) { return st.type == TAIL_POLY ? 1 : kFastOB * (st.type == TAIL_DECFIR ? st.D : 1); }
-__host__ __device__ inline int fast_ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+__host__ __device__ inline int fast_ilog2(int v) {
+#ifdef __CUDA_ARCH__
+    return v <= 1 ? 0 : 32 - __clz(v - 1);
+#else
+    int l = 0; while ((1 << l) < v) l++; return l;
+#endif
+}
 __host__ __device__ inline int fast_region_floats2(const TailStage& st, FastRegion* r, int base) {
     const int len = (st.T - 1) + st.n_in;
     const int M = fast_stage_M(st);
@@ -792,16 +801,22 @@ __host__ __device__ inline int fast_region_floats2(const TailStage& st, FastRegi
     if (r) { r->base = base; r->M = M; r->lgM = lgM; r->qs = qs; r->len = len; }
     return M > 1 ? ((M * qs + 1) & ~1) : ((padded + 1) & ~1);
 }
+// float4 table (h[s], h[s-D], h[s-2D], h[s-3D]) for s < T + 3D of a FIR stage, without / with the raw taps behind it
+__host__ __device__ inline int fast_table_floats(const TailStage& st) {
+    const int D = st.type == TAIL_DECFIR ? st.D : 1;
+    return 4 * (st.T + (kFastOB - 1) * D);
+}
 __host__ __device__ inline int fast_tap_floats(const TailStage& st) {
     if (st.type == TAIL_POLY) return (st.interp * st.T + 3) & ~3;
-    const int D = st.type == TAIL_DECFIR ? st.D : 1;
-    return 4 * (st.T + (kFastOB - 1) * D);   // float4 table (h[s], h[s-D], h[s-2D], h[s-3D]) for s < T + 3D
+    // the raw taps arrive by cp.async with everything else the block needs (one round trip) and the table is built from
+    // them out of shared memory: built straight from global loads, five stages of load -> store chains cost 16 k cycles
+    return fast_table_floats(st) + ((st.T + 3) & ~3);
 }
 
 __host__ __device__ inline int fast_tap_bytes(int tap_floats) { return (tap_floats * 4 + 15) & ~15; }
 // The narrow shape has to fit beside the persistent stage-1 CTA of the NEXT block (189 KB of the SM's 228 KB with its
 // four-chunk operand ring): tap tables + stage regions <= 41 KB, sized per group instead of a fixed tap area.
-constexpr int kFastNarrowBytes = 41984;
+constexpr int kFastNarrowBytes = 41728;
 
 bool tail_fast_fits(const TailGroup& g, int* samples, int threads, int* tap_floats) {
     const int kFastScratch = threads * kFastOB, kFastMaxSamples = fast_max_samples(threads);
@@ -857,20 +872,32 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
     const TailGroup& g = sg;
     float2* slab = vd.slab;
 
-    FastRegion reg[kTailMaxStages + 1];
-    int toff[kTailMaxStages];
-    int pos = 0;
-    {
-        int tp = 0;
-        for (int s = g.s_begin; s < g.nstages; s++) {
-            toff[s] = tp;
-            pos += fast_region_floats2(g.st[s], &reg[s], pos);
-            tp += fast_tap_floats(g.st[s]);
-        }
-        x = reinterpret_cast<float2*>(tail_smem + fast_tap_bytes(tp));
+    // Layout: thread s sizes stage s (the divisions and logarithms once, not 1024 times: 5.6 k cycles before), then everyone
+    // takes the prefix sums.
+    // Layout in SHARED memory. As per-thread arrays (dynamically indexed, so in local memory: 168 bytes x 1024 threads
+    // against an L1 that the shared-memory carve-out leaves at 28 KB) every reg[s] / toff[s] access was a trip to L2 -- the
+    // load-issue phase alone took 16 k cycles (tools/tailfast_trace.py). Thread s sizes stage s, thread 0 takes the prefix sums.
+    __shared__ FastRegion reg[kTailMaxStages + 1];
+    __shared__ int ssize[kTailMaxStages], toff[kTailMaxStages + 1];
+    if (tid >= g.s_begin && tid < g.nstages) {
+        ssize[tid] = fast_region_floats2(g.st[tid], &reg[tid], 0);
+        toff[tid] = fast_tap_floats(g.st[tid]);
     }
-    FastRegion& rf = reg[g.nstages];     // final: natural order, element 0 = last output of the previous block
-    rf.base = pos; rf.M = 1; rf.lgM = 0; rf.qs = 0; rf.len = g.n_final + 1;
+    __syncthreads();
+    if (tid == 0) {
+        int pos0 = 0, tp = 0;
+        for (int s = g.s_begin; s < g.nstages; s++) {
+            const int t = toff[s];
+            toff[s] = tp; tp += t;
+            reg[s].base = pos0; pos0 += ssize[s];
+        }
+        toff[kTailMaxStages] = tp;
+        FastRegion& f = reg[g.nstages];      // final: natural order, element 0 = last output of the previous block
+        f.base = pos0; f.M = 1; f.lgM = 0; f.qs = 0; f.len = g.n_final + 1;
+    }
+    __syncthreads();
+    x = reinterpret_cast<float2*>(tail_smem + fast_tap_bytes(toff[kTailMaxStages]));
+    const FastRegion rf = reg[g.nstages];
     float2* fin = x + rf.base + 1;
     float2* scratch = x + rf.base + ((g.n_final + 2 + 1) & ~1);
 
@@ -878,7 +905,7 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
     // ---- one round trip: everything this block needs ------------------------------------------------------------------
     if (g.s_begin < g.nstages) {
         const TailStage& st = g.st[g.s_begin];
-        const FastRegion& r = reg[g.s_begin];
+        const FastRegion r = reg[g.s_begin];   // by value: registers, not a shared-memory reload per access
         const float2* __restrict__ src = slab + st.in_off - (st.T - 1);     // [history | data], contiguous in the slab
         for (int i = tid; i < r.len; i += kFastThreads) cp_async8(&fast_at(x, r, i), src + i);
     } else {
@@ -890,31 +917,39 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
         const int hist = st.T - 1;
         if (s > g.s_begin) {
             const float2* __restrict__ hsrc = slab + st.in_off - hist;
-            for (int i = tid; i < hist; i += kFastThreads) cp_async8(&fast_at(x, reg[s], i), hsrc + i);
+            const FastRegion rs = reg[s];
+            for (int i = tid; i < hist; i += kFastThreads) cp_async8(&fast_at(x, rs, i), hsrc + i);
         }
-        if (st.type == TAIL_POLY) {
-            for (int i = tid; i < st.interp * st.T; i += kFastThreads) taps[toff[s] + i] = __ldg(st.taps + i);
-        } else {
-            const int D = st.type == TAIL_DECFIR ? st.D : 1, T = st.T;
-            float4* t4 = reinterpret_cast<float4*>(taps + toff[s]);
-            for (int sv = tid; sv < T + (kFastOB - 1) * D; sv += kFastThreads) {
-                float4 h;
-                h.x = sv < T ? __ldg(st.taps + sv) : 0.0f;
-                h.y = (sv - D >= 0 && sv - D < T) ? __ldg(st.taps + sv - D) : 0.0f;
-                h.z = (sv - 2 * D >= 0 && sv - 2 * D < T) ? __ldg(st.taps + sv - 2 * D) : 0.0f;
-                h.w = (sv - 3 * D >= 0 && sv - 3 * D < T) ? __ldg(st.taps + sv - 3 * D) : 0.0f;
-                t4[sv] = h;
-            }
-        }
+        // polyphase bank as it is; FIR taps raw, behind the place of their table
+        const int nraw = st.type == TAIL_POLY ? st.interp * st.T : st.T;
+        float* rdst = taps + toff[s] + (st.type == TAIL_POLY ? 0 : fast_table_floats(st));
+        for (int i = tid; i < nraw; i += kFastThreads) cp_async4(rdst + i, st.taps + i);
     }
     for (int s = g.s_begin; s < g.nstages; s++) {
-        if (reg[s].M == 1) continue;
+        const FastRegion rs = reg[s];
+        if (rs.M == 1) continue;
         const int D = g.st[s].type == TAIL_DECFIR ? g.st[s].D : 1;
-        for (int i = reg[s].len + tid; i < reg[s].len + 6 * D + 8; i += kFastThreads) fast_at(x, reg[s], i) = make_float2(0.0f, 0.0f);
+        for (int i = rs.len + tid; i < rs.len + 6 * D + 8; i += kFastThreads) fast_at(x, rs, i) = make_float2(0.0f, 0.0f);
     }
     if (tid == 0) fin[-1] = slab[g.final_off - 1];
     TF_MARK(2);
     cp_async_wait_all();
+    __syncthreads();
+    for (int s = g.s_begin; s < g.nstages; s++) {
+        const TailStage& st = g.st[s];
+        if (st.type == TAIL_POLY) continue;
+        const int D = st.type == TAIL_DECFIR ? st.D : 1, T = st.T;
+        float4* t4 = reinterpret_cast<float4*>(taps + toff[s]);
+        const float* __restrict__ raw = taps + toff[s] + fast_table_floats(st);
+        for (int sv = tid; sv < T + (kFastOB - 1) * D; sv += kFastThreads) {
+            float4 h;
+            h.x = sv < T ? raw[sv] : 0.0f;
+            h.y = (sv - D >= 0 && sv - D < T) ? raw[sv - D] : 0.0f;
+            h.z = (sv - 2 * D >= 0 && sv - 2 * D < T) ? raw[sv - 2 * D] : 0.0f;
+            h.w = (sv - 3 * D >= 0 && sv - 3 * D < T) ? raw[sv - 3 * D] : 0.0f;
+            t4[sv] = h;
+        }
+    }
     __syncthreads();
     TF_MARK(3);
 
@@ -922,8 +957,8 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
     for (int s = g.s_begin; s < g.nstages; s++) {
         const TailStage& st = g.st[s];
         const int T = st.T;
-        const FastRegion& ri = reg[s];
-        const FastRegion& ro = reg[s + 1];
+        const FastRegion ri = reg[s];
+        const FastRegion ro = reg[s + 1];
         const int obase = (s + 1 < g.nstages) ? (g.st[s + 1].T - 1) : 1;   // outputs land behind the consumer's history
         if (st.type == TAIL_POLY) {
             const float2* __restrict__ in = x + ri.base;
@@ -959,7 +994,9 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
         const int G = (n_out + kFastOB - 1) / kFastOB;
         const int S = (kFastOB - 1) * D + T;
         int KS = 1;
-        while (KS < 8 && G * KS * 2 <= kFastThreads && S >= 32 * KS) KS *= 2;
+        // split the window over as many thread groups as fit in the CTA, down to 8 window steps per thread: the stages are
+        // latency chains (~110-220 cycles per window step with a handful of warps busy), so halving the steps halves a stage
+        while (KS < 16 && G * KS * 2 <= kFastThreads && S >= 16 * KS) KS *= 2;
         const int Sk = (S + KS - 1) / KS;
         const float4* __restrict__ t4 = reinterpret_cast<const float4*>(taps + toff[s]);
         for (int g0 = 0; g0 < G; g0 += kFastThreads / KS) {
@@ -1032,7 +1069,9 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
         // empty block); later stages keep theirs in front of their own input area (fir.h:80)
         if (s == 0 || st.n_in > 0) {
             float2* dst = (s == 0) ? (slab + g.carry0_off - hist) : (slab + st.in_off - hist);
-            for (int i = tid; i < hist; i += kFastThreads) dst[i] = fast_at(x, reg[s], st.n_in + i);
+            const FastRegion rs = reg[s];
+            const int n_in = st.n_in;
+            for (int i = tid; i < hist; i += kFastThreads) dst[i] = fast_at(x, rs, n_in + i);
         }
     }
     if (tid == 0 && g.n_final > 0) slab[g.final_off - 1] = fin[g.n_final - 1];

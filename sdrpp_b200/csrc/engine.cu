@@ -1441,8 +1441,18 @@ static int process_block(sdrpp_cuda_frontend* fe, int fmt, const void* d_in, int
         // Measured (profiles/r2e): with fewer VFOs than SMs the tail is bound by one CTA's chain of dependent round trips
         // and the low-latency kernel wins (100 WFM VFOs: 73 -> 58 us per step); with several CTAs per SM both kernels are
         // bound by instruction issue and the general one (tap tables built per segment, fewer instructions) is ahead.
-        bool fast = (fe->tail_mode == 0 ? total_vfos_all <= fe->num_sms : fe->tail_mode != 1) && tail_fast_fits(tg, nullptr, fast_threads);
-        if (fast) for (int id : g.members) if (fe->vfos[(size_t)id].if_state) { fast = false; break; }
+        bool fast_ok = (fe->tail_mode == 0 ? total_vfos_all <= fe->num_sms : fe->tail_mode != 1);
+        if (fast_ok) for (int id : g.members) if (fe->vfos[(size_t)id].if_state) { fast_ok = false; break; }
+        bool fast = false;
+        if (fast_ok) {
+            // With the whole SM on one VFO even the first tail stage's input (9600 samples = 77 KB in cfg5) fits beside the
+            // other regions: the wide first-stage kernel, its launch and one more round trip through L2 drop out of the chain
+            // that every block of a small VFO set waits for (SDRPP_TAIL_FOLD=0: keep the wide kernel).
+            static const bool fold = !(getenv("SDRPP_TAIL_FOLD") && getenv("SDRPP_TAIL_FOLD")[0] == '0');
+            const int sb = tg.s_begin;
+            if (fold && sb == 1 && fast_threads == 1024) { tg.s_begin = 0; fast = tail_fast_fits(tg, nullptr, fast_threads); if (!fast) tg.s_begin = sb; }
+            if (!fast) fast = tail_fast_fits(tg, nullptr, fast_threads);
+        }
         std::vector<TailArgs>& lst = fast ? tails_fast : tails;
         std::vector<int>& tot = fast ? tail_fast_totals : tail_totals;
         if (lst.empty() || lst.back().ngroups == kTailMaxGroups) {
