@@ -648,10 +648,20 @@ tail_kernel(const TailArgs* __restrict__ ap) {
     float2* tsm = reinterpret_cast<float2*>(tail_smem + kTailTapFloats * 4);      // staged samples
     int vi = blockIdx.x, gi = 0;
     while (gi < a.ngroups - 1 && vi >= a.g[gi].nvfo) { vi -= a.g[gi].nvfo; gi++; }
-    const TailGroup& g = a.g[gi];
-    const VfoDev vd = a.vfos[g.first_vfo + vi];
-    float2* slab = vd.slab;
     const int tid = threadIdx.x;
+    // The group record lives in the per-block descriptor (device memory) since the command-list engine: read through a
+    // reference into global memory, every st.T / st.taps / st.n_out was a global load again after each store (the compiler
+    // cannot rule out aliasing with the slab). One coalesced copy into shared memory, like tail_fast_kernel.
+    __shared__ TailGroup sg;
+    {
+        const int* src = reinterpret_cast<const int*>(&a.g[gi]);
+        int* dst = reinterpret_cast<int*>(&sg);
+        for (int i = tid; i < (int)(sizeof(TailGroup) / sizeof(int)); i += kTailThreads) dst[i] = src[i];
+    }
+    const VfoDev vd = a.vfos[a.g[gi].first_vfo + vi];
+    __syncthreads();
+    const TailGroup& g = sg;
+    float2* slab = vd.slab;
 
     for (int s = g.s_begin; s < g.nstages; s++) { // stage 0 may already have run in tail_stage0_wide_kernel
         const TailStage& st = g.st[s];
