@@ -486,15 +486,28 @@ __device__ __forceinline__ void tail_fir_blocked(const TailStage& st, int D, con
                 for (int row = r0; row < r1; row++) {
                     const float2* __restrict__ xp = tsm + t_out + row;
                     const float4* __restrict__ tp = tt + ((ks * SEGq + (row - r0)) << lgM);
-#pragma unroll 4
-                    for (int sp = 0; sp < M; sp++) {
-                        const float2 v = xp[sp * qs];
-                        const float4 h = tp[sp];
+                    // four window steps per trip, all eight loads first: left to the compiler (#pragma unroll 4) every step's
+                    // FMAs waited for that step's own two loads in the same registers (SASS), a latency chain per step
+                    for (int sp = 0; sp < M; sp += 4) {     // M = OB * D is a multiple of 4
+                        const float2 v0 = xp[sp * qs], v1 = xp[(sp + 1) * qs], v2 = xp[(sp + 2) * qs], v3 = xp[(sp + 3) * qs];
+                        const float4 h0 = tp[sp], h1 = tp[sp + 1], h2 = tp[sp + 2], h3 = tp[sp + 3];
                         // packed FMA: (re, im) of one accumulator per instruction, the tap broadcast to both halves
-                        acc[0] = __ffma2_rn(make_float2(h.x, h.x), v, acc[0]);
-                        acc[1] = __ffma2_rn(make_float2(h.y, h.y), v, acc[1]);
-                        acc[2] = __ffma2_rn(make_float2(h.z, h.z), v, acc[2]);
-                        acc[3] = __ffma2_rn(make_float2(h.w, h.w), v, acc[3]);
+                        acc[0] = __ffma2_rn(make_float2(h0.x, h0.x), v0, acc[0]);
+                        acc[1] = __ffma2_rn(make_float2(h0.y, h0.y), v0, acc[1]);
+                        acc[2] = __ffma2_rn(make_float2(h0.z, h0.z), v0, acc[2]);
+                        acc[3] = __ffma2_rn(make_float2(h0.w, h0.w), v0, acc[3]);
+                        acc[0] = __ffma2_rn(make_float2(h1.x, h1.x), v1, acc[0]);
+                        acc[1] = __ffma2_rn(make_float2(h1.y, h1.y), v1, acc[1]);
+                        acc[2] = __ffma2_rn(make_float2(h1.z, h1.z), v1, acc[2]);
+                        acc[3] = __ffma2_rn(make_float2(h1.w, h1.w), v1, acc[3]);
+                        acc[0] = __ffma2_rn(make_float2(h2.x, h2.x), v2, acc[0]);
+                        acc[1] = __ffma2_rn(make_float2(h2.y, h2.y), v2, acc[1]);
+                        acc[2] = __ffma2_rn(make_float2(h2.z, h2.z), v2, acc[2]);
+                        acc[3] = __ffma2_rn(make_float2(h2.w, h2.w), v2, acc[3]);
+                        acc[0] = __ffma2_rn(make_float2(h3.x, h3.x), v3, acc[0]);
+                        acc[1] = __ffma2_rn(make_float2(h3.y, h3.y), v3, acc[1]);
+                        acc[2] = __ffma2_rn(make_float2(h3.z, h3.z), v3, acc[2]);
+                        acc[3] = __ffma2_rn(make_float2(h3.w, h3.w), v3, acc[3]);
                     }
                 }
             }
@@ -1022,8 +1035,33 @@ tail_fast_kernel(const TailArgs* __restrict__ ap) {
                 const int j1 = min(S, (ks + 1) * Sk);
                 // element e0 + j sits at plane (e0 + j) % M, position (e0 + j) / M; e0 = offset (mod M) for every group
                 const float2* __restrict__ xb = x + r_base;
-#pragma unroll 4
-                for (int j = ks * Sk; j < j1; j++) {
+                int j = ks * Sk;
+                // four window steps per trip with all eight loads first (see tail_fir_blocked), then the odd steps
+                for (; j + 4 <= j1; j += 4) {
+                    const int e = e0 + j;
+                    const float2 v0 = xb[(e & r_mask) * r_qs + (e >> r_lg)];
+                    const float2 v1 = xb[((e + 1) & r_mask) * r_qs + ((e + 1) >> r_lg)];
+                    const float2 v2 = xb[((e + 2) & r_mask) * r_qs + ((e + 2) >> r_lg)];
+                    const float2 v3 = xb[((e + 3) & r_mask) * r_qs + ((e + 3) >> r_lg)];
+                    const float4 h0 = t4[j], h1 = t4[j + 1], h2 = t4[j + 2], h3 = t4[j + 3];
+                    acc[0] = __ffma2_rn(make_float2(h0.x, h0.x), v0, acc[0]);
+                    acc[1] = __ffma2_rn(make_float2(h0.y, h0.y), v0, acc[1]);
+                    acc[2] = __ffma2_rn(make_float2(h0.z, h0.z), v0, acc[2]);
+                    acc[3] = __ffma2_rn(make_float2(h0.w, h0.w), v0, acc[3]);
+                    acc[0] = __ffma2_rn(make_float2(h1.x, h1.x), v1, acc[0]);
+                    acc[1] = __ffma2_rn(make_float2(h1.y, h1.y), v1, acc[1]);
+                    acc[2] = __ffma2_rn(make_float2(h1.z, h1.z), v1, acc[2]);
+                    acc[3] = __ffma2_rn(make_float2(h1.w, h1.w), v1, acc[3]);
+                    acc[0] = __ffma2_rn(make_float2(h2.x, h2.x), v2, acc[0]);
+                    acc[1] = __ffma2_rn(make_float2(h2.y, h2.y), v2, acc[1]);
+                    acc[2] = __ffma2_rn(make_float2(h2.z, h2.z), v2, acc[2]);
+                    acc[3] = __ffma2_rn(make_float2(h2.w, h2.w), v2, acc[3]);
+                    acc[0] = __ffma2_rn(make_float2(h3.x, h3.x), v3, acc[0]);
+                    acc[1] = __ffma2_rn(make_float2(h3.y, h3.y), v3, acc[1]);
+                    acc[2] = __ffma2_rn(make_float2(h3.z, h3.z), v3, acc[2]);
+                    acc[3] = __ffma2_rn(make_float2(h3.w, h3.w), v3, acc[3]);
+                }
+                for (; j < j1; j++) {
                     const int e = e0 + j;
                     const float2 v = xb[(e & r_mask) * r_qs + (e >> r_lg)];
                     const float4 h = t4[j];
