@@ -528,7 +528,7 @@ def run_gpu(args, rank, world, local_rank):
     demo = os.path.join(ROOT, "tests", "cpp", "mirror_demo")
     if rank == 0 and world == 1 and w.fmt == workloads.FMT_CF32 and os.path.exists(demo) and not args.no_cpp:
         try:
-            r = subprocess.run([demo, "bench", repr(w.sr), str(w.block), str(w.fft_size), str(w.nvfo), str(max(50, min(400, args.steps))), "8"],
+            r = subprocess.run([demo, "bench", repr(w.sr), str(w.block), str(w.fft_size), str(w.nvfo), str(max(300, min(600, args.steps))), "8"],
                                capture_output=True, text=True, timeout=300)
             last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
             if r.returncode == 0 and last:
