@@ -463,6 +463,10 @@ def run_gpu(args, rank, world, local_rank):
         bidir_gbs = reps * blk_bytes / (c0.elapsed_time(c1) * 1e-3) / 1e9
         e2e["h2d_link_gbs_with_results_going_back"] = bidir_gbs
         e2e["link_bound_bidirectional_msps"] = bidir_gbs * 1e9 / w.bytes_per_sample / 1e6
+        e2e["link_note"] = ("h2d_link_bound_msps: the block copy alone, back to back. link_bound_bidirectional_msps: the same copies with this "
+                            "rank's result bytes per step issued alternately on a second stream (an estimate, +-5 %, of what the link carries "
+                            "when every result is read back: the read requests of the block copy share the upstream direction with the result "
+                            "data). The end-to-end value sits at this second figure: it is bound by the host link, not by the kernels.")
         for p in pin:
             p.free()
     barrier()
