@@ -1,4 +1,5 @@
-"""Host-time breakdown of bench.py's multi-GPU step (broadcast of the IQ block + submit) and of cheaper variants.
+"""ROUND-1 TOOL, kept for the record of the measurements cited in profiles/README.md: it was written against round 1's bench.py (torch.distributed broadcast in the Python loop) and no longer runs -- the broadcast lives inside the library now (csrc/comm.cu); use tools/bcast_probe.py and bench.py --gpus N.
+Host-time breakdown of bench.py's multi-GPU step (broadcast of the IQ block + submit) and of cheaper variants.
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tools/mgpu_probe.py [steps]"""
 import os
 import sys

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Per-CTA phase timeline of the stage-1 kernel (debug build: SDRPP_EXTRA_NVCC=-DSDRPP_S1_TRACE, library passed
+"""ROUND-1 TOOL (FP32 stage-1 kernel), kept for the record of the measurements cited in profiles/README.md: written against round 1's bench.py, it no longer runs; the tensor-core stage 1 has tools/s1t_trace.py.
+Per-CTA phase timeline of the stage-1 kernel (debug build: SDRPP_EXTRA_NVCC=-DSDRPP_S1_TRACE, library passed
 through SDRPP_CUDA_LIB). Prints, per launch of the last block, the mean duration of each phase and the fraction of
 time both CTAs of an SM spend outside the main loop at once."""
 import ctypes as C
