@@ -1,5 +1,5 @@
 // tcgen05.mma issue/execute rate on one SM per N (M = 128, K = 16, fp16 -> fp32, both operands in shared memory,
-// K-major SWIZZLE_128B): cycles per MMA for N = 64..256, with the A/B descriptors (a) fixed and (b) walking over a
+// K-major SWIZZLE_128B): cycles per MMA for N = 32..256, with the A/B descriptors (a) fixed and (b) walking over a
 // 96 KB + 128 KB operand area like the channelizer's stage-1 kernel does, alone and with the stage-1 kernel's other
 // traffic running beside it: tcgen05.ld of the second accumulator stage, bulk copies into shared memory.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o umma_rate umma_rate.cu && ./umma_rate
@@ -113,7 +113,7 @@ int main() {
     const int ctas = 148, walk = 1, two = 0;
     for (int tma = 0; tma < 2; tma++)
         for (int lw : { 0, 1, 4 })
-                for (int N : { 128, 192, 224, 256 }) {
+                for (int N : { 32, 64, 96, 128, 192, 224, 256 }) {
                     k<<<ctas, 256, smem>>>(N, iters, walk, two, lw, tma, gsrc, d);
                     cudaError_t e = cudaDeviceSynchronize();
                     if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
