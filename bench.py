@@ -223,6 +223,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     w = workloads.config(args.config)
+
     vals, info = [], None
     for i in range(args.warmup + args.steps):
         v, info = cpu_reference(w, nblocks=1)
@@ -253,6 +254,26 @@ def run_gpu(args, rank, world, local_rank):
     if cuda.device_count() <= 0:
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
     w = workloads.config(args.config)
+    # ---- the C++ interface modules link against (IQFrontEnd + VFOManager + dsp::stream), N = 1 -------------------------
+    # First of all, before this process has a CUDA context of its own: the demo is a separate process, and beside a parent that
+    # holds a context, 160 MB of source blocks and its own threads it measured 2.7-3.0 GS/s instead of the 3.9-4.4 of a
+    # stand-alone run.
+    e2e_cpp = None
+    demo = os.path.join(ROOT, "tests", "cpp", "mirror_demo")
+    if rank == 0 and world == 1 and w.fmt == workloads.FMT_CF32 and os.path.exists(demo) and not args.no_cpp:
+        try:
+            r = subprocess.run([demo, "bench", repr(w.sr), str(w.block), str(w.fft_size), str(w.nvfo), str(max(300, min(600, args.steps))), "8"],
+                               capture_output=True, text=True, timeout=300)
+            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and last:
+                e2e_cpp = json.loads(last[-1])
+                e2e_cpp["note"] = ("tests/cpp/mirror_demo bench: a source thread swaps pinned blocks into the input dsp::stream, sigpath::iqFrontEnd "
+                                   "(ingest / deliver / spectrum threads over the C ABI) feeds VFOs created through sigpath::vfoManager, 8 consumer "
+                                   "threads read()/flush() every VFO::output stream, acquire/release receive every spectrum row")
+            else:
+                e2e_cpp = {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as ex:  # noqa: BLE001
+            e2e_cpp = {"error": str(ex)}
     torch.cuda.set_device(local_rank)
     cuda.init(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -526,24 +547,6 @@ def run_gpu(args, rank, world, local_rank):
                   "failures_rank0": res["failures"],
                   "note": "fresh front end(s) with the benchmarked VFO shards, blocks through the same submit path (N > 1: the library's "
                           "broadcast), spot VFOs of every rank's shard against the ideal-NCO oracle chain; tests/parity_workload.py"}
-
-    # ---- the C++ interface modules link against (IQFrontEnd + VFOManager + dsp::stream), N = 1 -------------------------
-    e2e_cpp = None
-    demo = os.path.join(ROOT, "tests", "cpp", "mirror_demo")
-    if rank == 0 and world == 1 and w.fmt == workloads.FMT_CF32 and os.path.exists(demo) and not args.no_cpp:
-        try:
-            r = subprocess.run([demo, "bench", repr(w.sr), str(w.block), str(w.fft_size), str(w.nvfo), str(max(300, min(600, args.steps))), "8"],
-                               capture_output=True, text=True, timeout=300)
-            last = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            if r.returncode == 0 and last:
-                e2e_cpp = json.loads(last[-1])
-                e2e_cpp["note"] = ("tests/cpp/mirror_demo bench: a source thread swaps pinned blocks into the input dsp::stream, sigpath::iqFrontEnd "
-                                   "(ingest / deliver / spectrum threads over the C ABI) feeds VFOs created through sigpath::vfoManager, 8 consumer "
-                                   "threads read()/flush() every VFO::output stream, acquire/release receive every spectrum row")
-            else:
-                e2e_cpp = {"error": (r.stderr or r.stdout)[-300:]}
-        except Exception as ex:  # noqa: BLE001
-            e2e_cpp = {"error": str(ex)}
 
     # ---- roofline + baseline objects (rank 0) -------------------------------------------------------------
     if rank == 0:

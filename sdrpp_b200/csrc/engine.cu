@@ -313,7 +313,7 @@ struct sdrpp_cuda_frontend {
     cudaStream_t st = nullptr, st_copy = nullptr, st_fft = nullptr, st_tail = nullptr, st_s1b = nullptr, st_d2h = nullptr;
     cudaEvent_t ev_ingest = nullptr, ev_s1 = nullptr, ev_fft[2] = { nullptr, nullptr }, ev_tail[2] = { nullptr, nullptr };
     bool ev_fft_valid[2] = { false, false };
-    cudaEvent_t ev_rows[5] = { nullptr };   // per result set: the block's spectrum rows (zoomed rows, level read-outs) are on the host
+    cudaEvent_t ev_rows[kSets] = { nullptr };   // per result set: the block's spectrum rows (zoomed rows, level read-outs) are on the host
     // One submitting thread and one waiting thread may use a front end concurrently (submit / wait_input on one,
     // wait + result getters on the other); everything else is serialised by the caller. wait() drops the lock while
     // it blocks on the block's completion event.
@@ -2093,10 +2093,8 @@ sdrpp_cuda_frontend* sdrpp_cuda_frontend_create(const sdrpp_cuda_frontend_cfg* c
         cudaEventCreateWithFlags(&fe->ev_tail[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_tail[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_desc, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&fe->ev_rows[0], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&fe->ev_rows[1], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&fe->ev_rows[2], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&fe->ev_rows[3], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&fe->ev_rows[4], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&fe->ev_fftk, cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
+    for (cudaEvent_t& e : fe->ev_rows) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return bail("event creation failed");
     fe->L.streams[SID_MAIN] = fe->st; fe->L.streams[SID_FFT] = fe->st_fft; fe->L.streams[SID_TAIL] = fe->st_tail;
     fe->L.streams[SID_S1B] = fe->st_s1b; fe->L.streams[SID_D2H] = fe->st_d2h;
     { const char* g = getenv("SDRPP_GRAPHS"); fe->graphs_on = !(g && g[0] == '0'); }
