@@ -575,6 +575,14 @@ static void fill_g_for_vfo(Group& g, int lane_index, const Vfo& v) {
 }
 
 static int rebuild_layout(sdrpp_cuda_frontend* fe) {
+    // A new layout makes new command sequences (grids, table and arena addresses): the instantiated graphs of the old one can
+    // never match again, and left in the cache they would fill it (kMaxGraphs) after a few dozen control calls and leave every
+    // later block to the command-by-command path. The streams are idle here (control calls quiesce before they mark the layout).
+    for (int k = 0; k < GRAPH_KINDS; k++) {
+        for (auto& e : fe->gcache[k]) if (e.second.exec) cudaGraphExecDestroy(e.second.exec);
+        fe->gcache[k].clear();
+        fe->gseen[k].clear();
+    }
     // device VFO table ordered by group; arena offsets by VFO
     int total = 0;
     size_t arena = 0;
