@@ -26,6 +26,8 @@
 
 namespace sdrpp {
 
+__host__ __device__ constexpr int ilog2c(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
 __device__ __forceinline__ float power_db(float2 x) {
     // volk_32fc_s32f_power_spectrum_32f with norm 1: log2(re^2+im^2) * 10/log2(10), -inf -> -127*3.0103
     float l = __log2f(x.x * x.x + x.y * x.y);
@@ -76,20 +78,27 @@ static cudaError_t get_tables(int N, int N1, int N2, SpectrumTables* out) {
     return cudaSuccess;
 }
 
-__device__ __forceinline__ void load_table(float2* dst, const float2* __restrict__ src, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+// Twiddle tables travel to shared memory by cp.async (16 B per copy, no register round trip): the copies are in flight
+// beside the frame's own loads instead of in front of the transform. As a load -> store loop every trip was one more
+// serialised L2 / DRAM round trip ahead of the first butterfly (ncu r2t: long_scoreboard 65 % of the cols kernel's samples).
+// n is a multiple of 2 (every table length is a power of two >= 64) and both sides are 16-byte aligned.
+__device__ __forceinline__ void stage_table(float2* dst, const float2* __restrict__ src, int n) {
+    for (int i = threadIdx.x * 2; i < n; i += blockDim.x * 2)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + i)), "l"(src + i) : "memory");
 }
+// (the matching cp.async.wait_all sits in front of block_fft's first __syncthreads, fft_core.cuh)
 
 // ---------------------------------------------------------------------------------------------
 // cols kernel: grid (N2/B, frames), block T*B, thread (t,b) with b fastest (coalesced columns)
 // ---------------------------------------------------------------------------------------------
-template <class P, int B>
-__global__ void __launch_bounds__(P::T* B)
-fft_cols_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N2, int log2N, int log2N2) {
-    const SpectrumArgs a = *ap;   // per-block arguments (launcher descriptor)
-    if ((int)blockIdx.y >= a.frames) return;
-    extern __shared__ __align__(16) float2 sm[];
+// SQUARE: N1 == N2 == L, the frame is fully windowed (nz == N) and does not wrap in the ring -- the saturated 1M-point
+// waterfall. Every stride is then a compile-time constant and the 32 frame loads, window loads and stores of a thread are one
+// base register plus an immediate each (a third of the general kernel's instructions were address arithmetic and range
+// predicates, SASS r2t).
+template <class P, int B, bool SQUARE>
+__device__ __forceinline__ void fft_cols_body(const SpectrumArgs& a, const SpectrumTables& tabs, float2* sm, int N2r, int log2N, int log2N2r) {
     constexpr int E = P::E, T = P::T, L = P::L;
+    const int N2 = SQUARE ? L : N2r;
     float2* tw = sm;              // [L]   exp(-2 pi i j / N1)
     float2* twlo = sm + L;        // [N2]  exp(-2 pi i j / N)
     float2* ex = twlo + N2;       // exchange buffer
@@ -99,34 +108,57 @@ fft_cols_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N2
     const uint32_t base = a.start + (uint32_t)f * a.frame_stride;
     const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in);
 
+    stage_table(tw, tabs.tw1, L);
+    stage_table(twlo, tabs.twlo, N2);
     float2 v[E];
+    if constexpr (SQUARE) {
+        const float2* __restrict__ x = in + (base & a.ring_mask) + (t * L + n2);
+        const float* __restrict__ w = a.window + (t * L + n2);
 #pragma unroll
-    for (int e = 0; e < E; e++) {
-        const int n = (t + T * e) * N2 + n2;
-        if (n < a.nz) {
-            const float2 x = __ldg(in + ((base + (uint32_t)n) & a.ring_mask));
-            const float w = __ldg(a.window + n);
-            v[e] = make_float2(x.x * w, x.y * w);
-        } else {
-            v[e] = make_float2(0.0f, 0.0f);
+        for (int e = 0; e < E; e++) {
+            const float2 xv = __ldg(x + e * (T * L));
+            const float wv = __ldg(w + e * (T * L));
+            v[e] = make_float2(xv.x * wv, xv.y * wv);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const int n = (t + T * e) * N2 + n2;
+            if (n < a.nz) {
+                const float2 x = __ldg(in + ((base + (uint32_t)n) & a.ring_mask));
+                const float w = __ldg(a.window + n);
+                v[e] = make_float2(x.x * w, x.y * w);
+            } else {
+                v[e] = make_float2(0.0f, 0.0f);
+            }
         }
     }
-    load_table(tw, tabs.tw1, L);
-    load_table(twlo, tabs.twlo, N2);
     block_fft<P, true, B>(v, ex, tw, t, b); // the first exchange's __syncthreads also publishes the tables
 
     // four-step twiddle W_N^m, m = n2*k1 < N: W_N^m = exp(-2 pi i (m >> log2N2) / N1) * exp(-2 pi i (m & (N2-1)) / N)
-    float2* __restrict__ out = a.inter + (size_t)f * ((size_t)1 << log2N);
+    const int log2N2 = SQUARE ? ilog2c(L) : log2N2r;
+    float2* __restrict__ out = a.inter + (size_t)f * ((size_t)1 << log2N) + (size_t)t * N2 + n2;
     const uint32_t lomask = (uint32_t)N2 - 1u;
     uint32_t m = (uint32_t)n2 * (uint32_t)t;
     const uint32_t dm = (uint32_t)n2 * (uint32_t)T;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const int k1 = t + T * e;
         const float2 w = cmul(tw[m >> log2N2], twlo[m & lomask]);
-        out[(size_t)k1 * N2 + n2] = cmul(v[e], w);
+        out[(size_t)e * T * N2] = cmul(v[e], w);       // row k1 = t + T*e
         m += dm;
     }
+}
+
+template <class P, int B>
+__global__ void __launch_bounds__(P::T* B)
+fft_cols_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N2, int log2N, int log2N2) {
+    const SpectrumArgs a = *ap;   // per-block arguments (launcher descriptor)
+    if ((int)blockIdx.y >= a.frames) return;
+    extern __shared__ __align__(16) float2 sm[];
+    const uint32_t first = (a.start + blockIdx.y * a.frame_stride) & a.ring_mask;
+    const bool square = N2 == P::L && a.nz == (1 << log2N) && (unsigned long long)first + (1ull << log2N) <= (unsigned long long)a.ring_mask + 1ull;
+    if (square) fft_cols_body<P, B, true>(a, tabs, sm, N2, log2N, log2N2);
+    else fft_cols_body<P, B, false>(a, tabs, sm, N2, log2N, log2N2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -150,6 +182,7 @@ fft_rows_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N1
         const bool live = f < a.frames;
         const uint32_t base = a.start + (uint32_t)f * a.frame_stride;
         const float2* __restrict__ in = reinterpret_cast<const float2*>(a.in);
+        stage_table(tw, tabs.tw2, L);
 #pragma unroll
         for (int e = 0; e < E; e++) {
             const int n = t + T * e;
@@ -161,8 +194,7 @@ fft_rows_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N1
                 v[e] = make_float2(0.0f, 0.0f);
             }
         }
-        load_table(tw, tabs.tw2, L);
-        block_fft<P, false, B>(v, ex, tw, t, b);
+            block_fft<P, false, B>(v, ex, tw, t, b);
         if (live) {
 #pragma unroll
             for (int e = 0; e < E; e++) {
@@ -176,10 +208,10 @@ fft_rows_kernel(const SpectrumArgs* __restrict__ ap, SpectrumTables tabs, int N1
         const int k1_0 = blockIdx.x * B;
         const size_t N = (size_t)1 << log2N;
         const float2* __restrict__ A = a.inter + (size_t)f * N + (size_t)(k1_0 + b) * L;
+        stage_table(tw, tabs.tw2, L);
 #pragma unroll
         for (int e = 0; e < E; e++) v[e] = A[t + T * e];
-        load_table(tw, tabs.tw2, L);
-        block_fft<P, false, B>(v, ex, tw, t, b);
+            block_fft<P, false, B>(v, ex, tw, t, b);
         if (a.X) {
 #pragma unroll
             for (int e = 0; e < E; e++) a.X[(size_t)f * N + (size_t)(k1_0 + b) + (size_t)N1 * (t + T * e)] = v[e];
@@ -345,13 +377,8 @@ int spectrum_split(int N, int* N1, int* N2) {
     return lg;
 }
 
-cudaError_t launch_spectrum(Launcher& L, int sid, int N, const SpectrumArgs& a, long long* launches) {
-    int N1, N2;
-    const int lg = spectrum_split(N, &N1, &N2);
-    if (lg < 0 || a.frames <= 0) return cudaErrorInvalidValue;
-    SpectrumTables tabs;
-    cudaError_t e = get_tables(N, N1, N2, &tabs);
-    if (e != cudaSuccess) return e;
+static cudaError_t launch_spectrum_frames(Launcher& L, int sid, int N, int N1, int N2, int lg, const SpectrumTables& tabs, const SpectrumArgs& a, long long* launches) {
+    cudaError_t e = cudaSuccess;
     const SpectrumArgs* d_a = L.push(a);
     if (!d_a) return cudaErrorMemoryAllocation;
     if (N1 == 1) {
@@ -387,6 +414,20 @@ cudaError_t launch_spectrum(Launcher& L, int sid, int N, const SpectrumArgs& a, 
     }
     if (launches) *launches += 2;
     return e;
+}
+
+// All frames of a call go through one pair of launches. Splitting a large batch into chunks whose four-step intermediate stays
+// in the L2 (32 MB at a time, the same region reused) was measured and is slower: 18 / 64 frames of 1M points 86.6 / 91.0 ->
+// 74.6 / 75.7 GS/s, 256 frames of 64K 131 -> 113 GS/s (profiles/r2x_fft_ab.txt) -- the partial last wave of every small launch
+// costs more than the intermediate's trip through HBM.
+cudaError_t launch_spectrum(Launcher& L, int sid, int N, const SpectrumArgs& a, long long* launches) {
+    int N1, N2;
+    const int lg = spectrum_split(N, &N1, &N2);
+    if (lg < 0 || a.frames <= 0) return cudaErrorInvalidValue;
+    SpectrumTables tabs;
+    cudaError_t e = get_tables(N, N1, N2, &tabs);
+    if (e != cudaSuccess) return e;
+    return launch_spectrum_frames(L, sid, N, N1, N2, lg, tabs, a, launches);
 }
 
 } // namespace sdrpp

@@ -39,14 +39,18 @@ __device__ __forceinline__ float2 mul_w32(float2 v) {
     }
 }
 
+// complex add / subtract as one packed instruction (FADD2, sm_100): the (re, im) pair of a float2 is the instruction's pair
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
 template <int R> __device__ __forceinline__ void dft_reg(float2 (&v)[R]);
 
 template <int R, int K>
 struct DftCombine {
     __device__ __forceinline__ static void run(float2 (&v)[R], const float2 (&e)[R / 2], const float2 (&o)[R / 2]) {
         const float2 t = mul_w32<K * (32 / R)>(o[K]);
-        v[K] = make_float2(e[K].x + t.x, e[K].y + t.y);
-        v[K + R / 2] = make_float2(e[K].x - t.x, e[K].y - t.y);
+        v[K] = cadd(e[K], t);
+        v[K + R / 2] = csub(e[K], t);
         if constexpr (K + 1 < R / 2) DftCombine<R, K + 1>::run(v, e, o);
     }
 };
@@ -56,8 +60,8 @@ template <int R>
 __device__ __forceinline__ void dft_reg(float2 (&v)[R]) {
     if constexpr (R == 2) {
         const float2 a = v[0], b = v[1];
-        v[0] = make_float2(a.x + b.x, a.y + b.y);
-        v[1] = make_float2(a.x - b.x, a.y - b.y);
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
     } else if constexpr (R > 2) {
         float2 e[R / 2], o[R / 2];
 #pragma unroll
@@ -81,7 +85,7 @@ struct FftPlan {
 
 template <class P, bool COLS, int B>
 __device__ __forceinline__ int smem_index(int idx, int b) {
-    if constexpr (COLS) return idx * B + b;
+    if constexpr (COLS) return (idx + idx / P::R0) * B + b;   // same padding: the pass-0 scatter of threads t, t+1 lands B*(R0+1) apart
     else return b * P::LP + idx + idx / P::R0;
 }
 
@@ -114,6 +118,10 @@ __device__ __forceinline__ void fft_pass(float2 (&v)[P::E], float2* sm, const fl
         }
     }
     if constexpr (!LAST) {
+        // the callers' twiddle tables arrive by cp.async (fft.cu: stage_table); the first exchange publishes them. Waiting here,
+        // behind the first butterflies' stores, keeps the wait out of the frame loads (ahead of block_fft the compiler hoisted
+        // it into the middle of them: one more serialised round trip)
+        if constexpr (NS == 1) asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < E; e++) v[e] = sm[smem_index<P, COLS, B>(t + T * e, b)];
@@ -132,7 +140,7 @@ __device__ __forceinline__ void block_fft(float2 (&v)[P::E], float2* sm, const f
 // exchange buffer elements (float2) for B transforms
 template <class P, bool COLS, int B>
 constexpr size_t fft_exchange_elems() {
-    return P::PASSES == 1 ? 0 : (COLS ? (size_t)P::L * B : (size_t)P::LP * B);
+    return P::PASSES == 1 ? 0 : (size_t)P::LP * B;
 }
 
 } // namespace sdrpp
