@@ -18,7 +18,7 @@
 
 namespace sdrpp {
 
-cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes, int carveout) {
     static std::mutex mtx;
     static std::map<std::pair<const void*, int>, size_t> done;
     int dev = 0;
@@ -31,8 +31,9 @@ cudaError_t ensure_dynamic_smem(const void* func, size_t bytes) {
     // The SM's shared-memory carve-out is chosen per kernel from what ITS CTAs need (stage 1: 189 KB -> the 196 KB setting),
     // and it cannot change while CTAs are resident: without this preference a tail CTA of the previous block never fits
     // beside the persistent stage-1 CTA although 228 KB would hold both (seen as a tail kernel that takes 75 us instead of 37
-    // whenever it overlaps stage 1, tools/timeline_probe.py). Every kernel with opt-in shared memory asks for the largest.
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    // whenever it overlaps stage 1, tools/timeline_probe.py). Every kernel with opt-in shared memory asks for the largest
+    // unless its launcher says otherwise (the spectrum kernels, fft.cu).
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
     if (e == cudaSuccess) cur = bytes;
     return e;
 }

@@ -23,7 +23,9 @@ __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / 
 
 // Opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device. The attribute is per device and the library
 // lets every thread pick its own (sdrpp_cuda_init), so what has been set is remembered per (kernel, device), under a lock.
-cudaError_t ensure_dynamic_smem(const void* func, size_t bytes);
+// carveout: cudaFuncAttributePreferredSharedMemoryCarveout for the kernel (percent of the largest setting, or
+// cudaSharedmemCarveoutDefault = -1 for the driver's own choice from the kernel's occupancy).
+cudaError_t ensure_dynamic_smem(const void* func, size_t bytes, int carveout = 100 /* cudaSharedmemCarveoutMaxShared */);
 
 // Bit-exact sample conversion. Each formula keeps the reference's operation
 // order with IEEE round-to-nearest intrinsics so the compiler can neither contract to FMA nor

@@ -12,6 +12,8 @@
 #include "fft_core.cuh"
 #include "kernels.h"
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -246,12 +248,28 @@ using P1024 = FftPlan<1024, 32, 32, 32, 1>;
 using P2048 = FftPlan<2048, 16, 16, 16, 8>;
 using P4096 = FftPlan<4096, 16, 16, 16, 16>;
 
+// Shared-memory carve-out preference of the spectrum kernels: the driver's own choice from the kernel's occupancy (two 84 KB
+// CTAs per SM -> the 196 KB setting, 60 KB of L1), not the largest setting every other kernel of the library asks for
+// (common.cuh): these kernels read their frame with per-thread loads of 64-B row segments, and the misses they can keep in
+// flight scale with the L1 that is left. One box, max -> default (profiles/r2x_fft_ab.txt): 18 frames of 1M points
+// 89.6 -> 113.2 GS/s, one frame 12.4 + 8.7 -> 9.8 + 8.4 us (ncu, cold), the streaming bench line unchanged (6831 / 6806
+// MS/s: the spectrum takes turns with the persistent stage-1 CTAs either way). SDRPP_FFT_CARVEOUT = max | default | percent.
+static int fft_carveout() {
+    static const int v = [] {
+        const char* e = getenv("SDRPP_FFT_CARVEOUT");
+        if (!e || !*e || !strcmp(e, "default")) return (int)cudaSharedmemCarveoutDefault;
+        if (!strcmp(e, "max")) return (int)cudaSharedmemCarveoutMaxShared;
+        return atoi(e);
+    }();
+    return v;
+}
+
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 template <class P, int B>
 static cudaError_t launch_cols(Launcher& L, int sid, const SpectrumArgs& a, const SpectrumArgs* d_a, const SpectrumTables& tabs, int N2, int log2N) {
     const size_t smem = (P::L + (size_t)N2 + fft_exchange_elems<P, true, B>()) * sizeof(float2);
-    if (cudaError_t e = ensure_dynamic_smem((const void*)fft_cols_kernel<P, B>, smem); e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_dynamic_smem((const void*)fft_cols_kernel<P, B>, smem, fft_carveout()); e != cudaSuccess) return e;
     dim3 grid(N2 / B, a.frames);
     return L.kernel(sid, (const void*)fft_cols_kernel<P, B>, grid, dim3(P::T * B), smem, d_a, tabs, N2, log2N, ilog2(N2));
 }
@@ -261,7 +279,7 @@ static cudaError_t launch_rows(Launcher& L, int sid, const SpectrumArgs& a, cons
     constexpr size_t ex = fft_exchange_elems<P, false, B>() * sizeof(float2);
     constexpr size_t tr = FROM_SAMPLES ? 0 : (size_t)P::L * (B + 1) * sizeof(float);
     constexpr size_t smem = P::L * sizeof(float2) + (ex > tr ? ex : tr);
-    if (cudaError_t e = ensure_dynamic_smem((const void*)fft_rows_kernel<P, B, FROM_SAMPLES>, smem); e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_dynamic_smem((const void*)fft_rows_kernel<P, B, FROM_SAMPLES>, smem, fft_carveout()); e != cudaSuccess) return e;
     dim3 grid(FROM_SAMPLES ? ceil_div(a.frames, B) : N1 / B, FROM_SAMPLES ? 1 : a.frames);
     return L.kernel(sid, (const void*)fft_rows_kernel<P, B, FROM_SAMPLES>, grid, dim3(P::T * B), smem, d_a, tabs, N1, log2N);
 }
