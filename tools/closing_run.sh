@@ -1,4 +1,4 @@
-# closing run of the round: whole GPU suite, the default bench line, the E16 spectrum variant, ncu launch list, ncu full of the FFT pair
+# closing run of the round (the E16 leg needs sdrpp_b200/libsdrpp_cuda_e16.so: SDRPP_EXTRA_NVCC=-DSDRPP_FFT1024_E16 python -m sdrpp_b200.build, copied aside): whole GPU suite, the default bench line, the E16 spectrum variant, ncu launch list, ncu full of the FFT pair
 timeout 260 python -m pytest tests -m gpu -x -q > gpurun_out/t40.log 2>&1; tail -2 gpurun_out/t40.log
 timeout 200 python bench.py --steps 20 --warmup 3 > gpurun_out/r2x_bench_default_20_steps.json 2> gpurun_out/r2x_default.err; python -c "
 import json;d=json.load(open('gpurun_out/r2x_bench_default_20_steps.json'));print('bench', round(d['value']), round(d['e2e']['value']), d.get('parity_check',{}).get('ok'), d.get('roofline_spectrum'))"

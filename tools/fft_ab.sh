@@ -1,3 +1,7 @@
+# A/B of two builds of the library on one box: spectrum tests on the new build, then batched timings and ncu per-launch
+# durations of the FFT pair for both. "old" is a build of the commit to compare against, kept beside the new one:
+#   git stash; python -m sdrpp_b200.build; cp sdrpp_b200/libsdrpp_cuda.so sdrpp_b200/libsdrpp_cuda_old.so; git stash pop; python -m sdrpp_b200.build
+# (sdrpp_b200/cuda.py loads SDRPP_CUDA_LIB when it is set).  gpurun -- 'bash tools/fft_ab.sh > gpurun_out/ab.log 2>&1'
 timeout 300 python -m pytest tests/test_gpu_spectrum.py tests/test_gpu_display.py -m gpu -x -q 2>&1 | tail -3
 for lib in old new; do
   if [ $lib = old ]; then export SDRPP_CUDA_LIB=$PWD/sdrpp_b200/libsdrpp_cuda_old.so; else unset SDRPP_CUDA_LIB; fi
